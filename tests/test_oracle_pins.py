@@ -1,0 +1,244 @@
+"""Pin the CPU oracle against every known-answer / cross-check test the reference holds for the
+hot path.  Each test cites the reference test it restates."""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import dre_b200
+from oracle import dre_oracle as O
+
+pencils = dre_b200.pencils
+
+
+def penzl(p):
+    return np.array([[-1.0, p], [-p, -1.0]])
+
+
+def modified_penzl(v):
+    return abs(v.real) * penzl(v.imag / v.real)
+
+
+class _Prob:
+    def __init__(self, E, A):
+        self.E, self.A = E, A
+
+
+def test_projection_penzl_known_answer():
+    """test/Shifts.jl:165-183 -- Projection(2), R = ones(3) -> single shift -5/6."""
+    n = 3
+    E = sp.identity(n, format="csc")
+    A = sp.lil_matrix((n, n))
+    A[0:2, 0:2] = penzl(1.0)
+    A[2, 2] = -0.5
+    A = A.tocsc()
+    with pytest.raises(ValueError):
+        O.Projection(1)
+    shifts = O.shifts_init(O.Projection(2), _Prob(E, A))
+    assert isinstance(shifts, O.BufferedIterator) and not shifts.buffer
+    shifts.update(O.lowrank(np.zeros((n, 0)), np.zeros((0, 0))), np.ones((n, 1)))
+    assert not shifts.buffer
+    assert np.isclose(shifts.take(), -5.0 / 6.0)
+    assert not shifts.buffer
+
+
+def _preserves_conj_pairs(take, n):
+    i = 0
+    while i < n:
+        i += 1
+        v = take()
+        if np.imag(v) != 0:
+            i += 1
+            w = take()
+            if not np.isclose(w, np.conj(v)):
+                return False
+    return True
+
+
+@pytest.mark.parametrize("f", [lambda a: -np.exp(1j * a), lambda a: -1 - 1j * a])
+def test_conjugated_pairs(f):
+    """test/Shifts.jl:185-226."""
+    n = 3
+    vals = [f(v) for v in range(-n, n + 1, 2)]
+    raw = list(vals)
+    assert not _preserves_conj_pairs(lambda: raw.pop(0), len(vals))
+    srt = O.safe_sort(vals)
+    assert _preserves_conj_pairs(lambda: srt.pop(0), len(vals))
+    A = np.zeros((4, 4))
+    A[0:2, 0:2] = modified_penzl(f(1))
+    A[2:4, 2:4] = modified_penzl(f(2))
+    shifts = O.shifts_init(O.Projection(2), _Prob(np.eye(4), A))
+    shifts.update(None, None, np.eye(4))
+    assert _preserves_conj_pairs(shifts.take, 4)
+
+
+def test_orth_zero():
+    """test/runtests.jl:12-19."""
+    assert O.orth(np.zeros((4, 1))).shape == (4, 0)
+    assert O.orth(sp.csc_matrix((4, 1))).shape == (4, 0)
+
+
+def test_stabilize_ritz_values():
+    """test/Shifts.jl:33-66."""
+    rng = np.random.default_rng(0)
+    v = rng.random(3)
+    with pytest.warns(UserWarning, match="All Ritz values"):
+        w = O.stabilize_ritz_values(v, "test")
+    assert len(w) == 3 and all(np.real(x) < 0 for x in w) and np.allclose(np.real(w) + v, 0)
+    v[0] = -v[0]
+    with pytest.warns(UserWarning, match="Discarding unstable"):
+        w = O.stabilize_ritz_values(v, "test")
+    assert len(w) == 1
+
+
+def test_ldlt_invariants():
+    """test/LDLt.jl:44-90."""
+    rng = np.random.default_rng(1)
+    n, k = 10, 2
+    U = rng.standard_normal((n, k))
+    S = rng.standard_normal((k, k))
+    S = S + S.T
+    for X in (O.lowrank(U), O.lowrank(U, S)):
+        M = X.to_dense()
+        assert X.rank() == k
+        assert np.isclose(O.norm(2 * X), 2 * O.norm(X))
+        assert np.isclose(O.norm(X), np.linalg.norm(M))
+        assert np.allclose((2 * X + 3 * X).to_dense(), 5 * M)
+        assert np.linalg.norm((X - X).to_dense()) / O.EPS < 10 * n
+        Z = X.zero()
+        assert Z.rank() == 0 and Z.iszero() and (X + Z) is X and (Z + X) is X
+        a, L, D = X
+        assert a == 1.0 and L is X.Ls[0] and D is X.Ds[0]
+        Y = O.compress(X + X)
+        assert Y.rank() == k and np.allclose(Y.to_dense(), 2 * M)
+    X = O.lowrank(U, S.copy())
+    X.Ds[0][:] = 0
+    X.Ds[0][0, 0] = 13
+    assert X.rank() == k and O.compress(X).rank() == 1
+
+
+def test_smw_solve():
+    """test/LowRankUpdate.jl:20-51 -- (A + inv(alpha) U V) X ~ B through SMW."""
+    rng = np.random.default_rng(2)
+    n, k = 10, 3
+    A = (sp.random(n, n, density=0.3, random_state=rng) + 4 * sp.identity(n)).tocsc()
+    U = rng.standard_normal((n, k))
+    V = rng.standard_normal((k, n))
+    alpha = rng.standard_normal()
+    AUV = O.lr_update(A, alpha, U, V)
+    assert isinstance(AUV, O.LowRankUpdate)
+    M = AUV.to_dense()
+    assert np.allclose(M, A.toarray() + U @ V / alpha)
+    B = rng.standard_normal((n, 1))
+    X = O.backslash(O.factorize(AUV), B)
+    assert np.allclose(M @ X, B)
+    E = sp.random(n, n, density=0.2, random_state=rng).tocsc()
+    assert np.allclose(AUV.plus_sparse(E).to_dense(), M + E.toarray())
+    assert np.allclose(AUV.adjoint().to_dense(), M.T)
+    assert np.allclose(AUV @ B, M @ B)
+
+
+@pytest.mark.parametrize("case", ["definite", "scaled", "indefinite"])
+def test_residual_lowrank_vs_dense(case):
+    """test/residual.jl:18-78 (n=20)."""
+    rng = np.random.default_rng(3)
+    n, k = 20, 3
+    E, A = pencils.random_spd_pencil(n, seed=5, density=0.2)
+    G = rng.standard_normal((n, 2))
+    C = O.lowrank(G, np.eye(2))
+    L = rng.standard_normal((n, k))
+    D = np.eye(k)
+    if case == "indefinite":
+        D = rng.standard_normal((k, k))
+        D = D + D.T
+    X = O.lowrank(L, D)
+    if case == "scaled":
+        X = 3.5 * X
+    prob = O.GALEProblem(E, A, C)
+    r0 = O.gale_residual(prob, X.zero())
+    assert r0 is not C and np.allclose(r0.to_dense(), C.to_dense())
+    lr = O.norm(O.gale_residual(prob, X))
+    dn = np.linalg.norm(O.gale_residual_dense(prob, X.to_dense()))
+    assert np.isclose(lr, dn, rtol=1e-10)
+    B = rng.standard_normal((n, 2))
+    are = O.GAREProblem(E, A, O.lowrank(B), O.lowrank(G))
+    lr = O.norm(O.gare_residual(are, X))
+    dn = np.linalg.norm(O.gare_residual_dense(are, X.to_dense()))
+    assert np.isclose(lr, dn, rtol=1e-10)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_adi_vs_bartels_stewart(seed):
+    """test/tiny_random.jl:10-57 -- n=50, rank-4 indefinite RHS, ADI() vs dense reference."""
+    n, g = 50, 4
+    rng = np.random.default_rng(seed)
+    E, A = pencils.random_spd_pencil(n, seed=seed)
+    G = rng.random((n, g))
+    C = -2 * O.lowrank(G, -np.eye(g))
+    prob = O.GALEProblem(E, A, C)
+    res0 = O.norm(C)
+    X_adi = O.solve_gale(prob, O.ADI())
+    X_ref = O.bartels_stewart(prob)
+    assert np.linalg.norm(O.gale_residual_dense(prob, X_ref)) / res0 < 1e-10
+    assert O.norm(O.gale_residual(prob, X_adi)) / res0 < 1e-10
+    assert O.delta(X_adi.to_dense(), X_ref) < 1e-10
+    # stepping API
+    solver = O.adi_init(prob, O.ADI())
+    prev = 0
+    for _ in solver:
+        curr = len(solver.shifts)
+        assert prev + 1 <= curr <= prev + 2
+        prev = curr
+    if solver.last_compression > 0:
+        O.adi_compress(solver)
+    assert np.allclose(solver.X.to_dense(), X_adi.to_dense(), rtol=0, atol=1e-13 * np.linalg.norm(X_ref))
+
+
+@pytest.fixture(scope="module")
+def rail371():
+    E, A, B, C, meta = pencils.rail_pencil(371)
+    L = spla.splu(E.tocsc()).solve(C.T)
+    X0 = O.lowrank(L, 0.01 * np.eye(C.shape[0]))
+    assert np.allclose(E @ X0.to_dense() @ E.T, C.T @ C / 100)  # test/rail.jl:32
+    return E, A, B, C, X0
+
+
+def test_rail_lowrank_ros1_vs_dense(rail371):
+    """test/rail.jl:52-60 -- low-rank Ros1 K[end] equals the dense Rosenbrock K[end]
+    within ||K|| * n * eps * 100, 5 steps over (4500, 4400)."""
+    E, A, B, C, X0 = rail371
+    tspan = (4500.0, 4400.0)
+    dt = (tspan[1] - tspan[0]) / 5
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sol = O.solve_gdre(O.GDREProblem(E, A, B, C, X0, tspan), O.Ros1(), dt=dt)
+    assert len(sol.X) == 2 and sol.X[0] is X0 and len(sol.K) == 6  # smoke tests rail.jl:36-46
+    Ks, _ = O.dense_ros1(E, A, B, C, X0.to_dense(), tspan, dt)
+    eps_ = np.linalg.norm(Ks[-1]) * E.shape[0] * O.EPS * 100
+    assert np.linalg.norm(Ks[-1] - sol.K[-1]) < eps_
+
+
+def test_rail_newton_adi(rail371):
+    """test/rail.jl:74-88 -- Newton-ADI residual < reltol * ||Q||, both shift strategies."""
+    E, A, B, C, _ = rail371
+    are = O.GAREProblem(E, A, O.lowrank(B), O.lowrank(C.T))
+    reltol = 1e-10
+    for kw in (dict(shifts=O.Projection(2)), dict(shifts=O.Cyclic(O.Heuristic(10, 20, 20)), maxiters=200)):
+        adi = O.ADI(ignore_initial_guess=True, **kw)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            X = O.solve_gare_newton(are, O.Newton(adi, maxiters=10, reltol=reltol))
+        assert O.norm(O.gare_residual(are, X)) < reltol * O.norm(are.Q)
+
+
+def test_rail_ros2_runs(rail371):
+    """test/rail.jl:62-70 smoke part (shapes, time direction) for low-rank Ros2."""
+    E, A, B, C, X0 = rail371
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sol = O.solve_gdre(O.GDREProblem(E, A, B, C, X0, (4500.0, 4400.0)), O.Ros2(), dt=-50.0, save_state=True)
+    assert len(sol.t) == len(sol.X) == len(sol.K) == 3
+    assert sol.t[0] > sol.t[-1]
+    assert all(np.isfinite(K).all() for K in sol.K)
