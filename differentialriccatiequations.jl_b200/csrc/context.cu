@@ -1,0 +1,1108 @@
+// C ABI of libdre_b200.so (include/dre_b200.h): context, device memory, orchestration of the
+// hand-written kernels.  Host-side C++17; the only third-party device library used is cuSOLVER's
+// dense symmetric eigensolver for the small (rho x rho) projected core inside compress!
+// (the reference calls LAPACK syevr for the same matrix, src/LDLt.jl:214).
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dre_b200.h"
+#include "kernels.h"
+#include "symbolic.h"
+
+using namespace dre;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Panel {
+    double* d = nullptr;
+    int cols = 0;
+    int64_t ld = 0;
+    bool alive = false;
+};
+
+}  // namespace
+
+struct dre_symbolic {
+    Symbolic sym;
+};
+
+struct dre_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t st = nullptr;
+    std::string err;
+    cusolverDnHandle_t cusolver = nullptr;
+
+    // pencil
+    bool has_pencil = false;
+    Symbolic sym;
+    DevSymbolic dS{};
+    std::vector<void*> owned;  // device arrays of the symbolic structure
+    int32_t* d_iperm = nullptr;
+    int32_t* d_csr_ptr = nullptr;
+    int32_t* d_csr_col = nullptr;
+    double* d_csr_a = nullptr;
+    double* d_csr_e = nullptr;
+    int32_t* d_level_sn = nullptr;
+    // per-level work lists
+    struct LevelWork {
+        int sn_begin = 0, sn_count = 0;
+        int ea_begin = 0, ea_count = 0, ea_gy = 1;
+        std::vector<std::pair<int, int>> steps;  // (offset into d_front_items, count)
+        int schur_begin = 0, schur_count = 0;
+        int64_t upd_elems = 0;
+    };
+    std::vector<LevelWork> levels;
+    int32_t* d_ea_parents = nullptr;
+    int2* d_front_items = nullptr;
+    int4* d_schur_items = nullptr;
+    int64_t dblk_elems = 0;
+
+    // factor storage (sized for complex, reused for real)
+    void* d_L = nullptr;
+    void* d_dblk = nullptr;
+    void* d_U[2] = {nullptr, nullptr};
+    DBuf<unsigned char> tbuf[2];
+    DBuf<unsigned char> Wbuf;
+    DBuf<double> btw, sol;
+    int32_t* d_errflag = nullptr;
+
+    // operator F = a A + e E + inv(alpha) U Vt'
+    double op_a = 1.0, op_e = 0.0, op_alpha = 1.0;
+    dre_view op_U{-1, 0, 0}, op_Vt{-1, 0, 0};
+
+    // panels
+    std::vector<Panel> panels;
+
+    // dense workspaces
+    DBuf<double> gram_partial, gbuf, gbuf2, cbuf, wsel, wsel2, small, stage, qws, pws, qtmp, rt, tmp_panel, evals;
+    DBuf<double> syevd_work;
+    DBuf<int32_t> ibuf;
+    double* h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+
+    // stats
+    dre_stats stats{};
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int fail(dre_context* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, DRE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+template <class T>
+int upload_vec(dre_context* c, const std::vector<T>& h, T** out) {
+    *out = nullptr;
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    CU(cudaMalloc((void**)out, bytes));
+    c->owned.push_back(*out);
+    if (!h.empty()) CU(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return DRE_OK;
+}
+
+int ensure_pinned(dre_context* c, size_t doubles) {
+    if (doubles <= c->h_pinned_cap) return DRE_OK;
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    c->h_pinned = nullptr;
+    c->h_pinned_cap = 0;
+    size_t want = doubles + doubles / 4 + 1024;
+    CU(cudaMallocHost((void**)&c->h_pinned, want * sizeof(double)));
+    c->h_pinned_cap = want;
+    return DRE_OK;
+}
+
+int check_view(dre_context* c, const dre_view& v, const char* what, bool allow_empty = false) {
+    if (v.ncols == 0 && allow_empty) return DRE_OK;
+    if (v.id < 0 || v.id >= (int)c->panels.size() || !c->panels[v.id].alive)
+        return fail(c, DRE_ERR_ARG, std::string(what) + ": invalid panel id");
+    const Panel& p = c->panels[v.id];
+    if (v.col0 < 0 || v.ncols < 0 || v.col0 + v.ncols > p.cols)
+        return fail(c, DRE_ERR_ARG, std::string(what) + ": column range outside the panel");
+    return DRE_OK;
+}
+
+inline double* vptr(dre_context* c, const dre_view& v) { return c->panels[v.id].d + v.col0; }
+inline int64_t vld(dre_context* c, const dre_view& v) { return c->panels[v.id].ld; }
+
+bool views_overlap(const dre_view& a, const dre_view& b) {
+    if (a.ncols == 0 || b.ncols == 0 || a.id != b.id) return false;
+    return a.col0 < b.col0 + b.ncols && b.col0 < a.col0 + a.ncols;
+}
+
+int check_errflag(dre_context* c) {
+    int32_t flag = 0;
+    CU(cudaMemcpyAsync(&flag, c->d_errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (flag != 0) {
+        CU(cudaMemsetAsync(c->d_errflag, 0, sizeof(int32_t), c->st));
+        return fail(c, DRE_ERR_NUMERIC,
+                    flag == 1 ? "numeric factorization broke down (zero or non-finite pivot)"
+                              : "Sherman-Morrison-Woodbury core is singular");
+    }
+    return DRE_OK;
+}
+
+struct Timer {
+    dre_context* c;
+    double* acc;
+    Timer(dre_context* c_, double* acc_) : c(c_), acc(acc_) {
+        if (c->timing) cudaEventRecord(c->ev0, c->st);
+    }
+    ~Timer() {
+        if (c->timing) {
+            cudaEventRecord(c->ev1, c->st);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            *acc += ms;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// gram helper: out (a x b, row-major ld) = X' diag(w) Y   (device result)
+// ---------------------------------------------------------------------------------------------
+int gram_dev(dre_context* c, const double* X, int64_t ldx, int a, const double* Y, int64_t ldy, int b, int64_t n,
+             const double* roww, double* out1, int64_t ld1, double* out2, int64_t ld2) {
+    if (a <= 0 || b <= 0) return DRE_OK;
+    GramPlan plan = gram_plan(n, a, b, c->sm_count);
+    CU(c->gram_partial.ensure(plan.partial_elems));
+    Timer t(c, &c->stats.ms_gram);
+    launch_gram(X, ldx, a, Y, ldy, b, n, roww, c->gram_partial.p, plan, out1, ld1, out2, ld2, c->st,
+                &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    return DRE_OK;
+}
+
+int tall_gemm(dre_context* c, double alpha, const double* X, int64_t ldx, int a, const double* W, int64_t ldw,
+              int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n) {
+    Timer t(c, &c->stats.ms_tallgemm);
+    launch_tall_gemm(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, c->st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    return DRE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// numeric factorization + solve
+// ---------------------------------------------------------------------------------------------
+template <class T>
+int factor(dre_context* c, T emu) {
+    const Symbolic& S = c->sym;
+    Timer t(c, &c->stats.ms_factor);
+    T* L = (T*)c->d_L;
+    T* dblk = (T*)c->d_dblk;
+    CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), c->st));
+    launch_assemble<T>(c->dS, L, c->op_a, emu, c->st, &c->stats.kernel_launches);
+    for (int l = 0; l < S.nlevels; ++l) {
+        const dre_context::LevelWork& lw = c->levels[l];
+        T* Ucur = (T*)c->d_U[l & 1];
+        const T* Uprev = (const T*)c->d_U[(l + 1) & 1];
+        if (lw.upd_elems > 0) CU(cudaMemsetAsync(Ucur, 0, (size_t)lw.upd_elems * sizeof(T), c->st));
+        if (lw.ea_count > 0)
+            launch_extend_add<T>(c->dS, c->d_ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, Ucur, Uprev, c->st,
+                                 &c->stats.kernel_launches);
+        for (size_t sidx = 0; sidx < lw.steps.size(); ++sidx)
+            launch_front_step<T>(c->dS, c->d_front_items + lw.steps[sidx].first, lw.steps[sidx].second, (int)sidx, L,
+                                 dblk, c->d_errflag, c->st, &c->stats.kernel_launches);
+        if (lw.schur_count > 0)
+            launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dblk, Ucur, c->st,
+                            &c->stats.kernel_launches);
+    }
+    CU(cudaGetLastError());
+    c->stats.factorizations++;
+    return DRE_OK;
+}
+
+template <class T>
+int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
+    const Symbolic& S = c->sym;
+    Timer t(c, &c->stats.ms_solve);
+    for (int par = 0; par < 2; ++par)
+        CU(c->tbuf[par].ensure((size_t)std::max<int64_t>(S.max_rhs_level[par], 1) * ldw * sizeof(T)));
+    const T* L = (const T*)c->d_L;
+    const T* dblk = (const T*)c->d_dblk;
+    for (int l = 0; l < S.nlevels; ++l) {
+        const dre_context::LevelWork& lw = c->levels[l];
+        launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, dblk, W, ldw, nrhs,
+                            (T*)c->tbuf[l & 1].p, (const T*)c->tbuf[(l + 1) & 1].p, c->st,
+                            &c->stats.kernel_launches);
+    }
+    for (int l = S.nlevels - 1; l >= 0; --l) {
+        const dre_context::LevelWork& lw = c->levels[l];
+        launch_bwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, dblk, W, ldw, nrhs, c->st,
+                            &c->stats.kernel_launches);
+    }
+    CU(cudaGetLastError());
+    c->stats.solves++;
+    return DRE_OK;
+}
+
+inline void make_emu(double e, double mr, double mi, double& out) { out = e + mr; (void)mi; }
+inline void make_emu(double e, double mr, double mi, cplx& out) { out = mk(e + mr, mi); }
+
+// mode: 0 real, 1 complex raw, 2 complex ADI pair
+template <class T>
+int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2, int mode) {
+    const int64_t n = c->sym.n;
+    const int r = R.ncols, m = c->op_U.ncols;
+    const int nrhs = r + m;
+    const int64_t ldw = (nrhs + 3) & ~3;
+    CU(c->Wbuf.ensure((size_t)n * ldw * sizeof(T)));
+    T* W = (T*)c->Wbuf.p;
+    launch_load_rhs<T>(W, ldw, vptr(c, R), vld(c, R), r, m ? vptr(c, c->op_Vt) : nullptr, m ? vld(c, c->op_Vt) : 0, m,
+                       n, c->st, &c->stats.kernel_launches);
+    T emu;
+    make_emu(c->op_e, mu_re, mu_im, emu);
+    int rc = factor<T>(c, emu);
+    if (rc) return rc;
+    rc = solve_sweeps<T>(c, W, ldw, nrhs);
+    if (rc) return rc;
+    const int tw = (int)(sizeof(T) / sizeof(double));  // 1 or 2 doubles per element
+    T* Sol = nullptr;
+    if (m > 0) {
+        CU(c->btw.ensure((size_t)m * nrhs * tw));
+        CU(c->sol.ensure((size_t)m * r * tw));
+        rc = gram_dev(c, vptr(c, c->op_U), vld(c, c->op_U), m, (const double*)W, ldw * tw, nrhs * tw, n, nullptr,
+                      c->btw.p, (int64_t)nrhs * tw, nullptr, 0);
+        if (rc) return rc;
+        Sol = (T*)c->sol.p;
+        launch_smw_core<T>((const T*)c->btw.p, nrhs, m, r, c->op_alpha, Sol, c->d_errflag, c->st,
+                           &c->stats.kernel_launches);
+    }
+    const double d = (mu_im != 0.0) ? mu_re / mu_im : 0.0;
+    launch_smw_apply<T>(W, ldw, r, m, Sol, mode, d, vptr(c, V1), vld(c, V1), mode ? vptr(c, V2) : nullptr,
+                        mode ? vld(c, V2) : 0, n, c->st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    return DRE_OK;
+}
+
+int shifted_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2, bool adi_pair) {
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    int rc;
+    if ((rc = check_view(c, R, "R"))) return rc;
+    if ((rc = check_view(c, V1, "V1"))) return rc;
+    if (V1.ncols != R.ncols) return fail(c, DRE_ERR_ARG, "V1 must have as many columns as R");
+    if (views_overlap(R, V1)) return fail(c, DRE_ERR_ARG, "V1 must not alias R");
+    if (c->op_U.ncols > 32) return fail(c, DRE_ERR_ARG, "low-rank update with more than 32 columns is not supported");
+    if (mu_im != 0.0) {
+        if ((rc = check_view(c, V2, "V2"))) return rc;
+        if (V2.ncols != R.ncols) return fail(c, DRE_ERR_ARG, "V2 must have as many columns as R");
+        if (views_overlap(R, V2) || views_overlap(V1, V2)) return fail(c, DRE_ERR_ARG, "V2 must not alias R or V1");
+        return shifted_solve_t<cplx>(c, mu_re, mu_im, R, V1, V2, adi_pair ? 2 : 1);
+    }
+    return shifted_solve_t<double>(c, mu_re, 0.0, R, V1, V2, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank-revealing block Gram-Schmidt (shared by compress! and rrqr)
+// ---------------------------------------------------------------------------------------------
+struct RRState {
+    double* Q = nullptr;   // n x qcap row-major
+    int64_t ldq = 0;
+    int qcap = 0;
+    int rho = 0;
+    double* RT = nullptr;  // ktot x ldrt row-major: coefficients of every input column in the basis
+    int64_t ldrt = 0;
+    double scale2 = 0.0;   // largest squared column norm seen so far
+    double drop_rel = 1e-11, drop_abs = 0.0;
+    int rounds = 0;
+};
+
+int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds, int cols, const double* d_colscale,
+                     int rt_row0) {
+    const int64_t n = c->sym.n;
+    constexpr int PB = 64;
+    CU(c->pws.ensure((size_t)n * PB));
+    CU(c->qtmp.ensure((size_t)n * PB));
+    CU(c->gbuf.ensure(PB * PB));
+    CU(c->gbuf2.ensure(PB * PB));
+    CU(c->wsel.ensure(PB * PB));
+    CU(c->wsel2.ensure(PB * PB));
+    CU(c->ibuf.ensure(8));
+    CU(c->small.ensure(8));
+    int rc = ensure_pinned(c, 16);
+    if (rc) return rc;
+    double* Pw = c->pws.p;
+    double* Qt = c->qtmp.p;
+    for (int c0 = 0; c0 < cols; c0 += PB) {
+        const int pb = std::min(PB, cols - c0);
+        launch_copy_scale(Pw, PB, src + c0, lds, n, pb, d_colscale ? d_colscale + c0 : nullptr, c->st,
+                          &c->stats.kernel_launches);
+        for (int round = 0; round < 8; ++round) {
+            s.rounds++;
+            if (s.rho > 0) {
+                CU(c->cbuf.ensure((size_t)PB * s.rho));
+                for (int pass = 0; pass < 2; ++pass) {
+                    // C' = Pw' Q (pb x rho): coefficients, accumulated into RT rows of this panel
+                    rc = gram_dev(c, Pw, PB, pb, s.Q, s.ldq, s.rho, n, nullptr, c->cbuf.p, s.rho,
+                                  s.RT + (int64_t)(rt_row0 + c0) * s.ldrt, s.ldrt);
+                    if (rc) return rc;
+                    rc = tall_gemm(c, -1.0, s.Q, s.ldq, s.rho, c->cbuf.p, s.rho, 1, 1.0, Pw, PB, pb, n);
+                    if (rc) return rc;
+                }
+            }
+            rc = gram_dev(c, Pw, PB, pb, Pw, PB, pb, n, nullptr, c->gbuf.p, PB, nullptr, 0);
+            if (rc) return rc;
+            const double drop = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
+            launch_pivchol(c->gbuf.p, PB, pb, drop * drop, 1e-8, c->wsel.p, c->ibuf.p, c->small.p, c->st,
+                           &c->stats.kernel_launches);
+            if (s.rho + PB > s.qcap) return fail(c, DRE_ERR_STATE, "rank-revealing QR: basis capacity exceeded");
+            rc = tall_gemm(c, 1.0, Pw, PB, pb, c->wsel.p, PB, 0, 0.0, Qt, PB, PB, n);
+            if (rc) return rc;
+            rc = gram_dev(c, Qt, PB, PB, Qt, PB, PB, n, nullptr, c->gbuf2.p, PB, nullptr, 0);
+            if (rc) return rc;
+            launch_pivchol(c->gbuf2.p, PB, PB, 0.01, 0.0, c->wsel2.p, c->ibuf.p + 2, c->small.p + 2, c->st,
+                           &c->stats.kernel_launches);
+            rc = tall_gemm(c, 1.0, Qt, PB, PB, c->wsel2.p, PB, 0, 0.0, s.Q + s.rho, s.ldq, PB, n);
+            if (rc) return rc;
+            int32_t* hi = (int32_t*)(c->h_pinned + 8);
+            CU(cudaMemcpyAsync(hi, c->ibuf.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(c->h_pinned, c->small.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            const int nsel = hi[0], nsel2 = hi[2];
+            const double dfirst = c->h_pinned[0], remaining = c->h_pinned[1];
+            if (round == 0) s.scale2 = std::max(s.scale2, dfirst);
+            if (nsel == 0 || nsel2 == 0) break;
+            s.rho += nsel2;
+            // the remaining (unselected) columns are certified negligible when the Gram rounding noise
+            // (~1e-13 * dfirst) is below the drop threshold and the remaining Schur diagonal is too
+            const double drop_now = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
+            if (nsel2 == nsel && remaining <= drop_now * drop_now && 1e-13 * dfirst <= drop_now * drop_now) break;
+            if (nsel == pb && nsel2 == pb && round > 0) { /* keep going: coefficients of the new columns */ }
+        }
+    }
+    return DRE_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* dre_version(void) { return "dre_b200 0.1 (sm_100a)"; }
+
+const char* dre_last_error(const dre_context* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int32_t dre_symbolic_create(int64_t n, const int64_t* Ecp, const int64_t* Eri, const double* Enz, const int64_t* Acp,
+                            const int64_t* Ari, const double* Anz, int32_t base, int32_t leaf_size,
+                            dre_symbolic** out) {
+    if (!out || !Ecp || !Eri || !Enz || !Acp || !Ari || !Anz) return fail(nullptr, DRE_ERR_ARG, "null argument");
+    dre_symbolic* s = new (std::nothrow) dre_symbolic();
+    if (!s) return fail(nullptr, DRE_ERR_LIB, "out of host memory");
+    AnalyzeOptions opt;
+    if (leaf_size > 0) opt.leaf_size = leaf_size;
+    std::string e;
+    try {
+        e = analyze(n, Ecp, Eri, Enz, Acp, Ari, Anz, base, opt, s->sym);
+    } catch (const std::exception& ex) {
+        e = std::string("analyze: ") + ex.what();
+    }
+    if (!e.empty()) { delete s; return fail(nullptr, DRE_ERR_ARG, e); }
+    *out = s;
+    return DRE_OK;
+}
+
+void dre_symbolic_destroy(dre_symbolic* s) { delete s; }
+
+static void fill_info(const Symbolic& S, dre_symbolic_info* info) {
+    info->n = S.n;
+    info->nnz_pattern = (int64_t)S.csr_col.size();
+    info->nnz_L = S.nnz_L;
+    info->sum_update_rows = S.sum_u;
+    info->factor_flops = S.flops;
+    info->nsupernodes = S.nsn;
+    info->nlevels = S.nlevels;
+    info->max_front = S.max_front;
+    info->max_supernode = S.max_sn;
+}
+
+int32_t dre_symbolic_get_info(const dre_symbolic* s, dre_symbolic_info* info) {
+    if (!s || !info) return fail(nullptr, DRE_ERR_ARG, "null argument");
+    fill_info(s->sym, info);
+    return DRE_OK;
+}
+
+int32_t dre_symbolic_export(const dre_symbolic* s, const char* what, void* buf, int64_t cap, int64_t* len) {
+    if (!s || !what || !len) return fail(nullptr, DRE_ERR_ARG, "null argument");
+    const Symbolic& S = s->sym;
+    std::string w(what);
+    auto put_i = [&](const auto& v) {
+        *len = (int64_t)v.size();
+        int64_t* o = (int64_t*)buf;
+        for (int64_t i = 0; buf && i < std::min<int64_t>(cap, *len); ++i) o[i] = (int64_t)v[i];
+        return DRE_OK;
+    };
+    auto put_d = [&](const std::vector<double>& v) {
+        *len = (int64_t)v.size();
+        double* o = (double*)buf;
+        for (int64_t i = 0; buf && i < std::min<int64_t>(cap, *len); ++i) o[i] = v[i];
+        return DRE_OK;
+    };
+    if (w == "perm") return put_i(S.perm);
+    if (w == "iperm") return put_i(S.iperm);
+    if (w == "sn_first") return put_i(S.sn_first);
+    if (w == "sn_rowptr") return put_i(S.sn_rowptr);
+    if (w == "sn_rows") return put_i(S.sn_rows);
+    if (w == "sn_parent") return put_i(S.sn_parent);
+    if (w == "sn_level") return put_i(S.sn_level);
+    if (w == "level_ptr") return put_i(S.level_ptr);
+    if (w == "level_sn") return put_i(S.level_sn);
+    if (w == "panel_off") return put_i(S.panel_off);
+    if (w == "upd_off") return put_i(S.upd_off);
+    if (w == "rhs_off") return put_i(S.rhs_off);
+    if (w == "child_ptr") return put_i(S.child_ptr);
+    if (w == "child_idx") return put_i(S.child_idx);
+    if (w == "relmap") return put_i(S.relmap);
+    if (w == "asm_dest") return put_i(S.asm_dest);
+    if (w == "asm_a") return put_d(S.asm_a);
+    if (w == "asm_e") return put_d(S.asm_e);
+    if (w == "csr_ptr") return put_i(S.csr_ptr);
+    if (w == "csr_col") return put_i(S.csr_col);
+    if (w == "csr_a") return put_d(S.csr_a);
+    if (w == "csr_e") return put_d(S.csr_e);
+    return fail(nullptr, DRE_ERR_ARG, "dre_symbolic_export: unknown array name " + w);
+}
+
+int32_t dre_create(int32_t device, dre_context** out) {
+    if (!out) return fail(nullptr, DRE_ERR_ARG, "null argument");
+    dre_context* c = new (std::nothrow) dre_context();
+    if (!c) return fail(nullptr, DRE_ERR_LIB, "out of host memory");
+    c->device = device;
+    auto bail = [&](const std::string& m) { g_last_error = m; delete c; return DRE_ERR_CUDA; };
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e) +
+                                      " (libdre_b200 has no CPU fallback; a CUDA device is required)");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major < 10) return bail("libdre_b200 is built for sm_100a (B200) only");
+    c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    if (cusolverDnCreate(&c->cusolver) != CUSOLVER_STATUS_SUCCESS) return bail("cusolverDnCreate failed");
+    cusolverDnSetStream(c->cusolver, c->st);
+    e = cudaMalloc((void**)&c->d_errflag, sizeof(int32_t));
+    if (e != cudaSuccess) return bail("cudaMalloc failed");
+    cudaMemset(c->d_errflag, 0, sizeof(int32_t));
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return DRE_OK;
+}
+
+static void release_pencil(dre_context* c) {
+    for (void* p : c->owned) cudaFree(p);
+    c->owned.clear();
+    if (c->d_L) cudaFree(c->d_L);
+    if (c->d_dblk) cudaFree(c->d_dblk);
+    for (int i = 0; i < 2; ++i) if (c->d_U[i]) cudaFree(c->d_U[i]);
+    c->d_L = c->d_dblk = c->d_U[0] = c->d_U[1] = nullptr;
+    c->has_pencil = false;
+}
+
+int32_t dre_destroy(dre_context* c) {
+    if (!c) return DRE_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    for (Panel& p : c->panels) if (p.alive && p.d) cudaFree(p.d);
+    release_pencil(c);
+    c->tbuf[0].release(); c->tbuf[1].release(); c->Wbuf.release(); c->btw.release(); c->sol.release();
+    c->gram_partial.release(); c->gbuf.release(); c->gbuf2.release(); c->cbuf.release(); c->wsel.release();
+    c->wsel2.release(); c->small.release(); c->stage.release(); c->qws.release(); c->pws.release();
+    c->qtmp.release(); c->rt.release(); c->tmp_panel.release(); c->evals.release(); c->syevd_work.release();
+    c->ibuf.release();
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->d_errflag) cudaFree(c->d_errflag);
+    if (c->cusolver) cusolverDnDestroy(c->cusolver);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+    return DRE_OK;
+}
+
+int32_t dre_sync(dre_context* c) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    CU(cudaStreamSynchronize(c->st));
+    return DRE_OK;
+}
+
+int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int64_t* Eri, const double* Enz,
+                       const int64_t* Acp, const int64_t* Ari, const double* Anz, int32_t base) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->st));
+    release_pencil(c);
+    for (Panel& p : c->panels) if (p.alive && p.d) { cudaFree(p.d); p.alive = false; p.d = nullptr; }
+    c->op_U = c->op_Vt = dre_view{-1, 0, 0};
+    AnalyzeOptions opt;
+    opt.leaf_size = 32;
+    std::string e;
+    try {
+        e = analyze(n, Ecp, Eri, Enz, Acp, Ari, Anz, base, opt, c->sym);
+    } catch (const std::exception& ex) {
+        e = std::string("analyze: ") + ex.what();
+    }
+    if (!e.empty()) return fail(c, DRE_ERR_ARG, e);
+    const Symbolic& S = c->sym;
+
+    // diagonal-block side storage offsets
+    std::vector<int64_t> dblk_off(S.nsn + 1, 0);
+    for (int J = 0; J < S.nsn; ++J) dblk_off[J + 1] = dblk_off[J] + (int64_t)((S.sn_size(J) + 31) / 32) * 1024;
+    c->dblk_elems = dblk_off[S.nsn];
+
+    int rc;
+    int32_t *d_sn_first, *d_sn_rows, *d_relmap, *d_child_ptr, *d_child_idx, *d_sn_level;
+    int64_t *d_sn_rowptr, *d_panel_off, *d_upd_off, *d_rhs_off, *d_dblk_off, *d_asm_dest;
+    double *d_asm_a, *d_asm_e;
+    if ((rc = upload_vec(c, S.sn_first, &d_sn_first))) return rc;
+    if ((rc = upload_vec(c, S.sn_rowptr, &d_sn_rowptr))) return rc;
+    if ((rc = upload_vec(c, S.sn_rows, &d_sn_rows))) return rc;
+    if ((rc = upload_vec(c, S.relmap, &d_relmap))) return rc;
+    if ((rc = upload_vec(c, S.child_ptr, &d_child_ptr))) return rc;
+    if ((rc = upload_vec(c, S.child_idx, &d_child_idx))) return rc;
+    if ((rc = upload_vec(c, S.panel_off, &d_panel_off))) return rc;
+    if ((rc = upload_vec(c, S.upd_off, &d_upd_off))) return rc;
+    if ((rc = upload_vec(c, S.rhs_off, &d_rhs_off))) return rc;
+    if ((rc = upload_vec(c, dblk_off, &d_dblk_off))) return rc;
+    if ((rc = upload_vec(c, S.sn_level, &d_sn_level))) return rc;
+    if ((rc = upload_vec(c, S.asm_dest, &d_asm_dest))) return rc;
+    if ((rc = upload_vec(c, S.asm_a, &d_asm_a))) return rc;
+    if ((rc = upload_vec(c, S.asm_e, &d_asm_e))) return rc;
+    if ((rc = upload_vec(c, S.iperm, &c->d_iperm))) return rc;
+    if ((rc = upload_vec(c, S.csr_ptr, &c->d_csr_ptr))) return rc;
+    if ((rc = upload_vec(c, S.csr_col, &c->d_csr_col))) return rc;
+    if ((rc = upload_vec(c, S.csr_a, &c->d_csr_a))) return rc;
+    if ((rc = upload_vec(c, S.csr_e, &c->d_csr_e))) return rc;
+    if ((rc = upload_vec(c, S.level_sn, &c->d_level_sn))) return rc;
+    DevSymbolic& D = c->dS;
+    D.n = S.n; D.nsn = S.nsn; D.nlevels = S.nlevels;
+    D.sn_first = d_sn_first; D.sn_rowptr = d_sn_rowptr; D.sn_rows = d_sn_rows; D.relmap = d_relmap;
+    D.child_ptr = d_child_ptr; D.child_idx = d_child_idx; D.panel_off = d_panel_off; D.upd_off = d_upd_off;
+    D.rhs_off = d_rhs_off; D.dblk_off = d_dblk_off; D.sn_level = d_sn_level;
+    D.nasm = (int64_t)S.asm_dest.size(); D.asm_dest = d_asm_dest; D.asm_a = d_asm_a; D.asm_e = d_asm_e;
+
+    // per-level work lists
+    c->levels.assign(S.nlevels, dre_context::LevelWork());
+    std::vector<int32_t> ea_parents;
+    std::vector<int2> front_items;
+    std::vector<int4> schur_items;
+    for (int l = 0; l < S.nlevels; ++l) {
+        dre_context::LevelWork& lw = c->levels[l];
+        lw.sn_begin = S.level_ptr[l];
+        lw.sn_count = S.level_ptr[l + 1] - S.level_ptr[l];
+        lw.ea_begin = (int)ea_parents.size();
+        int max_s = 0, max_f = 0;
+        for (int p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p) {
+            const int J = S.level_sn[p];
+            const int64_t u = S.sn_nrows(J);
+            lw.upd_elems += u * u;
+            max_s = std::max(max_s, S.sn_size(J));
+            max_f = std::max(max_f, S.front(J));
+            if (S.child_ptr[J + 1] > S.child_ptr[J]) ea_parents.push_back(J);
+        }
+        lw.ea_count = (int)ea_parents.size() - lw.ea_begin;
+        lw.ea_gy = std::min(32, std::max(1, max_f / 32));
+        const int nsteps = (max_s + 31) / 32;
+        for (int step = 0; step < nsteps; ++step) {
+            const int begin = (int)front_items.size();
+            for (int p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p) {
+                const int J = S.level_sn[p];
+                const int s = S.sn_size(J), f = S.front(J);
+                const int k0 = step * 32;
+                if (k0 >= s) continue;
+                const int nb = std::min(32, s - k0);
+                const int below = f - k0 - nb;
+                const int nslab = std::max(1, (below + 95) / 96);
+                for (int sl = 0; sl < nslab; ++sl) front_items.push_back(make_int2(J, sl));
+            }
+            lw.steps.push_back({begin, (int)front_items.size() - begin});
+        }
+        lw.schur_begin = (int)schur_items.size();
+        for (int p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p) {
+            const int J = S.level_sn[p];
+            const int u = S.sn_nrows(J);
+            const int nt = (u + 63) / 64;
+            for (int ti = 0; ti < nt; ++ti)
+                for (int tj = 0; tj <= ti; ++tj) schur_items.push_back(make_int4(J, ti, tj, 0));
+        }
+        lw.schur_count = (int)schur_items.size() - lw.schur_begin;
+    }
+    if ((rc = upload_vec(c, ea_parents, &c->d_ea_parents))) return rc;
+    if ((rc = upload_vec(c, front_items, &c->d_front_items))) return rc;
+    if ((rc = upload_vec(c, schur_items, &c->d_schur_items))) return rc;
+
+    // factor storage, sized for complex
+    CU(cudaMalloc(&c->d_L, (size_t)std::max<int64_t>(S.nnz_L, 1) * sizeof(cplx)));
+    CU(cudaMalloc(&c->d_dblk, (size_t)std::max<int64_t>(c->dblk_elems, 1) * sizeof(cplx)));
+    for (int par = 0; par < 2; ++par)
+        CU(cudaMalloc(&c->d_U[par], (size_t)std::max<int64_t>(S.max_upd_level[par], 1) * sizeof(cplx)));
+    c->has_pencil = true;
+    c->op_a = 1.0; c->op_e = 0.0; c->op_alpha = 1.0;
+    return DRE_OK;
+}
+
+int32_t dre_get_symbolic_info(const dre_context* c, dre_symbolic_info* info) {
+    if (!c || !info) return fail(nullptr, DRE_ERR_ARG, "null argument");
+    if (!c->has_pencil) return fail(const_cast<dre_context*>(c), DRE_ERR_STATE, "no pencil set");
+    fill_info(c->sym, info);
+    return DRE_OK;
+}
+
+// ---- panels ----
+int32_t dre_mat_create(dre_context* c, int32_t cols, int32_t* id) {
+    if (!c || !id) return fail(c, DRE_ERR_ARG, "null argument");
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    if (cols < 0) return fail(c, DRE_ERR_ARG, "negative column count");
+    Panel p;
+    p.cols = cols;
+    p.ld = std::max(1, (cols + 1) & ~1);  // even leading dimension: 16-byte aligned rows
+    CU(cudaMallocAsync((void**)&p.d, (size_t)c->sym.n * p.ld * sizeof(double), c->st));
+    p.alive = true;
+    for (size_t i = 0; i < c->panels.size(); ++i)
+        if (!c->panels[i].alive) { c->panels[i] = p; *id = (int32_t)i; return DRE_OK; }
+    c->panels.push_back(p);
+    *id = (int32_t)c->panels.size() - 1;
+    return DRE_OK;
+}
+
+int32_t dre_mat_free(dre_context* c, int32_t id) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (id < 0 || id >= (int)c->panels.size() || !c->panels[id].alive) return fail(c, DRE_ERR_ARG, "invalid panel id");
+    if (c->op_U.id == id || c->op_Vt.id == id) c->op_U = c->op_Vt = dre_view{-1, 0, 0};
+    CU(cudaFreeAsync(c->panels[id].d, c->st));
+    c->panels[id].alive = false;
+    c->panels[id].d = nullptr;
+    return DRE_OK;
+}
+
+int32_t dre_mat_upload(dre_context* c, dre_view dst, const double* host, int64_t ld) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    int rc;
+    if ((rc = check_view(c, dst, "dst", true))) return rc;
+    if (dst.ncols == 0) return DRE_OK;
+    const int64_t n = c->sym.n;
+    if (!host || ld < n) return fail(c, DRE_ERR_ARG, "bad host matrix");
+    CU(c->stage.ensure((size_t)n * dst.ncols));
+    CU(cudaMemcpy2DAsync(c->stage.p, n * sizeof(double), host, ld * sizeof(double), n * sizeof(double), dst.ncols,
+                         cudaMemcpyHostToDevice, c->st));
+    launch_colmajor_to_panel(vptr(c, dst), vld(c, dst), c->stage.p, n, n, dst.ncols, c->d_iperm, c->st,
+                             &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->st));  // the host buffer is only borrowed for the duration of the call
+    return DRE_OK;
+}
+
+int32_t dre_mat_download(dre_context* c, dre_view src, double* host, int64_t ld) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    int rc;
+    if ((rc = check_view(c, src, "src", true))) return rc;
+    if (src.ncols == 0) return DRE_OK;
+    const int64_t n = c->sym.n;
+    if (!host || ld < n) return fail(c, DRE_ERR_ARG, "bad host matrix");
+    CU(c->stage.ensure((size_t)n * src.ncols));
+    launch_panel_to_colmajor(c->stage.p, n, vptr(c, src), vld(c, src), n, src.ncols, c->d_iperm, c->st,
+                             &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy2DAsync(host, ld * sizeof(double), c->stage.p, n * sizeof(double), n * sizeof(double), src.ncols,
+                         cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return check_errflag(c);
+}
+
+int32_t dre_mat_copy(dre_context* c, dre_view dst, dre_view src) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    int rc;
+    if ((rc = check_view(c, dst, "dst", true)) || (rc = check_view(c, src, "src", true))) return rc;
+    if (dst.ncols != src.ncols) return fail(c, DRE_ERR_ARG, "copy: column counts differ");
+    if (views_overlap(dst, src)) return fail(c, DRE_ERR_ARG, "copy: views overlap");
+    if (dst.ncols == 0) return DRE_OK;
+    launch_copy_scale(vptr(c, dst), vld(c, dst), vptr(c, src), vld(c, src), c->sym.n, dst.ncols, nullptr, c->st,
+                      &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    return DRE_OK;
+}
+
+int32_t dre_mat_axpby(dre_context* c, double alpha, dre_view X, double beta, dre_view Y) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    int rc;
+    if ((rc = check_view(c, Y, "Y", true))) return rc;
+    if (Y.ncols == 0) return DRE_OK;
+    if (alpha != 0.0) {
+        if ((rc = check_view(c, X, "X"))) return rc;
+        if (X.ncols != Y.ncols) return fail(c, DRE_ERR_ARG, "axpby: column counts differ");
+    }
+    launch_axpby(alpha, alpha != 0.0 ? vptr(c, X) : nullptr, alpha != 0.0 ? vld(c, X) : 0, beta, vptr(c, Y),
+                 vld(c, Y), c->sym.n, Y.ncols, c->st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    return DRE_OK;
+}
+
+// ---- products ----
+int32_t dre_spmm(dre_context* c, int32_t op, double alpha, dre_view X, double beta, dre_view Y) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    int rc;
+    if ((rc = check_view(c, X, "X", true)) || (rc = check_view(c, Y, "Y", true))) return rc;
+    if (X.ncols != Y.ncols) return fail(c, DRE_ERR_ARG, "spmm: column counts differ");
+    if (views_overlap(X, Y)) return fail(c, DRE_ERR_ARG, "spmm: X and Y overlap");
+    if (X.ncols == 0) return DRE_OK;
+    const double* val = (op == 'E' || op == 'e') ? c->d_csr_e : (op == 'A' || op == 'a') ? c->d_csr_a : nullptr;
+    if (!val) return fail(c, DRE_ERR_ARG, "spmm: op must be 'E' or 'A'");
+    Timer t(c, &c->stats.ms_spmm);
+    launch_spmm(c->d_csr_ptr, c->d_csr_col, val, c->sym.n, alpha, vptr(c, X), vld(c, X), beta, vptr(c, Y), vld(c, Y),
+                X.ncols, c->st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    return DRE_OK;
+}
+
+int32_t dre_gemm_tn(dre_context* c, dre_view X, dre_view Y, double* out, int64_t ld) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    int rc;
+    if ((rc = check_view(c, X, "X", true)) || (rc = check_view(c, Y, "Y", true))) return rc;
+    const int a = X.ncols, b = Y.ncols;
+    if (a == 0 || b == 0) return DRE_OK;
+    if (!out || ld < a) return fail(c, DRE_ERR_ARG, "gemm_tn: bad output");
+    CU(c->gbuf.ensure((size_t)a * b));
+    if ((rc = gram_dev(c, vptr(c, X), vld(c, X), a, vptr(c, Y), vld(c, Y), b, c->sym.n, nullptr, c->gbuf.p, b, nullptr,
+                       0)))
+        return rc;
+    if ((rc = ensure_pinned(c, (size_t)a * b))) return rc;
+    CU(cudaMemcpyAsync(c->h_pinned, c->gbuf.p, (size_t)a * b * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < a; ++i)
+        for (int j = 0; j < b; ++j) out[i + (int64_t)j * ld] = c->h_pinned[(int64_t)i * b + j];
+    return check_errflag(c);
+}
+
+int32_t dre_gemm_nn(dre_context* c, double alpha, dre_view X, const double* W, int64_t ldw, double beta, dre_view Y) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    int rc;
+    if ((rc = check_view(c, X, "X", true)) || (rc = check_view(c, Y, "Y", true))) return rc;
+    const int a = X.ncols, b = Y.ncols;
+    if (b == 0) return DRE_OK;
+    if (views_overlap(X, Y)) return fail(c, DRE_ERR_ARG, "gemm_nn: X and Y overlap");
+    if (a == 0) return dre_mat_axpby(c, 0.0, X, beta, Y);
+    if (!W || ldw < a) return fail(c, DRE_ERR_ARG, "gemm_nn: bad W");
+    if ((rc = ensure_pinned(c, (size_t)a * b))) return rc;
+    CU(cudaStreamSynchronize(c->st));  // pinned staging may still be in flight
+    for (int i = 0; i < a; ++i)
+        for (int j = 0; j < b; ++j) c->h_pinned[(int64_t)i * b + j] = W[i + (int64_t)j * ldw];
+    CU(c->gbuf2.ensure((size_t)a * b));
+    CU(cudaMemcpyAsync(c->gbuf2.p, c->h_pinned, (size_t)a * b * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    rc = tall_gemm(c, alpha, vptr(c, X), vld(c, X), a, c->gbuf2.p, b, 0, beta, vptr(c, Y), vld(c, Y), b, c->sym.n);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->st));  // h_pinned / gbuf2 are reused by the next call
+    return DRE_OK;
+}
+
+// ---- operator and solves ----
+int32_t dre_set_operator(dre_context* c, double a, double e, double alpha, dre_view U, dre_view Vt) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    int rc;
+    if ((rc = check_view(c, U, "U", true)) || (rc = check_view(c, Vt, "Vt", true))) return rc;
+    if (U.ncols != Vt.ncols) return fail(c, DRE_ERR_ARG, "set_operator: U and Vt must have the same column count");
+    if (U.ncols > 0 && alpha == 0.0) return fail(c, DRE_ERR_ARG, "set_operator: alpha must be nonzero");
+    c->op_a = a; c->op_e = e; c->op_alpha = alpha;
+    c->op_U = U.ncols ? U : dre_view{-1, 0, 0};
+    c->op_Vt = Vt.ncols ? Vt : dre_view{-1, 0, 0};
+    return DRE_OK;
+}
+
+int32_t dre_shift_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    return shifted_solve(c, mu_re, mu_im, R, V1, V2, false);
+}
+
+int32_t dre_adi_step(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    int rc = shifted_solve(c, mu_re, mu_im, R, V1, V2, true);
+    if (rc) return rc;
+    const double coef = (mu_im != 0.0) ? -2.0 * 1.4142135623730951 * mu_re : -2.0 * mu_re;
+    Timer t(c, &c->stats.ms_spmm);
+    launch_spmm(c->d_csr_ptr, c->d_csr_col, c->d_csr_e, c->sym.n, coef, vptr(c, V1), vld(c, V1), 1.0, vptr(c, R),
+                vld(c, R), R.ncols, c->st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    return DRE_OK;
+}
+
+// ---- low-rank algebra ----
+int32_t dre_ldlt_norm(dre_context* c, dre_view L, const double* D, int64_t ldd, double alpha, double* out) {
+    if (!c || !out) return fail(c, DRE_ERR_ARG, "null argument");
+    int rc;
+    if ((rc = check_view(c, L, "L", true))) return rc;
+    const int k = L.ncols;
+    if (k == 0) { *out = 0.0; return DRE_OK; }
+    if (!D || ldd < k) return fail(c, DRE_ERR_ARG, "norm: bad core matrix");
+    bool diag = true;
+    for (int j = 0; j < k && diag; ++j)
+        for (int i = 0; i < k; ++i)
+            if (i != j && D[i + (int64_t)j * ldd] != 0.0) { diag = false; break; }
+    CU(c->gbuf.ensure((size_t)k * k));
+    if ((rc = gram_dev(c, vptr(c, L), vld(c, L), k, vptr(c, L), vld(c, L), k, c->sym.n, nullptr, c->gbuf.p, k, nullptr,
+                       0)))
+        return rc;
+    if ((rc = ensure_pinned(c, (size_t)k * k + k))) return rc;
+    if (diag) {
+        CU(cudaStreamSynchronize(c->st));
+        for (int i = 0; i < k; ++i) c->h_pinned[i] = D[i + (int64_t)i * ldd];
+        CU(c->small.ensure(k + 8));
+        CU(cudaMemcpyAsync(c->small.p + 8, c->h_pinned, k * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        launch_norm_diag(c->gbuf.p, k, k, c->small.p + 8, c->small.p, c->st, &c->stats.kernel_launches);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(c->h_pinned + k, c->small.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        const double v2 = c->h_pinned[k];
+        *out = std::fabs(alpha) * std::sqrt(std::max(v2, 0.0));
+    } else {
+        CU(cudaMemcpyAsync(c->h_pinned, c->gbuf.p, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        // ||L D L'||_F^2 = tr(G D G D),  G = L'L  (host, rare path: dense core)
+        std::vector<double> M((size_t)k * k, 0.0);
+        const double* G = c->h_pinned;  // row-major, symmetric
+        for (int i = 0; i < k; ++i)
+            for (int t = 0; t < k; ++t) {
+                const double g = G[(int64_t)i * k + t];
+                if (g == 0.0) continue;
+                for (int j = 0; j < k; ++j) M[(size_t)i * k + j] += g * D[t + (int64_t)j * ldd];
+            }
+        double tr = 0.0;
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) tr += M[(size_t)i * k + j] * M[(size_t)j * k + i];
+        *out = std::fabs(alpha) * std::sqrt(std::max(tr, 0.0));
+    }
+    return check_errflag(c);
+}
+
+static int eig_sym_dev(dre_context* c, double* S, int k, double* d_evals) {
+    int lwork = 0;
+    if (cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, S, k, d_evals,
+                                    &lwork) != CUSOLVER_STATUS_SUCCESS)
+        return fail(c, DRE_ERR_LIB, "cusolverDnDsyevd_bufferSize failed");
+    CU(c->syevd_work.ensure((size_t)lwork + 8));
+    CU(c->ibuf.ensure(8));
+    if (cusolverDnDsyevd(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, S, k, d_evals,
+                         c->syevd_work.p, lwork, c->ibuf.p + 4) != CUSOLVER_STATUS_SUCCESS)
+        return fail(c, DRE_ERR_LIB, "cusolverDnDsyevd failed");
+    return DRE_OK;
+}
+
+static int rr_setup(dre_context* c, RRState& s, int ktot, double drop_rel, double drop_abs) {
+    const int64_t n = c->sym.n;
+    s.qcap = (int)std::min<int64_t>(ktot, n) + 64;
+    s.ldq = (s.qcap + 1) & ~1;
+    CU(c->qws.ensure((size_t)n * s.ldq));
+    s.Q = c->qws.p;
+    s.ldrt = s.ldq;
+    CU(c->rt.ensure((size_t)ktot * s.ldrt));
+    s.RT = c->rt.p;
+    CU(cudaMemsetAsync(s.RT, 0, (size_t)ktot * s.ldrt * sizeof(double), c->st));
+    s.rho = 0;
+    s.scale2 = 0.0;
+    s.drop_rel = drop_rel;
+    s.drop_abs = drop_abs;
+    return DRE_OK;
+}
+
+int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, const double* const* Ds,
+                          const int64_t* ldds, const double* alphas, double tol_factor, dre_view out, double* lam,
+                          int32_t* newrank) {
+    if (!c || !Ls || !Ds || !ldds || !alphas || !lam || !newrank) return fail(c, DRE_ERR_ARG, "null argument");
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    int rc;
+    int ktot = 0;
+    for (int t = 0; t < nterms; ++t) {
+        if ((rc = check_view(c, Ls[t], "Ls[i]", true))) return rc;
+        ktot += Ls[t].ncols;
+    }
+    if ((rc = check_view(c, out, "out", true))) return rc;
+    *newrank = 0;
+    if (ktot == 0) return DRE_OK;
+    const int64_t n = c->sym.n;
+    RRState s;
+    if ((rc = rr_setup(c, s, ktot, 1e-11, 0.0))) return rc;
+    std::vector<double> signs(ktot, 1.0);
+    int row0 = 0;
+    for (int t = 0; t < nterms; ++t) {
+        const int k = Ls[t].ncols;
+        if (k == 0) continue;
+        const double* D = Ds[t];
+        const int64_t ldd = ldds[t];
+        if (!D || ldd < k) return fail(c, DRE_ERR_ARG, "compress: bad core matrix");
+        bool diag = true;
+        for (int j = 0; j < k && diag; ++j)
+            for (int i = 0; i < k; ++i)
+                if (i != j && D[i + (int64_t)j * ldd] != 0.0) { diag = false; break; }
+        if ((rc = ensure_pinned(c, (size_t)k * k + 64))) return rc;
+        CU(cudaStreamSynchronize(c->st));
+        if (diag) {
+            for (int j = 0; j < k; ++j) {
+                const double v = alphas[t] * D[j + (int64_t)j * ldd];
+                c->h_pinned[j] = std::sqrt(std::fabs(v));
+                signs[row0 + j] = (v < 0.0) ? -1.0 : 1.0;
+            }
+            CU(c->evals.ensure(k));
+            CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, k * sizeof(double), cudaMemcpyHostToDevice, c->st));
+            if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, c->evals.p, row0))) return rc;
+        } else {
+            // dense core: alpha*D = W Lambda W'  ->  block (L W |Lambda|^1/2) with signs sign(Lambda)
+            for (int j = 0; j < k; ++j)
+                for (int i = 0; i < k; ++i)
+                    c->h_pinned[i + (int64_t)j * k] =
+                        0.5 * alphas[t] * (D[i + (int64_t)j * ldd] + D[j + (int64_t)i * ldd]);
+            CU(c->gbuf2.ensure((size_t)k * k));
+            CU(c->evals.ensure(k));
+            CU(cudaMemcpyAsync(c->gbuf2.p, c->h_pinned, (size_t)k * k * sizeof(double), cudaMemcpyHostToDevice, c->st));
+            if ((rc = eig_sym_dev(c, c->gbuf2.p, k, c->evals.p))) return rc;
+            CU(cudaMemcpyAsync(c->h_pinned, c->evals.p, k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            for (int j = 0; j < k; ++j) {
+                signs[row0 + j] = (c->h_pinned[j] < 0.0) ? -1.0 : 1.0;
+                c->h_pinned[j] = std::sqrt(std::fabs(c->h_pinned[j]));
+            }
+            CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, k * sizeof(double), cudaMemcpyHostToDevice, c->st));
+            // eigenvector j = column j of the column-major result = row j of the row-major view:
+            // tmp = L * W  with W[i][j] = vec_j[i]  -> w_trans layout (stored j-major)
+            CU(c->tmp_panel.ensure((size_t)n * k));
+            if ((rc = tall_gemm(c, 1.0, vptr(c, Ls[t]), vld(c, Ls[t]), k, c->gbuf2.p, k, 1, 0.0, c->tmp_panel.p, k, k,
+                                n)))
+                return rc;
+            if ((rc = rr_process_block(c, s, c->tmp_panel.p, k, k, c->evals.p, row0))) return rc;
+        }
+        row0 += k;
+    }
+    const int rho = s.rho;
+    if (rho == 0) return check_errflag(c);
+    // S = RT' diag(signs) RT   (rho x rho)
+    if ((rc = ensure_pinned(c, (size_t)ktot + rho + 64))) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < ktot; ++i) c->h_pinned[i] = signs[i];
+    CU(c->evals.ensure((size_t)ktot + rho));
+    CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, ktot * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CU(c->gbuf.ensure((size_t)rho * rho));
+    if ((rc = gram_dev(c, s.RT, s.ldrt, rho, s.RT, s.ldrt, rho, ktot, c->evals.p, c->gbuf.p, rho, nullptr, 0))) return rc;
+    double* d_ev = c->evals.p + ktot;
+    if ((rc = eig_sym_dev(c, c->gbuf.p, rho, d_ev))) return rc;
+    CU(cudaMemcpyAsync(c->h_pinned, d_ev, rho * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    double lmax = 0.0;
+    for (int i = 0; i < rho; ++i) lmax = std::max(lmax, std::fabs(c->h_pinned[i]));
+    const double eps_ = tol_factor * lmax * 2.220446049250313e-16;
+    std::vector<int32_t> ids;
+    for (int i = 0; i < rho; ++i)
+        if (std::fabs(c->h_pinned[i]) >= eps_) ids.push_back(i);
+    const int k2 = (int)ids.size();
+    if (k2 > out.ncols) return fail(c, DRE_ERR_ARG, "compress: output panel too small for the compressed rank");
+    for (int j = 0; j < k2; ++j) lam[j] = c->h_pinned[ids[j]];
+    *newrank = k2;
+    if (k2 > 0) {
+        CU(c->ibuf.ensure((size_t)k2 + 16));
+        int32_t* hi = (int32_t*)(c->h_pinned + rho);
+        for (int j = 0; j < k2; ++j) hi[j] = ids[j];
+        CU(cudaMemcpyAsync(c->ibuf.p + 16, hi, k2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
+        CU(c->gbuf2.ensure((size_t)k2 * rho));
+        launch_gather_rows(c->gbuf2.p, rho, c->gbuf.p, rho, c->ibuf.p + 16, k2, rho, c->st, &c->stats.kernel_launches);
+        CU(cudaGetLastError());
+        if ((rc = tall_gemm(c, 1.0, s.Q, s.ldq, rho, c->gbuf2.p, rho, 1, 0.0, vptr(c, out), vld(c, out), k2, n)))
+            return rc;
+        CU(cudaStreamSynchronize(c->st));
+    }
+    return check_errflag(c);
+}
+
+int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double drop_rel, double drop_abs, dre_view Q,
+                 double* Rt, int64_t ldr, int32_t* rho_out) {
+    if (!c || !views || !rho_out) return fail(c, DRE_ERR_ARG, "null argument");
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    int rc;
+    int ktot = 0;
+    for (int t = 0; t < nviews; ++t) {
+        if ((rc = check_view(c, views[t], "views[i]", true))) return rc;
+        ktot += views[t].ncols;
+    }
+    if ((rc = check_view(c, Q, "Q", true))) return rc;
+    *rho_out = 0;
+    if (ktot == 0) return DRE_OK;
+    if (!Rt || ldr < ktot) return fail(c, DRE_ERR_ARG, "rrqr: bad Rt");
+    RRState s;
+    if ((rc = rr_setup(c, s, ktot, drop_rel, drop_abs))) return rc;
+    int row0 = 0;
+    for (int t = 0; t < nviews; ++t) {
+        const int k = views[t].ncols;
+        if (k == 0) continue;
+        if ((rc = rr_process_block(c, s, vptr(c, views[t]), vld(c, views[t]), k, nullptr, row0))) return rc;
+        row0 += k;
+    }
+    const int rho = s.rho;
+    if (rho > Q.ncols) return fail(c, DRE_ERR_ARG, "rrqr: Q panel too small");
+    *rho_out = rho;
+    if (rho == 0) return DRE_OK;
+    launch_copy_scale(vptr(c, Q), vld(c, Q), s.Q, s.ldq, c->sym.n, rho, nullptr, c->st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    if ((rc = ensure_pinned(c, (size_t)ktot * s.ldrt))) return rc;
+    CU(cudaMemcpyAsync(c->h_pinned, s.RT, (size_t)ktot * s.ldrt * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < ktot; ++i)
+        for (int j = 0; j < rho; ++j) Rt[i + (int64_t)j * ldr] = c->h_pinned[(int64_t)i * s.ldrt + j];
+    return check_errflag(c);
+}
+
+int32_t dre_stats_reset(dre_context* c, int32_t enable_event_timing) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    c->stats = dre_stats{};
+    c->timing = enable_event_timing != 0;
+    return DRE_OK;
+}
+
+int32_t dre_stats_get(dre_context* c, dre_stats* out) {
+    if (!c || !out) return fail(nullptr, DRE_ERR_ARG, "null argument");
+    *out = c->stats;
+    return DRE_OK;
+}
+
+}  // extern "C"

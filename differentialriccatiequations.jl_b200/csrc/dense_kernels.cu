@@ -1,0 +1,531 @@
+// Dense tall-skinny toolbox for the low-rank algebra of the ADI hot path:
+//   Gram products X'Y on the FP64 tensor cores (DMMA m8n8k4), deterministic split reduction,
+//   tall GEMM Y = beta Y + alpha X W (DMMA), rank-revealing pivoted-Cholesky panel selection,
+//   diagonal-core Frobenius norm, layout helpers.
+// Replaces LAPACK geqp3 / GEMM inside  norm(::LDLt) (src/LDLt.jl:77-89), compress! (:204-225),
+// orthf (:237-245), orth (src/Stuff.jl:13-18), restrict (src/Stuff.jl:9) of the reference.
+// Panels are row-major (row = state index in solver ordering, columns contiguous).
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace dre {
+
+// ------------------------------------------------------------------------------------------
+// Gram:  partial[s] (a x b) = sum_{rows in split s}  w[row] * X[row][:]^T Y[row][:]
+// CTA = 256 threads = 8 warps, output tile 64 x 64, k-chunks of 16 rows.
+// warp w owns output rows [8w, 8w+8) x 64 columns = 8 DMMA accumulators.
+// ------------------------------------------------------------------------------------------
+constexpr int GT = 64;    // tile edge
+constexpr int GK = 16;    // rows per chunk
+constexpr int GLD = 72;   // smem leading dimension (72 mod 16 == 8 -> 2 wavefronts per fragment load, the minimum)
+
+__global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, int64_t ldx, int a,
+                                              const double* __restrict__ Y, int64_t ldy, int b, int64_t n,
+                                              const double* __restrict__ roww, double* __restrict__ partial,
+                                              int tiles_b, int64_t rows_per_split) {
+    __shared__ double Xs[2][GK][GLD];
+    __shared__ double Ys[2][GK][GLD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ta = blockIdx.x / tiles_b, tb = blockIdx.x % tiles_b;
+    const int a0 = ta * GT, b0 = tb * GT;
+    const int64_t row_begin = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t row_end = min(n, row_begin + rows_per_split);
+
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+
+    const int lc = tid & 63;  // column inside the tile handled by this thread when loading
+    const int lr = tid >> 6;  // 0..3
+    double xr[4], yr[4];
+    auto gload = [&](int64_t row0) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            int64_t row = row0 + lr + 4 * it;
+            double xv = 0.0, yv = 0.0;
+            if (row < row_end) {
+                if (a0 + lc < a) {
+                    xv = X[row * ldx + a0 + lc];
+                    if (roww) xv *= roww[row];
+                }
+                if (b0 + lc < b) yv = Y[row * ldy + b0 + lc];
+            }
+            xr[it] = xv;
+            yr[it] = yv;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            Xs[buf][lr + 4 * it][lc] = xr[it];
+            Ys[buf][lr + 4 * it][lc] = yr[it];
+        }
+    };
+
+    int buf = 0;
+    if (row_begin < row_end) {
+        gload(row_begin);
+        sstore(0);
+    }
+    __syncthreads();
+    for (int64_t row0 = row_begin; row0 < row_end; row0 += GK) {
+        const bool more = row0 + GK < row_end;
+        if (more) gload(row0 + GK);
+#pragma unroll
+        for (int kk = 0; kk < GK; kk += 4) {
+            const double af = Xs[buf][kk + (lane & 3)][8 * warp + (lane >> 2)];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const double bf = Ys[buf][kk + (lane & 3)][8 * nb + (lane >> 2)];
+                dmma884(acc[nb][0], acc[nb][1], af, bf);
+            }
+        }
+        if (more) sstore(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+    double* P = partial + (int64_t)blockIdx.y * a * b;
+    const int i = a0 + 8 * warp + (lane >> 2);
+    if (i < a) {
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const int j = b0 + 8 * nb + 2 * (lane & 3);
+            if (j < b) P[(int64_t)i * b + j] = acc[nb][0];
+            if (j + 1 < b) P[(int64_t)i * b + j + 1] = acc[nb][1];
+        }
+    }
+}
+
+__global__ void k_reduce_partials(const double* __restrict__ partial, int nsplit, int a, int b, double* out1,
+                                  int64_t ld1, double* out2, int64_t ld2) {
+    const int64_t total = (int64_t)a * b;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nsplit; ++k) s += partial[(int64_t)k * total + idx];  // fixed order: deterministic
+        const int i = (int)(idx / b), j = (int)(idx % b);
+        if (out1) out1[(int64_t)i * ld1 + j] = s;
+        if (out2) out2[(int64_t)i * ld2 + j] += s;
+    }
+}
+
+GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
+    GramPlan p;
+    int tiles = ((a + GT - 1) / GT) * ((b + GT - 1) / GT);
+    if (tiles < 1) tiles = 1;
+    int64_t chunks = (n + GK - 1) / GK;
+    int want = std::max(1, (4 * sm_count + tiles - 1) / tiles);   // ~4 CTAs per SM
+    int64_t maxsplit = std::max<int64_t>(1, chunks / 8);          // at least 8 chunks (128 rows) per split
+    int nsplit = (int)std::min<int64_t>(want, maxsplit);
+    nsplit = std::min(nsplit, 1024);
+    int64_t cps = (chunks + nsplit - 1) / nsplit;
+    p.rows_per_split = cps * GK;
+    p.nsplit = (int)((n + p.rows_per_split - 1) / p.rows_per_split);
+    if (p.nsplit < 1) p.nsplit = 1;
+    p.partial_elems = (size_t)p.nsplit * (size_t)std::max(a, 1) * (size_t)std::max(b, 1);
+    return p;
+}
+
+void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t ldy, int b, int64_t n,
+                 const double* roww, double* partial, const GramPlan& plan, double* out1, int64_t ld1,
+                 double* out2, int64_t ld2, cudaStream_t st, int64_t* launches) {
+    if (a <= 0 || b <= 0) return;
+    const int tiles_a = (a + GT - 1) / GT, tiles_b = (b + GT - 1) / GT;
+    dim3 grid(tiles_a * tiles_b, plan.nsplit);
+    k_gram<<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, roww, partial, tiles_b, plan.rows_per_split);
+    const int64_t total = (int64_t)a * b;
+    int rb = (int)std::min<int64_t>((total + 255) / 256, 1024);
+    k_reduce_partials<<<rb, 256, 0, st>>>(partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
+    if (launches) *launches += 2;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tall GEMM:  Y[n x b] = beta*Y + alpha * X[n x a] * W        (DMMA)
+// CTA = 256 threads, output tile 64 rows x 64 cols, k-chunks of 32.
+// ------------------------------------------------------------------------------------------
+constexpr int TK = 32;
+constexpr int TXLD = 36;  // 36*i mod 16 = 4i -> minimal 2-wavefront fragment loads
+constexpr int TWLD = 72;
+
+__global__ void __launch_bounds__(256) k_tall_gemm(double alpha, const double* __restrict__ X, int64_t ldx, int a,
+                                                   const double* __restrict__ W, int64_t ldw, int w_trans,
+                                                   double beta, double* __restrict__ Y, int64_t ldy, int b,
+                                                   int64_t n) {
+    __shared__ double Xs[64][TXLD];
+    __shared__ double Ws[TK][TWLD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * 64;
+    const int b0 = blockIdx.y * 64;
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+
+    for (int k0 = 0; k0 < a; k0 += TK) {
+        // X tile: 64 rows x 32 k
+        {
+            const int kc = tid & 31, r = tid >> 5;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = r + 8 * it;
+                const int64_t row = row0 + rr;
+                double v = 0.0;
+                if (row < n && k0 + kc < a) v = X[row * ldx + k0 + kc];
+                Xs[rr][kc] = v;
+            }
+        }
+        // W tile: 32 k x 64 j
+        {
+            if (!w_trans) {
+                const int j = tid & 63, k = tid >> 6;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int kk = k + 4 * it;
+                    double v = 0.0;
+                    if (k0 + kk < a && b0 + j < b) v = W[(int64_t)(k0 + kk) * ldw + b0 + j];
+                    Ws[kk][j] = v;
+                }
+            } else {
+                const int kk = tid & 31, j = tid >> 5;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int jj = j + 8 * it;
+                    double v = 0.0;
+                    if (k0 + kk < a && b0 + jj < b) v = W[(int64_t)(b0 + jj) * ldw + k0 + kk];
+                    Ws[kk][jj] = v;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 4) {
+            const double af = Xs[8 * warp + (lane >> 2)][kk + (lane & 3)];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const double bf = Ws[kk + (lane & 3)][8 * nb + (lane >> 2)];
+                dmma884(acc[nb][0], acc[nb][1], af, bf);
+            }
+        }
+        __syncthreads();
+    }
+    const int64_t row = row0 + 8 * warp + (lane >> 2);
+    if (row < n) {
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const int j = b0 + 8 * nb + 2 * (lane & 3);
+            double* y = Y + row * ldy + j;
+            if (j < b) y[0] = (beta == 0.0 ? 0.0 : beta * y[0]) + alpha * acc[nb][0];
+            if (j + 1 < b) y[1] = (beta == 0.0 ? 0.0 : beta * y[1]) + alpha * acc[nb][1];
+        }
+    }
+}
+
+void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const double* W, int64_t ldw,
+                      int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n, cudaStream_t st,
+                      int64_t* launches) {
+    if (b <= 0 || n <= 0) return;
+    dim3 grid((unsigned)((n + 63) / 64), (unsigned)((b + 63) / 64));
+    k_tall_gemm<<<grid, 256, 0, st>>>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise helpers
+// ------------------------------------------------------------------------------------------
+__global__ void k_copy_scale(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
+                             int64_t n, int cols, const double* __restrict__ colscale) {
+    const int64_t total = n * cols;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / cols;
+        const int c = (int)(idx % cols);
+        double v = src[row * lds + c];
+        if (colscale) v *= colscale[c];
+        dst[row * ldd + c] = v;
+    }
+}
+
+void launch_copy_scale(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, int cols,
+                       const double* colscale, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || cols <= 0) return;
+    int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
+    k_copy_scale<<<blocks, 256, 0, st>>>(dst, ldd, src, lds, n, cols, colscale);
+    if (launches) *launches += 1;
+}
+
+__global__ void k_axpby(double alpha, const double* __restrict__ X, int64_t ldx, double beta, double* __restrict__ Y,
+                        int64_t ldy, int64_t n, int cols) {
+    const int64_t total = n * cols;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / cols;
+        const int c = (int)(idx % cols);
+        double v = (beta == 0.0) ? 0.0 : beta * Y[row * ldy + c];
+        if (alpha != 0.0) v += alpha * X[row * ldx + c];
+        Y[row * ldy + c] = v;
+    }
+}
+
+void launch_axpby(double alpha, const double* X, int64_t ldx, double beta, double* Y, int64_t ldy, int64_t n,
+                  int cols, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || cols <= 0) return;
+    int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
+    k_axpby<<<blocks, 256, 0, st>>>(alpha, X, ldx, beta, Y, ldy, n, cols);
+    if (launches) *launches += 1;
+}
+
+// column-major staging (original row order) <-> row-major panel (solver row order), 32x32 smem transpose
+__global__ void k_cm2panel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
+                           int64_t n, int cols, const int32_t* __restrict__ iperm) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+        const int64_t r = r0 + threadIdx.x;
+        if (r < n && c0 + cc < cols) tile[cc][threadIdx.x] = src[r + (int64_t)(c0 + cc) * lds];
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t r = r0 + rr;
+        const int c = c0 + threadIdx.x;
+        if (r < n && c < cols) {
+            const int64_t pr = iperm ? iperm[r] : r;
+            dst[pr * ldd + c] = tile[threadIdx.x][rr];
+        }
+    }
+}
+
+__global__ void k_panel2cm(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
+                           int64_t n, int cols, const int32_t* __restrict__ iperm) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t r = r0 + rr;
+        const int c = c0 + threadIdx.x;
+        if (r < n && c < cols) {
+            const int64_t pr = iperm ? iperm[r] : r;
+            tile[rr][threadIdx.x] = src[pr * lds + c];
+        }
+    }
+    __syncthreads();
+    for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+        const int64_t r = r0 + threadIdx.x;
+        if (r < n && c0 + cc < cols) dst[r + (int64_t)(c0 + cc) * ldd] = tile[threadIdx.x][cc];
+    }
+}
+
+void launch_colmajor_to_panel(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, int cols,
+                              const int32_t* iperm, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || cols <= 0) return;
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
+    k_cm2panel<<<grid, block, 0, st>>>(dst, ldd, src, lds, n, cols, iperm);
+    if (launches) *launches += 1;
+}
+
+void launch_panel_to_colmajor(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, int cols,
+                              const int32_t* iperm, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || cols <= 0) return;
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
+    k_panel2cm<<<grid, block, 0, st>>>(dst, ldd, src, lds, n, cols, iperm);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// pivoted Cholesky panel selection (single CTA, pb <= 64)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pivchol(const double* __restrict__ G, int64_t ldg, int pb, double drop2,
+                                                 double rel2, double* __restrict__ Wsel, int32_t* __restrict__ info,
+                                                 double* __restrict__ dinfo) {
+    extern __shared__ double pc_smem[];
+    double (*A)[65] = reinterpret_cast<double (*)[65]>(pc_smem);            // Gram matrix
+    double (*C)[65] = reinterpret_cast<double (*)[65]>(pc_smem + 64 * 65);  // Cholesky factor columns
+    double (*Z)[65] = A;  // inverse of the permuted triangular factor (reuses A after the factorization)
+    __shared__ double d[64];
+    __shared__ int piv[64];
+    __shared__ int s_p;
+    __shared__ double s_thr, s_dfirst;
+    __shared__ int s_nsel;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        const int i = idx >> 6, j = idx & 63;
+        A[i][j] = (i < pb && j < pb) ? G[(int64_t)i * ldg + j] : 0.0;
+        C[i][j] = 0.0;
+    }
+    __syncthreads();
+    if (tid < 64) d[tid] = (tid < pb) ? A[tid][tid] : -1.0;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int i = 0; i < pb; ++i) m = fmax(m, d[i]);
+        s_dfirst = m;
+        s_thr = fmax(drop2, rel2 * m);
+        s_nsel = 0;
+    }
+    __syncthreads();
+    for (int j = 0; j < pb; ++j) {
+        if (tid == 0) {
+            int p = -1;
+            double m = -1.0;
+            for (int i = 0; i < pb; ++i)
+                if (d[i] > m) { m = d[i]; p = i; }
+            s_p = (p >= 0 && m >= s_thr && m > 0.0) ? p : -1;
+        }
+        __syncthreads();
+        const int p = s_p;
+        if (p < 0) break;
+        const double cjj = sqrt(d[p]);
+        if (tid < pb) {
+            const int i = tid;
+            if (i == p) {
+                C[i][j] = cjj;
+            } else if (d[i] >= 0.0) {  // not yet selected
+                double v = A[i][p];
+                for (int t = 0; t < j; ++t) v -= C[i][t] * C[p][t];
+                v /= cjj;
+                C[i][j] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < pb) {
+            const int i = tid;
+            if (i == p) d[i] = -1.0;
+            else if (d[i] >= 0.0) d[i] = fmax(d[i] - C[i][j] * C[i][j], 0.0);
+        }
+        if (tid == 0) { piv[j] = p; s_nsel = j + 1; }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int nsel = s_nsel;
+    for (int idx = tid; idx < 64 * 64; idx += 256) Z[idx >> 6][idx & 63] = 0.0;
+    __syncthreads();
+    // Z = C11^-1 (lower), C11[a][b] = C[piv[a]][b]
+    if (tid < nsel) {
+        const int bcol = tid;
+        Z[bcol][bcol] = 1.0 / C[piv[bcol]][bcol];
+        for (int a2 = bcol + 1; a2 < nsel; ++a2) {
+            double v = 0.0;
+            for (int t = bcol; t < a2; ++t) v += C[piv[a2]][t] * Z[t][bcol];
+            Z[a2][bcol] = -v / C[piv[a2]][a2];
+        }
+    }
+    __syncthreads();
+    // Wsel[piv[a]][b] = Z[b][a]  (a <= b), zero elsewhere
+    for (int idx = tid; idx < 64 * 64; idx += 256) Wsel[idx] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < nsel * nsel; idx += 256) {
+        const int a2 = idx / nsel, b2 = idx % nsel;
+        if (a2 <= b2) Wsel[piv[a2] * 64 + b2] = Z[b2][a2];
+    }
+    if (tid == 0) {
+        info[0] = nsel;
+        double m = 0.0;
+        for (int i = 0; i < pb; ++i) m = fmax(m, d[i]);
+        dinfo[0] = s_dfirst;
+        dinfo[1] = m;
+    }
+}
+
+void launch_pivchol(const double* G, int64_t ldg, int pb, double drop2, double rel2, double* Wsel, int32_t* info,
+                    double* dinfo, cudaStream_t st, int64_t* launches) {
+    static bool attr_set = false;
+    const int smem = 2 * 64 * 65 * (int)sizeof(double);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_pivchol, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    k_pivchol<<<1, 256, smem, st>>>(G, ldg, pb, drop2, rel2, Wsel, info, dinfo);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// ||R diag(t) R'||_F^2 = sum_ij G_ij^2 t_i t_j,  G = R'R
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_norm_diag(const double* __restrict__ G, int64_t ldg, int r,
+                                                   const double* __restrict__ t, double* __restrict__ out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int idx = threadIdx.x; idx < r * r; idx += 256) {
+        const int i = idx / r, j = idx % r;
+        const double g = G[(int64_t)i * ldg + j];
+        s += g * g * t[i] * t[j];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+void launch_norm_diag(const double* G, int64_t ldg, int r, const double* t, double* out, cudaStream_t st,
+                      int64_t* launches) {
+    k_norm_diag<<<1, 256, 0, st>>>(G, ldg, r, t, out);
+    if (launches) *launches += 1;
+}
+
+__global__ void k_gather_rows(double* __restrict__ Wt, int64_t ldw, const double* __restrict__ V, int64_t ldv,
+                              const int32_t* __restrict__ ids, int nsel, int len) {
+    const int64_t total = (int64_t)nsel * len;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / len), k = (int)(idx % len);
+        Wt[(int64_t)j * ldw + k] = V[(int64_t)ids[j] * ldv + k];
+    }
+}
+
+void launch_gather_rows(double* Wt, int64_t ldw, const double* V, int64_t ldv, const int32_t* ids, int nsel,
+                        int len, cudaStream_t st, int64_t* launches) {
+    if (nsel <= 0 || len <= 0) return;
+    int blocks = (int)std::min<int64_t>(((int64_t)nsel * len + 255) / 256, 1024);
+    k_gather_rows<<<blocks, 256, 0, st>>>(Wt, ldw, V, ldv, ids, nsel, len);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR SpMM with fused axpby:  Y[row][:] = beta*Y[row][:] + alpha * sum_j val_j X[col_j][:]
+// One warp per row, lanes over the (contiguous) panel columns: every X-row read and every
+// Y-row write is a fully coalesced 256-byte segment; E / A values and indices are warp-broadcast.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_spmm(const int32_t* __restrict__ ptr, const int32_t* __restrict__ col,
+                                              const double* __restrict__ val, int64_t n, double alpha,
+                                              const double* __restrict__ X, int64_t ldx, double beta,
+                                              double* __restrict__ Y, int64_t ldy, int cols) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp; row < n; row += nwarps) {
+        const int p0 = ptr[row], p1 = ptr[row + 1];
+        for (int c0 = 0; c0 < cols; c0 += 128) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int p = p0; p < p1; ++p) {
+                const double v = val[p];
+                const double* xr = X + (int64_t)col[p] * ldx + c0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = lane + 32 * u;
+                    if (c0 + c < cols) acc[u] = fma(v, xr[c], acc[u]);
+                }
+            }
+            double* yr = Y + row * ldy + c0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = lane + 32 * u;
+                if (c0 + c < cols) yr[c] = (beta == 0.0 ? 0.0 : beta * yr[c]) + alpha * acc[u];
+            }
+        }
+    }
+}
+
+void launch_spmm(const int32_t* ptr, const int32_t* col, const double* val, int64_t n, double alpha,
+                 const double* X, int64_t ldx, double beta, double* Y, int64_t ldy, int cols, cudaStream_t st,
+                 int64_t* launches) {
+    if (n <= 0 || cols <= 0) return;
+    int64_t blocks = (n + 7) / 8;  // 8 warps per CTA, one row per warp
+    blocks = std::min<int64_t>(blocks, 148 * 32);
+    k_spmm<<<(unsigned)blocks, 256, 0, st>>>(ptr, col, val, n, alpha, X, ldx, beta, Y, ldy, cols);
+    if (launches) *launches += 1;
+}
+
+}  // namespace dre

@@ -1,0 +1,674 @@
+// Per-shift numeric supernodal LDL^T (no pivoting; real symmetric definite or complex symmetric)
+// and level-scheduled multifrontal block solves with many right-hand sides.
+//
+// Replaces, for the hot path, what the reference gets from SuiteSparse through
+//   factorize(A' + mu E')   src/blocklinear/backslash.jl:13, src/blocklinear/types.jl:41-42
+//   F \ R                    src/blocklinear/backslash.jl:19
+//   SMW correction           src/blocklinear/sherman-morrison-woodbury.jl:10-45
+// T = double for real shifts, T = cplx (complex SYMMETRIC, no conjugation) for complex shifts --
+// the complex pair path the reference lists as broken on GPU (README.md:174-176).
+//
+// Storage: panel_J = f_J x s_J column-major (ld f_J) with L21 below the supernode's own rows;
+// the factored diagonal blocks (unit-lower L_d and the pivots d, 32 x 32 each) live in a side
+// array `dblk` so that no CTA overwrites panel entries other CTAs of the same step still read.
+// Update matrices / update vectors live in two ping-pong buffers indexed by level parity: the
+// children of a supernode are all exactly one level below it (levels are tree depths).
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace dre {
+
+constexpr int NB = 32;     // block-column width of the blocked LDL^T
+constexpr int SLAB = 96;   // slab rows per CTA (plus the 32 diagonal-block rows)
+
+__device__ __forceinline__ int sn_s(const DevSymbolic& S, int J) { return S.sn_first[J + 1] - S.sn_first[J]; }
+__device__ __forceinline__ int sn_u(const DevSymbolic& S, int J) { return (int)(S.sn_rowptr[J + 1] - S.sn_rowptr[J]); }
+
+// ------------------------------------------------------------------------------------------
+// assembly: L[dest] = a*A + (e+mu)*E on the lower-triangular union pattern
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void k_assemble(int64_t nasm, const int64_t* __restrict__ dest, const double* __restrict__ va,
+                           const double* __restrict__ ve, T* __restrict__ L, double a, T emu) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nasm; i += (int64_t)gridDim.x * blockDim.x) {
+        T v;
+        from_real(a * va[i], v);
+        L[dest[i]] = add(v, mul(ve[i], emu));
+    }
+}
+
+template <class T>
+void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t st, int64_t* launches) {
+    int blocks = (int)std::min<int64_t>((S.nasm + 255) / 256, 148 * 8);
+    if (blocks < 1) blocks = 1;
+    k_assemble<T><<<blocks, 256, 0, st>>>(S.nasm, S.asm_dest, S.asm_a, S.asm_e, L, a, emu);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// extend-add: parent J gathers the update matrices of its children (deterministic: one CTA
+// column-class per parent column, children visited in a fixed order)
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_extend_add(DevSymbolic S, const int32_t* __restrict__ parents, T* L,
+                                                    T* Ucur, const T* __restrict__ Uprev) {
+    const int J = parents[blockIdx.x];
+    const int by = blockIdx.y, gy = gridDim.y;
+    const int sJ = sn_s(S, J), uJ = sn_u(S, J), fJ = sJ + uJ;
+    T* P = L + S.panel_off[J];
+    T* UJ = Ucur + S.upd_off[J];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int ci = S.child_ptr[J]; ci < S.child_ptr[J + 1]; ++ci) {
+        const int c = S.child_idx[ci];
+        const int uc = sn_u(S, c);
+        const int32_t* rel = S.relmap + S.sn_rowptr[c];
+        const T* Uc = Uprev + S.upd_off[c];
+        for (int j = warp; j < uc; j += nwarps) {
+            const int pc = rel[j];
+            if (pc % gy != by) continue;
+            for (int i = j + lane; i < uc; i += 32) {
+                const int pr = rel[i];
+                const T val = Uc[(int64_t)i + (int64_t)j * uc];
+                if (pc < sJ) {
+                    T* t = P + ((int64_t)pr + (int64_t)pc * fJ);
+                    *t = add(*t, val);
+                } else {
+                    T* t = UJ + ((int64_t)(pr - sJ) + (int64_t)(pc - sJ) * uJ);
+                    *t = add(*t, val);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class T>
+void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* Ucur,
+                       const T* Uprev, cudaStream_t st, int64_t* launches) {
+    if (nparents <= 0) return;
+    dim3 grid(nparents, gy);
+    k_extend_add<T><<<grid, 256, 0, st>>>(S, parents, L, Ucur, Uprev);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// one block-column step of the blocked left-looking LDL^T of every front in a level.
+// CTA (J, slab): rows = 32 diagonal-block rows (recomputed by every CTA of the front) + 96 slab
+// rows; C = P[rows, k0:k0+nb] - sum_{k<k0} L[rows,k] d_k L[k0+b,k];  factor the diagonal block in
+// shared memory, solve the slab against it.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_front_step(DevSymbolic S, const int2* __restrict__ items, int step,
+                                                    T* L, T* dblk, int32_t* errflag) {
+    constexpr int KC = 16;
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    T* smp = reinterpret_cast<T*>(dre_smem_raw);
+    T (*As)[128] = reinterpret_cast<T (*)[128]>(smp);                 smp += KC * 128;
+    T (*Bs)[NB] = reinterpret_cast<T (*)[NB]>(smp);                   smp += KC * NB;
+    T (*Ds)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*Ss)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += SLAB * (NB + 1);
+    T* tmp = smp;
+    const int2 item = items[blockIdx.x];
+    const int J = item.x, slab = item.y;
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    const int k0 = step * NB;
+    const int nb = min(NB, s - k0);
+    T* P = L + S.panel_off[J];
+    T* Dk = dblk + S.dblk_off[J];
+    const int tid = threadIdx.x;
+    const int tr = tid & 31, tc = tid >> 5;
+    const int slab_row0 = k0 + nb + slab * SLAB;
+
+    // global row of tile row m (or -1)
+    auto grow = [&](int m) -> int {
+        if (m < NB) return (m < nb) ? k0 + m : -1;
+        const int r = slab_row0 + (m - NB);
+        return (r < f) ? r : -1;
+    };
+
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = zero<T>();
+
+    for (int kk = 0; kk < k0; kk += KC) {
+        // A tile: 128 rows x 16 k
+        {
+            const int m = tid & 127;
+            const int g = grow(m);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int k = (tid >> 7) + 2 * it;
+                As[k][m] = (g >= 0) ? P[(int64_t)g + (int64_t)(kk + k) * f] : zero<T>();
+            }
+        }
+        __syncthreads();
+        // B tile = diagonal-block rows scaled by the pivots d_k of the (finished) previous columns
+        for (int idx = tid; idx < KC * NB; idx += 256) {
+            const int k = idx >> 5, b = idx & 31;
+            const int kg = kk + k;
+            const T d = Dk[(int64_t)(kg >> 5) * 1024 + (kg & 31) * 33];
+            Bs[k][b] = mul(As[k][b], d);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            T av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[k][tr + 32 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tc * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fma_acc(acc[i][j], av[i], bv[j]);
+        }
+        __syncthreads();
+    }
+    // C = P - acc  -> shared
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = tr + 32 * i;
+        const int g = grow(m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = tc * 4 + j;
+            T v = zero<T>();
+            if (g >= 0 && c < nb) v = sub(P[(int64_t)g + (int64_t)(k0 + c) * f], acc[i][j]);
+            if (m < NB) Ds[m][c] = v;
+            else Ss[m - NB][c] = v;
+        }
+    }
+    __syncthreads();
+    // unblocked LDL^T of the diagonal block (lower part of Ds)
+    for (int j = 0; j < nb; ++j) {
+        const T d = Ds[j][j];
+        if (tid == 0 && is_bad(d)) atomicExch(errflag, 1);
+        const T rd = recip(d);
+        if (tid > j && tid < nb) {
+            const T w = Ds[tid][j];
+            tmp[tid] = w;
+            Ds[tid][j] = mul(w, rd);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int i = idx >> 5, k = idx & 31;
+            if (k > j && i >= k && i < nb) Ds[i][k] = sub(Ds[i][k], mul(Ds[i][j], tmp[k]));
+        }
+        __syncthreads();
+    }
+    // slab rows: y_c = S[c] - sum_{t<c} y_t Ld[c][t];  L[c] = y_c / d_c
+    if (tid < SLAB) {
+        const int m = tid;
+        if (slab_row0 + m < f) {
+            for (int c = 0; c < nb; ++c) {
+                T v = Ss[m][c];
+                for (int t = 0; t < c; ++t) v = sub(v, mul(Ss[m][t], Ds[c][t]));
+                Ss[m][c] = v;
+            }
+            for (int c = 0; c < nb; ++c) Ss[m][c] = mul(Ss[m][c], recip(Ds[c][c]));
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < SLAB * NB; idx += 256) {
+        const int m = idx % SLAB, c = idx / SLAB;
+        const int r = slab_row0 + m;
+        if (r < f && c < nb) P[(int64_t)r + (int64_t)(k0 + c) * f] = Ss[m][c];
+    }
+    if (slab == 0) {
+        T* Db = Dk + (int64_t)step * 1024;
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int i = idx & 31, j = idx >> 5;
+            T v = zero<T>();
+            if (i < nb && j < nb && i >= j) v = Ds[i][j];
+            else if (i == j) v = one<T>();  // padding pivots of a partial block (never used)
+            Db[i + j * 32] = v;
+        }
+    }
+}
+
+template <class T>
+void launch_front_step(const DevSymbolic& S, const int2* items, int nitems, int step, T* L, T* dblk,
+                       int32_t* errflag, cudaStream_t st, int64_t* launches) {
+    if (nitems <= 0) return;
+    const int smem = (int)sizeof(T) * (16 * 128 + 16 * NB + NB * (NB + 1) + SLAB * (NB + 1) + NB);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_front_step<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    k_front_step<T><<<nitems, 256, smem, st>>>(S, items, step, L, dblk, errflag);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Schur complement U_J -= L21 D L21^T (lower triangle), 64x64 tiles, K = s_J
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_schur(DevSymbolic S, const int4* __restrict__ items, const T* __restrict__ L,
+                                               const T* __restrict__ dblk, T* Ucur) {
+    constexpr int KC = 16;
+    __shared__ T As[KC][64];
+    __shared__ T Bs[KC][64];
+    const int4 item = items[blockIdx.x];
+    const int J = item.x, i0 = item.y * 64, j0 = item.z * 64;
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    const T* P = L + S.panel_off[J];
+    const T* Dk = dblk + S.dblk_off[J];
+    T* U = Ucur + S.upd_off[J];
+    const int tid = threadIdx.x, tr = tid & 15, tc = tid >> 4;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = zero<T>();
+    for (int kk = 0; kk < s; kk += KC) {
+        const int m = tid & 63;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int k = (tid >> 6) + 4 * it;
+            const int kg = kk + k;
+            T av = zero<T>(), bv = zero<T>();
+            if (kg < s) {
+                if (i0 + m < u) av = P[(int64_t)(s + i0 + m) + (int64_t)kg * f];
+                if (j0 + m < u) {
+                    const T d = Dk[(int64_t)(kg >> 5) * 1024 + (kg & 31) * 33];
+                    bv = mul(P[(int64_t)(s + j0 + m) + (int64_t)kg * f], d);
+                }
+            }
+            As[k][m] = av;
+            Bs[k][m] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            T av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[k][tr + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tc + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fma_acc(acc[i][j], av[i], bv[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = i0 + tr + 16 * i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = j0 + tc + 16 * j;
+            if (gi < u && gj < u && gi >= gj) {
+                T* t = U + ((int64_t)gi + (int64_t)gj * u);
+                *t = sub(*t, acc[i][j]);
+            }
+        }
+    }
+}
+
+template <class T>
+void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dblk, T* Ucur,
+                  cudaStream_t st, int64_t* launches) {
+    if (nitems <= 0) return;
+    k_schur<T><<<nitems, 256, 0, st>>>(S, items, L, dblk, Ucur);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward sweep of one level:  y_J = L11^-1 (b_J + children),  t_J = children - L21 y_J
+// CTA = (supernode, 32 RHS columns).  W and the update-vector buffers are row-major with the same
+// leading dimension and column indexing.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_fwd_level(DevSymbolic S, const int32_t* __restrict__ sns,
+                                                   const T* __restrict__ L, const T* __restrict__ dblk, T* W,
+                                                   int64_t ldw, int nrhs, T* tcur, const T* __restrict__ tprev) {
+    __shared__ T xb[NB][NB + 1];
+    __shared__ T Ld[NB][NB + 1];
+    const int J = sns[blockIdx.x];
+    const int c0 = blockIdx.y * 32;
+    const int ncw = min(32, nrhs - c0);
+    const int first = S.sn_first[J];
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    const T* P = L + S.panel_off[J];
+    const T* Dk = dblk + S.dblk_off[J];
+    T* tJ = tcur + S.rhs_off[J] * ldw;
+    const int tid = threadIdx.x;
+
+    for (int idx = tid; idx < u * 32; idx += 256) {
+        const int i = idx >> 5, cc = idx & 31;
+        if (cc < ncw) tJ[(int64_t)i * ldw + c0 + cc] = zero<T>();
+    }
+    __syncthreads();
+    for (int ci = S.child_ptr[J]; ci < S.child_ptr[J + 1]; ++ci) {
+        const int c = S.child_idx[ci];
+        const int uc = sn_u(S, c);
+        const int32_t* rel = S.relmap + S.sn_rowptr[c];
+        const T* tch = tprev + S.rhs_off[c] * ldw;
+        for (int idx = tid; idx < uc * 32; idx += 256) {
+            const int i = idx >> 5, cc = idx & 31;
+            if (cc < ncw) {
+                const int pr = rel[i];
+                const T val = tch[(int64_t)i * ldw + c0 + cc];
+                T* t = (pr < s) ? (W + (int64_t)(first + pr) * ldw + c0 + cc)
+                                : (tJ + (int64_t)(pr - s) * ldw + c0 + cc);
+                *t = add(*t, val);
+            }
+        }
+        __syncthreads();
+    }
+    for (int jb = 0; jb < s; jb += NB) {
+        const int nb = min(NB, s - jb);
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int i = idx >> 5, cc = idx & 31;
+            xb[i][cc] = (i < nb && cc < ncw) ? W[(int64_t)(first + jb + i) * ldw + c0 + cc] : zero<T>();
+            const int li = idx & 31, lk = idx >> 5;
+            Ld[li][lk] = Dk[(int64_t)(jb >> 5) * 1024 + li + lk * 32];
+        }
+        __syncthreads();
+        if (tid < ncw) {
+            for (int i = 1; i < nb; ++i) {
+                T v = xb[i][tid];
+                for (int k = 0; k < i; ++k) v = sub(v, mul(Ld[i][k], xb[k][tid]));
+                xb[i][tid] = v;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int i = idx >> 5, cc = idx & 31;
+            if (i < nb && cc < ncw) W[(int64_t)(first + jb + i) * ldw + c0 + cc] = xb[i][cc];
+        }
+        const int rt = tid & 63, ct = tid >> 6;
+        for (int row = jb + nb + rt; row < f; row += 64) {
+            T acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = zero<T>();
+            for (int k = 0; k < nb; ++k) {
+                const T l = P[(int64_t)row + (int64_t)(jb + k) * f];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) fma_acc(acc[j], l, xb[k][ct * 8 + j]);
+            }
+            T* tgt = (row < s) ? (W + (int64_t)(first + row) * ldw) : (tJ + (int64_t)(row - s) * ldw);
+            tgt += c0 + ct * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (ct * 8 + j < ncw) tgt[j] = sub(tgt[j], acc[j]);
+        }
+        __syncthreads();
+    }
+}
+
+template <class T>
+void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
+                      int64_t ldw, int nrhs, T* tcur, const T* tprev, cudaStream_t st, int64_t* launches) {
+    if (nsns <= 0 || nrhs <= 0) return;
+    dim3 grid(nsns, (nrhs + 31) / 32);
+    k_fwd_level<T><<<grid, 256, 0, st>>>(S, sns, L, dblk, W, ldw, nrhs, tcur, tprev);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward sweep of one level:  x_J = L11^-T (D^-1 y_J - L21^T x_struct)
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_bwd_level(DevSymbolic S, const int32_t* __restrict__ sns,
+                                                   const T* __restrict__ L, const T* __restrict__ dblk, T* W,
+                                                   int64_t ldw, int nrhs) {
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    T* smp = reinterpret_cast<T*>(dre_smem_raw);
+    T (*Ls)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*Xs)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*zb)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*Ld)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);
+    const int J = sns[blockIdx.x];
+    const int c0 = blockIdx.y * 32;
+    const int ncw = min(32, nrhs - c0);
+    const int first = S.sn_first[J];
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    const T* P = L + S.panel_off[J];
+    const T* Dk = dblk + S.dblk_off[J];
+    const int32_t* rows = S.sn_rows + S.sn_rowptr[J];
+    const int tid = threadIdx.x;
+    const int kq = tid & 31, cg = tid >> 5;
+
+    for (int jb = ((s - 1) / NB) * NB; jb >= 0; jb -= NB) {
+        const int nb = min(NB, s - jb);
+        T acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = zero<T>();
+        for (int r0 = jb + nb; r0 < f; r0 += NB) {
+            for (int idx = tid; idx < NB * NB; idx += 256) {
+                {
+                    const int r = idx & 31, k = idx >> 5;
+                    Ls[r][k] = (r0 + r < f && k < nb) ? P[(int64_t)(r0 + r) + (int64_t)(jb + k) * f] : zero<T>();
+                }
+                {
+                    const int r = idx >> 5, cc = idx & 31;
+                    T v = zero<T>();
+                    if (r0 + r < f && cc < ncw) {
+                        const int lr = r0 + r;
+                        const int64_t g = (lr < s) ? (int64_t)(first + lr) : (int64_t)rows[lr - s];
+                        v = W[g * ldw + c0 + cc];
+                    }
+                    Xs[r][cc] = v;
+                }
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int r = 0; r < NB; ++r) {
+                const T l = Ls[r][kq];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fma_acc(acc[j], l, Xs[r][cg * 4 + j]);
+            }
+            __syncthreads();
+        }
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int i = idx >> 5, cc = idx & 31;
+            zb[i][cc] = (i < nb && cc < ncw) ? W[(int64_t)(first + jb + i) * ldw + c0 + cc] : zero<T>();
+            const int li = idx & 31, lk = idx >> 5;
+            Ld[li][lk] = Dk[(int64_t)(jb >> 5) * 1024 + li + lk * 32];
+        }
+        __syncthreads();
+        {
+            const T rd = (kq < nb) ? recip(Ld[kq][kq]) : zero<T>();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = cg * 4 + j;
+                zb[kq][c] = sub(mul(zb[kq][c], rd), acc[j]);
+            }
+        }
+        __syncthreads();
+        if (tid < ncw) {
+            for (int i = nb - 2; i >= 0; --i) {
+                T v = zb[i][tid];
+                for (int k = i + 1; k < nb; ++k) v = sub(v, mul(Ld[k][i], zb[k][tid]));
+                zb[i][tid] = v;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int i = idx >> 5, cc = idx & 31;
+            if (i < nb && cc < ncw) W[(int64_t)(first + jb + i) * ldw + c0 + cc] = zb[i][cc];
+        }
+        __syncthreads();
+    }
+}
+
+template <class T>
+void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
+                      int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches) {
+    if (nsns <= 0 || nrhs <= 0) return;
+    dim3 grid(nsns, (nrhs + 31) / 32);
+    const int smem = (int)sizeof(T) * 4 * NB * (NB + 1);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_bwd_level<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    k_bwd_level<T><<<grid, 256, smem, st>>>(S, sns, L, dblk, W, ldw, nrhs);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// RHS staging, SMW core and epilogue
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void k_load_rhs(T* __restrict__ W, int64_t ldw, const double* __restrict__ R, int64_t ldr, int r,
+                           const double* __restrict__ Vt, int64_t ldv, int m, int64_t n) {
+    const int tot = r + m;
+    const int64_t total = n * tot;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / tot;
+        const int c = (int)(idx % tot);
+        const double v = (c < r) ? R[row * ldr + c] : Vt[row * ldv + (c - r)];
+        T t;
+        from_real(v, t);
+        W[row * ldw + c] = t;
+    }
+}
+
+template <class T>
+void launch_load_rhs(T* W, int64_t ldw, const double* R, int64_t ldr, int r, const double* Vt, int64_t ldv, int m,
+                     int64_t n, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || r + m <= 0) return;
+    int blocks = (int)std::min<int64_t>((n * (r + m) + 255) / 256, 148 * 16);
+    k_load_rhs<T><<<blocks, 256, 0, st>>>(W, ldw, R, ldr, r, Vt, ldv, m, n);
+    if (launches) *launches += 1;
+}
+
+__device__ __forceinline__ double abs2(double a) { return a * a; }
+__device__ __forceinline__ double abs2(cplx a) { return a.x * a.x + a.y * a.y; }
+
+// S = alpha I + BtW[:, r:r+m];  Sol = S^-1 BtW[:, 0:r]   (m <= 32; LU with partial pivoting)
+template <class T>
+__global__ void __launch_bounds__(256) k_smw_core(const T* __restrict__ BtW, int64_t ldb, int m, int r, double alpha,
+                                                  T* __restrict__ Sol, int32_t* errflag) {
+    __shared__ T Sm[32][33];
+    __shared__ int piv[32];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < m * m; idx += 256) {
+        const int i = idx / m, j = idx % m;
+        T v = BtW[(int64_t)i * ldb + r + j];
+        if (i == j) {
+            T a;
+            from_real(alpha, a);
+            v = add(v, a);
+        }
+        Sm[i][j] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 0; k < m; ++k) {
+            int p = k;
+            double best = abs2(Sm[k][k]);
+            for (int i = k + 1; i < m; ++i) {
+                const double a2 = abs2(Sm[i][k]);
+                if (a2 > best) { best = a2; p = i; }
+            }
+            piv[k] = p;
+            if (p != k)
+                for (int j = 0; j < m; ++j) { T t = Sm[k][j]; Sm[k][j] = Sm[p][j]; Sm[p][j] = t; }
+            if (is_bad(Sm[k][k])) atomicExch(errflag, 2);
+            const T rd = recip(Sm[k][k]);
+            for (int i = k + 1; i < m; ++i) {
+                const T l = mul(Sm[i][k], rd);
+                Sm[i][k] = l;
+                for (int j = k + 1; j < m; ++j) Sm[i][j] = sub(Sm[i][j], mul(l, Sm[k][j]));
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < r; c += 256) {
+        T x[32];
+        for (int i = 0; i < m; ++i) x[i] = BtW[(int64_t)i * ldb + c];
+        for (int k = 0; k < m; ++k) {
+            const int p = piv[k];
+            if (p != k) { T t = x[k]; x[k] = x[p]; x[p] = t; }
+        }
+        for (int i = 1; i < m; ++i) {
+            T v = x[i];
+            for (int k = 0; k < i; ++k) v = sub(v, mul(Sm[i][k], x[k]));
+            x[i] = v;
+        }
+        for (int i = m - 1; i >= 0; --i) {
+            T v = x[i];
+            for (int k = i + 1; k < m; ++k) v = sub(v, mul(Sm[i][k], x[k]));
+            x[i] = mul(v, recip(Sm[i][i]));
+        }
+        for (int i = 0; i < m; ++i) Sol[(int64_t)i * r + c] = x[i];
+    }
+}
+
+template <class T>
+void launch_smw_core(const T* BtW, int64_t ldb, int m, int r, double alpha, T* Sol, int32_t* errflag,
+                     cudaStream_t st, int64_t* launches) {
+    if (m <= 0 || r <= 0) return;
+    k_smw_core<T><<<1, 256, 0, st>>>(BtW, ldb, m, r, alpha, Sol, errflag);
+    if (launches) *launches += 1;
+}
+
+__device__ __forceinline__ void emit(double v, int mode, double d, double* V1, double* V2, int64_t o1, int64_t o2) {
+    V1[o1] = v;
+}
+__device__ __forceinline__ void emit(cplx v, int mode, double d, double* V1, double* V2, int64_t o1, int64_t o2) {
+    if (mode == 2) {
+        V1[o1] = 1.4142135623730951 * v.x + (1.4142135623730951 * d) * v.y;
+        V2[o2] = sqrt(2.0 * d * d + 2.0) * v.y;
+    } else {
+        V1[o1] = v.x;
+        V2[o2] = v.y;
+    }
+}
+
+template <class T>
+__global__ void k_smw_apply(const T* __restrict__ W, int64_t ldw, int r, int m, const T* __restrict__ Sol, int mode,
+                            double d, double* __restrict__ V1, int64_t ld1, double* __restrict__ V2, int64_t ld2,
+                            int64_t n) {
+    const int64_t total = n * r;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / r;
+        const int c = (int)(idx % r);
+        const T* w = W + row * ldw;
+        T v = w[c];
+        for (int j = 0; j < m; ++j) v = sub(v, mul(w[r + j], Sol[(int64_t)j * r + c]));
+        emit(v, mode, d, V1, V2, row * ld1 + c, row * ld2 + c);
+    }
+}
+
+template <class T>
+void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int mode, double d, double* V1,
+                      int64_t ld1, double* V2, int64_t ld2, int64_t n, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || r <= 0) return;
+    int blocks = (int)std::min<int64_t>((n * r + 255) / 256, 148 * 16);
+    k_smw_apply<T><<<blocks, 256, 0, st>>>(W, ldw, r, m, Sol, mode, d, V1, ld1, V2, ld2, n);
+    if (launches) *launches += 1;
+}
+
+// ---- explicit instantiations ----
+#define DRE_INST(T)                                                                                                  \
+    template void launch_assemble<T>(const DevSymbolic&, T*, double, T, cudaStream_t, int64_t*);                     \
+    template void launch_extend_add<T>(const DevSymbolic&, const int32_t*, int, int, T*, T*, const T*, cudaStream_t, \
+                                       int64_t*);                                                                    \
+    template void launch_front_step<T>(const DevSymbolic&, const int2*, int, int, T*, T*, int32_t*, cudaStream_t,    \
+                                       int64_t*);                                                                    \
+    template void launch_schur<T>(const DevSymbolic&, const int4*, int, const T*, const T*, T*, cudaStream_t,        \
+                                  int64_t*);                                                                         \
+    template void launch_fwd_level<T>(const DevSymbolic&, const int32_t*, int, const T*, const T*, T*, int64_t, int, \
+                                      T*, const T*, cudaStream_t, int64_t*);                                         \
+    template void launch_bwd_level<T>(const DevSymbolic&, const int32_t*, int, const T*, const T*, T*, int64_t, int, \
+                                      cudaStream_t, int64_t*);                                                       \
+    template void launch_load_rhs<T>(T*, int64_t, const double*, int64_t, int, const double*, int64_t, int, int64_t, \
+                                     cudaStream_t, int64_t*);                                                        \
+    template void launch_smw_core<T>(const T*, int64_t, int, int, double, T*, int32_t*, cudaStream_t, int64_t*);     \
+    template void launch_smw_apply<T>(const T*, int64_t, int, int, const T*, int, double, double*, int64_t, double*, \
+                                      int64_t, int64_t, cudaStream_t, int64_t*);
+DRE_INST(double)
+DRE_INST(cplx)
+
+}  // namespace dre

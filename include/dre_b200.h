@@ -1,0 +1,157 @@
+/* dre_b200.h -- C ABI of libdre_b200.so: the B200-native LRSIF-ADI hot path of
+ * DifferentialRiccatiEquations.jl (reference v0.5.5 under /root/reference, cited as file:line).
+ *
+ * Plain C: opaque handles, pointers and sizes only.  The Julia glue reaches CUDA
+ * exclusively through `ccall` on these symbols; the Python host mirror (dre_b200.capi) binds the
+ * same symbols with ctypes.
+ *
+ * Conventions
+ *   - Every function returns int32 status: 0 ok; <0 argument/shape/state error; >0 CUDA / library /
+ *     numerical failure (zero pivot, non-finite).  The message is available from dre_last_error().
+ *     No C++ exception crosses the ABI.
+ *   - Host arrays are column-major (Julia/Fortran order) and are only borrowed for the duration of
+ *     the call.  Sparse matrices are CSC with 64-bit indices and index_base 0 or 1
+ *     (SparseMatrixCSC{Float64,Int64} zero-copy).
+ *   - Device "panels" are n x cols matrices (n = state dimension) owned by the context, addressed by
+ *     an integer id; a dre_view is a column range of a panel (hcat without copies,
+ *     cf. src/util/_hcat.jl:5-18).  Internally panels are stored row-major in the solver's
+ *     fill-reducing row ordering; upload/download apply the permutation, so the ordering is invisible.
+ *   - A context is not thread-safe; all work is queued on one CUDA stream and functions that do not
+ *     return host data are asynchronous.
+ */
+#ifndef DRE_B200_H
+#define DRE_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define DRE_API __attribute__((visibility("default")))
+#else
+#define DRE_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRE_OK 0
+#define DRE_ERR_ARG (-1)
+#define DRE_ERR_STATE (-2)
+#define DRE_ERR_CUDA 1
+#define DRE_ERR_NUMERIC 2
+#define DRE_ERR_LIB 3
+
+typedef struct dre_context dre_context;   /* device context (one GPU, one stream) */
+typedef struct dre_symbolic dre_symbolic; /* host-only symbolic analysis */
+
+typedef struct {
+    int32_t id;    /* panel id from dre_mat_create */
+    int32_t col0;  /* first column */
+    int32_t ncols; /* number of columns (0 = empty view) */
+} dre_view;
+
+typedef struct {
+    int64_t n;
+    int64_t nnz_pattern; /* nnz(pattern(A) u pattern(E)), both triangles */
+    int64_t nnz_L;       /* stored supernodal panel entries */
+    int64_t sum_update_rows;
+    double factor_flops; /* real flops of one LDL^T */
+    int32_t nsupernodes, nlevels, max_front, max_supernode;
+} dre_symbolic_info;
+
+/* ---- errors ---- */
+DRE_API const char* dre_last_error(const dre_context* ctx); /* ctx may be NULL: last error of ctx-less calls */
+DRE_API const char* dre_version(void);
+
+/* ---- host-only symbolic analysis (no GPU needed) ----
+ * Replaces the analysis half of `factorize` (src/blocklinear/types.jl:41-42, backslash.jl:13):
+ * nested-dissection ordering, supernode partition, elimination tree, level schedule, scatter maps
+ * for a*A + (e+mu)*E.  E and A must be symmetric (values checked). */
+DRE_API int32_t dre_symbolic_create(int64_t n, const int64_t* E_colptr, const int64_t* E_rowval, const double* E_nzval,
+                            const int64_t* A_colptr, const int64_t* A_rowval, const double* A_nzval,
+                            int32_t index_base, int32_t leaf_size, dre_symbolic** out);
+DRE_API void dre_symbolic_destroy(dre_symbolic* s);
+DRE_API int32_t dre_symbolic_get_info(const dre_symbolic* s, dre_symbolic_info* info);
+/* diagnostic export of internal arrays (tests): `what` is one of the names below; copies at most
+ * `cap` elements of 8 bytes (int64 or double) into buf and returns the full length in *len. */
+DRE_API int32_t dre_symbolic_export(const dre_symbolic* s, const char* what, void* buf, int64_t cap, int64_t* len);
+
+/* ---- context ---- */
+DRE_API int32_t dre_create(int32_t device, dre_context** out);
+DRE_API int32_t dre_destroy(dre_context* ctx);
+DRE_API int32_t dre_sync(dre_context* ctx);
+/* GALEProblem / GDREProblem matrices E, A (src/lyapunov/types.jl:10-16): runs the symbolic analysis
+ * once and uploads the permuted pencil. */
+DRE_API int32_t dre_set_pencil(dre_context* ctx, int64_t n, const int64_t* E_colptr, const int64_t* E_rowval,
+                       const double* E_nzval, const int64_t* A_colptr, const int64_t* A_rowval,
+                       const double* A_nzval, int32_t index_base);
+DRE_API int32_t dre_get_symbolic_info(const dre_context* ctx, dre_symbolic_info* info);
+
+/* ---- device panels (the outer factors L of LDLt, src/LDLt.jl:29-33; B, C', K') ---- */
+DRE_API int32_t dre_mat_create(dre_context* ctx, int32_t cols, int32_t* id);
+DRE_API int32_t dre_mat_free(dre_context* ctx, int32_t id);
+DRE_API int32_t dre_mat_upload(dre_context* ctx, dre_view dst, const double* host, int64_t ld);
+DRE_API int32_t dre_mat_download(dre_context* ctx, dre_view src, double* host, int64_t ld);
+DRE_API int32_t dre_mat_copy(dre_context* ctx, dre_view dst, dre_view src);
+/* Y = alpha*X + beta*Y (X may be an empty view when alpha == 0) */
+DRE_API int32_t dre_mat_axpby(dre_context* ctx, double alpha, dre_view X, double beta, dre_view Y);
+
+/* ---- products ----
+ * op: 'E' or 'A' (the pencil is symmetric, so E' L / A' L of src/lyapunov/residual.jl:18,
+ * lowrank_ros1.jl:42 use the same kernels).  Y = alpha*op*X + beta*Y.   */
+DRE_API int32_t dre_spmm(dre_context* ctx, int32_t op, double alpha, dre_view X, double beta, dre_view Y);
+/* out (X.ncols x Y.ncols, host column-major) = X' * Y   (B'L, Q'EQ, ...; synchronises) */
+DRE_API int32_t dre_gemm_tn(dre_context* ctx, dre_view X, dre_view Y, double* out, int64_t ld);
+/* Y = alpha * X * W + beta * Y with a small host matrix W (X.ncols x Y.ncols, column-major) */
+DRE_API int32_t dre_gemm_nn(dre_context* ctx, double alpha, dre_view X, const double* W, int64_t ldw, double beta,
+                    dre_view Y);
+
+/* ---- the shifted closed-loop solve ----
+ * Operator F = a*A + e*E + inv(alpha)*U*Vt'  (lr_update, src/LowRankUpdate.jl:38-39;
+ * Ros1: a=1, e=-1/(2 tau), alpha=-1, U=B, Vt=K' -- src/riccati/lowrank_ros1.jl:39).
+ * U, Vt are n x m panels (m may be 0: plain sparse operator, views with ncols = 0). */
+DRE_API int32_t dre_set_operator(dre_context* ctx, double a, double e, double alpha, dre_view U, dre_view Vt);
+/* Solve (F' + mu E') V = R   (src/lyapunov/adi.jl:156-159 real, :195-198 complex):
+ * numeric supernodal LDL^T of a*A+(e+mu)*E, block forward/backward sweeps for [R, Vt] and the fused
+ * Sherman-Morrison-Woodbury correction (src/blocklinear/sherman-morrison-woodbury.jl:10-45).
+ * mu_im == 0: V1 = V (V2 ignored).  mu_im != 0: V1 = Re V, V2 = Im V. */
+DRE_API int32_t dre_shift_solve(dre_context* ctx, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2);
+/* One ADI step (src/lyapunov/adi.jl:149-179 real, :181-225 complex pair):
+ *   real:     V1 = (F'+mu E')^-1 R;                          R += -2 mu E' V1
+ *   complex:  V  = (F'+mu E')^-1 R, d = Re mu / Im mu,
+ *             V1 = sqrt2 (Re V + d Im V), V2 = sqrt(2 d^2+2) Im V;   R += -2 sqrt2 Re(mu) E' V1
+ * R is updated in place; V1/V2 are freshly written panels. */
+DRE_API int32_t dre_adi_step(dre_context* ctx, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2);
+
+/* ---- low-rank algebra (src/LDLt.jl) ---- */
+/* |alpha| * || L D L' ||_F  (norm(::LDLt), src/LDLt.jl:77-89).  D: k x k host column-major. */
+DRE_API int32_t dre_ldlt_norm(dre_context* ctx, dre_view L, const double* D, int64_t ldd, double alpha, double* out);
+/* compress!(::LDLt) (src/LDLt.jl:204-225) of sum_i alphas[i] * Ls[i] * Ds[i] * Ls[i]':
+ * orthonormal basis of hcat(Ls) (rank-revealing block Gram-Schmidt = orthf, :237-245), eigen-
+ * decomposition of the projected core, truncation |lambda| >= tol_factor * max|lambda| * eps
+ * (tol_factor = 100 in the reference).  Writes the new outer factor into `out` (capacity
+ * out.ncols) and the new diagonal core into lam (capacity out.ncols); *newrank = kept columns. */
+DRE_API int32_t dre_ldlt_compress(dre_context* ctx, int32_t nterms, const dre_view* Ls, const double* const* Ds,
+                          const int64_t* ldds, const double* alphas, double tol_factor, dre_view out,
+                          double* lam, int32_t* newrank);
+/* Rank-revealing QR of N = hcat(views): N ~ Q * Rt' with orthonormal Q (n x rho) written to `Q`
+ * (capacity Q.ncols) and Rt (ncols(N) x rho, host column-major, ld = ldr).  Directions whose
+ * residual norm falls below max(drop_rel * max column norm, drop_abs) are discarded.  Building
+ * block of orth (src/Stuff.jl:13-18) for the Projection shifts (src/shifts/projection.jl:54-61). */
+DRE_API int32_t dre_rrqr(dre_context* ctx, int32_t nviews, const dre_view* views, double drop_rel, double drop_abs,
+                 dre_view Q, double* Rt, int64_t ldr, int32_t* rho);
+
+/* ---- timing / counters for bench.py ---- */
+typedef struct {
+    int64_t kernel_launches;    /* launches of this library's own kernels since the last reset */
+    int64_t factorizations;     /* numeric factorizations */
+    int64_t solves;             /* block solves */
+    double ms_factor, ms_solve, ms_spmm, ms_gram, ms_tallgemm; /* CUDA-event times when timing is enabled */
+} dre_stats;
+DRE_API int32_t dre_stats_reset(dre_context* ctx, int32_t enable_event_timing);
+DRE_API int32_t dre_stats_get(dre_context* ctx, dre_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRE_B200_H */
