@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- GDRE Ros1 LRSIF time steps per second on the Rail-shaped n=79841 pencil
+(BASELINE.json metric; config 4), plus the roofline of the dominant kernel class, the CPU
+baseline (oracle) and the end-to-end number through the public API with host buffers.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 79841]
+
+A "step" is one iteration of the Ros1 time loop (src/riccati/lowrank_ros1.jl:35-60 of the
+reference): build the closed-loop operator, build + compress the right-hand side, run the ADI
+solve (Projection(2) shifts, maxiters=100, compression every 10 increments), update K.
+Inputs are synthetic (dre_b200.pencils.rail_pencil).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GDRE Ros1 LRSIF steps/sec at n=79841"
+DT = -100.0
+T0 = 4500.0
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _problem(n):
+    import numpy as np
+    import scipy.sparse.linalg as spla
+
+    import dre_b200
+
+    E, A, B, C, meta = dre_b200.pencils.rail_pencil(n)
+    L0 = spla.splu(E.tocsc()).solve(C.T)
+    D0 = 0.01 * np.eye(C.shape[0])
+    return E, A, B, C, L0, D0, meta
+
+
+class IterCounter:
+    def __init__(self):
+        self.iters, self.ranks = [], []
+
+    def observe_gale_done(self, iters, X, res, rn):
+        self.iters.append(int(iters))
+        self.ranks.append((int(X.rank()), int(res.rank())))
+
+
+def _dist_init(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist_.init_process_group("nccl" if args.impl == "ours" else "gloo", rank=rank, world_size=world)
+        dist = dist_
+    return world, rank, local, dist
+
+
+def _fp64_peak(device):
+    """cuBLAS DGEMM 4096^3 through torch (plain library GEMM): denominator for the FP64 kernels."""
+    try:
+        import torch
+
+        a = torch.randn(4096, 4096, dtype=torch.float64, device=f"cuda:{device}")
+        b = torch.randn(4096, 4096, dtype=torch.float64, device=f"cuda:{device}")
+        for _ in range(2):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import numpy as np
+
+    world, rank, local, dist = _dist_init(args)
+    import dre_b200
+    from dre_b200 import api
+
+    n, K, W = args.n, args.steps, args.warmup
+    E, A, B, C, L0, D0, meta = _problem(n)
+    api.backend(local)
+    be = api.backend()
+    warnings.simplefilter("ignore")
+
+    def barrier():
+        be.ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- warm-up: W steps from t0 (also produces the state the timed steps start from) ----
+    cw = IterCounter()
+    tW = T0 + W * DT
+    sol = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(L0, D0), (T0, tW)), api.Ros1(), dt=DT, observer=cw)
+    XW = sol.X[-1]
+    info = be.ctx.symbolic_info()
+
+    # ---- timed region 1 (`value`): K more steps, state and pencil already resident in HBM ----
+    ct = IterCounter()
+    tK = tW + K * DT
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    be.ctx.stats_reset(False)
+    be.ctx.timer_start()
+    t_wall = time.perf_counter()
+    solK = api.solve(api.GDREProblem(E, A, B, C, XW, (tW, tK)), api.Ros1(), dt=DT, observer=ct)
+    ms = be.ctx.timer_stop()
+    wall = time.perf_counter() - t_wall
+    barrier()
+    clocks = sampler.stop()
+    st = be.ctx.stats()
+    if dist is not None:
+        import torch
+
+        tms = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * K / (ms * 1e-3)
+
+    # ---- instrumented pass (CUDA events around every kernel class) for the roofline ----
+    XK = solK.X[-1]
+    be.ctx.stats_reset(True)
+    api.solve(api.GDREProblem(E, A, B, C, XK, (tK, tK + DT)), api.Ros1(), dt=DT)
+    sti = be.ctx.stats()
+    be.ctx.stats_reset(False)
+    hbm_peak, peak_src = _peaks()
+    fp64_peak = _fp64_peak(local) if rank == 0 else None
+    classes = {}
+
+    def cls(name, ms_, count, bytes_=None, flops=None):
+        if count <= 0 or ms_ <= 0:
+            return
+        d = {"ms_total": round(ms_, 3), "launch_groups": int(count), "ms_avg": ms_ / count}
+        if bytes_ is not None:
+            d["GBps"] = bytes_ / (ms_ * 1e-3) / 1e9
+        if flops is not None:
+            d["TFLOPs"] = flops / (ms_ * 1e-3) / 1e12
+        classes[name] = d
+
+    cls("sptrsm_fwd_bwd_sweeps", sti["ms_solve"], sti["solves"], sti["bytes_solve"], sti["flops_solve"])
+    cls("supernodal_ldlt_factor", sti["ms_factor"], sti["factorizations"], None, sti["flops_factor"])
+    cls("csr_spmm", sti["ms_spmm"], sti["spmms"], sti["bytes_spmm"])
+    cls("gram_dmma", sti["ms_gram"], sti["grams"], sti["bytes_gram"], sti["flops_gram"])
+    cls("tall_gemm_dmma", sti["ms_tallgemm"], sti["tallgemms"], sti["bytes_tallgemm"], sti["flops_tallgemm"])
+    dom = max(classes, key=lambda k: classes[k]["ms_total"]) if classes else None
+    roofline = None
+    if dom is not None:
+        d = classes[dom]
+        if dom in ("sptrsm_fwd_bwd_sweeps", "csr_spmm"):
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": d["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": d["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src}
+        else:
+            pk = fp64_peak or 40.0
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": d["TFLOPs"], "peak": pk, "unit": "TFLOP/s",
+                        "frac": d["TFLOPs"] / pk, "traffic": None,
+                        "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (FP64 DMMA; MEASURED_PEAKS.json "
+                                       "holds no FP64 figure)" if fp64_peak else "nominal 40 TFLOP/s FP64"}
+        roofline["share_of_instrumented_step"] = d["ms_total"] / sum(c["ms_total"] for c in classes.values())
+
+    # ---- timed region 2 (`e2e`): the same K steps through the public API from HOST buffers ----
+    alphaW, LW, DW = XW.destructure()
+    LW_host = LW.to_host()
+    DW_host = alphaW * np.array(DW)
+    api.reset_backend()
+    api.backend(local)
+    be = api.backend()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    sol_e = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(LW_host, DW_host), (tW, tK)), api.Ros1(), dt=DT)
+    be.ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    h2d = (E.nnz + A.nnz) * 16 + 2 * (n + 1) * 8 + (B.size + C.size + LW_host.size) * 8
+    d2h = (K + 1) * B.shape[1] * n * 8
+    e2e = {"value": world * K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d / K,
+           "d2h_bytes_per_step": d2h / K,
+           "note": "includes symbolic analysis, pencil/B/C/X upload and the K(t) download of every step"}
+    kerr = max(float(np.linalg.norm(a - b) / np.linalg.norm(b)) for a, b in zip(sol_e.K, solK.K))
+
+    # ---- CPU baseline: the oracle on this box's host cores, bounded sample of the same step ----
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cpu = cpu_sample(E, A, B, C, LW_host, DW_host, ct.iters[0] if ct.iters else 100, args.cpu_iters)
+
+    if rank != 0:
+        return
+    out = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"Rail-shaped synthetic 2D P1-FEM pencil n={n} (7 inputs, 6 outputs), low-rank Ros1, "
+                               f"dt={DT}, t0={T0}, ADI defaults (Projection(2), maxiters=100, compression every 10)",
+                   "n": n, "nnz_E": meta["nnz_E"], "nnz_A": meta["nnz_A"],
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (sharding: see DESIGN.md)",
+                   "l2_policy": "inputs larger than L2: factor panels + RHS/solution panels + X factor exceed 126 MB",
+                   "adi_iters_per_timed_step": ct.iters, "rank_X_and_residual": ct.ranks,
+                   "symbolic": info},
+        "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
+        "gpu_counters": {k: st[k] for k in ("factorizations", "solves", "spmms", "grams", "tallgemms")},
+        "roofline": roofline, "kernel_classes": classes, "fp64_peak_tflops_measured": fp64_peak,
+        "cpu_baseline": cpu, "wall_s_timed_region": wall, "e2e_vs_resident_K_relerr": kerr,
+    }
+    print(json.dumps(out))
+
+
+def cpu_sample(E, A, B, C, L_host, D_host, iters_per_step, sample_iters):
+    """Time the oracle (NumPy/SciPy restatement of the reference) on the host cores: one ADI init of the
+    next Ros1 step plus `sample_iters` ADI iterations; steps/s is extrapolated with the iteration count the
+    GPU run needed for that step.  Periodic column compression of X is NOT included in the per-iteration
+    sample (fewer than 10 iterations), which favours the CPU."""
+    import numpy as np
+    from threadpoolctl import threadpool_limits
+
+    from oracle import dre_oracle as O
+
+    cores = os.cpu_count() or 1
+    nthreads = min(cores, 16)
+    tau = -DT
+    with threadpool_limits(limits=nthreads):
+        t0 = time.perf_counter()
+        X = O.lowrank(L_host, D_host)
+        alpha, L, D = X.destructure()
+        BtLD = (B.T @ L) @ D
+        EtL = E.T @ L
+        Kf = BtLD @ EtL.T
+        F = O.lr_update((A - E / (2 * tau)).tocsc(), -1.0, B, Kf)
+        G = np.concatenate([C.T, EtL], axis=1)
+        S = O._dcat([np.eye(C.shape[0]), BtLD.T @ BtLD + D / tau])
+        R = O.compress(O.lowrank(G, S))
+        cache = O.adi_init(O.GALEProblem(E, F, R), O.ADI(warn_convergence=False), initial_guess=X)
+        t_init = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for _ in range(sample_iters):
+                O.adi_step(cache)
+        t_iter = (time.perf_counter() - t0) / max(sample_iters, 1)
+    est = t_init + iters_per_step * t_iter
+    return {"value": 1.0 / est, "unit": "steps/s", "cores": nthreads, "kind": "port",
+            "sample": f"oracle (SciPy SuperLU + LAPACK): RHS build + ADI init ({t_init:.1f} s) + {sample_iters} ADI "
+                      f"iterations ({t_iter:.2f} s each) of the first timed step at the same state; extrapolated to "
+                      f"the {iters_per_step} iterations that step needs; periodic X compression excluded",
+            "t_init_s": t_init, "t_iter_s": t_iter, "host_cores": cores}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: Julia is not installed in this image or
+    on the GPU box) on the host cores, same config/metric; every step is a bounded sample."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from threadpoolctl import threadpool_limits
+
+    from oracle import dre_oracle as O
+
+    n, K, W = args.n, args.steps, args.warmup
+    E, A, B, C, L0, D0, meta = _problem(n)
+    cores = os.cpu_count() or 1
+    nthreads = min(cores, 16)
+    warnings.simplefilter("ignore")
+    tau = -DT
+    with threadpool_limits(limits=nthreads):
+        # reach a representative state: the first Ros1 step from X0 in full (narrow residual, cheap)
+        t0 = time.perf_counter()
+        sol = O.solve_gdre(O.GDREProblem(E, A, B, C, O.lowrank(L0, D0), (T0, T0 + DT)), O.Ros1(), dt=DT)
+        t_first = time.perf_counter() - t0
+        X = sol.X[-1]
+        t0 = time.perf_counter()
+        alpha, L, D = X.destructure()
+        BtLD = (B.T @ L) @ D
+        EtL = E.T @ L
+        Kf = BtLD @ EtL.T
+        F = O.lr_update((A - E / (2 * tau)).tocsc(), -1.0, B, Kf)
+        G = np.concatenate([C.T, EtL], axis=1)
+        S = O._dcat([np.eye(C.shape[0]), BtLD.T @ BtLD + D / tau])
+        R = O.compress(O.lowrank(G, S))
+        cache = O.adi_init(O.GALEProblem(E, F, R), O.ADI(warn_convergence=False), initial_guess=X)
+        t_init = time.perf_counter() - t0
+        for _ in range(min(W, 1)):
+            O.adi_step(cache)
+        times = []
+        for _ in range(K):
+            t0 = time.perf_counter()
+            O.adi_step(cache)
+            times.append(time.perf_counter() - t0)
+    t_iter = float(np.mean(times))
+    iters = 100  # default ADI(maxiters=100) is reached on every step after the first on this pencil
+    est = t_init + iters * t_iter
+    value = 1.0 / est
+    sample = (f"oracle port on {nthreads} host threads: first step in full ({t_first:.1f} s, untimed), then per timed "
+              f"'step' one ADI iteration of the second step ({t_iter:.2f} s mean) + ADI init {t_init:.1f} s; "
+              f"steps/s extrapolated to {iters} ADI iterations per step; periodic X compression excluded")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K,
+           "warmup": W, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"Rail-shaped synthetic 2D P1-FEM pencil n={n} (7 inputs, 6 outputs), low-rank "
+                                  f"Ros1, dt={DT}, t0={T0}, ADI defaults", "n": n},
+           "cpu_baseline": {"value": value, "unit": "steps/s", "cores": nthreads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=79841)
+    ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(min(os.cpu_count() or 1, 16)))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,3 +6,6 @@ Import as ``import dre_b200`` (shim at the repo root).  Submodules:
   api       host-side mirror of the reference's Julia API over the C ABI
 """
 from . import pencils  # noqa: F401
+from . import capi  # noqa: F401
+from .api import *  # noqa: F401,F403
+from . import api  # noqa: F401

@@ -1,0 +1,1251 @@
+"""Host-side mirror of the reference's Julia API for the LRSIF-ADI hot path, over the C ABI.
+
+Names, argument meaning, control flow, observer call order and error behaviour follow the reference
+(paths relative to /root/reference/; Julia's ``f!`` is spelled ``f_`` here):
+
+  lowrank / LDLt / concatenate_ / compress_ / norm           src/LDLt.jl
+  LowRankUpdate / lr_update                                  src/LowRankUpdate.jl
+  BlockLinearProblem / Backslash / ShermanMorrisonWoodbury   src/blocklinear/*.jl
+  Shifts.{Projection, Heuristic, Cyclic, Wrapped, ...}       src/Shifts.jl, src/shifts/*.jl
+  GALEProblem / ADI / init / step_ / solve_ / solve          src/lyapunov/{types,adi,residual}.jl
+  GDREProblem / Ros1 / Ros2 / GAREProblem / Newton / solve   src/riccati/*.jl
+  observers                                                  src/Callbacks.jl (method names without "!")
+
+Outer factors (the n x k matrices) live on the GPU as ``DeviceMatrix`` panels; the small k x k cores
+live on the host as NumPy arrays -- the "xpu" layout of the reference's own GPU test
+(test/cuda.jl:66, GPU outer factor + CPU core).  All heavy arithmetic goes through
+``libdre_b200.so``; there is no CPU fallback.  Tiny dense eigen/SVD problems of the Projection
+shift strategy run on the host LAPACK exactly like the reference does
+(src/shifts/projection.jl:63-67 "Ensure data lives on the CPU").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import math
+import warnings
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+from . import capi
+from .capi import View
+
+EPS = float(np.finfo(np.float64).eps)
+
+# =============================================================================================
+# backend: one context per process, device panels
+# =============================================================================================
+_backend = None
+
+
+class Backend:
+    def __init__(self, device=0):
+        self.ctx = capi.Context(device)
+        self.lib = self.ctx.lib
+        self.h = self.ctx.h
+        self.generation = 0
+        self.pencil_key = None
+        self.E = self.A = None
+        self.n = None
+
+    def ensure_pencil(self, E, A):
+        key = (id(E), id(A), E.shape, E.nnz, A.nnz)
+        if self.pencil_key == key:
+            return
+        if not (sp.issparse(E) and sp.issparse(A)):
+            raise TypeError("E and A must be scipy sparse matrices")
+        self.ctx.set_pencil(E, A)
+        self.generation += 1
+        self.pencil_key = key
+        self.E, self.A = E, A  # keep alive: the key uses id()
+        self.n = E.shape[0]
+
+    def check(self, rc):
+        self.ctx.check(rc)
+
+
+def backend(device=None) -> Backend:
+    global _backend
+    if _backend is None:
+        _backend = Backend(0 if device is None else device)
+    return _backend
+
+
+def reset_backend():
+    global _backend
+    if _backend is not None:
+        _backend.ctx.close()
+    _backend = None
+
+
+class _Panel:
+    """Owner of one device panel (freed when the last view dies)."""
+
+    def __init__(self, be: Backend, cols: int):
+        self.be, self.cols, self.gen = be, cols, be.generation
+        pid = C.c_int32(-1)
+        be.check(be.lib.dre_mat_create(be.h, cols, C.byref(pid)))
+        self.id = pid.value
+
+    def __del__(self):
+        try:
+            if self.be.ctx.h and self.gen == self.be.generation:
+                self.be.lib.dre_mat_free(self.be.h, self.id)
+        except Exception:
+            pass
+
+
+class DeviceMatrix:
+    """n x k real matrix on the GPU: a column range of a panel (cf. dre_view)."""
+
+    def __init__(self, panel: _Panel, col0: int, ncols: int):
+        self.panel, self.col0, self.ncols = panel, col0, ncols
+
+    @staticmethod
+    def empty(cols: int) -> "DeviceMatrix":
+        be = backend()
+        return DeviceMatrix(_Panel(be, max(cols, 0)), 0, cols)
+
+    @staticmethod
+    def from_host(M) -> "DeviceMatrix":
+        M = np.asfortranarray(np.asarray(M, dtype=np.float64))
+        if M.ndim == 1:
+            M = M.reshape(-1, 1, order="F")
+        be = backend()
+        if M.shape[0] != be.n:
+            raise ValueError(f"row count {M.shape[0]} does not match the pencil dimension {be.n}")
+        d = DeviceMatrix.empty(M.shape[1])
+        if M.shape[1]:
+            be.check(be.lib.dre_mat_upload(be.h, d.view, capi._dptr(M), M.shape[0]))
+        return d
+
+    @property
+    def view(self) -> View:
+        if self.panel.gen != self.panel.be.generation:
+            raise RuntimeError("stale DeviceMatrix: the pencil of the backend was replaced")
+        return View(self.panel.id, self.col0, self.ncols)
+
+    @property
+    def shape(self):
+        return (self.panel.be.n, self.ncols)
+
+    def cols(self, a: int, b: int) -> "DeviceMatrix":
+        assert 0 <= a <= b <= self.ncols
+        return DeviceMatrix(self.panel, self.col0 + a, b - a)
+
+    def to_host(self) -> np.ndarray:
+        be = self.panel.be
+        out = np.empty((be.n, self.ncols), dtype=np.float64, order="F")
+        if self.ncols:
+            be.check(be.lib.dre_mat_download(be.h, self.view, capi._dptr(out), be.n))
+        return out
+
+    def copy(self) -> "DeviceMatrix":
+        d = DeviceMatrix.empty(self.ncols)
+        if self.ncols:
+            be = self.panel.be
+            be.check(be.lib.dre_mat_copy(be.h, d.view, self.view))
+        return d
+
+    def __array__(self, dtype=None, copy=None):
+        return self.to_host()
+
+
+def _as_device(M) -> DeviceMatrix:
+    return M if isinstance(M, DeviceMatrix) else DeviceMatrix.from_host(M)
+
+
+def _ncols(L) -> int:
+    return L.ncols if isinstance(L, DeviceMatrix) else int(np.shape(L)[1])
+
+
+def hcat(Xs) -> DeviceMatrix:
+    """src/util/_hcat.jl:5-18 on device."""
+    Xs = list(Xs)
+    be = backend()
+    out = DeviceMatrix.empty(sum(X.ncols for X in Xs))
+    k = 0
+    for X in Xs:
+        if X.ncols:
+            be.check(be.lib.dre_mat_copy(be.h, out.cols(k, k + X.ncols).view, X.view))
+        k += X.ncols
+    return out
+
+
+def spmm(op: str, X: DeviceMatrix, alpha=1.0, Y: DeviceMatrix | None = None, beta=0.0) -> DeviceMatrix:
+    """Y = alpha * op * X + beta * Y, op in {'E','A'} (symmetric pencil: E'X == EX)."""
+    be = backend()
+    if Y is None:
+        Y = DeviceMatrix.empty(X.ncols)
+        beta = 0.0
+    be.check(be.lib.dre_spmm(be.h, ord(op), float(alpha), X.view, float(beta), Y.view))
+    return Y
+
+
+def gemm_tn(X: DeviceMatrix, Y: DeviceMatrix) -> np.ndarray:
+    """X' * Y -> host matrix."""
+    be = backend()
+    out = np.zeros((X.ncols, Y.ncols), dtype=np.float64, order="F")
+    if X.ncols and Y.ncols:
+        be.check(be.lib.dre_gemm_tn(be.h, X.view, Y.view, capi._dptr(out), max(X.ncols, 1)))
+    return out
+
+
+def gemm_nn(X: DeviceMatrix, W, alpha=1.0, Y: DeviceMatrix | None = None, beta=0.0) -> DeviceMatrix:
+    """Y = alpha * X * W + beta * Y with a small host matrix W."""
+    be = backend()
+    W = np.asfortranarray(np.asarray(W, dtype=np.float64))
+    assert W.shape[0] == X.ncols
+    if Y is None:
+        Y = DeviceMatrix.empty(W.shape[1])
+        beta = 0.0
+    assert W.shape[1] == Y.ncols
+    be.check(be.lib.dre_gemm_nn(be.h, float(alpha), X.view, capi._dptr(W), max(W.shape[0], 1), float(beta), Y.view))
+    return Y
+
+
+# =============================================================================================
+# observers (src/Callbacks.jl:97-187)
+# =============================================================================================
+def _observe(observer, name, *args):
+    if observer is None:
+        return
+    fn = getattr(observer, name, None)
+    if fn is not None:
+        fn(*args)
+
+
+# =============================================================================================
+# LDLt (src/LDLt.jl)
+# =============================================================================================
+class LDLt:
+    """src/LDLt.jl:29-33 -- lazy sum_i alpha_i L_i D_i L_i' with device outer factors."""
+
+    def __init__(self, alphas, Ls, Ds):
+        self.alphas, self.Ls, self.Ds = list(alphas), list(Ls), list(Ds)
+
+    def destructure(self):  # :54-60
+        if len(self.Ls) > 1:
+            compress_(self)
+        return self.alphas[0], self.Ls[0], self.Ds[0]
+
+    def __iter__(self):
+        return iter(self.destructure())
+
+    @property
+    def n(self):
+        return self.Ls[0].shape[0]
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def rank(self):  # :112
+        return sum(_ncols(L) for L in self.Ls)
+
+    def to_device_(self):
+        """Move host (NumPy) outer factors to the GPU in place; needs an uploaded pencil."""
+        for i, L in enumerate(self.Ls):
+            if not isinstance(L, DeviceMatrix):
+                self.Ls[i] = DeviceMatrix.from_host(L)
+        return self
+
+    def iszero(self):  # :114
+        return all(a == 0 for a in self.alphas) or self.rank() == 0
+
+    def zero(self):  # :116-121
+        return LDLt([1.0], [DeviceMatrix.empty(0)], [np.zeros((0, 0))])
+
+    def to_dense(self):  # :42-51 (testing only)
+        M = np.zeros((self.n, self.n))
+        for a, L, D in zip(self.alphas, self.Ls, self.Ds):
+            Lh = L.to_host()
+            M += Lh @ (a * D) @ Lh.T
+        return M
+
+    def __add__(self, other):  # :131-148
+        if self.iszero():
+            return other
+        if other.iszero():
+            return self
+        return LDLt(self.alphas + other.alphas, self.Ls + other.Ls, self.Ds + other.Ds)
+
+    def __neg__(self):  # :150-153
+        return LDLt([-a for a in self.alphas], self.Ls, self.Ds)
+
+    def __sub__(self, other):
+        return self + (-other)
+
+    def __rmul__(self, alpha):  # :156-159
+        return LDLt([alpha * a for a in self.alphas], self.Ls, self.Ds)
+
+    def __truediv__(self, alpha):
+        return (1.0 / alpha) * self
+
+
+def lowrank(L, D=None) -> LDLt:
+    """src/LDLt.jl:24-27; ``D=None`` is the UniformScaling I.  ``L`` may be a NumPy matrix (moved to the
+    GPU when the problem it belongs to is solved) or a DeviceMatrix."""
+    Ld = L if isinstance(L, DeviceMatrix) else np.asfortranarray(np.asarray(L, dtype=np.float64))
+    Dh = np.eye(_ncols(Ld)) if D is None else np.array(D, dtype=np.float64, order="F")
+    return LDLt([1.0], [Ld], [Dh])
+
+
+def _dcat(Xs, alphas=None):
+    """src/util/_dcat.jl:8-22."""
+    Xs = list(Xs)
+    alphas = [1.0] * len(Xs) if alphas is None else list(alphas)
+    n = sum(X.shape[0] for X in Xs)
+    D = np.zeros((n, n), order="F")
+    k = 0
+    for X, a in zip(Xs, alphas):
+        l = X.shape[0]
+        D[k:k + l, k:k + l] = X * a
+        k += l
+    return D
+
+
+def concatenate_(X: LDLt) -> LDLt:
+    """src/LDLt.jl:174-191."""
+    if len(X.alphas) == 1:
+        return X
+    L = hcat(X.Ls)
+    D = _dcat(X.Ds, X.alphas)
+    X.alphas[:] = [1.0]
+    X.Ls[:] = [L]
+    X.Ds[:] = [D]
+    return X
+
+
+def compress_(X: LDLt) -> LDLt:
+    """src/LDLt.jl:204-225 -- one C-ABI call (dre_ldlt_compress); no concatenation copy is needed."""
+    be = backend()
+    terms = [(a, L, np.asfortranarray(D, dtype=np.float64)) for a, L, D in zip(X.alphas, X.Ls, X.Ds) if L.ncols]
+    ktot = sum(L.ncols for _, L, _ in terms)
+    if ktot == 0:
+        raise ValueError("compress!: rank-0 input (reference: maximum of empty collection, src/LDLt.jl:216)")
+    nt = len(terms)
+    views = (View * nt)(*[L.view for _, L, _ in terms])
+    dptrs = (C.POINTER(C.c_double) * nt)(*[capi._dptr(D) for _, _, D in terms])
+    ldds = (C.c_int64 * nt)(*[max(D.shape[0], 1) for _, _, D in terms])
+    alphas = (C.c_double * nt)(*[float(a) for a, _, _ in terms])
+    cap = min(ktot, be.n)
+    out = DeviceMatrix.empty(cap)
+    lam = np.zeros(cap)
+    newrank = C.c_int32(0)
+    be.check(be.lib.dre_ldlt_compress(be.h, nt, views, dptrs, ldds, alphas, 100.0, out.view, capi._dptr(lam),
+                                      C.byref(newrank)))
+    k2 = newrank.value
+    Lnew = out.cols(0, k2)
+    if cap > 2 * max(k2, 1):  # do not keep a large mostly-unused panel alive
+        Lnew = Lnew.copy()
+    X.alphas[:] = [1.0]
+    X.Ls[:] = [Lnew]
+    X.Ds[:] = [np.asfortranarray(np.diag(lam[:k2]))]
+    return X
+
+
+def norm(X: LDLt) -> float:
+    """src/LDLt.jl:77-89."""
+    be = backend()
+    concatenate_(X)
+    a, L, D = X.alphas[0], X.Ls[0], X.Ds[0]
+    if L.ncols == 0:
+        return 0.0
+    D = np.asfortranarray(D, dtype=np.float64)
+    out = C.c_double(0.0)
+    be.check(be.lib.dre_ldlt_norm(be.h, L.view, capi._dptr(D), max(D.shape[0], 1), float(a), C.byref(out)))
+    return float(out.value)
+
+
+# =============================================================================================
+# operators: pencil combinations and LowRankUpdate (src/LowRankUpdate.jl)
+# =============================================================================================
+class PencilCombo:
+    """The sparse matrix a*A + e*E of the uploaded (symmetric) pencil -- what the reference builds
+    as a new SparseMatrixCSC per shift (adi.jl:156, lowrank_ros1.jl:39) is two scalars here."""
+
+    def __init__(self, a: float, e: float):
+        self.a, self.e = float(a), float(e)
+
+    @property
+    def shape(self):
+        n = backend().n
+        return (n, n)
+
+    @property
+    def T(self):
+        return self  # symmetric pencil
+
+    def __add__(self, other):
+        if isinstance(other, PencilCombo):
+            return PencilCombo(self.a + other.a, self.e + other.e)
+        return NotImplemented
+
+    def __sub__(self, other):
+        return PencilCombo(self.a - other.a, self.e - other.e)
+
+    def __mul__(self, s):
+        return PencilCombo(self.a * s, self.e * s)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, s):
+        return PencilCombo(self.a / s, self.e / s)
+
+    def matmul(self, X: DeviceMatrix) -> DeviceMatrix:
+        Y = None
+        if self.a != 0.0 or self.e == 0.0:
+            Y = spmm("A", X, self.a)
+        if self.e != 0.0:
+            Y = spmm("E", X, self.e, Y, 1.0 if Y is not None else 0.0)
+        return Y
+
+
+class LowRankUpdate:
+    """src/LowRankUpdate.jl:18-26 -- lazy A + inv(alpha) U V with U (n x m) and V (m x n, held as its
+    transpose panel Vt, n x m)."""
+
+    def __init__(self, A: PencilCombo, alpha: float, U: DeviceMatrix, Vt: DeviceMatrix):
+        self.A, self.alpha, self.U, self.Vt = A, float(alpha), U, Vt
+
+    @property
+    def shape(self):
+        return self.A.shape
+
+    def adjoint(self):  # :51-54
+        return LowRankUpdate(self.A.T, self.alpha, self.Vt, self.U)
+
+    def plus_sparse(self, E: PencilCombo):  # :66-70
+        return LowRankUpdate(self.A + E, self.alpha, self.U, self.Vt)
+
+    def matmul(self, X: DeviceMatrix) -> DeviceMatrix:  # :72-86
+        if X.ncols == X.shape[0]:
+            warnings.warn("Multiplying LowRankUpdate by square matrix; memory usage may increase severely")
+        Y = self.A.matmul(X)
+        VX = gemm_tn(self.Vt, X)  # m x k
+        return gemm_nn(self.U, VX, 1.0 / self.alpha, Y, 1.0)
+
+
+def lr_update(A, alpha, U, V_or_Vt, *, transposed=False):
+    """src/LowRankUpdate.jl:38-39.  ``V`` is m x n on the host, or (transposed=True) its n x m panel."""
+    if not isinstance(A, PencilCombo):
+        raise TypeError("lr_update: A must be a PencilCombo of the uploaded pencil")
+    Ud = _as_device(U)
+    Vt = V_or_Vt if transposed else _as_device(np.asarray(V_or_Vt).T)
+    return LowRankUpdate(A, alpha, Ud, Vt)
+
+
+def _matmul(A, X: DeviceMatrix) -> DeviceMatrix:
+    return A.matmul(X)
+
+
+def _adj_matmul(A, X: DeviceMatrix) -> DeviceMatrix:
+    return A.adjoint().matmul(X) if isinstance(A, LowRankUpdate) else A.T.matmul(X)
+
+
+# =============================================================================================
+# block linear solvers (src/blocklinear/*.jl)
+# =============================================================================================
+class BlockLinearProblem:  # types.jl:10-13
+    def __init__(self, A, B):
+        self.A, self.B = A, B
+
+
+class BlockLinearSolver:
+    pass
+
+
+class Backslash(BlockLinearSolver):  # types.jl:31-34
+    """Sparse direct solve on the GPU: numeric supernodal LDL^T per shift + block sweeps."""
+
+
+class ShermanMorrisonWoodbury(BlockLinearSolver):  # types.jl:35-39
+    def __init__(self, ALG=None, alg=None):
+        self.ALG = ALG if ALG is not None else Backslash()
+        self.alg = alg if alg is not None else Backslash()
+
+
+def _set_operator(F, *, transpose: bool):
+    """Tell the library which operator the next shifted solves use.  The library solves with
+    (F' + mu E'); ``transpose=False`` (solve with F itself) swaps the low-rank factors."""
+    be = backend()
+    if isinstance(F, LowRankUpdate):
+        U, Vt = (F.U, F.Vt) if transpose else (F.Vt, F.U)
+        be.check(be.lib.dre_set_operator(be.h, F.A.a, F.A.e, F.alpha, U.view, Vt.view))
+    else:
+        z = View(-1, 0, 0)
+        be.check(be.lib.dre_set_operator(be.h, F.a, F.e, 1.0, z, z))
+
+
+def solve_block(prob: BlockLinearProblem, alg: BlockLinearSolver | None = None, *, mu: complex = 0.0):
+    """CommonSolve.solve(::BlockLinearProblem, alg): X = (prob.A + mu E) \\ prob.B  (backslash.jl:8-21,
+    sherman-morrison-woodbury.jl:10-45 when prob.A is a LowRankUpdate).  Returns a DeviceMatrix, or a
+    pair (Re X, Im X) for complex mu."""
+    be = backend()
+    alg = alg if alg is not None else Backslash()
+    if not isinstance(alg, (Backslash, ShermanMorrisonWoodbury)):
+        return alg.solve(prob, mu=mu)  # user-defined BlockLinearSolver (types.jl:15-30)
+    _set_operator(prob.A, transpose=False)
+    B = prob.B
+    V1 = DeviceMatrix.empty(B.ncols)
+    mu = complex(mu)
+    if mu.imag == 0.0:
+        be.check(be.lib.dre_shift_solve(be.h, mu.real, 0.0, B.view, V1.view, View(-1, 0, 0)))
+        return V1
+    V2 = DeviceMatrix.empty(B.ncols)
+    be.check(be.lib.dre_shift_solve(be.h, mu.real, mu.imag, B.view, V1.view, V2.view))
+    return V1, V2
+
+
+# =============================================================================================
+# Shifts (src/Shifts.jl, src/shifts/*.jl)
+# =============================================================================================
+class Shifts:
+    """Namespace mirroring the reference's ``Shifts`` module."""
+
+    class Strategy:
+        pass
+
+    @staticmethod
+    def safe_sort(shifts):  # helpers.jl:122
+        shifts = list(shifts)
+        shifts.sort(key=lambda v: (np.real(v), abs(np.imag(v))))
+        return shifts
+
+    @staticmethod
+    def stabilize_ritz_values(lam, desc):  # helpers.jl:129-140
+        lam = list(lam)
+        assert len(lam) > 0
+        n_unstable = sum(1 for v in lam if not np.real(v) < 0)
+        if 0 < n_unstable < len(lam):
+            warnings.warn(f"Discarding unstable Ritz values of {desc}")
+            lam = [v for v in lam if np.real(v) < 0]
+        elif n_unstable == len(lam):
+            warnings.warn(f"All Ritz values of {desc} are unstable; flipping along imaginary axis")
+            lam = [complex(-np.real(v), np.imag(v)) if np.iscomplexobj(v) else -v for v in lam]
+        return lam
+
+    @staticmethod
+    def heuristic(R, nshifts=None):  # heuristic.jl:82-101
+        R = list(R)
+        nshifts = len(R) if nshifts is None else nshifts
+
+        def s(t, P):
+            return math.prod(abs(t - p) / abs(t + p) for p in P)
+
+        vals = [max(s(t, (p,)) for t in R) for p in R]
+        p = R[int(np.argmin(vals))]
+        P = [p] if np.imag(p) == 0 else [p, np.conj(p)]
+        while len(P) < nshifts:
+            vals = [s(t, P) for t in R]
+            p = R[int(np.argmax(vals))]
+            if np.imag(p) == 0:
+                P.append(p)
+            else:
+                P.extend((p, np.conj(p)))
+        return P
+
+
+class Projection(Shifts.Strategy):  # projection.jl:25-32
+    def __init__(self, u):
+        if u % 2 == 1:
+            raise ValueError(f"History must be even; got {u}")
+        self.n_history = u
+
+
+class Heuristic(Shifts.Strategy):  # heuristic.jl:22-30
+    def __init__(self, nshifts, k_plus, k_minus, alg_E=None, alg_A=None):
+        self.nshifts, self.k_plus, self.k_minus = nshifts, k_plus, k_minus
+        self.alg_E = alg_E if alg_E is not None else Backslash()
+        self.alg_A = alg_A if alg_A is not None else Backslash()
+
+
+class Cyclic(Shifts.Strategy):  # helpers.jl:19-27
+    def __init__(self, inner):
+        self.inner = inner
+
+
+class Wrapped(Shifts.Strategy):  # helpers.jl:48-58
+    def __init__(self, func, inner):
+        self.func, self.inner = func, inner
+
+
+Shifts.Projection, Shifts.Heuristic, Shifts.Cyclic, Shifts.Wrapped = Projection, Heuristic, Cyclic, Wrapped
+
+
+def orth_restrict(Vs, E, A):
+    """Q = orth(hcat(Vs)) (src/Stuff.jl:13-18) and the restrictions Q'EQ, Q'AQ (src/Stuff.jl:9,
+    src/util/restrict.jl:5-8), without ever forming the SVD basis on the device: a rank-revealing QR
+    N = Q0 Rt' runs on the GPU, the small SVD of Rt' on the host selects the singular directions
+    > n*eps exactly as the reference, and the projected pencils are rotated on the host."""
+    be = backend()
+    n = be.n
+    ktot = sum(V.ncols for V in Vs)
+    if ktot == 0:
+        return np.zeros((0, 0)), np.zeros((0, 0))
+    views = (View * len(Vs))(*[V.view for V in Vs])
+    cap = min(ktot, n)
+    Q0 = DeviceMatrix.empty(cap)
+    Rt = np.zeros((ktot, cap), order="F")
+    rho = C.c_int32(0)
+    be.check(be.lib.dre_rrqr(be.h, len(Vs), views, 1e-15, 1e-3 * n * EPS, Q0.view, capi._dptr(Rt), ktot,
+                             C.byref(rho)))
+    rho = rho.value
+    if rho == 0:
+        return np.zeros((0, 0)), np.zeros((0, 0))
+    Q0 = Q0.cols(0, rho)
+    U, s, _ = sla.svd(Rt[:, :rho].T, full_matrices=False, lapack_driver="gesdd")  # N = Q0 (U s W')
+    ids = np.nonzero(np.abs(s) > n * EPS)[0]  # Stuff.jl:15-16
+    Us = U[:, ids]
+    EQ = spmm("E", Q0)
+    Et = gemm_tn(Q0, EQ)
+    if isinstance(A, LowRankUpdate):
+        AQ = A.A.matmul(Q0)
+        At = gemm_tn(Q0, AQ) + (1.0 / A.alpha) * (gemm_tn(Q0, A.U) @ gemm_tn(A.Vt, Q0))
+    else:
+        At = gemm_tn(Q0, A.matmul(Q0))
+    return Us.T @ Et @ Us, Us.T @ At @ Us
+
+
+class ProjectionShiftIterator:  # projection.jl:34-73
+    def __init__(self, prob, n_history):
+        self.prob, self.n_history, self.Vs = prob, n_history, []
+
+    def update(self, X, R, *Vs):  # :45-52
+        if not Vs:
+            self.Vs.append(R)  # aliases the residual factor, which ADI updates in place (adi.jl:171)
+        self.Vs.extend(Vs)
+        lst = len(self.Vs)
+        fst = max(0, lst - self.n_history)
+        self.Vs = self.Vs[fst:lst]
+
+    def take_many(self):  # :54-73
+        Et, At = orth_restrict(self.Vs, self.prob.E, self.prob.A)
+        lam = sla.eigvals(At, Et)
+        if np.all(np.imag(lam) == 0):
+            lam = np.real(lam)
+        lam = Shifts.stabilize_ritz_values(lam, "(A, E)")
+        return Shifts.safe_sort(lam)
+
+
+class BufferedIterator:  # helpers.jl:70-75, 106-113
+    def __init__(self, gen):
+        self.buffer, self.generator = [], gen
+
+    def update(self, *args):
+        upd = getattr(self.generator, "update", None)
+        if upd is not None:
+            upd(*args)
+
+    def take(self):
+        if not self.buffer:
+            self.buffer = list(self.generator.take_many())
+        return self.buffer.pop(0)
+
+
+class WrappedIterator:  # helpers.jl:85-104
+    def __init__(self, func, gen):
+        self.func, self.generator = func, gen
+
+    def update(self, *args):
+        upd = getattr(self.generator, "update", None)
+        if upd is not None:
+            upd(*args)
+
+    def take_many(self):
+        return self.func(_take_many(self.generator))
+
+
+class _CycleIterator:  # Stateful(cycle(values)), helpers.jl:93
+    def __init__(self, values):
+        self.values = list(values)
+        self._it = itertools.cycle(self.values)
+
+    def update(self, *args):
+        return None
+
+    def take(self):
+        return next(self._it)
+
+
+class _ListIterator:  # plain vector: take! = popfirst! (Shifts.jl:116)
+    def __init__(self, values):
+        self.values = list(values)
+
+    def update(self, *args):
+        return None
+
+    def take(self):
+        return self.values.pop(0)
+
+    def take_many(self):
+        return self.values
+
+
+def _take_many(gen):
+    return gen.take_many() if hasattr(gen, "take_many") else list(gen)
+
+
+def _arnoldi_ritz(op, b0, k, desc):
+    """heuristic.jl:103-130 -- Arnoldi with twice-repeated MGS on host vectors; ``op`` runs on the GPU."""
+    n = len(b0)
+    H = np.zeros((k + 1, k))
+    V = np.zeros((n, k + 1))
+    V[:, 0] = (1.0 / np.linalg.norm(b0)) * b0
+    for j in range(k):
+        w = np.array(op(V[:, j]), dtype=float).reshape(n)
+        for _ in range(2):
+            for i in range(j + 1):
+                g = float(V[:, i] @ w)
+                H[i, j] += g
+                w -= V[:, i] * g
+        beta = float(np.linalg.norm(w))
+        H[j + 1, j] = beta
+        V[:, j + 1] = (1.0 / beta) * w
+    ritz = sla.eigvals(H[:k, :k])
+    if np.all(np.imag(ritz) == 0):
+        ritz = np.real(ritz)
+    return Shifts.stabilize_ritz_values(ritz, desc)
+
+
+def shifts_init(strategy, prob):
+    """Shifts.init (projection.jl:40-43, heuristic.jl:39-66, helpers.jl:86-99)."""
+    if isinstance(strategy, Projection):
+        return BufferedIterator(ProjectionShiftIterator(prob, strategy.n_history))
+    if isinstance(strategy, Heuristic):
+        E, A = prob.E, prob.A
+        n = backend().n
+        b0 = np.ones(n)  # heuristic.jl:75-80
+
+        def op_plus(x):  # E \ (A x)
+            Ax = _matmul(A, DeviceMatrix.from_host(x))
+            return solve_block(BlockLinearProblem(E, Ax), strategy.alg_E).to_host()[:, 0]
+
+        def op_minus(x):  # A \ (E x)
+            Ex = _matmul(E, DeviceMatrix.from_host(x))
+            return solve_block(BlockLinearProblem(A, Ex), strategy.alg_A).to_host()[:, 0]
+
+        R_plus = _arnoldi_ritz(op_plus, b0, strategy.k_plus, "E^-1 A")
+        R_minus = _arnoldi_ritz(op_minus, b0, strategy.k_minus, "A^-1 E")
+        R = list(R_plus) + [1.0 / v for v in R_minus]
+        return _ListIterator(Shifts.heuristic(R, strategy.nshifts))
+    if isinstance(strategy, Cyclic):
+        inner = strategy.inner
+        vals = _take_many(shifts_init(inner, prob)) if isinstance(inner, Shifts.Strategy) else list(inner)
+        return _CycleIterator(vals)
+    if isinstance(strategy, Wrapped):
+        it = shifts_init(strategy.inner, prob)
+        if isinstance(it, BufferedIterator):
+            return BufferedIterator(WrappedIterator(strategy.func, it.generator))
+        return WrappedIterator(strategy.func, it)
+    return strategy.init(prob)  # custom strategy protocol (Shifts.jl:13-67)
+
+
+# =============================================================================================
+# GALE / ADI (src/lyapunov/types.jl, residual.jl, adi.jl)
+# =============================================================================================
+class GALEProblem:  # types.jl:10-16   A'XE + E'XA = -C
+    def __init__(self, E, A, C):
+        self.E, self.A, self.C = E, A, C
+
+
+class ADI:  # types.jl:20-32
+    def __init__(self, inner_alg=None, *, maxiters=100, reltol=None, abstol=None, shifts=None,
+                 ignore_initial_guess=False, compression_interval=10, compression=True, warn_convergence=True):
+        self.maxiters, self.reltol, self.abstol = maxiters, reltol, abstol
+        self.shifts = shifts if shifts is not None else Projection(2)
+        self.ignore_initial_guess = ignore_initial_guess
+        self.inner_alg = inner_alg if inner_alg is not None else Backslash()
+        self.compression_interval, self.compression = compression_interval, compression
+        self.warn_convergence = warn_convergence
+
+
+def _device_problem(prob: GALEProblem) -> GALEProblem:
+    """Accept host inputs (scipy E/A, NumPy factors) like the reference accepts SparseMatrixCSC/Matrix
+    and move them to the GPU once."""
+    E, A, Cm = prob.E, prob.A, prob.C
+    if sp.issparse(E):
+        if not sp.issparse(A):
+            raise TypeError("E is sparse but A is not")
+        backend().ensure_pencil(E, A)
+        E, A = PencilCombo(0.0, 1.0), PencilCombo(1.0, 0.0)
+    if not isinstance(E, PencilCombo) or not isinstance(A, (PencilCombo, LowRankUpdate)):
+        raise TypeError("GALEProblem: E/A must be scipy sparse matrices or device operators")
+    if (E.a, E.e) != (0.0, 1.0):
+        raise ValueError("GALEProblem: E must be the uploaded mass matrix")
+    Cm.to_device_()
+    return GALEProblem(E, A, Cm)
+
+
+def residual(prob: GALEProblem, val: LDLt) -> LDLt:
+    """src/lyapunov/residual.jl:3-31."""
+    E, A, Cm = prob.E, prob.A, prob.C
+    if val.iszero():
+        return LDLt(list(Cm.alphas), [L.copy() for L in Cm.Ls], [np.array(D, order="F") for D in Cm.Ds])
+    alpha, G, S = Cm.destructure()
+    beta, L, D = val.destructure()
+    n_G, n_0 = G.ncols, L.ncols
+    dim = n_G + 2 * n_0
+    be = backend()
+    R = DeviceMatrix.empty(dim)
+    be.check(be.lib.dre_mat_copy(be.h, R.cols(0, n_G).view, G.view))
+    spmm("E", L, 1.0, R.cols(n_G, n_G + n_0), 0.0)
+    AtL = _adj_matmul(A, L)
+    be.check(be.lib.dre_mat_copy(be.h, R.cols(n_G + n_0, dim).view, AtL.view))
+    T = np.zeros((dim, dim), order="F")
+    T[:n_G, :n_G] = alpha * S
+    T[n_G:n_G + n_0, n_G + n_0:] = beta * D
+    T[n_G + n_0:, n_G:n_G + n_0] = T[n_G:n_G + n_0, n_G + n_0:]
+    return compress_(LDLt([1.0], [R], [T]))
+
+
+class ADICache:
+    """src/lyapunov/adi.jl:5-21."""
+
+    def __init__(self, **kw):
+        self.last_compression = 0
+        self.__dict__.update(kw)
+
+    def __iter__(self):  # adi.jl:91-95
+        done = False
+        while not done:
+            step_(self)
+            done = isdone(self)
+            yield self
+
+
+def init(prob: GALEProblem, alg: ADI, *, initial_guess=None, initial_residual=None, abstol=None,
+         observer=None) -> ADICache:
+    """CommonSolve.init(::GALEProblem{<:LDLt}, ::ADI) -- src/lyapunov/adi.jl:29-69."""
+    _observe(observer, "observe_gale_start", prob, alg)
+    prob = _device_problem(prob)
+    Cm = prob.C
+    if alg.ignore_initial_guess or initial_guess is None:
+        initial_guess = Cm.zero()
+    initial_guess.to_device_()
+    if initial_residual is None:
+        initial_residual = residual(prob, initial_guess)
+    X = initial_guess
+    _, R, _T = initial_residual.destructure()
+    residual_norm = norm(initial_residual)
+    oracle = shifts_init(alg.shifts, prob)
+    oracle.update(X, R)
+    reltol = alg.reltol if alg.reltol is not None else prob.A.shape[0] * EPS
+    if abstol is None:
+        abstol = alg.abstol if alg.abstol is not None else reltol * norm(Cm)
+    _observe(observer, "observe_gale_step", 0, X, initial_residual, residual_norm)
+    increment = initial_residual.zero()
+    return ADICache(prob=prob, alg=alg, abstol=abstol, observer=observer, shifts_oracle=oracle, shifts=[], X=X,
+                    increment=increment, residual=initial_residual, residual_norm=residual_norm)
+
+
+def isdone(cache: ADICache) -> bool:
+    """adi.jl:130-141."""
+    if cache.residual_norm <= cache.abstol:
+        return True
+    niters = len(cache.shifts)
+    if niters > 0 and cache.increment.iszero():
+        return True
+    return niters >= cache.alg.maxiters
+
+
+def compress_cache_(cache: ADICache):
+    """adi.jl:143-147."""
+    compress_(cache.X)
+    cache.last_compression = 0
+
+
+def _fused_inner(alg: ADI) -> bool:
+    return isinstance(alg.inner_alg, (Backslash, ShermanMorrisonWoodbury))
+
+
+def perform_single_step_(cache: ADICache, mu: float):
+    """adi.jl:149-179: V = (A' + mu E')^-1 R; X += -2 mu alpha V T V'; R -= 2 mu E' V."""
+    be = backend()
+    prob, alg = cache.prob, cache.alg
+    alpha, R, T = cache.residual.destructure()
+    if _fused_inner(alg):
+        # one C-ABI call: numeric LDL^T of A_s + mu E, block sweeps for [R, K'], SMW, SpMM update
+        _set_operator(prob.A, transpose=True)
+        V = DeviceMatrix.empty(R.ncols)
+        be.check(be.lib.dre_adi_step(be.h, mu, 0.0, R.view, V.view, View(-1, 0, 0)))
+    else:
+        F = (prob.A.adjoint().plus_sparse(PencilCombo(0.0, mu)) if isinstance(prob.A, LowRankUpdate)
+             else prob.A.T + PencilCombo(0.0, mu))
+        V = alg.inner_alg.solve(BlockLinearProblem(F, R))
+        spmm("E", V, -2.0 * mu, R, 1.0)
+    cache.increment = (-2.0 * mu * alpha) * LDLt([1.0], [V], [T])
+    cache.X = cache.X + cache.increment
+    cache.last_compression += 1
+    cache.shifts_oracle.update(cache.X, R, V)
+
+
+def perform_double_step_(cache: ADICache, mu: complex):
+    """adi.jl:181-225 (complex pair; note (conj(mu) E)' == mu E', adi.jl:195)."""
+    be = backend()
+    prob, alg = cache.prob, cache.alg
+    alpha, R, T = cache.residual.destructure()
+    mu_next = cache.shifts_oracle.take()
+    assert np.isclose(mu_next, np.conj(mu)), (mu, mu_next)
+    cache.shifts.append(complex(mu_next))
+    _observe(cache.observer, "observe_gale_metadata", "ADI shifts", mu_next)
+    if _fused_inner(alg):
+        _set_operator(prob.A, transpose=True)
+        V1 = DeviceMatrix.empty(R.ncols)
+        V2 = DeviceMatrix.empty(R.ncols)
+        be.check(be.lib.dre_adi_step(be.h, mu.real, mu.imag, R.view, V1.view, V2.view))
+    else:
+        F = (prob.A.adjoint().plus_sparse(PencilCombo(0.0, 0.0)) if isinstance(prob.A, LowRankUpdate)
+             else prob.A.T)
+        Vr, Vi = alg.inner_alg.solve(BlockLinearProblem(F, R), mu=mu)
+        d = mu.real / mu.imag
+        V1 = Vr.copy()
+        be.check(be.lib.dre_mat_axpby(be.h, math.sqrt(2.0) * d, Vi.view, math.sqrt(2.0), V1.view))
+        V2 = Vi.copy()
+        be.check(be.lib.dre_mat_axpby(be.h, 0.0, View(-1, 0, 0), math.sqrt(2 * d * d + 2), V2.view))
+        spmm("E", V1, -2.0 * math.sqrt(2.0) * mu.real, R, 1.0)
+    cache.increment = (-2.0 * mu.real * alpha) * (LDLt([1.0], [V1], [T]) + LDLt([1.0], [V2], [T]))
+    cache.X = cache.X + cache.increment
+    cache.last_compression += 2
+    cache.shifts_oracle.update(cache.X, R, V1, V2)
+
+
+def step_(cache: ADICache):
+    """CommonSolve.step!(::ADICache) -- adi.jl:97-128."""
+    alg, abstol, observer = cache.alg, cache.abstol, cache.observer
+    mu = cache.shifts_oracle.take()
+    cache.shifts.append(complex(mu))
+    _observe(observer, "observe_gale_metadata", "ADI shifts", mu)
+    if np.imag(mu) == 0:
+        perform_single_step_(cache, float(np.real(mu)))
+    else:
+        perform_double_step_(cache, complex(mu))
+    if alg.compression and cache.last_compression >= alg.compression_interval:
+        compress_cache_(cache)
+    res_norm = cache.residual_norm = norm(cache.residual)
+    i = len(cache.shifts)
+    _observe(observer, "observe_gale_step", i, cache.X, cache.residual, res_norm)
+    if res_norm <= abstol:
+        return
+    if i < alg.maxiters:
+        return
+    _observe(observer, "observe_gale_failed")
+    if alg.warn_convergence:
+        warnings.warn(f"ADI did not converge: residual={res_norm} abstol={abstol} maxiters={alg.maxiters}")
+
+
+def solve_(cache: ADICache) -> LDLt:
+    """CommonSolve.solve!(::ADICache) -- adi.jl:71-89."""
+    while not isdone(cache):
+        step_(cache)
+    if cache.alg.compression and cache.last_compression > 0:
+        compress_cache_(cache)
+    iters = len(cache.shifts)
+    _observe(cache.observer, "observe_gale_done", iters, cache.X, cache.residual, cache.residual_norm)
+    return cache.X
+
+
+# =============================================================================================
+# Riccati drivers (src/riccati/*.jl)
+# =============================================================================================
+class GDREProblem:  # riccati/types.jl:11-20
+    def __init__(self, E, A, B, C, X0, tspan):
+        self.E, self.A, self.B, self.C, self.X0, self.tspan = E, A, B, C, X0, tspan
+
+
+class DRESolution:  # riccati/types.jl:35-39
+    def __init__(self, X, K, t):
+        self.X, self.K, self.t = X, K, t
+
+
+class GAREProblem:  # riccati/types.jl:46-51
+    def __init__(self, E, A, G, Q):
+        self.E, self.A, self.G, self.Q = E, A, G, Q
+
+
+class Ros1:  # DifferentialRiccatiEquations.jl:55-57
+    def __init__(self, inner_alg=None):
+        self.inner_alg = inner_alg
+
+
+class Ros2:  # DifferentialRiccatiEquations.jl:58-60
+    def __init__(self, inner_alg=None):
+        self.inner_alg = inner_alg
+
+
+def quadratic_forcing(_i, residual_norm):  # newton.jl:165
+    return min(0.1, 0.9 * residual_norm)
+
+
+def superlinear_forcing(i, _r):  # newton.jl:156
+    return 1.0 / (i ** 3 + 1)
+
+
+class Newton:  # riccati/types.jl:95-106
+    def __init__(self, inner_alg=None, *, maxiters=5, reltol=None, abstol=None, inexact=True, inexact_hybrid=True,
+                 inexact_forcing=quadratic_forcing, linesearch=True):
+        self.inner_alg = inner_alg if inner_alg is not None else ADI()
+        self.maxiters, self.reltol, self.abstol = maxiters, reltol, abstol
+        self.inexact, self.inexact_hybrid = inexact, inexact_hybrid
+        self.inexact_forcing, self.linesearch = inexact_forcing, linesearch
+
+
+def _tstops(tspan, dt):
+    t0, tf = tspan
+    nsteps = int(math.floor((tf - t0) / dt + 1e-12))
+    return [t0 + i * dt for i in range(nsteps + 1)]
+
+
+def _feedback(Bd: DeviceMatrix, X: LDLt):
+    """lowrank_ros1.jl:25-28 / 53-56: K = (B'L D alpha)(L'E); returns the n x k panel E'L too."""
+    alpha, L, D = X.destructure()
+    BtLD = gemm_tn(Bd, L) @ D
+    if alpha != 1:
+        BtLD = BtLD * alpha
+    EtL = spmm("E", L)
+    Kt = gemm_nn(EtL, BtLD.T)  # K' = E'L (B'LD)'
+    return alpha, L, D, BtLD, EtL, Kt
+
+
+def _upload_gdre(prob: GDREProblem):
+    be = backend()
+    be.ensure_pencil(prob.E, prob.A)
+    Bd = _as_device(np.asarray(prob.B))
+    Ctd = _as_device(np.asarray(prob.C).T)
+    prob.X0.to_device_()
+    return be, Bd, Ctd
+
+
+def _solve_ros1(prob: GDREProblem, alg: Ros1, *, dt, save_state, observer) -> DRESolution:
+    """src/riccati/lowrank_ros1.jl:3-66."""
+    _observe(observer, "observe_gdre_start", prob, alg)
+    be, Bd, Ctd = _upload_gdre(prob)
+    E, A = PencilCombo(0.0, 1.0), PencilCombo(1.0, 0.0)
+    q = Ctd.ncols
+    X = prob.X0
+    tstops = _tstops(prob.tspan, dt)
+    Xs = [X]
+    alpha, L, D, BtLD, EtL, Kt = _feedback(Bd, X)
+    Ks = [Kt.to_host().T.copy()]
+    _observe(observer, "observe_gdre_step", tstops[0], X, Ks[-1])
+    inner_alg = alg.inner_alg if alg.inner_alg is not None else ADI()
+    for i in range(1, len(tstops)):
+        tau = tstops[i - 1] - tstops[i]
+        F = LowRankUpdate(A - E / (2 * tau), -1.0, Bd, Kt)  # lr_update(A - E/(2tau), -1, B, K), :39
+        G = hcat([Ctd, EtL])  # :42
+        S = _dcat([np.eye(q), BtLD.T @ BtLD + D / tau])  # :43
+        R = compress_(LDLt([1.0], [G], [S]))  # :44
+        lyap = GALEProblem(E, F, R)
+        X = solve(lyap, inner_alg, observer=observer, initial_guess=X)  # :47-49
+        if save_state:
+            Xs.append(X)
+        alpha, L, D, BtLD, EtL, Kt = _feedback(Bd, X)
+        Ks.append(Kt.to_host().T.copy())
+        _observe(observer, "observe_gdre_step", tstops[i], X, Ks[-1])
+    if not save_state:
+        Xs.append(X)
+    _observe(observer, "observe_gdre_done")
+    return DRESolution(Xs, Ks, tstops)
+
+
+def _solve_ros2(prob: GDREProblem, alg: Ros2, *, dt, save_state, observer) -> DRESolution:
+    """src/riccati/lowrank_ros2.jl:3-89."""
+    _observe(observer, "observe_gdre_start", prob, alg)
+    be, Bd, Ctd = _upload_gdre(prob)
+    E, A = PencilCombo(0.0, 1.0), PencilCombo(1.0, 0.0)
+    q = Ctd.ncols
+    X = prob.X0
+    tstops = _tstops(prob.tspan, dt)
+    gamma = 1 + 1 / math.sqrt(2)
+    Xs = [X]
+    alpha, L, D, BtLD, EtL, Kt = _feedback(Bd, X)
+    Ks = [Kt.to_host().T.copy()]
+    _observe(observer, "observe_gdre_step", tstops[0], X, Ks[-1])
+    inner_alg = alg.inner_alg if alg.inner_alg is not None else ADI()
+    for i in range(1, len(tstops)):
+        tau = tstops[i - 1] - tstops[i]
+        gt = gamma * tau
+        F = LowRankUpdate(gt * A - E / 2, 1.0 / (-gt), Bd, Kt)  # :41
+        AtL = spmm("A", L)
+        G = hcat([Ctd, AtL, EtL])  # :44
+        n_G, n_L = G.ncols, L.ncols
+        S = np.zeros((n_G, n_G), order="F")
+        S[:q, :q] = np.eye(q)
+        S[q:q + n_L, n_G - n_L:] = D
+        S[n_G - n_L:, q:q + n_L] = D
+        S[n_G - n_L:, n_G - n_L:] = -(BtLD.T @ BtLD)
+        R1 = compress_(LDLt([1.0], [G], [S]))
+        K1 = solve(GALEProblem(E, F, R1), inner_alg, observer=observer)  # :57-58
+        kappa, T1, D1 = K1.destructure()
+        BtT1D1 = gemm_tn(Bd, T1) @ D1
+        if kappa != 1:
+            BtT1D1 = BtT1D1 * kappa
+        G2 = spmm("E", T1)
+        S2 = (tau ** 2 * BtT1D1).T @ BtT1D1 + (2 - 1 / gamma) * D1
+        R2 = LDLt([1.0], [G2], [np.asfortranarray(S2)])
+        K2 = solve(GALEProblem(E, F, R2), inner_alg, observer=observer)  # :68-69
+        X = X + ((2 - 1 / (2 * gamma)) * tau) * K1 + (-tau / 2) * K2  # :72
+        if save_state:
+            Xs.append(X)
+        alpha, L, D, BtLD, EtL, Kt = _feedback(Bd, X)
+        Ks.append(Kt.to_host().T.copy())
+        _observe(observer, "observe_gdre_step", tstops[i], X, Ks[-1])
+    if not save_state:
+        Xs.append(X)
+    _observe(observer, "observe_gdre_done")
+    return DRESolution(Xs, Ks, tstops)
+
+
+def gare_residual(prob: GAREProblem, X: LDLt, *, AtL=None, EtL=None, BtLD=None, DLtGLD=None, _dev=None) -> LDLt:
+    """src/riccati/residual.jl:6-52."""
+    be = backend()
+    Bd, Ctd = _dev
+    Q, G = prob.Q, prob.G
+    if X.iszero():
+        return LDLt(list(Q.alphas), [L.copy() for L in Q.Ls], [np.array(D, order="F") for D in Q.Ds])
+    gamma, _Ct, S = Q.destructure()
+    beta, _B, Rinv = G.destructure()
+    alpha, L, D = X.destructure()
+    h, zk = Ctd.ncols, L.ncols
+    dim = h + 2 * zk
+    AtL = AtL if AtL is not None else spmm("A", L)
+    EtL = EtL if EtL is not None else spmm("E", L)
+    if DLtGLD is None:
+        if BtLD is None:
+            BtLD = gemm_tn(Bd, L) @ D
+            if alpha * beta != 1:
+                BtLD = BtLD * (alpha * beta)
+        DLtGLD = BtLD.T @ Rinv @ BtLD
+    R = hcat([Ctd, AtL, EtL])
+    T = np.zeros((dim, dim), order="F")
+    T[:h, :h] = gamma * S
+    T[h:h + zk, h + zk:] = alpha * D
+    T[h + zk:, h:h + zk] = T[h:h + zk, h + zk:]
+    T[h + zk:, h + zk:] = -DLtGLD
+    return compress_(LDLt([1.0], [R], [T]))
+
+
+def _solve_newton(prob: GAREProblem, alg: Newton, *, observer=None) -> LDLt:
+    """src/riccati/newton.jl:3-147."""
+    _observe(observer, "observe_gare_start", prob, alg)
+    be = backend()
+    be.ensure_pencil(prob.E, prob.A)
+    prob.G.to_device_()
+    prob.Q.to_device_()
+    a0, Bm, _ = prob.G.destructure()
+    assert a0 == 1, "Scaled prob.G not yet implemented"
+    a0, Ctm, _ = prob.Q.destructure()
+    assert a0 == 1, "Scaled prob.Q not yet implemented"
+    Bd, Ctd = Bm, Ctm  # device panels (lowrank() uploaded them)
+    E, A = PencilCombo(0.0, 1.0), PencilCombo(1.0, 0.0)
+    res = prob.Q
+    res_norm = norm(res)
+    n = be.n
+    reltol = alg.reltol if alg.reltol is not None else n * EPS
+    abstol = alg.abstol if alg.abstol is not None else reltol * res_norm
+    X = LDLt([1.0], [DeviceMatrix.empty(0)], [np.zeros((0, 0))])
+    i = 0
+    X_prev = None
+    inner_alg = alg.inner_alg
+    inner_reltol = inner_alg.reltol if getattr(inner_alg, "reltol", None) is not None else reltol / 10
+    m, q = Bd.ncols, Ctd.ncols
+
+    def aux(Xc):
+        alpha, L, D = Xc.destructure()
+        EtL = spmm("E", L) if L.ncols else DeviceMatrix.empty(0)
+        BtLD = gemm_tn(Bd, L) @ D if L.ncols else np.zeros((m, 0))
+        if alpha != 1:
+            BtLD = BtLD * alpha
+        DLtGLD = BtLD.T @ BtLD
+        Kt = gemm_nn(EtL, BtLD.T) if L.ncols else None
+        return EtL, BtLD, DLtGLD, Kt
+
+    while True:
+        EtL, BtLD, DLtGLD, Kt = aux(X)
+        res = gare_residual(prob, X, EtL=EtL, DLtGLD=DLtGLD, _dev=(Bd, Ctd))
+        res_norm_prev = res_norm
+        res_norm = norm(res)
+        if i > 0 and alg.linesearch:
+            a_ = 0.1
+            if res_norm > (1 - a_) * res_norm_prev:
+                X_tilde = X
+                beta_ = 0.5
+                lam = beta_
+                while True:
+                    X = (1 - lam) * X_prev + lam * X_tilde
+                    res = gare_residual(prob, X, _dev=(Bd, Ctd))
+                    res_norm = norm(res)
+                    if res_norm < (1 - lam * a_) * res_norm_prev:
+                        EtL, BtLD, DLtGLD, Kt = aux(X)
+                        break
+                    lam *= beta_
+                    if lam < EPS:
+                        warnings.warn("Line search failed; using un-modified iterate")
+                        lam = 1.0
+                        X = X_tilde
+                        break
+                _observe(observer, "observe_gare_metadata", "line search", lam)
+        _observe(observer, "observe_gare_step", i, X, res, res_norm)
+        if res_norm <= abstol:
+            break
+        if i >= alg.maxiters:
+            _observe(observer, "observe_gare_failed")
+            warnings.warn("Newton method did not converge")
+            break
+        i += 1
+        if Kt is None:  # X == 0: K = 0
+            Kt = DeviceMatrix.from_host(np.zeros((n, m)))
+            EtXB = DeviceMatrix.from_host(np.zeros((n, m)))
+        else:
+            EtXB = gemm_nn(EtL, BtLD.T)  # E'L (B'LD)' = E'XB
+        F = LowRankUpdate(A, -1.0, Bd, Kt)  # :103
+        G = hcat([Ctd, EtXB])  # :106-111
+        S = _dcat([np.eye(q), np.eye(m)])
+        RHS = LDLt([1.0], [G], [S])
+        lyap = GALEProblem(E, F, RHS)
+        if alg.inexact:
+            eta = alg.inexact_forcing(i, res_norm)
+            inner_abstol = eta * res_norm
+            if alg.inexact_hybrid:
+                classical_abstol = inner_reltol * norm(lyap.C)
+                switch_back = classical_abstol > inner_abstol
+                _observe(observer, "observe_gare_metadata", "inexact", not switch_back)
+                if switch_back:
+                    inner_abstol = classical_abstol
+            else:
+                _observe(observer, "observe_gare_metadata", "inexact", True)
+        else:
+            inner_abstol = inner_reltol * norm(lyap.C)
+        X_prev = X
+        X = solve(lyap, inner_alg, abstol=inner_abstol, initial_guess=X_prev, observer=observer)
+    _observe(observer, "observe_gare_done", i, X, res, res_norm)
+    return X
+
+
+def solve(prob, alg, **kw):
+    """CommonSolve.solve for every problem/algorithm pair of the hot path
+    (src/DifferentialRiccatiEquations.jl:78-94 for GDRE; solve = solve!(init(...)) for GALE)."""
+    if isinstance(prob, GALEProblem) and isinstance(alg, ADI):
+        return solve_(init(prob, alg, **kw))
+    if isinstance(prob, GDREProblem):
+        dt = kw.pop("dt")
+        save_state = kw.pop("save_state", False)
+        observer = kw.pop("observer", None)
+        if isinstance(alg, Ros1):
+            return _solve_ros1(prob, alg, dt=dt, save_state=save_state, observer=observer)
+        if isinstance(alg, Ros2):
+            return _solve_ros2(prob, alg, dt=dt, save_state=save_state, observer=observer)
+    if isinstance(prob, GAREProblem) and isinstance(alg, Newton):
+        return _solve_newton(prob, alg, **kw)
+    if isinstance(prob, BlockLinearProblem):
+        return solve_block(prob, alg, **kw)
+    raise TypeError(f"solve: unsupported combination {type(prob).__name__}, {type(alg).__name__}")
+
+
+def upload_pencil(E, A):
+    """Upload E, A (runs the symbolic analysis once).  Needed before ``lowrank`` can place factors on
+    the device when building X0 / G / Q for a problem."""
+    backend().ensure_pencil(E, A)

@@ -19,7 +19,8 @@ EXPORTED_SYMBOLS = [
     "dre_symbolic_export", "dre_create", "dre_destroy", "dre_sync", "dre_set_pencil", "dre_get_symbolic_info",
     "dre_mat_create", "dre_mat_free", "dre_mat_upload", "dre_mat_download", "dre_mat_copy", "dre_mat_axpby",
     "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_shift_solve", "dre_adi_step",
-    "dre_ldlt_norm", "dre_ldlt_compress", "dre_rrqr", "dre_stats_reset", "dre_stats_get",
+    "dre_ldlt_norm", "dre_ldlt_compress", "dre_rrqr", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
+    "dre_stats_get",
 ]
 
 
@@ -44,8 +45,12 @@ class SymbolicInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("factorizations", C.c_int64), ("solves", C.c_int64),
+                ("spmms", C.c_int64), ("grams", C.c_int64), ("tallgemms", C.c_int64),
                 ("ms_factor", C.c_double), ("ms_solve", C.c_double), ("ms_spmm", C.c_double),
-                ("ms_gram", C.c_double), ("ms_tallgemm", C.c_double)]
+                ("ms_gram", C.c_double), ("ms_tallgemm", C.c_double),
+                ("flops_factor", C.c_double), ("flops_gram", C.c_double), ("flops_tallgemm", C.c_double),
+                ("flops_solve", C.c_double), ("bytes_solve", C.c_double), ("bytes_spmm", C.c_double),
+                ("bytes_gram", C.c_double), ("bytes_tallgemm", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -96,6 +101,8 @@ def load():
     lib.dre_ldlt_compress.argtypes = [p, i32, C.POINTER(View), C.POINTER(pdbl), pi64, pdbl, dbl, View, pdbl,
                                       C.POINTER(i32)]
     lib.dre_rrqr.argtypes = [p, i32, C.POINTER(View), dbl, dbl, View, pdbl, i64, C.POINTER(i32)]
+    lib.dre_timer_start.argtypes = [p]
+    lib.dre_timer_stop.argtypes = [p, pdbl]
     lib.dre_stats_reset.argtypes = [p, i32]
     lib.dre_stats_get.argtypes = [p, C.POINTER(Stats)]
     for name in EXPORTED_SYMBOLS:
@@ -205,6 +212,14 @@ class Context:
         info = SymbolicInfo()
         self.check(self.lib.dre_get_symbolic_info(self.h, C.byref(info)))
         return info.as_dict()
+
+    def timer_start(self):
+        self.check(self.lib.dre_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0.0)
+        self.check(self.lib.dre_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def stats_reset(self, timing=False):
         self.check(self.lib.dre_stats_reset(self.h, 1 if timing else 0))

@@ -92,6 +92,11 @@ struct dre_context {
     DBuf<double> btw, sol;
     int32_t* d_errflag = nullptr;
 
+    // key of the numeric factorization currently held in d_L (re-used when the shift repeats)
+    bool fact_valid = false;
+    double fact_a = 0, fact_re = 0, fact_im = 0;
+    int fact_tw = 0;
+
     // operator F = a A + e E + inv(alpha) U Vt'
     double op_a = 1.0, op_e = 0.0, op_alpha = 1.0;
     dre_view op_U{-1, 0, 0}, op_Vt{-1, 0, 0};
@@ -110,6 +115,7 @@ struct dre_context {
     dre_stats stats{};
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t tev0 = nullptr, tev1 = nullptr;
 };
 
 namespace {
@@ -208,6 +214,9 @@ int gram_dev(dre_context* c, const double* X, int64_t ldx, int a, const double* 
     launch_gram(X, ldx, a, Y, ldy, b, n, roww, c->gram_partial.p, plan, out1, ld1, out2, ld2, c->st,
                 &c->stats.kernel_launches);
     CU(cudaGetLastError());
+    c->stats.grams++;
+    c->stats.flops_gram += 2.0 * (double)n * a * b;
+    c->stats.bytes_gram += 8.0 * (double)n * ((X == Y && a == b) ? a : (a + b));
     return DRE_OK;
 }
 
@@ -216,6 +225,9 @@ int tall_gemm(dre_context* c, double alpha, const double* X, int64_t ldx, int a,
     Timer t(c, &c->stats.ms_tallgemm);
     launch_tall_gemm(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, c->st, &c->stats.kernel_launches);
     CU(cudaGetLastError());
+    c->stats.tallgemms++;
+    c->stats.flops_tallgemm += 2.0 * (double)n * a * b;
+    c->stats.bytes_tallgemm += 8.0 * (double)n * (a + (beta == 0.0 ? 1.0 : 2.0) * b);
     return DRE_OK;
 }
 
@@ -247,6 +259,7 @@ int factor(dre_context* c, T emu) {
     }
     CU(cudaGetLastError());
     c->stats.factorizations++;
+    c->stats.flops_factor += S.flops * (sizeof(T) == sizeof(double) ? 1.0 : 4.0);
     return DRE_OK;
 }
 
@@ -271,6 +284,11 @@ int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
     }
     CU(cudaGetLastError());
     c->stats.solves++;
+    {   // 2*nnz(L)*w (factor read once per sweep) + 4*n*r_tot*w (RHS read+write per sweep)
+        const double w = (double)sizeof(T);
+        c->stats.bytes_solve += 2.0 * (double)S.nnz_L * w + 4.0 * (double)S.n * nrhs * w;
+        c->stats.flops_solve += 4.0 * (double)S.nnz_L * nrhs * (sizeof(T) == sizeof(double) ? 1.0 : 4.0);
+    }
     return DRE_OK;
 }
 
@@ -290,11 +308,18 @@ int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_
                        n, c->st, &c->stats.kernel_launches);
     T emu;
     make_emu(c->op_e, mu_re, mu_im, emu);
-    int rc = factor<T>(c, emu);
-    if (rc) return rc;
+    const int tw = (int)(sizeof(T) / sizeof(double));  // 1 or 2 doubles per element
+    int rc = DRE_OK;
+    if (!(c->fact_valid && c->fact_a == c->op_a && c->fact_re == c->op_e + mu_re && c->fact_im == mu_im &&
+          c->fact_tw == tw)) {
+        c->fact_valid = false;
+        rc = factor<T>(c, emu);
+        if (rc) return rc;
+        c->fact_valid = true;
+        c->fact_a = c->op_a; c->fact_re = c->op_e + mu_re; c->fact_im = mu_im; c->fact_tw = tw;
+    }
     rc = solve_sweeps<T>(c, W, ldw, nrhs);
     if (rc) return rc;
-    const int tw = (int)(sizeof(T) / sizeof(double));  // 1 or 2 doubles per element
     T* Sol = nullptr;
     if (m > 0) {
         CU(c->btw.ensure((size_t)m * nrhs * tw));
@@ -341,7 +366,7 @@ struct RRState {
     double* RT = nullptr;  // ktot x ldrt row-major: coefficients of every input column in the basis
     int64_t ldrt = 0;
     double scale2 = 0.0;   // largest squared column norm seen so far
-    double drop_rel = 1e-11, drop_abs = 0.0;
+    double drop_rel = 3e-15, drop_abs = 0.0;
     int rounds = 0;
 };
 
@@ -381,7 +406,7 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
             rc = gram_dev(c, Pw, PB, pb, Pw, PB, pb, n, nullptr, c->gbuf.p, PB, nullptr, 0);
             if (rc) return rc;
             const double drop = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
-            launch_pivchol(c->gbuf.p, PB, pb, drop * drop, 1e-8, c->wsel.p, c->ibuf.p, c->small.p, c->st,
+            launch_pivchol(c->gbuf.p, PB, pb, drop * drop, 1e-12, c->wsel.p, c->ibuf.p, c->small.p, c->st,
                            &c->stats.kernel_launches);
             if (s.rho + PB > s.qcap) return fail(c, DRE_ERR_STATE, "rank-revealing QR: basis capacity exceeded");
             rc = tall_gemm(c, 1.0, Pw, PB, pb, c->wsel.p, PB, 0, 0.0, Qt, PB, PB, n);
@@ -391,6 +416,14 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
             launch_pivchol(c->gbuf2.p, PB, PB, 0.01, 0.0, c->wsel2.p, c->ibuf.p + 2, c->small.p + 2, c->st,
                            &c->stats.kernel_launches);
             rc = tall_gemm(c, 1.0, Qt, PB, PB, c->wsel2.p, PB, 0, 0.0, s.Q + s.rho, s.ldq, PB, n);
+            if (rc) return rc;
+            // coefficients of the panel in the new directions (candidate columns beyond nsel2 are zero) and
+            // removal of that part, so that the basis is complete even if this was the last round
+            CU(c->cbuf.ensure((size_t)PB * std::max(s.rho, PB)));
+            rc = gram_dev(c, Pw, PB, pb, s.Q + s.rho, s.ldq, PB, n, nullptr, c->cbuf.p, PB,
+                          s.RT + (int64_t)(rt_row0 + c0) * s.ldrt + s.rho, s.ldrt);
+            if (rc) return rc;
+            rc = tall_gemm(c, -1.0, s.Q + s.rho, s.ldq, PB, c->cbuf.p, PB, 1, 1.0, Pw, PB, pb, n);
             if (rc) return rc;
             int32_t* hi = (int32_t*)(c->h_pinned + 8);
             CU(cudaMemcpyAsync(hi, c->ibuf.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
@@ -520,6 +553,8 @@ int32_t dre_create(int32_t device, dre_context** out) {
     if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    cudaEventCreate(&c->tev0);
+    cudaEventCreate(&c->tev1);
     if (cusolverDnCreate(&c->cusolver) != CUSOLVER_STATUS_SUCCESS) return bail("cusolverDnCreate failed");
     cusolverDnSetStream(c->cusolver, c->st);
     e = cudaMalloc((void**)&c->d_errflag, sizeof(int32_t));
@@ -542,6 +577,7 @@ static void release_pencil(dre_context* c) {
     for (int i = 0; i < 2; ++i) if (c->d_U[i]) cudaFree(c->d_U[i]);
     c->d_L = c->d_dblk = c->d_U[0] = c->d_U[1] = nullptr;
     c->has_pencil = false;
+    c->fact_valid = false;
 }
 
 int32_t dre_destroy(dre_context* c) {
@@ -560,6 +596,8 @@ int32_t dre_destroy(dre_context* c) {
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tev0) cudaEventDestroy(c->tev0);
+    if (c->tev1) cudaEventDestroy(c->tev1);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
     return DRE_OK;
@@ -797,6 +835,9 @@ int32_t dre_spmm(dre_context* c, int32_t op, double alpha, dre_view X, double be
     launch_spmm(c->d_csr_ptr, c->d_csr_col, val, c->sym.n, alpha, vptr(c, X), vld(c, X), beta, vptr(c, Y), vld(c, Y),
                 X.ncols, c->st, &c->stats.kernel_launches);
     CU(cudaGetLastError());
+    c->stats.spmms++;
+    c->stats.bytes_spmm += (double)c->sym.csr_col.size() * 12.0 + (double)(c->sym.n + 1) * 4.0 +
+                           8.0 * (double)c->sym.n * X.ncols * (beta == 0.0 ? 2.0 : 3.0);
     return DRE_OK;
 }
 
@@ -868,6 +909,9 @@ int32_t dre_adi_step(dre_context* c, double mu_re, double mu_im, dre_view R, dre
     launch_spmm(c->d_csr_ptr, c->d_csr_col, c->d_csr_e, c->sym.n, coef, vptr(c, V1), vld(c, V1), 1.0, vptr(c, R),
                 vld(c, R), R.ncols, c->st, &c->stats.kernel_launches);
     CU(cudaGetLastError());
+    c->stats.spmms++;
+    c->stats.bytes_spmm += (double)c->sym.csr_col.size() * 12.0 + (double)(c->sym.n + 1) * 4.0 +
+                           8.0 * (double)c->sym.n * R.ncols * 3.0;
     return DRE_OK;
 }
 
@@ -965,7 +1009,7 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     if (ktot == 0) return DRE_OK;
     const int64_t n = c->sym.n;
     RRState s;
-    if ((rc = rr_setup(c, s, ktot, 1e-11, 0.0))) return rc;
+    if ((rc = rr_setup(c, s, ktot, 3e-15, 0.0))) return rc;
     std::vector<double> signs(ktot, 1.0);
     int row0 = 0;
     for (int t = 0; t < nterms; ++t) {
@@ -1090,6 +1134,23 @@ int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double d
     for (int i = 0; i < ktot; ++i)
         for (int j = 0; j < rho; ++j) Rt[i + (int64_t)j * ldr] = c->h_pinned[(int64_t)i * s.ldrt + j];
     return check_errflag(c);
+}
+
+int32_t dre_timer_start(dre_context* c) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaEventRecord(c->tev0, c->st));
+    return DRE_OK;
+}
+
+int32_t dre_timer_stop(dre_context* c, double* ms) {
+    if (!c || !ms) return fail(c, DRE_ERR_ARG, "null argument");
+    CU(cudaEventRecord(c->tev1, c->st));
+    CU(cudaEventSynchronize(c->tev1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, c->tev0, c->tev1));
+    *ms = f;
+    return DRE_OK;
 }
 
 int32_t dre_stats_reset(dre_context* c, int32_t enable_event_timing) {

@@ -145,9 +145,17 @@ DRE_API int32_t dre_rrqr(dre_context* ctx, int32_t nviews, const dre_view* views
 typedef struct {
     int64_t kernel_launches;    /* launches of this library's own kernels since the last reset */
     int64_t factorizations;     /* numeric factorizations */
-    int64_t solves;             /* block solves */
+    int64_t solves;             /* block solves (forward + backward sweep pairs) */
+    int64_t spmms, grams, tallgemms;
     double ms_factor, ms_solve, ms_spmm, ms_gram, ms_tallgemm; /* CUDA-event times when timing is enabled */
+    /* algorithmic work (SURVEY.md section 8d formulas), accumulated per call */
+    double flops_factor, flops_gram, flops_tallgemm, flops_solve;
+    double bytes_solve, bytes_spmm, bytes_gram, bytes_tallgemm;
 } dre_stats;
+/* CUDA-event stopwatch on the context's own stream (torch events cannot see this stream):
+ * start records an event; stop records a second one, synchronises and returns the elapsed ms. */
+DRE_API int32_t dre_timer_start(dre_context* ctx);
+DRE_API int32_t dre_timer_stop(dre_context* ctx, double* ms);
 DRE_API int32_t dre_stats_reset(dre_context* ctx, int32_t enable_event_timing);
 DRE_API int32_t dre_stats_get(dre_context* ctx, dre_stats* out);
 
