@@ -39,47 +39,46 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region, read through NVML in a low-rate background
+    thread (an `nvidia-smi -lms 200` loop was measured to slow this launch-heavy workload by 2x: every
+    query contends for the driver lock the kernel launches need)."""
 
-    def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index: int, period_s: float = 1.0):
+        self.gpu, self.period, self.samples, self.stop_flag = gpu_index, period_s, [], threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _loop(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, mx, rs))
+                self.stop_flag.wait(self.period)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        sm = sorted(s[0] for s in self.samples)
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted({name for _, _, r in self.samples for b, name in bits.items() if r & b})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "samples": len(sm), "how": "NVML, 1 s period"}
 
 
 def _problem(n):
@@ -172,7 +171,8 @@ def run_ours(args):
     tK = tW + K * DT
     sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    if not args.no_clocks:
+        sampler.start()
     be.ctx.stats_reset(False)
     be.ctx.timer_start()
     t_wall = time.perf_counter()
@@ -391,6 +391,7 @@ def main():
     ap.add_argument("--n", type=int, default=79841)
     ap.add_argument("--cpu-iters", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true")
     args = ap.parse_args()
     os.environ.setdefault("OPENBLAS_NUM_THREADS", str(min(os.cpu_count() or 1, 16)))
     if args.impl == "reference":

@@ -251,8 +251,8 @@ int factor(dre_context* c, T emu) {
             launch_extend_add<T>(c->dS, c->d_ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, Ucur, Uprev, c->st,
                                  &c->stats.kernel_launches);
         for (size_t sidx = 0; sidx < lw.steps.size(); ++sidx)
-            launch_front_step<T>(c->dS, c->d_front_items + lw.steps[sidx].first, lw.steps[sidx].second, (int)sidx, L,
-                                 dblk, c->d_errflag, c->st, &c->stats.kernel_launches);
+            launch_front<T>(c->dS, c->d_front_items + lw.steps[sidx].first, lw.steps[sidx].second, L, dblk,
+                            c->d_errflag, c->st, &c->stats.kernel_launches);
         if (lw.schur_count > 0)
             launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dblk, Ucur, c->st,
                             &c->stats.kernel_launches);
@@ -462,7 +462,8 @@ int32_t dre_symbolic_create(int64_t n, const int64_t* Ecp, const int64_t* Eri, c
     dre_symbolic* s = new (std::nothrow) dre_symbolic();
     if (!s) return fail(nullptr, DRE_ERR_LIB, "out of host memory");
     AnalyzeOptions opt;
-    if (leaf_size > 0) opt.leaf_size = leaf_size;
+    if (leaf_size > 0) opt.leaf_size = leaf_size & 0xffff;
+    if ((leaf_size >> 16) > 0) opt.max_snode = leaf_size >> 16;  // upper half-word: supernode width cap
     std::string e;
     try {
         e = analyze(n, Ecp, Eri, Enz, Acp, Ari, Anz, base, opt, s->sym);
@@ -619,6 +620,7 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     c->op_U = c->op_Vt = dre_view{-1, 0, 0};
     AnalyzeOptions opt;
     opt.leaf_size = 32;
+    opt.max_snode = 32;  // the kernels assume a single 32-column block per supernode
     std::string e;
     try {
         e = analyze(n, Ecp, Eri, Enz, Acp, Ari, Anz, base, opt, c->sym);
@@ -684,7 +686,7 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
             if (S.child_ptr[J + 1] > S.child_ptr[J]) ea_parents.push_back(J);
         }
         lw.ea_count = (int)ea_parents.size() - lw.ea_begin;
-        lw.ea_gy = std::min(32, std::max(1, max_f / 32));
+        lw.ea_gy = std::min(64, std::max(1, max_f / 8));
         const int nsteps = (max_s + 31) / 32;
         for (int step = 0; step < nsteps; ++step) {
             const int begin = (int)front_items.size();
@@ -694,6 +696,7 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
                 const int k0 = step * 32;
                 if (k0 >= s) continue;
                 const int nb = std::min(32, s - k0);
+                if (s > 32) return fail(c, DRE_ERR_STATE, "internal error: supernode wider than 32 columns");
                 const int below = f - k0 - nb;
                 const int nslab = std::max(1, (below + 95) / 96);
                 for (int sl = 0; sl < nslab; ++sl) front_items.push_back(make_int2(J, sl));

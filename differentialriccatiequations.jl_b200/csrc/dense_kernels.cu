@@ -97,16 +97,37 @@ __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, int6
     }
 }
 
-__global__ void k_reduce_partials(const double* __restrict__ partial, int nsplit, int a, int b, double* out1,
-                                  int64_t ld1, double* out2, int64_t ld2) {
+// Each warp reduces 4 consecutive output elements: lane = (split lane 0..7) x (element 0..3), so every
+// load instruction reads full 32-byte sectors; fixed split assignment + fixed-shape shuffle tree keep the
+// result deterministic, and hundreds of splits are no longer summed in one serial loop.
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ partial, int nsplit, int a,
+                                                         int b, double* out1, int64_t ld1, double* out2,
+                                                         int64_t ld2) {
     const int64_t total = (int64_t)a * b;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int k = 0; k < nsplit; ++k) s += partial[(int64_t)k * total + idx];  // fixed order: deterministic
-        const int i = (int)(idx / b), j = (int)(idx % b);
-        if (out1) out1[(int64_t)i * ld1 + j] = s;
-        if (out2) out2[(int64_t)i * ld2 + j] += s;
+    const int lane = threadIdx.x & 31;
+    const int e = lane & 3, kl = lane >> 2;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp0 * 4; base < total; base += nwarps * 4) {
+        const int64_t idx = base + e;
+        double s0 = 0.0, s1 = 0.0;
+        if (idx < total) {
+            int k = kl;
+            for (; k + 8 < nsplit; k += 16) {
+                s0 += partial[(int64_t)k * total + idx];
+                s1 += partial[(int64_t)(k + 8) * total + idx];
+            }
+            if (k < nsplit) s0 += partial[(int64_t)k * total + idx];
+        }
+        double s = s0 + s1;
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (kl == 0 && idx < total) {
+            const int i = (int)(idx / b), j = (int)(idx % b);
+            if (out1) out1[(int64_t)i * ld1 + j] = s;
+            if (out2) out2[(int64_t)i * ld2 + j] += s;
+        }
     }
 }
 
@@ -115,10 +136,11 @@ GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
     int tiles = ((a + GT - 1) / GT) * ((b + GT - 1) / GT);
     if (tiles < 1) tiles = 1;
     int64_t chunks = (n + GK - 1) / GK;
-    int want = std::max(1, (4 * sm_count + tiles - 1) / tiles);   // ~4 CTAs per SM
+    int want = std::max(1, (2 * sm_count + tiles - 1) / tiles);   // ~2 CTAs per SM
+    if (a <= 16 && b >= 64) want = std::max(1, 4 * sm_count / ((b + 255) / 256));  // skinny kernel: thread per column
     int64_t maxsplit = std::max<int64_t>(1, chunks / 8);          // at least 8 chunks (128 rows) per split
     int nsplit = (int)std::min<int64_t>(want, maxsplit);
-    nsplit = std::min(nsplit, 1024);
+    nsplit = std::min(nsplit, 320);
     int64_t cps = (chunks + nsplit - 1) / nsplit;
     p.rows_per_split = cps * GK;
     p.nsplit = (int)((n + p.rows_per_split - 1) / p.rows_per_split);
@@ -127,15 +149,66 @@ GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
     return p;
 }
 
+// Skinny variant (a <= MMAX columns on the X side, e.g. B' [Z, Y] of the SMW correction with m = 7):
+// the 64x64 DMMA tile would be 9x padding, so each thread owns one Y column and keeps the a partial
+// sums in registers; Y rows are read fully coalesced, X rows are warp-broadcast.
+template <int MMAX>
+__global__ void __launch_bounds__(256) k_gram_skinny(const double* __restrict__ X, int64_t ldx, int a,
+                                                     const double* __restrict__ Y, int64_t ldy, int b, int64_t n,
+                                                     double* __restrict__ partial, int64_t rows_per_split) {
+    const int64_t row_begin = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t row_end = min(n, row_begin + rows_per_split);
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    double acc[MMAX];
+#pragma unroll
+    for (int i = 0; i < MMAX; ++i) acc[i] = 0.0;
+    if (j < b) {
+        int64_t row = row_begin;
+        for (; row + 4 <= row_end; row += 4) {
+            double y[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) y[q] = Y[(row + q) * ldy + j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double* xr = X + (row + q) * ldx;
+#pragma unroll
+                for (int i = 0; i < MMAX; ++i)
+                    if (i < a) acc[i] = fma(xr[i], y[q], acc[i]);
+            }
+        }
+        for (; row < row_end; ++row) {
+            const double y = Y[row * ldy + j];
+            const double* xr = X + row * ldx;
+#pragma unroll
+            for (int i = 0; i < MMAX; ++i)
+                if (i < a) acc[i] = fma(xr[i], y, acc[i]);
+        }
+        double* P = partial + (int64_t)blockIdx.y * a * b;
+#pragma unroll
+        for (int i = 0; i < MMAX; ++i)
+            if (i < a) P[(int64_t)i * b + j] = acc[i];
+    }
+}
+
 void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t ldy, int b, int64_t n,
                  const double* roww, double* partial, const GramPlan& plan, double* out1, int64_t ld1,
                  double* out2, int64_t ld2, cudaStream_t st, int64_t* launches) {
     if (a <= 0 || b <= 0) return;
+    if (a <= 16 && roww == nullptr && b >= 64) {
+        dim3 grid((b + 255) / 256, plan.nsplit);
+        if (a <= 8) k_gram_skinny<8><<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, partial, plan.rows_per_split);
+        else k_gram_skinny<16><<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, partial, plan.rows_per_split);
+        const int64_t total = (int64_t)a * b;
+        int rb = (int)std::min<int64_t>((total + 31) / 32, 148 * 8);
+        k_reduce_partials<<<rb, 256, 0, st>>>(partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
+        if (launches) *launches += 2;
+        return;
+    }
     const int tiles_a = (a + GT - 1) / GT, tiles_b = (b + GT - 1) / GT;
     dim3 grid(tiles_a * tiles_b, plan.nsplit);
     k_gram<<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, roww, partial, tiles_b, plan.rows_per_split);
     const int64_t total = (int64_t)a * b;
-    int rb = (int)std::min<int64_t>((total + 255) / 256, 1024);
+    int rb = (int)std::min<int64_t>((total + 31) / 32, 148 * 8);  // 8 warps per CTA, 4 output elements per warp
     k_reduce_partials<<<rb, 256, 0, st>>>(partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
     if (launches) *launches += 2;
 }
@@ -364,26 +437,34 @@ __global__ void __launch_bounds__(256) k_pivchol(const double* __restrict__ G, i
     }
     __syncthreads();
     for (int j = 0; j < pb; ++j) {
-        if (tid == 0) {
-            int p = -1;
-            double m = -1.0;
-            for (int i = 0; i < pb; ++i)
-                if (d[i] > m) { m = d[i]; p = i; }
-            s_p = (p >= 0 && m >= s_thr && m > 0.0) ? p : -1;
+        // pivot = arg max of the remaining Schur diagonal (warp 0; ties -> smallest index)
+        if (tid < 32) {
+            double v = (tid < pb) ? d[tid] : -1.0;
+            int ix = tid;
+            const double v2 = (tid + 32 < pb) ? d[tid + 32] : -1.0;
+            if (v2 > v) { v = v2; ix = tid + 32; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, v, off);
+                const int oi = __shfl_down_sync(0xffffffffu, ix, off);
+                if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+            }
+            if (tid == 0) s_p = (v >= s_thr && v > 0.0) ? ix : -1;
         }
         __syncthreads();
         const int p = s_p;
         if (p < 0) break;
         const double cjj = sqrt(d[p]);
-        if (tid < pb) {
-            const int i = tid;
-            if (i == p) {
-                C[i][j] = cjj;
-            } else if (d[i] >= 0.0) {  // not yet selected
-                double v = A[i][p];
-                for (int t = 0; t < j; ++t) v -= C[i][t] * C[p][t];
-                v /= cjj;
-                C[i][j] = v;
+        {   // column j of the factor: 4 threads per row split the dot product
+            const int i = tid >> 2, q = tid & 3;
+            double acc = 0.0;
+            if (i < pb && i != p && d[i] >= 0.0)
+                for (int t = q; t < j; t += 4) acc += C[i][t] * C[p][t];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0 && i < pb) {
+                if (i == p) C[i][j] = cjj;
+                else if (d[i] >= 0.0) C[i][j] = (A[i][p] - acc) / cjj;
             }
         }
         __syncthreads();

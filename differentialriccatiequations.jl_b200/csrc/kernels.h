@@ -90,11 +90,11 @@ template <class T>
 void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* Ucur,
                        const T* Uprev, cudaStream_t st, int64_t* launches);
 
-// one block-column step of the left-looking blocked LDL^T on every front of a level
+// panel factorization (LDL^T of the <=32-column diagonal block + L21 slab solve) of every front of a level
 // items: (J, slab) pairs
 template <class T>
-void launch_front_step(const DevSymbolic& S, const int2* items, int nitems, int step, T* L, T* dblk,
-                       int32_t* errflag, cudaStream_t st, int64_t* launches);
+void launch_front(const DevSymbolic& S, const int2* items, int nitems, T* L, T* dblk, int32_t* errflag,
+                  cudaStream_t st, int64_t* launches);
 
 // Schur complement  U_J -= L21 D L21'  (lower triangle, 64x64 tiles); items: (J, ti, tj)
 template <class T>

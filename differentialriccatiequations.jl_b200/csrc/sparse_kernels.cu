@@ -93,101 +93,43 @@ void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparent
 }
 
 // ------------------------------------------------------------------------------------------
-// one block-column step of the blocked left-looking LDL^T of every front in a level.
-// CTA (J, slab): rows = 32 diagonal-block rows (recomputed by every CTA of the front) + 96 slab
-// rows; C = P[rows, k0:k0+nb] - sum_{k<k0} L[rows,k] d_k L[k0+b,k];  factor the diagonal block in
-// shared memory, solve the slab against it.
+// panel factorization of every front of a level (all supernodes have at most 32 columns: wider
+// dissection blocks are split into chains by the symbolic analysis).  CTA (J, slab): the 32x32
+// diagonal block is factored (LDL^T, no pivoting) in shared memory by every CTA of the front, the CTA's
+// 96-row slab of L21 is solved against it; slab 0 also stores the pivots and the INVERSE of the unit
+// lower factor into the side array, so that the block solves are plain multiplications.
 // ------------------------------------------------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(256) k_front_step(DevSymbolic S, const int2* __restrict__ items, int step,
-                                                    T* L, T* dblk, int32_t* errflag) {
-    constexpr int KC = 16;
+__global__ void __launch_bounds__(256) k_front(DevSymbolic S, const int2* __restrict__ items, T* L, T* dblk,
+                                               int32_t* errflag) {
     extern __shared__ __align__(16) unsigned char dre_smem_raw[];
     T* smp = reinterpret_cast<T*>(dre_smem_raw);
-    T (*As)[128] = reinterpret_cast<T (*)[128]>(smp);                 smp += KC * 128;
-    T (*Bs)[NB] = reinterpret_cast<T (*)[NB]>(smp);                   smp += KC * NB;
     T (*Ds)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
     T (*Ss)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += SLAB * (NB + 1);
+    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
     T* tmp = smp;
     const int2 item = items[blockIdx.x];
     const int J = item.x, slab = item.y;
     const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
-    const int k0 = step * NB;
-    const int nb = min(NB, s - k0);
     T* P = L + S.panel_off[J];
-    T* Dk = dblk + S.dblk_off[J];
     const int tid = threadIdx.x;
-    const int tr = tid & 31, tc = tid >> 5;
-    const int slab_row0 = k0 + nb + slab * SLAB;
+    const int row0 = s + slab * SLAB;
 
-    // global row of tile row m (or -1)
-    auto grow = [&](int m) -> int {
-        if (m < NB) return (m < nb) ? k0 + m : -1;
-        const int r = slab_row0 + (m - NB);
-        return (r < f) ? r : -1;
-    };
-
-    T acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = zero<T>();
-
-    for (int kk = 0; kk < k0; kk += KC) {
-        // A tile: 128 rows x 16 k
-        {
-            const int m = tid & 127;
-            const int g = grow(m);
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int k = (tid >> 7) + 2 * it;
-                As[k][m] = (g >= 0) ? P[(int64_t)g + (int64_t)(kk + k) * f] : zero<T>();
-            }
-        }
-        __syncthreads();
-        // B tile = diagonal-block rows scaled by the pivots d_k of the (finished) previous columns
-        for (int idx = tid; idx < KC * NB; idx += 256) {
-            const int k = idx >> 5, b = idx & 31;
-            const int kg = kk + k;
-            const T d = Dk[(int64_t)(kg >> 5) * 1024 + (kg & 31) * 33];
-            Bs[k][b] = mul(As[k][b], d);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            T av[4], bv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = As[k][tr + 32 * i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tc * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) fma_acc(acc[i][j], av[i], bv[j]);
-        }
-        __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx & 31, c = idx >> 5;
+        Ds[i][c] = (i < s && c < s) ? P[(int64_t)i + (int64_t)c * f] : zero<T>();
     }
-    // C = P - acc  -> shared
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = tr + 32 * i;
-        const int g = grow(m);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = tc * 4 + j;
-            T v = zero<T>();
-            if (g >= 0 && c < nb) v = sub(P[(int64_t)g + (int64_t)(k0 + c) * f], acc[i][j]);
-            if (m < NB) Ds[m][c] = v;
-            else Ss[m - NB][c] = v;
-        }
+    for (int idx = tid; idx < SLAB * NB; idx += 256) {
+        const int m = idx % SLAB, c = idx / SLAB;
+        Ss[m][c] = (row0 + m < f && c < s) ? P[(int64_t)(row0 + m) + (int64_t)c * f] : zero<T>();
     }
     __syncthreads();
     // unblocked LDL^T of the diagonal block (lower part of Ds)
-    for (int j = 0; j < nb; ++j) {
+    for (int j = 0; j < s; ++j) {
         const T d = Ds[j][j];
         if (tid == 0 && is_bad(d)) atomicExch(errflag, 1);
         const T rd = recip(d);
-        if (tid > j && tid < nb) {
+        if (tid > j && tid < s) {
             const T w = Ds[tid][j];
             tmp[tid] = w;
             Ds[tid][j] = mul(w, rd);
@@ -195,51 +137,64 @@ __global__ void __launch_bounds__(256) k_front_step(DevSymbolic S, const int2* _
         __syncthreads();
         for (int idx = tid; idx < NB * NB; idx += 256) {
             const int i = idx >> 5, k = idx & 31;
-            if (k > j && i >= k && i < nb) Ds[i][k] = sub(Ds[i][k], mul(Ds[i][j], tmp[k]));
+            if (k > j && i >= k && i < s) Ds[i][k] = sub(Ds[i][k], mul(Ds[i][j], tmp[k]));
         }
         __syncthreads();
     }
     // slab rows: y_c = S[c] - sum_{t<c} y_t Ld[c][t];  L[c] = y_c / d_c
     if (tid < SLAB) {
         const int m = tid;
-        if (slab_row0 + m < f) {
-            for (int c = 0; c < nb; ++c) {
+        if (row0 + m < f) {
+            for (int c = 0; c < s; ++c) {
                 T v = Ss[m][c];
                 for (int t = 0; t < c; ++t) v = sub(v, mul(Ss[m][t], Ds[c][t]));
                 Ss[m][c] = v;
             }
-            for (int c = 0; c < nb; ++c) Ss[m][c] = mul(Ss[m][c], recip(Ds[c][c]));
+            for (int c = 0; c < s; ++c) Ss[m][c] = mul(Ss[m][c], recip(Ds[c][c]));
+        }
+    } else if (slab == 0 && tid >= 128 && tid < 128 + NB) {
+        // inverse of the unit lower factor, one column per thread (warp 4)
+        const int c = tid - 128;
+        if (c < s) {
+            for (int i = c + 1; i < s; ++i) {
+                T v = Ds[i][c];  // Ld[i][c] * z[c], z[c] = 1
+                for (int k = c + 1; k < i; ++k) fma_acc(v, Ds[i][k], Li[k][c]);
+                Li[i][c] = sub(zero<T>(), v);
+            }
         }
     }
     __syncthreads();
     for (int idx = tid; idx < SLAB * NB; idx += 256) {
         const int m = idx % SLAB, c = idx / SLAB;
-        const int r = slab_row0 + m;
-        if (r < f && c < nb) P[(int64_t)r + (int64_t)(k0 + c) * f] = Ss[m][c];
+        if (row0 + m < f && c < s) P[(int64_t)(row0 + m) + (int64_t)c * f] = Ss[m][c];
     }
     if (slab == 0) {
-        T* Db = Dk + (int64_t)step * 1024;
+        T* Db = dblk + S.dblk_off[J];
         for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int i = idx & 31, j = idx >> 5;
+            const int i = idx & 31, c = idx >> 5;
             T v = zero<T>();
-            if (i < nb && j < nb && i >= j) v = Ds[i][j];
-            else if (i == j) v = one<T>();  // padding pivots of a partial block (never used)
-            Db[i + j * 32] = v;
+            if (i < s && c < s) {
+                if (i > c) v = Li[i][c];
+                else if (i == c) v = Ds[i][i];
+            } else if (i == c) {
+                v = one<T>();
+            }
+            Db[i + c * 32] = v;
         }
     }
 }
 
 template <class T>
-void launch_front_step(const DevSymbolic& S, const int2* items, int nitems, int step, T* L, T* dblk,
-                       int32_t* errflag, cudaStream_t st, int64_t* launches) {
+void launch_front(const DevSymbolic& S, const int2* items, int nitems, T* L, T* dblk, int32_t* errflag,
+                  cudaStream_t st, int64_t* launches) {
     if (nitems <= 0) return;
-    const int smem = (int)sizeof(T) * (16 * 128 + 16 * NB + NB * (NB + 1) + SLAB * (NB + 1) + NB);
+    const int smem = (int)sizeof(T) * (2 * NB * (NB + 1) + SLAB * (NB + 1) + NB);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_front_step<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_front<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
     }
-    k_front_step<T><<<nitems, 256, smem, st>>>(S, items, step, L, dblk, errflag);
+    k_front<T><<<nitems, 256, smem, st>>>(S, items, L, dblk, errflag);
     if (launches) *launches += 1;
 }
 
@@ -274,7 +229,7 @@ __global__ void __launch_bounds__(256) k_schur(DevSymbolic S, const int4* __rest
             if (kg < s) {
                 if (i0 + m < u) av = P[(int64_t)(s + i0 + m) + (int64_t)kg * f];
                 if (j0 + m < u) {
-                    const T d = Dk[(int64_t)(kg >> 5) * 1024 + (kg & 31) * 33];
+                    const T d = Dk[kg * 33];
                     bv = mul(P[(int64_t)(s + j0 + m) + (int64_t)kg * f], d);
                 }
             }
@@ -320,18 +275,21 @@ void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* 
 
 // ------------------------------------------------------------------------------------------
 // forward sweep of one level:  y_J = L11^-1 (b_J + children),  t_J = children - L21 y_J
-// CTA = (supernode, 32 RHS columns).  W and the update-vector buffers are row-major with the same
-// leading dimension and column indexing.
+// CTA = (supernode, CW right-hand-side columns).  W is row-major (n x ldw); the update vectors t_J are
+// column-major per supernode (u_J contiguous per RHS column) inside the level's ping-pong buffer.
 // ------------------------------------------------------------------------------------------
-template <class T>
-__global__ void __launch_bounds__(256) k_fwd_level(DevSymbolic S, const int32_t* __restrict__ sns,
-                                                   const T* __restrict__ L, const T* __restrict__ dblk, T* W,
-                                                   int64_t ldw, int nrhs, T* tcur, const T* __restrict__ tprev) {
-    __shared__ T xb[NB][NB + 1];
-    __shared__ T Ld[NB][NB + 1];
+template <class T, int CW>
+__global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
+                                             const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs, T* tcur,
+                                             const T* __restrict__ tprev) {
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    T* smp = reinterpret_cast<T*>(dre_smem_raw);
+    T (*xb)[CW + 1] = reinterpret_cast<T (*)[CW + 1]>(smp);           smp += NB * (CW + 1);
+    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*Ls)[64 + 1] = reinterpret_cast<T (*)[64 + 1]>(smp);
     const int J = sns[blockIdx.x];
-    const int c0 = blockIdx.y * 32;
-    const int ncw = min(32, nrhs - c0);
+    const int c0 = blockIdx.y * CW;
+    const int ncw = min(CW, nrhs - c0);
     const int first = S.sn_first[J];
     const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
     const T* P = L + S.panel_off[J];
@@ -339,9 +297,9 @@ __global__ void __launch_bounds__(256) k_fwd_level(DevSymbolic S, const int32_t*
     T* tJ = tcur + S.rhs_off[J] * ldw;
     const int tid = threadIdx.x;
 
-    for (int idx = tid; idx < u * 32; idx += 256) {
-        const int i = idx >> 5, cc = idx & 31;
-        if (cc < ncw) tJ[(int64_t)i * ldw + c0 + cc] = zero<T>();
+    for (int idx = tid; idx < u * ncw; idx += 256) {
+        const int cc = idx / u, r = idx - cc * u;
+        tJ[(int64_t)(c0 + cc) * u + r] = zero<T>();
     }
     __syncthreads();
     for (int ci = S.child_ptr[J]; ci < S.child_ptr[J + 1]; ++ci) {
@@ -349,56 +307,73 @@ __global__ void __launch_bounds__(256) k_fwd_level(DevSymbolic S, const int32_t*
         const int uc = sn_u(S, c);
         const int32_t* rel = S.relmap + S.sn_rowptr[c];
         const T* tch = tprev + S.rhs_off[c] * ldw;
-        for (int idx = tid; idx < uc * 32; idx += 256) {
-            const int i = idx >> 5, cc = idx & 31;
-            if (cc < ncw) {
-                const int pr = rel[i];
-                const T val = tch[(int64_t)i * ldw + c0 + cc];
-                T* t = (pr < s) ? (W + (int64_t)(first + pr) * ldw + c0 + cc)
-                                : (tJ + (int64_t)(pr - s) * ldw + c0 + cc);
-                *t = add(*t, val);
-            }
+        for (int idx = tid; idx < uc * ncw; idx += 256) {
+            const int cc = idx / uc, i = idx - cc * uc;
+            const int pr = rel[i];
+            const T val = tch[(int64_t)(c0 + cc) * uc + i];
+            T* t = (pr < s) ? (W + (int64_t)(first + pr) * ldw + c0 + cc) : (tJ + (int64_t)(c0 + cc) * u + (pr - s));
+            *t = add(*t, val);
         }
         __syncthreads();
     }
-    for (int jb = 0; jb < s; jb += NB) {
-        const int nb = min(NB, s - jb);
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int i = idx >> 5, cc = idx & 31;
-            xb[i][cc] = (i < nb && cc < ncw) ? W[(int64_t)(first + jb + i) * ldw + c0 + cc] : zero<T>();
-            const int li = idx & 31, lk = idx >> 5;
-            Ld[li][lk] = Dk[(int64_t)(jb >> 5) * 1024 + li + lk * 32];
+    for (int idx = tid; idx < NB * CW; idx += 256) {
+        const int i = idx / CW, cc = idx - i * CW;
+        xb[i][cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
+    }
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx & 31, k = idx >> 5;
+        Li[i][k] = (k < i) ? Dk[i + k * 32] : zero<T>();
+    }
+    __syncthreads();
+    {   // y = Linv x  (unit lower): thread (row i, column group)
+        constexpr int CPT = CW / 8;
+        const int i = tid & 31, cg = tid >> 5;
+        T acc[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[c] = xb[i][cg * CPT + c];
+        for (int k = 0; k < i; ++k) {
+            const T l = Li[i][k];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, xb[k][cg * CPT + c]);
         }
         __syncthreads();
-        if (tid < ncw) {
-            for (int i = 1; i < nb; ++i) {
-                T v = xb[i][tid];
-                for (int k = 0; k < i; ++k) v = sub(v, mul(Ld[i][k], xb[k][tid]));
-                xb[i][tid] = v;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) xb[i][cg * CPT + c] = acc[c];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NB * CW; idx += 256) {
+        const int i = idx / CW, cc = idx - i * CW;
+        if (i < s && cc < ncw) W[(int64_t)(first + i) * ldw + c0 + cc] = xb[i][cc];
+    }
+    {   // t_J -= L21 y, 64-row tiles of L21 staged in shared memory
+        constexpr int CPT = CW / 4;
+        const int rl = tid & 63, cg = tid >> 6;
+        for (int r0 = 0; r0 < u; r0 += 64) {
+            __syncthreads();
+            for (int idx = tid; idx < NB * 64; idx += 256) {
+                const int rr = idx & 63, k = idx >> 6;
+                Ls[k][rr] = (r0 + rr < u && k < s) ? P[(int64_t)(s + r0 + rr) + (int64_t)k * f] : zero<T>();
+            }
+            __syncthreads();
+            T acc[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[c] = zero<T>();
+            for (int k = 0; k < s; ++k) {
+                const T l = Ls[k][rl];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, xb[k][cg * CPT + c]);
+            }
+            if (r0 + rl < u) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int cc = cg * CPT + c;
+                    if (cc < ncw) {
+                        T* t = tJ + (int64_t)(c0 + cc) * u + r0 + rl;
+                        *t = sub(*t, acc[c]);
+                    }
+                }
             }
         }
-        __syncthreads();
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int i = idx >> 5, cc = idx & 31;
-            if (i < nb && cc < ncw) W[(int64_t)(first + jb + i) * ldw + c0 + cc] = xb[i][cc];
-        }
-        const int rt = tid & 63, ct = tid >> 6;
-        for (int row = jb + nb + rt; row < f; row += 64) {
-            T acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = zero<T>();
-            for (int k = 0; k < nb; ++k) {
-                const T l = P[(int64_t)row + (int64_t)(jb + k) * f];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) fma_acc(acc[j], l, xb[k][ct * 8 + j]);
-            }
-            T* tgt = (row < s) ? (W + (int64_t)(first + row) * ldw) : (tJ + (int64_t)(row - s) * ldw);
-            tgt += c0 + ct * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (ct * 8 + j < ncw) tgt[j] = sub(tgt[j], acc[j]);
-        }
-        __syncthreads();
     }
 }
 
@@ -406,27 +381,40 @@ template <class T>
 void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
                       int64_t ldw, int nrhs, T* tcur, const T* tprev, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    dim3 grid(nsns, (nrhs + 31) / 32);
-    k_fwd_level<T><<<grid, 256, 0, st>>>(S, sns, L, dblk, W, ldw, nrhs, tcur, tprev);
+    const int smem32 = (int)sizeof(T) * (NB * 33 + NB * (NB + 1) + NB * 65);
+    const int smem8 = (int)sizeof(T) * (NB * 9 + NB * (NB + 1) + NB * 65);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_fwd<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+        cudaFuncSetAttribute(k_fwd<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
+        attr_set = true;
+    }
+    if ((int64_t)nsns * ((nrhs + 31) / 32) >= 2 * 148) {
+        dim3 grid(nsns, (nrhs + 31) / 32);
+        k_fwd<T, 32><<<grid, 256, smem32, st>>>(S, sns, L, dblk, W, ldw, nrhs, tcur, tprev);
+    } else {
+        dim3 grid(nsns, (nrhs + 7) / 8);
+        k_fwd<T, 8><<<grid, 256, smem8, st>>>(S, sns, L, dblk, W, ldw, nrhs, tcur, tprev);
+    }
     if (launches) *launches += 1;
 }
 
 // ------------------------------------------------------------------------------------------
 // backward sweep of one level:  x_J = L11^-T (D^-1 y_J - L21^T x_struct)
 // ------------------------------------------------------------------------------------------
-template <class T>
-__global__ void __launch_bounds__(256) k_bwd_level(DevSymbolic S, const int32_t* __restrict__ sns,
-                                                   const T* __restrict__ L, const T* __restrict__ dblk, T* W,
-                                                   int64_t ldw, int nrhs) {
+template <class T, int CW>
+__global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
+                                             const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs) {
     extern __shared__ __align__(16) unsigned char dre_smem_raw[];
     T* smp = reinterpret_cast<T*>(dre_smem_raw);
     T (*Ls)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Xs)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*zb)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Ld)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);
+    T (*Xs)[CW + 1] = reinterpret_cast<T (*)[CW + 1]>(smp);           smp += NB * (CW + 1);
+    T (*zb)[CW + 1] = reinterpret_cast<T (*)[CW + 1]>(smp);           smp += NB * (CW + 1);
+    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);
+    constexpr int CPT = CW / 8;
     const int J = sns[blockIdx.x];
-    const int c0 = blockIdx.y * 32;
-    const int ncw = min(32, nrhs - c0);
+    const int c0 = blockIdx.y * CW;
+    const int ncw = min(CW, nrhs - c0);
     const int first = S.sn_first[J];
     const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
     const T* P = L + S.panel_off[J];
@@ -435,66 +423,63 @@ __global__ void __launch_bounds__(256) k_bwd_level(DevSymbolic S, const int32_t*
     const int tid = threadIdx.x;
     const int kq = tid & 31, cg = tid >> 5;
 
-    for (int jb = ((s - 1) / NB) * NB; jb >= 0; jb -= NB) {
-        const int nb = min(NB, s - jb);
-        T acc[4];
+    T acc[CPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = zero<T>();
-        for (int r0 = jb + nb; r0 < f; r0 += NB) {
-            for (int idx = tid; idx < NB * NB; idx += 256) {
-                {
-                    const int r = idx & 31, k = idx >> 5;
-                    Ls[r][k] = (r0 + r < f && k < nb) ? P[(int64_t)(r0 + r) + (int64_t)(jb + k) * f] : zero<T>();
-                }
-                {
-                    const int r = idx >> 5, cc = idx & 31;
-                    T v = zero<T>();
-                    if (r0 + r < f && cc < ncw) {
-                        const int lr = r0 + r;
-                        const int64_t g = (lr < s) ? (int64_t)(first + lr) : (int64_t)rows[lr - s];
-                        v = W[g * ldw + c0 + cc];
-                    }
-                    Xs[r][cc] = v;
-                }
-            }
-            __syncthreads();
+    for (int c = 0; c < CPT; ++c) acc[c] = zero<T>();
+    for (int r0 = 0; r0 < u; r0 += NB) {
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int r = idx & 31, k = idx >> 5;
+            Ls[r][k] = (r0 + r < u && k < s) ? P[(int64_t)(s + r0 + r) + (int64_t)k * f] : zero<T>();
+        }
+        for (int idx = tid; idx < NB * CW; idx += 256) {
+            const int r = idx / CW, cc = idx - r * CW;
+            T v = zero<T>();
+            if (r0 + r < u && cc < ncw) v = W[(int64_t)rows[r0 + r] * ldw + c0 + cc];
+            Xs[r][cc] = v;
+        }
+        __syncthreads();
 #pragma unroll 8
-            for (int r = 0; r < NB; ++r) {
-                const T l = Ls[r][kq];
+        for (int r = 0; r < NB; ++r) {
+            const T l = Ls[r][kq];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) fma_acc(acc[j], l, Xs[r][cg * 4 + j]);
-            }
-            __syncthreads();
-        }
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int i = idx >> 5, cc = idx & 31;
-            zb[i][cc] = (i < nb && cc < ncw) ? W[(int64_t)(first + jb + i) * ldw + c0 + cc] : zero<T>();
-            const int li = idx & 31, lk = idx >> 5;
-            Ld[li][lk] = Dk[(int64_t)(jb >> 5) * 1024 + li + lk * 32];
+            for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, Xs[r][cg * CPT + c]);
         }
         __syncthreads();
-        {
-            const T rd = (kq < nb) ? recip(Ld[kq][kq]) : zero<T>();
+    }
+    for (int idx = tid; idx < NB * CW; idx += 256) {
+        const int i = idx / CW, cc = idx - i * CW;
+        zb[i][cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
+    }
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx & 31, k = idx >> 5;
+        Li[i][k] = Dk[i + k * 32];  // strictly lower: Linv, diagonal: pivots
+    }
+    __syncthreads();
+    {
+        const T rd = (kq < s) ? recip(Li[kq][kq]) : zero<T>();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = cg * 4 + j;
-                zb[kq][c] = sub(mul(zb[kq][c], rd), acc[j]);
+        for (int c = 0; c < CPT; ++c) {
+            const int cc = cg * CPT + c;
+            zb[kq][cc] = sub(mul(zb[kq][cc], rd), acc[c]);
+        }
+    }
+    __syncthreads();
+    {   // x = Linv^T z : x_i = z_i + sum_{k>i} Linv[k][i] z_k
+        T xv[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) xv[c] = zb[kq][cg * CPT + c];
+        for (int k = kq + 1; k < s; ++k) {
+            const T l = Li[k][kq];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) fma_acc(xv[c], l, zb[k][cg * CPT + c]);
+        }
+        if (kq < s) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int cc = cg * CPT + c;
+                if (cc < ncw) W[(int64_t)(first + kq) * ldw + c0 + cc] = xv[c];
             }
         }
-        __syncthreads();
-        if (tid < ncw) {
-            for (int i = nb - 2; i >= 0; --i) {
-                T v = zb[i][tid];
-                for (int k = i + 1; k < nb; ++k) v = sub(v, mul(Ld[k][i], zb[k][tid]));
-                zb[i][tid] = v;
-            }
-        }
-        __syncthreads();
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int i = idx >> 5, cc = idx & 31;
-            if (i < nb && cc < ncw) W[(int64_t)(first + jb + i) * ldw + c0 + cc] = zb[i][cc];
-        }
-        __syncthreads();
     }
 }
 
@@ -502,14 +487,21 @@ template <class T>
 void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
                       int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    dim3 grid(nsns, (nrhs + 31) / 32);
-    const int smem = (int)sizeof(T) * 4 * NB * (NB + 1);
+    const int smem32 = (int)sizeof(T) * (2 * NB * (NB + 1) + 2 * NB * 33);
+    const int smem8 = (int)sizeof(T) * (2 * NB * (NB + 1) + 2 * NB * 9);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_bwd_level<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_bwd<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+        cudaFuncSetAttribute(k_bwd<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
         attr_set = true;
     }
-    k_bwd_level<T><<<grid, 256, smem, st>>>(S, sns, L, dblk, W, ldw, nrhs);
+    if ((int64_t)nsns * ((nrhs + 31) / 32) >= 2 * 148) {
+        dim3 grid(nsns, (nrhs + 31) / 32);
+        k_bwd<T, 32><<<grid, 256, smem32, st>>>(S, sns, L, dblk, W, ldw, nrhs);
+    } else {
+        dim3 grid(nsns, (nrhs + 7) / 8);
+        k_bwd<T, 8><<<grid, 256, smem8, st>>>(S, sns, L, dblk, W, ldw, nrhs);
+    }
     if (launches) *launches += 1;
 }
 
@@ -655,8 +647,7 @@ void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int m
     template void launch_assemble<T>(const DevSymbolic&, T*, double, T, cudaStream_t, int64_t*);                     \
     template void launch_extend_add<T>(const DevSymbolic&, const int32_t*, int, int, T*, T*, const T*, cudaStream_t, \
                                        int64_t*);                                                                    \
-    template void launch_front_step<T>(const DevSymbolic&, const int2*, int, int, T*, T*, int32_t*, cudaStream_t,    \
-                                       int64_t*);                                                                    \
+    template void launch_front<T>(const DevSymbolic&, const int2*, int, T*, T*, int32_t*, cudaStream_t, int64_t*);   \
     template void launch_schur<T>(const DevSymbolic&, const int4*, int, const T*, const T*, T*, cudaStream_t,        \
                                   int64_t*);                                                                         \
     template void launch_fwd_level<T>(const DevSymbolic&, const int32_t*, int, const T*, const T*, T*, int64_t, int, \

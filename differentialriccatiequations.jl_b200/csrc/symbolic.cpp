@@ -340,10 +340,24 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
     S.perm = dis.order;
     S.iperm.assign(n, -1);
     for (int64_t k = 0; k < n; ++k) S.iperm[S.perm[k]] = (int32_t)k;
-    S.nsn = (int32_t)dis.block_end.size();
-    S.sn_first.resize(S.nsn + 1);
-    S.sn_first[0] = 0;
-    for (int32_t J = 0; J < S.nsn; ++J) S.sn_first[J + 1] = dis.block_end[J];
+    // supernodes = dissection blocks, split into chains of at most max_snode columns (a chain link's
+    // parent is the next link: the within-separator dependency becomes tree levels, so every front has
+    // a single block column and the wide parts of its update parallelise over rows)
+    {
+        const int32_t cap = std::max(1, opt.max_snode);
+        S.sn_first.clear();
+        S.sn_first.push_back(0);
+        int32_t b0 = 0;
+        for (int32_t b1 : dis.block_end) {
+            const int32_t size = b1 - b0;
+            const int32_t nchunk = (size + cap - 1) / cap;
+            const int32_t csz = (size + nchunk - 1) / nchunk;
+            for (int32_t c = b0 + csz; c < b1; c += csz) S.sn_first.push_back(c);
+            S.sn_first.push_back(b1);
+            b0 = b1;
+        }
+        S.nsn = (int32_t)S.sn_first.size() - 1;
+    }
     std::vector<int32_t> sn_of(n);
     for (int32_t J = 0; J < S.nsn; ++J)
         for (int32_t c = S.sn_first[J]; c < S.sn_first[J + 1]; ++c) sn_of[c] = J;

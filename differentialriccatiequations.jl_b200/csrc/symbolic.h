@@ -63,7 +63,7 @@ struct Symbolic {
 
 struct AnalyzeOptions {
     int32_t leaf_size = 48;       // dissection stops below this many vertices
-    int32_t max_snode = 1 << 30;  // (unused cap; dissection blocks are kept whole)
+    int32_t max_snode = 1 << 30;  // dissection blocks wider than this are split into chains of supernodes
 };
 
 // E and A: CSC, index_base 0 or 1, 64-bit indices (Julia SparseMatrixCSC{Float64,Int64} zero-copy).
