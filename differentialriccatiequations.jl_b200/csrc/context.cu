@@ -70,12 +70,12 @@ struct dre_context {
     double* d_csr_e = nullptr;
     int32_t* d_level_sn = nullptr;
     // per-level work lists
-    struct LevelWork {
+    struct LevelWork {   // one per TOP level
         int sn_begin = 0, sn_count = 0;
         int ea_begin = 0, ea_count = 0, ea_gy = 1;
-        std::vector<std::pair<int, int>> steps;  // (offset into d_front_items, count)
+        int front_begin = 0, front_count = 0;
         int schur_begin = 0, schur_count = 0;
-        int64_t upd_elems = 0;
+        int64_t upd_begin = 0, upd_elems = 0;
     };
     std::vector<LevelWork> levels;
     int32_t* d_ea_parents = nullptr;
@@ -86,8 +86,8 @@ struct dre_context {
     // factor storage (sized for complex, reused for real)
     void* d_L = nullptr;
     void* d_dblk = nullptr;
-    void* d_U[2] = {nullptr, nullptr};
-    DBuf<unsigned char> tbuf[2];
+    void* d_U = nullptr;
+    DBuf<unsigned char> tbuf;
     DBuf<unsigned char> Wbuf;
     DBuf<double> btw, sol;
     int32_t* d_errflag = nullptr;
@@ -240,21 +240,21 @@ int factor(dre_context* c, T emu) {
     Timer t(c, &c->stats.ms_factor);
     T* L = (T*)c->d_L;
     T* dblk = (T*)c->d_dblk;
+    T* U = (T*)c->d_U;
     CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), c->st));
     launch_assemble<T>(c->dS, L, c->op_a, emu, c->st, &c->stats.kernel_launches);
-    for (int l = 0; l < S.nlevels; ++l) {
+    launch_factor_subtrees<T>(c->dS, L, dblk, U, c->d_errflag, c->st, &c->stats.kernel_launches);
+    for (int l = 0; l < S.ntoplevels; ++l) {
         const dre_context::LevelWork& lw = c->levels[l];
-        T* Ucur = (T*)c->d_U[l & 1];
-        const T* Uprev = (const T*)c->d_U[(l + 1) & 1];
-        if (lw.upd_elems > 0) CU(cudaMemsetAsync(Ucur, 0, (size_t)lw.upd_elems * sizeof(T), c->st));
+        if (lw.upd_elems > 0)
+            CU(cudaMemsetAsync(U + lw.upd_begin, 0, (size_t)lw.upd_elems * sizeof(T), c->st));
         if (lw.ea_count > 0)
-            launch_extend_add<T>(c->dS, c->d_ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, Ucur, Uprev, c->st,
+            launch_extend_add<T>(c->dS, c->d_ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, U, c->st,
                                  &c->stats.kernel_launches);
-        for (size_t sidx = 0; sidx < lw.steps.size(); ++sidx)
-            launch_front<T>(c->dS, c->d_front_items + lw.steps[sidx].first, lw.steps[sidx].second, L, dblk,
-                            c->d_errflag, c->st, &c->stats.kernel_launches);
+        launch_front<T>(c->dS, c->d_front_items + lw.front_begin, lw.front_count, L, dblk, c->d_errflag, c->st,
+                        &c->stats.kernel_launches);
         if (lw.schur_count > 0)
-            launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dblk, Ucur, c->st,
+            launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dblk, U, c->st,
                             &c->stats.kernel_launches);
     }
     CU(cudaGetLastError());
@@ -267,21 +267,22 @@ template <class T>
 int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
     const Symbolic& S = c->sym;
     Timer t(c, &c->stats.ms_solve);
-    for (int par = 0; par < 2; ++par)
-        CU(c->tbuf[par].ensure((size_t)std::max<int64_t>(S.max_rhs_level[par], 1) * ldw * sizeof(T)));
+    CU(c->tbuf.ensure((size_t)std::max<int64_t>(S.sum_u, 1) * ldw * sizeof(T)));
     const T* L = (const T*)c->d_L;
     const T* dblk = (const T*)c->d_dblk;
-    for (int l = 0; l < S.nlevels; ++l) {
+    T* tb = (T*)c->tbuf.p;
+    launch_fwd_subtrees<T>(c->dS, L, dblk, W, ldw, nrhs, tb, c->st, &c->stats.kernel_launches);
+    for (int l = 0; l < S.ntoplevels; ++l) {
         const dre_context::LevelWork& lw = c->levels[l];
-        launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, dblk, W, ldw, nrhs,
-                            (T*)c->tbuf[l & 1].p, (const T*)c->tbuf[(l + 1) & 1].p, c->st,
+        launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, dblk, W, ldw, nrhs, tb, c->st,
                             &c->stats.kernel_launches);
     }
-    for (int l = S.nlevels - 1; l >= 0; --l) {
+    for (int l = S.ntoplevels - 1; l >= 0; --l) {
         const dre_context::LevelWork& lw = c->levels[l];
         launch_bwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, dblk, W, ldw, nrhs, c->st,
                             &c->stats.kernel_launches);
     }
+    launch_bwd_subtrees<T>(c->dS, L, dblk, W, ldw, nrhs, c->st, &c->stats.kernel_launches);
     CU(cudaGetLastError());
     c->stats.solves++;
     {   // 2*nnz(L)*w (factor read once per sweep) + 4*n*r_tot*w (RHS read+write per sweep)
@@ -464,6 +465,7 @@ int32_t dre_symbolic_create(int64_t n, const int64_t* Ecp, const int64_t* Eri, c
     AnalyzeOptions opt;
     if (leaf_size > 0) opt.leaf_size = leaf_size & 0xffff;
     if ((leaf_size >> 16) > 0) opt.max_snode = leaf_size >> 16;  // upper half-word: supernode width cap
+    else opt.max_snode = 32;                                     // what dre_set_pencil uses
     std::string e;
     try {
         e = analyze(n, Ecp, Eri, Enz, Acp, Ari, Anz, base, opt, s->sym);
@@ -518,6 +520,11 @@ int32_t dre_symbolic_export(const dre_symbolic* s, const char* what, void* buf, 
     if (w == "sn_rows") return put_i(S.sn_rows);
     if (w == "sn_parent") return put_i(S.sn_parent);
     if (w == "sn_level") return put_i(S.sn_level);
+    if (w == "sn_subtree") return put_i(S.sn_subtree);
+    if (w == "st_ptr") return put_i(S.st_ptr);
+    if (w == "st_sn") return put_i(S.st_sn);
+    if (w == "top_level_ptr") return put_i(S.top_level_ptr);
+    if (w == "top_level_sn") return put_i(S.top_level_sn);
     if (w == "level_ptr") return put_i(S.level_ptr);
     if (w == "level_sn") return put_i(S.level_sn);
     if (w == "panel_off") return put_i(S.panel_off);
@@ -575,8 +582,8 @@ static void release_pencil(dre_context* c) {
     c->owned.clear();
     if (c->d_L) cudaFree(c->d_L);
     if (c->d_dblk) cudaFree(c->d_dblk);
-    for (int i = 0; i < 2; ++i) if (c->d_U[i]) cudaFree(c->d_U[i]);
-    c->d_L = c->d_dblk = c->d_U[0] = c->d_U[1] = nullptr;
+    if (c->d_U) cudaFree(c->d_U);
+    c->d_L = c->d_dblk = c->d_U = nullptr;
     c->has_pencil = false;
     c->fact_valid = false;
 }
@@ -587,7 +594,7 @@ int32_t dre_destroy(dre_context* c) {
     cudaStreamSynchronize(c->st);
     for (Panel& p : c->panels) if (p.alive && p.d) cudaFree(p.d);
     release_pencil(c);
-    c->tbuf[0].release(); c->tbuf[1].release(); c->Wbuf.release(); c->btw.release(); c->sol.release();
+    c->tbuf.release(); c->Wbuf.release(); c->btw.release(); c->sol.release();
     c->gram_partial.release(); c->gbuf.release(); c->gbuf2.release(); c->cbuf.release(); c->wsel.release();
     c->wsel2.release(); c->small.release(); c->stage.release(); c->qws.release(); c->pws.release();
     c->qtmp.release(); c->rt.release(); c->tmp_panel.release(); c->evals.release(); c->syevd_work.release();
@@ -636,7 +643,7 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     c->dblk_elems = dblk_off[S.nsn];
 
     int rc;
-    int32_t *d_sn_first, *d_sn_rows, *d_relmap, *d_child_ptr, *d_child_idx, *d_sn_level;
+    int32_t *d_sn_first, *d_sn_rows, *d_relmap, *d_child_ptr, *d_child_idx, *d_st_ptr, *d_st_sn;
     int64_t *d_sn_rowptr, *d_panel_off, *d_upd_off, *d_rhs_off, *d_dblk_off, *d_asm_dest;
     double *d_asm_a, *d_asm_e;
     if ((rc = upload_vec(c, S.sn_first, &d_sn_first))) return rc;
@@ -649,7 +656,8 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     if ((rc = upload_vec(c, S.upd_off, &d_upd_off))) return rc;
     if ((rc = upload_vec(c, S.rhs_off, &d_rhs_off))) return rc;
     if ((rc = upload_vec(c, dblk_off, &d_dblk_off))) return rc;
-    if ((rc = upload_vec(c, S.sn_level, &d_sn_level))) return rc;
+    if ((rc = upload_vec(c, S.st_ptr, &d_st_ptr))) return rc;
+    if ((rc = upload_vec(c, S.st_sn, &d_st_sn))) return rc;
     if ((rc = upload_vec(c, S.asm_dest, &d_asm_dest))) return rc;
     if ((rc = upload_vec(c, S.asm_a, &d_asm_a))) return rc;
     if ((rc = upload_vec(c, S.asm_e, &d_asm_e))) return rc;
@@ -658,60 +666,45 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     if ((rc = upload_vec(c, S.csr_col, &c->d_csr_col))) return rc;
     if ((rc = upload_vec(c, S.csr_a, &c->d_csr_a))) return rc;
     if ((rc = upload_vec(c, S.csr_e, &c->d_csr_e))) return rc;
-    if ((rc = upload_vec(c, S.level_sn, &c->d_level_sn))) return rc;
+    if ((rc = upload_vec(c, S.top_level_sn, &c->d_level_sn))) return rc;
     DevSymbolic& D = c->dS;
-    D.n = S.n; D.nsn = S.nsn; D.nlevels = S.nlevels;
+    D.n = S.n; D.nsn = S.nsn; D.nlevels = S.nlevels; D.nsubtrees = S.nsubtrees;
     D.sn_first = d_sn_first; D.sn_rowptr = d_sn_rowptr; D.sn_rows = d_sn_rows; D.relmap = d_relmap;
     D.child_ptr = d_child_ptr; D.child_idx = d_child_idx; D.panel_off = d_panel_off; D.upd_off = d_upd_off;
-    D.rhs_off = d_rhs_off; D.dblk_off = d_dblk_off; D.sn_level = d_sn_level;
+    D.rhs_off = d_rhs_off; D.dblk_off = d_dblk_off; D.st_ptr = d_st_ptr; D.st_sn = d_st_sn;
     D.nasm = (int64_t)S.asm_dest.size(); D.asm_dest = d_asm_dest; D.asm_a = d_asm_a; D.asm_e = d_asm_e;
 
-    // per-level work lists
-    c->levels.assign(S.nlevels, dre_context::LevelWork());
+    // per-level work lists of the TOP part of the tree
+    c->levels.assign(S.ntoplevels, dre_context::LevelWork());
     std::vector<int32_t> ea_parents;
     std::vector<int2> front_items;
     std::vector<int4> schur_items;
-    for (int l = 0; l < S.nlevels; ++l) {
+    for (int l = 0; l < S.ntoplevels; ++l) {
         dre_context::LevelWork& lw = c->levels[l];
-        lw.sn_begin = S.level_ptr[l];
-        lw.sn_count = S.level_ptr[l + 1] - S.level_ptr[l];
+        lw.sn_begin = S.top_level_ptr[l];
+        lw.sn_count = S.top_level_ptr[l + 1] - S.top_level_ptr[l];
+        lw.upd_begin = S.top_level_upd_begin[l];
+        lw.upd_elems = S.top_level_upd_elems[l];
         lw.ea_begin = (int)ea_parents.size();
-        int max_s = 0, max_f = 0;
-        for (int p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p) {
-            const int J = S.level_sn[p];
-            const int64_t u = S.sn_nrows(J);
-            lw.upd_elems += u * u;
-            max_s = std::max(max_s, S.sn_size(J));
+        lw.front_begin = (int)front_items.size();
+        lw.schur_begin = (int)schur_items.size();
+        int max_f = 0;
+        for (int p = S.top_level_ptr[l]; p < S.top_level_ptr[l + 1]; ++p) {
+            const int J = S.top_level_sn[p];
+            const int s = S.sn_size(J), u = S.sn_nrows(J);
+            if (s > 32) return fail(c, DRE_ERR_STATE, "internal error: supernode wider than 32 columns");
             max_f = std::max(max_f, S.front(J));
             if (S.child_ptr[J + 1] > S.child_ptr[J]) ea_parents.push_back(J);
-        }
-        lw.ea_count = (int)ea_parents.size() - lw.ea_begin;
-        lw.ea_gy = std::min(64, std::max(1, max_f / 8));
-        const int nsteps = (max_s + 31) / 32;
-        for (int step = 0; step < nsteps; ++step) {
-            const int begin = (int)front_items.size();
-            for (int p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p) {
-                const int J = S.level_sn[p];
-                const int s = S.sn_size(J), f = S.front(J);
-                const int k0 = step * 32;
-                if (k0 >= s) continue;
-                const int nb = std::min(32, s - k0);
-                if (s > 32) return fail(c, DRE_ERR_STATE, "internal error: supernode wider than 32 columns");
-                const int below = f - k0 - nb;
-                const int nslab = std::max(1, (below + 95) / 96);
-                for (int sl = 0; sl < nslab; ++sl) front_items.push_back(make_int2(J, sl));
-            }
-            lw.steps.push_back({begin, (int)front_items.size() - begin});
-        }
-        lw.schur_begin = (int)schur_items.size();
-        for (int p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p) {
-            const int J = S.level_sn[p];
-            const int u = S.sn_nrows(J);
+            const int nslab = std::max(1, (u + 95) / 96);
+            for (int sl = 0; sl < nslab; ++sl) front_items.push_back(make_int2(J, sl));
             const int nt = (u + 63) / 64;
             for (int ti = 0; ti < nt; ++ti)
                 for (int tj = 0; tj <= ti; ++tj) schur_items.push_back(make_int4(J, ti, tj, 0));
         }
+        lw.ea_count = (int)ea_parents.size() - lw.ea_begin;
+        lw.front_count = (int)front_items.size() - lw.front_begin;
         lw.schur_count = (int)schur_items.size() - lw.schur_begin;
+        lw.ea_gy = std::min(64, std::max(1, max_f / 8));
     }
     if ((rc = upload_vec(c, ea_parents, &c->d_ea_parents))) return rc;
     if ((rc = upload_vec(c, front_items, &c->d_front_items))) return rc;
@@ -720,8 +713,8 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     // factor storage, sized for complex
     CU(cudaMalloc(&c->d_L, (size_t)std::max<int64_t>(S.nnz_L, 1) * sizeof(cplx)));
     CU(cudaMalloc(&c->d_dblk, (size_t)std::max<int64_t>(c->dblk_elems, 1) * sizeof(cplx)));
-    for (int par = 0; par < 2; ++par)
-        CU(cudaMalloc(&c->d_U[par], (size_t)std::max<int64_t>(S.max_upd_level[par], 1) * sizeof(cplx)));
+    CU(cudaMalloc(&c->d_U, (size_t)std::max<int64_t>(S.upd_bottom_elems + S.max_upd_level[0] + S.max_upd_level[1], 1) *
+                               sizeof(cplx)));
     c->has_pencil = true;
     c->op_a = 1.0; c->op_e = 0.0; c->op_alpha = 1.0;
     return DRE_OK;

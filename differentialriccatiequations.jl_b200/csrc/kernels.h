@@ -63,7 +63,7 @@ void launch_spmm(const int32_t* ptr, const int32_t* col, const double* val, int6
 // ---------------- sparse: supernodal LDL^T + block solves ----------------
 struct DevSymbolic {
     int64_t n;
-    int32_t nsn, nlevels;
+    int32_t nsn, nlevels, nsubtrees;
     const int32_t* sn_first;
     const int64_t* sn_rowptr;
     const int32_t* sn_rows;
@@ -71,10 +71,11 @@ struct DevSymbolic {
     const int32_t* child_ptr;
     const int32_t* child_idx;
     const int64_t* panel_off;
-    const int64_t* upd_off;
-    const int64_t* rhs_off;
-    const int64_t* dblk_off;   // offset of the supernode's factored 32x32 diagonal blocks (1024 entries each)
-    const int32_t* sn_level;
+    const int64_t* upd_off;    // absolute offsets of the update matrices (bottom region, then top ping-pong)
+    const int64_t* rhs_off;    // row offsets of the update vectors (cumulative over all supernodes)
+    const int64_t* dblk_off;   // offset of the supernode's 32x32 block: pivots + inverse unit-lower factor
+    const int32_t* st_ptr;     // bottom subtrees: supernode lists (ascending)
+    const int32_t* st_sn;
     // assembly
     int64_t nasm;
     const int64_t* asm_dest;
@@ -85,29 +86,36 @@ struct DevSymbolic {
 template <class T>
 void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t st, int64_t* launches);
 
-// extend-add of the children's update matrices into the parents of one level
+// top levels: extend-add of the children's update matrices into the parents of one level
 template <class T>
-void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* Ucur,
-                       const T* Uprev, cudaStream_t st, int64_t* launches);
-
-// panel factorization (LDL^T of the <=32-column diagonal block + L21 slab solve) of every front of a level
-// items: (J, slab) pairs
+void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* U,
+                       cudaStream_t st, int64_t* launches);
+// top levels: panel factorization of every front of a level; items: (J, slab) pairs
 template <class T>
 void launch_front(const DevSymbolic& S, const int2* items, int nitems, T* L, T* dblk, int32_t* errflag,
                   cudaStream_t st, int64_t* launches);
-
-// Schur complement  U_J -= L21 D L21'  (lower triangle, 64x64 tiles); items: (J, ti, tj)
+// top levels: Schur complement  U_J -= L21 D L21'  (lower triangle, 64x64 tiles); items: (J, ti, tj)
 template <class T>
-void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dblk, T* Ucur,
+void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dblk, T* U,
                   cudaStream_t st, int64_t* launches);
+// bottom subtrees: one CTA factors a whole subtree
+template <class T>
+void launch_factor_subtrees(const DevSymbolic& S, T* L, T* dblk, T* U, int32_t* errflag, cudaStream_t st,
+                            int64_t* launches);
 
-// forward / backward sweeps of one level on the row-major RHS block W (n x ldw), nrhs columns
+// forward / backward sweeps on the row-major RHS block W (n x ldw), nrhs columns
 template <class T>
 void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
-                      int64_t ldw, int nrhs, T* tcur, const T* tprev, cudaStream_t st, int64_t* launches);
+                      int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches);
 template <class T>
 void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
                       int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches);
+template <class T>
+void launch_fwd_subtrees(const DevSymbolic& S, const T* L, const T* dblk, T* W, int64_t ldw, int nrhs, T* tbuf,
+                         cudaStream_t st, int64_t* launches);
+template <class T>
+void launch_bwd_subtrees(const DevSymbolic& S, const T* L, const T* dblk, T* W, int64_t ldw, int nrhs,
+                         cudaStream_t st, int64_t* launches);
 
 // W[:, 0:r] = R, W[:, r:r+m] = Vt   (real -> T)
 template <class T>

@@ -1,5 +1,5 @@
 // Per-shift numeric supernodal LDL^T (no pivoting; real symmetric definite or complex symmetric)
-// and level-scheduled multifrontal block solves with many right-hand sides.
+// and multifrontal block solves with many right-hand sides.
 //
 // Replaces, for the hot path, what the reference gets from SuiteSparse through
 //   factorize(A' + mu E')   src/blocklinear/backslash.jl:13, src/blocklinear/types.jl:41-42
@@ -8,22 +8,32 @@
 // T = double for real shifts, T = cplx (complex SYMMETRIC, no conjugation) for complex shifts --
 // the complex pair path the reference lists as broken on GPU (README.md:174-176).
 //
-// Storage: panel_J = f_J x s_J column-major (ld f_J) with L21 below the supernode's own rows;
-// the factored diagonal blocks (unit-lower L_d and the pivots d, 32 x 32 each) live in a side
-// array `dblk` so that no CTA overwrites panel entries other CTAs of the same step still read.
-// Update matrices / update vectors live in two ping-pong buffers indexed by level parity: the
-// children of a supernode are all exactly one level below it (levels are tree depths).
+// Structure (from csrc/symbolic.cpp): every supernode has at most 32 columns (wider dissection blocks
+// are chains).  The tree is cut into
+//   * bottom subtrees (<= a few hundred columns each): ONE CTA walks a whole subtree in elimination
+//     order, so the thousands of tiny fronts of the lower levels cost one launch per phase;
+//   * top supernodes, processed level by level (one launch per level and phase).
+// Storage: panel_J = f_J x s_J column-major (ld f_J), L21 below the supernode's own rows; the pivots and
+// the INVERSE of the unit-lower diagonal block live in a side array (32x32 per supernode) so that the
+// block solves are plain multiplications.  Update matrices: one region per bottom supernode plus two
+// ping-pong regions for the top levels.  Update vectors of the solves: one region per supernode,
+// column-major (u_J contiguous per right-hand side).
 #include <algorithm>
 
 #include "kernels.h"
 
 namespace dre {
 
-constexpr int NB = 32;     // block-column width of the blocked LDL^T
-constexpr int SLAB = 96;   // slab rows per CTA (plus the 32 diagonal-block rows)
+constexpr int NB = 32;     // maximum supernode width
+constexpr int SLAB = 96;   // L21 rows handled per slab
 
 __device__ __forceinline__ int sn_s(const DevSymbolic& S, int J) { return S.sn_first[J + 1] - S.sn_first[J]; }
 __device__ __forceinline__ int sn_u(const DevSymbolic& S, int J) { return (int)(S.sn_rowptr[J + 1] - S.sn_rowptr[J]); }
+
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ cplx shfl(cplx v, int src) {
+    return mk(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
 
 // ------------------------------------------------------------------------------------------
 // assembly: L[dest] = a*A + (e+mu)*E on the lower-triangular union pattern
@@ -47,172 +57,138 @@ void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t s
 }
 
 // ------------------------------------------------------------------------------------------
-// extend-add: parent J gathers the update matrices of its children (deterministic: one CTA
-// column-class per parent column, children visited in a fixed order)
+// device bodies shared by the per-level (top) kernels and the subtree (bottom) kernels
 // ------------------------------------------------------------------------------------------
+
+// extend-add: supernode J gathers the update matrices of its children through the relative index maps.
+// Deterministic: parent column pc is owned by column class (pc % gy == by); children in fixed order.
 template <class T>
-__global__ void __launch_bounds__(256) k_extend_add(DevSymbolic S, const int32_t* __restrict__ parents, T* L,
-                                                    T* Ucur, const T* __restrict__ Uprev) {
-    const int J = parents[blockIdx.x];
-    const int by = blockIdx.y, gy = gridDim.y;
+__device__ __forceinline__ void ea_body(const DevSymbolic& S, int J, int by, int gy, T* L, T* U) {
     const int sJ = sn_s(S, J), uJ = sn_u(S, J), fJ = sJ + uJ;
     T* P = L + S.panel_off[J];
-    T* UJ = Ucur + S.upd_off[J];
+    T* UJ = U + S.upd_off[J];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int ci = S.child_ptr[J]; ci < S.child_ptr[J + 1]; ++ci) {
         const int c = S.child_idx[ci];
         const int uc = sn_u(S, c);
         const int32_t* rel = S.relmap + S.sn_rowptr[c];
-        const T* Uc = Uprev + S.upd_off[c];
+        const T* Uc = U + S.upd_off[c];
         for (int j = warp; j < uc; j += nwarps) {
             const int pc = rel[j];
             if (pc % gy != by) continue;
             for (int i = j + lane; i < uc; i += 32) {
                 const int pr = rel[i];
                 const T val = Uc[(int64_t)i + (int64_t)j * uc];
-                if (pc < sJ) {
-                    T* t = P + ((int64_t)pr + (int64_t)pc * fJ);
-                    *t = add(*t, val);
-                } else {
-                    T* t = UJ + ((int64_t)(pr - sJ) + (int64_t)(pc - sJ) * uJ);
-                    *t = add(*t, val);
-                }
+                T* t = (pc < sJ) ? (P + ((int64_t)pr + (int64_t)pc * fJ))
+                                 : (UJ + ((int64_t)(pr - sJ) + (int64_t)(pc - sJ) * uJ));
+                *t = add(*t, val);
             }
         }
         __syncthreads();
     }
 }
 
+// LDL^T of the (identity-padded) 32x32 diagonal block by ONE warp: lane i holds row i in registers.
 template <class T>
-void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* Ucur,
-                       const T* Uprev, cudaStream_t st, int64_t* launches) {
-    if (nparents <= 0) return;
-    dim3 grid(nparents, gy);
-    k_extend_add<T><<<grid, 256, 0, st>>>(S, parents, L, Ucur, Uprev);
-    if (launches) *launches += 1;
+__device__ __forceinline__ void warp_ldlt32(T (&a)[NB], int lane, int32_t* errflag) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const T d = shfl(a[j], j);
+        if (lane == j && is_bad(d)) atomicExch(errflag, 1);
+        const T w = a[j];                 // unscaled column entry of this row
+        const T l = mul(w, recip(d));
+#pragma unroll
+        for (int k = j + 1; k < NB; ++k) {
+            const T wk = shfl(w, k);      // w of row k = A[k][j]
+            if (lane >= k) a[k] = sub(a[k], mul(l, wk));
+        }
+        if (lane > j) a[j] = l;
+    }
 }
 
-// ------------------------------------------------------------------------------------------
-// panel factorization of every front of a level (all supernodes have at most 32 columns: wider
-// dissection blocks are split into chains by the symbolic analysis).  CTA (J, slab): the 32x32
-// diagonal block is factored (LDL^T, no pivoting) in shared memory by every CTA of the front, the CTA's
-// 96-row slab of L21 is solved against it; slab 0 also stores the pivots and the INVERSE of the unit
-// lower factor into the side array, so that the block solves are plain multiplications.
-// ------------------------------------------------------------------------------------------
+// phase A: factor the diagonal block of front J (all threads call; warp 0 works), optionally store it.
+// Ds: strictly lower = L_d, diagonal = pivots.  Li: strictly lower part of the inverse of the unit factor.
 template <class T>
-__global__ void __launch_bounds__(256) k_front(DevSymbolic S, const int2* __restrict__ items, T* L, T* dblk,
-                                               int32_t* errflag) {
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    T* smp = reinterpret_cast<T*>(dre_smem_raw);
-    T (*Ds)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Ss)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += SLAB * (NB + 1);
-    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T* tmp = smp;
-    const int2 item = items[blockIdx.x];
-    const int J = item.x, slab = item.y;
+__device__ __forceinline__ void front_diag(const DevSymbolic& S, int J, T* L, T* dblk, int32_t* errflag,
+                                           T (*Ds)[NB + 1], T (*Li)[NB + 1], bool store) {
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    const T* P = L + S.panel_off[J];
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        const int lane = tid;
+        T a[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            T v = (lane == c) ? one<T>() : zero<T>();
+            if (lane < s && c < s && c <= lane) v = P[(int64_t)lane + (int64_t)c * f];
+            a[c] = v;
+        }
+        warp_ldlt32<T>(a, lane, errflag);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) Ds[lane][c] = a[c];
+        __syncwarp();
+        // inverse of the unit lower factor: lane c owns column c
+        const int c = lane;
+        for (int i = c + 1; i < NB; ++i) {
+            T v = Ds[i][c];
+            for (int k = c + 1; k < i; ++k) fma_acc(v, Ds[i][k], Li[k][c]);
+            Li[i][c] = sub(zero<T>(), v);
+        }
+        __syncwarp();
+        if (store) {
+            T* Db = dblk + S.dblk_off[J];
+            for (int i = 0; i < NB; ++i) {
+                // element (i, c): strictly lower -> Linv, diagonal -> pivot, upper -> 0
+                T v = zero<T>();
+                if (i > c) v = Li[i][c];
+                else if (i == c) v = Ds[i][i];
+                Db[i + c * 32] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// phase B: L21 slab = S * Linv^T * D^-1 for rows [row0, row0 + SLAB) of the front (row0 >= s)
+template <class T>
+__device__ __forceinline__ void front_slab(const DevSymbolic& S, int J, int row0, T* L, T (*Ds)[NB + 1],
+                                           T (*Li)[NB + 1], T (*Ss)[NB + 1]) {
     const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
     T* P = L + S.panel_off[J];
     const int tid = threadIdx.x;
-    const int row0 = s + slab * SLAB;
-
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx & 31, c = idx >> 5;
-        Ds[i][c] = (i < s && c < s) ? P[(int64_t)i + (int64_t)c * f] : zero<T>();
-    }
     for (int idx = tid; idx < SLAB * NB; idx += 256) {
         const int m = idx % SLAB, c = idx / SLAB;
         Ss[m][c] = (row0 + m < f && c < s) ? P[(int64_t)(row0 + m) + (int64_t)c * f] : zero<T>();
     }
     __syncthreads();
-    // unblocked LDL^T of the diagonal block (lower part of Ds)
-    for (int j = 0; j < s; ++j) {
-        const T d = Ds[j][j];
-        if (tid == 0 && is_bad(d)) atomicExch(errflag, 1);
-        const T rd = recip(d);
-        if (tid > j && tid < s) {
-            const T w = Ds[tid][j];
-            tmp[tid] = w;
-            Ds[tid][j] = mul(w, rd);
-        }
-        __syncthreads();
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int i = idx >> 5, k = idx & 31;
-            if (k > j && i >= k && i < s) Ds[i][k] = sub(Ds[i][k], mul(Ds[i][j], tmp[k]));
-        }
-        __syncthreads();
+    // out[m][c] = (S[m][c] + sum_{t<c} S[m][t] * Linv[c][t]) / d_c ; each thread computes 12 outputs
+    T outv[SLAB * NB / 256];
+#pragma unroll
+    for (int q = 0; q < SLAB * NB / 256; ++q) {
+        const int idx = tid + 256 * q;
+        const int m = idx % SLAB, c = idx / SLAB;
+        T v = Ss[m][c];
+        for (int t = 0; t < c; ++t) fma_acc(v, Ss[m][t], Li[c][t]);
+        outv[q] = mul(v, recip(Ds[c][c]));
     }
-    // slab rows: y_c = S[c] - sum_{t<c} y_t Ld[c][t];  L[c] = y_c / d_c
-    if (tid < SLAB) {
-        const int m = tid;
-        if (row0 + m < f) {
-            for (int c = 0; c < s; ++c) {
-                T v = Ss[m][c];
-                for (int t = 0; t < c; ++t) v = sub(v, mul(Ss[m][t], Ds[c][t]));
-                Ss[m][c] = v;
-            }
-            for (int c = 0; c < s; ++c) Ss[m][c] = mul(Ss[m][c], recip(Ds[c][c]));
-        }
-    } else if (slab == 0 && tid >= 128 && tid < 128 + NB) {
-        // inverse of the unit lower factor, one column per thread (warp 4)
-        const int c = tid - 128;
-        if (c < s) {
-            for (int i = c + 1; i < s; ++i) {
-                T v = Ds[i][c];  // Ld[i][c] * z[c], z[c] = 1
-                for (int k = c + 1; k < i; ++k) fma_acc(v, Ds[i][k], Li[k][c]);
-                Li[i][c] = sub(zero<T>(), v);
-            }
-        }
+#pragma unroll
+    for (int q = 0; q < SLAB * NB / 256; ++q) {
+        const int idx = tid + 256 * q;
+        const int m = idx % SLAB, c = idx / SLAB;
+        if (row0 + m < f && c < s) P[(int64_t)(row0 + m) + (int64_t)c * f] = outv[q];
     }
     __syncthreads();
-    for (int idx = tid; idx < SLAB * NB; idx += 256) {
-        const int m = idx % SLAB, c = idx / SLAB;
-        if (row0 + m < f && c < s) P[(int64_t)(row0 + m) + (int64_t)c * f] = Ss[m][c];
-    }
-    if (slab == 0) {
-        T* Db = dblk + S.dblk_off[J];
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int i = idx & 31, c = idx >> 5;
-            T v = zero<T>();
-            if (i < s && c < s) {
-                if (i > c) v = Li[i][c];
-                else if (i == c) v = Ds[i][i];
-            } else if (i == c) {
-                v = one<T>();
-            }
-            Db[i + c * 32] = v;
-        }
-    }
 }
 
+// Schur tile: U_J[i0:i0+64, j0:j0+64] -= L21 D L21^T  (lower triangle), K = s_J
 template <class T>
-void launch_front(const DevSymbolic& S, const int2* items, int nitems, T* L, T* dblk, int32_t* errflag,
-                  cudaStream_t st, int64_t* launches) {
-    if (nitems <= 0) return;
-    const int smem = (int)sizeof(T) * (2 * NB * (NB + 1) + SLAB * (NB + 1) + NB);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_front<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
-    k_front<T><<<nitems, 256, smem, st>>>(S, items, L, dblk, errflag);
-    if (launches) *launches += 1;
-}
-
-// ------------------------------------------------------------------------------------------
-// Schur complement U_J -= L21 D L21^T (lower triangle), 64x64 tiles, K = s_J
-// ------------------------------------------------------------------------------------------
-template <class T>
-__global__ void __launch_bounds__(256) k_schur(DevSymbolic S, const int4* __restrict__ items, const T* __restrict__ L,
-                                               const T* __restrict__ dblk, T* Ucur) {
+__device__ __forceinline__ void schur_tile(const DevSymbolic& S, int J, int i0, int j0, const T* L, const T* dblk,
+                                           T* U, T (*As)[64], T (*Bs)[64]) {
     constexpr int KC = 16;
-    __shared__ T As[KC][64];
-    __shared__ T Bs[KC][64];
-    const int4 item = items[blockIdx.x];
-    const int J = item.x, i0 = item.y * 64, j0 = item.z * 64;
     const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
     const T* P = L + S.panel_off[J];
     const T* Dk = dblk + S.dblk_off[J];
-    T* U = Ucur + S.upd_off[J];
+    T* UJ = U + S.upd_off[J];
     const int tid = threadIdx.x, tr = tid & 15, tc = tid >> 4;
     T acc[4][4];
 #pragma unroll
@@ -228,10 +204,7 @@ __global__ void __launch_bounds__(256) k_schur(DevSymbolic S, const int4* __rest
             T av = zero<T>(), bv = zero<T>();
             if (kg < s) {
                 if (i0 + m < u) av = P[(int64_t)(s + i0 + m) + (int64_t)kg * f];
-                if (j0 + m < u) {
-                    const T d = Dk[kg * 33];
-                    bv = mul(P[(int64_t)(s + j0 + m) + (int64_t)kg * f], d);
-                }
+                if (j0 + m < u) bv = mul(P[(int64_t)(s + j0 + m) + (int64_t)kg * f], Dk[kg * 33]);
             }
             As[k][m] = av;
             Bs[k][m] = bv;
@@ -258,43 +231,148 @@ __global__ void __launch_bounds__(256) k_schur(DevSymbolic S, const int4* __rest
         for (int j = 0; j < 4; ++j) {
             const int gj = j0 + tc + 16 * j;
             if (gi < u && gj < u && gi >= gj) {
-                T* t = U + ((int64_t)gi + (int64_t)gj * u);
+                T* t = UJ + ((int64_t)gi + (int64_t)gj * u);
                 *t = sub(*t, acc[i][j]);
             }
         }
     }
 }
 
+// ---- top-level factorization kernels ----
 template <class T>
-void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dblk, T* Ucur,
+__global__ void __launch_bounds__(256) k_extend_add(DevSymbolic S, const int32_t* __restrict__ parents, T* L, T* U) {
+    ea_body<T>(S, parents[blockIdx.x], blockIdx.y, gridDim.y, L, U);
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) k_front(DevSymbolic S, const int2* __restrict__ items, T* L, T* dblk,
+                                               int32_t* errflag) {
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    T* smp = reinterpret_cast<T*>(dre_smem_raw);
+    T (*Ds)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*Ss)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);
+    const int2 item = items[blockIdx.x];
+    const int J = item.x, slab = item.y;
+    front_diag<T>(S, J, L, dblk, errflag, Ds, Li, slab == 0);
+    const int s = sn_s(S, J), u = sn_u(S, J);
+    if (slab * SLAB < u) front_slab<T>(S, J, s + slab * SLAB, L, Ds, Li, Ss);
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) k_schur(DevSymbolic S, const int4* __restrict__ items, const T* __restrict__ L,
+                                               const T* __restrict__ dblk, T* U) {
+    __shared__ T As[16][64];
+    __shared__ T Bs[16][64];
+    const int4 item = items[blockIdx.x];
+    schur_tile<T>(S, item.x, item.y * 64, item.z * 64, L, dblk, U, As, Bs);
+}
+
+// ---- bottom subtrees: one CTA factors a whole subtree (zero U, extend-add, panel, Schur per front) ----
+template <class T>
+__global__ void __launch_bounds__(256) k_factor_subtree(DevSymbolic S, T* L, T* dblk, T* U, int32_t* errflag) {
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    T* smp = reinterpret_cast<T*>(dre_smem_raw);
+    T (*Ds)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
+    T (*Ss)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += SLAB * (NB + 1);
+    T (*As)[64] = reinterpret_cast<T (*)[64]>(smp);                   smp += 16 * 64;
+    T (*Bs)[64] = reinterpret_cast<T (*)[64]>(smp);
+    const int t = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int p = S.st_ptr[t]; p < S.st_ptr[t + 1]; ++p) {
+        const int J = S.st_sn[p];
+        const int s = sn_s(S, J), u = sn_u(S, J);
+        T* UJ = U + S.upd_off[J];
+        for (int64_t idx = tid; idx < (int64_t)u * u; idx += 256) UJ[idx] = zero<T>();
+        __syncthreads();
+        ea_body<T>(S, J, 0, 1, L, U);
+        __syncthreads();
+        front_diag<T>(S, J, L, dblk, errflag, Ds, Li, true);
+        for (int r0 = 0; r0 < u; r0 += SLAB) front_slab<T>(S, J, s + r0, L, Ds, Li, Ss);
+        const int nt = (u + 63) / 64;
+        for (int ti = 0; ti < nt; ++ti)
+            for (int tj = 0; tj <= ti; ++tj) schur_tile<T>(S, J, ti * 64, tj * 64, L, dblk, U, As, Bs);
+        __syncthreads();
+    }
+}
+
+template <class T>
+void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* U,
+                       cudaStream_t st, int64_t* launches) {
+    if (nparents <= 0) return;
+    dim3 grid(nparents, gy);
+    k_extend_add<T><<<grid, 256, 0, st>>>(S, parents, L, U);
+    if (launches) *launches += 1;
+}
+
+template <class T>
+void launch_front(const DevSymbolic& S, const int2* items, int nitems, T* L, T* dblk, int32_t* errflag,
                   cudaStream_t st, int64_t* launches) {
     if (nitems <= 0) return;
-    k_schur<T><<<nitems, 256, 0, st>>>(S, items, L, dblk, Ucur);
+    const int smem = (int)sizeof(T) * (2 * NB * (NB + 1) + SLAB * (NB + 1));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_front<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    k_front<T><<<nitems, 256, smem, st>>>(S, items, L, dblk, errflag);
+    if (launches) *launches += 1;
+}
+
+template <class T>
+void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dblk, T* U,
+                  cudaStream_t st, int64_t* launches) {
+    if (nitems <= 0) return;
+    k_schur<T><<<nitems, 256, 0, st>>>(S, items, L, dblk, U);
+    if (launches) *launches += 1;
+}
+
+template <class T>
+void launch_factor_subtrees(const DevSymbolic& S, T* L, T* dblk, T* U, int32_t* errflag, cudaStream_t st,
+                            int64_t* launches) {
+    if (S.nsubtrees <= 0) return;
+    const int smem = (int)sizeof(T) * (2 * NB * (NB + 1) + SLAB * (NB + 1) + 2 * 16 * 64);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_factor_subtree<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    k_factor_subtree<T><<<S.nsubtrees, 256, smem, st>>>(S, L, dblk, U, errflag);
     if (launches) *launches += 1;
 }
 
 // ------------------------------------------------------------------------------------------
-// forward sweep of one level:  y_J = L11^-1 (b_J + children),  t_J = children - L21 y_J
-// CTA = (supernode, CW right-hand-side columns).  W is row-major (n x ldw); the update vectors t_J are
-// column-major per supernode (u_J contiguous per RHS column) inside the level's ping-pong buffer.
+// solves.  W is row-major (n x ldw); the update vector of supernode J is column-major
+// (u_J contiguous per RHS column) at  t + rhs_off[J]*ldw.
+// forward:  y_J = L11^-1 (b_J + children),  t_J = children - L21 y_J
+// backward: x_J = L11^-T (D^-1 y_J - L21^T x_struct)
 // ------------------------------------------------------------------------------------------
 template <class T, int CW>
-__global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
-                                             const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs, T* tcur,
-                                             const T* __restrict__ tprev) {
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    T* smp = reinterpret_cast<T*>(dre_smem_raw);
-    T (*xb)[CW + 1] = reinterpret_cast<T (*)[CW + 1]>(smp);           smp += NB * (CW + 1);
-    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Ls)[64 + 1] = reinterpret_cast<T (*)[64 + 1]>(smp);
-    const int J = sns[blockIdx.x];
-    const int c0 = blockIdx.y * CW;
-    const int ncw = min(CW, nrhs - c0);
+struct SweepSmem {
+    T (*xb)[CW + 1];   // [32][CW+1]
+    T (*Li)[NB + 1];   // [32][33]
+    T (*Ls)[64 + 1];   // [32][65]  (forward: L21 tile; backward uses it as [32][33])
+    T (*Xs)[CW + 1];   // [32][CW+1]
+    __device__ SweepSmem(unsigned char* raw) {
+        T* smp = reinterpret_cast<T*>(raw);
+        xb = reinterpret_cast<T (*)[CW + 1]>(smp);  smp += NB * (CW + 1);
+        Li = reinterpret_cast<T (*)[NB + 1]>(smp);  smp += NB * (NB + 1);
+        Ls = reinterpret_cast<T (*)[64 + 1]>(smp);  smp += NB * 65;
+        Xs = reinterpret_cast<T (*)[CW + 1]>(smp);
+    }
+    static constexpr int bytes() { return (int)sizeof(T) * (2 * NB * (CW + 1) + NB * (NB + 1) + NB * 65); }
+};
+
+template <class T, int CW>
+__device__ __forceinline__ void fwd_body(const DevSymbolic& S, int J, int c0, int ncw, const T* __restrict__ L,
+                                         const T* __restrict__ dblk, T* W, int64_t ldw, T* tbuf,
+                                         SweepSmem<T, CW>& sm) {
     const int first = S.sn_first[J];
     const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
     const T* P = L + S.panel_off[J];
     const T* Dk = dblk + S.dblk_off[J];
-    T* tJ = tcur + S.rhs_off[J] * ldw;
+    T* tJ = tbuf + S.rhs_off[J] * ldw;
     const int tid = threadIdx.x;
 
     for (int idx = tid; idx < u * ncw; idx += 256) {
@@ -306,7 +384,7 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
         const int c = S.child_idx[ci];
         const int uc = sn_u(S, c);
         const int32_t* rel = S.relmap + S.sn_rowptr[c];
-        const T* tch = tprev + S.rhs_off[c] * ldw;
+        const T* tch = tbuf + S.rhs_off[c] * ldw;
         for (int idx = tid; idx < uc * ncw; idx += 256) {
             const int cc = idx / uc, i = idx - cc * uc;
             const int pr = rel[i];
@@ -318,11 +396,11 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
     }
     for (int idx = tid; idx < NB * CW; idx += 256) {
         const int i = idx / CW, cc = idx - i * CW;
-        xb[i][cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
+        sm.xb[i][cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
     }
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int i = idx & 31, k = idx >> 5;
-        Li[i][k] = (k < i) ? Dk[i + k * 32] : zero<T>();
+        sm.Li[i][k] = (k < i) ? Dk[i + k * 32] : zero<T>();
     }
     __syncthreads();
     {   // y = Linv x  (unit lower): thread (row i, column group)
@@ -330,20 +408,20 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
         const int i = tid & 31, cg = tid >> 5;
         T acc[CPT];
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[c] = xb[i][cg * CPT + c];
+        for (int c = 0; c < CPT; ++c) acc[c] = sm.xb[i][cg * CPT + c];
         for (int k = 0; k < i; ++k) {
-            const T l = Li[i][k];
+            const T l = sm.Li[i][k];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, xb[k][cg * CPT + c]);
+            for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, sm.xb[k][cg * CPT + c]);
         }
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) xb[i][cg * CPT + c] = acc[c];
+        for (int c = 0; c < CPT; ++c) sm.xb[i][cg * CPT + c] = acc[c];
     }
     __syncthreads();
     for (int idx = tid; idx < NB * CW; idx += 256) {
         const int i = idx / CW, cc = idx - i * CW;
-        if (i < s && cc < ncw) W[(int64_t)(first + i) * ldw + c0 + cc] = xb[i][cc];
+        if (i < s && cc < ncw) W[(int64_t)(first + i) * ldw + c0 + cc] = sm.xb[i][cc];
     }
     {   // t_J -= L21 y, 64-row tiles of L21 staged in shared memory
         constexpr int CPT = CW / 4;
@@ -352,16 +430,16 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
             __syncthreads();
             for (int idx = tid; idx < NB * 64; idx += 256) {
                 const int rr = idx & 63, k = idx >> 6;
-                Ls[k][rr] = (r0 + rr < u && k < s) ? P[(int64_t)(s + r0 + rr) + (int64_t)k * f] : zero<T>();
+                sm.Ls[k][rr] = (r0 + rr < u && k < s) ? P[(int64_t)(s + r0 + rr) + (int64_t)k * f] : zero<T>();
             }
             __syncthreads();
             T acc[CPT];
 #pragma unroll
             for (int c = 0; c < CPT; ++c) acc[c] = zero<T>();
             for (int k = 0; k < s; ++k) {
-                const T l = Ls[k][rl];
+                const T l = sm.Ls[k][rl];
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, xb[k][cg * CPT + c]);
+                for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, sm.xb[k][cg * CPT + c]);
             }
             if (r0 + rl < u) {
 #pragma unroll
@@ -375,46 +453,14 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
             }
         }
     }
+    __syncthreads();
 }
 
-template <class T>
-void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
-                      int64_t ldw, int nrhs, T* tcur, const T* tprev, cudaStream_t st, int64_t* launches) {
-    if (nsns <= 0 || nrhs <= 0) return;
-    const int smem32 = (int)sizeof(T) * (NB * 33 + NB * (NB + 1) + NB * 65);
-    const int smem8 = (int)sizeof(T) * (NB * 9 + NB * (NB + 1) + NB * 65);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_fwd<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
-        cudaFuncSetAttribute(k_fwd<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
-        attr_set = true;
-    }
-    if ((int64_t)nsns * ((nrhs + 31) / 32) >= 2 * 148) {
-        dim3 grid(nsns, (nrhs + 31) / 32);
-        k_fwd<T, 32><<<grid, 256, smem32, st>>>(S, sns, L, dblk, W, ldw, nrhs, tcur, tprev);
-    } else {
-        dim3 grid(nsns, (nrhs + 7) / 8);
-        k_fwd<T, 8><<<grid, 256, smem8, st>>>(S, sns, L, dblk, W, ldw, nrhs, tcur, tprev);
-    }
-    if (launches) *launches += 1;
-}
-
-// ------------------------------------------------------------------------------------------
-// backward sweep of one level:  x_J = L11^-T (D^-1 y_J - L21^T x_struct)
-// ------------------------------------------------------------------------------------------
 template <class T, int CW>
-__global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
-                                             const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs) {
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    T* smp = reinterpret_cast<T*>(dre_smem_raw);
-    T (*Ls)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Xs)[CW + 1] = reinterpret_cast<T (*)[CW + 1]>(smp);           smp += NB * (CW + 1);
-    T (*zb)[CW + 1] = reinterpret_cast<T (*)[CW + 1]>(smp);           smp += NB * (CW + 1);
-    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);
+__device__ __forceinline__ void bwd_body(const DevSymbolic& S, int J, int c0, int ncw, const T* __restrict__ L,
+                                         const T* __restrict__ dblk, T* W, int64_t ldw, SweepSmem<T, CW>& sm) {
     constexpr int CPT = CW / 8;
-    const int J = sns[blockIdx.x];
-    const int c0 = blockIdx.y * CW;
-    const int ncw = min(CW, nrhs - c0);
+    T (*Lt)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(sm.Ls);  // [32 rows][33] tile of L21
     const int first = S.sn_first[J];
     const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
     const T* P = L + S.panel_off[J];
@@ -429,49 +475,49 @@ __global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __res
     for (int r0 = 0; r0 < u; r0 += NB) {
         for (int idx = tid; idx < NB * NB; idx += 256) {
             const int r = idx & 31, k = idx >> 5;
-            Ls[r][k] = (r0 + r < u && k < s) ? P[(int64_t)(s + r0 + r) + (int64_t)k * f] : zero<T>();
+            Lt[r][k] = (r0 + r < u && k < s) ? P[(int64_t)(s + r0 + r) + (int64_t)k * f] : zero<T>();
         }
         for (int idx = tid; idx < NB * CW; idx += 256) {
             const int r = idx / CW, cc = idx - r * CW;
             T v = zero<T>();
             if (r0 + r < u && cc < ncw) v = W[(int64_t)rows[r0 + r] * ldw + c0 + cc];
-            Xs[r][cc] = v;
+            sm.Xs[r][cc] = v;
         }
         __syncthreads();
 #pragma unroll 8
         for (int r = 0; r < NB; ++r) {
-            const T l = Ls[r][kq];
+            const T l = Lt[r][kq];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, Xs[r][cg * CPT + c]);
+            for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, sm.Xs[r][cg * CPT + c]);
         }
         __syncthreads();
     }
     for (int idx = tid; idx < NB * CW; idx += 256) {
         const int i = idx / CW, cc = idx - i * CW;
-        zb[i][cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
+        sm.xb[i][cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
     }
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int i = idx & 31, k = idx >> 5;
-        Li[i][k] = Dk[i + k * 32];  // strictly lower: Linv, diagonal: pivots
+        sm.Li[i][k] = Dk[i + k * 32];  // strictly lower: Linv, diagonal: pivots
     }
     __syncthreads();
     {
-        const T rd = (kq < s) ? recip(Li[kq][kq]) : zero<T>();
+        const T rd = (kq < s) ? recip(sm.Li[kq][kq]) : zero<T>();
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int cc = cg * CPT + c;
-            zb[kq][cc] = sub(mul(zb[kq][cc], rd), acc[c]);
+            sm.xb[kq][cc] = sub(mul(sm.xb[kq][cc], rd), acc[c]);
         }
     }
     __syncthreads();
     {   // x = Linv^T z : x_i = z_i + sum_{k>i} Linv[k][i] z_k
         T xv[CPT];
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) xv[c] = zb[kq][cg * CPT + c];
+        for (int c = 0; c < CPT; ++c) xv[c] = sm.xb[kq][cg * CPT + c];
         for (int k = kq + 1; k < s; ++k) {
-            const T l = Li[k][kq];
+            const T l = sm.Li[k][kq];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) fma_acc(xv[c], l, zb[k][cg * CPT + c]);
+            for (int c = 0; c < CPT; ++c) fma_acc(xv[c], l, sm.xb[k][cg * CPT + c]);
         }
         if (kq < s) {
 #pragma unroll
@@ -481,26 +527,126 @@ __global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __res
             }
         }
     }
+    __syncthreads();
+}
+
+template <class T, int CW>
+__global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
+                                             const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs, T* tbuf) {
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    SweepSmem<T, CW> sm(dre_smem_raw);
+    const int c0 = blockIdx.y * CW;
+    fwd_body<T, CW>(S, sns[blockIdx.x], c0, min(CW, nrhs - c0), L, dblk, W, ldw, tbuf, sm);
+}
+
+template <class T, int CW>
+__global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
+                                             const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs) {
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    SweepSmem<T, CW> sm(dre_smem_raw);
+    const int c0 = blockIdx.y * CW;
+    bwd_body<T, CW>(S, sns[blockIdx.x], c0, min(CW, nrhs - c0), L, dblk, W, ldw, sm);
+}
+
+// bottom subtrees: CTA (subtree, column chunk) walks the subtree (ascending for forward, descending for
+// backward); right-hand-side columns are independent, so no inter-CTA synchronisation is needed.
+template <class T, int CW>
+__global__ void __launch_bounds__(256) k_fwd_subtree(DevSymbolic S, const T* __restrict__ L,
+                                                     const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs,
+                                                     T* tbuf) {
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    SweepSmem<T, CW> sm(dre_smem_raw);
+    const int c0 = blockIdx.y * CW;
+    const int ncw = min(CW, nrhs - c0);
+    const int t = blockIdx.x;
+    for (int p = S.st_ptr[t]; p < S.st_ptr[t + 1]; ++p)
+        fwd_body<T, CW>(S, S.st_sn[p], c0, ncw, L, dblk, W, ldw, tbuf, sm);
+}
+
+template <class T, int CW>
+__global__ void __launch_bounds__(256) k_bwd_subtree(DevSymbolic S, const T* __restrict__ L,
+                                                     const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs) {
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    SweepSmem<T, CW> sm(dre_smem_raw);
+    const int c0 = blockIdx.y * CW;
+    const int ncw = min(CW, nrhs - c0);
+    const int t = blockIdx.x;
+    for (int p = S.st_ptr[t + 1] - 1; p >= S.st_ptr[t]; --p)
+        bwd_body<T, CW>(S, S.st_sn[p], c0, ncw, L, dblk, W, ldw, sm);
+}
+
+template <class T, int CW>
+static void set_sweep_attrs() {
+    static bool done = false;
+    if (done) return;
+    const int smem = SweepSmem<T, CW>::bytes();
+    cudaFuncSetAttribute(k_fwd<T, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_bwd<T, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_fwd_subtree<T, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_bwd_subtree<T, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    done = true;
+}
+
+template <class T>
+void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
+                      int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches) {
+    if (nsns <= 0 || nrhs <= 0) return;
+    set_sweep_attrs<T, 32>();
+    set_sweep_attrs<T, 8>();
+    if ((int64_t)nsns * ((nrhs + 31) / 32) >= 2 * 148) {
+        dim3 grid(nsns, (nrhs + 31) / 32);
+        k_fwd<T, 32><<<grid, 256, SweepSmem<T, 32>::bytes(), st>>>(S, sns, L, dblk, W, ldw, nrhs, tbuf);
+    } else {
+        dim3 grid(nsns, (nrhs + 7) / 8);
+        k_fwd<T, 8><<<grid, 256, SweepSmem<T, 8>::bytes(), st>>>(S, sns, L, dblk, W, ldw, nrhs, tbuf);
+    }
+    if (launches) *launches += 1;
 }
 
 template <class T>
 void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
                       int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    const int smem32 = (int)sizeof(T) * (2 * NB * (NB + 1) + 2 * NB * 33);
-    const int smem8 = (int)sizeof(T) * (2 * NB * (NB + 1) + 2 * NB * 9);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_bwd<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
-        cudaFuncSetAttribute(k_bwd<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
-        attr_set = true;
-    }
+    set_sweep_attrs<T, 32>();
+    set_sweep_attrs<T, 8>();
     if ((int64_t)nsns * ((nrhs + 31) / 32) >= 2 * 148) {
         dim3 grid(nsns, (nrhs + 31) / 32);
-        k_bwd<T, 32><<<grid, 256, smem32, st>>>(S, sns, L, dblk, W, ldw, nrhs);
+        k_bwd<T, 32><<<grid, 256, SweepSmem<T, 32>::bytes(), st>>>(S, sns, L, dblk, W, ldw, nrhs);
     } else {
         dim3 grid(nsns, (nrhs + 7) / 8);
-        k_bwd<T, 8><<<grid, 256, smem8, st>>>(S, sns, L, dblk, W, ldw, nrhs);
+        k_bwd<T, 8><<<grid, 256, SweepSmem<T, 8>::bytes(), st>>>(S, sns, L, dblk, W, ldw, nrhs);
+    }
+    if (launches) *launches += 1;
+}
+
+template <class T>
+void launch_fwd_subtrees(const DevSymbolic& S, const T* L, const T* dblk, T* W, int64_t ldw, int nrhs, T* tbuf,
+                         cudaStream_t st, int64_t* launches) {
+    if (S.nsubtrees <= 0 || nrhs <= 0) return;
+    set_sweep_attrs<T, 32>();
+    set_sweep_attrs<T, 8>();
+    if ((int64_t)S.nsubtrees * ((nrhs + 31) / 32) >= 2 * 148) {
+        dim3 grid(S.nsubtrees, (nrhs + 31) / 32);
+        k_fwd_subtree<T, 32><<<grid, 256, SweepSmem<T, 32>::bytes(), st>>>(S, L, dblk, W, ldw, nrhs, tbuf);
+    } else {
+        dim3 grid(S.nsubtrees, (nrhs + 7) / 8);
+        k_fwd_subtree<T, 8><<<grid, 256, SweepSmem<T, 8>::bytes(), st>>>(S, L, dblk, W, ldw, nrhs, tbuf);
+    }
+    if (launches) *launches += 1;
+}
+
+template <class T>
+void launch_bwd_subtrees(const DevSymbolic& S, const T* L, const T* dblk, T* W, int64_t ldw, int nrhs,
+                         cudaStream_t st, int64_t* launches) {
+    if (S.nsubtrees <= 0 || nrhs <= 0) return;
+    set_sweep_attrs<T, 32>();
+    set_sweep_attrs<T, 8>();
+    if ((int64_t)S.nsubtrees * ((nrhs + 31) / 32) >= 2 * 148) {
+        dim3 grid(S.nsubtrees, (nrhs + 31) / 32);
+        k_bwd_subtree<T, 32><<<grid, 256, SweepSmem<T, 32>::bytes(), st>>>(S, L, dblk, W, ldw, nrhs);
+    } else {
+        dim3 grid(S.nsubtrees, (nrhs + 7) / 8);
+        k_bwd_subtree<T, 8><<<grid, 256, SweepSmem<T, 8>::bytes(), st>>>(S, L, dblk, W, ldw, nrhs);
     }
     if (launches) *launches += 1;
 }
@@ -645,15 +791,20 @@ void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int m
 // ---- explicit instantiations ----
 #define DRE_INST(T)                                                                                                  \
     template void launch_assemble<T>(const DevSymbolic&, T*, double, T, cudaStream_t, int64_t*);                     \
-    template void launch_extend_add<T>(const DevSymbolic&, const int32_t*, int, int, T*, T*, const T*, cudaStream_t, \
+    template void launch_extend_add<T>(const DevSymbolic&, const int32_t*, int, int, T*, T*, cudaStream_t,           \
                                        int64_t*);                                                                    \
     template void launch_front<T>(const DevSymbolic&, const int2*, int, T*, T*, int32_t*, cudaStream_t, int64_t*);   \
     template void launch_schur<T>(const DevSymbolic&, const int4*, int, const T*, const T*, T*, cudaStream_t,        \
                                   int64_t*);                                                                         \
+    template void launch_factor_subtrees<T>(const DevSymbolic&, T*, T*, T*, int32_t*, cudaStream_t, int64_t*);       \
     template void launch_fwd_level<T>(const DevSymbolic&, const int32_t*, int, const T*, const T*, T*, int64_t, int, \
-                                      T*, const T*, cudaStream_t, int64_t*);                                         \
+                                      T*, cudaStream_t, int64_t*);                                                   \
     template void launch_bwd_level<T>(const DevSymbolic&, const int32_t*, int, const T*, const T*, T*, int64_t, int, \
                                       cudaStream_t, int64_t*);                                                       \
+    template void launch_fwd_subtrees<T>(const DevSymbolic&, const T*, const T*, T*, int64_t, int, T*, cudaStream_t, \
+                                         int64_t*);                                                                  \
+    template void launch_bwd_subtrees<T>(const DevSymbolic&, const T*, const T*, T*, int64_t, int, cudaStream_t,     \
+                                         int64_t*);                                                                  \
     template void launch_load_rhs<T>(T*, int64_t, const double*, int64_t, int, const double*, int64_t, int, int64_t, \
                                      cudaStream_t, int64_t*);                                                        \
     template void launch_smw_core<T>(const T*, int64_t, int, int, double, T*, int32_t*, cudaStream_t, int64_t*);     \

@@ -12,6 +12,7 @@ NB = 32
 
 class Sym:
     def __init__(self, sa):
+        self._sa = sa
         for name in ("perm", "iperm", "sn_first", "sn_rowptr", "sn_rows", "sn_parent", "sn_level", "level_ptr",
                      "level_sn", "panel_off", "upd_off", "rhs_off", "child_ptr", "child_idx", "relmap", "asm_dest",
                      "asm_a", "asm_e", "csr_ptr", "csr_col", "csr_a", "csr_e"):

@@ -178,11 +178,15 @@ def _free_run_check(n, nsteps, ros, dt):
         for r in ro.runs[:i * per_step]:
             unconverged = max(unconverged, r["res"][-1][1] / r["res"][0][1])
         assert np.linalg.norm(Kg - Ko) / np.linalg.norm(Ko) <= max(1e-8, 100 * self_dev, unconverged)
-    for a, b in zip(ro.runs, rg.runs):
-        if a["iters"] >= 100:  # solves that run into the maxiters cap must do so on the GPU too
-            assert b["iters"] == a["iters"]
+    # Iteration counts of a free run inherit the same sensitivity (identical counts are asserted in lock-step,
+    # test_lockstep_parity_forced_shifts).  Here the GPU count must lie in the band spanned by the two CPU
+    # runs, widened by 40 %; a solve that both CPU runs end at the maxiters cap must get (nearly) there too.
+    for a, p_, b in zip(ro.runs, rp.runs, rg.runs):
+        lo, hi = min(a["iters"], p_["iters"]), max(a["iters"], p_["iters"])
+        if lo >= 100:
+            assert b["iters"] >= 85, (a["iters"], p_["iters"], b["iters"])
         else:
-            assert abs(b["iters"] - a["iters"]) <= 0.4 * a["iters"]
+            assert 0.6 * lo <= b["iters"] <= min(100, 1.4 * hi), (a["iters"], p_["iters"], b["iters"])
     return so, sg, ro, rg
 
 

@@ -12,6 +12,10 @@ from tests import hostcheck
 pencils = dre_b200.pencils
 
 
+def sa_export(S, name):
+    return S._sa.export(name)
+
+
 def _check_structure(S):
     n = S.n
     assert sorted(S.perm.tolist()) == list(range(n))
@@ -29,6 +33,35 @@ def _check_structure(S):
             assert np.all(np.diff(rel) > 0) and rel[-1] < S.s(P) + S.u(P)
         else:
             assert S.sn_parent[J] == -1
+    # device processing order: bottom subtrees (ascending lists), then top levels; every child must be
+    # finished before its parent, and a subtree must contain all descendants of its root
+    sub = sa_export(S, "sn_subtree")
+    st_ptr, st_sn = sa_export(S, "st_ptr"), sa_export(S, "st_sn")
+    tl_ptr, tl_sn = sa_export(S, "top_level_ptr"), sa_export(S, "top_level_sn")
+    order = {}
+    k = 0
+    for t in range(len(st_ptr) - 1):
+        lst = st_sn[st_ptr[t]:st_ptr[t + 1]]
+        assert np.all(np.diff(lst) > 0) and np.all(sub[lst] == t)
+        for J in lst:
+            order[int(J)] = (0, t, k)
+            k += 1
+    for l in range(len(tl_ptr) - 1):
+        for J in tl_sn[tl_ptr[l]:tl_ptr[l + 1]]:
+            assert sub[J] == -1
+            order[int(J)] = (1, l, 0)
+    assert len(order) == S.nsn
+    for J in range(S.nsn):
+        P = S.sn_parent[J]
+        if P < 0:
+            continue
+        if sub[P] >= 0:
+            assert sub[J] == sub[P] and order[J][2] < order[P][2]
+        elif sub[J] >= 0:
+            pass  # subtree root below a top supernode: bottom phase runs first
+        else:
+            assert order[J][1] < order[P][1]
+    assert S.s(0) <= 32 and max(S.s(J) for J in range(S.nsn)) <= 32
 
 
 @pytest.mark.parametrize("n", [371, 1357])
