@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "dre_symbolic_export", "dre_create", "dre_destroy", "dre_sync", "dre_set_pencil", "dre_get_symbolic_info",
     "dre_mat_create", "dre_mat_free", "dre_mat_upload", "dre_mat_download", "dre_mat_copy", "dre_mat_axpby",
     "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_shift_solve", "dre_adi_step",
-    "dre_ldlt_norm", "dre_ldlt_compress", "dre_rrqr", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
+    "dre_ldlt_norm", "dre_ldlt_compress", "dre_rrqr", "dre_debug_export", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
     "dre_stats_get",
 ]
 
@@ -101,6 +101,7 @@ def load():
     lib.dre_ldlt_compress.argtypes = [p, i32, C.POINTER(View), C.POINTER(pdbl), pi64, pdbl, dbl, View, pdbl,
                                       C.POINTER(i32)]
     lib.dre_rrqr.argtypes = [p, i32, C.POINTER(View), dbl, dbl, View, pdbl, i64, C.POINTER(i32)]
+    lib.dre_debug_export.argtypes = [p, C.c_char_p, p, i64, pi64]
     lib.dre_timer_start.argtypes = [p]
     lib.dre_timer_stop.argtypes = [p, pdbl]
     lib.dre_stats_reset.argtypes = [p, i32]
@@ -212,6 +213,15 @@ class Context:
         info = SymbolicInfo()
         self.check(self.lib.dre_get_symbolic_info(self.h, C.byref(info)))
         return info.as_dict()
+
+    def debug_export(self, what, complex_valued=False):
+        """Raw numeric-factorization arrays ("L", "Linv", "dvec", "U") of the factorization currently held."""
+        ln = C.c_int64(0)
+        self.check(self.lib.dre_debug_export(self.h, what.encode(), None, 0, C.byref(ln)))
+        buf = np.empty(ln.value // (16 if complex_valued else 8), dtype=np.complex128 if complex_valued else np.float64)
+        self.check(self.lib.dre_debug_export(self.h, what.encode(), buf.ctypes.data_as(C.c_void_p), ln.value,
+                                             C.byref(ln)))
+        return buf
 
     def timer_start(self):
         self.check(self.lib.dre_timer_start(self.h))

@@ -7,7 +7,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,6 +45,40 @@ struct Panel {
     int cols = 0;
     int64_t ld = 0;
     bool alive = false;
+    size_t cap = 0;   // bytes of the underlying block (>= n * ld * 8)
+};
+
+// Caching allocator for the panels.  Everything runs on ONE stream, so a block released by dre_mat_free can
+// be handed out again immediately (its next use is stream-ordered behind the last one); blocks only go back
+// to the driver when an allocation fails or the context dies.  The stream-ordered pool of the driver
+// (cudaMallocAsync) was measured at 25 ms per 150 MB panel in the ADI loop (tools/host_profile.py):
+// growing / re-mapping the pool stalls the launch thread while the GPU drains.
+struct BlockCache {
+    std::vector<std::pair<size_t, void*>> free_blocks;  // (bytes, ptr)
+    size_t cached_bytes = 0;
+    // smallest cached block with  bytes <= size <= 1.5 * bytes + 1 MiB ; *got = its size
+    void* take(size_t bytes, size_t* got) {
+        int best = -1;
+        for (int i = 0; i < (int)free_blocks.size(); ++i) {
+            const size_t b = free_blocks[i].first;
+            if (b >= bytes && b <= bytes + bytes / 2 + (1u << 20) && (best < 0 || b < free_blocks[best].first)) best = i;
+        }
+        if (best < 0) return nullptr;
+        void* p = free_blocks[best].second;
+        *got = free_blocks[best].first;
+        cached_bytes -= *got;
+        free_blocks.erase(free_blocks.begin() + best);
+        return p;
+    }
+    void give(size_t bytes, void* p) {
+        free_blocks.emplace_back(bytes, p);
+        cached_bytes += bytes;
+    }
+    void flush() {
+        for (auto& b : free_blocks) cudaFree(b.second);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
 };
 
 }  // namespace
@@ -69,23 +105,23 @@ struct dre_context {
     double* d_csr_a = nullptr;
     double* d_csr_e = nullptr;
     int32_t* d_level_sn = nullptr;
-    // per-level work lists
-    struct LevelWork {   // one per TOP level
-        int sn_begin = 0, sn_count = 0;
+    // per-level work lists (levels = heights in the supernodal tree, leaves first)
+    struct LevelWork {
+        int sn_begin = 0, sn_count = 0, smax = 0;
         int ea_begin = 0, ea_count = 0, ea_gy = 1;
-        int front_begin = 0, front_count = 0;
+        int l21_begin = 0, l21_count = 0;
         int schur_begin = 0, schur_count = 0;
-        int64_t upd_begin = 0, upd_elems = 0;
     };
     std::vector<LevelWork> levels;
     int32_t* d_ea_parents = nullptr;
-    int2* d_front_items = nullptr;
+    int2* d_l21_items = nullptr;
     int4* d_schur_items = nullptr;
-    int64_t dblk_elems = 0;
+    int64_t linv_elems = 0, upd_elems = 0;
 
     // factor storage (sized for complex, reused for real)
     void* d_L = nullptr;
-    void* d_dblk = nullptr;
+    void* d_Linv = nullptr;
+    void* d_dvec = nullptr;
     void* d_U = nullptr;
     DBuf<unsigned char> tbuf;
     DBuf<unsigned char> Wbuf;
@@ -103,6 +139,7 @@ struct dre_context {
 
     // panels
     std::vector<Panel> panels;
+    BlockCache cache;
 
     // dense workspaces
     DBuf<double> gram_partial, gbuf, gbuf2, cbuf, wsel, wsel2, small, stage, qws, pws, qtmp, rt, tmp_panel, evals;
@@ -185,6 +222,20 @@ int check_errflag(dre_context* c) {
     return DRE_OK;
 }
 
+// host wall-clock trace of the C-ABI internals (DRE_TRACE=1): where does the launching thread block?
+static const bool g_trace = getenv("DRE_TRACE") != nullptr;
+struct HostTrace {
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTrace(const char* n) : name(n) { if (g_trace) t0 = std::chrono::steady_clock::now(); }
+    ~HostTrace() {
+        if (g_trace) {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (ms > 0.5) fprintf(stderr, "[dre trace] %-24s %9.3f ms\n", name, ms);
+        }
+    }
+};
+
 struct Timer {
     dre_context* c;
     double* acc;
@@ -239,22 +290,24 @@ int factor(dre_context* c, T emu) {
     const Symbolic& S = c->sym;
     Timer t(c, &c->stats.ms_factor);
     T* L = (T*)c->d_L;
-    T* dblk = (T*)c->d_dblk;
+    T* Linv = (T*)c->d_Linv;
+    T* dvec = (T*)c->d_dvec;
     T* U = (T*)c->d_U;
     CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), c->st));
+    if (c->upd_elems > 0) CU(cudaMemsetAsync(U, 0, (size_t)c->upd_elems * sizeof(T), c->st));
     launch_assemble<T>(c->dS, L, c->op_a, emu, c->st, &c->stats.kernel_launches);
-    launch_factor_subtrees<T>(c->dS, L, dblk, U, c->d_errflag, c->st, &c->stats.kernel_launches);
-    for (int l = 0; l < S.ntoplevels; ++l) {
+    for (int l = 0; l < S.nlevels; ++l) {
         const dre_context::LevelWork& lw = c->levels[l];
-        if (lw.upd_elems > 0)
-            CU(cudaMemsetAsync(U + lw.upd_begin, 0, (size_t)lw.upd_elems * sizeof(T), c->st));
         if (lw.ea_count > 0)
             launch_extend_add<T>(c->dS, c->d_ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, U, c->st,
                                  &c->stats.kernel_launches);
-        launch_front<T>(c->dS, c->d_front_items + lw.front_begin, lw.front_count, L, dblk, c->d_errflag, c->st,
-                        &c->stats.kernel_launches);
+        launch_diag<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, Linv, dvec, c->d_errflag, c->st,
+                       &c->stats.kernel_launches);
+        if (lw.l21_count > 0)
+            launch_l21<T>(c->dS, c->d_l21_items + lw.l21_begin, lw.l21_count, L, Linv, dvec, c->st,
+                          &c->stats.kernel_launches);
         if (lw.schur_count > 0)
-            launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dblk, U, c->st,
+            launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dvec, U, c->st,
                             &c->stats.kernel_launches);
     }
     CU(cudaGetLastError());
@@ -267,22 +320,24 @@ template <class T>
 int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
     const Symbolic& S = c->sym;
     Timer t(c, &c->stats.ms_solve);
-    CU(c->tbuf.ensure((size_t)std::max<int64_t>(S.sum_u, 1) * ldw * sizeof(T)));
+    {
+        HostTrace tr("tbuf.ensure");
+        CU(c->tbuf.ensure((size_t)std::max<int64_t>(S.sum_u, 1) * ldw * sizeof(T)));
+    }
     const T* L = (const T*)c->d_L;
-    const T* dblk = (const T*)c->d_dblk;
+    const T* Linv = (const T*)c->d_Linv;
+    const T* dvec = (const T*)c->d_dvec;
     T* tb = (T*)c->tbuf.p;
-    launch_fwd_subtrees<T>(c->dS, L, dblk, W, ldw, nrhs, tb, c->st, &c->stats.kernel_launches);
-    for (int l = 0; l < S.ntoplevels; ++l) {
+    for (int l = 0; l < S.nlevels; ++l) {
         const dre_context::LevelWork& lw = c->levels[l];
-        launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, dblk, W, ldw, nrhs, tb, c->st,
-                            &c->stats.kernel_launches);
+        launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, lw.smax, L, Linv, W, ldw, nrhs, tb,
+                            c->st, &c->stats.kernel_launches);
     }
-    for (int l = S.ntoplevels - 1; l >= 0; --l) {
+    for (int l = S.nlevels - 1; l >= 0; --l) {
         const dre_context::LevelWork& lw = c->levels[l];
-        launch_bwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, dblk, W, ldw, nrhs, c->st,
-                            &c->stats.kernel_launches);
+        launch_bwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, lw.smax, L, Linv, dvec, W, ldw, nrhs,
+                            c->st, &c->stats.kernel_launches);
     }
-    launch_bwd_subtrees<T>(c->dS, L, dblk, W, ldw, nrhs, c->st, &c->stats.kernel_launches);
     CU(cudaGetLastError());
     c->stats.solves++;
     {   // 2*nnz(L)*w (factor read once per sweep) + 4*n*r_tot*w (RHS read+write per sweep)
@@ -303,7 +358,10 @@ int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_
     const int r = R.ncols, m = c->op_U.ncols;
     const int nrhs = r + m;
     const int64_t ldw = (nrhs + 3) & ~3;
-    CU(c->Wbuf.ensure((size_t)n * ldw * sizeof(T)));
+    {
+        HostTrace tr("Wbuf.ensure");
+        CU(c->Wbuf.ensure((size_t)n * ldw * sizeof(T)));
+    }
     T* W = (T*)c->Wbuf.p;
     launch_load_rhs<T>(W, ldw, vptr(c, R), vld(c, R), r, m ? vptr(c, c->op_Vt) : nullptr, m ? vld(c, c->op_Vt) : 0, m,
                        n, c->st, &c->stats.kernel_launches);
@@ -314,12 +372,16 @@ int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_
     if (!(c->fact_valid && c->fact_a == c->op_a && c->fact_re == c->op_e + mu_re && c->fact_im == mu_im &&
           c->fact_tw == tw)) {
         c->fact_valid = false;
+        HostTrace tr(sizeof(T) == 8 ? "factor<double> launch" : "factor<cplx> launch");
         rc = factor<T>(c, emu);
         if (rc) return rc;
         c->fact_valid = true;
         c->fact_a = c->op_a; c->fact_re = c->op_e + mu_re; c->fact_im = mu_im; c->fact_tw = tw;
     }
-    rc = solve_sweeps<T>(c, W, ldw, nrhs);
+    {
+        HostTrace tr(sizeof(T) == 8 ? "sweeps<double> launch" : "sweeps<cplx> launch");
+        rc = solve_sweeps<T>(c, W, ldw, nrhs);
+    }
     if (rc) return rc;
     T* Sol = nullptr;
     if (m > 0) {
@@ -462,10 +524,9 @@ int32_t dre_symbolic_create(int64_t n, const int64_t* Ecp, const int64_t* Eri, c
     if (!out || !Ecp || !Eri || !Enz || !Acp || !Ari || !Anz) return fail(nullptr, DRE_ERR_ARG, "null argument");
     dre_symbolic* s = new (std::nothrow) dre_symbolic();
     if (!s) return fail(nullptr, DRE_ERR_LIB, "out of host memory");
-    AnalyzeOptions opt;
-    if (leaf_size > 0) opt.leaf_size = leaf_size & 0xffff;
-    if ((leaf_size >> 16) > 0) opt.max_snode = leaf_size >> 16;  // upper half-word: supernode width cap
-    else opt.max_snode = 32;                                     // what dre_set_pencil uses
+    AnalyzeOptions opt;   // defaults = what dre_set_pencil uses
+    if ((leaf_size & 0xffff) > 0) opt.leaf_size = leaf_size & 0xffff;
+    if ((leaf_size >> 16) > 0) opt.max_snode = std::min(leaf_size >> 16, (int)SN_MAX);  // upper half-word: width cap
     std::string e;
     try {
         e = analyze(n, Ecp, Eri, Enz, Acp, Ari, Anz, base, opt, s->sym);
@@ -520,11 +581,7 @@ int32_t dre_symbolic_export(const dre_symbolic* s, const char* what, void* buf, 
     if (w == "sn_rows") return put_i(S.sn_rows);
     if (w == "sn_parent") return put_i(S.sn_parent);
     if (w == "sn_level") return put_i(S.sn_level);
-    if (w == "sn_subtree") return put_i(S.sn_subtree);
-    if (w == "st_ptr") return put_i(S.st_ptr);
-    if (w == "st_sn") return put_i(S.st_sn);
-    if (w == "top_level_ptr") return put_i(S.top_level_ptr);
-    if (w == "top_level_sn") return put_i(S.top_level_sn);
+    if (w == "linv_off") return put_i(S.linv_off);
     if (w == "level_ptr") return put_i(S.level_ptr);
     if (w == "level_sn") return put_i(S.level_sn);
     if (w == "panel_off") return put_i(S.panel_off);
@@ -581,9 +638,10 @@ static void release_pencil(dre_context* c) {
     for (void* p : c->owned) cudaFree(p);
     c->owned.clear();
     if (c->d_L) cudaFree(c->d_L);
-    if (c->d_dblk) cudaFree(c->d_dblk);
+    if (c->d_Linv) cudaFree(c->d_Linv);
+    if (c->d_dvec) cudaFree(c->d_dvec);
     if (c->d_U) cudaFree(c->d_U);
-    c->d_L = c->d_dblk = c->d_U = nullptr;
+    c->d_L = c->d_Linv = c->d_dvec = c->d_U = nullptr;
     c->has_pencil = false;
     c->fact_valid = false;
 }
@@ -593,6 +651,7 @@ int32_t dre_destroy(dre_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     for (Panel& p : c->panels) if (p.alive && p.d) cudaFree(p.d);
+    c->cache.flush();
     release_pencil(c);
     c->tbuf.release(); c->Wbuf.release(); c->btw.release(); c->sol.release();
     c->gram_partial.release(); c->gbuf.release(); c->gbuf2.release(); c->cbuf.release(); c->wsel.release();
@@ -624,10 +683,12 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     CU(cudaStreamSynchronize(c->st));
     release_pencil(c);
     for (Panel& p : c->panels) if (p.alive && p.d) { cudaFree(p.d); p.alive = false; p.d = nullptr; }
+    c->cache.flush();
     c->op_U = c->op_Vt = dre_view{-1, 0, 0};
     AnalyzeOptions opt;
-    opt.leaf_size = 32;
-    opt.max_snode = 32;  // the kernels assume a single 32-column block per supernode
+    if (const char* ev = getenv("DRE_LEAF_SIZE")) opt.leaf_size = std::max(8, atoi(ev));
+    if (const char* ev = getenv("DRE_MAX_SNODE")) opt.max_snode = std::max(8, atoi(ev));
+    opt.max_snode = std::min(opt.max_snode, (int)SN_MAX);
     std::string e;
     try {
         e = analyze(n, Ecp, Eri, Enz, Acp, Ari, Anz, base, opt, c->sym);
@@ -636,15 +697,13 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     }
     if (!e.empty()) return fail(c, DRE_ERR_ARG, e);
     const Symbolic& S = c->sym;
-
-    // diagonal-block side storage offsets
-    std::vector<int64_t> dblk_off(S.nsn + 1, 0);
-    for (int J = 0; J < S.nsn; ++J) dblk_off[J + 1] = dblk_off[J] + (int64_t)((S.sn_size(J) + 31) / 32) * 1024;
-    c->dblk_elems = dblk_off[S.nsn];
+    if (S.max_sn > SN_MAX) return fail(c, DRE_ERR_STATE, "internal error: supernode wider than SN_MAX");
+    c->linv_elems = S.linv_off[S.nsn];
+    c->upd_elems = S.upd_off[S.nsn];
 
     int rc;
-    int32_t *d_sn_first, *d_sn_rows, *d_relmap, *d_child_ptr, *d_child_idx, *d_st_ptr, *d_st_sn;
-    int64_t *d_sn_rowptr, *d_panel_off, *d_upd_off, *d_rhs_off, *d_dblk_off, *d_asm_dest;
+    int32_t *d_sn_first, *d_sn_rows, *d_relmap, *d_child_ptr, *d_child_idx;
+    int64_t *d_sn_rowptr, *d_panel_off, *d_linv_off, *d_upd_off, *d_rhs_off, *d_asm_dest;
     double *d_asm_a, *d_asm_e;
     if ((rc = upload_vec(c, S.sn_first, &d_sn_first))) return rc;
     if ((rc = upload_vec(c, S.sn_rowptr, &d_sn_rowptr))) return rc;
@@ -653,11 +712,9 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     if ((rc = upload_vec(c, S.child_ptr, &d_child_ptr))) return rc;
     if ((rc = upload_vec(c, S.child_idx, &d_child_idx))) return rc;
     if ((rc = upload_vec(c, S.panel_off, &d_panel_off))) return rc;
+    if ((rc = upload_vec(c, S.linv_off, &d_linv_off))) return rc;
     if ((rc = upload_vec(c, S.upd_off, &d_upd_off))) return rc;
     if ((rc = upload_vec(c, S.rhs_off, &d_rhs_off))) return rc;
-    if ((rc = upload_vec(c, dblk_off, &d_dblk_off))) return rc;
-    if ((rc = upload_vec(c, S.st_ptr, &d_st_ptr))) return rc;
-    if ((rc = upload_vec(c, S.st_sn, &d_st_sn))) return rc;
     if ((rc = upload_vec(c, S.asm_dest, &d_asm_dest))) return rc;
     if ((rc = upload_vec(c, S.asm_a, &d_asm_a))) return rc;
     if ((rc = upload_vec(c, S.asm_e, &d_asm_e))) return rc;
@@ -666,55 +723,52 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     if ((rc = upload_vec(c, S.csr_col, &c->d_csr_col))) return rc;
     if ((rc = upload_vec(c, S.csr_a, &c->d_csr_a))) return rc;
     if ((rc = upload_vec(c, S.csr_e, &c->d_csr_e))) return rc;
-    if ((rc = upload_vec(c, S.top_level_sn, &c->d_level_sn))) return rc;
+    if ((rc = upload_vec(c, S.level_sn, &c->d_level_sn))) return rc;
     DevSymbolic& D = c->dS;
-    D.n = S.n; D.nsn = S.nsn; D.nlevels = S.nlevels; D.nsubtrees = S.nsubtrees;
+    D.n = S.n; D.nsn = S.nsn; D.nlevels = S.nlevels;
     D.sn_first = d_sn_first; D.sn_rowptr = d_sn_rowptr; D.sn_rows = d_sn_rows; D.relmap = d_relmap;
-    D.child_ptr = d_child_ptr; D.child_idx = d_child_idx; D.panel_off = d_panel_off; D.upd_off = d_upd_off;
-    D.rhs_off = d_rhs_off; D.dblk_off = d_dblk_off; D.st_ptr = d_st_ptr; D.st_sn = d_st_sn;
+    D.child_ptr = d_child_ptr; D.child_idx = d_child_idx; D.panel_off = d_panel_off; D.linv_off = d_linv_off;
+    D.upd_off = d_upd_off; D.rhs_off = d_rhs_off;
     D.nasm = (int64_t)S.asm_dest.size(); D.asm_dest = d_asm_dest; D.asm_a = d_asm_a; D.asm_e = d_asm_e;
 
-    // per-level work lists of the TOP part of the tree
-    c->levels.assign(S.ntoplevels, dre_context::LevelWork());
+    // per-level work lists
+    c->levels.assign(S.nlevels, dre_context::LevelWork());
     std::vector<int32_t> ea_parents;
-    std::vector<int2> front_items;
+    std::vector<int2> l21_items;
     std::vector<int4> schur_items;
-    for (int l = 0; l < S.ntoplevels; ++l) {
+    for (int l = 0; l < S.nlevels; ++l) {
         dre_context::LevelWork& lw = c->levels[l];
-        lw.sn_begin = S.top_level_ptr[l];
-        lw.sn_count = S.top_level_ptr[l + 1] - S.top_level_ptr[l];
-        lw.upd_begin = S.top_level_upd_begin[l];
-        lw.upd_elems = S.top_level_upd_elems[l];
+        lw.sn_begin = S.level_ptr[l];
+        lw.sn_count = S.level_ptr[l + 1] - S.level_ptr[l];
         lw.ea_begin = (int)ea_parents.size();
-        lw.front_begin = (int)front_items.size();
+        lw.l21_begin = (int)l21_items.size();
         lw.schur_begin = (int)schur_items.size();
         int max_f = 0;
-        for (int p = S.top_level_ptr[l]; p < S.top_level_ptr[l + 1]; ++p) {
-            const int J = S.top_level_sn[p];
-            const int s = S.sn_size(J), u = S.sn_nrows(J);
-            if (s > 32) return fail(c, DRE_ERR_STATE, "internal error: supernode wider than 32 columns");
+        for (int p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p) {
+            const int J = S.level_sn[p];
+            const int u = S.sn_nrows(J);
+            lw.smax = std::max(lw.smax, S.sn_size(J));
             max_f = std::max(max_f, S.front(J));
             if (S.child_ptr[J + 1] > S.child_ptr[J]) ea_parents.push_back(J);
-            const int nslab = std::max(1, (u + 95) / 96);
-            for (int sl = 0; sl < nslab; ++sl) front_items.push_back(make_int2(J, sl));
+            for (int sl = 0; sl * 64 < u; ++sl) l21_items.push_back(make_int2(J, sl));
             const int nt = (u + 63) / 64;
             for (int ti = 0; ti < nt; ++ti)
                 for (int tj = 0; tj <= ti; ++tj) schur_items.push_back(make_int4(J, ti, tj, 0));
         }
         lw.ea_count = (int)ea_parents.size() - lw.ea_begin;
-        lw.front_count = (int)front_items.size() - lw.front_begin;
+        lw.l21_count = (int)l21_items.size() - lw.l21_begin;
         lw.schur_count = (int)schur_items.size() - lw.schur_begin;
         lw.ea_gy = std::min(64, std::max(1, max_f / 8));
     }
     if ((rc = upload_vec(c, ea_parents, &c->d_ea_parents))) return rc;
-    if ((rc = upload_vec(c, front_items, &c->d_front_items))) return rc;
+    if ((rc = upload_vec(c, l21_items, &c->d_l21_items))) return rc;
     if ((rc = upload_vec(c, schur_items, &c->d_schur_items))) return rc;
 
     // factor storage, sized for complex
     CU(cudaMalloc(&c->d_L, (size_t)std::max<int64_t>(S.nnz_L, 1) * sizeof(cplx)));
-    CU(cudaMalloc(&c->d_dblk, (size_t)std::max<int64_t>(c->dblk_elems, 1) * sizeof(cplx)));
-    CU(cudaMalloc(&c->d_U, (size_t)std::max<int64_t>(S.upd_bottom_elems + S.max_upd_level[0] + S.max_upd_level[1], 1) *
-                               sizeof(cplx)));
+    CU(cudaMalloc(&c->d_Linv, (size_t)std::max<int64_t>(c->linv_elems, 1) * sizeof(cplx)));
+    CU(cudaMalloc(&c->d_dvec, (size_t)S.n * sizeof(cplx)));
+    CU(cudaMalloc(&c->d_U, (size_t)std::max<int64_t>(c->upd_elems, 1) * sizeof(cplx)));
     c->has_pencil = true;
     c->op_a = 1.0; c->op_e = 0.0; c->op_alpha = 1.0;
     return DRE_OK;
@@ -735,7 +789,25 @@ int32_t dre_mat_create(dre_context* c, int32_t cols, int32_t* id) {
     Panel p;
     p.cols = cols;
     p.ld = std::max(1, (cols + 1) & ~1);  // even leading dimension: 16-byte aligned rows
-    CU(cudaMallocAsync((void**)&p.d, (size_t)c->sym.n * p.ld * sizeof(double), c->st));
+    {
+        // size classes of 8 columns keep slightly different residual widths (242, 244, ...) interchangeable
+        const size_t want = (size_t)c->sym.n * (size_t)((p.ld + 7) & ~7) * sizeof(double);
+        size_t got = 0;
+        void* blk = c->cache.take(want, &got);
+        if (!blk) {
+            HostTrace tr("panel cudaMalloc");
+            cudaError_t e = cudaMalloc(&blk, want);
+            if (e != cudaSuccess) {  // give the cached blocks back to the driver and retry once
+                cudaGetLastError();
+                CU(cudaStreamSynchronize(c->st));
+                c->cache.flush();
+                CU(cudaMalloc(&blk, want));
+            }
+            got = want;
+        }
+        p.d = (double*)blk;
+        p.cap = got;
+    }
     p.alive = true;
     for (size_t i = 0; i < c->panels.size(); ++i)
         if (!c->panels[i].alive) { c->panels[i] = p; *id = (int32_t)i; return DRE_OK; }
@@ -748,7 +820,7 @@ int32_t dre_mat_free(dre_context* c, int32_t id) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     if (id < 0 || id >= (int)c->panels.size() || !c->panels[id].alive) return fail(c, DRE_ERR_ARG, "invalid panel id");
     if (c->op_U.id == id || c->op_Vt.id == id) c->op_U = c->op_Vt = dre_view{-1, 0, 0};
-    CU(cudaFreeAsync(c->panels[id].d, c->st));
+    c->cache.give(c->panels[id].cap, c->panels[id].d);
     c->panels[id].alive = false;
     c->panels[id].d = nullptr;
     return DRE_OK;
@@ -1129,6 +1201,26 @@ int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double d
     CU(cudaStreamSynchronize(c->st));
     for (int i = 0; i < ktot; ++i)
         for (int j = 0; j < rho; ++j) Rt[i + (int64_t)j * ldr] = c->h_pinned[(int64_t)i * s.ldrt + j];
+    return check_errflag(c);
+}
+
+int32_t dre_debug_export(dre_context* c, const char* what, void* buf, int64_t cap_bytes, int64_t* len_bytes) {
+    if (!c || !what || !len_bytes) return fail(c, DRE_ERR_ARG, "null argument");
+    if (!c->has_pencil || !c->fact_valid) return fail(c, DRE_ERR_STATE, "no numeric factorization held");
+    const std::string w(what);
+    const size_t tw = (size_t)c->fact_tw * sizeof(double);
+    const void* src = nullptr;
+    size_t bytes = 0;
+    if (w == "L") { src = c->d_L; bytes = (size_t)c->sym.nnz_L * tw; }
+    else if (w == "Linv") { src = c->d_Linv; bytes = (size_t)c->linv_elems * tw; }
+    else if (w == "dvec") { src = c->d_dvec; bytes = (size_t)c->sym.n * tw; }
+    else if (w == "U") { src = c->d_U; bytes = (size_t)c->upd_elems * tw; }
+    else return fail(c, DRE_ERR_ARG, "dre_debug_export: unknown array name " + w);
+    *len_bytes = (int64_t)bytes;
+    if (buf && cap_bytes > 0) {
+        CU(cudaStreamSynchronize(c->st));
+        CU(cudaMemcpy(buf, src, std::min<size_t>(bytes, (size_t)cap_bytes), cudaMemcpyDeviceToHost));
+    }
     return check_errflag(c);
 }
 

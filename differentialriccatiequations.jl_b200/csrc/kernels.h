@@ -61,9 +61,16 @@ void launch_spmm(const int32_t* ptr, const int32_t* col, const double* val, int6
                  int64_t* launches);
 
 // ---------------- sparse: supernodal LDL^T + block solves ----------------
+// Supernodes are dense and wide (a dissection leaf is one supernode of up to ~100 columns, separators up to
+// SN_MAX columns).  Besides the panel L (f_J x s_J, column-major) the factorization stores the explicit
+// inverse of the unit-lower diagonal block (s_J x s_J, column-major, ones on / zeros above the diagonal) and
+// the pivots, so that every step of factorization and solves is a plain matrix product on the FP64 tensor
+// cores -- no dependent chain inside a supernode.
+constexpr int SN_MAX = 256;  // widest supernode the kernels accept (register accumulators of the sweeps)
+
 struct DevSymbolic {
     int64_t n;
-    int32_t nsn, nlevels, nsubtrees;
+    int32_t nsn, nlevels;
     const int32_t* sn_first;
     const int64_t* sn_rowptr;
     const int32_t* sn_rows;
@@ -71,11 +78,9 @@ struct DevSymbolic {
     const int32_t* child_ptr;
     const int32_t* child_idx;
     const int64_t* panel_off;
-    const int64_t* upd_off;    // absolute offsets of the update matrices (bottom region, then top ping-pong)
+    const int64_t* linv_off;
+    const int64_t* upd_off;
     const int64_t* rhs_off;    // row offsets of the update vectors (cumulative over all supernodes)
-    const int64_t* dblk_off;   // offset of the supernode's 32x32 block: pivots + inverse unit-lower factor
-    const int32_t* st_ptr;     // bottom subtrees: supernode lists (ascending)
-    const int32_t* st_sn;
     // assembly
     int64_t nasm;
     const int64_t* asm_dest;
@@ -85,37 +90,31 @@ struct DevSymbolic {
 
 template <class T>
 void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t st, int64_t* launches);
-
-// top levels: extend-add of the children's update matrices into the parents of one level
+// parents of one level gather their children's update matrices (grid.y = gy column classes)
 template <class T>
 void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* U,
                        cudaStream_t st, int64_t* launches);
-// top levels: panel factorization of every front of a level; items: (J, slab) pairs
+// LDL^T of the s x s diagonal blocks of one level + inverse of the unit-lower factor (one CTA per supernode)
 template <class T>
-void launch_front(const DevSymbolic& S, const int2* items, int nitems, T* L, T* dblk, int32_t* errflag,
+void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, T* L, T* Linv, T* dvec, int32_t* errflag,
+                 cudaStream_t st, int64_t* launches);
+// L21 = A21 Linv' D^-1; items: (J, 64-row slab)
+template <class T>
+void launch_l21(const DevSymbolic& S, const int2* items, int nitems, T* L, const T* Linv, const T* dvec,
+                cudaStream_t st, int64_t* launches);
+// U_J -= L21 D L21'  (lower triangle, 64x64 tiles); items: (J, ti, tj)
+template <class T>
+void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dvec, T* U,
                   cudaStream_t st, int64_t* launches);
-// top levels: Schur complement  U_J -= L21 D L21'  (lower triangle, 64x64 tiles); items: (J, ti, tj)
-template <class T>
-void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dblk, T* U,
-                  cudaStream_t st, int64_t* launches);
-// bottom subtrees: one CTA factors a whole subtree
-template <class T>
-void launch_factor_subtrees(const DevSymbolic& S, T* L, T* dblk, T* U, int32_t* errflag, cudaStream_t st,
-                            int64_t* launches);
 
-// forward / backward sweeps on the row-major RHS block W (n x ldw), nrhs columns
+// forward / backward sweeps of one level on the row-major RHS block W (n x ldw), nrhs columns.
+// smax = widest supernode of the level (sizes the dynamic shared memory).
 template <class T>
-void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
-                      int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches);
+void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
+                      T* W, int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches);
 template <class T>
-void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
-                      int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches);
-template <class T>
-void launch_fwd_subtrees(const DevSymbolic& S, const T* L, const T* dblk, T* W, int64_t ldw, int nrhs, T* tbuf,
-                         cudaStream_t st, int64_t* launches);
-template <class T>
-void launch_bwd_subtrees(const DevSymbolic& S, const T* L, const T* dblk, T* W, int64_t ldw, int nrhs,
-                         cudaStream_t st, int64_t* launches);
+void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
+                      const T* dvec, T* W, int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches);
 
 // W[:, 0:r] = R, W[:, r:r+m] = Vt   (real -> T)
 template <class T>

@@ -8,24 +8,30 @@
 // T = double for real shifts, T = cplx (complex SYMMETRIC, no conjugation) for complex shifts --
 // the complex pair path the reference lists as broken on GPU (README.md:174-176).
 //
-// Structure (from csrc/symbolic.cpp): every supernode has at most 32 columns (wider dissection blocks
-// are chains).  The tree is cut into
-//   * bottom subtrees (<= a few hundred columns each): ONE CTA walks a whole subtree in elimination
-//     order, so the thousands of tiny fronts of the lower levels cost one launch per phase;
-//   * top supernodes, processed level by level (one launch per level and phase).
-// Storage: panel_J = f_J x s_J column-major (ld f_J), L21 below the supernode's own rows; the pivots and
-// the INVERSE of the unit-lower diagonal block live in a side array (32x32 per supernode) so that the
-// block solves are plain multiplications.  Update matrices: one region per bottom supernode plus two
-// ping-pong regions for the top levels.  Update vectors of the solves: one region per supernode,
-// column-major (u_J contiguous per right-hand side).
+// Design (from csrc/symbolic.cpp): supernodes are the nested-dissection blocks -- a leaf is ONE dense
+// supernode of up to ~100 columns, separators are split into chains of at most SN_MAX = 256 columns -- so
+// the elimination tree has ~a dozen levels and every level is a handful of fat launches:
+//   factor  : extend-add -> k_diag (LDL^T of the s x s diagonal block + explicit inverse of its unit-lower
+//             factor, one CTA per supernode) -> k_l21 (L21 = A21 Linv' D^-1, plain GEMM over row slabs)
+//             -> k_schur (U -= L21 D L21', 64x64 tiles)
+//   forward : y = Linv (b + children);  t = children - L21 y        (one launch per level)
+//   backward: x = Linv' (D^-1 y - L21' x_struct)                    (one launch per level)
+// Because the inverse of the diagonal block is explicit, no step contains a dependent chain: everything is
+// a matrix product and runs on the FP64 tensor cores (DMMA m8n8k4) with operand fragments loaded straight
+// from global memory / L2 (each factor entry is used by exactly one warp per right-hand-side chunk, so
+// staging it in shared memory would only add a barrier); right-hand sides live in shared memory.
+// Complex symmetric arithmetic uses the same 8x8x4 real tiles: an 8-column tile holds 4 complex columns
+// (re, im interleaved) and  C += Ar*[Xr Xi] + Ai*[-Xi Xr]  is two DMMAs.
+// Storage: panel_J = f_J x s_J column-major (ld f_J); Linv_J = s_J x s_J column-major (ones on, zeros above
+// the diagonal inside the 32x32 diagonal blocks); pivots in dvec[n]; update matrices u_J x u_J (lower) and
+// update vectors (u_J per right-hand side, column-major), one region per supernode.
 #include <algorithm>
 
 #include "kernels.h"
 
 namespace dre {
 
-constexpr int NB = 32;     // maximum supernode width
-constexpr int SLAB = 96;   // L21 rows handled per slab
+constexpr int NB = 32;     // block size of the in-supernode LDL^T
 
 __device__ __forceinline__ int sn_s(const DevSymbolic& S, int J) { return S.sn_first[J + 1] - S.sn_first[J]; }
 __device__ __forceinline__ int sn_u(const DevSymbolic& S, int J) { return (int)(S.sn_rowptr[J + 1] - S.sn_rowptr[J]); }
@@ -34,6 +40,105 @@ __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0
 __device__ __forceinline__ cplx shfl(cplx v, int src) {
     return mk(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
+
+// ------------------------------------------------------------------------------------------
+// FP64 tensor-core tiles, generic over T.  m8n8k4 fragments: lane l holds
+//   A[l>>2][l&3],  B[l&3][l>>2],  C[l>>2][2*(l&3) + {0,1}].
+// ------------------------------------------------------------------------------------------
+template <class T> struct MM;
+template <> struct MM<double> {
+    static constexpr int CPN = 8;  // T-columns covered by one 8x8 tile
+    __device__ __forceinline__ static int bcol(int lane) { return lane >> 2; }
+    __device__ __forceinline__ static void mma(double (&c)[2], double a, double b, int) { dmma884(c[0], c[1], a, b); }
+    template <class F>
+    __device__ __forceinline__ static void each(const double (&c)[2], int lane, F f) {
+        f(2 * (lane & 3), c[0]);
+        f(2 * (lane & 3) + 1, c[1]);
+    }
+};
+template <> struct MM<cplx> {
+    static constexpr int CPN = 4;
+    __device__ __forceinline__ static int bcol(int lane) { return lane >> 3; }
+    // b = X[k][complex column lane>>3]; the lane's real column is the re (even) or im (odd) part of it
+    __device__ __forceinline__ static void mma(double (&c)[2], cplx a, cplx b, int lane) {
+        const bool im = (lane >> 2) & 1;
+        dmma884(c[0], c[1], a.x, im ? b.y : b.x);
+        dmma884(c[0], c[1], a.y, im ? b.x : -b.y);
+    }
+    template <class F>
+    __device__ __forceinline__ static void each(const double (&c)[2], int lane, F f) {
+        f(lane & 3, mk(c[0], c[1]));
+    }
+};
+
+// shared-memory leading dimension (in T) of a right-hand-side tile with CW columns: fragment loads hit the
+// minimum of two wavefronts (real: ld = 8 mod 16 doubles; complex: ld = 4 mod 8 elements)
+template <class T, int CW>
+struct RhsLd {
+    static constexpr int value = sizeof(T) == 8 ? (((CW + 15) & ~15) + 8) : (((CW + 7) & ~7) + 4);
+};
+
+// acc[nt] (8 rows x NT tiles) += sum_{k in [kbeg, kend)} A(row, k) * B(k, tile nt)
+// fa(k): this lane's A element (row = lane>>2 fixed by the caller), fb(k, nt): this lane's B element.
+// Both must return zero outside their valid range (kend need not be a multiple of 4).
+template <class T, int NT, class FA, class FB>
+__device__ __forceinline__ void strip_mma(double (&acc)[NT][2], int kbeg, int kend, int lane, FA fa, FB fb) {
+    const int kk = lane & 3;
+    int k0 = kbeg;
+    for (; k0 + 16 <= kend; k0 += 16) {
+        T a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = fa(k0 + 4 * q + kk);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) MM<T>::mma(acc[nt], a[q], fb(k0 + 4 * q + kk, nt), lane);
+    }
+    for (; k0 < kend; k0 += 4) {
+        const T a = fa(k0 + kk);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) MM<T>::mma(acc[nt], a, fb(k0 + kk, nt), lane);
+    }
+}
+
+// 32 x 32 (in T) block product per warp: acc[mt][nt] += sum_{k<K} A(i, k) B(k, j)
+// fa(i, k), fb(k, j) with i, j in [0, 32) return zero outside their valid range.
+template <class T>
+struct Blk32 {
+    static constexpr int NTW = 32 / MM<T>::CPN;
+    double acc[4][NTW][2];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    }
+    template <class FA, class FB>
+    __device__ __forceinline__ void gemm(int K, int lane, FA fa, FB fb) {
+        const int kk = lane & 3, r = lane >> 2, bc = MM<T>::bcol(lane);
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            T a[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) a[mt] = fa(mt * 8 + r, k0 + kk);
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                const T b = fb(k0 + kk, nt * MM<T>::CPN + bc);
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) MM<T>::mma(acc[mt][nt], a[mt], b, lane);
+            }
+        }
+    }
+    // f(i, j, value) for every element of the block held by this lane
+    template <class F>
+    __device__ __forceinline__ void each(int lane, F f) const {
+        const int r = lane >> 2;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt)
+                MM<T>::each(acc[mt][nt], lane, [&](int c, T v) { f(mt * 8 + r, nt * MM<T>::CPN + c, v); });
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // assembly: L[dest] = a*A + (e+mu)*E on the lower-triangular union pattern
@@ -55,10 +160,6 @@ void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t s
     k_assemble<T><<<blocks, 256, 0, st>>>(S.nasm, S.asm_dest, S.asm_a, S.asm_e, L, a, emu);
     if (launches) *launches += 1;
 }
-
-// ------------------------------------------------------------------------------------------
-// device bodies shared by the per-level (top) kernels and the subtree (bottom) kernels
-// ------------------------------------------------------------------------------------------
 
 // extend-add: supernode J gathers the update matrices of its children through the relative index maps.
 // Deterministic: parent column pc is owned by column class (pc % gy == by); children in fixed order.
@@ -106,195 +207,221 @@ __device__ __forceinline__ void warp_ldlt32(T (&a)[NB], int lane, int32_t* errfl
     }
 }
 
-// phase A: factor the diagonal block of front J (all threads call; warp 0 works), optionally store it.
-// Ds: strictly lower = L_d, diagonal = pivots.  Li: strictly lower part of the inverse of the unit factor.
-template <class T>
-__device__ __forceinline__ void front_diag(const DevSymbolic& S, int J, T* L, T* dblk, int32_t* errflag,
-                                           T (*Ds)[NB + 1], T (*Li)[NB + 1], bool store) {
-    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
-    const T* P = L + S.panel_off[J];
-    const int tid = threadIdx.x;
-    if (tid < 32) {
-        const int lane = tid;
-        T a[NB];
-#pragma unroll
-        for (int c = 0; c < NB; ++c) {
-            T v = (lane == c) ? one<T>() : zero<T>();
-            if (lane < s && c < s && c <= lane) v = P[(int64_t)lane + (int64_t)c * f];
-            a[c] = v;
-        }
-        warp_ldlt32<T>(a, lane, errflag);
-#pragma unroll
-        for (int c = 0; c < NB; ++c) Ds[lane][c] = a[c];
-        __syncwarp();
-        // inverse of the unit lower factor: lane c owns column c
-        const int c = lane;
-        for (int i = c + 1; i < NB; ++i) {
-            T v = Ds[i][c];
-            for (int k = c + 1; k < i; ++k) fma_acc(v, Ds[i][k], Li[k][c]);
-            Li[i][c] = sub(zero<T>(), v);
-        }
-        __syncwarp();
-        if (store) {
-            T* Db = dblk + S.dblk_off[J];
-            for (int i = 0; i < NB; ++i) {
-                // element (i, c): strictly lower -> Linv, diagonal -> pivot, upper -> 0
-                T v = zero<T>();
-                if (i > c) v = Li[i][c];
-                else if (i == c) v = Ds[i][i];
-                Db[i + c * 32] = v;
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// phase B: L21 slab = S * Linv^T * D^-1 for rows [row0, row0 + SLAB) of the front (row0 >= s)
-template <class T>
-__device__ __forceinline__ void front_slab(const DevSymbolic& S, int J, int row0, T* L, T (*Ds)[NB + 1],
-                                           T (*Li)[NB + 1], T (*Ss)[NB + 1]) {
-    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
-    T* P = L + S.panel_off[J];
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < SLAB * NB; idx += 256) {
-        const int m = idx % SLAB, c = idx / SLAB;
-        Ss[m][c] = (row0 + m < f && c < s) ? P[(int64_t)(row0 + m) + (int64_t)c * f] : zero<T>();
-    }
-    __syncthreads();
-    // out[m][c] = (S[m][c] + sum_{t<c} S[m][t] * Linv[c][t]) / d_c ; each thread computes 12 outputs
-    T outv[SLAB * NB / 256];
-#pragma unroll
-    for (int q = 0; q < SLAB * NB / 256; ++q) {
-        const int idx = tid + 256 * q;
-        const int m = idx % SLAB, c = idx / SLAB;
-        T v = Ss[m][c];
-        for (int t = 0; t < c; ++t) fma_acc(v, Ss[m][t], Li[c][t]);
-        outv[q] = mul(v, recip(Ds[c][c]));
-    }
-#pragma unroll
-    for (int q = 0; q < SLAB * NB / 256; ++q) {
-        const int idx = tid + 256 * q;
-        const int m = idx % SLAB, c = idx / SLAB;
-        if (row0 + m < f && c < s) P[(int64_t)(row0 + m) + (int64_t)c * f] = outv[q];
-    }
-    __syncthreads();
-}
-
-// Schur tile: U_J[i0:i0+64, j0:j0+64] -= L21 D L21^T  (lower triangle), K = s_J
-template <class T>
-__device__ __forceinline__ void schur_tile(const DevSymbolic& S, int J, int i0, int j0, const T* L, const T* dblk,
-                                           T* U, T (*As)[64], T (*Bs)[64]) {
-    constexpr int KC = 16;
-    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
-    const T* P = L + S.panel_off[J];
-    const T* Dk = dblk + S.dblk_off[J];
-    T* UJ = U + S.upd_off[J];
-    const int tid = threadIdx.x, tr = tid & 15, tc = tid >> 4;
-    T acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = zero<T>();
-    for (int kk = 0; kk < s; kk += KC) {
-        const int m = tid & 63;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int k = (tid >> 6) + 4 * it;
-            const int kg = kk + k;
-            T av = zero<T>(), bv = zero<T>();
-            if (kg < s) {
-                if (i0 + m < u) av = P[(int64_t)(s + i0 + m) + (int64_t)kg * f];
-                if (j0 + m < u) bv = mul(P[(int64_t)(s + j0 + m) + (int64_t)kg * f], Dk[kg * 33]);
-            }
-            As[k][m] = av;
-            Bs[k][m] = bv;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            T av[4], bv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = As[k][tr + 16 * i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tc + 16 * j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) fma_acc(acc[i][j], av[i], bv[j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gi = i0 + tr + 16 * i;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gj = j0 + tc + 16 * j;
-            if (gi < u && gj < u && gi >= gj) {
-                T* t = UJ + ((int64_t)gi + (int64_t)gj * u);
-                *t = sub(*t, acc[i][j]);
-            }
-        }
-    }
-}
-
-// ---- top-level factorization kernels ----
+// ------------------------------------------------------------------------------------------
+// factorization kernels
+// ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(256) k_extend_add(DevSymbolic S, const int32_t* __restrict__ parents, T* L, T* U) {
     ea_body<T>(S, parents[blockIdx.x], blockIdx.y, gridDim.y, L, U);
 }
 
+// LDL^T of the s x s diagonal block of supernode J (right-looking over 32-column blocks, in place in the
+// panel) and the explicit inverse of its unit-lower factor.  One CTA per supernode; every 32x32x32 block
+// product is done by one warp on the tensor cores.
 template <class T>
-__global__ void __launch_bounds__(256) k_front(DevSymbolic S, const int2* __restrict__ items, T* L, T* dblk,
-                                               int32_t* errflag) {
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    T* smp = reinterpret_cast<T*>(dre_smem_raw);
-    T (*Ds)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Ss)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);
-    const int2 item = items[blockIdx.x];
-    const int J = item.x, slab = item.y;
-    front_diag<T>(S, J, L, dblk, errflag, Ds, Li, slab == 0);
-    const int s = sn_s(S, J), u = sn_u(S, J);
-    if (slab * SLAB < u) front_slab<T>(S, J, s + slab * SLAB, L, Ds, Li, Ss);
-}
+__global__ void __launch_bounds__(256) k_diag(DevSymbolic S, const int32_t* __restrict__ sns, T* L, T* Linv, T* dvec,
+                                              int32_t* errflag) {
+    __shared__ T Ds[NB][NB + 1];   // current diagonal block: strictly lower = L_bb, diagonal = pivots
+    __shared__ T Li[NB][NB + 1];   // inverse of the unit-lower L_bb (ones on, zeros above the diagonal)
+    const int J = sns[blockIdx.x];
+    const int s = sn_s(S, J), f = s + sn_u(S, J);
+    T* P = L + S.panel_off[J];
+    T* LI = Linv + S.linv_off[J];
+    T* dv = dvec + S.sn_first[J];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbk = (s + NB - 1) / NB;
+    Blk32<T> blk;
 
-template <class T>
-__global__ void __launch_bounds__(256) k_schur(DevSymbolic S, const int4* __restrict__ items, const T* __restrict__ L,
-                                               const T* __restrict__ dblk, T* U) {
-    __shared__ T As[16][64];
-    __shared__ T Bs[16][64];
-    const int4 item = items[blockIdx.x];
-    schur_tile<T>(S, item.x, item.y * 64, item.z * 64, L, dblk, U, As, Bs);
-}
-
-// ---- bottom subtrees: one CTA factors a whole subtree (zero U, extend-add, panel, Schur per front) ----
-template <class T>
-__global__ void __launch_bounds__(256) k_factor_subtree(DevSymbolic S, T* L, T* dblk, T* U, int32_t* errflag) {
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    T* smp = reinterpret_cast<T*>(dre_smem_raw);
-    T (*Ds)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Li)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += NB * (NB + 1);
-    T (*Ss)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(smp);           smp += SLAB * (NB + 1);
-    T (*As)[64] = reinterpret_cast<T (*)[64]>(smp);                   smp += 16 * 64;
-    T (*Bs)[64] = reinterpret_cast<T (*)[64]>(smp);
-    const int t = blockIdx.x;
-    const int tid = threadIdx.x;
-    for (int p = S.st_ptr[t]; p < S.st_ptr[t + 1]; ++p) {
-        const int J = S.st_sn[p];
-        const int s = sn_s(S, J), u = sn_u(S, J);
-        T* UJ = U + S.upd_off[J];
-        for (int64_t idx = tid; idx < (int64_t)u * u; idx += 256) UJ[idx] = zero<T>();
+    for (int b = 0; b < nbk; ++b) {
+        const int jb = b * NB, nb = min(NB, s - jb);
+        if (warp == 0) {
+            T a[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                T v = (lane == c) ? one<T>() : zero<T>();
+                if (lane < nb && c < nb && c <= lane) v = P[(int64_t)(jb + lane) + (int64_t)(jb + c) * f];
+                a[c] = v;
+            }
+            warp_ldlt32<T>(a, lane, errflag);
+#pragma unroll
+            for (int c = 0; c < NB; ++c) Ds[lane][c] = a[c];
+            __syncwarp();
+            // inverse of the unit-lower factor: lane j owns column j, x_i = delta_ij - sum_{k<i} L[i][k] x_k
+            T x[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                T v0 = zero<T>(), v1 = zero<T>();
+#pragma unroll
+                for (int k = 0; k + 1 < i; k += 2) {
+                    fma_acc(v0, Ds[i][k], x[k]);
+                    fma_acc(v1, Ds[i][k + 1], x[k + 1]);
+                }
+                if (i & 1) fma_acc(v0, Ds[i][i - 1], x[i - 1]);
+                x[i] = sub((i == lane) ? one<T>() : zero<T>(), add(v0, v1));
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) Li[i][lane] = x[i];
+            __syncwarp();
+            if (lane < nb) dv[jb + lane] = Ds[lane][lane];
+            // block (b, b) of the inverse, coalesced along rows
+            for (int c = 0; c < nb; ++c)
+                if (lane < nb) {
+                    LI[(int64_t)(jb + lane) + (int64_t)(jb + c) * s] = Li[lane][c];
+                    if (c <= lane) P[(int64_t)(jb + lane) + (int64_t)(jb + c) * f] = Ds[lane][c];  // L_bb and pivots
+                }
+        }
         __syncthreads();
-        ea_body<T>(S, J, 0, 1, L, U);
+        // block rows below (inside the diagonal block): L_Ib = A_Ib Linv_bb' D_b^-1
+        for (int I = b + 1 + warp; I < nbk; I += 8) {
+            blk.clear();
+            blk.gemm(NB, lane,
+                     [&](int i, int k) {
+                         const int row = I * NB + i;
+                         return (row < s && k < nb) ? P[(int64_t)row + (int64_t)(jb + k) * f] : zero<T>();
+                     },
+                     [&](int k, int j) { return Li[j][k]; });
+            blk.each(lane, [&](int i, int j, T v) {
+                const int row = I * NB + i;
+                if (row < s && j < nb) P[(int64_t)row + (int64_t)(jb + j) * f] = mul(v, recip(Ds[j][j]));
+            });
+        }
         __syncthreads();
-        front_diag<T>(S, J, L, dblk, errflag, Ds, Li, true);
-        for (int r0 = 0; r0 < u; r0 += SLAB) front_slab<T>(S, J, s + r0, L, Ds, Li, Ss);
-        const int nt = (u + 63) / 64;
-        for (int ti = 0; ti < nt; ++ti)
-            for (int tj = 0; tj <= ti; ++tj) schur_tile<T>(S, J, ti * 64, tj * 64, L, dblk, U, As, Bs);
+        // trailing update of the diagonal block: C_IK -= L_Ib D_b L_Kb'   for b < K <= I
+        const int m = nbk - b - 1;
+        for (int p = warp; p < m * (m + 1) / 2; p += 8) {
+            int Ii = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
+            while ((Ii + 1) * (Ii + 2) / 2 <= p) ++Ii;
+            while (Ii * (Ii + 1) / 2 > p) --Ii;
+            const int Ki = p - Ii * (Ii + 1) / 2;
+            const int I = b + 1 + Ii, K = b + 1 + Ki;
+            blk.clear();
+            blk.gemm(NB, lane,
+                     [&](int i, int k) {
+                         const int row = I * NB + i;
+                         return (row < s && k < nb) ? P[(int64_t)row + (int64_t)(jb + k) * f] : zero<T>();
+                     },
+                     [&](int k, int j) {
+                         const int col = K * NB + j;
+                         return (col < s && k < nb) ? mul(P[(int64_t)col + (int64_t)(jb + k) * f], Ds[k][k]) : zero<T>();
+                     });
+            blk.each(lane, [&](int i, int j, T v) {
+                const int row = I * NB + i, col = K * NB + j;
+                if (row < s && col < s) {
+                    T* t = P + ((int64_t)row + (int64_t)col * f);
+                    *t = sub(*t, v);
+                }
+            });
+        }
         __syncthreads();
     }
+    // off-diagonal blocks of the inverse, one block column per warp:
+    //   Linv[I][Jc] = -Linv[I][I] * sum_{K=Jc}^{I-1} L[I][K] Linv[K][Jc]
+    for (int Jc = warp; Jc < nbk; Jc += 8) {
+        for (int I = Jc + 1; I < nbk; ++I) {
+            blk.clear();
+            for (int K = Jc; K < I; ++K)
+                blk.gemm(NB, lane,
+                         [&](int i, int k) {
+                             const int row = I * NB + i, col = K * NB + k;
+                             return (row < s && col < s) ? P[(int64_t)row + (int64_t)col * f] : zero<T>();
+                         },
+                         [&](int k, int j) {
+                             const int row = K * NB + k, col = Jc * NB + j;
+                             return (row < s && col < s) ? LI[(int64_t)row + (int64_t)col * s] : zero<T>();
+                         });
+            blk.each(lane, [&](int i, int j, T v) {
+                const int row = I * NB + i, col = Jc * NB + j;
+                if (row < s && col < s) LI[(int64_t)row + (int64_t)col * s] = v;
+            });
+            __syncwarp();
+            blk.clear();
+            blk.gemm(NB, lane,
+                     [&](int i, int k) {
+                         const int row = I * NB + i, col = I * NB + k;
+                         return (row < s && col < s) ? LI[(int64_t)row + (int64_t)col * s] : zero<T>();
+                     },
+                     [&](int k, int j) {
+                         const int row = I * NB + k, col = Jc * NB + j;
+                         return (row < s && col < s) ? LI[(int64_t)row + (int64_t)col * s] : zero<T>();
+                     });
+            __syncwarp();
+            blk.each(lane, [&](int i, int j, T v) {
+                const int row = I * NB + i, col = Jc * NB + j;
+                if (row < s && col < s) LI[(int64_t)row + (int64_t)col * s] = sub(zero<T>(), v);
+            });
+            __syncwarp();
+        }
+    }
+}
+
+// L21 = A21 Linv' D^-1.  CTA = (supernode, 64-row slab of L21), warp = 8 rows x all s columns, computed in
+// place from the last column block to the first (block c only reads columns <= c of the warp's own rows).
+template <class T>
+__global__ void __launch_bounds__(256) k_l21(DevSymbolic S, const int2* __restrict__ items, T* L, const T* Linv,
+                                             const T* dvec) {
+    constexpr int NT = 4, CPN = MM<T>::CPN, PW = NT * CPN;
+    const int2 item = items[blockIdx.x];
+    const int J = item.x;
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    T* P = L + S.panel_off[J];
+    const T* LI = Linv + S.linv_off[J];
+    const T* dv = dvec + S.sn_first[J];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = item.y * 64 + warp * 8;
+    if (r0 >= u) return;
+    const int row = r0 + (lane >> 2), bc = MM<T>::bcol(lane);
+    const T* Prow = P + (s + row);
+    for (int cb = (s + PW - 1) / PW - 1; cb >= 0; --cb) {
+        const int c0 = cb * PW;
+        double acc[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        strip_mma<T, NT>(acc, 0, min(s, c0 + PW), lane,
+                         [&](int k) { return (row < u && k < s) ? Prow[(int64_t)k * f] : zero<T>(); },
+                         [&](int k, int nt) {
+                             const int col = c0 + nt * CPN + bc;
+                             return (col < s && k < s) ? LI[(int64_t)col + (int64_t)k * s] : zero<T>();
+                         });
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+            MM<T>::each(acc[nt], lane, [&](int c, T v) {
+                const int col = c0 + nt * CPN + c;
+                if (row < u && col < s) P[(int64_t)(s + row) + (int64_t)col * f] = mul(v, recip(dv[col]));
+            });
+    }
+}
+
+// Schur complement U_J -= L21 D L21' (lower triangle).  CTA = 64x64 tile, 4 warps of 32x32.
+template <class T>
+__global__ void __launch_bounds__(128) k_schur(DevSymbolic S, const int4* __restrict__ items, const T* __restrict__ L,
+                                               const T* __restrict__ dvec, T* U) {
+    const int4 item = items[blockIdx.x];
+    const int J = item.x;
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    const T* P = L + S.panel_off[J] + s;   // L21, ld f
+    const T* dv = dvec + S.sn_first[J];
+    T* UJ = U + S.upd_off[J];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = item.y * 64 + (warp >> 1) * 32, j0 = item.z * 64 + (warp & 1) * 32;
+    if (i0 >= u || j0 >= u || j0 > i0 + 31) return;
+    Blk32<T> blk;
+    blk.clear();
+    blk.gemm(s, lane,
+             [&](int i, int k) {
+                 const int r = i0 + i;
+                 return (r < u && k < s) ? mul(P[(int64_t)r + (int64_t)k * f], dv[k]) : zero<T>();
+             },
+             [&](int k, int j) {
+                 const int c = j0 + j;
+                 return (c < u && k < s) ? P[(int64_t)c + (int64_t)k * f] : zero<T>();
+             });
+    blk.each(lane, [&](int i, int j, T v) {
+        const int r = i0 + i, c = j0 + j;
+        if (r < u && c < u && r >= c) {
+            T* t = UJ + ((int64_t)r + (int64_t)c * u);
+            *t = sub(*t, v);
+        }
+    });
 }
 
 template <class T>
@@ -307,77 +434,63 @@ void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparent
 }
 
 template <class T>
-void launch_front(const DevSymbolic& S, const int2* items, int nitems, T* L, T* dblk, int32_t* errflag,
-                  cudaStream_t st, int64_t* launches) {
-    if (nitems <= 0) return;
-    const int smem = (int)sizeof(T) * (2 * NB * (NB + 1) + SLAB * (NB + 1));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_front<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
-    k_front<T><<<nitems, 256, smem, st>>>(S, items, L, dblk, errflag);
+void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, T* L, T* Linv, T* dvec, int32_t* errflag,
+                 cudaStream_t st, int64_t* launches) {
+    if (nsns <= 0) return;
+    k_diag<T><<<nsns, 256, 0, st>>>(S, sns, L, Linv, dvec, errflag);
     if (launches) *launches += 1;
 }
 
 template <class T>
-void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dblk, T* U,
-                  cudaStream_t st, int64_t* launches) {
+void launch_l21(const DevSymbolic& S, const int2* items, int nitems, T* L, const T* Linv, const T* dvec,
+                cudaStream_t st, int64_t* launches) {
     if (nitems <= 0) return;
-    k_schur<T><<<nitems, 256, 0, st>>>(S, items, L, dblk, U);
+    k_l21<T><<<nitems, 256, 0, st>>>(S, items, L, Linv, dvec);
     if (launches) *launches += 1;
 }
 
 template <class T>
-void launch_factor_subtrees(const DevSymbolic& S, T* L, T* dblk, T* U, int32_t* errflag, cudaStream_t st,
-                            int64_t* launches) {
-    if (S.nsubtrees <= 0) return;
-    const int smem = (int)sizeof(T) * (2 * NB * (NB + 1) + SLAB * (NB + 1) + 2 * 16 * 64);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_factor_subtree<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
-    k_factor_subtree<T><<<S.nsubtrees, 256, smem, st>>>(S, L, dblk, U, errflag);
+void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dvec, T* U,
+                  cudaStream_t st, int64_t* launches) {
+    if (nitems <= 0) return;
+    k_schur<T><<<nitems, 128, 0, st>>>(S, items, L, dvec, U);
     if (launches) *launches += 1;
 }
 
 // ------------------------------------------------------------------------------------------
 // solves.  W is row-major (n x ldw); the update vector of supernode J is column-major
 // (u_J contiguous per RHS column) at  t + rhs_off[J]*ldw.
-// forward:  y_J = L11^-1 (b_J + children),  t_J = children - L21 y_J
-// backward: x_J = L11^-T (D^-1 y_J - L21^T x_struct)
+// forward:  y_J = Linv (b_J + children),  t_J = children - L21 y_J
+// backward: x_J = Linv' (D^-1 y_J - L21' x_struct)
+// CTA = (supernode, chunk of CW = NT * CPN right-hand sides); 8 warps; warp w owns the 8-row strips
+// w, w+8, w+16, w+24 of the supernode (s <= SN_MAX = 256) and keeps their results in registers, so the
+// right-hand-side tile in shared memory is updated in place after one barrier.
 // ------------------------------------------------------------------------------------------
-template <class T, int CW>
-struct SweepSmem {
-    T (*xb)[CW + 1];   // [32][CW+1]
-    T (*Li)[NB + 1];   // [32][33]
-    T (*Ls)[64 + 1];   // [32][65]  (forward: L21 tile; backward uses it as [32][33])
-    T (*Xs)[CW + 1];   // [32][CW+1]
-    __device__ SweepSmem(unsigned char* raw) {
-        T* smp = reinterpret_cast<T*>(raw);
-        xb = reinterpret_cast<T (*)[CW + 1]>(smp);  smp += NB * (CW + 1);
-        Li = reinterpret_cast<T (*)[NB + 1]>(smp);  smp += NB * (NB + 1);
-        Ls = reinterpret_cast<T (*)[64 + 1]>(smp);  smp += NB * 65;
-        Xs = reinterpret_cast<T (*)[CW + 1]>(smp);
-    }
-    static constexpr int bytes() { return (int)sizeof(T) * (2 * NB * (CW + 1) + NB * (NB + 1) + NB * 65); }
-};
+constexpr int SWEEP_Q = SN_MAX / 64;  // strips per warp
 
-template <class T, int CW>
-__device__ __forceinline__ void fwd_body(const DevSymbolic& S, int J, int c0, int ncw, const T* __restrict__ L,
-                                         const T* __restrict__ dblk, T* W, int64_t ldw, T* tbuf,
-                                         SweepSmem<T, CW>& sm) {
+template <class T, int NT>
+__global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
+                                             const T* __restrict__ Linv, T* W, int64_t ldw, int nrhs, T* tbuf) {
+    constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value;
+    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    T* xs = reinterpret_cast<T*>(dre_smem_raw);   // [s8][LDB]
+    const int J = sns[blockIdx.x];
+    const int c0 = blockIdx.y * CW, ncw = min(CW, nrhs - c0);
     const int first = S.sn_first[J];
-    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u, s8 = (s + 7) & ~7;
     const T* P = L + S.panel_off[J];
-    const T* Dk = dblk + S.dblk_off[J];
+    const T* LI = Linv + S.linv_off[J];
     T* tJ = tbuf + S.rhs_off[J] * ldw;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, bc = MM<T>::bcol(lane);
 
+    for (int idx = tid; idx < s8 * CW; idx += 256) {
+        const int i = idx / CW, cc = idx - i * CW;
+        xs[i * LDB + cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
+    }
     for (int idx = tid; idx < u * ncw; idx += 256) {
-        const int cc = idx / u, r = idx - cc * u;
-        tJ[(int64_t)(c0 + cc) * u + r] = zero<T>();
+        const int cc = idx / u, i = idx - cc * u;
+        tJ[(int64_t)(c0 + cc) * u + i] = zero<T>();
     }
     __syncthreads();
     for (int ci = S.child_ptr[J]; ci < S.child_ptr[J + 1]; ++ci) {
@@ -389,265 +502,208 @@ __device__ __forceinline__ void fwd_body(const DevSymbolic& S, int J, int c0, in
             const int cc = idx / uc, i = idx - cc * uc;
             const int pr = rel[i];
             const T val = tch[(int64_t)(c0 + cc) * uc + i];
-            T* t = (pr < s) ? (W + (int64_t)(first + pr) * ldw + c0 + cc) : (tJ + (int64_t)(c0 + cc) * u + (pr - s));
+            T* t = (pr < s) ? (xs + pr * LDB + cc) : (tJ + (int64_t)(c0 + cc) * u + (pr - s));
             *t = add(*t, val);
         }
         __syncthreads();
     }
-    for (int idx = tid; idx < NB * CW; idx += 256) {
-        const int i = idx / CW, cc = idx - i * CW;
-        sm.xb[i][cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
-    }
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx & 31, k = idx >> 5;
-        sm.Li[i][k] = (k < i) ? Dk[i + k * 32] : zero<T>();
-    }
-    __syncthreads();
-    {   // y = Linv x  (unit lower): thread (row i, column group)
-        constexpr int CPT = CW / 8;
-        const int i = tid & 31, cg = tid >> 5;
-        T acc[CPT];
+    // y = Linv x (lower triangular): results stay in registers until every warp has read x
+    double acc[SWEEP_Q][NT][2];
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[c] = sm.xb[i][cg * CPT + c];
-        for (int k = 0; k < i; ++k) {
-            const T l = sm.Li[i][k];
+    for (int q = 0; q < SWEEP_Q; ++q) {
+        const int i0 = (warp + 8 * q) * 8;
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, sm.xb[k][cg * CPT + c]);
+        for (int nt = 0; nt < NT; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
+        if (i0 < s) {
+            const int row = i0 + r;
+            const T* Lrow = LI + row;
+            strip_mma<T, NT>(acc[q], 0, min(i0 + 8, s), lane,
+                             [&](int k) { return (row < s && k < s) ? Lrow[(int64_t)k * s] : zero<T>(); },
+                             [&](int k, int nt) { return xs[k * LDB + nt * CPN + bc]; });
         }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) sm.xb[i][cg * CPT + c] = acc[c];
     }
     __syncthreads();
-    for (int idx = tid; idx < NB * CW; idx += 256) {
-        const int i = idx / CW, cc = idx - i * CW;
-        if (i < s && cc < ncw) W[(int64_t)(first + i) * ldw + c0 + cc] = sm.xb[i][cc];
+#pragma unroll
+    for (int q = 0; q < SWEEP_Q; ++q) {
+        const int row = (warp + 8 * q) * 8 + r;
+        if (row < s) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                MM<T>::each(acc[q][nt], lane, [&](int c, T v) { xs[row * LDB + nt * CPN + c] = v; });
+        }
     }
-    {   // t_J -= L21 y, 64-row tiles of L21 staged in shared memory
-        constexpr int CPT = CW / 4;
-        const int rl = tid & 63, cg = tid >> 6;
-        for (int r0 = 0; r0 < u; r0 += 64) {
-            __syncthreads();
-            for (int idx = tid; idx < NB * 64; idx += 256) {
-                const int rr = idx & 63, k = idx >> 6;
-                sm.Ls[k][rr] = (r0 + rr < u && k < s) ? P[(int64_t)(s + r0 + rr) + (int64_t)k * f] : zero<T>();
-            }
-            __syncthreads();
-            T acc[CPT];
+    __syncthreads();
+    for (int idx = tid; idx < s * CW; idx += 256) {
+        const int i = idx / CW, cc = idx - i * CW;
+        if (cc < ncw) W[(int64_t)(first + i) * ldw + c0 + cc] = xs[i * LDB + cc];
+    }
+    // t_J -= L21 y
+    for (int i0 = warp * 8; i0 < u; i0 += 64) {
+        const int row = i0 + r;
+        const T* Lrow = P + (s + row);
+        double a1[NT][2];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) acc[c] = zero<T>();
-            for (int k = 0; k < s; ++k) {
-                const T l = sm.Ls[k][rl];
+        for (int nt = 0; nt < NT; ++nt) a1[nt][0] = a1[nt][1] = 0.0;
+        strip_mma<T, NT>(a1, 0, s, lane,
+                         [&](int k) { return (row < u && k < s) ? Lrow[(int64_t)k * f] : zero<T>(); },
+                         [&](int k, int nt) { return xs[k * LDB + nt * CPN + bc]; });
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, sm.xb[k][cg * CPT + c]);
-            }
-            if (r0 + rl < u) {
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int cc = cg * CPT + c;
-                    if (cc < ncw) {
-                        T* t = tJ + (int64_t)(c0 + cc) * u + r0 + rl;
-                        *t = sub(*t, acc[c]);
-                    }
+        for (int nt = 0; nt < NT; ++nt)
+            MM<T>::each(a1[nt], lane, [&](int c, T v) {
+                const int col = nt * CPN + c;
+                if (row < u && col < ncw) {
+                    T* t = tJ + (int64_t)(c0 + col) * u + row;
+                    *t = sub(*t, v);
                 }
-            }
-        }
+            });
     }
-    __syncthreads();
 }
 
-template <class T, int CW>
-__device__ __forceinline__ void bwd_body(const DevSymbolic& S, int J, int c0, int ncw, const T* __restrict__ L,
-                                         const T* __restrict__ dblk, T* W, int64_t ldw, SweepSmem<T, CW>& sm) {
-    constexpr int CPT = CW / 8;
-    T (*Lt)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(sm.Ls);  // [32 rows][33] tile of L21
-    const int first = S.sn_first[J];
-    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
-    const T* P = L + S.panel_off[J];
-    const T* Dk = dblk + S.dblk_off[J];
-    const int32_t* rows = S.sn_rows + S.sn_rowptr[J];
-    const int tid = threadIdx.x;
-    const int kq = tid & 31, cg = tid >> 5;
-
-    T acc[CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[c] = zero<T>();
-    for (int r0 = 0; r0 < u; r0 += NB) {
-        for (int idx = tid; idx < NB * NB; idx += 256) {
-            const int r = idx & 31, k = idx >> 5;
-            Lt[r][k] = (r0 + r < u && k < s) ? P[(int64_t)(s + r0 + r) + (int64_t)k * f] : zero<T>();
-        }
-        for (int idx = tid; idx < NB * CW; idx += 256) {
-            const int r = idx / CW, cc = idx - r * CW;
-            T v = zero<T>();
-            if (r0 + r < u && cc < ncw) v = W[(int64_t)rows[r0 + r] * ldw + c0 + cc];
-            sm.Xs[r][cc] = v;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int r = 0; r < NB; ++r) {
-            const T l = Lt[r][kq];
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) fma_acc(acc[c], l, sm.Xs[r][cg * CPT + c]);
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < NB * CW; idx += 256) {
-        const int i = idx / CW, cc = idx - i * CW;
-        sm.xb[i][cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
-    }
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx & 31, k = idx >> 5;
-        sm.Li[i][k] = Dk[i + k * 32];  // strictly lower: Linv, diagonal: pivots
-    }
-    __syncthreads();
-    {
-        const T rd = (kq < s) ? recip(sm.Li[kq][kq]) : zero<T>();
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const int cc = cg * CPT + c;
-            sm.xb[kq][cc] = sub(mul(sm.xb[kq][cc], rd), acc[c]);
-        }
-    }
-    __syncthreads();
-    {   // x = Linv^T z : x_i = z_i + sum_{k>i} Linv[k][i] z_k
-        T xv[CPT];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) xv[c] = sm.xb[kq][cg * CPT + c];
-        for (int k = kq + 1; k < s; ++k) {
-            const T l = sm.Li[k][kq];
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) fma_acc(xv[c], l, sm.xb[k][cg * CPT + c]);
-        }
-        if (kq < s) {
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int cc = cg * CPT + c;
-                if (cc < ncw) W[(int64_t)(first + kq) * ldw + c0 + cc] = xv[c];
-            }
-        }
-    }
-    __syncthreads();
-}
-
-template <class T, int CW>
-__global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
-                                             const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs, T* tbuf) {
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    SweepSmem<T, CW> sm(dre_smem_raw);
-    const int c0 = blockIdx.y * CW;
-    fwd_body<T, CW>(S, sns[blockIdx.x], c0, min(CW, nrhs - c0), L, dblk, W, ldw, tbuf, sm);
-}
-
-template <class T, int CW>
+template <class T, int NT>
 __global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
-                                             const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs) {
+                                             const T* __restrict__ Linv, const T* __restrict__ dvec, T* W, int64_t ldw,
+                                             int nrhs, int srows) {
+    constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value;
     extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    SweepSmem<T, CW> sm(dre_smem_raw);
-    const int c0 = blockIdx.y * CW;
-    bwd_body<T, CW>(S, sns[blockIdx.x], c0, min(CW, nrhs - c0), L, dblk, W, ldw, sm);
+    T* xs = reinterpret_cast<T*>(dre_smem_raw);   // [srows][LDB]: z
+    T* xt = xs + (size_t)srows * LDB;             // [64][LDB]: tile of x at the structure rows
+    const int J = sns[blockIdx.x];
+    const int c0 = blockIdx.y * CW, ncw = min(CW, nrhs - c0);
+    const int first = S.sn_first[J];
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u, s8 = (s + 7) & ~7;
+    const T* P = L + S.panel_off[J];
+    const T* LI = Linv + S.linv_off[J];
+    const T* dv = dvec + first;
+    const int32_t* rows = S.sn_rows + S.sn_rowptr[J];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, bc = MM<T>::bcol(lane);
+
+    double acc[SWEEP_Q][NT][2];
+#pragma unroll
+    for (int q = 0; q < SWEEP_Q; ++q)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
+    // acc = L21' x_struct, 64 structure rows at a time
+    for (int r0 = 0; r0 < u; r0 += 64) {
+        for (int idx = tid; idx < 64 * CW; idx += 256) {
+            const int i = idx / CW, cc = idx - i * CW;
+            xt[i * LDB + cc] = (r0 + i < u && cc < ncw) ? W[(int64_t)rows[r0 + i] * ldw + c0 + cc] : zero<T>();
+        }
+        __syncthreads();
+        const int kt = min(64, u - r0);
+#pragma unroll
+        for (int q = 0; q < SWEEP_Q; ++q) {
+            const int i0 = (warp + 8 * q) * 8;
+            if (i0 < s) {
+                const int col = i0 + r;   // output row = column of L21
+                const T* Lcol = P + (s + r0) + (int64_t)col * f;
+                strip_mma<T, NT>(acc[q], 0, kt, lane,
+                                 [&](int k) { return (col < s && k < kt) ? Lcol[k] : zero<T>(); },
+                                 [&](int k, int nt) { return xt[k * LDB + nt * CPN + bc]; });
+            }
+        }
+        __syncthreads();
+    }
+    // z = D^-1 y - acc
+    for (int idx = tid; idx < (s8 - s) * CW; idx += 256) {
+        const int i = s + idx / CW, cc = idx % CW;
+        xs[i * LDB + cc] = zero<T>();
+    }
+#pragma unroll
+    for (int q = 0; q < SWEEP_Q; ++q) {
+        const int row = (warp + 8 * q) * 8 + r;
+        if (row < s) {
+            const T rd = recip(dv[row]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                MM<T>::each(acc[q][nt], lane, [&](int c, T v) {
+                    const int col = nt * CPN + c;
+                    const T y = (col < ncw) ? W[(int64_t)(first + row) * ldw + c0 + col] : zero<T>();
+                    xs[row * LDB + col] = sub(mul(y, rd), v);
+                });
+        }
+    }
+    __syncthreads();
+    // x = Linv' z (upper triangular)
+#pragma unroll
+    for (int q = 0; q < SWEEP_Q; ++q) {
+        const int i0 = (warp + 8 * q) * 8;
+        if (i0 < s) {
+            const int row = i0 + r;
+            const T* Lcol = LI + (int64_t)row * s;
+            double a1[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) a1[nt][0] = a1[nt][1] = 0.0;
+            strip_mma<T, NT>(a1, i0, s, lane,
+                             [&](int k) { return (row < s && k < s) ? Lcol[k] : zero<T>(); },
+                             [&](int k, int nt) { return xs[k * LDB + nt * CPN + bc]; });
+            if (row < s) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    MM<T>::each(a1[nt], lane, [&](int c, T v) {
+                        const int col = nt * CPN + c;
+                        if (col < ncw) W[(int64_t)(first + row) * ldw + c0 + col] = v;
+                    });
+            }
+        }
+    }
 }
 
-// bottom subtrees: CTA (subtree, column chunk) walks the subtree (ascending for forward, descending for
-// backward); right-hand-side columns are independent, so no inter-CTA synchronisation is needed.
-template <class T, int CW>
-__global__ void __launch_bounds__(256) k_fwd_subtree(DevSymbolic S, const T* __restrict__ L,
-                                                     const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs,
-                                                     T* tbuf) {
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    SweepSmem<T, CW> sm(dre_smem_raw);
-    const int c0 = blockIdx.y * CW;
-    const int ncw = min(CW, nrhs - c0);
-    const int t = blockIdx.x;
-    for (int p = S.st_ptr[t]; p < S.st_ptr[t + 1]; ++p)
-        fwd_body<T, CW>(S, S.st_sn[p], c0, ncw, L, dblk, W, ldw, tbuf, sm);
+template <class T, int NT>
+static int fwd_smem(int smax) {
+    return (int)sizeof(T) * ((smax + 7) & ~7) * RhsLd<T, NT * MM<T>::CPN>::value;
+}
+template <class T, int NT>
+static int bwd_smem(int smax) {
+    return (int)sizeof(T) * (((smax + 7) & ~7) + 64) * RhsLd<T, NT * MM<T>::CPN>::value;
 }
 
-template <class T, int CW>
-__global__ void __launch_bounds__(256) k_bwd_subtree(DevSymbolic S, const T* __restrict__ L,
-                                                     const T* __restrict__ dblk, T* W, int64_t ldw, int nrhs) {
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
-    SweepSmem<T, CW> sm(dre_smem_raw);
-    const int c0 = blockIdx.y * CW;
-    const int ncw = min(CW, nrhs - c0);
-    const int t = blockIdx.x;
-    for (int p = S.st_ptr[t + 1] - 1; p >= S.st_ptr[t]; --p)
-        bwd_body<T, CW>(S, S.st_sn[p], c0, ncw, L, dblk, W, ldw, sm);
-}
-
-template <class T, int CW>
+template <class T, int NT>
 static void set_sweep_attrs() {
     static bool done = false;
     if (done) return;
-    const int smem = SweepSmem<T, CW>::bytes();
-    cudaFuncSetAttribute(k_fwd<T, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_bwd<T, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_fwd_subtree<T, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_bwd_subtree<T, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_fwd<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<T, NT>(SN_MAX));
+    cudaFuncSetAttribute(k_bwd<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<T, NT>(SN_MAX));
     done = true;
 }
 
+// widest chunk that still gives every SM a CTA; narrow chunks for the few fat supernodes near the root
 template <class T>
-void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
-                      int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches) {
+static int pick_nt(int nsns, int nrhs) {
+    const int cpn = MM<T>::CPN;
+    if ((int64_t)nsns * ((nrhs + 4 * cpn - 1) / (4 * cpn)) >= 148) return 4;
+    if ((int64_t)nsns * ((nrhs + 2 * cpn - 1) / (2 * cpn)) >= 148) return 2;
+    return 1;
+}
+
+template <class T>
+void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
+                      T* W, int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    set_sweep_attrs<T, 32>();
-    set_sweep_attrs<T, 8>();
-    if ((int64_t)nsns * ((nrhs + 31) / 32) >= 2 * 148) {
-        dim3 grid(nsns, (nrhs + 31) / 32);
-        k_fwd<T, 32><<<grid, 256, SweepSmem<T, 32>::bytes(), st>>>(S, sns, L, dblk, W, ldw, nrhs, tbuf);
-    } else {
-        dim3 grid(nsns, (nrhs + 7) / 8);
-        k_fwd<T, 8><<<grid, 256, SweepSmem<T, 8>::bytes(), st>>>(S, sns, L, dblk, W, ldw, nrhs, tbuf);
-    }
+    set_sweep_attrs<T, 4>();
+    set_sweep_attrs<T, 2>();
+    set_sweep_attrs<T, 1>();
+    const int nt = pick_nt<T>(nsns, nrhs), cw = nt * MM<T>::CPN;
+    dim3 grid(nsns, (nrhs + cw - 1) / cw);
+    if (nt == 4) k_fwd<T, 4><<<grid, 256, fwd_smem<T, 4>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
+    else if (nt == 2) k_fwd<T, 2><<<grid, 256, fwd_smem<T, 2>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
+    else k_fwd<T, 1><<<grid, 256, fwd_smem<T, 1>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
     if (launches) *launches += 1;
 }
 
 template <class T>
-void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, const T* L, const T* dblk, T* W,
-                      int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches) {
+void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
+                      const T* dvec, T* W, int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    set_sweep_attrs<T, 32>();
-    set_sweep_attrs<T, 8>();
-    if ((int64_t)nsns * ((nrhs + 31) / 32) >= 2 * 148) {
-        dim3 grid(nsns, (nrhs + 31) / 32);
-        k_bwd<T, 32><<<grid, 256, SweepSmem<T, 32>::bytes(), st>>>(S, sns, L, dblk, W, ldw, nrhs);
-    } else {
-        dim3 grid(nsns, (nrhs + 7) / 8);
-        k_bwd<T, 8><<<grid, 256, SweepSmem<T, 8>::bytes(), st>>>(S, sns, L, dblk, W, ldw, nrhs);
-    }
-    if (launches) *launches += 1;
-}
-
-template <class T>
-void launch_fwd_subtrees(const DevSymbolic& S, const T* L, const T* dblk, T* W, int64_t ldw, int nrhs, T* tbuf,
-                         cudaStream_t st, int64_t* launches) {
-    if (S.nsubtrees <= 0 || nrhs <= 0) return;
-    set_sweep_attrs<T, 32>();
-    set_sweep_attrs<T, 8>();
-    if ((int64_t)S.nsubtrees * ((nrhs + 31) / 32) >= 2 * 148) {
-        dim3 grid(S.nsubtrees, (nrhs + 31) / 32);
-        k_fwd_subtree<T, 32><<<grid, 256, SweepSmem<T, 32>::bytes(), st>>>(S, L, dblk, W, ldw, nrhs, tbuf);
-    } else {
-        dim3 grid(S.nsubtrees, (nrhs + 7) / 8);
-        k_fwd_subtree<T, 8><<<grid, 256, SweepSmem<T, 8>::bytes(), st>>>(S, L, dblk, W, ldw, nrhs, tbuf);
-    }
-    if (launches) *launches += 1;
-}
-
-template <class T>
-void launch_bwd_subtrees(const DevSymbolic& S, const T* L, const T* dblk, T* W, int64_t ldw, int nrhs,
-                         cudaStream_t st, int64_t* launches) {
-    if (S.nsubtrees <= 0 || nrhs <= 0) return;
-    set_sweep_attrs<T, 32>();
-    set_sweep_attrs<T, 8>();
-    if ((int64_t)S.nsubtrees * ((nrhs + 31) / 32) >= 2 * 148) {
-        dim3 grid(S.nsubtrees, (nrhs + 31) / 32);
-        k_bwd_subtree<T, 32><<<grid, 256, SweepSmem<T, 32>::bytes(), st>>>(S, L, dblk, W, ldw, nrhs);
-    } else {
-        dim3 grid(S.nsubtrees, (nrhs + 7) / 8);
-        k_bwd_subtree<T, 8><<<grid, 256, SweepSmem<T, 8>::bytes(), st>>>(S, L, dblk, W, ldw, nrhs);
-    }
+    set_sweep_attrs<T, 4>();
+    set_sweep_attrs<T, 2>();
+    set_sweep_attrs<T, 1>();
+    const int nt = pick_nt<T>(nsns, nrhs), cw = nt * MM<T>::CPN;
+    const int srows = (smax + 7) & ~7;
+    dim3 grid(nsns, (nrhs + cw - 1) / cw);
+    if (nt == 4) k_bwd<T, 4><<<grid, 256, bwd_smem<T, 4>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs, srows);
+    else if (nt == 2) k_bwd<T, 2><<<grid, 256, bwd_smem<T, 2>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs, srows);
+    else k_bwd<T, 1><<<grid, 256, bwd_smem<T, 1>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs, srows);
     if (launches) *launches += 1;
 }
 
@@ -793,18 +849,16 @@ void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int m
     template void launch_assemble<T>(const DevSymbolic&, T*, double, T, cudaStream_t, int64_t*);                     \
     template void launch_extend_add<T>(const DevSymbolic&, const int32_t*, int, int, T*, T*, cudaStream_t,           \
                                        int64_t*);                                                                    \
-    template void launch_front<T>(const DevSymbolic&, const int2*, int, T*, T*, int32_t*, cudaStream_t, int64_t*);   \
+    template void launch_diag<T>(const DevSymbolic&, const int32_t*, int, T*, T*, T*, int32_t*, cudaStream_t,        \
+                                 int64_t*);                                                                          \
+    template void launch_l21<T>(const DevSymbolic&, const int2*, int, T*, const T*, const T*, cudaStream_t,          \
+                                int64_t*);                                                                           \
     template void launch_schur<T>(const DevSymbolic&, const int4*, int, const T*, const T*, T*, cudaStream_t,        \
                                   int64_t*);                                                                         \
-    template void launch_factor_subtrees<T>(const DevSymbolic&, T*, T*, T*, int32_t*, cudaStream_t, int64_t*);       \
-    template void launch_fwd_level<T>(const DevSymbolic&, const int32_t*, int, const T*, const T*, T*, int64_t, int, \
-                                      T*, cudaStream_t, int64_t*);                                                   \
-    template void launch_bwd_level<T>(const DevSymbolic&, const int32_t*, int, const T*, const T*, T*, int64_t, int, \
-                                      cudaStream_t, int64_t*);                                                       \
-    template void launch_fwd_subtrees<T>(const DevSymbolic&, const T*, const T*, T*, int64_t, int, T*, cudaStream_t, \
-                                         int64_t*);                                                                  \
-    template void launch_bwd_subtrees<T>(const DevSymbolic&, const T*, const T*, T*, int64_t, int, cudaStream_t,     \
-                                         int64_t*);                                                                  \
+    template void launch_fwd_level<T>(const DevSymbolic&, const int32_t*, int, int, const T*, const T*, T*, int64_t, \
+                                      int, T*, cudaStream_t, int64_t*);                                              \
+    template void launch_bwd_level<T>(const DevSymbolic&, const int32_t*, int, int, const T*, const T*, const T*,    \
+                                      T*, int64_t, int, cudaStream_t, int64_t*);                                     \
     template void launch_load_rhs<T>(T*, int64_t, const double*, int64_t, int, const double*, int64_t, int, int64_t, \
                                      cudaStream_t, int64_t*);                                                        \
     template void launch_smw_core<T>(const T*, int64_t, int, int, double, T*, int32_t*, cudaStream_t, int64_t*);     \

@@ -401,112 +401,44 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
     for (int32_t J = 0; J < S.nsn; ++J)
         std::copy(children[J].begin(), children[J].end(), S.child_idx.begin() + S.child_ptr[J]);
 
-    // ---- levels by depth (deepest = level 0) ----
+    // ---- levels by height (leaves = level 0; children precede parents in the numbering) ----
     {
-        std::vector<int32_t> depth(S.nsn, 0);
-        int32_t maxd = 0;
-        for (int32_t J = S.nsn - 1; J >= 0; --J) {
-            depth[J] = S.sn_parent[J] < 0 ? 0 : depth[S.sn_parent[J]] + 1;
-            maxd = std::max(maxd, depth[J]);
-        }
-        S.nlevels = maxd + 1;
-        S.sn_level.resize(S.nsn);
-        S.level_ptr.assign(S.nlevels + 1, 0);
+        S.sn_level.assign(S.nsn, 0);
+        int32_t maxl = 0;
         for (int32_t J = 0; J < S.nsn; ++J) {
-            S.sn_level[J] = maxd - depth[J];
-            S.level_ptr[S.sn_level[J] + 1]++;
+            const int32_t P = S.sn_parent[J];
+            if (P >= 0) S.sn_level[P] = std::max(S.sn_level[P], S.sn_level[J] + 1);
+            maxl = std::max(maxl, S.sn_level[J]);
         }
+        S.nlevels = maxl + 1;
+        S.level_ptr.assign(S.nlevels + 1, 0);
+        for (int32_t J = 0; J < S.nsn; ++J) S.level_ptr[S.sn_level[J] + 1]++;
         for (int32_t l = 0; l < S.nlevels; ++l) S.level_ptr[l + 1] += S.level_ptr[l];
         S.level_sn.resize(S.nsn);
         std::vector<int32_t> pos(S.level_ptr.begin(), S.level_ptr.end() - 1);
         for (int32_t J = 0; J < S.nsn; ++J) S.level_sn[pos[S.sn_level[J]]++] = J;
     }
 
-    // ---- bottom subtrees and top levels ----
-    {
-        int32_t thr = opt.subtree_cols > 0 ? opt.subtree_cols
-                                            : (int32_t)std::min<int64_t>(1024, std::max<int64_t>(64, n / 400));
-        std::vector<int64_t> cols_sub(S.nsn, 0);
-        for (int32_t J = 0; J < S.nsn; ++J) {
-            cols_sub[J] += S.sn_size(J);
-            if (S.sn_parent[J] >= 0) cols_sub[S.sn_parent[J]] += cols_sub[J];
-        }
-        // a supernode is "bottom" iff its whole subtree fits the cap; roots = bottom nodes with a top parent
-        std::vector<int32_t> root_of(S.nsn, -1);
-        S.sn_subtree.assign(S.nsn, -1);
-        S.nsubtrees = 0;
-        std::vector<int32_t> root_id(S.nsn, -1);
-        for (int32_t J = S.nsn - 1; J >= 0; --J) {
-            if (cols_sub[J] > thr) continue;
-            const int32_t P = S.sn_parent[J];
-            root_of[J] = (P >= 0 && root_of[P] >= 0) ? root_of[P] : J;
-        }
-        for (int32_t J = 0; J < S.nsn; ++J)
-            if (root_of[J] == J) root_id[J] = S.nsubtrees++;
-        S.st_ptr.assign(S.nsubtrees + 1, 0);
-        for (int32_t J = 0; J < S.nsn; ++J)
-            if (root_of[J] >= 0) { S.sn_subtree[J] = root_id[root_of[J]]; S.st_ptr[S.sn_subtree[J] + 1]++; }
-        for (int32_t t = 0; t < S.nsubtrees; ++t) S.st_ptr[t + 1] += S.st_ptr[t];
-        S.st_sn.resize(S.st_ptr[S.nsubtrees]);
-        {
-            std::vector<int32_t> pos(S.st_ptr.begin(), S.st_ptr.end() - 1);
-            for (int32_t J = 0; J < S.nsn; ++J)
-                if (S.sn_subtree[J] >= 0) S.st_sn[pos[S.sn_subtree[J]]++] = J;
-        }
-        // top levels = the depth levels restricted to top supernodes (empty levels dropped)
-        S.top_level_ptr.assign(1, 0);
-        for (int32_t l = 0; l < S.nlevels; ++l) {
-            const size_t before = S.top_level_sn.size();
-            for (int32_t p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p)
-                if (S.sn_subtree[S.level_sn[p]] < 0) S.top_level_sn.push_back(S.level_sn[p]);
-            if (S.top_level_sn.size() > before) S.top_level_ptr.push_back((int32_t)S.top_level_sn.size());
-        }
-        S.ntoplevels = (int32_t)S.top_level_ptr.size() - 1;
-    }
-
     // ---- storage offsets, statistics ----
     S.panel_off.assign(S.nsn + 1, 0);
-    S.upd_off.assign(S.nsn, 0);
+    S.linv_off.assign(S.nsn + 1, 0);
+    S.upd_off.assign(S.nsn + 1, 0);
     S.rhs_off.assign(S.nsn, 0);
     {
-        int64_t roff = 0, boff = 0;
+        int64_t roff = 0;
         for (int32_t J = 0; J < S.nsn; ++J) {
             int64_t s = S.sn_size(J), u = S.sn_nrows(J), f = s + u;
             S.panel_off[J + 1] = S.panel_off[J] + f * s;
+            S.linv_off[J + 1] = S.linv_off[J] + s * s;
+            S.upd_off[J + 1] = S.upd_off[J] + u * u;
             S.flops += 2.0 * ((double)s * s * s / 3.0 + (double)u * s * s + (double)u * u * s);
             S.max_front = std::max<int32_t>(S.max_front, (int32_t)f);
             S.max_sn = std::max<int32_t>(S.max_sn, (int32_t)s);
             S.sum_u += u;
             S.rhs_off[J] = roff;
             roff += u;
-            if (S.sn_subtree[J] >= 0) { S.upd_off[J] = boff; boff += u * u; }
         }
         S.nnz_L = S.panel_off[S.nsn];
-        S.upd_bottom_elems = boff;
-        // top part: ping-pong by parity of the DEPTH level (children of a top supernode that are themselves
-        // top supernodes sit exactly one depth level below it)
-        std::vector<int64_t> lvl_elems(S.nlevels, 0);
-        for (int32_t J = 0; J < S.nsn; ++J)
-            if (S.sn_subtree[J] < 0) {
-                const int64_t u = S.sn_nrows(J);
-                lvl_elems[S.sn_level[J]] += u * u;
-            }
-        for (int32_t l = 0; l < S.nlevels; ++l)
-            S.max_upd_level[l & 1] = std::max(S.max_upd_level[l & 1], lvl_elems[l]);
-        std::vector<int64_t> lvl_off(S.nlevels, 0);
-        for (int32_t t = 0; t < S.ntoplevels; ++t) {
-            const int32_t l = S.sn_level[S.top_level_sn[S.top_level_ptr[t]]];
-            const int64_t base = S.upd_bottom_elems + ((l & 1) ? S.max_upd_level[0] : 0);
-            int64_t off = 0;
-            for (int32_t p = S.top_level_ptr[t]; p < S.top_level_ptr[t + 1]; ++p) {
-                const int32_t J = S.top_level_sn[p];
-                const int64_t u = S.sn_nrows(J);
-                S.upd_off[J] = base + off;
-                off += u * u;
-            }
-            S.top_level_upd_begin.push_back(base);
-            S.top_level_upd_elems.push_back(off);
-        }
     }
 
     // ---- relative maps child struct row -> parent front local index ----

@@ -5,7 +5,7 @@
 //   factorize(::LowRankUpdate)  /root/reference/src/LowRankUpdate.jl:88-91
 // pattern(A) u pattern(E) is constant over all shifts and time steps, so
 // this runs ONCE per pencil: nested-dissection ordering, supernode partition (= the dissection
-// blocks), supernodal elimination tree, row structures, level schedule (by depth, deepest first),
+// blocks), supernodal elimination tree, row structures, level schedule (by height, leaves first),
 // extend-add index maps and the scatter map that assembles a*A+(e+mu)*E into the supernodal panels
 // with two scalars per shift.
 #pragma once
@@ -26,31 +26,15 @@ struct Symbolic {
     std::vector<int64_t> sn_rowptr;  // nsn+1: offsets into sn_rows
     std::vector<int32_t> sn_rows;    // below-supernode row structure (sorted, new indices)
     std::vector<int32_t> sn_parent;  // supernodal etree (-1 = root)
-    std::vector<int32_t> sn_level;   // level index, 0 = deepest level (processed first in factor/forward)
+    std::vector<int32_t> sn_level;   // level = height in the tree (leaves 0): level l only depends on levels < l
     int32_t nlevels = 0;
     std::vector<int32_t> level_ptr;  // nlevels+1 offsets into level_sn
     std::vector<int32_t> level_sn;   // supernodes grouped by level
 
-    // bottom subtrees: maximal subtrees with at most `subtree_cols` columns.  One CTA walks a whole
-    // subtree, so the (many, tiny) lower levels of the tree need a single kernel launch; only the "top"
-    // supernodes above the subtree roots are processed level by level.
-    std::vector<int32_t> sn_subtree;   // nsn: subtree id, -1 for top supernodes
-    int32_t nsubtrees = 0;
-    std::vector<int32_t> st_ptr;       // nsubtrees+1 offsets into st_sn
-    std::vector<int32_t> st_sn;        // supernodes of each subtree, ascending (children before parents)
-    int32_t ntoplevels = 0;
-    std::vector<int32_t> top_level_ptr;  // ntoplevels+1 offsets into top_level_sn (deepest top level first)
-    std::vector<int32_t> top_level_sn;
-
     std::vector<int64_t> panel_off;  // nsn+1: offset of the f_J x s_J column-major panel (ld = f_J) in L storage
-    // update matrices (u_J x u_J): absolute offsets into one buffer laid out as
-    //   [ all bottom supernodes | top levels of even parity | top levels of odd parity ]
-    std::vector<int64_t> upd_off;
-    int64_t upd_bottom_elems = 0;
-    int64_t max_upd_level[2] = {0, 0};  // top part, even / odd (top-)levels
-    std::vector<int64_t> top_level_upd_begin, top_level_upd_elems;  // per top level: absolute range to clear
-    // update vectors of the solves: row offset (cumulative over ALL supernodes, no buffer reuse)
-    std::vector<int64_t> rhs_off;
+    std::vector<int64_t> linv_off;   // nsn+1: offset of the s_J x s_J column-major inverse of the unit-lower diagonal block
+    std::vector<int64_t> upd_off;    // nsn+1: offset of the u_J x u_J column-major update matrix (no buffer reuse)
+    std::vector<int64_t> rhs_off;    // nsn: row offset of the u_J-row update vector of the solves (cumulative)
 
     // children lists (CSR by parent) and relative maps child-struct-row -> parent front local index
     std::vector<int32_t> child_ptr, child_idx;
@@ -77,9 +61,8 @@ struct Symbolic {
 };
 
 struct AnalyzeOptions {
-    int32_t leaf_size = 48;       // dissection stops below this many vertices
-    int32_t max_snode = 1 << 30;  // dissection blocks wider than this are split into chains of supernodes
-    int32_t subtree_cols = 0;     // bottom-subtree size cap; 0 = automatic (n/400 clamped to [64, 1024])
+    int32_t leaf_size = 96;       // dissection stops below this many vertices (a leaf is ONE dense supernode)
+    int32_t max_snode = 256;      // dissection blocks wider than this are split into chains of supernodes
 };
 
 // E and A: CSC, index_base 0 or 1, 64-bit indices (Julia SparseMatrixCSC{Float64,Int64} zero-copy).

@@ -141,6 +141,12 @@ DRE_API int32_t dre_ldlt_compress(dre_context* ctx, int32_t nterms, const dre_vi
 DRE_API int32_t dre_rrqr(dre_context* ctx, int32_t nviews, const dre_view* views, double drop_rel, double drop_abs,
                  dre_view Q, double* Rt, int64_t ldr, int32_t* rho);
 
+/* ---- diagnostics (tests) ----
+ * Raw copy of the numeric factorization currently held: what = "L" (supernodal panels), "Linv" (inverse
+ * unit-lower diagonal blocks), "dvec" (pivots), "U" (update matrices); elements are double (real shift) or
+ * interleaved complex (complex shift).  Copies at most cap_bytes and returns the full size in *len_bytes. */
+DRE_API int32_t dre_debug_export(dre_context* ctx, const char* what, void* buf, int64_t cap_bytes, int64_t* len_bytes);
+
 /* ---- timing / counters for bench.py ---- */
 typedef struct {
     int64_t kernel_launches;    /* launches of this library's own kernels since the last reset */

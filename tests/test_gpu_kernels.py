@@ -11,10 +11,13 @@ pytestmark = pytest.mark.gpu
 pencils = dre_b200.pencils
 
 
-@pytest.fixture(scope="module")
+_RAIL = pencils.rail_pencil(1357)[:4]
+
+
+@pytest.fixture()
 def rail():
-    E, A, B, C, _ = pencils.rail_pencil(1357)
-    api.upload_pencil(E, A)
+    E, A, B, C = _RAIL
+    api.upload_pencil(E, A)  # no-op while the same pencil is resident
     return E, A, B, C
 
 
@@ -87,6 +90,58 @@ def test_shift_solve_plain(rail, mu):
         V = out.to_host()
     assert _rel(V, ref) < 1e-10
     assert _rel(M @ V, R) < 1e-11
+
+
+@pytest.mark.parametrize("n,leaf,cap", [(1357, 96, 256), (5177, 96, 256), (5177, 24, 40), (20209, 128, 256)])
+def test_factor_arrays_and_wide_solves(n, leaf, cap, monkeypatch):
+    """The numeric factorization on the device (panels L, explicit inverse diagonal blocks, pivots) against
+    the NumPy emulation of the same algorithm on the same symbolic structure (tests/hostcheck.py), entry by
+    entry, and the block solve with 250 / 37 / 3 right-hand sides against SuperLU; real and complex shifts.
+    (leaf, cap) = (24, 40) forces chains of narrow supernodes, (128, 256) the widest leaves."""
+    from dre_b200 import capi
+    from tests import hostcheck
+
+    monkeypatch.setenv("DRE_LEAF_SIZE", str(leaf))
+    monkeypatch.setenv("DRE_MAX_SNODE", str(cap))
+    E, A, B, C, _ = pencils.rail_pencil(n)
+    api.reset_backend()
+    api.upload_pencil(E, A)
+    be = api.backend()
+    S = hostcheck.Sym(capi.SymbolicAnalysis(E, A, leaf_size=leaf | (cap << 16)))
+    info = be.ctx.symbolic_info()
+    assert info["nnz_L"] == S.info["nnz_L"] and info["nsupernodes"] == S.nsn
+    rng = np.random.default_rng(11)
+    a, e = 1.0, -1.0 / 200.0
+    F = api.PencilCombo(a, e)
+    for mu in (-0.37, -0.02 + 0.11j):
+        cx = isinstance(mu, complex)
+        dtype = complex if cx else float
+        for nrhs in (250, 37, 3):
+            R = rng.standard_normal((n, nrhs))
+            out = api.solve_block(api.BlockLinearProblem(F, api.DeviceMatrix.from_host(R)), mu=mu)
+            V = out[0].to_host() + 1j * out[1].to_host() if cx else out.to_host()
+            if nrhs == 250:
+                Lh, Linvh, dvech = hostcheck.factor(S, a, e + mu, dtype)
+                dv = be.ctx.debug_export("dvec", cx)
+                assert _rel(dv, dvech) < 1e-11, "pivots"
+                Ld = be.ctx.debug_export("L", cx)
+                for J in range(S.nsn):
+                    s_, f_ = S.s(J), S.s(J) + S.u(J)
+                    Pd = Ld[S.panel_off[J]:S.panel_off[J + 1]].reshape(s_, f_).T
+                    Ph = Lh[S.panel_off[J]:S.panel_off[J + 1]].reshape(s_, f_).T
+                    assert _rel(np.tril(Pd[:s_], -1), np.tril(Ph[:s_], -1)) < 1e-10 or \
+                        np.linalg.norm(np.tril(Ph[:s_], -1)) < 1e-300, ("L11", J)
+                    assert _rel(Pd[s_:], Ph[s_:]) < 1e-10 or np.linalg.norm(Ph[s_:]) < 1e-300, ("L21", J)
+                Li = be.ctx.debug_export("Linv", cx)
+                for J in range(S.nsn):
+                    s_ = S.s(J)
+                    Lid = Li[S.linv_off[J]:S.linv_off[J + 1]].reshape(s_, s_).T
+                    assert _rel(np.tril(Lid), Linvh[J]) < 1e-10, ("Linv", J)
+            M = (a * A + (e + mu) * E).tocsc()
+            ref = spla.splu(M.astype(dtype)).solve(R.astype(dtype))
+            assert _rel(V, ref) < 1e-10, (mu, nrhs)
+            assert _rel(M @ V, R) < 1e-11, (mu, nrhs)
+    api.reset_backend()
 
 
 @pytest.mark.parametrize("mu", [-0.2, -0.05 + 0.3j])
