@@ -645,6 +645,10 @@ class BufferedIterator:  # helpers.jl:70-75, 106-113
             self.buffer = list(self.generator.take_many())
         return self.buffer.pop(0)
 
+    def peek(self):
+        """Next shift if it is already buffered (never triggers take_many!), else None."""
+        return self.buffer[0] if self.buffer else None
+
 
 class WrappedIterator:  # helpers.jl:85-104
     def __init__(self, func, gen):
@@ -670,6 +674,10 @@ class _CycleIterator:  # Stateful(cycle(values)), helpers.jl:93
     def take(self):
         return next(self._it)
 
+    def peek(self):
+        self._it, probe = itertools.tee(self._it)
+        return next(probe)
+
 
 class _ListIterator:  # plain vector: take! = popfirst! (Shifts.jl:116)
     def __init__(self, values):
@@ -680,6 +688,9 @@ class _ListIterator:  # plain vector: take! = popfirst! (Shifts.jl:116)
 
     def take(self):
         return self.values.pop(0)
+
+    def peek(self):
+        return self.values[0] if self.values else None
 
     def take_many(self):
         return self.values
@@ -862,6 +873,20 @@ def _fused_inner(alg: ADI) -> bool:
     return isinstance(alg.inner_alg, (Backslash, ShermanMorrisonWoodbury))
 
 
+def _prefetch_next_factorization(cache: ADICache):
+    """Performance hint only: when the next shift is already known (buffered), queue its numeric
+    factorization on the library's side stream so that it overlaps this step's remaining work."""
+    peek = getattr(cache.shifts_oracle, "peek", None)
+    if peek is None or not _fused_inner(cache.alg) or len(cache.shifts) >= cache.alg.maxiters:
+        return
+    nxt = peek()
+    if nxt is None:
+        return
+    be = backend()
+    nxt = complex(nxt)
+    be.check(be.lib.dre_prefactor(be.h, nxt.real, nxt.imag))
+
+
 def perform_single_step_(cache: ADICache, mu: float):
     """adi.jl:149-179: V = (A' + mu E')^-1 R; X += -2 mu alpha V T V'; R -= 2 mu E' V."""
     be = backend()
@@ -872,6 +897,7 @@ def perform_single_step_(cache: ADICache, mu: float):
         _set_operator(prob.A, transpose=True)
         V = DeviceMatrix.empty(R.ncols)
         be.check(be.lib.dre_adi_step(be.h, mu, 0.0, R.view, V.view, View(-1, 0, 0)))
+        _prefetch_next_factorization(cache)
     else:
         F = (prob.A.adjoint().plus_sparse(PencilCombo(0.0, mu)) if isinstance(prob.A, LowRankUpdate)
              else prob.A.T + PencilCombo(0.0, mu))
@@ -897,6 +923,7 @@ def perform_double_step_(cache: ADICache, mu: complex):
         V1 = DeviceMatrix.empty(R.ncols)
         V2 = DeviceMatrix.empty(R.ncols)
         be.check(be.lib.dre_adi_step(be.h, mu.real, mu.imag, R.view, V1.view, V2.view))
+        _prefetch_next_factorization(cache)
     else:
         F = (prob.A.adjoint().plus_sparse(PencilCombo(0.0, 0.0)) if isinstance(prob.A, LowRankUpdate)
              else prob.A.T)

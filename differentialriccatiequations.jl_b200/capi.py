@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "dre_last_error", "dre_version", "dre_symbolic_create", "dre_symbolic_destroy", "dre_symbolic_get_info",
     "dre_symbolic_export", "dre_create", "dre_destroy", "dre_sync", "dre_set_pencil", "dre_get_symbolic_info",
     "dre_mat_create", "dre_mat_free", "dre_mat_upload", "dre_mat_download", "dre_mat_copy", "dre_mat_axpby",
-    "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_shift_solve", "dre_adi_step",
+    "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_prefactor", "dre_shift_solve", "dre_adi_step",
     "dre_ldlt_norm", "dre_ldlt_compress", "dre_rrqr", "dre_debug_export", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
     "dre_stats_get",
 ]
@@ -46,6 +46,7 @@ class SymbolicInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("factorizations", C.c_int64), ("solves", C.c_int64),
                 ("spmms", C.c_int64), ("grams", C.c_int64), ("tallgemms", C.c_int64),
+                ("prefactors", C.c_int64), ("prefactor_hits", C.c_int64),
                 ("ms_factor", C.c_double), ("ms_solve", C.c_double), ("ms_spmm", C.c_double),
                 ("ms_gram", C.c_double), ("ms_tallgemm", C.c_double),
                 ("flops_factor", C.c_double), ("flops_gram", C.c_double), ("flops_tallgemm", C.c_double),
@@ -95,6 +96,7 @@ def load():
     lib.dre_gemm_tn.argtypes = [p, View, View, pdbl, i64]
     lib.dre_gemm_nn.argtypes = [p, dbl, View, pdbl, i64, dbl, View]
     lib.dre_set_operator.argtypes = [p, dbl, dbl, dbl, View, View]
+    lib.dre_prefactor.argtypes = [p, dbl, dbl]
     lib.dre_shift_solve.argtypes = [p, dbl, dbl, View, View, View]
     lib.dre_adi_step.argtypes = [p, dbl, dbl, View, View, View]
     lib.dre_ldlt_norm.argtypes = [p, View, pdbl, i64, dbl, pdbl]

@@ -119,19 +119,29 @@ struct dre_context {
     int64_t linv_elems = 0, upd_elems = 0;
 
     // factor storage (sized for complex, reused for real)
-    void* d_L = nullptr;
-    void* d_Linv = nullptr;
-    void* d_dvec = nullptr;
-    void* d_U = nullptr;
+    // Two factor slots: while the sweeps of ADI step i read slot `cur` on the main stream, the numeric
+    // factorization of the NEXT shift (dre_prefactor) runs on the side stream into the other slot -- the
+    // factorization is a latency-bound chain of small launches that leaves most SMs idle, the sweeps /
+    // Gram / compression kernels of the main stream fill them.
+    struct FactorSlot {
+        void* L = nullptr;
+        void* Linv = nullptr;
+        void* dvec = nullptr;
+        void* U = nullptr;           // update matrices (scratch of the factorization)
+        bool valid = false;          // key below describes the factorization held (or in flight)
+        double a = 0, re = 0, im = 0;
+        int tw = 0;                  // 1 real, 2 complex
+        cudaEvent_t ready = nullptr; // recorded behind the factorization
+        cudaEvent_t released = nullptr;  // recorded on the main stream behind the last sweeps that read the slot
+        bool has_reader = false;
+    };
+    FactorSlot slot[2];
+    int cur = 0;
+    cudaStream_t st2 = nullptr;      // side stream of dre_prefactor
     DBuf<unsigned char> tbuf;
     DBuf<unsigned char> Wbuf;
     DBuf<double> btw, sol;
     int32_t* d_errflag = nullptr;
-
-    // key of the numeric factorization currently held in d_L (re-used when the shift repeats)
-    bool fact_valid = false;
-    double fact_a = 0, fact_re = 0, fact_im = 0;
-    int fact_tw = 0;
 
     // operator F = a A + e E + inv(alpha) U Vt'
     double op_a = 1.0, op_e = 0.0, op_alpha = 1.0;
@@ -142,7 +152,7 @@ struct dre_context {
     BlockCache cache;
 
     // dense workspaces
-    DBuf<double> gram_partial, gbuf, gbuf2, cbuf, wsel, wsel2, small, stage, qws, pws, qtmp, rt, tmp_panel, evals;
+    DBuf<double> gram_partial, gbuf, gbuf2, cbuf, wsel, wsel2, small, stage, qws, pws, qtmp, rt, rt2, tmp_panel, evals, cnorm;
     DBuf<double> syevd_work;
     DBuf<int32_t> ibuf;
     double* h_pinned = nullptr;
@@ -227,9 +237,16 @@ static const bool g_trace = getenv("DRE_TRACE") != nullptr;
 struct HostTrace {
     const char* name;
     std::chrono::steady_clock::time_point t0;
-    explicit HostTrace(const char* n) : name(n) { if (g_trace) t0 = std::chrono::steady_clock::now(); }
+    cudaStream_t sync_stream = nullptr;   // when set, the scope ends with a stream sync (GPU time attribution)
+    explicit HostTrace(const char* n, cudaStream_t s = nullptr) : name(n), sync_stream(s) {
+        if (g_trace) {
+            if (sync_stream) cudaStreamSynchronize(sync_stream);
+            t0 = std::chrono::steady_clock::now();
+        }
+    }
     ~HostTrace() {
         if (g_trace) {
+            if (sync_stream) cudaStreamSynchronize(sync_stream);
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (ms > 0.5) fprintf(stderr, "[dre trace] %-24s %9.3f ms\n", name, ms);
         }
@@ -286,28 +303,28 @@ int tall_gemm(dre_context* c, double alpha, const double* X, int64_t ldx, int a,
 // numeric factorization + solve
 // ---------------------------------------------------------------------------------------------
 template <class T>
-int factor(dre_context* c, T emu) {
+int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) {
     const Symbolic& S = c->sym;
     Timer t(c, &c->stats.ms_factor);
-    T* L = (T*)c->d_L;
-    T* Linv = (T*)c->d_Linv;
-    T* dvec = (T*)c->d_dvec;
-    T* U = (T*)c->d_U;
-    CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), c->st));
-    if (c->upd_elems > 0) CU(cudaMemsetAsync(U, 0, (size_t)c->upd_elems * sizeof(T), c->st));
-    launch_assemble<T>(c->dS, L, c->op_a, emu, c->st, &c->stats.kernel_launches);
+    T* L = (T*)fs.L;
+    T* Linv = (T*)fs.Linv;
+    T* dvec = (T*)fs.dvec;
+    T* U = (T*)fs.U;
+    CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), st));
+    if (c->upd_elems > 0) CU(cudaMemsetAsync(U, 0, (size_t)c->upd_elems * sizeof(T), st));
+    launch_assemble<T>(c->dS, L, c->op_a, emu, st, &c->stats.kernel_launches);
     for (int l = 0; l < S.nlevels; ++l) {
         const dre_context::LevelWork& lw = c->levels[l];
         if (lw.ea_count > 0)
-            launch_extend_add<T>(c->dS, c->d_ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, U, c->st,
+            launch_extend_add<T>(c->dS, c->d_ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, U, st,
                                  &c->stats.kernel_launches);
-        launch_diag<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, Linv, dvec, c->d_errflag, c->st,
+        launch_diag<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, Linv, dvec, c->d_errflag, st,
                        &c->stats.kernel_launches);
         if (lw.l21_count > 0)
-            launch_l21<T>(c->dS, c->d_l21_items + lw.l21_begin, lw.l21_count, L, Linv, dvec, c->st,
+            launch_l21<T>(c->dS, c->d_l21_items + lw.l21_begin, lw.l21_count, L, Linv, dvec, st,
                           &c->stats.kernel_launches);
         if (lw.schur_count > 0)
-            launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dvec, U, c->st,
+            launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dvec, U, st,
                             &c->stats.kernel_launches);
     }
     CU(cudaGetLastError());
@@ -324,9 +341,10 @@ int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
         HostTrace tr("tbuf.ensure");
         CU(c->tbuf.ensure((size_t)std::max<int64_t>(S.sum_u, 1) * ldw * sizeof(T)));
     }
-    const T* L = (const T*)c->d_L;
-    const T* Linv = (const T*)c->d_Linv;
-    const T* dvec = (const T*)c->d_dvec;
+    dre_context::FactorSlot& fs = c->slot[c->cur];
+    const T* L = (const T*)fs.L;
+    const T* Linv = (const T*)fs.Linv;
+    const T* dvec = (const T*)fs.dvec;
     T* tb = (T*)c->tbuf.p;
     for (int l = 0; l < S.nlevels; ++l) {
         const dre_context::LevelWork& lw = c->levels[l];
@@ -339,12 +357,68 @@ int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
                             c->st, &c->stats.kernel_launches);
     }
     CU(cudaGetLastError());
+    CU(cudaEventRecord(fs.released, c->st));
+    fs.has_reader = true;
     c->stats.solves++;
     {   // 2*nnz(L)*w (factor read once per sweep) + 4*n*r_tot*w (RHS read+write per sweep)
         const double w = (double)sizeof(T);
         c->stats.bytes_solve += 2.0 * (double)S.nnz_L * w + 4.0 * (double)S.n * nrhs * w;
         c->stats.flops_solve += 4.0 * (double)S.nnz_L * nrhs * (sizeof(T) == sizeof(double) ? 1.0 : 4.0);
     }
+    return DRE_OK;
+}
+
+inline bool slot_matches(const dre_context* c, const dre_context::FactorSlot& fs, double mu_re, double mu_im, int tw) {
+    return fs.valid && fs.a == c->op_a && fs.re == c->op_e + mu_re && fs.im == mu_im && fs.tw == tw;
+}
+
+// Make c->cur a slot holding the factorization for (op, mu) as seen from stream `st` (the main stream):
+// a slot filled by dre_prefactor is adopted behind its `ready` event; otherwise the slot not used by the
+// last sweeps is (re)factored on `st`.
+template <class T>
+int acquire_factor(dre_context* c, double mu_re, double mu_im, T emu, cudaStream_t st) {
+    const int tw = (int)(sizeof(T) / sizeof(double));
+    for (int k = 0; k < 2; ++k) {
+        const int i = (c->cur + k) & 1;
+        if (slot_matches(c, c->slot[i], mu_re, mu_im, tw)) {
+            CU(cudaStreamWaitEvent(st, c->slot[i].ready, 0));
+            if (i != c->cur) c->stats.prefactor_hits++;
+            c->cur = i;
+            return DRE_OK;
+        }
+    }
+    const int i = c->cur ^ 1;
+    dre_context::FactorSlot& fs = c->slot[i];
+    if (fs.valid) CU(cudaStreamWaitEvent(st, fs.ready, 0));   // an unused prefactorization may still be in flight
+    fs.valid = false;
+    HostTrace tr(sizeof(T) == 8 ? "factor<double> launch" : "factor<cplx> launch");
+    int rc = factor<T>(c, fs, st, emu);
+    if (rc) return rc;
+    CU(cudaEventRecord(fs.ready, st));
+    fs.valid = true;
+    fs.a = c->op_a; fs.re = c->op_e + mu_re; fs.im = mu_im; fs.tw = tw;
+    fs.has_reader = false;
+    c->cur = i;
+    return DRE_OK;
+}
+
+template <class T>
+int prefactor_t(dre_context* c, double mu_re, double mu_im, T emu) {
+    const int tw = (int)(sizeof(T) / sizeof(double));
+    for (int k = 0; k < 2; ++k)
+        if (slot_matches(c, c->slot[k], mu_re, mu_im, tw)) return DRE_OK;   // already held / in flight
+    const int i = c->cur ^ 1;
+    dre_context::FactorSlot& fs = c->slot[i];
+    if (fs.valid) CU(cudaStreamWaitEvent(c->st2, fs.ready, 0));
+    if (fs.has_reader) CU(cudaStreamWaitEvent(c->st2, fs.released, 0));   // sweeps that still read the slot
+    fs.valid = false;
+    int rc = factor<T>(c, fs, c->st2, emu);
+    if (rc) return rc;
+    CU(cudaEventRecord(fs.ready, c->st2));
+    fs.valid = true;
+    fs.a = c->op_a; fs.re = c->op_e + mu_re; fs.im = mu_im; fs.tw = tw;
+    fs.has_reader = false;
+    c->stats.prefactors++;
     return DRE_OK;
 }
 
@@ -369,15 +443,8 @@ int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_
     make_emu(c->op_e, mu_re, mu_im, emu);
     const int tw = (int)(sizeof(T) / sizeof(double));  // 1 or 2 doubles per element
     int rc = DRE_OK;
-    if (!(c->fact_valid && c->fact_a == c->op_a && c->fact_re == c->op_e + mu_re && c->fact_im == mu_im &&
-          c->fact_tw == tw)) {
-        c->fact_valid = false;
-        HostTrace tr(sizeof(T) == 8 ? "factor<double> launch" : "factor<cplx> launch");
-        rc = factor<T>(c, emu);
-        if (rc) return rc;
-        c->fact_valid = true;
-        c->fact_a = c->op_a; c->fact_re = c->op_e + mu_re; c->fact_im = mu_im; c->fact_tw = tw;
-    }
+    rc = acquire_factor<T>(c, mu_re, mu_im, emu, c->st);
+    if (rc) return rc;
     {
         HostTrace tr(sizeof(T) == 8 ? "sweeps<double> launch" : "sweeps<cplx> launch");
         rc = solve_sweeps<T>(c, W, ldw, nrhs);
@@ -435,9 +502,13 @@ struct RRState {
 
 int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds, int cols, const double* d_colscale,
                      int rt_row0) {
+    // Block Gram-Schmidt in two granularities: a block of up to PBIG columns is projected twice against the
+    // basis it finds (two fat Gram + tall-GEMM pairs, where the flops are), then its 64-column sub-panels
+    // only have to be projected against the few directions added inside the block before the pivoted-
+    // Cholesky selection / CholQR2 of their remainder.
     const int64_t n = c->sym.n;
-    constexpr int PB = 64;
-    CU(c->pws.ensure((size_t)n * PB));
+    constexpr int PB = 64, PBIG = 256;
+    CU(c->pws.ensure((size_t)n * PBIG));
     CU(c->qtmp.ensure((size_t)n * PB));
     CU(c->gbuf.ensure(PB * PB));
     CU(c->gbuf2.ensure(PB * PB));
@@ -447,61 +518,123 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
     CU(c->small.ensure(8));
     int rc = ensure_pinned(c, 16);
     if (rc) return rc;
-    double* Pw = c->pws.p;
+    double* Pbig = c->pws.p;
     double* Qt = c->qtmp.p;
-    for (int c0 = 0; c0 < cols; c0 += PB) {
-        const int pb = std::min(PB, cols - c0);
-        launch_copy_scale(Pw, PB, src + c0, lds, n, pb, d_colscale ? d_colscale + c0 : nullptr, c->st,
+    for (int c0 = 0; c0 < cols; c0 += PBIG) {
+        const int pbig = std::min(PBIG, cols - c0);
+        launch_copy_scale(Pbig, PBIG, src + c0, lds, n, pbig, d_colscale ? d_colscale + c0 : nullptr, c->st,
                           &c->stats.kernel_launches);
-        for (int round = 0; round < 8; ++round) {
-            s.rounds++;
-            if (s.rho > 0) {
-                CU(c->cbuf.ensure((size_t)PB * s.rho));
-                for (int pass = 0; pass < 2; ++pass) {
-                    // C' = Pw' Q (pb x rho): coefficients, accumulated into RT rows of this panel
-                    rc = gram_dev(c, Pw, PB, pb, s.Q, s.ldq, s.rho, n, nullptr, c->cbuf.p, s.rho,
-                                  s.RT + (int64_t)(rt_row0 + c0) * s.ldrt, s.ldrt);
-                    if (rc) return rc;
-                    rc = tall_gemm(c, -1.0, s.Q, s.ldq, s.rho, c->cbuf.p, s.rho, 1, 1.0, Pw, PB, pb, n);
-                    if (rc) return rc;
-                }
-            }
-            rc = gram_dev(c, Pw, PB, pb, Pw, PB, pb, n, nullptr, c->gbuf.p, PB, nullptr, 0);
-            if (rc) return rc;
-            const double drop = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
-            launch_pivchol(c->gbuf.p, PB, pb, drop * drop, 1e-12, c->wsel.p, c->ibuf.p, c->small.p, c->st,
-                           &c->stats.kernel_launches);
-            if (s.rho + PB > s.qcap) return fail(c, DRE_ERR_STATE, "rank-revealing QR: basis capacity exceeded");
-            rc = tall_gemm(c, 1.0, Pw, PB, pb, c->wsel.p, PB, 0, 0.0, Qt, PB, PB, n);
-            if (rc) return rc;
-            rc = gram_dev(c, Qt, PB, PB, Qt, PB, PB, n, nullptr, c->gbuf2.p, PB, nullptr, 0);
-            if (rc) return rc;
-            launch_pivchol(c->gbuf2.p, PB, PB, 0.01, 0.0, c->wsel2.p, c->ibuf.p + 2, c->small.p + 2, c->st,
-                           &c->stats.kernel_launches);
-            rc = tall_gemm(c, 1.0, Qt, PB, PB, c->wsel2.p, PB, 0, 0.0, s.Q + s.rho, s.ldq, PB, n);
-            if (rc) return rc;
-            // coefficients of the panel in the new directions (candidate columns beyond nsel2 are zero) and
-            // removal of that part, so that the basis is complete even if this was the last round
-            CU(c->cbuf.ensure((size_t)PB * std::max(s.rho, PB)));
-            rc = gram_dev(c, Pw, PB, pb, s.Q + s.rho, s.ldq, PB, n, nullptr, c->cbuf.p, PB,
-                          s.RT + (int64_t)(rt_row0 + c0) * s.ldrt + s.rho, s.ldrt);
-            if (rc) return rc;
-            rc = tall_gemm(c, -1.0, s.Q + s.rho, s.ldq, PB, c->cbuf.p, PB, 1, 1.0, Pw, PB, pb, n);
-            if (rc) return rc;
-            int32_t* hi = (int32_t*)(c->h_pinned + 8);
-            CU(cudaMemcpyAsync(hi, c->ibuf.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
-            CU(cudaMemcpyAsync(c->h_pinned, c->small.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        {   // the drop threshold is relative to the largest ORIGINAL column norm met so far
+            constexpr int NBLK = 296;
+            CU(c->gram_partial.ensure((size_t)NBLK * PBIG));
+            CU(c->cnorm.ensure(PBIG));
+            launch_colnorm2(Pbig, PBIG, n, pbig, c->gram_partial.p, NBLK, c->cnorm.p, c->st, &c->stats.kernel_launches);
+            if ((rc = ensure_pinned(c, PBIG + 16))) return rc;
+            CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
             CU(cudaStreamSynchronize(c->st));
-            const int nsel = hi[0], nsel2 = hi[2];
-            const double dfirst = c->h_pinned[0], remaining = c->h_pinned[1];
-            if (round == 0) s.scale2 = std::max(s.scale2, dfirst);
-            if (nsel == 0 || nsel2 == 0) break;
-            s.rho += nsel2;
-            // the remaining (unselected) columns are certified negligible when the Gram rounding noise
-            // (~1e-13 * dfirst) is below the drop threshold and the remaining Schur diagonal is too
-            const double drop_now = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
-            if (nsel2 == nsel && remaining <= drop_now * drop_now && 1e-13 * dfirst <= drop_now * drop_now) break;
-            if (nsel == pb && nsel2 == pb && round > 0) { /* keep going: coefficients of the new columns */ }
+            for (int j = 0; j < pbig; ++j) s.scale2 = std::max(s.scale2, c->h_pinned[16 + j]);
+        }
+        const int rho0 = s.rho;
+        if (rho0 > 0) {
+            CU(c->cbuf.ensure((size_t)PBIG * rho0));
+            for (int pass = 0; pass < 2; ++pass) {
+                // C' = P' Q (pbig x rho0): coefficients, accumulated into the RT rows of this block
+                rc = gram_dev(c, Pbig, PBIG, pbig, s.Q, s.ldq, rho0, n, nullptr, c->cbuf.p, rho0,
+                              s.RT + (int64_t)(rt_row0 + c0) * s.ldrt, s.ldrt);
+                if (rc) return rc;
+                rc = tall_gemm(c, -1.0, s.Q, s.ldq, rho0, c->cbuf.p, rho0, 1, 1.0, Pbig, PBIG, pbig, n);
+                if (rc) return rc;
+            }
+        }
+        for (int sc = 0; sc < pbig; sc += PB) {
+            const int pb = std::min(PB, pbig - sc);
+            double* Pw = Pbig + sc;
+            double* RTrow = s.RT + (int64_t)(rt_row0 + c0 + sc) * s.ldrt;
+            double trace_d0 = 0.0;
+            if (g_trace) {   // diagnostic only: largest squared column norm of the sub-panel's remainder so far
+                rc = gram_dev(c, Pw, PBIG, pb, Pw, PBIG, pb, n, nullptr, c->gbuf.p, PB, nullptr, 0);
+                if (rc) return rc;
+                std::vector<double> hg((size_t)PB * PB);
+                CU(cudaMemcpyAsync(hg.data(), c->gbuf.p, sizeof(double) * PB * PB, cudaMemcpyDeviceToHost, c->st));
+                CU(cudaStreamSynchronize(c->st));
+                for (int i = 0; i < pb; ++i) trace_d0 = std::max(trace_d0, hg[(size_t)i * PB + i]);
+            }
+            for (int round = 0; round < 8; ++round) {
+                s.rounds++;
+                const int nnew = s.rho - rho0;   // directions added inside this block
+                if (nnew > 0) {
+                    CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
+                    for (int pass = 0; pass < 2; ++pass) {
+                        rc = gram_dev(c, Pw, PBIG, pb, s.Q + rho0, s.ldq, nnew, n, nullptr, c->cbuf.p, nnew,
+                                      RTrow + rho0, s.ldrt);
+                        if (rc) return rc;
+                        rc = tall_gemm(c, -1.0, s.Q + rho0, s.ldq, nnew, c->cbuf.p, nnew, 1, 1.0, Pw, PBIG, pb, n);
+                        if (rc) return rc;
+                    }
+                }
+                rc = gram_dev(c, Pw, PBIG, pb, Pw, PBIG, pb, n, nullptr, c->gbuf.p, PB, nullptr, 0);
+                if (rc) return rc;
+                const double drop = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
+                launch_pivchol(c->gbuf.p, PB, pb, drop * drop, 1e-12, c->wsel.p, c->ibuf.p, c->small.p, c->st,
+                               &c->stats.kernel_launches);
+                if (s.rho + PB > s.qcap) return fail(c, DRE_ERR_STATE, "rank-revealing QR: basis capacity exceeded");
+                // the host needs nsel before it is worth orthonormalising candidates: most sub-panels of a
+                // late ADI increment add nothing
+                int32_t* hi = (int32_t*)(c->h_pinned + 8);
+                CU(cudaMemcpyAsync(hi, c->ibuf.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+                CU(cudaMemcpyAsync(c->h_pinned, c->small.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+                CU(cudaStreamSynchronize(c->st));
+                const int nsel = hi[0];
+                const double dfirst = c->h_pinned[0];
+                const double remaining = c->h_pinned[1];
+                if (round == 0) s.scale2 = std::max(s.scale2, dfirst);
+                int nsel2 = 0;
+                if (nsel > 0) {
+                    rc = tall_gemm(c, 1.0, Pw, PBIG, pb, c->wsel.p, PB, 0, 0.0, Qt, PB, PB, n);
+                    if (rc) return rc;
+                    if (s.rho > 0) {
+                        // Re-orthogonalise the (unit-norm) candidates against the WHOLE basis: Wsel combines columns
+                        // with coefficients up to 1e6, which lifts the eps-level basis components of the large
+                        // columns to ~1e-10 of a small selected direction; without this step the basis loses
+                        // orthogonality and later panels "find" directions that are already in it.
+                        CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
+                        rc = gram_dev(c, Qt, PB, PB, s.Q, s.ldq, s.rho, n, nullptr, c->cbuf.p, s.rho, nullptr, 0);
+                        if (rc) return rc;
+                        rc = tall_gemm(c, -1.0, s.Q, s.ldq, s.rho, c->cbuf.p, s.rho, 1, 1.0, Qt, PB, PB, n);
+                        if (rc) return rc;
+                    }
+                    rc = gram_dev(c, Qt, PB, PB, Qt, PB, PB, n, nullptr, c->gbuf2.p, PB, nullptr, 0);
+                    if (rc) return rc;
+                    launch_pivchol(c->gbuf2.p, PB, PB, 0.01, 0.0, c->wsel2.p, c->ibuf.p + 2, c->small.p + 2, c->st,
+                                   &c->stats.kernel_launches);
+                    rc = tall_gemm(c, 1.0, Qt, PB, PB, c->wsel2.p, PB, 0, 0.0, s.Q + s.rho, s.ldq, PB, n);
+                    if (rc) return rc;
+                    // coefficients of the sub-panel in the new directions (candidate columns beyond nsel2 are
+                    // zero) and removal of that part, so that the basis is complete even if this was the last round
+                    CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
+                    rc = gram_dev(c, Pw, PBIG, pb, s.Q + s.rho, s.ldq, PB, n, nullptr, c->cbuf.p, PB, RTrow + s.rho,
+                                  s.ldrt);
+                    if (rc) return rc;
+                    rc = tall_gemm(c, -1.0, s.Q + s.rho, s.ldq, PB, c->cbuf.p, PB, 1, 1.0, Pw, PBIG, pb, n);
+                    if (rc) return rc;
+                    CU(cudaMemcpyAsync(hi + 2, c->ibuf.p + 2, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+                    CU(cudaStreamSynchronize(c->st));
+                    nsel2 = hi[2];
+                }
+                if (g_trace)
+                    fprintf(stderr,
+                            "[dre rr] row0 %5d c0 %4d pb %2d round %d rho %4d nsel %2d nsel2 %2d rem/col %.2e left %.2e "
+                            "scale %.2e\n",
+                            rt_row0, c0 + sc, pb, round, s.rho, nsel, nsel2,
+                            std::sqrt(dfirst / std::max(trace_d0, 1e-300)),
+                            std::sqrt(remaining / std::max(trace_d0, 1e-300)), std::sqrt(s.scale2));
+                if (nsel == 0 || nsel2 == 0) break;
+                s.rho += nsel2;
+                // the remaining (unselected) columns are certified negligible when the Gram rounding noise
+                // (~1e-13 * dfirst) is below the drop threshold and the remaining Schur diagonal is too
+                const double drop_now = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
+                if (nsel2 == nsel && remaining <= drop_now * drop_now && 1e-13 * dfirst <= drop_now * drop_now) break;
+            }
         }
     }
     return DRE_OK;
@@ -616,6 +749,12 @@ int32_t dre_create(int32_t device, dre_context** out) {
     c->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    e = cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    for (auto& fs : c->slot) {
+        cudaEventCreateWithFlags(&fs.ready, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&fs.released, cudaEventDisableTiming);
+    }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     cudaEventCreate(&c->tev0);
@@ -635,15 +774,19 @@ int32_t dre_create(int32_t device, dre_context** out) {
 }
 
 static void release_pencil(dre_context* c) {
+    if (c->st2) cudaStreamSynchronize(c->st2);
     for (void* p : c->owned) cudaFree(p);
     c->owned.clear();
-    if (c->d_L) cudaFree(c->d_L);
-    if (c->d_Linv) cudaFree(c->d_Linv);
-    if (c->d_dvec) cudaFree(c->d_dvec);
-    if (c->d_U) cudaFree(c->d_U);
-    c->d_L = c->d_Linv = c->d_dvec = c->d_U = nullptr;
+    for (auto& fs : c->slot) {
+        if (fs.L) cudaFree(fs.L);
+        if (fs.Linv) cudaFree(fs.Linv);
+        if (fs.dvec) cudaFree(fs.dvec);
+        if (fs.U) cudaFree(fs.U);
+        fs.L = fs.Linv = fs.dvec = fs.U = nullptr;
+        fs.valid = fs.has_reader = false;
+    }
+    c->cur = 0;
     c->has_pencil = false;
-    c->fact_valid = false;
 }
 
 int32_t dre_destroy(dre_context* c) {
@@ -656,7 +799,7 @@ int32_t dre_destroy(dre_context* c) {
     c->tbuf.release(); c->Wbuf.release(); c->btw.release(); c->sol.release();
     c->gram_partial.release(); c->gbuf.release(); c->gbuf2.release(); c->cbuf.release(); c->wsel.release();
     c->wsel2.release(); c->small.release(); c->stage.release(); c->qws.release(); c->pws.release();
-    c->qtmp.release(); c->rt.release(); c->tmp_panel.release(); c->evals.release(); c->syevd_work.release();
+    c->qtmp.release(); c->rt.release(); c->rt2.release(); c->cnorm.release(); c->tmp_panel.release(); c->evals.release(); c->syevd_work.release();
     c->ibuf.release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->d_errflag) cudaFree(c->d_errflag);
@@ -665,6 +808,11 @@ int32_t dre_destroy(dre_context* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->tev0) cudaEventDestroy(c->tev0);
     if (c->tev1) cudaEventDestroy(c->tev1);
+    for (auto& fs : c->slot) {
+        if (fs.ready) cudaEventDestroy(fs.ready);
+        if (fs.released) cudaEventDestroy(fs.released);
+    }
+    if (c->st2) cudaStreamDestroy(c->st2);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
     return DRE_OK;
@@ -673,6 +821,7 @@ int32_t dre_destroy(dre_context* c) {
 int32_t dre_sync(dre_context* c) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->st2));
     return DRE_OK;
 }
 
@@ -765,10 +914,12 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     if ((rc = upload_vec(c, schur_items, &c->d_schur_items))) return rc;
 
     // factor storage, sized for complex
-    CU(cudaMalloc(&c->d_L, (size_t)std::max<int64_t>(S.nnz_L, 1) * sizeof(cplx)));
-    CU(cudaMalloc(&c->d_Linv, (size_t)std::max<int64_t>(c->linv_elems, 1) * sizeof(cplx)));
-    CU(cudaMalloc(&c->d_dvec, (size_t)S.n * sizeof(cplx)));
-    CU(cudaMalloc(&c->d_U, (size_t)std::max<int64_t>(c->upd_elems, 1) * sizeof(cplx)));
+    for (auto& fs : c->slot) {
+        CU(cudaMalloc(&fs.L, (size_t)std::max<int64_t>(S.nnz_L, 1) * sizeof(cplx)));
+        CU(cudaMalloc(&fs.Linv, (size_t)std::max<int64_t>(c->linv_elems, 1) * sizeof(cplx)));
+        CU(cudaMalloc(&fs.dvec, (size_t)S.n * sizeof(cplx)));
+        CU(cudaMalloc(&fs.U, (size_t)std::max<int64_t>(c->upd_elems, 1) * sizeof(cplx)));
+    }
     c->has_pencil = true;
     c->op_a = 1.0; c->op_e = 0.0; c->op_alpha = 1.0;
     return DRE_OK;
@@ -963,6 +1114,20 @@ int32_t dre_set_operator(dre_context* c, double a, double e, double alpha, dre_v
     return DRE_OK;
 }
 
+int32_t dre_prefactor(dre_context* c, double mu_re, double mu_im) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    if (c->timing) return DRE_OK;   // per-class event timing serialises everything: no overlap to gain
+    if (mu_im != 0.0) {
+        cplx emu;
+        make_emu(c->op_e, mu_re, mu_im, emu);
+        return prefactor_t<cplx>(c, mu_re, mu_im, emu);
+    }
+    double emu;
+    make_emu(c->op_e, mu_re, 0.0, emu);
+    return prefactor_t<double>(c, mu_re, 0.0, emu);
+}
+
 int32_t dre_shift_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     return shifted_solve(c, mu_re, mu_im, R, V1, V2, false);
@@ -1032,6 +1197,7 @@ int32_t dre_ldlt_norm(dre_context* c, dre_view L, const double* D, int64_t ldd, 
 }
 
 static int eig_sym_dev(dre_context* c, double* S, int k, double* d_evals) {
+    HostTrace tr("eig_sym_dev (syevd)", c->st);
     int lwork = 0;
     if (cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, S, k, d_evals,
                                     &lwork) != CUSOLVER_STATUS_SUCCESS)
@@ -1079,6 +1245,8 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     RRState s;
     if ((rc = rr_setup(c, s, ktot, 3e-15, 0.0))) return rc;
     std::vector<double> signs(ktot, 1.0);
+    struct DenseTerm { int t, row0, k; };
+    std::vector<DenseTerm> dense_terms;
     int row0 = 0;
     for (int t = 0; t < nterms; ++t) {
         const int k = Ls[t].ncols;
@@ -1100,44 +1268,53 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
             }
             CU(c->evals.ensure(k));
             CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, k * sizeof(double), cudaMemcpyHostToDevice, c->st));
+            HostTrace tr("compress: rr block (diag core)", c->st);
             if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, c->evals.p, row0))) return rc;
         } else {
-            // dense core: alpha*D = W Lambda W'  ->  block (L W |Lambda|^1/2) with signs sign(Lambda)
-            for (int j = 0; j < k; ++j)
-                for (int i = 0; i < k; ++i)
-                    c->h_pinned[i + (int64_t)j * k] =
-                        0.5 * alphas[t] * (D[i + (int64_t)j * ldd] + D[j + (int64_t)i * ldd]);
-            CU(c->gbuf2.ensure((size_t)k * k));
-            CU(c->evals.ensure(k));
-            CU(cudaMemcpyAsync(c->gbuf2.p, c->h_pinned, (size_t)k * k * sizeof(double), cudaMemcpyHostToDevice, c->st));
-            if ((rc = eig_sym_dev(c, c->gbuf2.p, k, c->evals.p))) return rc;
-            CU(cudaMemcpyAsync(c->h_pinned, c->evals.p, k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-            CU(cudaStreamSynchronize(c->st));
-            for (int j = 0; j < k; ++j) {
-                signs[row0 + j] = (c->h_pinned[j] < 0.0) ? -1.0 : 1.0;
-                c->h_pinned[j] = std::sqrt(std::fabs(c->h_pinned[j]));
-            }
-            CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, k * sizeof(double), cudaMemcpyHostToDevice, c->st));
-            // eigenvector j = column j of the column-major result = row j of the row-major view:
-            // tmp = L * W  with W[i][j] = vec_j[i]  -> w_trans layout (stored j-major)
-            CU(c->tmp_panel.ensure((size_t)n * k));
-            if ((rc = tall_gemm(c, 1.0, vptr(c, Ls[t]), vld(c, Ls[t]), k, c->gbuf2.p, k, 1, 0.0, c->tmp_panel.p, k, k,
-                                n)))
-                return rc;
-            if ((rc = rr_process_block(c, s, c->tmp_panel.p, k, k, c->evals.p, row0))) return rc;
+            // Non-diagonal core (e.g. T = [aS 0 0; 0 0 bD; 0 bD 0] of the Lyapunov residual,
+            // src/lyapunov/residual.jl:21-28): exactly as the reference does (src/LDLt.jl:206-213) the basis is
+            // built from the raw columns and the core enters afterwards, S += R_t' (alpha_t D_t) R_t.
+            dense_terms.push_back({t, row0, k});
+            HostTrace tr("compress: rr block (dense core)", c->st);
+            if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, nullptr, row0))) return rc;
         }
         row0 += k;
     }
     const int rho = s.rho;
     if (rho == 0) return check_errflag(c);
-    // S = RT' diag(signs) RT   (rho x rho)
+    // S = RT' C RT (rho x rho), C = blockdiag(diag(signs) for the scaled diagonal-core terms, alpha_t D_t for the
+    // dense-core terms):  M = C RT block by block, then one Gram product RT' M over the ktot coefficient rows.
     if ((rc = ensure_pinned(c, (size_t)ktot + rho + 64))) return rc;
     CU(cudaStreamSynchronize(c->st));
     for (int i = 0; i < ktot; ++i) c->h_pinned[i] = signs[i];
     CU(c->evals.ensure((size_t)ktot + rho));
     CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, ktot * sizeof(double), cudaMemcpyHostToDevice, c->st));
     CU(c->gbuf.ensure((size_t)rho * rho));
-    if ((rc = gram_dev(c, s.RT, s.ldrt, rho, s.RT, s.ldrt, rho, ktot, c->evals.p, c->gbuf.p, rho, nullptr, 0))) return rc;
+    const double* Mmat = s.RT;
+    if (!dense_terms.empty()) {
+        CU(c->rt2.ensure((size_t)ktot * s.ldrt));
+        CU(cudaMemcpyAsync(c->rt2.p, s.RT, (size_t)ktot * s.ldrt * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        for (const DenseTerm& dt : dense_terms) {
+            const double* D = Ds[dt.t];
+            const int64_t ldd = ldds[dt.t];
+            const int k = dt.k;
+            if ((rc = ensure_pinned(c, (size_t)k * k + 64))) return rc;
+            CU(cudaStreamSynchronize(c->st));
+            for (int j = 0; j < k; ++j)
+                for (int i = 0; i < k; ++i)
+                    c->h_pinned[i + (int64_t)j * k] =
+                        0.5 * alphas[dt.t] * (D[i + (int64_t)j * ldd] + D[j + (int64_t)i * ldd]);
+            CU(c->gbuf2.ensure((size_t)k * k));
+            CU(cudaMemcpyAsync(c->gbuf2.p, c->h_pinned, (size_t)k * k * sizeof(double), cudaMemcpyHostToDevice, c->st));
+            // M_block (k x rho) = C_t (k x k, symmetric) * RT_block (k x rho)
+            if ((rc = tall_gemm(c, 1.0, c->gbuf2.p, k, k, s.RT + (int64_t)dt.row0 * s.ldrt, s.ldrt, 0, 0.0,
+                                c->rt2.p + (int64_t)dt.row0 * s.ldrt, s.ldrt, rho, k)))
+                return rc;
+            CU(cudaStreamSynchronize(c->st));   // h_pinned / gbuf2 are reused
+        }
+        Mmat = c->rt2.p;
+    }
+    if ((rc = gram_dev(c, s.RT, s.ldrt, rho, Mmat, s.ldrt, rho, ktot, c->evals.p, c->gbuf.p, rho, nullptr, 0))) return rc;
     double* d_ev = c->evals.p + ktot;
     if ((rc = eig_sym_dev(c, c->gbuf.p, rho, d_ev))) return rc;
     CU(cudaMemcpyAsync(c->h_pinned, d_ev, rho * sizeof(double), cudaMemcpyDeviceToHost, c->st));
@@ -1206,15 +1383,16 @@ int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double d
 
 int32_t dre_debug_export(dre_context* c, const char* what, void* buf, int64_t cap_bytes, int64_t* len_bytes) {
     if (!c || !what || !len_bytes) return fail(c, DRE_ERR_ARG, "null argument");
-    if (!c->has_pencil || !c->fact_valid) return fail(c, DRE_ERR_STATE, "no numeric factorization held");
+    if (!c->has_pencil || !c->slot[c->cur].valid) return fail(c, DRE_ERR_STATE, "no numeric factorization held");
     const std::string w(what);
-    const size_t tw = (size_t)c->fact_tw * sizeof(double);
+    const dre_context::FactorSlot& fs = c->slot[c->cur];
+    const size_t tw = (size_t)fs.tw * sizeof(double);
     const void* src = nullptr;
     size_t bytes = 0;
-    if (w == "L") { src = c->d_L; bytes = (size_t)c->sym.nnz_L * tw; }
-    else if (w == "Linv") { src = c->d_Linv; bytes = (size_t)c->linv_elems * tw; }
-    else if (w == "dvec") { src = c->d_dvec; bytes = (size_t)c->sym.n * tw; }
-    else if (w == "U") { src = c->d_U; bytes = (size_t)c->upd_elems * tw; }
+    if (w == "L") { src = fs.L; bytes = (size_t)c->sym.nnz_L * tw; }
+    else if (w == "Linv") { src = fs.Linv; bytes = (size_t)c->linv_elems * tw; }
+    else if (w == "dvec") { src = fs.dvec; bytes = (size_t)c->sym.n * tw; }
+    else if (w == "U") { src = fs.U; bytes = (size_t)c->upd_elems * tw; }
     else return fail(c, DRE_ERR_ARG, "dre_debug_export: unknown array name " + w);
     *len_bytes = (int64_t)bytes;
     if (buf && cap_bytes > 0) {

@@ -131,9 +131,235 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double* __restric
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// cp.async helpers (LDGSTS): 16-byte (.cg) and 8-byte (.ca) global -> shared copies with zero fill
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ------------------------------------------------------------------------------------------
+// Gram, pipelined:  partial[split] (a x b) = sum_{rows in split} X[row][:]^T Y[row][:]
+// CTA = 256 threads, output tile 64 (a) x 128 (b), 16-row chunks in a 3-stage cp.async pipeline;
+// warp tile 32 x 32 (4 x 4 DMMA tiles: 8 fragment loads feed 16 DMMAs).
+// ------------------------------------------------------------------------------------------
+constexpr int G2A = 64, G2B = 128, G2K = 16, G2ST = 3;
+constexpr int G2LDA = G2A + 8, G2LDB = G2B + 8;   // = 8 mod 16: two-wavefront fragment loads
+constexpr int G2_STAGE = G2K * (G2LDA + G2LDB);   // doubles per stage
+
+__global__ void __launch_bounds__(256) k_gram2(const double* __restrict__ X, int64_t ldx, int a,
+                                               const double* __restrict__ Y, int64_t ldy, int b, int64_t n,
+                                               double* __restrict__ partial, int tiles_b, int64_t rows_per_split,
+                                               int aligned) {
+    extern __shared__ __align__(16) double g2_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ta = blockIdx.x / tiles_b, tb = blockIdx.x % tiles_b;
+    const int a0 = ta * G2A, b0 = tb * G2B;
+    const int64_t row_begin = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t row_end = min(n, row_begin + rows_per_split);
+    const int nchunks = (int)((row_end - row_begin + G2K - 1) / G2K);
+
+    auto load_stage = [&](int chunk, int st) {
+        double* Xs = g2_smem + st * G2_STAGE;
+        double* Ys = Xs + G2K * G2LDA;
+        const int64_t r0 = row_begin + (int64_t)chunk * G2K;
+        if (aligned) {
+            for (int c = tid; c < G2K * (G2A / 2); c += 256) {      // 16 rows x 32 chunks of 2 doubles
+                const int r = c / (G2A / 2), cc = (c % (G2A / 2)) * 2;
+                const int64_t row = r0 + r;
+                int nb = 0;
+                if (row < row_end) nb = 8 * max(0, min(2, a - (a0 + cc)));
+                cp_async16(Xs + r * G2LDA + cc, nb ? (const void*)(X + row * ldx + a0 + cc) : (const void*)X, nb);
+            }
+            for (int c = tid; c < G2K * (G2B / 2); c += 256) {
+                const int r = c / (G2B / 2), cc = (c % (G2B / 2)) * 2;
+                const int64_t row = r0 + r;
+                int nb = 0;
+                if (row < row_end) nb = 8 * max(0, min(2, b - (b0 + cc)));
+                cp_async16(Ys + r * G2LDB + cc, nb ? (const void*)(Y + row * ldy + b0 + cc) : (const void*)Y, nb);
+            }
+        } else {
+            for (int c = tid; c < G2K * G2A; c += 256) {
+                const int r = c / G2A, cc = c % G2A;
+                const int64_t row = r0 + r;
+                const bool ok = row < row_end && a0 + cc < a;
+                cp_async8(Xs + r * G2LDA + cc, ok ? (const void*)(X + row * ldx + a0 + cc) : (const void*)X, ok ? 8 : 0);
+            }
+            for (int c = tid; c < G2K * G2B; c += 256) {
+                const int r = c / G2B, cc = c % G2B;
+                const int64_t row = r0 + r;
+                const bool ok = row < row_end && b0 + cc < b;
+                cp_async8(Ys + r * G2LDB + cc, ok ? (const void*)(Y + row * ldy + b0 + cc) : (const void*)Y, ok ? 8 : 0);
+            }
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wa = (warp & 1) * 32, wb = (warp >> 1) * 32;
+    const int kk = lane & 3, rr = lane >> 2;
+
+#pragma unroll
+    for (int st = 0; st < G2ST - 1; ++st) {
+        if (st < nchunks) load_stage(st, st);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nchunks; ++it) {
+        cp_async_wait<G2ST - 2>();
+        __syncthreads();
+        if (it + G2ST - 1 < nchunks) load_stage(it + G2ST - 1, (it + G2ST - 1) % G2ST);
+        cp_async_commit();
+        const double* Xs = g2_smem + (it % G2ST) * G2_STAGE;
+        const double* Ys = Xs + G2K * G2LDA;
+#pragma unroll
+        for (int k0 = 0; k0 < G2K; k0 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[mt] = Xs[(k0 + kk) * G2LDA + wa + mt * 8 + rr];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) bf[nt] = Ys[(k0 + kk) * G2LDB + wb + nt * 8 + rr];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+    }
+    cp_async_wait<0>();
+    double* P = partial + (int64_t)blockIdx.y * a * b;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int i = a0 + wa + mt * 8 + rr;
+        if (i >= a) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int j = b0 + wb + nt * 8 + 2 * kk;
+            if (j < b) P[(int64_t)i * b + j] = acc[mt][nt][0];
+            if (j + 1 < b) P[(int64_t)i * b + j + 1] = acc[mt][nt][1];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tall GEMM, pipelined:  Y[n x b] = beta*Y + alpha * X[n x a] * W
+// CTA = 256 threads, output tile 128 rows x 64 cols, K chunks of 16 in a 3-stage cp.async pipeline;
+// warp tile 32 x 32.
+// ------------------------------------------------------------------------------------------
+constexpr int T2M = 128, T2N = 64, T2K = 16, T2ST = 3;
+constexpr int T2LDX = T2K + 4;   // = 4 mod 16
+constexpr int T2LDW = T2N + 8;   // = 8 mod 16
+constexpr int T2_STAGE = T2M * T2LDX + T2K * T2LDW;
+
+__global__ void __launch_bounds__(256) k_tall_gemm2(double alpha, const double* __restrict__ X, int64_t ldx, int a,
+                                                    const double* __restrict__ W, int64_t ldw, int w_trans,
+                                                    double beta, double* __restrict__ Y, int64_t ldy, int b,
+                                                    int64_t n, int aligned_x, int aligned_w) {
+    extern __shared__ __align__(16) double t2_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * T2M;
+    const int b0 = blockIdx.y * T2N;
+    const int nchunks = (a + T2K - 1) / T2K;
+
+    auto load_stage = [&](int chunk, int st) {
+        double* Xs = t2_smem + st * T2_STAGE;
+        double* Ws = Xs + T2M * T2LDX;
+        const int k0 = chunk * T2K;
+        if (aligned_x) {
+            for (int c = tid; c < T2M * (T2K / 2); c += 256) {   // 128 rows x 8 chunks of 2 doubles
+                const int r = c / (T2K / 2), kc = (c % (T2K / 2)) * 2;
+                const int64_t row = row0 + r;
+                int nb = 0;
+                if (row < n) nb = 8 * max(0, min(2, a - (k0 + kc)));
+                cp_async16(Xs + r * T2LDX + kc, nb ? (const void*)(X + row * ldx + k0 + kc) : (const void*)X, nb);
+            }
+        } else {
+            for (int c = tid; c < T2M * T2K; c += 256) {
+                const int r = c / T2K, kc = c % T2K;
+                const int64_t row = row0 + r;
+                const bool ok = row < n && k0 + kc < a;
+                cp_async8(Xs + r * T2LDX + kc, ok ? (const void*)(X + row * ldx + k0 + kc) : (const void*)X, ok ? 8 : 0);
+            }
+        }
+        if (!w_trans && aligned_w) {
+            for (int c = tid; c < T2K * (T2N / 2); c += 256) {
+                const int k = c / (T2N / 2), j = (c % (T2N / 2)) * 2;
+                int nb = 0;
+                if (k0 + k < a) nb = 8 * max(0, min(2, b - (b0 + j)));
+                cp_async16(Ws + k * T2LDW + j, nb ? (const void*)(W + (int64_t)(k0 + k) * ldw + b0 + j) : (const void*)W, nb);
+            }
+        } else {
+            for (int c = tid; c < T2K * T2N; c += 256) {
+                int k, j;
+                if (w_trans) { k = c % T2K; j = c / T2K; } else { k = c / T2N; j = c % T2N; }
+                const bool ok = k0 + k < a && b0 + j < b;
+                const double* src = w_trans ? W + (int64_t)(b0 + j) * ldw + k0 + k : W + (int64_t)(k0 + k) * ldw + b0 + j;
+                cp_async8(Ws + k * T2LDW + j, ok ? (const void*)src : (const void*)W, ok ? 8 : 0);
+            }
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int kk = lane & 3, rr = lane >> 2;
+
+#pragma unroll
+    for (int st = 0; st < T2ST - 1; ++st) {
+        if (st < nchunks) load_stage(st, st);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nchunks; ++it) {
+        cp_async_wait<T2ST - 2>();
+        __syncthreads();
+        if (it + T2ST - 1 < nchunks) load_stage(it + T2ST - 1, (it + T2ST - 1) % T2ST);
+        cp_async_commit();
+        const double* Xs = t2_smem + (it % T2ST) * T2_STAGE;
+        const double* Ws = Xs + T2M * T2LDX;
+#pragma unroll
+        for (int k0 = 0; k0 < T2K; k0 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[mt] = Xs[(wr + mt * 8 + rr) * T2LDX + k0 + kk];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) bf[nt] = Ws[(k0 + kk) * T2LDW + wc + nt * 8 + rr];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int64_t row = row0 + wr + mt * 8 + rr;
+        if (row >= n) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int j = b0 + wc + nt * 8 + 2 * kk;
+            double* y = Y + row * ldy + j;
+            if (j < b) y[0] = (beta == 0.0 ? 0.0 : beta * y[0]) + alpha * acc[mt][nt][0];
+            if (j + 1 < b) y[1] = (beta == 0.0 ? 0.0 : beta * y[1]) + alpha * acc[mt][nt][1];
+        }
+    }
+}
+
 GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
     GramPlan p;
-    int tiles = ((a + GT - 1) / GT) * ((b + GT - 1) / GT);
+    int tiles = ((a + G2A - 1) / G2A) * ((b + G2B - 1) / G2B);   // pipelined kernel: 64 x 128 output tiles
     if (tiles < 1) tiles = 1;
     int64_t chunks = (n + GK - 1) / GK;
     int want = std::max(1, (2 * sm_count + tiles - 1) / tiles);   // ~2 CTAs per SM
@@ -204,11 +430,25 @@ void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t l
         if (launches) *launches += 2;
         return;
     }
-    const int tiles_a = (a + GT - 1) / GT, tiles_b = (b + GT - 1) / GT;
-    dim3 grid(tiles_a * tiles_b, plan.nsplit);
-    k_gram<<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, roww, partial, tiles_b, plan.rows_per_split);
     const int64_t total = (int64_t)a * b;
     int rb = (int)std::min<int64_t>((total + 31) / 32, 148 * 8);  // 8 warps per CTA, 4 output elements per warp
+    if (roww) {   // weighted variant (small core products only): simple 64x64 kernel
+        const int tiles_a = (a + GT - 1) / GT, tiles_b = (b + GT - 1) / GT;
+        dim3 grid(tiles_a * tiles_b, plan.nsplit);
+        k_gram<<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, roww, partial, tiles_b, plan.rows_per_split);
+    } else {
+        static bool attr_set = false;
+        const int smem = G2ST * G2_STAGE * (int)sizeof(double);
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        const int tiles_a = (a + G2A - 1) / G2A, tiles_b = (b + G2B - 1) / G2B;
+        dim3 grid(tiles_a * tiles_b, plan.nsplit);
+        const int aligned = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0) &&
+                            ldx % 2 == 0 && ldy % 2 == 0;
+        k_gram2<<<grid, 256, smem, st>>>(X, ldx, a, Y, ldy, b, n, partial, tiles_b, plan.rows_per_split, aligned);
+    }
     k_reduce_partials<<<rb, 256, 0, st>>>(partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
     if (launches) *launches += 2;
 }
@@ -297,8 +537,16 @@ void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const d
                       int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n, cudaStream_t st,
                       int64_t* launches) {
     if (b <= 0 || n <= 0) return;
-    dim3 grid((unsigned)((n + 63) / 64), (unsigned)((b + 63) / 64));
-    k_tall_gemm<<<grid, 256, 0, st>>>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n);
+    static bool attr_set = false;
+    const int smem = T2ST * T2_STAGE * (int)sizeof(double);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_tall_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((n + T2M - 1) / T2M), (unsigned)((b + T2N - 1) / T2N));
+    const int ax = reinterpret_cast<uintptr_t>(X) % 16 == 0 && ldx % 2 == 0;
+    const int aw = reinterpret_cast<uintptr_t>(W) % 16 == 0 && ldw % 2 == 0;
+    k_tall_gemm2<<<grid, 256, smem, st>>>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, ax, aw);
     if (launches) *launches += 1;
 }
 
@@ -323,6 +571,56 @@ void launch_copy_scale(double* dst, int64_t ldd, const double* src, int64_t lds,
     if (n <= 0 || cols <= 0) return;
     int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
     k_copy_scale<<<blocks, 256, 0, st>>>(dst, ldd, src, lds, n, cols, colscale);
+    if (launches) *launches += 1;
+}
+
+// partial[blk][c] = sum over the block's row range of P[row][c]^2   (cols <= 256, thread per column)
+__global__ void __launch_bounds__(256) k_colnorm2(const double* __restrict__ P, int64_t ldp, int64_t n, int cols,
+                                                  int64_t rows_per_blk, double* __restrict__ partial) {
+    const int c = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_blk, r1 = min(n, r0 + rows_per_blk);
+    double s0 = 0.0, s1 = 0.0;
+    if (c < cols) {
+        int64_t row = r0;
+        for (; row + 1 < r1; row += 2) {
+            const double v0 = P[row * ldp + c], v1 = P[(row + 1) * ldp + c];
+            s0 = fma(v0, v0, s0);
+            s1 = fma(v1, v1, s1);
+        }
+        if (row < r1) { const double v = P[row * ldp + c]; s0 = fma(v, v, s0); }
+        partial[(int64_t)blockIdx.x * cols + c] = s0 + s1;
+    }
+}
+
+// out[c] = sum_rows P[row][c]^2 for c < cols <= 256 (deterministic two-stage reduction); partial: nblk*cols doubles
+void launch_colnorm2(const double* P, int64_t ldp, int64_t n, int cols, double* partial, int nblk, double* out,
+                     cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || cols <= 0) return;
+    const int64_t rpb = (n + nblk - 1) / nblk;
+    k_colnorm2<<<nblk, 256, 0, st>>>(P, ldp, n, cols, rpb, partial);
+    k_reduce_partials<<<(cols + 31) / 32, 256, 0, st>>>(partial, nblk, 1, cols, out, cols, nullptr, 0);
+    if (launches) *launches += 2;
+}
+
+// dst[row][c] = w1[c] * src[row][c] + w2[c] * src[row][idx2[c]]   (two-term column combination)
+__global__ void k_combine_cols(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
+                               int64_t n, int cols, const int32_t* __restrict__ idx2, const double* __restrict__ w1,
+                               const double* __restrict__ w2) {
+    const int64_t total = n * cols;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / cols;
+        const int c = (int)(idx % cols);
+        const double* sr = src + row * lds;
+        dst[row * ldd + c] = w1[c] * sr[c] + w2[c] * sr[idx2[c]];
+    }
+}
+
+void launch_combine_cols(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, int cols,
+                         const int32_t* idx2, const double* w1, const double* w2, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || cols <= 0) return;
+    int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
+    k_combine_cols<<<blocks, 256, 0, st>>>(dst, ldd, src, lds, n, cols, idx2, w1, w2);
     if (launches) *launches += 1;
 }
 

@@ -116,6 +116,11 @@ DRE_API int32_t dre_set_operator(dre_context* ctx, double a, double e, double al
  * Sherman-Morrison-Woodbury correction (src/blocklinear/sherman-morrison-woodbury.jl:10-45).
  * mu_im == 0: V1 = V (V2 ignored).  mu_im != 0: V1 = Re V, V2 = Im V. */
 DRE_API int32_t dre_shift_solve(dre_context* ctx, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2);
+/* Hint: the shift the NEXT dre_adi_step / dre_shift_solve will use (the ADI shift buffer is known ahead,
+ * src/shifts/helpers.jl:106-113).  Queues the numeric factorization for it on a side stream into the spare
+ * factor slot, overlapping the current step's sweeps / Gram / compression work.  Purely a performance hint:
+ * results are identical with or without it. */
+DRE_API int32_t dre_prefactor(dre_context* ctx, double mu_re, double mu_im);
 /* One ADI step (src/lyapunov/adi.jl:149-179 real, :181-225 complex pair):
  *   real:     V1 = (F'+mu E')^-1 R;                          R += -2 mu E' V1
  *   complex:  V  = (F'+mu E')^-1 R, d = Re mu / Im mu,
@@ -153,6 +158,7 @@ typedef struct {
     int64_t factorizations;     /* numeric factorizations */
     int64_t solves;             /* block solves (forward + backward sweep pairs) */
     int64_t spmms, grams, tallgemms;
+    int64_t prefactors, prefactor_hits; /* side-stream factorizations queued / adopted by a solve */
     double ms_factor, ms_solve, ms_spmm, ms_gram, ms_tallgemm; /* CUDA-event times when timing is enabled */
     /* algorithmic work (SURVEY.md section 8d formulas), accumulated per call */
     double flops_factor, flops_gram, flops_tallgemm, flops_solve;
