@@ -30,6 +30,7 @@ import scipy.linalg as sla
 import scipy.sparse as sp
 
 from . import capi
+from . import dist as _dist
 from .capi import View
 
 EPS = float(np.finfo(np.float64).eps)
@@ -338,6 +339,7 @@ def compress_(X: LDLt) -> LDLt:
     be.check(be.lib.dre_ldlt_compress(be.h, nt, views, dptrs, ldds, alphas, 100.0, out.view, capi._dptr(lam),
                                       C.byref(newrank)))
     k2 = newrank.value
+    _dist.assert_same_int(k2, "the rank after compress!")
     Lnew = out.cols(0, k2)
     if cap > 2 * max(k2, 1):  # do not keep a large mostly-unused panel alive
         Lnew = Lnew.copy()
@@ -642,7 +644,7 @@ class BufferedIterator:  # helpers.jl:70-75, 106-113
 
     def take(self):
         if not self.buffer:
-            self.buffer = list(self.generator.take_many())
+            self.buffer = list(_dist.agree_array(np.asarray(self.generator.take_many())))
         return self.buffer.pop(0)
 
     def peek(self):
@@ -896,7 +898,13 @@ def perform_single_step_(cache: ADICache, mu: float):
         # one C-ABI call: numeric LDL^T of A_s + mu E, block sweeps for [R, K'], SMW, SpMM update
         _set_operator(prob.A, transpose=True)
         V = DeviceMatrix.empty(R.ncols)
-        be.check(be.lib.dre_adi_step(be.h, mu, 0.0, R.view, V.view, View(-1, 0, 0)))
+        if _dist.active():
+            # column blocks of R on different GPUs, replicated factorization; all-gather of V, then the
+            # residual update on the full panel (cheaper than gathering the updated R blocks as well)
+            _dist.sharded_adi_solve(be, complex(mu), R, V, None, View(-1, 0, 0))
+            spmm("E", V, -2.0 * mu, R, 1.0)
+        else:
+            be.check(be.lib.dre_adi_step(be.h, mu, 0.0, R.view, V.view, View(-1, 0, 0)))
         _prefetch_next_factorization(cache)
     else:
         F = (prob.A.adjoint().plus_sparse(PencilCombo(0.0, mu)) if isinstance(prob.A, LowRankUpdate)
@@ -922,7 +930,11 @@ def perform_double_step_(cache: ADICache, mu: complex):
         _set_operator(prob.A, transpose=True)
         V1 = DeviceMatrix.empty(R.ncols)
         V2 = DeviceMatrix.empty(R.ncols)
-        be.check(be.lib.dre_adi_step(be.h, mu.real, mu.imag, R.view, V1.view, V2.view))
+        if _dist.active():
+            _dist.sharded_adi_solve(be, complex(mu), R, V1, V2, View(-1, 0, 0))
+            spmm("E", V1, -2.0 * math.sqrt(2.0) * mu.real, R, 1.0)
+        else:
+            be.check(be.lib.dre_adi_step(be.h, mu.real, mu.imag, R.view, V1.view, V2.view))
         _prefetch_next_factorization(cache)
     else:
         F = (prob.A.adjoint().plus_sparse(PencilCombo(0.0, 0.0)) if isinstance(prob.A, LowRankUpdate)
@@ -952,7 +964,7 @@ def step_(cache: ADICache):
         perform_double_step_(cache, complex(mu))
     if alg.compression and cache.last_compression >= alg.compression_interval:
         compress_cache_(cache)
-    res_norm = cache.residual_norm = norm(cache.residual)
+    res_norm = cache.residual_norm = _dist.agree_scalar(norm(cache.residual))
     i = len(cache.shifts)
     _observe(observer, "observe_gale_step", i, cache.X, cache.residual, res_norm)
     if res_norm <= abstol:

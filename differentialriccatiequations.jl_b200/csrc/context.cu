@@ -598,9 +598,10 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                         // columns to ~1e-10 of a small selected direction; without this step the basis loses
                         // orthogonality and later panels "find" directions that are already in it.
                         CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
-                        rc = gram_dev(c, Qt, PB, PB, s.Q, s.ldq, s.rho, n, nullptr, c->cbuf.p, s.rho, nullptr, 0);
+                        // (only the first nsel candidate columns are nonzero: narrow kernels when nsel <= 16)
+                        rc = gram_dev(c, Qt, PB, nsel, s.Q, s.ldq, s.rho, n, nullptr, c->cbuf.p, s.rho, nullptr, 0);
                         if (rc) return rc;
-                        rc = tall_gemm(c, -1.0, s.Q, s.ldq, s.rho, c->cbuf.p, s.rho, 1, 1.0, Qt, PB, PB, n);
+                        rc = tall_gemm(c, -1.0, s.Q, s.ldq, s.rho, c->cbuf.p, s.rho, 1, 1.0, Qt, PB, nsel, n);
                         if (rc) return rc;
                     }
                     rc = gram_dev(c, Qt, PB, PB, Qt, PB, PB, n, nullptr, c->gbuf2.p, PB, nullptr, 0);
@@ -1131,6 +1132,20 @@ int32_t dre_prefactor(dre_context* c, double mu_re, double mu_im) {
 int32_t dre_shift_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     return shifted_solve(c, mu_re, mu_im, R, V1, V2, false);
+}
+
+int32_t dre_adi_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    return shifted_solve(c, mu_re, mu_im, R, V1, V2, true);
+}
+
+int32_t dre_mat_devptr(dre_context* c, dre_view v, void** ptr, int64_t* ld) {
+    if (!c || !ptr || !ld) return fail(c, DRE_ERR_ARG, "null argument");
+    int rc;
+    if ((rc = check_view(c, v, "view"))) return rc;
+    *ptr = vptr(c, v);
+    *ld = vld(c, v);
+    return DRE_OK;
 }
 
 int32_t dre_adi_step(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2) {

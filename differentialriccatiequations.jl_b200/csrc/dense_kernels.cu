@@ -256,16 +256,24 @@ __global__ void __launch_bounds__(256) k_gram2(const double* __restrict__ X, int
 // CTA = 256 threads, output tile 128 rows x 64 cols, K chunks of 16 in a 3-stage cp.async pipeline;
 // warp tile 32 x 32.
 // ------------------------------------------------------------------------------------------
-constexpr int T2M = 128, T2N = 64, T2K = 16, T2ST = 3;
+constexpr int T2M = 128, T2K = 16, T2ST = 3;
 constexpr int T2LDX = T2K + 4;   // = 4 mod 16
-constexpr int T2LDW = T2N + 8;   // = 8 mod 16
-constexpr int T2_STAGE = T2M * T2LDX + T2K * T2LDW;
+template <int T2N> struct T2Cfg {
+    static constexpr int LDW = ((T2N + 15) & ~15) + 8;   // = 8 mod 16
+    static constexpr int STAGE = T2M * T2LDX + T2K * LDW;
+    static constexpr int WC = T2N >= 64 ? 2 : 1, WR = 8 / WC;   // warps along columns / rows
+    static constexpr int MT = T2M / (WR * 8), NT = T2N / (WC * 8);
+};
 
+// T2N = 64: warp tile 32 x 32;  T2N = 16 (a handful of candidate directions): warp tile 16 x 16
+template <int T2N>
 __global__ void __launch_bounds__(256) k_tall_gemm2(double alpha, const double* __restrict__ X, int64_t ldx, int a,
                                                     const double* __restrict__ W, int64_t ldw, int w_trans,
                                                     double beta, double* __restrict__ Y, int64_t ldy, int b,
                                                     int64_t n, int aligned_x, int aligned_w) {
     extern __shared__ __align__(16) double t2_smem[];
+    constexpr int T2LDW = T2Cfg<T2N>::LDW, T2_STAGE = T2Cfg<T2N>::STAGE;
+    constexpr int MT = T2Cfg<T2N>::MT, NT = T2Cfg<T2N>::NT, WR = T2Cfg<T2N>::WR;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t row0 = (int64_t)blockIdx.x * T2M;
     const int b0 = blockIdx.y * T2N;
@@ -309,12 +317,12 @@ __global__ void __launch_bounds__(256) k_tall_gemm2(double alpha, const double* 
         }
     };
 
-    double acc[4][4][2];
+    double acc[MT][NT][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wr = (warp % WR) * (MT * 8), wc = (warp / WR) * (NT * 8);
     const int kk = lane & 3, rr = lane >> 2;
 
 #pragma unroll
@@ -331,24 +339,24 @@ __global__ void __launch_bounds__(256) k_tall_gemm2(double alpha, const double* 
         const double* Ws = Xs + T2M * T2LDX;
 #pragma unroll
         for (int k0 = 0; k0 < T2K; k0 += 4) {
-            double af[4], bf[4];
+            double af[MT], bf[NT];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) af[mt] = Xs[(wr + mt * 8 + rr) * T2LDX + k0 + kk];
+            for (int mt = 0; mt < MT; ++mt) af[mt] = Xs[(wr + mt * 8 + rr) * T2LDX + k0 + kk];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bf[nt] = Ws[(k0 + kk) * T2LDW + wc + nt * 8 + rr];
+            for (int nt = 0; nt < NT; ++nt) bf[nt] = Ws[(k0 + kk) * T2LDW + wc + nt * 8 + rr];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
     }
     cp_async_wait<0>();
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
         const int64_t row = row0 + wr + mt * 8 + rr;
         if (row >= n) continue;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             const int j = b0 + wc + nt * 8 + 2 * kk;
             double* y = Y + row * ldy + j;
             if (j < b) y[0] = (beta == 0.0 ? 0.0 : beta * y[0]) + alpha * acc[mt][nt][0];
@@ -453,100 +461,27 @@ void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t l
     if (launches) *launches += 2;
 }
 
-// ------------------------------------------------------------------------------------------
-// Tall GEMM:  Y[n x b] = beta*Y + alpha * X[n x a] * W        (DMMA)
-// CTA = 256 threads, output tile 64 rows x 64 cols, k-chunks of 32.
-// ------------------------------------------------------------------------------------------
-constexpr int TK = 32;
-constexpr int TXLD = 36;  // 36*i mod 16 = 4i -> minimal 2-wavefront fragment loads
-constexpr int TWLD = 72;
-
-__global__ void __launch_bounds__(256) k_tall_gemm(double alpha, const double* __restrict__ X, int64_t ldx, int a,
-                                                   const double* __restrict__ W, int64_t ldw, int w_trans,
-                                                   double beta, double* __restrict__ Y, int64_t ldy, int b,
-                                                   int64_t n) {
-    __shared__ double Xs[64][TXLD];
-    __shared__ double Ws[TK][TWLD];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t row0 = (int64_t)blockIdx.x * 64;
-    const int b0 = blockIdx.y * 64;
-    double acc[8][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
-
-    for (int k0 = 0; k0 < a; k0 += TK) {
-        // X tile: 64 rows x 32 k
-        {
-            const int kc = tid & 31, r = tid >> 5;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rr = r + 8 * it;
-                const int64_t row = row0 + rr;
-                double v = 0.0;
-                if (row < n && k0 + kc < a) v = X[row * ldx + k0 + kc];
-                Xs[rr][kc] = v;
-            }
-        }
-        // W tile: 32 k x 64 j
-        {
-            if (!w_trans) {
-                const int j = tid & 63, k = tid >> 6;
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int kk = k + 4 * it;
-                    double v = 0.0;
-                    if (k0 + kk < a && b0 + j < b) v = W[(int64_t)(k0 + kk) * ldw + b0 + j];
-                    Ws[kk][j] = v;
-                }
-            } else {
-                const int kk = tid & 31, j = tid >> 5;
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int jj = j + 8 * it;
-                    double v = 0.0;
-                    if (k0 + kk < a && b0 + jj < b) v = W[(int64_t)(b0 + jj) * ldw + k0 + kk];
-                    Ws[kk][jj] = v;
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < TK; kk += 4) {
-            const double af = Xs[8 * warp + (lane >> 2)][kk + (lane & 3)];
-#pragma unroll
-            for (int nb = 0; nb < 8; ++nb) {
-                const double bf = Ws[kk + (lane & 3)][8 * nb + (lane >> 2)];
-                dmma884(acc[nb][0], acc[nb][1], af, bf);
-            }
-        }
-        __syncthreads();
+template <int T2N>
+static void launch_tall_gemm_t(double alpha, const double* X, int64_t ldx, int a, const double* W, int64_t ldw,
+                               int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n, cudaStream_t st) {
+    static bool attr_set = false;
+    const int smem = T2ST * T2Cfg<T2N>::STAGE * (int)sizeof(double);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_tall_gemm2<T2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
     }
-    const int64_t row = row0 + 8 * warp + (lane >> 2);
-    if (row < n) {
-#pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
-            const int j = b0 + 8 * nb + 2 * (lane & 3);
-            double* y = Y + row * ldy + j;
-            if (j < b) y[0] = (beta == 0.0 ? 0.0 : beta * y[0]) + alpha * acc[nb][0];
-            if (j + 1 < b) y[1] = (beta == 0.0 ? 0.0 : beta * y[1]) + alpha * acc[nb][1];
-        }
-    }
+    dim3 grid((unsigned)((n + T2M - 1) / T2M), (unsigned)((b + T2N - 1) / T2N));
+    const int ax = reinterpret_cast<uintptr_t>(X) % 16 == 0 && ldx % 2 == 0;
+    const int aw = reinterpret_cast<uintptr_t>(W) % 16 == 0 && ldw % 2 == 0;
+    k_tall_gemm2<T2N><<<grid, 256, smem, st>>>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, ax, aw);
 }
 
 void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const double* W, int64_t ldw,
                       int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n, cudaStream_t st,
                       int64_t* launches) {
     if (b <= 0 || n <= 0) return;
-    static bool attr_set = false;
-    const int smem = T2ST * T2_STAGE * (int)sizeof(double);
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_tall_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
-    dim3 grid((unsigned)((n + T2M - 1) / T2M), (unsigned)((b + T2N - 1) / T2N));
-    const int ax = reinterpret_cast<uintptr_t>(X) % 16 == 0 && ldx % 2 == 0;
-    const int aw = reinterpret_cast<uintptr_t>(W) % 16 == 0 && ldw % 2 == 0;
-    k_tall_gemm2<<<grid, 256, smem, st>>>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, ax, aw);
+    if (b <= 16) launch_tall_gemm_t<16>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, st);
+    else launch_tall_gemm_t<64>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, st);
     if (launches) *launches += 1;
 }
 

@@ -93,6 +93,11 @@ DRE_API int32_t dre_mat_free(dre_context* ctx, int32_t id);
 DRE_API int32_t dre_mat_upload(dre_context* ctx, dre_view dst, const double* host, int64_t ld);
 DRE_API int32_t dre_mat_download(dre_context* ctx, dre_view src, double* host, int64_t ld);
 DRE_API int32_t dre_mat_copy(dre_context* ctx, dre_view dst, dre_view src);
+/* Raw device address of a view for the host-side collective plumbing (NCCL through torch.distributed, or
+ * CUDA.jl-free MPI/NCCL bindings on the Julia side): element (row, col) of the view is ptr[row * ld + col]
+ * with rows in the solver's internal ordering (identical on every rank for the same pencil).  The caller must
+ * dre_sync() before touching the memory from another stream and must not keep the pointer past dre_mat_free. */
+DRE_API int32_t dre_mat_devptr(dre_context* ctx, dre_view v, void** ptr, int64_t* ld);
 /* Y = alpha*X + beta*Y (X may be an empty view when alpha == 0) */
 DRE_API int32_t dre_mat_axpby(dre_context* ctx, double alpha, dre_view X, double beta, dre_view Y);
 
@@ -127,6 +132,11 @@ DRE_API int32_t dre_prefactor(dre_context* ctx, double mu_re, double mu_im);
  *             V1 = sqrt2 (Re V + d Im V), V2 = sqrt(2 d^2+2) Im V;   R += -2 sqrt2 Re(mu) E' V1
  * R is updated in place; V1/V2 are freshly written panels. */
 DRE_API int32_t dre_adi_step(dre_context* ctx, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2);
+/* The solve half of dre_adi_step only (V1 / V2 as above, R untouched).  Used when the right-hand-side column
+ * blocks are sharded over several GPUs: every rank solves its own column block, the blocks are exchanged
+ * (NCCL all-gather driven by the host side) and the residual update R += c E' V1 runs on the full panel
+ * through dre_spmm. */
+DRE_API int32_t dre_adi_solve(dre_context* ctx, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2);
 
 /* ---- low-rank algebra (src/LDLt.jl) ---- */
 /* |alpha| * || L D L' ||_F  (norm(::LDLt), src/LDLt.jl:77-89).  D: k x k host column-major. */
