@@ -66,6 +66,14 @@ class Backend:
     def check(self, rc):
         self.ctx.check(rc)
 
+    def scratch(self, cols: int) -> "DeviceMatrix":
+        """View of a persistent scratch panel with at least `cols` columns (valid until the next call)."""
+        sp_ = getattr(self, "_scratch", None)
+        if sp_ is None or sp_.gen != self.generation or sp_.cols < cols:
+            self._scratch = None  # release the old one first
+            sp_ = self._scratch = _Panel(self, max(cols + cols // 2, 512))
+        return DeviceMatrix(sp_, 0, cols)
+
 
 def backend(device=None) -> Backend:
     global _backend
@@ -333,16 +341,14 @@ def compress_(X: LDLt) -> LDLt:
     ldds = (C.c_int64 * nt)(*[max(D.shape[0], 1) for _, _, D in terms])
     alphas = (C.c_double * nt)(*[float(a) for a, _, _ in terms])
     cap = min(ktot, be.n)
-    out = DeviceMatrix.empty(cap)
+    out = be.scratch(cap)  # persistent, geometrically grown: allocating ~2 GB per call costs tens of ms
     lam = np.zeros(cap)
     newrank = C.c_int32(0)
     be.check(be.lib.dre_ldlt_compress(be.h, nt, views, dptrs, ldds, alphas, 100.0, out.view, capi._dptr(lam),
                                       C.byref(newrank)))
     k2 = newrank.value
     _dist.assert_same_int(k2, "the rank after compress!")
-    Lnew = out.cols(0, k2)
-    if cap > 2 * max(k2, 1):  # do not keep a large mostly-unused panel alive
-        Lnew = Lnew.copy()
+    Lnew = out.cols(0, k2).copy()  # exact-size panel; the scratch panel is reused by the next compress!
     X.alphas[:] = [1.0]
     X.Ls[:] = [Lnew]
     X.Ds[:] = [np.asfortranarray(np.diag(lam[:k2]))]
@@ -647,9 +653,9 @@ class BufferedIterator:  # helpers.jl:70-75, 106-113
             self.buffer = list(_dist.agree_array(np.asarray(self.generator.take_many())))
         return self.buffer.pop(0)
 
-    def peek(self):
-        """Next shift if it is already buffered (never triggers take_many!), else None."""
-        return self.buffer[0] if self.buffer else None
+    def peek_many(self, k):
+        """Up to k next shifts that are already buffered (never triggers take_many!)."""
+        return list(self.buffer[:k])
 
 
 class WrappedIterator:  # helpers.jl:85-104
@@ -676,9 +682,9 @@ class _CycleIterator:  # Stateful(cycle(values)), helpers.jl:93
     def take(self):
         return next(self._it)
 
-    def peek(self):
+    def peek_many(self, k):
         self._it, probe = itertools.tee(self._it)
-        return next(probe)
+        return list(itertools.islice(probe, k))
 
 
 class _ListIterator:  # plain vector: take! = popfirst! (Shifts.jl:116)
@@ -691,8 +697,8 @@ class _ListIterator:  # plain vector: take! = popfirst! (Shifts.jl:116)
     def take(self):
         return self.values.pop(0)
 
-    def peek(self):
-        return self.values[0] if self.values else None
+    def peek_many(self, k):
+        return list(self.values[:k])
 
     def take_many(self):
         return self.values
@@ -875,18 +881,29 @@ def _fused_inner(alg: ADI) -> bool:
     return isinstance(alg.inner_alg, (Backslash, ShermanMorrisonWoodbury))
 
 
+PREFACTOR_DEPTH = 3  # factorizations queued ahead of the ADI step in flight (the library keeps 4 factor slots)
+
+
 def _prefetch_next_factorization(cache: ADICache):
-    """Performance hint only: when the next shift is already known (buffered), queue its numeric
-    factorization on the library's side stream so that it overlaps this step's remaining work."""
-    peek = getattr(cache.shifts_oracle, "peek", None)
-    if peek is None or not _fused_inner(cache.alg) or len(cache.shifts) >= cache.alg.maxiters:
+    """Performance hint only: the next shifts are usually known (buffered), so their numeric factorizations
+    are queued on the library's side streams and overlap this step's remaining work."""
+    peek = getattr(cache.shifts_oracle, "peek_many", None)
+    if peek is None or not _fused_inner(cache.alg):
         return
-    nxt = peek()
-    if nxt is None:
-        return
+    left = cache.alg.maxiters - len(cache.shifts)
     be = backend()
-    nxt = complex(nxt)
-    be.check(be.lib.dre_prefactor(be.h, nxt.real, nxt.imag))
+    queued, skip = 0, False
+    for nxt in peek(2 * PREFACTOR_DEPTH):
+        if left <= 0 or queued >= PREFACTOR_DEPTH:
+            break
+        left -= 1
+        if skip:  # conjugate partner of a complex shift: the double step needs one factorization only
+            skip = False
+            continue
+        nxt = complex(nxt)
+        skip = nxt.imag != 0
+        be.check(be.lib.dre_prefactor(be.h, nxt.real, nxt.imag))
+        queued += 1
 
 
 def perform_single_step_(cache: ADICache, mu: float):

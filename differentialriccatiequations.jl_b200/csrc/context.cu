@@ -31,7 +31,7 @@ struct DBuf {
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = n + n / 8 + 64;
+        size_t want = n + n / 2 + 64;   // geometric growth: cudaMalloc / cudaFree of large blocks cost tens of ms
         cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
         if (e != cudaSuccess) { p = nullptr; return e; }
         cap = want;
@@ -56,12 +56,12 @@ struct Panel {
 struct BlockCache {
     std::vector<std::pair<size_t, void*>> free_blocks;  // (bytes, ptr)
     size_t cached_bytes = 0;
-    // smallest cached block with  bytes <= size <= 1.5 * bytes + 1 MiB ; *got = its size
+    // smallest cached block with  bytes <= size <= 2 * bytes + 1 MiB ; *got = its size
     void* take(size_t bytes, size_t* got) {
         int best = -1;
         for (int i = 0; i < (int)free_blocks.size(); ++i) {
             const size_t b = free_blocks[i].first;
-            if (b >= bytes && b <= bytes + bytes / 2 + (1u << 20) && (best < 0 || b < free_blocks[best].first)) best = i;
+            if (b >= bytes && b <= 2 * bytes + (1u << 20) && (best < 0 || b < free_blocks[best].first)) best = i;
         }
         if (best < 0) return nullptr;
         void* p = free_blocks[best].second;
@@ -119,10 +119,10 @@ struct dre_context {
     int64_t linv_elems = 0, upd_elems = 0;
 
     // factor storage (sized for complex, reused for real)
-    // Two factor slots: while the sweeps of ADI step i read slot `cur` on the main stream, the numeric
-    // factorization of the NEXT shift (dre_prefactor) runs on the side stream into the other slot -- the
-    // factorization is a latency-bound chain of small launches that leaves most SMs idle, the sweeps /
-    // Gram / compression kernels of the main stream fill them.
+    // Factor slots: while the sweeps of ADI step i read slot `cur` on the main stream, the numeric
+    // factorizations of the NEXT shifts (dre_prefactor) run on side streams into the other slots -- one
+    // factorization is a latency-bound chain of small launches that leaves most SMs idle; several of them and
+    // the sweeps / Gram / compression kernels of the main stream fill the machine together.
     struct FactorSlot {
         void* L = nullptr;
         void* Linv = nullptr;
@@ -134,10 +134,12 @@ struct dre_context {
         cudaEvent_t ready = nullptr; // recorded behind the factorization
         cudaEvent_t released = nullptr;  // recorded on the main stream behind the last sweeps that read the slot
         bool has_reader = false;
+        bool pending = false;        // queued by dre_prefactor and not yet adopted by a solve
+        cudaStream_t st = nullptr;   // side stream of this slot (factorizations of different slots overlap)
     };
-    FactorSlot slot[2];
+    static constexpr int NSLOT = 4;  // the slot in use + up to three prefactorizations in flight
+    FactorSlot slot[NSLOT];
     int cur = 0;
-    cudaStream_t st2 = nullptr;      // side stream of dre_prefactor
     DBuf<unsigned char> tbuf;
     DBuf<unsigned char> Wbuf;
     DBuf<double> btw, sol;
@@ -248,7 +250,7 @@ struct HostTrace {
         if (g_trace) {
             if (sync_stream) cudaStreamSynchronize(sync_stream);
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            if (ms > 0.5) fprintf(stderr, "[dre trace] %-24s %9.3f ms\n", name, ms);
+            if (ms > 0.1) fprintf(stderr, "[dre trace] %-24s %9.3f ms\n", name, ms);
         }
     }
 };
@@ -348,6 +350,7 @@ int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
     T* tb = (T*)c->tbuf.p;
     for (int l = 0; l < S.nlevels; ++l) {
         const dre_context::LevelWork& lw = c->levels[l];
+        HostTrace tr("  one fwd level launch");
         launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, lw.smax, L, Linv, W, ldw, nrhs, tb,
                             c->st, &c->stats.kernel_launches);
     }
@@ -372,25 +375,35 @@ inline bool slot_matches(const dre_context* c, const dre_context::FactorSlot& fs
     return fs.valid && fs.a == c->op_a && fs.re == c->op_e + mu_re && fs.im == mu_im && fs.tw == tw;
 }
 
+// slot to (re)fill: an empty one, else a consumed one, else (only when `allow_pending`) a queued one
+inline int pick_slot(dre_context* c, bool allow_pending) {
+    for (int i = 0; i < dre_context::NSLOT; ++i)
+        if (i != c->cur && !c->slot[i].valid) return i;
+    for (int i = 0; i < dre_context::NSLOT; ++i)
+        if (i != c->cur && !c->slot[i].pending) return i;
+    if (!allow_pending) return -1;
+    return (c->cur + 1) % dre_context::NSLOT;
+}
+
 // Make c->cur a slot holding the factorization for (op, mu) as seen from stream `st` (the main stream):
-// a slot filled by dre_prefactor is adopted behind its `ready` event; otherwise the slot not used by the
-// last sweeps is (re)factored on `st`.
+// a slot filled by dre_prefactor is adopted behind its `ready` event; otherwise a free slot is factored on `st`.
 template <class T>
 int acquire_factor(dre_context* c, double mu_re, double mu_im, T emu, cudaStream_t st) {
     const int tw = (int)(sizeof(T) / sizeof(double));
-    for (int k = 0; k < 2; ++k) {
-        const int i = (c->cur + k) & 1;
-        if (slot_matches(c, c->slot[i], mu_re, mu_im, tw)) {
-            CU(cudaStreamWaitEvent(st, c->slot[i].ready, 0));
-            if (i != c->cur) c->stats.prefactor_hits++;
+    for (int i = 0; i < dre_context::NSLOT; ++i) {
+        dre_context::FactorSlot& fs = c->slot[i];
+        if (slot_matches(c, fs, mu_re, mu_im, tw)) {
+            CU(cudaStreamWaitEvent(st, fs.ready, 0));
+            if (fs.pending) c->stats.prefactor_hits++;
+            fs.pending = false;
             c->cur = i;
             return DRE_OK;
         }
     }
-    const int i = c->cur ^ 1;
+    const int i = pick_slot(c, true);
     dre_context::FactorSlot& fs = c->slot[i];
     if (fs.valid) CU(cudaStreamWaitEvent(st, fs.ready, 0));   // an unused prefactorization may still be in flight
-    fs.valid = false;
+    fs.valid = fs.pending = false;
     HostTrace tr(sizeof(T) == 8 ? "factor<double> launch" : "factor<cplx> launch");
     int rc = factor<T>(c, fs, st, emu);
     if (rc) return rc;
@@ -405,17 +418,19 @@ int acquire_factor(dre_context* c, double mu_re, double mu_im, T emu, cudaStream
 template <class T>
 int prefactor_t(dre_context* c, double mu_re, double mu_im, T emu) {
     const int tw = (int)(sizeof(T) / sizeof(double));
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < dre_context::NSLOT; ++k)
         if (slot_matches(c, c->slot[k], mu_re, mu_im, tw)) return DRE_OK;   // already held / in flight
-    const int i = c->cur ^ 1;
+    const int i = pick_slot(c, false);
+    if (i < 0) return DRE_OK;                                               // every spare slot is queued
     dre_context::FactorSlot& fs = c->slot[i];
-    if (fs.valid) CU(cudaStreamWaitEvent(c->st2, fs.ready, 0));
-    if (fs.has_reader) CU(cudaStreamWaitEvent(c->st2, fs.released, 0));   // sweeps that still read the slot
+    if (fs.valid) CU(cudaStreamWaitEvent(fs.st, fs.ready, 0));
+    if (fs.has_reader) CU(cudaStreamWaitEvent(fs.st, fs.released, 0));     // sweeps that still read the slot
     fs.valid = false;
-    int rc = factor<T>(c, fs, c->st2, emu);
+    int rc = factor<T>(c, fs, fs.st, emu);
     if (rc) return rc;
-    CU(cudaEventRecord(fs.ready, c->st2));
+    CU(cudaEventRecord(fs.ready, fs.st));
     fs.valid = true;
+    fs.pending = true;
     fs.a = c->op_a; fs.re = c->op_e + mu_re; fs.im = mu_im; fs.tw = tw;
     fs.has_reader = false;
     c->stats.prefactors++;
@@ -498,6 +513,7 @@ struct RRState {
     double scale2 = 0.0;   // largest squared column norm seen so far
     double drop_rel = 3e-15, drop_abs = 0.0;
     int rounds = 0;
+    int skipped = 0;   // sub-panels skipped because their remainder was below the drop threshold
 };
 
 int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds, int cols, const double* d_colscale,
@@ -524,6 +540,7 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
         const int pbig = std::min(PBIG, cols - c0);
         launch_copy_scale(Pbig, PBIG, src + c0, lds, n, pbig, d_colscale ? d_colscale + c0 : nullptr, c->st,
                           &c->stats.kernel_launches);
+        double block_max2 = 0.0;
         {   // the drop threshold is relative to the largest ORIGINAL column norm met so far
             constexpr int NBLK = 296;
             CU(c->gram_partial.ensure((size_t)NBLK * PBIG));
@@ -532,12 +549,20 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
             if ((rc = ensure_pinned(c, PBIG + 16))) return rc;
             CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
             CU(cudaStreamSynchronize(c->st));
-            for (int j = 0; j < pbig; ++j) s.scale2 = std::max(s.scale2, c->h_pinned[16 + j]);
+            for (int j = 0; j < pbig; ++j) {
+                s.scale2 = std::max(s.scale2, c->h_pinned[16 + j]);
+                block_max2 = std::max(block_max2, c->h_pinned[16 + j]);
+            }
         }
         const int rho0 = s.rho;
+        // One projection pass leaves a basis component of ~30 eps |p| in a column p.  Columns below 5 % of the
+        // global scale therefore stay an order of magnitude under the drop threshold (3e-15 * scale) after a
+        // single pass, and the second ("twice is enough") pass is only spent on blocks with large columns.  The
+        // orthogonality of the basis does not depend on it: candidates are re-orthogonalised below.
+        const int npass = (block_max2 <= 0.0025 * s.scale2) ? 1 : 2;
         if (rho0 > 0) {
             CU(c->cbuf.ensure((size_t)PBIG * rho0));
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = 0; pass < npass; ++pass) {
                 // C' = P' Q (pbig x rho0): coefficients, accumulated into the RT rows of this block
                 rc = gram_dev(c, Pbig, PBIG, pbig, s.Q, s.ldq, rho0, n, nullptr, c->cbuf.p, rho0,
                               s.RT + (int64_t)(rt_row0 + c0) * s.ldrt, s.ldrt);
@@ -546,8 +571,28 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                 if (rc) return rc;
             }
         }
+        // remainder norms after the block passes: a sub-panel whose columns are all below the drop threshold
+        // cannot contribute a direction (pivoted Cholesky would select nothing) and is skipped without its
+        // Gram / selection / synchronisation
+        std::vector<double> rem2(pbig, 0.0);
+        bool have_rem = false;
+        if (rho0 > 0) {
+            constexpr int NBLK = 296;
+            launch_colnorm2(Pbig, PBIG, n, pbig, c->gram_partial.p, NBLK, c->cnorm.p, c->st, &c->stats.kernel_launches);
+            CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            for (int j = 0; j < pbig; ++j) rem2[j] = c->h_pinned[16 + j];
+            have_rem = true;
+        }
         for (int sc = 0; sc < pbig; sc += PB) {
             const int pb = std::min(PB, pbig - sc);
+            if (have_rem && !g_trace) {
+                double m2 = 0.0;
+                for (int j = sc; j < sc + pb; ++j) m2 = std::max(m2, rem2[j]);
+                const double drop0 = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
+                // (projections against directions added inside this block can only shrink the columns further)
+                if (m2 < drop0 * drop0) { s.skipped++; continue; }
+            }
             double* Pw = Pbig + sc;
             double* RTrow = s.RT + (int64_t)(rt_row0 + c0 + sc) * s.ldrt;
             double trace_d0 = 0.0;
@@ -750,9 +795,9 @@ int32_t dre_create(int32_t device, dre_context** out) {
     c->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
-    e = cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking);
-    if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     for (auto& fs : c->slot) {
+        e = cudaStreamCreateWithFlags(&fs.st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
         cudaEventCreateWithFlags(&fs.ready, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&fs.released, cudaEventDisableTiming);
     }
@@ -775,7 +820,7 @@ int32_t dre_create(int32_t device, dre_context** out) {
 }
 
 static void release_pencil(dre_context* c) {
-    if (c->st2) cudaStreamSynchronize(c->st2);
+    for (auto& fs : c->slot) if (fs.st) cudaStreamSynchronize(fs.st);
     for (void* p : c->owned) cudaFree(p);
     c->owned.clear();
     for (auto& fs : c->slot) {
@@ -784,7 +829,7 @@ static void release_pencil(dre_context* c) {
         if (fs.dvec) cudaFree(fs.dvec);
         if (fs.U) cudaFree(fs.U);
         fs.L = fs.Linv = fs.dvec = fs.U = nullptr;
-        fs.valid = fs.has_reader = false;
+        fs.valid = fs.has_reader = fs.pending = false;
     }
     c->cur = 0;
     c->has_pencil = false;
@@ -812,8 +857,8 @@ int32_t dre_destroy(dre_context* c) {
     for (auto& fs : c->slot) {
         if (fs.ready) cudaEventDestroy(fs.ready);
         if (fs.released) cudaEventDestroy(fs.released);
+        if (fs.st) cudaStreamDestroy(fs.st);
     }
-    if (c->st2) cudaStreamDestroy(c->st2);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
     return DRE_OK;
@@ -822,7 +867,7 @@ int32_t dre_destroy(dre_context* c) {
 int32_t dre_sync(dre_context* c) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     CU(cudaStreamSynchronize(c->st));
-    CU(cudaStreamSynchronize(c->st2));
+    for (auto& fs : c->slot) CU(cudaStreamSynchronize(fs.st));
     return DRE_OK;
 }
 
@@ -942,8 +987,8 @@ int32_t dre_mat_create(dre_context* c, int32_t cols, int32_t* id) {
     p.cols = cols;
     p.ld = std::max(1, (cols + 1) & ~1);  // even leading dimension: 16-byte aligned rows
     {
-        // size classes of 8 columns keep slightly different residual widths (242, 244, ...) interchangeable
-        const size_t want = (size_t)c->sym.n * (size_t)((p.ld + 7) & ~7) * sizeof(double);
+        // size classes of 32 columns keep slightly different residual widths (242, 249, ...) interchangeable
+        const size_t want = (size_t)c->sym.n * (size_t)((p.ld + 31) & ~31) * sizeof(double);
         size_t got = 0;
         void* blk = c->cache.take(want, &got);
         if (!blk) {

@@ -153,14 +153,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // warp tile 32 x 32 (4 x 4 DMMA tiles: 8 fragment loads feed 16 DMMAs).
 // ------------------------------------------------------------------------------------------
 constexpr int G2A = 64, G2B = 128, G2K = 16, G2ST = 3;
-constexpr int G2LDA = G2A + 8, G2LDB = G2B + 8;   // = 8 mod 16: two-wavefront fragment loads
-constexpr int G2_STAGE = G2K * (G2LDA + G2LDB);   // doubles per stage
+constexpr int G2LDA = G2A + 8;   // = 8 mod 16: two-wavefront fragment loads
 
+// TB = 128: 64 x 128 output tile (warp tile 32 x 32);  TB = 64: 64 x 64 tile for the many 64-column panels
+template <int TB>
 __global__ void __launch_bounds__(256) k_gram2(const double* __restrict__ X, int64_t ldx, int a,
                                                const double* __restrict__ Y, int64_t ldy, int b, int64_t n,
                                                double* __restrict__ partial, int tiles_b, int64_t rows_per_split,
                                                int aligned) {
     extern __shared__ __align__(16) double g2_smem[];
+    constexpr int G2B = TB, G2LDB = TB + 8, G2_STAGE = G2K * (G2LDA + G2LDB), NT = TB / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ta = blockIdx.x / tiles_b, tb = blockIdx.x % tiles_b;
     const int a0 = ta * G2A, b0 = tb * G2B;
@@ -203,12 +205,12 @@ __global__ void __launch_bounds__(256) k_gram2(const double* __restrict__ X, int
         }
     };
 
-    double acc[4][4][2];
+    double acc[4][NT][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int wa = (warp & 1) * 32, wb = (warp >> 1) * 32;
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wa = (warp & 1) * 32, wb = (warp >> 1) * (NT * 8);
     const int kk = lane & 3, rr = lane >> 2;
 
 #pragma unroll
@@ -225,15 +227,15 @@ __global__ void __launch_bounds__(256) k_gram2(const double* __restrict__ X, int
         const double* Ys = Xs + G2K * G2LDA;
 #pragma unroll
         for (int k0 = 0; k0 < G2K; k0 += 4) {
-            double af[4], bf[4];
+            double af[4], bf[NT];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) af[mt] = Xs[(k0 + kk) * G2LDA + wa + mt * 8 + rr];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bf[nt] = Ys[(k0 + kk) * G2LDB + wb + nt * 8 + rr];
+            for (int nt = 0; nt < NT; ++nt) bf[nt] = Ys[(k0 + kk) * G2LDB + wb + nt * 8 + rr];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
     }
     cp_async_wait<0>();
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(256) k_gram2(const double* __restrict__ X, int
         const int i = a0 + wa + mt * 8 + rr;
         if (i >= a) continue;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             const int j = b0 + wb + nt * 8 + 2 * kk;
             if (j < b) P[(int64_t)i * b + j] = acc[mt][nt][0];
             if (j + 1 < b) P[(int64_t)i * b + j + 1] = acc[mt][nt][1];
@@ -367,7 +369,8 @@ __global__ void __launch_bounds__(256) k_tall_gemm2(double alpha, const double* 
 
 GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
     GramPlan p;
-    int tiles = ((a + G2A - 1) / G2A) * ((b + G2B - 1) / G2B);   // pipelined kernel: 64 x 128 output tiles
+    const int tbw = b <= 64 ? 64 : G2B;
+    int tiles = ((a + G2A - 1) / G2A) * ((b + tbw - 1) / tbw);   // pipelined kernel: 64 x 128 (64 x 64) output tiles
     if (tiles < 1) tiles = 1;
     int64_t chunks = (n + GK - 1) / GK;
     int want = std::max(1, (2 * sm_count + tiles - 1) / tiles);   // ~2 CTAs per SM
@@ -446,16 +449,23 @@ void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t l
         k_gram<<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, roww, partial, tiles_b, plan.rows_per_split);
     } else {
         static bool attr_set = false;
-        const int smem = G2ST * G2_STAGE * (int)sizeof(double);
+        const int smem128 = G2ST * G2K * (G2LDA + 128 + 8) * (int)sizeof(double);
+        const int smem64 = G2ST * G2K * (G2LDA + 64 + 8) * (int)sizeof(double);
         if (!attr_set) {
-            cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(k_gram2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128);
+            cudaFuncSetAttribute(k_gram2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
             attr_set = true;
         }
-        const int tiles_a = (a + G2A - 1) / G2A, tiles_b = (b + G2B - 1) / G2B;
+        const int tbw = b <= 64 ? 64 : G2B;
+        const int tiles_a = (a + G2A - 1) / G2A, tiles_b = (b + tbw - 1) / tbw;
         dim3 grid(tiles_a * tiles_b, plan.nsplit);
         const int aligned = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0) &&
                             ldx % 2 == 0 && ldy % 2 == 0;
-        k_gram2<<<grid, 256, smem, st>>>(X, ldx, a, Y, ldy, b, n, partial, tiles_b, plan.rows_per_split, aligned);
+        if (tbw == 64)
+            k_gram2<64><<<grid, 256, smem64, st>>>(X, ldx, a, Y, ldy, b, n, partial, tiles_b, plan.rows_per_split, aligned);
+        else
+            k_gram2<128><<<grid, 256, smem128, st>>>(X, ldx, a, Y, ldy, b, n, partial, tiles_b, plan.rows_per_split,
+                                                      aligned);
     }
     k_reduce_partials<<<rb, 256, 0, st>>>(partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
     if (launches) *launches += 2;

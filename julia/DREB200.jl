@@ -148,6 +148,29 @@ function adi_step!(ctx::Context, F::DeviceOperator, μ::Complex, R::DeviceMatrix
     V1, V2
 end
 
+# Performance hint (results unchanged): the next shifts of the buffered iterator (src/shifts/helpers.jl:106-113)
+# are factored ahead on the library's side streams while the current step's sweeps / Gram / compression run.
+prefactor!(ctx::Context, μ::Complex) =
+    check(ctx, ccall((:dre_prefactor, LIB), Int32, (Ptr{Cvoid}, Float64, Float64), ctx.h, real(μ), imag(μ)))
+
+# Multi-GPU (one Julia process per GPU, e.g. MPI.jl ranks): every rank solves its own block of R's columns with
+# the replicated factorization, then the solved blocks are exchanged.  `dre_mat_devptr` hands the raw device
+# address of a view (row-major, leading dimension ld) to the collective library (NCCL.jl / CUDA-aware MPI);
+# the residual update runs afterwards on the full panel through `spmm!`.
+function adi_solve_block!(ctx::Context, μ::Complex, R::DeviceMatrix, V1::DeviceMatrix, V2, cols::UnitRange{Int})
+    sub(M) = View(M.p.id, M.col0 + first(cols) - 1, length(cols))
+    z = View(-1, 0, 0)
+    check(ctx, ccall((:dre_adi_solve, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, View, View, View),
+                     ctx.h, real(μ), imag(μ), sub(R), sub(V1), V2 === nothing ? z : sub(V2)))
+end
+function devptr(M::DeviceMatrix)
+    p = Ref{Ptr{Cvoid}}(C_NULL); ld = Ref{Int64}(0)
+    check(M.p.ctx, ccall((:dre_mat_devptr, LIB), Int32, (Ptr{Cvoid}, View, Ref{Ptr{Cvoid}}, Ref{Int64}),
+                         M.p.ctx.h, view_of(M), p, ld))
+    check(M.p.ctx, ccall((:dre_sync, LIB), Int32, (Ptr{Cvoid},), M.p.ctx.h))
+    p[], ld[]
+end
+
 # E'L, A'L  (src/lyapunov/residual.jl:18, src/riccati/lowrank_ros1.jl:42)
 function spmm!(Y::DeviceMatrix, op::Char, X::DeviceMatrix, α::Real, β::Real)
     check(X.p.ctx, ccall((:dre_spmm, LIB), Int32, (Ptr{Cvoid}, Int32, Float64, View, Float64, View),
