@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -48,36 +49,66 @@ struct Panel {
     size_t cap = 0;   // bytes of the underlying block (>= n * ld * 8)
 };
 
-// Caching allocator for the panels.  Everything runs on ONE stream, so a block released by dre_mat_free can
-// be handed out again immediately (its next use is stream-ordered behind the last one); blocks only go back
-// to the driver when an allocation fails or the context dies.  The stream-ordered pool of the driver
-// (cudaMallocAsync) was measured at 25 ms per 150 MB panel in the ADI loop (tools/host_profile.py):
-// growing / re-mapping the pool stalls the launch thread while the GPU drains.
-struct BlockCache {
-    std::vector<std::pair<size_t, void*>> free_blocks;  // (bytes, ptr)
-    size_t cached_bytes = 0;
-    // smallest cached block with  bytes <= size <= 2 * bytes + 1 MiB ; *got = its size
-    void* take(size_t bytes, size_t* got) {
-        int best = -1;
-        for (int i = 0; i < (int)free_blocks.size(); ++i) {
-            const size_t b = free_blocks[i].first;
-            if (b >= bytes && b <= 2 * bytes + (1u << 20) && (best < 0 || b < free_blocks[best].first)) best = i;
+// Arena allocator for the panels.  Everything that touches panels runs on ONE stream, so a block released by
+// dre_mat_free can be handed out again immediately (its next use is stream-ordered behind the last one).
+// cudaMalloc / cudaFree of the 0.1 - 2 GB panels of this workload were measured at 0.3 - 75 ms per call
+// (tools/host_profile.py, DRE_TRACE=1) and the driver's stream-ordered pool at 25 ms, which made the ADI loop
+// host-bound; the arena grabs a few large chunks (2, 4, 8, ... GB) once and sub-allocates first-fit with
+// coalescing.  Chunks go back to the driver when the context dies or a new pencil is set.
+struct Arena {
+    struct Chunk {
+        char* base = nullptr;
+        size_t size = 0;
+        std::map<size_t, size_t> free;   // offset -> length of the free ranges
+    };
+    std::vector<Chunk> chunks;
+    size_t next_chunk = (size_t)2 << 30;
+    static size_t align_up(size_t b) { return (b + 511) & ~(size_t)511; }
+    void* alloc(size_t bytes, size_t* got) {
+        bytes = align_up(std::max<size_t>(bytes, 512));
+        for (int pass = 0; pass < 2; ++pass) {
+            for (Chunk& ch : chunks)
+                for (auto it = ch.free.begin(); it != ch.free.end(); ++it)
+                    if (it->second >= bytes) {
+                        const size_t off = it->first, len = it->second;
+                        ch.free.erase(it);
+                        if (len > bytes) ch.free[off + bytes] = len - bytes;
+                        *got = bytes;
+                        return ch.base + off;
+                    }
+            if (pass == 1) break;
+            Chunk ch;
+            ch.size = std::max(next_chunk, align_up(bytes));
+            if (cudaMalloc((void**)&ch.base, ch.size) != cudaSuccess) {
+                cudaGetLastError();
+                ch.size = align_up(bytes);   // memory is tight: exactly what is needed
+                if (cudaMalloc((void**)&ch.base, ch.size) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            }
+            ch.free[0] = ch.size;
+            chunks.push_back(std::move(ch));
+            next_chunk = std::min<size_t>(next_chunk * 2, (size_t)16 << 30);
         }
-        if (best < 0) return nullptr;
-        void* p = free_blocks[best].second;
-        *got = free_blocks[best].first;
-        cached_bytes -= *got;
-        free_blocks.erase(free_blocks.begin() + best);
-        return p;
+        return nullptr;
     }
-    void give(size_t bytes, void* p) {
-        free_blocks.emplace_back(bytes, p);
-        cached_bytes += bytes;
+    void release(void* p, size_t bytes) {
+        for (Chunk& ch : chunks) {
+            char* q = (char*)p;
+            if (q < ch.base || q >= ch.base + ch.size) continue;
+            size_t off = (size_t)(q - ch.base), len = bytes;
+            auto nx = ch.free.lower_bound(off);
+            if (nx != ch.free.end() && off + len == nx->first) { len += nx->second; nx = ch.free.erase(nx); }
+            if (nx != ch.free.begin()) {
+                auto pv = std::prev(nx);
+                if (pv->first + pv->second == off) { off = pv->first; len += pv->second; ch.free.erase(pv); }
+            }
+            ch.free[off] = len;
+            return;
+        }
     }
-    void flush() {
-        for (auto& b : free_blocks) cudaFree(b.second);
-        free_blocks.clear();
-        cached_bytes = 0;
+    void destroy() {
+        for (Chunk& ch : chunks) cudaFree(ch.base);
+        chunks.clear();
+        next_chunk = (size_t)2 << 30;
     }
 };
 
@@ -151,7 +182,7 @@ struct dre_context {
 
     // panels
     std::vector<Panel> panels;
-    BlockCache cache;
+    Arena arena;
 
     // dense workspaces
     DBuf<double> gram_partial, gbuf, gbuf2, cbuf, wsel, wsel2, small, stage, qws, pws, qtmp, rt, rt2, tmp_panel, evals, cnorm;
@@ -839,8 +870,7 @@ int32_t dre_destroy(dre_context* c) {
     if (!c) return DRE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
-    for (Panel& p : c->panels) if (p.alive && p.d) cudaFree(p.d);
-    c->cache.flush();
+    c->arena.destroy();
     release_pencil(c);
     c->tbuf.release(); c->Wbuf.release(); c->btw.release(); c->sol.release();
     c->gram_partial.release(); c->gbuf.release(); c->gbuf2.release(); c->cbuf.release(); c->wsel.release();
@@ -877,8 +907,8 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->st));
     release_pencil(c);
-    for (Panel& p : c->panels) if (p.alive && p.d) { cudaFree(p.d); p.alive = false; p.d = nullptr; }
-    c->cache.flush();
+    for (Panel& p : c->panels) { p.alive = false; p.d = nullptr; }
+    c->arena.destroy();
     c->op_U = c->op_Vt = dre_view{-1, 0, 0};
     AnalyzeOptions opt;
     if (const char* ev = getenv("DRE_LEAF_SIZE")) opt.leaf_size = std::max(8, atoi(ev));
@@ -987,21 +1017,14 @@ int32_t dre_mat_create(dre_context* c, int32_t cols, int32_t* id) {
     p.cols = cols;
     p.ld = std::max(1, (cols + 1) & ~1);  // even leading dimension: 16-byte aligned rows
     {
-        // size classes of 32 columns keep slightly different residual widths (242, 249, ...) interchangeable
-        const size_t want = (size_t)c->sym.n * (size_t)((p.ld + 31) & ~31) * sizeof(double);
+        const size_t want = (size_t)c->sym.n * (size_t)p.ld * sizeof(double);
         size_t got = 0;
-        void* blk = c->cache.take(want, &got);
-        if (!blk) {
-            HostTrace tr("panel cudaMalloc");
-            cudaError_t e = cudaMalloc(&blk, want);
-            if (e != cudaSuccess) {  // give the cached blocks back to the driver and retry once
-                cudaGetLastError();
-                CU(cudaStreamSynchronize(c->st));
-                c->cache.flush();
-                CU(cudaMalloc(&blk, want));
-            }
-            got = want;
+        void* blk;
+        {
+            HostTrace tr("panel arena alloc");
+            blk = c->arena.alloc(want, &got);
         }
+        if (!blk) return fail(c, DRE_ERR_CUDA, "out of device memory for a panel");
         p.d = (double*)blk;
         p.cap = got;
     }
@@ -1017,7 +1040,7 @@ int32_t dre_mat_free(dre_context* c, int32_t id) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     if (id < 0 || id >= (int)c->panels.size() || !c->panels[id].alive) return fail(c, DRE_ERR_ARG, "invalid panel id");
     if (c->op_U.id == id || c->op_Vt.id == id) c->op_U = c->op_Vt = dre_view{-1, 0, 0};
-    c->cache.give(c->panels[id].cap, c->panels[id].d);
+    c->arena.release(c->panels[id].d, c->panels[id].cap);
     c->panels[id].alive = false;
     c->panels[id].d = nullptr;
     return DRE_OK;
