@@ -373,7 +373,8 @@ GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
     int tiles = ((a + G2A - 1) / G2A) * ((b + tbw - 1) / tbw);   // pipelined kernel: 64 x 128 (64 x 64) output tiles
     if (tiles < 1) tiles = 1;
     int64_t chunks = (n + GK - 1) / GK;
-    int want = std::max(1, (2 * sm_count + tiles - 1) / tiles);   // ~2 CTAs per SM
+    int want = std::max(1, (2 * sm_count) / tiles);   // at most 2 CTAs per SM: ONE full wave (19 x 16 tiles = 304 CTAs
+                                                      // on 296 slots was measured at twice the time of 18 x 16)
     if (a <= 16 && b >= 64) want = std::max(1, 4 * sm_count / ((b + 255) / 256));  // skinny kernel: thread per column
     int64_t maxsplit = std::max<int64_t>(1, chunks / 8);          // at least 8 chunks (128 rows) per split
     int nsplit = (int)std::min<int64_t>(want, maxsplit);
@@ -765,27 +766,36 @@ void launch_pivchol(const double* G, int64_t ldg, int pb, double drop2, double r
 // ------------------------------------------------------------------------------------------
 // ||R diag(t) R'||_F^2 = sum_ij G_ij^2 t_i t_j,  G = R'R
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_norm_diag(const double* __restrict__ G, int64_t ldg, int r,
-                                                   const double* __restrict__ t, double* __restrict__ out) {
-    __shared__ double red[256];
+__global__ void __launch_bounds__(1024) k_norm_diag(const double* __restrict__ G, int64_t ldg, int r,
+                                                    const double* __restrict__ t, double* __restrict__ out) {
+    // one CTA of 32 warps; warp w sums rows w, w+32, ... (coalesced along the row), fixed-shape reduction
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double s = 0.0;
-    for (int idx = threadIdx.x; idx < r * r; idx += 256) {
-        const int i = idx / r, j = idx % r;
-        const double g = G[(int64_t)i * ldg + j];
-        s += g * g * t[i] * t[j];
+    for (int i = warp; i < r; i += 32) {
+        const double ti = t[i];
+        double si = 0.0;
+        for (int j = lane; j < r; j += 32) {
+            const double g = G[(int64_t)i * ldg + j];
+            si = fma(g * g, t[j], si);
+        }
+        s = fma(si, ti, s);
     }
-    red[threadIdx.x] = s;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) red[warp] = s;
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
-        __syncthreads();
+    if (warp == 0) {
+        double v = red[lane];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) out[0] = v;
     }
-    if (threadIdx.x == 0) out[0] = red[0];
 }
 
 void launch_norm_diag(const double* G, int64_t ldg, int r, const double* t, double* out, cudaStream_t st,
                       int64_t* launches) {
-    k_norm_diag<<<1, 256, 0, st>>>(G, ldg, r, t, out);
+    k_norm_diag<<<1, 1024, 0, st>>>(G, ldg, r, t, out);
     if (launches) *launches += 1;
 }
 

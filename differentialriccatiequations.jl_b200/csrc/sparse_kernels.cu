@@ -85,14 +85,27 @@ template <class T, int NT, class FA, class FB>
 __device__ __forceinline__ void strip_mma(double (&acc)[NT][2], int kbeg, int kend, int lane, FA fa, FB fb) {
     const int kk = lane & 3;
     int k0 = kbeg;
-    for (; k0 + 16 <= kend; k0 += 16) {
-        T a[4];
+    if (k0 + 16 <= kend) {
+        // software pipeline: the next four A fragments (global / L2 loads) are in flight while the current
+        // four feed the tensor cores
+        T a[4], an[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) a[q] = fa(k0 + 4 * q + kk);
+        for (; k0 + 32 <= kend; k0 += 16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) an[q] = fa(k0 + 16 + 4 * q + kk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) MM<T>::mma(acc[nt], a[q], fb(k0 + 4 * q + kk, nt), lane);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = an[q];
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) MM<T>::mma(acc[nt], a[q], fb(k0 + 4 * q + kk, nt), lane);
+        k0 += 16;
     }
     for (; k0 < kend; k0 += 4) {
         const T a = fa(k0 + kk);
@@ -466,9 +479,10 @@ void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* 
 // w, w+8, w+16, w+24 of the supernode (s <= SN_MAX = 256) and keeps their results in registers, so the
 // right-hand-side tile in shared memory is updated in place after one barrier.
 // ------------------------------------------------------------------------------------------
-constexpr int SWEEP_Q = SN_MAX / 64;  // strips per warp
 
-template <class T, int NT>
+// SWEEP_Q = strips per warp: 4 covers supernodes up to SN_MAX = 256 columns, 2 (levels whose widest supernode has
+// <= 128 columns, i.e. the populous leaf levels) halves the accumulator registers -> one more CTA per SM
+template <class T, int NT, int SWEEP_Q>
 __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
                                              const T* __restrict__ Linv, T* W, int64_t ldw, int nrhs, T* tbuf) {
     constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value;
@@ -559,7 +573,7 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
     }
 }
 
-template <class T, int NT>
+template <class T, int NT, int SWEEP_Q>
 __global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
                                              const T* __restrict__ Linv, const T* __restrict__ dvec, T* W, int64_t ldw,
                                              int nrhs, int srows) {
@@ -658,12 +672,12 @@ static int bwd_smem(int smax) {
     return (int)sizeof(T) * (((smax + 7) & ~7) + 64) * RhsLd<T, NT * MM<T>::CPN>::value;
 }
 
-template <class T, int NT>
+template <class T, int NT, int Q>
 static void set_sweep_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(k_fwd<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<T, NT>(SN_MAX));
-    cudaFuncSetAttribute(k_bwd<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<T, NT>(SN_MAX));
+    cudaFuncSetAttribute(k_fwd<T, NT, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<T, NT>(64 * Q));
+    cudaFuncSetAttribute(k_bwd<T, NT, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<T, NT>(64 * Q));
     done = true;
 }
 
@@ -676,18 +690,35 @@ static int pick_nt(int nsns, int nrhs) {
     return 1;
 }
 
+template <class T, int NT, int Q>
+static void launch_fwd_t(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv, T* W,
+                         int64_t ldw, int nrhs, T* tbuf, cudaStream_t st) {
+    set_sweep_attrs<T, NT, Q>();
+    const int cw = NT * MM<T>::CPN;
+    dim3 grid(nsns, (nrhs + cw - 1) / cw);
+    k_fwd<T, NT, Q><<<grid, 256, fwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
+}
+
+template <class T, int NT, int Q>
+static void launch_bwd_t(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
+                         const T* dvec, T* W, int64_t ldw, int nrhs, cudaStream_t st) {
+    set_sweep_attrs<T, NT, Q>();
+    const int cw = NT * MM<T>::CPN;
+    dim3 grid(nsns, (nrhs + cw - 1) / cw);
+    k_bwd<T, NT, Q><<<grid, 256, bwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs, (smax + 7) & ~7);
+}
+
 template <class T>
 void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
                       T* W, int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    set_sweep_attrs<T, 4>();
-    set_sweep_attrs<T, 2>();
-    set_sweep_attrs<T, 1>();
-    const int nt = pick_nt<T>(nsns, nrhs), cw = nt * MM<T>::CPN;
-    dim3 grid(nsns, (nrhs + cw - 1) / cw);
-    if (nt == 4) k_fwd<T, 4><<<grid, 256, fwd_smem<T, 4>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
-    else if (nt == 2) k_fwd<T, 2><<<grid, 256, fwd_smem<T, 2>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
-    else k_fwd<T, 1><<<grid, 256, fwd_smem<T, 1>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
+    const int nt = pick_nt<T>(nsns, nrhs);
+    const bool narrow = smax <= 128;
+#define DRE_FWD(NT_, Q_) launch_fwd_t<T, NT_, Q_>(S, sns, nsns, smax, L, Linv, W, ldw, nrhs, tbuf, st)
+    if (nt == 4) { if (narrow) DRE_FWD(4, 2); else DRE_FWD(4, 4); }
+    else if (nt == 2) { if (narrow) DRE_FWD(2, 2); else DRE_FWD(2, 4); }
+    else { if (narrow) DRE_FWD(1, 2); else DRE_FWD(1, 4); }
+#undef DRE_FWD
     if (launches) *launches += 1;
 }
 
@@ -695,15 +726,13 @@ template <class T>
 void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
                       const T* dvec, T* W, int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    set_sweep_attrs<T, 4>();
-    set_sweep_attrs<T, 2>();
-    set_sweep_attrs<T, 1>();
-    const int nt = pick_nt<T>(nsns, nrhs), cw = nt * MM<T>::CPN;
-    const int srows = (smax + 7) & ~7;
-    dim3 grid(nsns, (nrhs + cw - 1) / cw);
-    if (nt == 4) k_bwd<T, 4><<<grid, 256, bwd_smem<T, 4>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs, srows);
-    else if (nt == 2) k_bwd<T, 2><<<grid, 256, bwd_smem<T, 2>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs, srows);
-    else k_bwd<T, 1><<<grid, 256, bwd_smem<T, 1>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs, srows);
+    const int nt = pick_nt<T>(nsns, nrhs);
+    const bool narrow = smax <= 128;
+#define DRE_BWD(NT_, Q_) launch_bwd_t<T, NT_, Q_>(S, sns, nsns, smax, L, Linv, dvec, W, ldw, nrhs, st)
+    if (nt == 4) { if (narrow) DRE_BWD(4, 2); else DRE_BWD(4, 4); }
+    else if (nt == 2) { if (narrow) DRE_BWD(2, 2); else DRE_BWD(2, 4); }
+    else { if (narrow) DRE_BWD(1, 2); else DRE_BWD(1, 4); }
+#undef DRE_BWD
     if (launches) *launches += 1;
 }
 
