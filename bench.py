@@ -432,8 +432,10 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K,
            "warmup": W, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"Rail-shaped synthetic 2D P1-FEM pencil n={n} (7 inputs, 6 outputs), low-rank "
-                                  f"Ros1, dt={DT}, t0={T0}, ADI defaults", "n": n},
+           "config": {"workload": f"Rail-shaped synthetic 2D P1-FEM pencil n={n} (7 inputs, 6 outputs), low-rank Ros1, "
+                                  f"dt={DT}, t0={T0}, ADI defaults (Projection(2), maxiters=100, compression every 10)",
+                      "n": n, "nnz_E": meta["nnz_E"], "nnz_A": meta["nnz_A"],
+                      "parallelism": f"{nthreads} host threads (CPU reference arm)"},
            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": nthreads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

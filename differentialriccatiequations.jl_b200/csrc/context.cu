@@ -180,6 +180,7 @@ struct dre_context {
     double op_a = 1.0, op_e = 0.0, op_alpha = 1.0;
     dre_view op_U{-1, 0, 0}, op_Vt{-1, 0, 0};
 
+    dre_view ortho_hint{-1, 0, 0};   // dre_hint_orthonormal: consumed by the next dre_ldlt_compress
     // panels
     std::vector<Panel> panels;
     Arena arena;
@@ -1327,6 +1328,8 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     const int64_t n = c->sym.n;
     RRState s;
     if ((rc = rr_setup(c, s, ktot, 3e-15, 0.0))) return rc;
+    const dre_view hint = c->ortho_hint;
+    c->ortho_hint = dre_view{-1, 0, 0};
     std::vector<double> signs(ktot, 1.0);
     struct DenseTerm { int t, row0, k; };
     std::vector<DenseTerm> dense_terms;
@@ -1351,8 +1354,21 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
             }
             CU(c->evals.ensure(k));
             CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, k * sizeof(double), cudaMemcpyHostToDevice, c->st));
-            HostTrace tr("compress: rr block (diag core)", c->st);
-            if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, c->evals.p, row0))) return rc;
+            const bool hinted = s.rho == 0 && hint.id == Ls[t].id && hint.col0 == Ls[t].col0 &&
+                                hint.ncols == Ls[t].ncols && k + 64 <= s.qcap;
+            if (hinted) {
+                // the caller vouches that these columns are orthonormal (the outer factor a previous compress!
+                // produced): they ARE the first k basis vectors, their coefficients are the column scalings
+                launch_copy_scale(s.Q, s.ldq, vptr(c, Ls[t]), vld(c, Ls[t]), n, k, nullptr, c->st,
+                                  &c->stats.kernel_launches);
+                CU(cudaMemcpy2DAsync(s.RT + (int64_t)row0 * s.ldrt, (size_t)(s.ldrt + 1) * sizeof(double), c->evals.p,
+                                     sizeof(double), sizeof(double), k, cudaMemcpyDeviceToDevice, c->st));
+                for (int j = 0; j < k; ++j) s.scale2 = std::max(s.scale2, c->h_pinned[j] * c->h_pinned[j]);
+                s.rho = k;
+            } else {
+                HostTrace tr("compress: rr block (diag core)", c->st);
+                if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, c->evals.p, row0))) return rc;
+            }
         } else {
             // Non-diagonal core (e.g. T = [aS 0 0; 0 0 bD; 0 bD 0] of the Lyapunov residual,
             // src/lyapunov/residual.jl:21-28): exactly as the reference does (src/LDLt.jl:206-213) the basis is
@@ -1425,6 +1441,14 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
         CU(cudaStreamSynchronize(c->st));
     }
     return check_errflag(c);
+}
+
+int32_t dre_hint_orthonormal(dre_context* c, dre_view v) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    int rc;
+    if ((rc = check_view(c, v, "view", true))) return rc;
+    c->ortho_hint = v;
+    return DRE_OK;
 }
 
 int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double drop_rel, double drop_abs, dre_view Q,

@@ -375,10 +375,10 @@ GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
     int64_t chunks = (n + GK - 1) / GK;
     int want = std::max(1, (2 * sm_count) / tiles);   // at most 2 CTAs per SM: ONE full wave (19 x 16 tiles = 304 CTAs
                                                       // on 296 slots was measured at twice the time of 18 x 16)
-    if (a <= 16 && b >= 64) want = std::max(1, 4 * sm_count / ((b + 255) / 256));  // skinny kernel: thread per column
+    if (a <= 16 && b >= 64) want = std::max(1, 8 * sm_count / ((b + 255) / 256));  // skinny kernel: thread per column
     int64_t maxsplit = std::max<int64_t>(1, chunks / 8);          // at least 8 chunks (128 rows) per split
     int nsplit = (int)std::min<int64_t>(want, maxsplit);
-    nsplit = std::min(nsplit, 320);
+    nsplit = std::min(nsplit, (a <= 16 && b >= 64) ? 1184 : 320);   // skinny kernel: bytes in flight need many CTAs
     int64_t cps = (chunks + nsplit - 1) / nsplit;
     p.rows_per_split = cps * GK;
     p.nsplit = (int)((n + p.rows_per_split - 1) / p.rows_per_split);

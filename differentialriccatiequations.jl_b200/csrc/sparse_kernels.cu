@@ -848,19 +848,27 @@ __device__ __forceinline__ void emit(cplx v, int mode, double d, double* V1, dou
     }
 }
 
-template <class T>
-__global__ void k_smw_apply(const T* __restrict__ W, int64_t ldw, int r, int m, const T* __restrict__ Sol, int mode,
-                            double d, double* __restrict__ V1, int64_t ld1, double* __restrict__ V2, int64_t ld2,
-                            int64_t n) {
-    const int64_t total = n * r;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = idx / r;
-        const int c = (int)(idx % r);
+// one warp per row: the m correction coefficients of the row are loaded once, lanes run over the r columns
+template <class T, int MR>
+__global__ void __launch_bounds__(256) k_smw_apply(const T* __restrict__ W, int64_t ldw, int r, int m,
+                                                   const T* __restrict__ Sol, int mode, double d,
+                                                   double* __restrict__ V1, int64_t ld1, double* __restrict__ V2,
+                                                   int64_t ld2, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp0; row < n; row += nwarps) {
         const T* w = W + row * ldw;
-        T v = w[c];
-        for (int j = 0; j < m; ++j) v = sub(v, mul(w[r + j], Sol[(int64_t)j * r + c]));
-        emit(v, mode, d, V1, V2, row * ld1 + c, row * ld2 + c);
+        T y[MR];
+#pragma unroll
+        for (int j = 0; j < MR; ++j) y[j] = (j < m) ? w[r + j] : zero<T>();
+        for (int c = lane; c < r; c += 32) {
+            T v = w[c];
+#pragma unroll
+            for (int j = 0; j < MR; ++j)
+                if (j < m) v = sub(v, mul(y[j], Sol[(int64_t)j * r + c]));
+            emit(v, mode, d, V1, V2, row * ld1 + c, row * ld2 + c);
+        }
     }
 }
 
@@ -868,8 +876,9 @@ template <class T>
 void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int mode, double d, double* V1,
                       int64_t ld1, double* V2, int64_t ld2, int64_t n, cudaStream_t st, int64_t* launches) {
     if (n <= 0 || r <= 0) return;
-    int blocks = (int)std::min<int64_t>((n * r + 255) / 256, 148 * 16);
-    k_smw_apply<T><<<blocks, 256, 0, st>>>(W, ldw, r, m, Sol, mode, d, V1, ld1, V2, ld2, n);
+    int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 16);
+    if (m <= 8) k_smw_apply<T, 8><<<blocks, 256, 0, st>>>(W, ldw, r, m, Sol, mode, d, V1, ld1, V2, ld2, n);
+    else k_smw_apply<T, 32><<<blocks, 256, 0, st>>>(W, ldw, r, m, Sol, mode, d, V1, ld1, V2, ld2, n);
     if (launches) *launches += 1;
 }
 

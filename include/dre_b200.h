@@ -149,6 +149,11 @@ DRE_API int32_t dre_ldlt_norm(dre_context* ctx, dre_view L, const double* D, int
 DRE_API int32_t dre_ldlt_compress(dre_context* ctx, int32_t nterms, const dre_view* Ls, const double* const* Ds,
                           const int64_t* ldds, const double* alphas, double tol_factor, dre_view out,
                           double* lam, int32_t* newrank);
+/* Hint for the NEXT dre_ldlt_compress only: the columns of `v` are orthonormal (they are the outer factor a
+ * previous compress! produced, src/LDLt.jl:219-222).  If `v` is the first term of that call and its core is
+ * diagonal, its columns are adopted as the first basis vectors without re-orthogonalisation.  Results agree
+ * with the unhinted call to round-off. */
+DRE_API int32_t dre_hint_orthonormal(dre_context* ctx, dre_view v);
 /* Rank-revealing QR of N = hcat(views): N ~ Q * Rt' with orthonormal Q (n x rho) written to `Q`
  * (capacity Q.ncols) and Rt (ncols(N) x rho, host column-major, ld = ldr).  Directions whose
  * residual norm falls below max(drop_rel * max column norm, drop_abs) are discarded.  Building
