@@ -155,7 +155,14 @@ def run_ours(args):
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     try:
-        out = _run_ours(args)
+        # The host side of this path is one launching thread plus tiny LAPACK calls (r x r cores, one ~500 x 500
+        # eigenproblem per ADI solve).  A 16-thread BLAS pool spin-waits after every call and competes with the
+        # launching thread for the box's 16 cores: measured 0.89 steps/s with 16 BLAS threads vs 1.06-1.09 with
+        # 1-4 on the same box.  (The CPU-baseline leg sets its own, full thread count.)
+        from threadpoolctl import threadpool_limits
+
+        with threadpool_limits(limits=args.blas_threads):
+            out = _run_ours(args)
     finally:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -451,6 +458,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--blas-threads", type=int, default=2, help="host BLAS threads during the GPU arm")
     args = ap.parse_args()
     os.environ.setdefault("OPENBLAS_NUM_THREADS", str(min(os.cpu_count() or 1, 16)))
     if args.impl == "reference":

@@ -641,7 +641,8 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                 const int nnew = s.rho - rho0;   // directions added inside this block
                 if (nnew > 0) {
                     CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
-                    for (int pass = 0; pass < 2; ++pass) {
+                    // same rule as for the block passes: one pass unless the block holds large columns
+                    for (int pass = 0; pass < npass; ++pass) {
                         rc = gram_dev(c, Pw, PBIG, pb, s.Q + rho0, s.ldq, nnew, n, nullptr, c->cbuf.p, nnew,
                                       RTrow + rho0, s.ldrt);
                         if (rc) return rc;

@@ -472,6 +472,81 @@ void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t l
     if (launches) *launches += 2;
 }
 
+// Small-K variant (a <= 64, b <= 64 per CTA column block): the whole X tile (128 x 64) and W (64 x 64) are
+// fetched with one cp.async burst -- one barrier instead of a 4-chunk pipeline whose prologue dominates.
+constexpr int TSK = 64, TSLDX = TSK + 4, TSLDW = 64 + 8;
+__global__ void __launch_bounds__(256) k_tall_gemm_smallk(double alpha, const double* __restrict__ X, int64_t ldx,
+                                                          int a, const double* __restrict__ W, int64_t ldw,
+                                                          int w_trans, double beta, double* __restrict__ Y,
+                                                          int64_t ldy, int b, int64_t n, int aligned_x) {
+    extern __shared__ __align__(16) double ts_smem[];
+    double* Xs = ts_smem;                 // [128][TSLDX]
+    double* Ws = ts_smem + T2M * TSLDX;   // [64][TSLDW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * T2M;
+    const int b0 = blockIdx.y * 64;
+    const int a4 = (a + 3) & ~3;
+    if (aligned_x) {
+        for (int c = tid; c < T2M * (TSK / 2); c += 256) {
+            const int r = c / (TSK / 2), kc = (c % (TSK / 2)) * 2;
+            if (kc >= a4) continue;
+            const int64_t row = row0 + r;
+            int nb = 0;
+            if (row < n) nb = 8 * max(0, min(2, a - kc));
+            cp_async16(Xs + r * TSLDX + kc, nb ? (const void*)(X + row * ldx + kc) : (const void*)X, nb);
+        }
+    } else {
+        for (int c = tid; c < T2M * TSK; c += 256) {
+            const int r = c / TSK, kc = c % TSK;
+            if (kc >= a4) continue;
+            const int64_t row = row0 + r;
+            const bool ok = row < n && kc < a;
+            cp_async8(Xs + r * TSLDX + kc, ok ? (const void*)(X + row * ldx + kc) : (const void*)X, ok ? 8 : 0);
+        }
+    }
+    for (int c = tid; c < TSK * 64; c += 256) {
+        int k, j;
+        if (w_trans) { k = c % TSK; j = c / TSK; } else { k = c / 64; j = c % 64; }
+        if (k >= a4) continue;
+        const bool ok = k < a && b0 + j < b;
+        const double* src = w_trans ? W + (int64_t)(b0 + j) * ldw + k : W + (int64_t)k * ldw + b0 + j;
+        cp_async8(Ws + k * TSLDW + j, ok ? (const void*)src : (const void*)W, ok ? 8 : 0);
+    }
+    cp_async_commit();
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int kk = lane & 3, rr = lane >> 2;
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int k0 = 0; k0 < a4; k0 += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) af[mt] = Xs[(wr + mt * 8 + rr) * TSLDX + k0 + kk];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bf[nt] = Ws[(k0 + kk) * TSLDW + wc + nt * 8 + rr];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int64_t row = row0 + wr + mt * 8 + rr;
+        if (row >= n) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int j = b0 + wc + nt * 8 + 2 * kk;
+            double* y = Y + row * ldy + j;
+            if (j < b) y[0] = (beta == 0.0 ? 0.0 : beta * y[0]) + alpha * acc[mt][nt][0];
+            if (j + 1 < b) y[1] = (beta == 0.0 ? 0.0 : beta * y[1]) + alpha * acc[mt][nt][1];
+        }
+    }
+}
+
 template <int T2N>
 static void launch_tall_gemm_t(double alpha, const double* X, int64_t ldx, int a, const double* W, int64_t ldw,
                                int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n, cudaStream_t st) {
@@ -491,8 +566,21 @@ void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const d
                       int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n, cudaStream_t st,
                       int64_t* launches) {
     if (b <= 0 || n <= 0) return;
-    if (b <= 16) launch_tall_gemm_t<16>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, st);
-    else launch_tall_gemm_t<64>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, st);
+    if (a <= TSK && b > 16) {
+        static bool attr_set = false;
+        const int smem = (T2M * TSLDX + TSK * TSLDW) * (int)sizeof(double);
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_tall_gemm_smallk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        dim3 grid((unsigned)((n + T2M - 1) / T2M), (unsigned)((b + 63) / 64));
+        const int ax = reinterpret_cast<uintptr_t>(X) % 16 == 0 && ldx % 2 == 0;
+        k_tall_gemm_smallk<<<grid, 256, smem, st>>>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, ax);
+    } else if (b <= 16) {
+        launch_tall_gemm_t<16>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, st);
+    } else {
+        launch_tall_gemm_t<64>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, st);
+    }
     if (launches) *launches += 1;
 }
 

@@ -482,8 +482,10 @@ void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* 
 
 // SWEEP_Q = strips per warp: 4 covers supernodes up to SN_MAX = 256 columns, 2 (levels whose widest supernode has
 // <= 128 columns, i.e. the populous leaf levels) halves the accumulator registers -> one more CTA per SM
-template <class T, int NT, int SWEEP_Q>
-__global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
+// NW = warps per CTA: 8 normally, 16 for the few fat supernodes near the root (half as many strips per warp
+// -> half the dependent-load chain per level, which is what those levels cost)
+template <class T, int NT, int SWEEP_Q, int NW>
+__global__ void __launch_bounds__(32 * NW) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
                                              const T* __restrict__ Linv, T* W, int64_t ldw, int nrhs, T* tbuf) {
     constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value;
     extern __shared__ __align__(16) unsigned char dre_smem_raw[];
@@ -498,11 +500,11 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = lane >> 2, bc = MM<T>::bcol(lane);
 
-    for (int idx = tid; idx < s8 * CW; idx += 256) {
+    for (int idx = tid; idx < s8 * CW; idx += 32 * NW) {
         const int i = idx / CW, cc = idx - i * CW;
         xs[i * LDB + cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
     }
-    for (int idx = tid; idx < u * ncw; idx += 256) {
+    for (int idx = tid; idx < u * ncw; idx += 32 * NW) {
         const int cc = idx / u, i = idx - cc * u;
         tJ[(int64_t)(c0 + cc) * u + i] = zero<T>();
     }
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
         const int uc = sn_u(S, c);
         const int32_t* rel = S.relmap + S.sn_rowptr[c];
         const T* tch = tbuf + S.rhs_off[c] * ldw;
-        for (int idx = tid; idx < uc * ncw; idx += 256) {
+        for (int idx = tid; idx < uc * ncw; idx += 32 * NW) {
             const int cc = idx / uc, i = idx - cc * uc;
             const int pr = rel[i];
             const T val = tch[(int64_t)(c0 + cc) * uc + i];
@@ -525,7 +527,7 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
     double acc[SWEEP_Q][NT][2];
 #pragma unroll
     for (int q = 0; q < SWEEP_Q; ++q) {
-        const int i0 = (warp + 8 * q) * 8;
+        const int i0 = (warp + NW * q) * 8;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
         if (i0 < s) {
@@ -539,7 +541,7 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < SWEEP_Q; ++q) {
-        const int row = (warp + 8 * q) * 8 + r;
+        const int row = (warp + NW * q) * 8 + r;
         if (row < s) {
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
@@ -547,12 +549,12 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
         }
     }
     __syncthreads();
-    for (int idx = tid; idx < s * CW; idx += 256) {
+    for (int idx = tid; idx < s * CW; idx += 32 * NW) {
         const int i = idx / CW, cc = idx - i * CW;
         if (cc < ncw) W[(int64_t)(first + i) * ldw + c0 + cc] = xs[i * LDB + cc];
     }
     // t_J -= L21 y
-    for (int i0 = warp * 8; i0 < u; i0 += 64) {
+    for (int i0 = warp * 8; i0 < u; i0 += 8 * NW) {
         const int row = i0 + r;
         const T* Lrow = P + (s + row);
         double a1[NT][2];
@@ -573,8 +575,8 @@ __global__ void __launch_bounds__(256) k_fwd(DevSymbolic S, const int32_t* __res
     }
 }
 
-template <class T, int NT, int SWEEP_Q>
-__global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
+template <class T, int NT, int SWEEP_Q, int NW>
+__global__ void __launch_bounds__(32 * NW) k_bwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
                                              const T* __restrict__ Linv, const T* __restrict__ dvec, T* W, int64_t ldw,
                                              int nrhs, int srows) {
     constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value;
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __res
         for (int nt = 0; nt < NT; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
     // acc = L21' x_struct, 64 structure rows at a time
     for (int r0 = 0; r0 < u; r0 += 64) {
-        for (int idx = tid; idx < 64 * CW; idx += 256) {
+        for (int idx = tid; idx < 64 * CW; idx += 32 * NW) {
             const int i = idx / CW, cc = idx - i * CW;
             xt[i * LDB + cc] = (r0 + i < u && cc < ncw) ? W[(int64_t)rows[r0 + i] * ldw + c0 + cc] : zero<T>();
         }
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __res
         const int kt = min(64, u - r0);
 #pragma unroll
         for (int q = 0; q < SWEEP_Q; ++q) {
-            const int i0 = (warp + 8 * q) * 8;
+            const int i0 = (warp + NW * q) * 8;
             if (i0 < s) {
                 const int col = i0 + r;   // output row = column of L21
                 const T* Lcol = P + (s + r0) + (int64_t)col * f;
@@ -619,13 +621,13 @@ __global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __res
         __syncthreads();
     }
     // z = D^-1 y - acc
-    for (int idx = tid; idx < (s8 - s) * CW; idx += 256) {
+    for (int idx = tid; idx < (s8 - s) * CW; idx += 32 * NW) {
         const int i = s + idx / CW, cc = idx % CW;
         xs[i * LDB + cc] = zero<T>();
     }
 #pragma unroll
     for (int q = 0; q < SWEEP_Q; ++q) {
-        const int row = (warp + 8 * q) * 8 + r;
+        const int row = (warp + NW * q) * 8 + r;
         if (row < s) {
             const T rd = recip(dv[row]);
 #pragma unroll
@@ -641,7 +643,7 @@ __global__ void __launch_bounds__(256) k_bwd(DevSymbolic S, const int32_t* __res
     // x = Linv' z (upper triangular)
 #pragma unroll
     for (int q = 0; q < SWEEP_Q; ++q) {
-        const int i0 = (warp + 8 * q) * 8;
+        const int i0 = (warp + NW * q) * 8;
         if (i0 < s) {
             const int row = i0 + r;
             const T* Lcol = LI + (int64_t)row * s;
@@ -672,12 +674,12 @@ static int bwd_smem(int smax) {
     return (int)sizeof(T) * (((smax + 7) & ~7) + 64) * RhsLd<T, NT * MM<T>::CPN>::value;
 }
 
-template <class T, int NT, int Q>
+template <class T, int NT, int Q, int NW>
 static void set_sweep_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(k_fwd<T, NT, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<T, NT>(64 * Q));
-    cudaFuncSetAttribute(k_bwd<T, NT, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<T, NT>(64 * Q));
+    cudaFuncSetAttribute(k_fwd<T, NT, Q, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<T, NT>(8 * NW * Q));
+    cudaFuncSetAttribute(k_bwd<T, NT, Q, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<T, NT>(8 * NW * Q));
     done = true;
 }
 
@@ -690,22 +692,23 @@ static int pick_nt(int nsns, int nrhs) {
     return 1;
 }
 
-template <class T, int NT, int Q>
+template <class T, int NT, int Q, int NW>
 static void launch_fwd_t(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv, T* W,
                          int64_t ldw, int nrhs, T* tbuf, cudaStream_t st) {
-    set_sweep_attrs<T, NT, Q>();
+    set_sweep_attrs<T, NT, Q, NW>();
     const int cw = NT * MM<T>::CPN;
     dim3 grid(nsns, (nrhs + cw - 1) / cw);
-    k_fwd<T, NT, Q><<<grid, 256, fwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
+    k_fwd<T, NT, Q, NW><<<grid, 32 * NW, fwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
 }
 
-template <class T, int NT, int Q>
+template <class T, int NT, int Q, int NW>
 static void launch_bwd_t(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
                          const T* dvec, T* W, int64_t ldw, int nrhs, cudaStream_t st) {
-    set_sweep_attrs<T, NT, Q>();
+    set_sweep_attrs<T, NT, Q, NW>();
     const int cw = NT * MM<T>::CPN;
     dim3 grid(nsns, (nrhs + cw - 1) / cw);
-    k_bwd<T, NT, Q><<<grid, 256, bwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs, (smax + 7) & ~7);
+    k_bwd<T, NT, Q, NW><<<grid, 32 * NW, bwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs,
+                                                                      (smax + 7) & ~7);
 }
 
 template <class T>
@@ -714,10 +717,10 @@ void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int sm
     if (nsns <= 0 || nrhs <= 0) return;
     const int nt = pick_nt<T>(nsns, nrhs);
     const bool narrow = smax <= 128;
-#define DRE_FWD(NT_, Q_) launch_fwd_t<T, NT_, Q_>(S, sns, nsns, smax, L, Linv, W, ldw, nrhs, tbuf, st)
-    if (nt == 4) { if (narrow) DRE_FWD(4, 2); else DRE_FWD(4, 4); }
-    else if (nt == 2) { if (narrow) DRE_FWD(2, 2); else DRE_FWD(2, 4); }
-    else { if (narrow) DRE_FWD(1, 2); else DRE_FWD(1, 4); }
+#define DRE_FWD(NT_, Q_, NW_) launch_fwd_t<T, NT_, Q_, NW_>(S, sns, nsns, smax, L, Linv, W, ldw, nrhs, tbuf, st)
+    if (nt == 4) { if (narrow) DRE_FWD(4, 2, 8); else DRE_FWD(4, 4, 8); }
+    else if (nt == 2) { if (narrow) DRE_FWD(2, 2, 8); else DRE_FWD(2, 2, 16); }
+    else { if (narrow) DRE_FWD(1, 2, 8); else DRE_FWD(1, 2, 16); }
 #undef DRE_FWD
     if (launches) *launches += 1;
 }
@@ -728,10 +731,10 @@ void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int sm
     if (nsns <= 0 || nrhs <= 0) return;
     const int nt = pick_nt<T>(nsns, nrhs);
     const bool narrow = smax <= 128;
-#define DRE_BWD(NT_, Q_) launch_bwd_t<T, NT_, Q_>(S, sns, nsns, smax, L, Linv, dvec, W, ldw, nrhs, st)
-    if (nt == 4) { if (narrow) DRE_BWD(4, 2); else DRE_BWD(4, 4); }
-    else if (nt == 2) { if (narrow) DRE_BWD(2, 2); else DRE_BWD(2, 4); }
-    else { if (narrow) DRE_BWD(1, 2); else DRE_BWD(1, 4); }
+#define DRE_BWD(NT_, Q_, NW_) launch_bwd_t<T, NT_, Q_, NW_>(S, sns, nsns, smax, L, Linv, dvec, W, ldw, nrhs, st)
+    if (nt == 4) { if (narrow) DRE_BWD(4, 2, 8); else DRE_BWD(4, 4, 8); }
+    else if (nt == 2) { if (narrow) DRE_BWD(2, 2, 8); else DRE_BWD(2, 2, 16); }
+    else { if (narrow) DRE_BWD(1, 2, 8); else DRE_BWD(1, 2, 16); }
 #undef DRE_BWD
     if (launches) *launches += 1;
 }

@@ -144,6 +144,61 @@ def test_factor_arrays_and_wide_solves(n, leaf, cap, monkeypatch):
     api.reset_backend()
 
 
+def test_full_size_solve_and_compress_properties():
+    """BASELINE's full size (n = 79 841, 250 right-hand sides), checked through size-independent properties
+    because SuperLU / dense references are out of reach here:  the residual of the shifted block solve
+    ||(a A + (e+mu) E) V - R|| / ||R|| computed with the device SpMM (real and complex shift), and the
+    compress! invariants -- value preserved under a second compression, orthonormal outer factor, norm
+    unchanged (test/LDLt.jl:63-90)."""
+    n = 79841
+    E, A, B, C, _ = pencils.rail_pencil(n)
+    api.reset_backend()
+    api.upload_pencil(E, A)
+    rng = np.random.default_rng(21)
+    R = rng.standard_normal((n, 250))
+    Rd = api.DeviceMatrix.from_host(R)
+    a, e = 1.0, -1.0 / 200.0
+    F = api.PencilCombo(a, e)
+    for mu in (-0.37, -0.02 + 0.11j):
+        out = api.solve_block(api.BlockLinearProblem(F, Rd), mu=mu)
+        parts = out if isinstance(mu, complex) else (out,)
+        res = []
+        for part, (cr, ci) in zip(parts, ((1.0, 0.0), (0.0, 1.0))):
+            res.append((part, cr, ci))
+        # real part of M V:  a A Vr + Re(e+mu) E Vr - Im(mu) E Vi ;  imaginary part analogously
+        Vr = parts[0]
+        Vi = parts[1] if isinstance(mu, complex) else None
+        mr, mi = (e + mu.real, mu.imag) if isinstance(mu, complex) else (e + mu, 0.0)
+        Yr = api.spmm("A", Vr, a)
+        api.spmm("E", Vr, mr, Yr, 1.0)
+        if Vi is not None:
+            api.spmm("E", Vi, -mi, Yr, 1.0)
+        resid = Yr.to_host() - R
+        assert np.linalg.norm(resid) <= 1e-10 * np.linalg.norm(R), mu
+        if Vi is not None:
+            Yi = api.spmm("A", Vi, a)
+            api.spmm("E", Vi, mr, Yi, 1.0)
+            api.spmm("E", Vr, mi, Yi, 1.0)
+            assert np.linalg.norm(Yi.to_host()) <= 1e-10 * np.linalg.norm(R), mu
+    # compress! invariants on a rank-deficient 250-column factor with an indefinite diagonal core
+    base = rng.standard_normal((n, 40))
+    L = base @ rng.standard_normal((40, 120))
+    d = rng.standard_normal(120)
+    X = api.lowrank(api.DeviceMatrix.from_host(L), np.diag(d))
+    nrm0 = api.norm(X)
+    api.compress_(X)
+    k1 = X.rank()
+    assert 38 <= k1 <= 42
+    assert abs(api.norm(X) - nrm0) <= 1e-10 * nrm0
+    G = api.gemm_tn(X.Ls[0], X.Ls[0])
+    assert np.linalg.norm(G - np.eye(k1)) < 1e-10
+    lam1 = np.sort(np.diag(X.Ds[0]))
+    api.compress_(X)  # idempotent up to round-off (uses the orthonormal hint of the first result)
+    assert X.rank() == k1
+    assert np.allclose(np.sort(np.diag(X.Ds[0])), lam1, rtol=1e-9, atol=1e-9 * np.abs(lam1).max())
+    api.reset_backend()
+
+
 @pytest.mark.parametrize("mu", [-0.2, -0.05 + 0.3j])
 def test_shift_solve_lowrank_smw(rail, mu):
     """Closed-loop operator (A_s - B K + mu E) with the fused SMW correction
