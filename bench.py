@@ -47,19 +47,31 @@ class ClockSampler:
         self.gpu, self.period, self.samples, self.stop_flag = gpu_index, period_s, [], threading.Event()
         self.thread = None
         self.err = None
-
-    def _loop(self):
-        try:
+        self.nvml = self.handle = self.max_mhz = None
+        self.query_ms = []
+        try:  # NVML initialisation (hundreds of ms, takes driver locks) happens OUTSIDE the timed region
             import pynvml
 
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
-            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def _loop(self):
+        if self.nvml is None:
+            return
+        nv, h = self.nvml, self.handle
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.stop_flag.wait(0.25)
             while not self.stop_flag.is_set():
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
-                    pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, mx, rs))
+                t0 = time.perf_counter()
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = reasons(h)
+                self.query_ms.append(1e3 * (time.perf_counter() - t0))
+                self.samples.append((sm, self.max_mhz, rs))
                 self.stop_flag.wait(self.period)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
@@ -78,7 +90,7 @@ class ClockSampler:
         bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         reasons = sorted({name for _, _, r in self.samples for b, name in bits.items() if r & b})
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
-                "samples": len(sm), "how": "NVML, 1 s period"}
+                "samples": len(sm), "how": "NVML, 1 s period", "nvml_query_ms_max": round(max(self.query_ms), 2)}
 
 
 def _problem(n):

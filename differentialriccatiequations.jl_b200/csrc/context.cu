@@ -368,7 +368,7 @@ int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) 
 }
 
 template <class T>
-int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
+int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs, const RhsSource& src) {
     const Symbolic& S = c->sym;
     Timer t(c, &c->stats.ms_solve);
     {
@@ -383,7 +383,7 @@ int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs) {
     for (int l = 0; l < S.nlevels; ++l) {
         const dre_context::LevelWork& lw = c->levels[l];
         HostTrace tr("  one fwd level launch");
-        launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, lw.smax, L, Linv, W, ldw, nrhs, tb,
+        launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, lw.smax, L, Linv, W, ldw, nrhs, tb, src,
                             c->st, &c->stats.kernel_launches);
     }
     for (int l = S.nlevels - 1; l >= 0; --l) {
@@ -484,8 +484,7 @@ int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_
         CU(c->Wbuf.ensure((size_t)n * ldw * sizeof(T)));
     }
     T* W = (T*)c->Wbuf.p;
-    launch_load_rhs<T>(W, ldw, vptr(c, R), vld(c, R), r, m ? vptr(c, c->op_Vt) : nullptr, m ? vld(c, c->op_Vt) : 0, m,
-                       n, c->st, &c->stats.kernel_launches);
+    const RhsSource rhs_src{vptr(c, R), vld(c, R), r, m ? vptr(c, c->op_Vt) : nullptr, m ? vld(c, c->op_Vt) : 0};
     T emu;
     make_emu(c->op_e, mu_re, mu_im, emu);
     const int tw = (int)(sizeof(T) / sizeof(double));  // 1 or 2 doubles per element
@@ -494,7 +493,7 @@ int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_
     if (rc) return rc;
     {
         HostTrace tr(sizeof(T) == 8 ? "sweeps<double> launch" : "sweeps<cplx> launch");
-        rc = solve_sweeps<T>(c, W, ldw, nrhs);
+        rc = solve_sweeps<T>(c, W, ldw, nrhs, rhs_src);
     }
     if (rc) return rc;
     T* Sol = nullptr;

@@ -113,11 +113,20 @@ template <class T>
 void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dvec, T* U,
                   cudaStream_t st, int64_t* launches);
 
+// where the forward sweep finds the right-hand side: columns [0, r) in R, [r, r+m) in Vt (real row-major panels)
+struct RhsSource {
+    const double* R;
+    int64_t ldr;
+    int r;
+    const double* Vt;
+    int64_t ldv;
+};
+
 // forward / backward sweeps of one level on the row-major RHS block W (n x ldw), nrhs columns.
 // smax = widest supernode of the level (sizes the dynamic shared memory).
 template <class T>
 void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
-                      T* W, int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches);
+                      T* W, int64_t ldw, int nrhs, T* tbuf, const RhsSource& src, cudaStream_t st, int64_t* launches);
 template <class T>
 void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
                       const T* dvec, T* W, int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches);

@@ -26,6 +26,7 @@
 // the diagonal inside the 32x32 diagonal blocks); pivots in dvec[n]; update matrices u_J x u_J (lower) and
 // update vectors (u_J per right-hand side, column-major), one region per supernode.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -486,7 +487,8 @@ void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* 
 // -> half the dependent-load chain per level, which is what those levels cost)
 template <class T, int NT, int SWEEP_Q, int NW>
 __global__ void __launch_bounds__(32 * NW) k_fwd(DevSymbolic S, const int32_t* __restrict__ sns, const T* __restrict__ L,
-                                             const T* __restrict__ Linv, T* W, int64_t ldw, int nrhs, T* tbuf) {
+                                             const T* __restrict__ Linv, T* W, int64_t ldw, int nrhs, T* tbuf,
+                                             RhsSource src) {
     constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value;
     extern __shared__ __align__(16) unsigned char dre_smem_raw[];
     T* xs = reinterpret_cast<T*>(dre_smem_raw);   // [s8][LDB]
@@ -500,9 +502,17 @@ __global__ void __launch_bounds__(32 * NW) k_fwd(DevSymbolic S, const int32_t* _
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = lane >> 2, bc = MM<T>::bcol(lane);
 
+    // the right-hand side [R, Vt] (real panels) is read where it lies: every row is first touched by the
+    // supernode that owns it, so no staging copy into W is needed
     for (int idx = tid; idx < s8 * CW; idx += 32 * NW) {
         const int i = idx / CW, cc = idx - i * CW;
-        xs[i * LDB + cc] = (i < s && cc < ncw) ? W[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
+        T v = zero<T>();
+        if (i < s && cc < ncw) {
+            const int col = c0 + cc;
+            const int64_t row = first + i;
+            from_real(col < src.r ? src.R[row * src.ldr + col] : src.Vt[row * src.ldv + (col - src.r)], v);
+        }
+        xs[i * LDB + cc] = v;
     }
     for (int idx = tid; idx < u * ncw; idx += 32 * NW) {
         const int cc = idx / u, i = idx - cc * u;
@@ -685,8 +695,11 @@ static void set_sweep_attrs() {
 
 // widest chunk that still gives every SM a CTA; narrow chunks for the few fat supernodes near the root
 template <class T>
-static int pick_nt(int nsns, int nrhs) {
+static int pick_nt(int nsns, int nrhs, bool narrow) {
     const int cpn = MM<T>::CPN;
+    // populous narrow levels: 64-column chunks halve the factor re-reads (each A fragment feeds 8 tiles)
+    static const bool use_nt8 = getenv("DRE_NT8") != nullptr;   // experimental (164 registers: 1 CTA/SM)
+    if (use_nt8 && narrow && (int64_t)nsns * ((nrhs + 8 * cpn - 1) / (8 * cpn)) >= 2 * 148) return 8;
     if ((int64_t)nsns * ((nrhs + 4 * cpn - 1) / (4 * cpn)) >= 148) return 4;
     if ((int64_t)nsns * ((nrhs + 2 * cpn - 1) / (2 * cpn)) >= 148) return 2;
     return 1;
@@ -694,11 +707,11 @@ static int pick_nt(int nsns, int nrhs) {
 
 template <class T, int NT, int Q, int NW>
 static void launch_fwd_t(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv, T* W,
-                         int64_t ldw, int nrhs, T* tbuf, cudaStream_t st) {
+                         int64_t ldw, int nrhs, T* tbuf, const RhsSource& src, cudaStream_t st) {
     set_sweep_attrs<T, NT, Q, NW>();
     const int cw = NT * MM<T>::CPN;
     dim3 grid(nsns, (nrhs + cw - 1) / cw);
-    k_fwd<T, NT, Q, NW><<<grid, 32 * NW, fwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf);
+    k_fwd<T, NT, Q, NW><<<grid, 32 * NW, fwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf, src);
 }
 
 template <class T, int NT, int Q, int NW>
@@ -713,12 +726,13 @@ static void launch_bwd_t(const DevSymbolic& S, const int32_t* sns, int nsns, int
 
 template <class T>
 void launch_fwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
-                      T* W, int64_t ldw, int nrhs, T* tbuf, cudaStream_t st, int64_t* launches) {
+                      T* W, int64_t ldw, int nrhs, T* tbuf, const RhsSource& src, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    const int nt = pick_nt<T>(nsns, nrhs);
     const bool narrow = smax <= 128;
-#define DRE_FWD(NT_, Q_, NW_) launch_fwd_t<T, NT_, Q_, NW_>(S, sns, nsns, smax, L, Linv, W, ldw, nrhs, tbuf, st)
-    if (nt == 4) { if (narrow) DRE_FWD(4, 2, 8); else DRE_FWD(4, 4, 8); }
+    const int nt = pick_nt<T>(nsns, nrhs, narrow);
+#define DRE_FWD(NT_, Q_, NW_) launch_fwd_t<T, NT_, Q_, NW_>(S, sns, nsns, smax, L, Linv, W, ldw, nrhs, tbuf, src, st)
+    if (nt == 8) DRE_FWD(8, 2, 8);
+    else if (nt == 4) { if (narrow) DRE_FWD(4, 2, 8); else DRE_FWD(4, 4, 8); }
     else if (nt == 2) { if (narrow) DRE_FWD(2, 2, 8); else DRE_FWD(2, 2, 16); }
     else { if (narrow) DRE_FWD(1, 2, 8); else DRE_FWD(1, 2, 16); }
 #undef DRE_FWD
@@ -729,10 +743,11 @@ template <class T>
 void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
                       const T* dvec, T* W, int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches) {
     if (nsns <= 0 || nrhs <= 0) return;
-    const int nt = pick_nt<T>(nsns, nrhs);
     const bool narrow = smax <= 128;
+    const int nt = pick_nt<T>(nsns, nrhs, narrow);
 #define DRE_BWD(NT_, Q_, NW_) launch_bwd_t<T, NT_, Q_, NW_>(S, sns, nsns, smax, L, Linv, dvec, W, ldw, nrhs, st)
-    if (nt == 4) { if (narrow) DRE_BWD(4, 2, 8); else DRE_BWD(4, 4, 8); }
+    if (nt == 8) DRE_BWD(8, 2, 8);
+    else if (nt == 4) { if (narrow) DRE_BWD(4, 2, 8); else DRE_BWD(4, 4, 8); }
     else if (nt == 2) { if (narrow) DRE_BWD(2, 2, 8); else DRE_BWD(2, 2, 16); }
     else { if (narrow) DRE_BWD(1, 2, 8); else DRE_BWD(1, 2, 16); }
 #undef DRE_BWD
@@ -897,7 +912,7 @@ void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int m
     template void launch_schur<T>(const DevSymbolic&, const int4*, int, const T*, const T*, T*, cudaStream_t,        \
                                   int64_t*);                                                                         \
     template void launch_fwd_level<T>(const DevSymbolic&, const int32_t*, int, int, const T*, const T*, T*, int64_t, \
-                                      int, T*, cudaStream_t, int64_t*);                                              \
+                                      int, T*, const RhsSource&, cudaStream_t, int64_t*);                            \
     template void launch_bwd_level<T>(const DevSymbolic&, const int32_t*, int, int, const T*, const T*, const T*,    \
                                       T*, int64_t, int, cudaStream_t, int64_t*);                                     \
     template void launch_load_rhs<T>(T*, int64_t, const double*, int64_t, int, const double*, int64_t, int, int64_t, \
