@@ -25,30 +25,6 @@ namespace {
 
 thread_local std::string g_last_error;
 
-template <class T>
-struct DBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = n + n / 2 + 64;   // geometric growth: cudaMalloc / cudaFree of large blocks cost tens of ms
-        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
-        if (e != cudaSuccess) { p = nullptr; return e; }
-        cap = want;
-        return cudaSuccess;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct Panel {
-    double* d = nullptr;
-    int cols = 0;
-    int64_t ld = 0;
-    bool alive = false;
-    size_t cap = 0;   // bytes of the underlying block (>= n * ld * 8)
-};
-
 // Arena allocator for the panels.  Everything that touches panels runs on ONE stream, so a block released by
 // dre_mat_free can be handed out again immediately (its next use is stream-ordered behind the last one).
 // cudaMalloc / cudaFree of the 0.1 - 2 GB panels of this workload were measured at 0.3 - 75 ms per call
@@ -79,6 +55,15 @@ struct Arena {
             if (pass == 1) break;
             Chunk ch;
             ch.size = std::max(next_chunk, align_up(bytes));
+            const auto t0 = std::chrono::steady_clock::now();
+            struct Report {
+                const Chunk& ch; std::chrono::steady_clock::time_point t0;
+                ~Report() {
+                    if (getenv("DRE_TRACE_ALLOC"))
+                        fprintf(stderr, "[dre alloc] new arena chunk %.2f GB in %.1f ms\n", ch.size / 1073741824.0,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                }
+            } report{ch, t0};
             if (cudaMalloc((void**)&ch.base, ch.size) != cudaSuccess) {
                 cudaGetLastError();
                 ch.size = align_up(bytes);   // memory is tight: exactly what is needed
@@ -110,6 +95,39 @@ struct Arena {
         chunks.clear();
         next_chunk = (size_t)2 << 30;
     }
+};
+
+// Growable device workspace, sub-allocated from the context's arena (all users run on the main stream, so a
+// released block may be handed out again immediately).  Growing through cudaFree + cudaMalloc cost up to 650 ms
+// for the GB-sized Gram-Schmidt workspaces and showed up as outlier time steps.
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;       // elements
+    size_t bytes = 0;     // size of the arena block
+    Arena* arena = nullptr;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { arena->release(p, bytes); p = nullptr; cap = 0; bytes = 0; }
+        const size_t want = n + n / 2 + 64;
+        size_t got = 0;
+        void* q = arena->alloc(want * sizeof(T), &got);
+        if (!q) return cudaErrorMemoryAllocation;
+        p = (T*)q;
+        bytes = got;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p && arena) arena->release(p, bytes); p = nullptr; cap = 0; bytes = 0; }
+    void forget() { p = nullptr; cap = 0; bytes = 0; }   // the arena itself was destroyed
+};
+
+struct Panel {
+    double* d = nullptr;
+    int cols = 0;
+    int64_t ld = 0;
+    bool alive = false;
+    size_t cap = 0;   // bytes of the underlying block (>= n * ld * 8)
 };
 
 }  // namespace
@@ -200,6 +218,13 @@ struct dre_context {
 };
 
 namespace {
+
+template <class F>
+void for_each_workspace(dre_context* c, F f) {
+    f(c->tbuf); f(c->Wbuf); f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
+    f(c->wsel); f(c->wsel2); f(c->small); f(c->stage); f(c->qws); f(c->pws); f(c->qtmp); f(c->rt); f(c->rt2);
+    f(c->tmp_panel); f(c->evals); f(c->cnorm); f(c->syevd_work); f(c->ibuf);
+}
 
 int fail(dre_context* c, int code, const std::string& msg) {
     if (c) c->err = msg;
@@ -811,6 +836,8 @@ int32_t dre_symbolic_export(const dre_symbolic* s, const char* what, void* buf, 
     return fail(nullptr, DRE_ERR_ARG, "dre_symbolic_export: unknown array name " + w);
 }
 
+static void prime_eigensolver(dre_context* c);
+
 int32_t dre_create(int32_t device, dre_context** out) {
     if (!out) return fail(nullptr, DRE_ERR_ARG, "null argument");
     dre_context* c = new (std::nothrow) dre_context();
@@ -833,6 +860,7 @@ int32_t dre_create(int32_t device, dre_context** out) {
         cudaEventCreateWithFlags(&fs.ready, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&fs.released, cudaEventDisableTiming);
     }
+    for_each_workspace(c, [&](auto& w) { w.arena = &c->arena; });
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     cudaEventCreate(&c->tev0);
@@ -847,6 +875,7 @@ int32_t dre_create(int32_t device, dre_context** out) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    prime_eigensolver(c);
     *out = c;
     return DRE_OK;
 }
@@ -867,17 +896,50 @@ static void release_pencil(dre_context* c) {
     c->has_pencil = false;
 }
 
+// cuSOLVER loads its kernels lazily, per size class, at the first call that needs them (CUDA lazy module loading):
+// 1.5 - 2.3 s stalls were measured inside individual compress! calls of the first time steps whenever the projected
+// core crossed a size threshold (tools/step_times.py).  One throw-away Dsyevd per size class at the first context
+// of the process moves that cost to start-up (DRE_NO_PRIME=1 skips it).
+static void prime_eigensolver(dre_context* c) {
+    static bool done = false;
+    if (done || getenv("DRE_NO_PRIME")) return;
+    done = true;
+    const int sizes[] = {32, 128, 256, 512, 1024};
+    const int nmax = 1024;
+    double* A = nullptr;
+    double* w = nullptr;
+    if (cudaMalloc((void**)&A, sizeof(double) * nmax * nmax) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaMalloc((void**)&w, sizeof(double) * nmax) != cudaSuccess) { cudaGetLastError(); cudaFree(A); return; }
+    std::vector<double> h((size_t)nmax * nmax);
+    for (int k : sizes) {
+        for (int j = 0; j < k; ++j)
+            for (int i = 0; i < k; ++i) h[(size_t)i + (size_t)j * k] = (i == j) ? 1.0 + j : 1.0 / (1.0 + i + j);
+        cudaMemcpyAsync(A, h.data(), sizeof(double) * k * k, cudaMemcpyHostToDevice, c->st);
+        int lwork = 0;
+        if (cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, A, k, w,
+                                        &lwork) != CUSOLVER_STATUS_SUCCESS)
+            break;
+        double* work = nullptr;
+        int* info = nullptr;
+        if (cudaMalloc((void**)&work, sizeof(double) * (lwork + 8)) != cudaSuccess) { cudaGetLastError(); break; }
+        if (cudaMalloc((void**)&info, sizeof(int)) != cudaSuccess) { cudaGetLastError(); cudaFree(work); break; }
+        cusolverDnDsyevd(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, A, k, w, work, lwork, info);
+        cudaStreamSynchronize(c->st);
+        cudaFree(work);
+        cudaFree(info);
+    }
+    cudaFree(A);
+    cudaFree(w);
+    cudaGetLastError();
+}
+
 int32_t dre_destroy(dre_context* c) {
     if (!c) return DRE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     c->arena.destroy();
     release_pencil(c);
-    c->tbuf.release(); c->Wbuf.release(); c->btw.release(); c->sol.release();
-    c->gram_partial.release(); c->gbuf.release(); c->gbuf2.release(); c->cbuf.release(); c->wsel.release();
-    c->wsel2.release(); c->small.release(); c->stage.release(); c->qws.release(); c->pws.release();
-    c->qtmp.release(); c->rt.release(); c->rt2.release(); c->cnorm.release(); c->tmp_panel.release(); c->evals.release(); c->syevd_work.release();
-    c->ibuf.release();
+    for_each_workspace(c, [](auto& w) { w.forget(); });   // the arena (destroyed above) owned their memory
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->d_errflag) cudaFree(c->d_errflag);
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
@@ -909,6 +971,7 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     CU(cudaStreamSynchronize(c->st));
     release_pencil(c);
     for (Panel& p : c->panels) { p.alive = false; p.d = nullptr; }
+    for_each_workspace(c, [](auto& w) { w.forget(); });
     c->arena.destroy();
     c->op_U = c->op_Vt = dre_view{-1, 0, 0};
     AnalyzeOptions opt;
