@@ -332,6 +332,9 @@ def _run_ours(args):
     if rank == 0 and not args.no_cpu:
         cpu = cpu_sample(E, A, B, C, LW_host, DW_host, ct.iters[0] if ct.iters else 100, args.cpu_iters)
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return None
     out = {

@@ -1271,6 +1271,12 @@ int32_t dre_adi_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dr
     return shifted_solve(c, mu_re, mu_im, R, V1, V2, true);
 }
 
+int32_t dre_get_stream(dre_context* c, void** stream) {
+    if (!c || !stream) return fail(c, DRE_ERR_ARG, "null argument");
+    *stream = (void*)c->st;
+    return DRE_OK;
+}
+
 int32_t dre_mat_devptr(dre_context* c, dre_view v, void** ptr, int64_t* ld) {
     if (!c || !ptr || !ld) return fail(c, DRE_ERR_ARG, "null argument");
     int rc;

@@ -97,28 +97,54 @@ def panel_tensor(be, M):
     return torch.as_tensor(_CudaArray(ptr.value, be.n, M.ncols, ld.value), device=f"cuda:{dev}")
 
 
+def _library_stream(be):
+    """The context's main stream as a torch ExternalStream: copies and NCCL collectives issued under it are
+    stream-ordered with the library's kernels (no host synchronisation on the data path)."""
+    import torch
+
+    cached = getattr(be, "_torch_stream", None)
+    if cached is not None and cached[0] == be.h.value:
+        return cached[1]
+    ptr = C.c_void_p()
+    be.check(be.lib.dre_get_stream(be.h, C.byref(ptr)))
+    dev = _STATE.device if _STATE is not None and _STATE.device is not None else 0
+    st = torch.cuda.ExternalStream(ptr.value, device=f"cuda:{dev}")
+    be._torch_stream = (be.h.value, st)
+    return st
+
+
 def sharded_adi_solve(be, mu: complex, R, V1, V2, empty_view):
     """Column-sharded version of the solve half of dre_adi_step: this rank solves its block of R's columns,
-    then every rank receives all blocks of V1 (and V2 for a complex pair)."""
+    then every rank receives all blocks of V1 (and V2 for a complex pair).  Everything is queued on the
+    library's stream: solve -> pad/copy of the local block -> NCCL all-gather -> scatter into the full panel."""
     import torch
+    import torch.distributed as dist
 
     st = _STATE
     blocks = partition(R.ncols, st.world)
     c0, c1 = blocks[st.rank]
     widths = [b - a for a, b in blocks]
+    wmax = max(widths)
     if c1 > c0:
         v2 = V2.cols(c0, c1).view if V2 is not None else empty_view
         be.check(be.lib.dre_adi_solve(be.h, mu.real, mu.imag, R.cols(c0, c1).view, V1.cols(c0, c1).view, v2))
-    be.ctx.sync()
-    for V in (V1, V2):
-        if V is None:
-            continue
-        full = panel_tensor(be, V)
-        gathered = allgather_columns(full[:, c0:c1].contiguous(), widths, st.group)
-        full.copy_(gathered)
-        st.bytes_gathered += gathered.numel() * 8
-        st.gathers += 1
-    torch.cuda.synchronize()
+    n = be.n
+    with torch.cuda.stream(_library_stream(be)):
+        for V in (V1, V2):
+            if V is None or wmax == 0:
+                continue
+            full = panel_tensor(be, V)
+            pad = torch.empty((n, wmax), dtype=torch.float64, device=full.device)
+            pad[:, :c1 - c0].copy_(full[:, c0:c1])
+            if c1 - c0 < wmax:
+                pad[:, c1 - c0:].zero_()
+            out = torch.empty((st.world * n, wmax), dtype=torch.float64, device=full.device)
+            dist.all_gather_into_tensor(out, pad, group=st.group)
+            for g, (b0, b1) in enumerate(blocks):
+                if g != st.rank and b1 > b0:
+                    full[:, b0:b1].copy_(out[g * n:(g + 1) * n, :b1 - b0])
+            st.bytes_gathered += out.numel() * 8
+            st.gathers += 1
 
 
 def agree_scalar(x: float) -> float:

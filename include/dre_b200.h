@@ -98,6 +98,9 @@ DRE_API int32_t dre_mat_copy(dre_context* ctx, dre_view dst, dre_view src);
  * with rows in the solver's internal ordering (identical on every rank for the same pencil).  The caller must
  * dre_sync() before touching the memory from another stream and must not keep the pointer past dre_mat_free. */
 DRE_API int32_t dre_mat_devptr(dre_context* ctx, dre_view v, void** ptr, int64_t* ld);
+/* The context's main CUDA stream (a cudaStream_t).  Collectives and copies queued on it by the host side are
+ * ordered with the library's own work, so the multi-GPU exchange needs no host synchronisation. */
+DRE_API int32_t dre_get_stream(dre_context* ctx, void** stream);
 /* Y = alpha*X + beta*Y (X may be an empty view when alpha == 0) */
 DRE_API int32_t dre_mat_axpby(dre_context* ctx, double alpha, dre_view X, double beta, dre_view Y);
 
