@@ -219,7 +219,7 @@ def _run_ours(args):
     tK = tW + K * DT
     sampler = ClockSampler(local)
     barrier()
-    if not args.no_clocks:
+    if not args.no_clocks and rank == 0:
         sampler.start()
     be.ctx.stats_reset(False)
     be.ctx.timer_start()

@@ -20,7 +20,10 @@ import ctypes as C
 
 import numpy as np
 
+import os
+
 _STATE = None
+_PARANOID = os.environ.get("DRE_DIST_PARANOID") is not None   # also broadcast every residual norm from rank 0
 
 
 class _State:
@@ -129,7 +132,15 @@ def sharded_adi_solve(be, mu: complex, R, V1, V2, empty_view):
         v2 = V2.cols(c0, c1).view if V2 is not None else empty_view
         be.check(be.lib.dre_adi_solve(be.h, mu.real, mu.imag, R.cols(c0, c1).view, V1.cols(c0, c1).view, v2))
     n = be.n
-    with torch.cuda.stream(_library_stream(be)):
+    trace = os.environ.get("DRE_DIST_TRACE") is not None
+    lib_stream = _library_stream(be)
+    if trace:
+        import time
+
+        t_host0 = time.perf_counter()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record(lib_stream)
+    with torch.cuda.stream(lib_stream):
         for V in (V1, V2):
             if V is None or wmax == 0:
                 continue
@@ -139,19 +150,34 @@ def sharded_adi_solve(be, mu: complex, R, V1, V2, empty_view):
             if c1 - c0 < wmax:
                 pad[:, c1 - c0:].zero_()
             out = torch.empty((st.world * n, wmax), dtype=torch.float64, device=full.device)
+            if trace:
+                ev[1].record(lib_stream)
             dist.all_gather_into_tensor(out, pad, group=st.group)
+            if trace:
+                ev[2].record(lib_stream)
             for g, (b0, b1) in enumerate(blocks):
                 if g != st.rank and b1 > b0:
                     full[:, b0:b1].copy_(out[g * n:(g + 1) * n, :b1 - b0])
             st.bytes_gathered += out.numel() * 8
             st.gathers += 1
+    if trace:
+        t_host1 = time.perf_counter()
+        ev[2].synchronize()
+        acc = st.__dict__.setdefault("trace", [0.0, 0.0, 0.0, 0])
+        acc[0] += ev[0].elapsed_time(ev[1])   # solve (+ anything queued before) + pad copy
+        acc[1] += ev[1].elapsed_time(ev[2])   # all-gather incl. waiting for the slowest rank
+        acc[2] += 1e3 * (t_host1 - t_host0)   # host time to enqueue
+        acc[3] += 1
+        if acc[3] % 100 == 0 and st.rank == 0:
+            print(f"[dre dist] per call: solve+pad {acc[0] / acc[3]:.3f} ms, all-gather(+wait) {acc[1] / acc[3]:.3f} ms, "
+                  f"host enqueue {acc[2] / acc[3]:.3f} ms", flush=True)
 
 
 def agree_scalar(x: float) -> float:
     """Rank 0's value of a control-flow scalar (all ranks compute it from identical data; this only
     guarantees that a discrepancy cannot desynchronise the collectives)."""
-    if not active():
-        return x
+    if not active() or not _PARANOID:
+        return x   # ranks are bit-identical by construction (tests/test_gpu_dist.py); checked at every compress!
     return float(agree_array(np.array([x], dtype=np.float64))[0])
 
 

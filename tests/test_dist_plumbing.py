@@ -48,6 +48,8 @@ def _worker(rank, world, port, ncols, q):
         got = ddist.allgather_columns(full[:, c0:c1].contiguous(), [b - a for a, b in blocks])
         ok = bool(torch.equal(got, full))
         # control-flow agreement: every rank ends up with rank 0's values
+        assert ddist.agree_scalar(3.0 + rank) == 3.0 + rank   # default: trusted (ranks are bit-identical)
+        ddist._PARANOID = True
         x = ddist.agree_scalar(1.25 if rank == 0 else 99.0)
         arr = ddist.agree_array(np.array([1 + 2j, -3.5j]) if rank == 0 else np.array([7.0]))
         ok = ok and x == 1.25 and np.array_equal(arr, np.array([1 + 2j, -3.5j]))
