@@ -145,11 +145,18 @@ def sharded_adi_solve(be, mu: complex, R, V1, V2, empty_view):
             if V is None or wmax == 0:
                 continue
             full = panel_tensor(be, V)
-            pad = torch.empty((n, wmax), dtype=torch.float64, device=full.device)
+            # persistent exchange buffers: a fresh 160 MB tensor per call makes the caching allocator (which must
+            # honour NCCL's record_stream) fall back to cudaMalloc -- a device synchronisation per ADI iteration
+            key = (n, wmax, st.world, str(full.device))
+            bufs = st.__dict__.setdefault("buffers", {})
+            if key not in bufs:
+                bufs.clear()
+                bufs[key] = (torch.empty((n, wmax), dtype=torch.float64, device=full.device),
+                             torch.empty((st.world * n, wmax), dtype=torch.float64, device=full.device))
+            pad, out = bufs[key]
             pad[:, :c1 - c0].copy_(full[:, c0:c1])
             if c1 - c0 < wmax:
                 pad[:, c1 - c0:].zero_()
-            out = torch.empty((st.world * n, wmax), dtype=torch.float64, device=full.device)
             if trace:
                 ev[1].record(lib_stream)
             dist.all_gather_into_tensor(out, pad, group=st.group)
