@@ -8,6 +8,9 @@
 #include <cstring>
 #include <numeric>
 #include <queue>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace dre {
 namespace {
@@ -245,27 +248,55 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
     if (base != 0 && base != 1) return "analyze: index_base must be 0 or 1";
     S = Symbolic();
     S.n = n;
+    const bool trace = getenv("DRE_TRACE_SYMBOLIC") != nullptr;
+    auto tprev = std::chrono::steady_clock::now();
+    auto phase = [&](const char* name) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dre symbolic] %-28s %7.1f ms\n", name, std::chrono::duration<double, std::milli>(now - tprev).count());
+        tprev = now;
+    };
     const int64_t nnzE = Ecp[n] - base, nnzA = Acp[n] - base;
     if (Ecp[0] != base || Acp[0] != base) return "analyze: colptr[0] != index_base";
 
-    // ---- union triplets in OLD indices (full pattern, both triangles as given) ----
+    // ---- union triplets in OLD indices (full pattern, both triangles as given), sorted by (column, row) ----
     struct Trip { int64_t key; double a, e; };
     std::vector<Trip> trip;
     trip.reserve(nnzE + nnzA);
-    for (int64_t j = 0; j < n; ++j) {
-        for (int64_t p = Ecp[j] - base; p < Ecp[j + 1] - base; ++p) {
-            int64_t i = Eri[p] - base;
-            if (i < 0 || i >= n) return "analyze: E row index out of range";
-            trip.push_back({j * n + i, 0.0, Enz[p]});
-        }
-        for (int64_t p = Acp[j] - base; p < Acp[j + 1] - base; ++p) {
-            int64_t i = Ari[p] - base;
-            if (i < 0 || i >= n) return "analyze: A row index out of range";
-            trip.push_back({j * n + i, Anz[p], 0.0});
-        }
+    bool sorted_input = true;   // SparseMatrixCSC keeps row indices sorted per column: merge instead of sorting
+    for (int64_t j = 0; j < n && sorted_input; ++j) {
+        for (int64_t p = Ecp[j] - base + 1; p < Ecp[j + 1] - base; ++p)
+            if (Eri[p] <= Eri[p - 1]) { sorted_input = false; break; }
+        for (int64_t p = Acp[j] - base + 1; p < Acp[j + 1] - base && sorted_input; ++p)
+            if (Ari[p] <= Ari[p - 1]) { sorted_input = false; break; }
     }
-    std::sort(trip.begin(), trip.end(), [](const Trip& x, const Trip& y) { return x.key < y.key; });
-    {
+    if (sorted_input) {
+        for (int64_t j = 0; j < n; ++j) {
+            int64_t pe = Ecp[j] - base, pe1 = Ecp[j + 1] - base, pa = Acp[j] - base, pa1 = Acp[j + 1] - base;
+            while (pe < pe1 || pa < pa1) {
+                const int64_t ie = pe < pe1 ? Eri[pe] - base : INT64_MAX, ia = pa < pa1 ? Ari[pa] - base : INT64_MAX;
+                const int64_t i = std::min(ie, ia);
+                if (i < 0 || i >= n) return ie <= ia ? "analyze: E row index out of range" : "analyze: A row index out of range";
+                Trip t{j * n + i, 0.0, 0.0};
+                if (ie == i) t.e = Enz[pe++];
+                if (ia == i) t.a = Anz[pa++];
+                trip.push_back(t);
+            }
+        }
+    } else {
+        for (int64_t j = 0; j < n; ++j) {
+            for (int64_t p = Ecp[j] - base; p < Ecp[j + 1] - base; ++p) {
+                int64_t i = Eri[p] - base;
+                if (i < 0 || i >= n) return "analyze: E row index out of range";
+                trip.push_back({j * n + i, 0.0, Enz[p]});
+            }
+            for (int64_t p = Acp[j] - base; p < Acp[j + 1] - base; ++p) {
+                int64_t i = Ari[p] - base;
+                if (i < 0 || i >= n) return "analyze: A row index out of range";
+                trip.push_back({j * n + i, Anz[p], 0.0});
+            }
+        }
+        std::sort(trip.begin(), trip.end(), [](const Trip& x, const Trip& y) { return x.key < y.key; });
         size_t w = 0;
         for (size_t r = 0; r < trip.size(); ++r) {
             if (w > 0 && trip[w - 1].key == trip[r].key) {
@@ -277,25 +308,29 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
         }
         trip.resize(w);
     }
-    // symmetry check of values (the symmetric pencil is the scope of this build)
+    // symmetry check of values (the symmetric pencil is the scope of this build): (i, j) is looked up in column i
     {
         double amax = 0, emax = 0;
         for (auto& t : trip) { amax = std::max(amax, std::fabs(t.a)); emax = std::max(emax, std::fabs(t.e)); }
-        auto find = [&](int64_t key) -> const Trip* {
-            auto it = std::lower_bound(trip.begin(), trip.end(), key,
-                                       [](const Trip& x, int64_t k) { return x.key < k; });
-            return (it != trip.end() && it->key == key) ? &*it : nullptr;
+        std::vector<int64_t> colstart(n + 1, 0);
+        for (auto& t : trip) colstart[t.key / n + 1]++;
+        for (int64_t j = 0; j < n; ++j) colstart[j + 1] += colstart[j];
+        auto find = [&](int64_t col, int64_t row) -> const Trip* {
+            auto b = trip.begin() + colstart[col], e = trip.begin() + colstart[col + 1];
+            auto it = std::lower_bound(b, e, col * n + row, [](const Trip& x, int64_t k) { return x.key < k; });
+            return (it != e && it->key == col * n + row) ? &*it : nullptr;
         };
         for (auto& t : trip) {
             int64_t j = t.key / n, i = t.key % n;
             if (i == j) continue;
-            const Trip* o = find(i * n + j);
+            const Trip* o = find(i, j);
             double oa = o ? o->a : 0.0, oe = o ? o->e : 0.0;
             if (std::fabs(t.a - oa) > 1e-12 * amax || std::fabs(t.e - oe) > 1e-12 * emax)
                 return "analyze: E and A must be symmetric (nonsymmetric pencils are not supported by this build)";
         }
     }
 
+    phase("triplets + symmetry check");
     // ---- adjacency graph (symmetrized pattern, no diagonal) ----
     Graph g;
     g.n = n;
@@ -331,6 +366,7 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
         g.ptr.swap(nptr);
     }
 
+    phase("adjacency graph");
     // ---- nested dissection -> permutation + supernode blocks ----
     Dissector dis(g, std::max(4, opt.leaf_size));
     {
@@ -364,6 +400,7 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
     for (int32_t J = 0; J < S.nsn; ++J)
         for (int32_t c = S.sn_first[J]; c < S.sn_first[J + 1]; ++c) sn_of[c] = J;
 
+    phase("nested dissection");
     // ---- supernodal symbolic factorization ----
     S.sn_rowptr.assign(S.nsn + 1, 0);
     S.sn_parent.assign(S.nsn, -1);
@@ -403,6 +440,7 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
     for (int32_t J = 0; J < S.nsn; ++J)
         std::copy(children[J].begin(), children[J].end(), S.child_idx.begin() + S.child_ptr[J]);
 
+    phase("symbolic factorization");
     // ---- levels by height (leaves = level 0; children precede parents in the numbering) ----
     {
         S.sn_level.assign(S.nsn, 0);
@@ -463,6 +501,7 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
         }
     }
 
+    phase("levels, offsets, relmaps");
     // ---- permuted matrices: assembly scatter map (lower triangle) and full CSR ----
     {
         struct PT { int32_t r, c; double a, e; };
@@ -473,10 +512,18 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
             int64_t jo = t.key / n, io = t.key % n;
             pt.push_back({S.iperm[io], S.iperm[jo], t.a, t.e});
         }
-        std::sort(pt.begin(), pt.end(), [](const PT& x, const PT& y) { return x.r != y.r ? x.r < y.r : x.c < y.c; });
         S.csr_ptr.assign(n + 1, 0);
         for (auto& p : pt) S.csr_ptr[p.r + 1]++;
         for (int64_t i = 0; i < n; ++i) S.csr_ptr[i + 1] += S.csr_ptr[i];
+        {   // counting sort by row, then the handful of entries of every row by column
+            std::vector<PT> sorted(pt.size());
+            std::vector<int32_t> pos(S.csr_ptr.begin(), S.csr_ptr.end() - 1);
+            for (auto& p : pt) sorted[pos[p.r]++] = p;
+            pt.swap(sorted);
+            for (int64_t i = 0; i < n; ++i)
+                std::sort(pt.begin() + S.csr_ptr[i], pt.begin() + S.csr_ptr[i + 1],
+                          [](const PT& x, const PT& y) { return x.c < y.c; });
+        }
         S.csr_col.resize(pt.size());
         S.csr_a.resize(pt.size());
         S.csr_e.resize(pt.size());
@@ -502,6 +549,7 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
             S.asm_e.push_back(p.e);
         }
     }
+    phase("permuted CSR + scatter map");
     return "";
 }
 
