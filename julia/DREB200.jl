@@ -148,6 +148,18 @@ function adi_step!(ctx::Context, F::DeviceOperator, μ::Complex, R::DeviceMatrix
     V1, V2
 end
 
+# After compress! the outer factor has orthonormal columns; telling the library lets the next compress! adopt
+# them as basis vectors without re-orthogonalisation (call right before compress! on X + increments).
+hint_orthonormal!(L::DeviceMatrix) =
+    check(L.p.ctx, ccall((:dre_hint_orthonormal, LIB), Int32, (Ptr{Cvoid}, View), L.p.ctx.h, view_of(L)))
+
+# The context's CUDA stream (cudaStream_t) for stream-ordered collectives on the raw panel pointers.
+function cuda_stream(ctx::Context)
+    s = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:dre_get_stream, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx.h, s))
+    s[]
+end
+
 # Performance hint (results unchanged): the next shifts of the buffered iterator (src/shifts/helpers.jl:106-113)
 # are factored ahead on the library's side streams while the current step's sweeps / Gram / compression run.
 prefactor!(ctx::Context, μ::Complex) =

@@ -242,3 +242,28 @@ def test_rail_ros2_runs(rail371):
     assert len(sol.t) == len(sol.X) == len(sol.K) == 3
     assert sol.t[0] > sol.t[-1]
     assert all(np.isfinite(K).all() for K in sol.K)
+
+
+def test_projection_ritz_values_cholesky_reduction_matches_generalized_solver():
+    """api._pencil_eigvals (host side of the GPU path, src/shifts/projection.jl:67): the Cholesky-reduced standard
+    eigenproblem gives the same Ritz values as eigvals(At, Et) (what the reference and the oracle call), and the
+    generalized solver is used when Et is not symmetric positive definite."""
+    import scipy.linalg as sla
+
+    from dre_b200 import api
+
+    rng = np.random.default_rng(5)
+    k = 60
+    X = rng.standard_normal((k, k))
+    Et = X @ X.T / k + 0.1 * np.eye(k)
+    At = -(0.1 * rng.standard_normal((k, k)) + np.diag(np.logspace(-3, 3, k)))
+    ref = sla.eigvals(At, Et)
+    got = api._pencil_eigvals(At, Et)
+    d = np.abs(ref[:, None] - got[None, :])
+    assert np.max(d.min(axis=1) / np.abs(ref)) < 1e-9 and np.max(d.min(axis=0) / np.abs(got)) < 1e-9
+    # indefinite "mass" matrix: falls back to the generalized solver, same values as scipy
+    Et2 = Et - 2.0 * np.eye(k)
+    ref2, got2 = sla.eigvals(At, Et2), api._pencil_eigvals(At, Et2)
+    d2 = np.abs(ref2[:, None] - got2[None, :])
+    assert np.max(d2.min(axis=1) / np.abs(ref2)) < 1e-9
+    assert api._pencil_eigvals(np.zeros((0, 0)), np.zeros((0, 0))).shape == (0,)
