@@ -55,9 +55,25 @@ __host__ __device__ __forceinline__ void from_real(double v, cplx& out) { out = 
 // fragment layout (PTX ISA, mma.m8n8k4 .f64): lane l holds
 //   a = A[l/4][l%4],  b = B[l%4][l/4],  c0,c1 = C[l/4][2*(l%4) + {0,1}]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+#ifdef DRE_SIMT_EMU
+    simt::dmma884(c0, c1, a, b);
+#else
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+#endif
 }
+
+// ---- kernel launch / dynamic shared memory spelling ----
+// The kernel sources are also compiled by g++ against the host-side SIMT emulator of the CPU test tier
+// (tests/simt/stub/cuda_runtime.h, -DDRE_SIMT_EMU), which supplies its own versions of these three macros;
+// the product build sees plain CUDA.
+#define DRE_UNPAREN(...) __VA_ARGS__
+#ifndef DRE_SIMT_EMU
+#define DRE_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    DRE_UNPAREN kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define DRE_DYN_SMEM(type, name) extern __shared__ type name[]
+#define DRE_DYN_SMEM_ALIGNED(type, name) extern __shared__ __align__(16) type name[]
+#endif
 
 }  // namespace dre

@@ -17,6 +17,7 @@
 
 #include "../../include/dre_b200.h"
 #include "kernels.h"
+#include "schedule.h"
 #include "symbolic.h"
 
 using namespace dre;
@@ -154,13 +155,7 @@ struct dre_context {
     double* d_csr_a = nullptr;
     double* d_csr_e = nullptr;
     int32_t* d_level_sn = nullptr;
-    // per-level work lists (levels = heights in the supernodal tree, leaves first)
-    struct LevelWork {
-        int sn_begin = 0, sn_count = 0, smax = 0;
-        int ea_begin = 0, ea_count = 0, ea_gy = 1;
-        int l21_begin = 0, l21_count = 0;
-        int schur_begin = 0, schur_count = 0;
-    };
+    // per-level work lists (schedule.h)
     std::vector<LevelWork> levels;
     int32_t* d_ea_parents = nullptr;
     int2* d_l21_items = nullptr;
@@ -361,6 +356,11 @@ int tall_gemm(dre_context* c, double alpha, const double* X, int64_t ldx, int a,
 // ---------------------------------------------------------------------------------------------
 // numeric factorization + solve
 // ---------------------------------------------------------------------------------------------
+inline DevSchedule dev_schedule(const dre_context* c) {
+    return DevSchedule{c->levels.data(), (int)c->levels.size(), c->d_level_sn, c->d_ea_parents, c->d_l21_items,
+                       c->d_schur_items};
+}
+
 template <class T>
 int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) {
     const Symbolic& S = c->sym;
@@ -371,21 +371,8 @@ int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) 
     T* U = (T*)fs.U;
     CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), st));
     if (c->upd_elems > 0) CU(cudaMemsetAsync(U, 0, (size_t)c->upd_elems * sizeof(T), st));
-    launch_assemble<T>(c->dS, L, c->op_a, emu, st, &c->stats.kernel_launches);
-    for (int l = 0; l < S.nlevels; ++l) {
-        const dre_context::LevelWork& lw = c->levels[l];
-        if (lw.ea_count > 0)
-            launch_extend_add<T>(c->dS, c->d_ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, U, st,
-                                 &c->stats.kernel_launches);
-        launch_diag<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, L, Linv, dvec, c->d_errflag, st,
-                       &c->stats.kernel_launches);
-        if (lw.l21_count > 0)
-            launch_l21<T>(c->dS, c->d_l21_items + lw.l21_begin, lw.l21_count, L, Linv, dvec, st,
-                          &c->stats.kernel_launches);
-        if (lw.schur_count > 0)
-            launch_schur<T>(c->dS, c->d_schur_items + lw.schur_begin, lw.schur_count, L, dvec, U, st,
-                            &c->stats.kernel_launches);
-    }
+    enqueue_factor<T>(c->dS, dev_schedule(c), L, Linv, dvec, U, c->op_a, emu, c->d_errflag, st,
+                      &c->stats.kernel_launches);
     CU(cudaGetLastError());
     c->stats.factorizations++;
     c->stats.flops_factor += S.flops * (sizeof(T) == sizeof(double) ? 1.0 : 4.0);
@@ -405,17 +392,7 @@ int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs, const RhsSource& s
     const T* Linv = (const T*)fs.Linv;
     const T* dvec = (const T*)fs.dvec;
     T* tb = (T*)c->tbuf.p;
-    for (int l = 0; l < S.nlevels; ++l) {
-        const dre_context::LevelWork& lw = c->levels[l];
-        HostTrace tr("  one fwd level launch");
-        launch_fwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, lw.smax, L, Linv, W, ldw, nrhs, tb, src,
-                            c->st, &c->stats.kernel_launches);
-    }
-    for (int l = S.nlevels - 1; l >= 0; --l) {
-        const dre_context::LevelWork& lw = c->levels[l];
-        launch_bwd_level<T>(c->dS, c->d_level_sn + lw.sn_begin, lw.sn_count, lw.smax, L, Linv, dvec, W, ldw, nrhs,
-                            c->st, &c->stats.kernel_launches);
-    }
+    enqueue_sweeps<T>(c->dS, dev_schedule(c), L, Linv, dvec, W, ldw, nrhs, tb, src, c->st, &c->stats.kernel_launches);
     CU(cudaGetLastError());
     CU(cudaEventRecord(fs.released, c->st));
     fs.has_reader = true;
@@ -1021,34 +998,12 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     D.nasm = (int64_t)S.asm_dest.size(); D.asm_dest = d_asm_dest; D.asm_a = d_asm_a; D.asm_e = d_asm_e;
 
     // per-level work lists
-    c->levels.assign(S.nlevels, dre_context::LevelWork());
-    std::vector<int32_t> ea_parents;
-    std::vector<int2> l21_items;
-    std::vector<int4> schur_items;
-    for (int l = 0; l < S.nlevels; ++l) {
-        dre_context::LevelWork& lw = c->levels[l];
-        lw.sn_begin = S.level_ptr[l];
-        lw.sn_count = S.level_ptr[l + 1] - S.level_ptr[l];
-        lw.ea_begin = (int)ea_parents.size();
-        lw.l21_begin = (int)l21_items.size();
-        lw.schur_begin = (int)schur_items.size();
-        int max_f = 0;
-        for (int p = S.level_ptr[l]; p < S.level_ptr[l + 1]; ++p) {
-            const int J = S.level_sn[p];
-            const int u = S.sn_nrows(J);
-            lw.smax = std::max(lw.smax, S.sn_size(J));
-            max_f = std::max(max_f, S.front(J));
-            if (S.child_ptr[J + 1] > S.child_ptr[J]) ea_parents.push_back(J);
-            for (int sl = 0; sl * 64 < u; ++sl) l21_items.push_back(make_int2(J, sl));
-            const int nt = (u + 63) / 64;
-            for (int ti = 0; ti < nt; ++ti)
-                for (int tj = 0; tj <= ti; ++tj) schur_items.push_back(make_int4(J, ti, tj, 0));
-        }
-        lw.ea_count = (int)ea_parents.size() - lw.ea_begin;
-        lw.l21_count = (int)l21_items.size() - lw.l21_begin;
-        lw.schur_count = (int)schur_items.size() - lw.schur_begin;
-        lw.ea_gy = std::min(64, std::max(1, max_f / 8));
-    }
+    LevelLists lists;
+    build_level_lists(S, lists);
+    c->levels = lists.levels;
+    const std::vector<int32_t>& ea_parents = lists.ea_parents;
+    const std::vector<int2>& l21_items = lists.l21_items;
+    const std::vector<int4>& schur_items = lists.schur_items;
     if ((rc = upload_vec(c, ea_parents, &c->d_ea_parents))) return rc;
     if ((rc = upload_vec(c, l21_items, &c->d_l21_items))) return rc;
     if ((rc = upload_vec(c, schur_items, &c->d_schur_items))) return rc;

@@ -135,6 +135,17 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double* __restric
 // ------------------------------------------------------------------------------------------
 // cp.async helpers (LDGSTS): 16-byte (.cg) and 8-byte (.ca) global -> shared copies with zero fill
 // ------------------------------------------------------------------------------------------
+#ifdef DRE_SIMT_EMU
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    simt::cp_async(smem, gmem, 16, src_bytes);
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    simt::cp_async(smem, gmem, 8, src_bytes);
+}
+__device__ __forceinline__ void cp_async_commit() { simt::cp_async_commit(); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { simt::cp_async_wait(N); }
+#else
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
@@ -146,6 +157,7 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Gram, pipelined:  partial[split] (a x b) = sum_{rows in split} X[row][:]^T Y[row][:]
@@ -161,7 +173,7 @@ __global__ void __launch_bounds__(256) k_gram2(const double* __restrict__ X, int
                                                const double* __restrict__ Y, int64_t ldy, int b, int64_t n,
                                                double* __restrict__ partial, int tiles_b, int64_t rows_per_split,
                                                int aligned) {
-    extern __shared__ __align__(16) double g2_smem[];
+    DRE_DYN_SMEM_ALIGNED(double, g2_smem);
     constexpr int G2B = TB, G2LDB = TB + 8, G2_STAGE = G2K * (G2LDA + G2LDB), NT = TB / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ta = blockIdx.x / tiles_b, tb = blockIdx.x % tiles_b;
@@ -273,7 +285,7 @@ __global__ void __launch_bounds__(256) k_tall_gemm2(double alpha, const double* 
                                                     const double* __restrict__ W, int64_t ldw, int w_trans,
                                                     double beta, double* __restrict__ Y, int64_t ldy, int b,
                                                     int64_t n, int aligned_x, int aligned_w) {
-    extern __shared__ __align__(16) double t2_smem[];
+    DRE_DYN_SMEM_ALIGNED(double, t2_smem);
     constexpr int T2LDW = T2Cfg<T2N>::LDW, T2_STAGE = T2Cfg<T2N>::STAGE;
     constexpr int MT = T2Cfg<T2N>::MT, NT = T2Cfg<T2N>::NT, WR = T2Cfg<T2N>::WR;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -434,11 +446,12 @@ void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t l
     if (a <= 0 || b <= 0) return;
     if (a <= 16 && roww == nullptr && b >= 64) {
         dim3 grid((b + 255) / 256, plan.nsplit);
-        if (a <= 8) k_gram_skinny<8><<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, partial, plan.rows_per_split);
-        else k_gram_skinny<16><<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, partial, plan.rows_per_split);
+        if (a <= 8) DRE_LAUNCH((k_gram_skinny<8>), grid, 256, 0, st, X, ldx, a, Y, ldy, b, n, partial,
+                               plan.rows_per_split);
+        else DRE_LAUNCH((k_gram_skinny<16>), grid, 256, 0, st, X, ldx, a, Y, ldy, b, n, partial, plan.rows_per_split);
         const int64_t total = (int64_t)a * b;
         int rb = (int)std::min<int64_t>((total + 31) / 32, 148 * 8);
-        k_reduce_partials<<<rb, 256, 0, st>>>(partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
+        DRE_LAUNCH((k_reduce_partials), rb, 256, 0, st, partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
         if (launches) *launches += 2;
         return;
     }
@@ -447,7 +460,7 @@ void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t l
     if (roww) {   // weighted variant (small core products only): simple 64x64 kernel
         const int tiles_a = (a + GT - 1) / GT, tiles_b = (b + GT - 1) / GT;
         dim3 grid(tiles_a * tiles_b, plan.nsplit);
-        k_gram<<<grid, 256, 0, st>>>(X, ldx, a, Y, ldy, b, n, roww, partial, tiles_b, plan.rows_per_split);
+        DRE_LAUNCH((k_gram), grid, 256, 0, st, X, ldx, a, Y, ldy, b, n, roww, partial, tiles_b, plan.rows_per_split);
     } else {
         static bool attr_set = false;
         const int smem128 = G2ST * G2K * (G2LDA + 128 + 8) * (int)sizeof(double);
@@ -463,12 +476,13 @@ void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t l
         const int aligned = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0) &&
                             ldx % 2 == 0 && ldy % 2 == 0;
         if (tbw == 64)
-            k_gram2<64><<<grid, 256, smem64, st>>>(X, ldx, a, Y, ldy, b, n, partial, tiles_b, plan.rows_per_split, aligned);
+            DRE_LAUNCH((k_gram2<64>), grid, 256, smem64, st, X, ldx, a, Y, ldy, b, n, partial, tiles_b,
+                       plan.rows_per_split, aligned);
         else
-            k_gram2<128><<<grid, 256, smem128, st>>>(X, ldx, a, Y, ldy, b, n, partial, tiles_b, plan.rows_per_split,
-                                                      aligned);
+            DRE_LAUNCH((k_gram2<128>), grid, 256, smem128, st, X, ldx, a, Y, ldy, b, n, partial, tiles_b,
+                       plan.rows_per_split, aligned);
     }
-    k_reduce_partials<<<rb, 256, 0, st>>>(partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
+    DRE_LAUNCH((k_reduce_partials), rb, 256, 0, st, partial, plan.nsplit, a, b, out1, ld1, out2, ld2);
     if (launches) *launches += 2;
 }
 
@@ -479,7 +493,7 @@ __global__ void __launch_bounds__(256) k_tall_gemm_smallk(double alpha, const do
                                                           int a, const double* __restrict__ W, int64_t ldw,
                                                           int w_trans, double beta, double* __restrict__ Y,
                                                           int64_t ldy, int b, int64_t n, int aligned_x) {
-    extern __shared__ __align__(16) double ts_smem[];
+    DRE_DYN_SMEM_ALIGNED(double, ts_smem);
     double* Xs = ts_smem;                 // [128][TSLDX]
     double* Ws = ts_smem + T2M * TSLDX;   // [64][TSLDW]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -559,7 +573,8 @@ static void launch_tall_gemm_t(double alpha, const double* X, int64_t ldx, int a
     dim3 grid((unsigned)((n + T2M - 1) / T2M), (unsigned)((b + T2N - 1) / T2N));
     const int ax = reinterpret_cast<uintptr_t>(X) % 16 == 0 && ldx % 2 == 0;
     const int aw = reinterpret_cast<uintptr_t>(W) % 16 == 0 && ldw % 2 == 0;
-    k_tall_gemm2<T2N><<<grid, 256, smem, st>>>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, ax, aw);
+    DRE_LAUNCH((k_tall_gemm2<T2N>), grid, 256, smem, st, alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, ax,
+               aw);
 }
 
 void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const double* W, int64_t ldw,
@@ -575,7 +590,8 @@ void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const d
         }
         dim3 grid((unsigned)((n + T2M - 1) / T2M), (unsigned)((b + 63) / 64));
         const int ax = reinterpret_cast<uintptr_t>(X) % 16 == 0 && ldx % 2 == 0;
-        k_tall_gemm_smallk<<<grid, 256, smem, st>>>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, ax);
+        DRE_LAUNCH((k_tall_gemm_smallk), grid, 256, smem, st, alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n,
+                   ax);
     } else if (b <= 16) {
         launch_tall_gemm_t<16>(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, st);
     } else {
@@ -604,7 +620,7 @@ void launch_copy_scale(double* dst, int64_t ldd, const double* src, int64_t lds,
                        const double* colscale, cudaStream_t st, int64_t* launches) {
     if (n <= 0 || cols <= 0) return;
     int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
-    k_copy_scale<<<blocks, 256, 0, st>>>(dst, ldd, src, lds, n, cols, colscale);
+    DRE_LAUNCH((k_copy_scale), blocks, 256, 0, st, dst, ldd, src, lds, n, cols, colscale);
     if (launches) *launches += 1;
 }
 
@@ -631,8 +647,8 @@ void launch_colnorm2(const double* P, int64_t ldp, int64_t n, int cols, double* 
                      cudaStream_t st, int64_t* launches) {
     if (n <= 0 || cols <= 0) return;
     const int64_t rpb = (n + nblk - 1) / nblk;
-    k_colnorm2<<<nblk, 256, 0, st>>>(P, ldp, n, cols, rpb, partial);
-    k_reduce_partials<<<(cols + 31) / 32, 256, 0, st>>>(partial, nblk, 1, cols, out, cols, nullptr, 0);
+    DRE_LAUNCH((k_colnorm2), nblk, 256, 0, st, P, ldp, n, cols, rpb, partial);
+    DRE_LAUNCH((k_reduce_partials), (cols + 31) / 32, 256, 0, st, partial, nblk, 1, cols, out, cols, nullptr, 0);
     if (launches) *launches += 2;
 }
 
@@ -654,7 +670,7 @@ void launch_combine_cols(double* dst, int64_t ldd, const double* src, int64_t ld
                          const int32_t* idx2, const double* w1, const double* w2, cudaStream_t st, int64_t* launches) {
     if (n <= 0 || cols <= 0) return;
     int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
-    k_combine_cols<<<blocks, 256, 0, st>>>(dst, ldd, src, lds, n, cols, idx2, w1, w2);
+    DRE_LAUNCH((k_combine_cols), blocks, 256, 0, st, dst, ldd, src, lds, n, cols, idx2, w1, w2);
     if (launches) *launches += 1;
 }
 
@@ -675,7 +691,7 @@ void launch_axpby(double alpha, const double* X, int64_t ldx, double beta, doubl
                   int cols, cudaStream_t st, int64_t* launches) {
     if (n <= 0 || cols <= 0) return;
     int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
-    k_axpby<<<blocks, 256, 0, st>>>(alpha, X, ldx, beta, Y, ldy, n, cols);
+    DRE_LAUNCH((k_axpby), blocks, 256, 0, st, alpha, X, ldx, beta, Y, ldy, n, cols);
     if (launches) *launches += 1;
 }
 
@@ -724,7 +740,7 @@ void launch_colmajor_to_panel(double* dst, int64_t ldd, const double* src, int64
                               const int32_t* iperm, cudaStream_t st, int64_t* launches) {
     if (n <= 0 || cols <= 0) return;
     dim3 grid((unsigned)((n + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
-    k_cm2panel<<<grid, block, 0, st>>>(dst, ldd, src, lds, n, cols, iperm);
+    DRE_LAUNCH((k_cm2panel), grid, block, 0, st, dst, ldd, src, lds, n, cols, iperm);
     if (launches) *launches += 1;
 }
 
@@ -732,7 +748,7 @@ void launch_panel_to_colmajor(double* dst, int64_t ldd, const double* src, int64
                               const int32_t* iperm, cudaStream_t st, int64_t* launches) {
     if (n <= 0 || cols <= 0) return;
     dim3 grid((unsigned)((n + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
-    k_panel2cm<<<grid, block, 0, st>>>(dst, ldd, src, lds, n, cols, iperm);
+    DRE_LAUNCH((k_panel2cm), grid, block, 0, st, dst, ldd, src, lds, n, cols, iperm);
     if (launches) *launches += 1;
 }
 
@@ -742,7 +758,7 @@ void launch_panel_to_colmajor(double* dst, int64_t ldd, const double* src, int64
 __global__ void __launch_bounds__(256) k_pivchol(const double* __restrict__ G, int64_t ldg, int pb, double drop2,
                                                  double rel2, double* __restrict__ Wsel, int32_t* __restrict__ info,
                                                  double* __restrict__ dinfo) {
-    extern __shared__ double pc_smem[];
+    DRE_DYN_SMEM(double, pc_smem);
     double (*A)[65] = reinterpret_cast<double (*)[65]>(pc_smem);            // Gram matrix
     double (*C)[65] = reinterpret_cast<double (*)[65]>(pc_smem + 64 * 65);  // Cholesky factor columns
     double (*Z)[65] = A;  // inverse of the permuted triangular factor (reuses A after the factorization)
@@ -847,7 +863,7 @@ void launch_pivchol(const double* G, int64_t ldg, int pb, double drop2, double r
         cudaFuncSetAttribute(k_pivchol, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
     }
-    k_pivchol<<<1, 256, smem, st>>>(G, ldg, pb, drop2, rel2, Wsel, info, dinfo);
+    DRE_LAUNCH((k_pivchol), 1, 256, smem, st, G, ldg, pb, drop2, rel2, Wsel, info, dinfo);
     if (launches) *launches += 1;
 }
 
@@ -883,7 +899,7 @@ __global__ void __launch_bounds__(1024) k_norm_diag(const double* __restrict__ G
 
 void launch_norm_diag(const double* G, int64_t ldg, int r, const double* t, double* out, cudaStream_t st,
                       int64_t* launches) {
-    k_norm_diag<<<1, 1024, 0, st>>>(G, ldg, r, t, out);
+    DRE_LAUNCH((k_norm_diag), 1, 1024, 0, st, G, ldg, r, t, out);
     if (launches) *launches += 1;
 }
 
@@ -901,7 +917,7 @@ void launch_gather_rows(double* Wt, int64_t ldw, const double* V, int64_t ldv, c
                         int len, cudaStream_t st, int64_t* launches) {
     if (nsel <= 0 || len <= 0) return;
     int blocks = (int)std::min<int64_t>(((int64_t)nsel * len + 255) / 256, 1024);
-    k_gather_rows<<<blocks, 256, 0, st>>>(Wt, ldw, V, ldv, ids, nsel, len);
+    DRE_LAUNCH((k_gather_rows), blocks, 256, 0, st, Wt, ldw, V, ldv, ids, nsel, len);
     if (launches) *launches += 1;
 }
 
@@ -946,7 +962,7 @@ void launch_spmm(const int32_t* ptr, const int32_t* col, const double* val, int6
     if (n <= 0 || cols <= 0) return;
     int64_t blocks = (n + 7) / 8;  // 8 warps per CTA, one row per warp
     blocks = std::min<int64_t>(blocks, 148 * 32);
-    k_spmm<<<(unsigned)blocks, 256, 0, st>>>(ptr, col, val, n, alpha, X, ldx, beta, Y, ldy, cols);
+    DRE_LAUNCH((k_spmm), (unsigned)blocks, 256, 0, st, ptr, col, val, n, alpha, X, ldx, beta, Y, ldy, cols);
     if (launches) *launches += 1;
 }
 

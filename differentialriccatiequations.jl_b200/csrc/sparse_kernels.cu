@@ -171,7 +171,7 @@ template <class T>
 void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t st, int64_t* launches) {
     int blocks = (int)std::min<int64_t>((S.nasm + 255) / 256, 148 * 8);
     if (blocks < 1) blocks = 1;
-    k_assemble<T><<<blocks, 256, 0, st>>>(S.nasm, S.asm_dest, S.asm_a, S.asm_e, L, a, emu);
+    DRE_LAUNCH((k_assemble<T>), blocks, 256, 0, st, S.nasm, S.asm_dest, S.asm_a, S.asm_e, L, a, emu);
     if (launches) *launches += 1;
 }
 
@@ -443,7 +443,7 @@ void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparent
                        cudaStream_t st, int64_t* launches) {
     if (nparents <= 0) return;
     dim3 grid(nparents, gy);
-    k_extend_add<T><<<grid, 256, 0, st>>>(S, parents, L, U);
+    DRE_LAUNCH((k_extend_add<T>), grid, 256, 0, st, S, parents, L, U);
     if (launches) *launches += 1;
 }
 
@@ -451,7 +451,7 @@ template <class T>
 void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, T* L, T* Linv, T* dvec, int32_t* errflag,
                  cudaStream_t st, int64_t* launches) {
     if (nsns <= 0) return;
-    k_diag<T><<<nsns, 256, 0, st>>>(S, sns, L, Linv, dvec, errflag);
+    DRE_LAUNCH((k_diag<T>), nsns, 256, 0, st, S, sns, L, Linv, dvec, errflag);
     if (launches) *launches += 1;
 }
 
@@ -459,7 +459,7 @@ template <class T>
 void launch_l21(const DevSymbolic& S, const int2* items, int nitems, T* L, const T* Linv, const T* dvec,
                 cudaStream_t st, int64_t* launches) {
     if (nitems <= 0) return;
-    k_l21<T><<<nitems, 256, 0, st>>>(S, items, L, Linv, dvec);
+    DRE_LAUNCH((k_l21<T>), nitems, 256, 0, st, S, items, L, Linv, dvec);
     if (launches) *launches += 1;
 }
 
@@ -467,7 +467,7 @@ template <class T>
 void launch_schur(const DevSymbolic& S, const int4* items, int nitems, const T* L, const T* dvec, T* U,
                   cudaStream_t st, int64_t* launches) {
     if (nitems <= 0) return;
-    k_schur<T><<<nitems, 128, 0, st>>>(S, items, L, dvec, U);
+    DRE_LAUNCH((k_schur<T>), nitems, 128, 0, st, S, items, L, dvec, U);
     if (launches) *launches += 1;
 }
 
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(32 * NW) k_fwd(DevSymbolic S, const int32_t* _
                                              const T* __restrict__ Linv, T* W, int64_t ldw, int nrhs, T* tbuf,
                                              RhsSource src) {
     constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value;
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    DRE_DYN_SMEM_ALIGNED(unsigned char, dre_smem_raw);
     T* xs = reinterpret_cast<T*>(dre_smem_raw);   // [s8][LDB]
     const int J = sns[blockIdx.x];
     const int c0 = blockIdx.y * CW, ncw = min(CW, nrhs - c0);
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(32 * NW) k_bwd(DevSymbolic S, const int32_t* _
                                              const T* __restrict__ Linv, const T* __restrict__ dvec, T* W, int64_t ldw,
                                              int nrhs, int srows) {
     constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value;
-    extern __shared__ __align__(16) unsigned char dre_smem_raw[];
+    DRE_DYN_SMEM_ALIGNED(unsigned char, dre_smem_raw);
     T* xs = reinterpret_cast<T*>(dre_smem_raw);   // [srows][LDB]: z
     T* xt = xs + (size_t)srows * LDB;             // [64][LDB]: tile of x at the structure rows
     const int J = sns[blockIdx.x];
@@ -711,7 +711,8 @@ static void launch_fwd_t(const DevSymbolic& S, const int32_t* sns, int nsns, int
     set_sweep_attrs<T, NT, Q, NW>();
     const int cw = NT * MM<T>::CPN;
     dim3 grid(nsns, (nrhs + cw - 1) / cw);
-    k_fwd<T, NT, Q, NW><<<grid, 32 * NW, fwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, W, ldw, nrhs, tbuf, src);
+    DRE_LAUNCH((k_fwd<T, NT, Q, NW>), grid, 32 * NW, (fwd_smem<T, NT>(smax)), st, S, sns, L, Linv, W, ldw, nrhs, tbuf,
+               src);
 }
 
 template <class T, int NT, int Q, int NW>
@@ -720,8 +721,8 @@ static void launch_bwd_t(const DevSymbolic& S, const int32_t* sns, int nsns, int
     set_sweep_attrs<T, NT, Q, NW>();
     const int cw = NT * MM<T>::CPN;
     dim3 grid(nsns, (nrhs + cw - 1) / cw);
-    k_bwd<T, NT, Q, NW><<<grid, 32 * NW, bwd_smem<T, NT>(smax), st>>>(S, sns, L, Linv, dvec, W, ldw, nrhs,
-                                                                      (smax + 7) & ~7);
+    DRE_LAUNCH((k_bwd<T, NT, Q, NW>), grid, 32 * NW, (bwd_smem<T, NT>(smax)), st, S, sns, L, Linv, dvec, W, ldw, nrhs,
+               (smax + 7) & ~7);
 }
 
 template <class T>
@@ -778,7 +779,7 @@ void launch_load_rhs(T* W, int64_t ldw, const double* R, int64_t ldr, int r, con
                      int64_t n, cudaStream_t st, int64_t* launches) {
     if (n <= 0 || r + m <= 0) return;
     int blocks = (int)std::min<int64_t>((n * (r + m) + 255) / 256, 148 * 16);
-    k_load_rhs<T><<<blocks, 256, 0, st>>>(W, ldw, R, ldr, r, Vt, ldv, m, n);
+    DRE_LAUNCH((k_load_rhs<T>), blocks, 256, 0, st, W, ldw, R, ldr, r, Vt, ldv, m, n);
     if (launches) *launches += 1;
 }
 
@@ -849,7 +850,7 @@ template <class T>
 void launch_smw_core(const T* BtW, int64_t ldb, int m, int r, double alpha, T* Sol, int32_t* errflag,
                      cudaStream_t st, int64_t* launches) {
     if (m <= 0 || r <= 0) return;
-    k_smw_core<T><<<1, 256, 0, st>>>(BtW, ldb, m, r, alpha, Sol, errflag);
+    DRE_LAUNCH((k_smw_core<T>), 1, 256, 0, st, BtW, ldb, m, r, alpha, Sol, errflag);
     if (launches) *launches += 1;
 }
 
@@ -895,8 +896,8 @@ void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int m
                       int64_t ld1, double* V2, int64_t ld2, int64_t n, cudaStream_t st, int64_t* launches) {
     if (n <= 0 || r <= 0) return;
     int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 16);
-    if (m <= 8) k_smw_apply<T, 8><<<blocks, 256, 0, st>>>(W, ldw, r, m, Sol, mode, d, V1, ld1, V2, ld2, n);
-    else k_smw_apply<T, 32><<<blocks, 256, 0, st>>>(W, ldw, r, m, Sol, mode, d, V1, ld1, V2, ld2, n);
+    if (m <= 8) DRE_LAUNCH((k_smw_apply<T, 8>), blocks, 256, 0, st, W, ldw, r, m, Sol, mode, d, V1, ld1, V2, ld2, n);
+    else DRE_LAUNCH((k_smw_apply<T, 32>), blocks, 256, 0, st, W, ldw, r, m, Sol, mode, d, V1, ld1, V2, ld2, n);
     if (launches) *launches += 1;
 }
 
