@@ -160,6 +160,12 @@ struct dre_context {
     int32_t* d_ea_parents = nullptr;
     int2* d_l21_items = nullptr;
     int4* d_schur_items = nullptr;
+    // Row-split sweeps (sparse_kernels.cu "sweep v2"): opt-in with DRE_SWEEP2=1 until measured on the GPU.
+    // The factorization then leaves M21 = L21 Linv in the panels, so the flag is fixed per context.
+    bool sweep2 = false;
+    int2* d_fwd2_items = nullptr;
+    int2* d_bwd2_items = nullptr;
+    DBuf<unsigned char> Ybuf;
     int64_t linv_elems = 0, upd_elems = 0;
 
     // factor storage (sized for complex, reused for real)
@@ -216,7 +222,7 @@ namespace {
 
 template <class F>
 void for_each_workspace(dre_context* c, F f) {
-    f(c->tbuf); f(c->Wbuf); f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
+    f(c->tbuf); f(c->Wbuf); f(c->Ybuf); f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
     f(c->wsel); f(c->wsel2); f(c->small); f(c->stage); f(c->qws); f(c->pws); f(c->qtmp); f(c->rt); f(c->rt2);
     f(c->tmp_panel); f(c->evals); f(c->cnorm); f(c->syevd_work); f(c->ibuf);
 }
@@ -358,7 +364,7 @@ int tall_gemm(dre_context* c, double alpha, const double* X, int64_t ldx, int a,
 // ---------------------------------------------------------------------------------------------
 inline DevSchedule dev_schedule(const dre_context* c) {
     return DevSchedule{c->levels.data(), (int)c->levels.size(), c->d_level_sn, c->d_ea_parents, c->d_l21_items,
-                       c->d_schur_items};
+                       c->d_schur_items, c->d_fwd2_items, c->d_bwd2_items};
 }
 
 template <class T>
@@ -372,7 +378,7 @@ int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) 
     CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), st));
     if (c->upd_elems > 0) CU(cudaMemsetAsync(U, 0, (size_t)c->upd_elems * sizeof(T), st));
     enqueue_factor<T>(c->dS, dev_schedule(c), L, Linv, dvec, U, c->op_a, emu, c->d_errflag, st,
-                      &c->stats.kernel_launches);
+                      &c->stats.kernel_launches, c->sweep2);
     CU(cudaGetLastError());
     c->stats.factorizations++;
     c->stats.flops_factor += S.flops * (sizeof(T) == sizeof(double) ? 1.0 : 4.0);
@@ -392,7 +398,14 @@ int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs, const RhsSource& s
     const T* Linv = (const T*)fs.Linv;
     const T* dvec = (const T*)fs.dvec;
     T* tb = (T*)c->tbuf.p;
-    enqueue_sweeps<T>(c->dS, dev_schedule(c), L, Linv, dvec, W, ldw, nrhs, tb, src, c->st, &c->stats.kernel_launches);
+    if (c->sweep2) {
+        CU(c->Ybuf.ensure((size_t)S.n * ldw * sizeof(T)));
+        enqueue_sweeps2<T>(c->dS, dev_schedule(c), L, Linv, dvec, W, (T*)c->Ybuf.p, ldw, nrhs, tb, src, c->st,
+                           &c->stats.kernel_launches);
+    } else {
+        enqueue_sweeps<T>(c->dS, dev_schedule(c), L, Linv, dvec, W, ldw, nrhs, tb, src, c->st,
+                          &c->stats.kernel_launches);
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(fs.released, c->st));
     fs.has_reader = true;
@@ -829,6 +842,7 @@ int32_t dre_create(int32_t device, dre_context** out) {
     if (e != cudaSuccess) return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
     if (prop.major < 10) return bail("libdre_b200 is built for sm_100a (B200) only");
     c->sm_count = prop.multiProcessorCount;
+    if (const char* ev = getenv("DRE_SWEEP2")) c->sweep2 = atoi(ev) != 0;
     e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     for (auto& fs : c->slot) {
@@ -1007,6 +1021,8 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     if ((rc = upload_vec(c, ea_parents, &c->d_ea_parents))) return rc;
     if ((rc = upload_vec(c, l21_items, &c->d_l21_items))) return rc;
     if ((rc = upload_vec(c, schur_items, &c->d_schur_items))) return rc;
+    if ((rc = upload_vec(c, lists.fwd2_items, &c->d_fwd2_items))) return rc;
+    if ((rc = upload_vec(c, lists.bwd2_items, &c->d_bwd2_items))) return rc;
 
     // factor storage, sized for complex
     for (auto& fs : c->slot) {

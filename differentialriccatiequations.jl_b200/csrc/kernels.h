@@ -131,6 +131,20 @@ template <class T>
 void launch_bwd_level(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, const T* L, const T* Linv,
                       const T* dvec, T* W, int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches);
 
+// ---- row-split sweeps (sweep v2): see the comment block in sparse_kernels.cu ----
+// M21 = L21 Linv in place; items: (J, 64-row slab) as for launch_l21, after launch_schur of the level
+template <class T>
+void launch_m21(const DevSymbolic& S, const int2* items, int nitems, T* L, const T* Linv, cudaStream_t st,
+                int64_t* launches);
+// items: (J, row block of 8*q strips) from schedule.h; q in {1, 3} forward, {1, 2} backward
+template <class T>
+void launch_fwd2_level(const DevSymbolic& S, const int2* items, int nitems, int q, int smax, const T* L, const T* Linv,
+                       const T* dvec, T* Y, int64_t ldw, int nrhs, T* tbuf, const RhsSource& src, int has_children,
+                       cudaStream_t st, int64_t* launches);
+template <class T>
+void launch_bwd2_level(const DevSymbolic& S, const int2* items, int nitems, int q, int smax, const T* L, const T* Linv,
+                       const T* Y, T* W, int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches);
+
 // W[:, 0:r] = R, W[:, r:r+m] = Vt   (real -> T)
 template <class T>
 void launch_load_rhs(T* W, int64_t ldw, const double* R, int64_t ldr, int r, const double* Vt, int64_t ldv, int m,

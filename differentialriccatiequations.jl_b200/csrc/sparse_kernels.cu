@@ -901,6 +901,313 @@ void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int m
     if (launches) *launches += 1;
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-split sweeps ("sweep v2", DRE_SWEEP2=1).
+// The per-level sweeps above give one CTA all rows of a supernode and run two dependent phases
+// (y = Linv x, then t -= L21 y), so the few fat supernodes near the root of the tree occupy a handful of SMs for
+// a long dependent chain.  With  M21 = L21 Linv  (k_m21, after the Schur complement of the level, in place
+// in the panel) both products act on the same vector,
+//   forward : [ y' ; t ] = [ D^-1 Linv ; -M21 ] (b + children)   (+ children's contributions to t)
+//   backward: x = Linv' y' - M21' x_struct,
+// every 8-row strip is independent, and a supernode's strips are spread over several CTAs (items (J, rb)).
+// The forward sweep writes y' into a second block Y (the backward sweep of another row block of the same
+// supernode must still find y' after this one has written its x into W).
+// ------------------------------------------------------------------------------------------
+
+// M21 = L21 Linv, in place.  CTA = (supernode, 64-row slab of L21), warp = 8 rows x all s columns, column blocks
+// ascending (block c only reads columns >= c of the warp's own rows).
+template <class T>
+__global__ void __launch_bounds__(256) k_m21(DevSymbolic S, const int2* __restrict__ items, T* L, const T* Linv) {
+    constexpr int NT = 4, CPN = MM<T>::CPN, PW = NT * CPN;
+    const int2 item = items[blockIdx.x];
+    const int J = item.x;
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u;
+    T* P = L + S.panel_off[J];
+    const T* LI = Linv + S.linv_off[J];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = item.y * 64 + warp * 8;
+    if (r0 >= u) return;
+    const int row = r0 + (lane >> 2), bc = MM<T>::bcol(lane);
+    const T* Prow = P + (s + row);
+    for (int c0 = 0; c0 < s; c0 += PW) {
+        double acc[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        strip_mma<T, NT>(acc, c0, s, lane,
+                         [&](int k) { return (row < u && k < s) ? Prow[(int64_t)k * f] : zero<T>(); },
+                         [&](int k, int nt) {
+                             const int col = c0 + nt * CPN + bc;
+                             return (col < s && k < s) ? LI[(int64_t)k + (int64_t)col * s] : zero<T>();
+                         });
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+            MM<T>::each(acc[nt], lane, [&](int c, T v) {
+                const int col = c0 + nt * CPN + c;
+                if (row < u && col < s) P[(int64_t)(s + row) + (int64_t)col * f] = v;
+            });
+    }
+}
+
+template <class T>
+void launch_m21(const DevSymbolic& S, const int2* items, int nitems, T* L, const T* Linv, cudaStream_t st,
+                int64_t* launches) {
+    if (nitems <= 0) return;
+    DRE_LAUNCH((k_m21<T>), nitems, 256, 0, st, S, items, L, Linv);
+    if (launches) *launches += 1;
+}
+
+// strips of supernode J: sy = ceil(s/8) strips of y rows, then ceil(u/8) strips of update rows
+// CTA = (item (J, rb), chunk of CW right-hand sides); 8 warps x Q strips = strips [rb*8Q, (rb+1)*8Q)
+template <class T, int NT, int Q>
+__global__ void __launch_bounds__(256) k_fwd2(DevSymbolic S, const int2* __restrict__ items, const T* __restrict__ L,
+                                              const T* __restrict__ Linv, const T* __restrict__ dvec, T* Y, int64_t ldw,
+                                              int nrhs, T* tbuf, RhsSource src, int srows, int has_children) {
+    constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value, NW = 8, NS = NW * Q;
+    DRE_DYN_SMEM_ALIGNED(unsigned char, dre_smem_raw);
+    T* xs = reinterpret_cast<T*>(dre_smem_raw);   // [srows][LDB]: x = b + children
+    T* ts = xs + (size_t)srows * LDB;             // [8*NS][LDB]: children's contributions to this block's update rows
+    const int2 item = items[blockIdx.x];
+    const int J = item.x;
+    const int c0 = blockIdx.y * CW, ncw = min(CW, nrhs - c0);
+    const int first = S.sn_first[J];
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u, s8 = (s + 7) & ~7, sy = s8 >> 3;
+    const int strip0 = item.y * NS;                         // first strip of this block
+    const int t0 = max(0, strip0 - sy) * 8;                 // first update row covered by this block
+    const int t1 = min(u, max(0, strip0 + NS - sy) * 8);    // one past the last
+    const T* P = L + S.panel_off[J];
+    const T* LI = Linv + S.linv_off[J];
+    T* tJ = tbuf + S.rhs_off[J] * ldw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, bc = MM<T>::bcol(lane);
+
+    for (int idx = tid; idx < s8 * CW; idx += 256) {
+        const int i = idx / CW, cc = idx - i * CW;
+        T v = zero<T>();
+        if (i < s && cc < ncw) {
+            const int col = c0 + cc;
+            const int64_t row = first + i;
+            from_real(col < src.r ? src.R[row * src.ldr + col] : src.Vt[row * src.ldv + (col - src.r)], v);
+        }
+        xs[i * LDB + cc] = v;
+    }
+    if (has_children) {
+        for (int idx = tid; idx < 8 * NS * CW; idx += 256) {
+            const int i = idx / CW, cc = idx - i * CW;
+            ts[i * LDB + cc] = zero<T>();
+        }
+        __syncthreads();
+        for (int ci = S.child_ptr[J]; ci < S.child_ptr[J + 1]; ++ci) {
+            const int c = S.child_idx[ci];
+            const int uc = sn_u(S, c);
+            const int32_t* rel = S.relmap + S.sn_rowptr[c];
+            const T* tch = tbuf + S.rhs_off[c] * ldw;
+            for (int idx = tid; idx < uc * ncw; idx += 256) {
+                const int cc = idx / uc, i = idx - cc * uc;
+                const int pr = rel[i];
+                if (pr < s) {
+                    T* t = xs + pr * LDB + cc;
+                    *t = add(*t, tch[(int64_t)(c0 + cc) * uc + i]);
+                } else if (pr - s >= t0 && pr - s < t1) {
+                    T* t = ts + (pr - s - t0) * LDB + cc;
+                    *t = add(*t, tch[(int64_t)(c0 + cc) * uc + i]);
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int strip = strip0 + warp + NW * q;
+        double acc[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        if (strip < sy) {
+            // y' = D^-1 Linv x (lower triangular)
+            const int i0 = strip * 8, row = i0 + r;
+            const T* Lrow = LI + row;
+            strip_mma<T, NT>(acc, 0, min(i0 + 8, s), lane,
+                             [&](int k) { return (row < s && k < s) ? Lrow[(int64_t)k * s] : zero<T>(); },
+                             [&](int k, int nt) { return xs[k * LDB + nt * CPN + bc]; });
+            if (row < s) {
+                const T rd = recip(dvec[first + row]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    MM<T>::each(acc[nt], lane, [&](int c, T v) {
+                        const int col = nt * CPN + c;
+                        if (col < ncw) Y[(int64_t)(first + row) * ldw + c0 + col] = mul(v, rd);
+                    });
+            }
+        } else {
+            // t = children - M21 x
+            const int i0 = (strip - sy) * 8, row = i0 + r;
+            if (i0 < u) {
+                const T* Lrow = P + (s + row);
+                strip_mma<T, NT>(acc, 0, s, lane,
+                                 [&](int k) { return (row < u && k < s) ? Lrow[(int64_t)k * f] : zero<T>(); },
+                                 [&](int k, int nt) { return xs[k * LDB + nt * CPN + bc]; });
+                if (row < u) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+                        MM<T>::each(acc[nt], lane, [&](int c, T v) {
+                            const int col = nt * CPN + c;
+                            if (col < ncw) {
+                                const T base = has_children ? ts[(row - t0) * LDB + col] : zero<T>();
+                                tJ[(int64_t)(c0 + col) * u + row] = sub(base, v);
+                            }
+                        });
+                }
+            }
+        }
+    }
+}
+
+// CTA = (item (J, rb), chunk): strips [rb*8Q, (rb+1)*8Q) of the s rows of supernode J
+template <class T, int NT, int Q>
+__global__ void __launch_bounds__(256) k_bwd2(DevSymbolic S, const int2* __restrict__ items, const T* __restrict__ L,
+                                              const T* __restrict__ Linv, const T* __restrict__ Y, T* W, int64_t ldw,
+                                              int nrhs, int srows) {
+    constexpr int CPN = MM<T>::CPN, CW = NT * CPN, LDB = RhsLd<T, CW>::value, NW = 8, NS = NW * Q;
+    DRE_DYN_SMEM_ALIGNED(unsigned char, dre_smem_raw);
+    T* xs = reinterpret_cast<T*>(dre_smem_raw);   // [srows][LDB]: y' (rows >= the first strip of this block)
+    T* xt = xs + (size_t)srows * LDB;             // [64][LDB]: tile of x at the structure rows
+    const int2 item = items[blockIdx.x];
+    const int J = item.x;
+    const int c0 = blockIdx.y * CW, ncw = min(CW, nrhs - c0);
+    const int first = S.sn_first[J];
+    const int s = sn_s(S, J), u = sn_u(S, J), f = s + u, s8 = (s + 7) & ~7;
+    const int strip0 = item.y * NS;
+    const T* P = L + S.panel_off[J];
+    const T* LI = Linv + S.linv_off[J];
+    const int32_t* rows = S.sn_rows + S.sn_rowptr[J];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, bc = MM<T>::bcol(lane);
+
+    double acc[Q][NT][2];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
+    // y' rows [8*strip0, s) (the upper-triangular product of a strip only needs the rows below its first one)
+    for (int idx = tid + strip0 * 8 * CW; idx < s8 * CW; idx += 256) {
+        const int i = idx / CW, cc = idx - i * CW;
+        xs[i * LDB + cc] = (i < s && cc < ncw) ? Y[(int64_t)(first + i) * ldw + c0 + cc] : zero<T>();
+    }
+    // acc = M21' x_struct, 64 structure rows at a time
+    for (int r0 = 0; r0 < u; r0 += 64) {
+        if (r0) __syncthreads();
+        for (int idx = tid; idx < 64 * CW; idx += 256) {
+            const int i = idx / CW, cc = idx - i * CW;
+            xt[i * LDB + cc] = (r0 + i < u && cc < ncw) ? W[(int64_t)rows[r0 + i] * ldw + c0 + cc] : zero<T>();
+        }
+        __syncthreads();
+        const int kt = min(64, u - r0);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int i0 = (strip0 + warp + NW * q) * 8;
+            if (i0 < s) {
+                const int col = i0 + r;   // output row = column of M21
+                const T* Lcol = P + (s + r0) + (int64_t)col * f;
+                strip_mma<T, NT>(acc[q], 0, kt, lane,
+                                 [&](int k) { return (col < s && k < kt) ? Lcol[k] : zero<T>(); },
+                                 [&](int k, int nt) { return xt[k * LDB + nt * CPN + bc]; });
+            }
+        }
+    }
+    __syncthreads();
+    // x = Linv' y' - acc
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int i0 = (strip0 + warp + NW * q) * 8;
+        if (i0 < s) {
+            const int row = i0 + r;
+            const T* Lcol = LI + (int64_t)row * s;
+            double a1[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) a1[nt][0] = a1[nt][1] = 0.0;
+            strip_mma<T, NT>(a1, i0, s, lane,
+                             [&](int k) { return (row < s && k < s) ? Lcol[k] : zero<T>(); },
+                             [&](int k, int nt) { return xs[k * LDB + nt * CPN + bc]; });
+            if (row < s) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    double d2[2] = {a1[nt][0] - acc[q][nt][0], a1[nt][1] - acc[q][nt][1]};
+                    MM<T>::each(d2, lane, [&](int c, T v) {
+                        const int col = nt * CPN + c;
+                        if (col < ncw) W[(int64_t)(first + row) * ldw + c0 + col] = v;
+                    });
+                }
+            }
+        }
+    }
+}
+
+template <class T, int NT, int Q>
+static void launch_fwd2_t(const DevSymbolic& S, const int2* items, int nitems, int smax, const T* L, const T* Linv,
+                          const T* dvec, T* Y, int64_t ldw, int nrhs, T* tbuf, const RhsSource& src, int has_children,
+                          cudaStream_t st) {
+    constexpr int LDB = RhsLd<T, NT * MM<T>::CPN>::value;
+    const int srows = (smax + 7) & ~7;
+    const int smem = (int)sizeof(T) * (srows + (has_children ? 64 * Q : 0)) * LDB;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(k_fwd2<T, NT, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        smem_set = smem;
+    }
+    const int cw = NT * MM<T>::CPN;
+    dim3 grid(nitems, (nrhs + cw - 1) / cw);
+    DRE_LAUNCH((k_fwd2<T, NT, Q>), grid, 256, smem, st, S, items, L, Linv, dvec, Y, ldw, nrhs, tbuf, src, srows,
+               has_children);
+}
+
+template <class T, int NT, int Q>
+static void launch_bwd2_t(const DevSymbolic& S, const int2* items, int nitems, int smax, const T* L, const T* Linv,
+                          const T* Y, T* W, int64_t ldw, int nrhs, cudaStream_t st) {
+    constexpr int LDB = RhsLd<T, NT * MM<T>::CPN>::value;
+    const int srows = (smax + 7) & ~7;
+    const int smem = (int)sizeof(T) * (srows + 64) * LDB;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(k_bwd2<T, NT, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        smem_set = smem;
+    }
+    const int cw = NT * MM<T>::CPN;
+    dim3 grid(nitems, (nrhs + cw - 1) / cw);
+    DRE_LAUNCH((k_bwd2<T, NT, Q>), grid, 256, smem, st, S, items, L, Linv, Y, W, ldw, nrhs, srows);
+}
+
+// q = strips per warp the item list was built for (schedule.h: Sweep2Level), wide = 8-tile chunks
+template <class T>
+void launch_fwd2_level(const DevSymbolic& S, const int2* items, int nitems, int q, int smax, const T* L, const T* Linv,
+                       const T* dvec, T* Y, int64_t ldw, int nrhs, T* tbuf, const RhsSource& src, int has_children,
+                       cudaStream_t st, int64_t* launches) {
+    if (nitems <= 0 || nrhs <= 0) return;
+    const int cpn = MM<T>::CPN;
+    const bool nt4 = q == 3 || (int64_t)nitems * ((nrhs + 4 * cpn - 1) / (4 * cpn)) >= 148;
+#define DRE_FWD2(NT_, Q_) \
+    launch_fwd2_t<T, NT_, Q_>(S, items, nitems, smax, L, Linv, dvec, Y, ldw, nrhs, tbuf, src, has_children, st)
+    if (q == 3) DRE_FWD2(4, 3);
+    else if (nt4) DRE_FWD2(4, 1);
+    else DRE_FWD2(2, 1);
+#undef DRE_FWD2
+    if (launches) *launches += 1;
+}
+
+template <class T>
+void launch_bwd2_level(const DevSymbolic& S, const int2* items, int nitems, int q, int smax, const T* L, const T* Linv,
+                       const T* Y, T* W, int64_t ldw, int nrhs, cudaStream_t st, int64_t* launches) {
+    if (nitems <= 0 || nrhs <= 0) return;
+    const int cpn = MM<T>::CPN;
+    const bool nt4 = q == 2 || (int64_t)nitems * ((nrhs + 4 * cpn - 1) / (4 * cpn)) >= 148;
+#define DRE_BWD2(NT_, Q_) launch_bwd2_t<T, NT_, Q_>(S, items, nitems, smax, L, Linv, Y, W, ldw, nrhs, st)
+    if (q == 2) DRE_BWD2(4, 2);
+    else if (nt4) DRE_BWD2(4, 1);
+    else DRE_BWD2(2, 1);
+#undef DRE_BWD2
+    if (launches) *launches += 1;
+}
+
 // ---- explicit instantiations ----
 #define DRE_INST(T)                                                                                                  \
     template void launch_assemble<T>(const DevSymbolic&, T*, double, T, cudaStream_t, int64_t*);                     \
@@ -920,7 +1227,12 @@ void launch_smw_apply(const T* W, int64_t ldw, int r, int m, const T* Sol, int m
                                      cudaStream_t, int64_t*);                                                        \
     template void launch_smw_core<T>(const T*, int64_t, int, int, double, T*, int32_t*, cudaStream_t, int64_t*);     \
     template void launch_smw_apply<T>(const T*, int64_t, int, int, const T*, int, double, double*, int64_t, double*, \
-                                      int64_t, int64_t, cudaStream_t, int64_t*);
+                                      int64_t, int64_t, cudaStream_t, int64_t*);                                     \
+    template void launch_m21<T>(const DevSymbolic&, const int2*, int, T*, const T*, cudaStream_t, int64_t*);         \
+    template void launch_fwd2_level<T>(const DevSymbolic&, const int2*, int, int, int, const T*, const T*, const T*, \
+                                       T*, int64_t, int, T*, const RhsSource&, int, cudaStream_t, int64_t*);         \
+    template void launch_bwd2_level<T>(const DevSymbolic&, const int2*, int, int, int, const T*, const T*, const T*, \
+                                       T*, int64_t, int, cudaStream_t, int64_t*);
 DRE_INST(double)
 DRE_INST(cplx)
 

@@ -29,10 +29,10 @@ class Sym:
         return int(self.sn_rowptr[J + 1] - self.sn_rowptr[J])
 
 
-def factor(S: Sym, a, emu, dtype):
+def factor(S: Sym, a, emu, dtype, m21=False):
     """Returns (L storage, Linv dict, dvec) exactly as the kernels produce them: per level (leaves first)
     extend-add, LDL^T of the dense s x s diagonal block, explicit inverse of its unit-lower factor,
-    L21 = A21 Linv' D^-1, U -= L21 D L21'."""
+    L21 = A21 Linv' D^-1, U -= L21 D L21'.  m21: the panels end up holding M21 = L21 Linv (row-split sweeps)."""
     L = np.zeros(S.info["nnz_L"], dtype=dtype)
     np.add.at(L, S.asm_dest, a * S.asm_a + emu * S.asm_e)  # duplicates cannot occur; add.at == assignment
     Linv, U = {}, {}
@@ -85,6 +85,8 @@ def factor(S: Sym, a, emu, dtype):
             if u:
                 P[s:, :] = (P[s:, :] @ Linv[J].T) / d
                 UJ -= np.tril((P[s:, :] * d) @ P[s:, :].T)
+                if m21:
+                    P[s:, :] = P[s:, :] @ Linv[J]
             U[J] = UJ
     return L, Linv, dvec
 

@@ -4,6 +4,7 @@ device code does; `perm[new] = old` converts."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -19,13 +20,14 @@ _lp = C.POINTER(C.c_int64)
 def lib():
     global _lib
     if _lib is None:
-        _lib = C.CDLL(build_emu.build())
+        # DRE_EMU_LIB: an alternative build of the same sources (e.g. with -fsanitize=address, see tests/simt/README.md)
+        _lib = C.CDLL(os.environ.get("DRE_EMU_LIB") or build_emu.build())
         _lib.emu_open.argtypes = [C.c_int64, _lp, _lp, _dp, _lp, _lp, _dp, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_void_p)]
         _lib.emu_close.argtypes = [C.c_void_p]
         _lib.emu_sizes.argtypes = [C.c_void_p, _lp]
         _lib.emu_perm.argtypes = [C.c_void_p, _ip]
-        _lib.emu_factor.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        _lib.emu_factor.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         _lib.emu_get.argtypes = [C.c_void_p, C.c_int, _dp]
         _lib.emu_sweeps.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int, _dp, C.c_int64, C.c_int, _dp, C.c_int64]
         _lib.emu_smw.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, _dp, C.c_int64, C.c_int, C.c_double,
@@ -80,9 +82,10 @@ class Solver:
             lib().emu_close(self.h)
             self.h = None
 
-    def factor(self, a, emu):
+    def factor(self, a, emu, m21=False):
+        """m21: leave M21 = L21 Linv in the panels; sweeps() then runs the row-split kernels (sweep v2)."""
         self.cplx = isinstance(emu, complex)
-        return lib().emu_factor(self.h, int(self.cplx), float(a), float(np.real(emu)), float(np.imag(emu)))
+        return lib().emu_factor(self.h, int(self.cplx), float(a), float(np.real(emu)), float(np.imag(emu)), int(m21))
 
     def get(self, what):
         cnt = {"L": self.sizes["nnz_L"], "Linv": self.sizes["linv_elems"], "dvec": self.n}[what]

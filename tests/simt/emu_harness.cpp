@@ -25,12 +25,14 @@ struct Emu {
     std::vector<double> L, Linv, dvec, U;   // sized for complex
     int32_t errflag = 0;
     int tw = 1;
+    bool m21 = false;   // panels hold M21 = L21 Linv (row-split sweeps)
     std::string err;
 };
 
 DevSchedule schedule_of(const Emu* e) {
     return DevSchedule{e->lists.levels.data(), (int)e->lists.levels.size(), e->S.level_sn.data(),
-                       e->lists.ea_parents.data(), e->lists.l21_items.data(), e->lists.schur_items.data()};
+                       e->lists.ea_parents.data(), e->lists.l21_items.data(), e->lists.schur_items.data(),
+                       e->lists.fwd2_items.data(), e->lists.bwd2_items.data()};
 }
 
 }  // namespace
@@ -82,7 +84,7 @@ EMU_API void emu_perm(void* h, int32_t* perm) {
 }
 
 template <class T>
-static int factor_t(Emu* e, double a, T emu) {
+static int factor_t(Emu* e, double a, T emu, bool m21) {
     const Symbolic& S = e->S;
     T* L = (T*)e->L.data();
     T* U = (T*)e->U.data();
@@ -94,14 +96,15 @@ static int factor_t(Emu* e, double a, T emu) {
     e->errflag = 0;
     int64_t launches = 0;
     enqueue_factor<T>(e->dS, schedule_of(e), L, (T*)e->Linv.data(), (T*)e->dvec.data(), U, a, emu, &e->errflag, nullptr,
-                      &launches);
+                      &launches, m21);
     e->tw = (int)(sizeof(T) / sizeof(double));
+    e->m21 = m21;
     return e->errflag;
 }
 
-EMU_API int emu_factor(void* h, int is_cplx, double a, double emu_re, double emu_im) {
+EMU_API int emu_factor(void* h, int is_cplx, double a, double emu_re, double emu_im, int m21) {
     Emu* e = (Emu*)h;
-    return is_cplx ? factor_t<cplx>(e, a, mk(emu_re, emu_im)) : factor_t<double>(e, a, emu_re);
+    return is_cplx ? factor_t<cplx>(e, a, mk(emu_re, emu_im), m21 != 0) : factor_t<double>(e, a, emu_re, m21 != 0);
 }
 
 // what: 0 = L (nnz_L), 1 = Linv (linv_elems), 2 = dvec (n); tw doubles per element
@@ -113,6 +116,25 @@ EMU_API void emu_get(void* h, int what, double* buf) {
     memcpy(buf, v.data(), sizeof(double) * (size_t)cnt * e->tw);
 }
 
+template <class T>
+static void sweeps_t(Emu* e, const RhsSource& src, T* W, int64_t ldw, int nrhs, int64_t* launches) {
+    const Symbolic& S = e->S;
+    std::vector<T> tbuf((size_t)std::max<int64_t>(S.sum_u, 1) * ldw);
+    memset((void*)tbuf.data(), 0xFF, tbuf.size() * sizeof(T));
+    memset((void*)W, 0xFF, sizeof(T) * (size_t)S.n * ldw);
+    const T* L = (const T*)e->L.data();
+    const T* Linv = (const T*)e->Linv.data();
+    const T* dvec = (const T*)e->dvec.data();
+    if (e->m21) {
+        std::vector<T> Y((size_t)S.n * ldw);
+        memset((void*)Y.data(), 0xFF, Y.size() * sizeof(T));
+        enqueue_sweeps2<T>(e->dS, schedule_of(e), L, Linv, dvec, W, Y.data(), ldw, nrhs, tbuf.data(), src, nullptr,
+                           launches);
+    } else {
+        enqueue_sweeps<T>(e->dS, schedule_of(e), L, Linv, dvec, W, ldw, nrhs, tbuf.data(), src, nullptr, launches);
+    }
+}
+
 // Block solve of the current factorization.  R (n x r, row-major ld ldr) and Vt (n x m, row-major ld ldv) are in
 // SOLVER ordering; W (n x ldw elements of tw doubles) receives the solution of all r + m columns.
 EMU_API int emu_sweeps(void* h, const double* R, int64_t ldr, int r, const double* Vt, int64_t ldv, int m, double* W,
@@ -122,19 +144,8 @@ EMU_API int emu_sweeps(void* h, const double* R, int64_t ldr, int r, const doubl
     const RhsSource src{R, ldr, r, m ? Vt : nullptr, m ? ldv : 0};
     const int nrhs = r + m;
     int64_t launches = 0;
-    if (e->tw == 1) {
-        std::vector<double> tbuf((size_t)std::max<int64_t>(S.sum_u, 1) * ldw);
-        memset(tbuf.data(), 0xFF, tbuf.size() * sizeof(double));
-        memset(W, 0xFF, sizeof(double) * (size_t)S.n * ldw);
-        enqueue_sweeps<double>(e->dS, schedule_of(e), e->L.data(), e->Linv.data(), e->dvec.data(), W, ldw, nrhs,
-                               tbuf.data(), src, nullptr, &launches);
-    } else {
-        std::vector<cplx> tbuf((size_t)std::max<int64_t>(S.sum_u, 1) * ldw);
-        memset(tbuf.data(), 0xFF, tbuf.size() * sizeof(cplx));
-        memset(W, 0xFF, sizeof(cplx) * (size_t)S.n * ldw);
-        enqueue_sweeps<cplx>(e->dS, schedule_of(e), (const cplx*)e->L.data(), (const cplx*)e->Linv.data(),
-                             (const cplx*)e->dvec.data(), (cplx*)W, ldw, nrhs, tbuf.data(), src, nullptr, &launches);
-    }
+    if (e->tw == 1) sweeps_t<double>(e, src, W, ldw, nrhs, &launches);
+    else sweeps_t<cplx>(e, src, (cplx*)W, ldw, nrhs, &launches);
     return (int)launches;
 }
 

@@ -1,0 +1,76 @@
+"""GPU tests of code paths that are opt-in until they have been measured on the B200 (they were developed on the
+host-side SIMT emulator, tests/test_simt_kernels.py, while no GPU was available).  Enable with
+DRE_TEST_EXPERIMENTAL=1:   DRE_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+import dre_b200
+from dre_b200 import api
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("DRE_TEST_EXPERIMENTAL") != "1",
+                                 reason="opt-in paths: set DRE_TEST_EXPERIMENTAL=1")]
+pencils = dre_b200.pencils
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture()
+def sweep2(monkeypatch):
+    """A fresh context with the row-split sweeps (the flag is read when the context is created)."""
+    monkeypatch.setenv("DRE_SWEEP2", "1")
+    api.reset_backend()
+    yield
+    api.reset_backend()
+
+
+@pytest.mark.parametrize("n,leaf,cap", [(1357, 96, 256), (5177, 24, 40), (20209, 96, 256)])
+def test_row_split_sweeps_against_superlu(sweep2, monkeypatch, n, leaf, cap):
+    """DRE_SWEEP2=1: M21 panels + k_fwd2 / k_bwd2, 250 / 37 / 3 right-hand sides, real and complex shift,
+    plain and closed-loop (SMW) operator."""
+    monkeypatch.setenv("DRE_LEAF_SIZE", str(leaf))
+    monkeypatch.setenv("DRE_MAX_SNODE", str(cap))
+    E, A, B, C, _ = pencils.rail_pencil(n)
+    api.upload_pencil(E, A)
+    rng = np.random.default_rng(3)
+    a, e = 1.0, -1.0 / 200.0
+    F = api.PencilCombo(a, e)
+    for mu in (-0.37, -0.02 + 0.11j):
+        cx = isinstance(mu, complex)
+        dtype = complex if cx else float
+        M = (a * A + (e + mu) * E).tocsc().astype(dtype)
+        lu = spla.splu(M)
+        for nrhs in (250, 37, 3):
+            R = rng.standard_normal((n, nrhs))
+            out = api.solve_block(api.BlockLinearProblem(F, api.DeviceMatrix.from_host(R)), mu=mu)
+            V = out[0].to_host() + 1j * out[1].to_host() if cx else out.to_host()
+            assert _rel(V, lu.solve(R.astype(dtype))) < 1e-10, (mu, nrhs)
+            assert _rel(M @ V, R) < 1e-11, (mu, nrhs)
+
+
+@pytest.mark.parametrize("n,nsteps,ros", [(371, 3, 1), (371, 2, 2), (1357, 2, 1)])
+def test_row_split_sweeps_lockstep_parity(sweep2, n, nsteps, ros):
+    """The parity gate of tests/test_gpu_parity.py (K(t) 1e-8, residual norms 1e-10, equal iteration counts, shifts
+    replayed from the oracle) with the row-split sweeps."""
+    from tests import test_gpu_parity as P
+    from oracle import dre_oracle as O
+
+    dt = -100.0 if ros == 1 else -50.0
+    so, ro = P._oracle_run(n, nsteps, O.Ros1() if ros == 1 else O.Ros2(), dt=dt)
+    adi = api.ADI(shifts=P.ForcedShifts([r["shifts"] for r in ro.runs]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sg, rg = P._gpu_run(n, nsteps, api.Ros1(adi) if ros == 1 else api.Ros2(adi), dt=dt)
+    for Ko, Kg in zip(so.K, sg.K):
+        assert np.linalg.norm(Kg - Ko) <= 1e-8 * np.linalg.norm(Ko)
+    assert [r["iters"] for r in ro.runs] == [r["iters"] for r in rg.runs]
+    for a_, b_ in zip(ro.runs, rg.runs):
+        ra = np.array([x for _, x in a_["res"]])
+        rb = np.array([x for _, x in b_["res"]])
+        assert np.max(np.abs(ra - rb) / ra) <= 1e-10

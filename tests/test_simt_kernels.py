@@ -58,6 +58,35 @@ def test_emulated_factorization_and_sweeps(n, leaf, cap, nrhs):
     S.close()
 
 
+@pytest.mark.parametrize("n,leaf,cap,nrhs", [(371, 0, 0, 37), (1357, 24, 40, 150), (1357, 96, 256, 70)])
+def test_emulated_row_split_sweeps(n, leaf, cap, nrhs):
+    """Sweep v2 (DRE_SWEEP2): k_m21 leaves M21 = L21 Linv in the panels, k_fwd2 / k_bwd2 spread the strips of a
+    supernode over several CTAs.  (1357, 24, 40) has a populous leaf level (3 / 2 strips per warp) and sparse
+    upper levels (1 strip per warp, 16- and 32-column chunks); (1357, 96, 256) has supernodes of several row blocks."""
+    E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
+    S = emu.Solver(E, A, leaf, cap)
+    H = _SymFromEmu(E, A, leaf, cap)
+    rng = np.random.default_rng(8)
+    a, e = 1.0, -1.0 / 200.0
+    for mu in (-0.37, -0.02 + 0.11j):
+        dtype = complex if isinstance(mu, complex) else float
+        assert S.factor(a, e + mu, m21=True) == 0
+        Lh, Linvh, dvech = hostcheck.factor(H, a, e + mu, dtype, m21=True)
+        Ld = S.get("L")
+        for J in range(H.nsn):
+            s_, f_ = H.s(J), H.s(J) + H.u(J)
+            Pd = Ld[H.panel_off[J]:H.panel_off[J + 1]].reshape(s_, f_).T
+            Ph = Lh[H.panel_off[J]:H.panel_off[J + 1]].reshape(s_, f_).T
+            assert _rel(Pd[s_:], Ph[s_:]) < 1e-11 or np.linalg.norm(Ph[s_:]) == 0
+        R, Vt = rng.standard_normal((n, nrhs)), rng.standard_normal((n, 7))
+        W = S.sweeps(R, Vt)
+        M = (a * A + (e + mu) * E).tocsc().astype(dtype)
+        RHS = np.hstack([R, Vt]).astype(dtype)
+        assert _rel(W, spla.splu(M).solve(RHS)) < 1e-11
+        assert _rel(M @ W, RHS) < 1e-12
+    S.close()
+
+
 def test_emulated_sweeps_with_extra_rhs_panel():
     """The forward sweep reads [R, Vt] where the two panels lie (RhsSource): the SMW columns of the closed loop."""
     n = 371
