@@ -100,6 +100,7 @@ void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t s
 template <class T>
 void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* U,
                        cudaStream_t st, int64_t* launches);
+extern int diag_narrow_min;   // launch_diag: levels with >= this many supernodes use 64-thread CTAs
 // LDL^T of the s x s diagonal blocks of one level + inverse of the unit-lower factor (one CTA per supernode)
 template <class T>
 void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, T* L, T* Linv, T* dvec, int32_t* errflag,

@@ -34,6 +34,14 @@ namespace dre {
 
 constexpr int NB = 32;     // block size of the in-supernode LDL^T
 
+// Levels with at least this many supernodes run k_diag with 64-thread CTAs.  Opt-in until measured on the GPU:
+// DRE_DIAG_NARROW_MIN=296 (two CTAs per SM) is the intended setting; the emulator tests lower it to reach the variant.
+static int diag_narrow_min_default() {
+    const char* ev = getenv("DRE_DIAG_NARROW_MIN");
+    return ev ? std::max(1, atoi(ev)) : (1 << 30);
+}
+int diag_narrow_min = diag_narrow_min_default();
+
 __device__ __forceinline__ int sn_s(const DevSymbolic& S, int J) { return S.sn_first[J + 1] - S.sn_first[J]; }
 __device__ __forceinline__ int sn_u(const DevSymbolic& S, int J) { return (int)(S.sn_rowptr[J + 1] - S.sn_rowptr[J]); }
 
@@ -232,9 +240,12 @@ __global__ void __launch_bounds__(256) k_extend_add(DevSymbolic S, const int32_t
 // LDL^T of the s x s diagonal block of supernode J (right-looking over 32-column blocks, in place in the
 // panel) and the explicit inverse of its unit-lower factor.  One CTA per supernode; every 32x32x32 block
 // product is done by one warp on the tensor cores.
-template <class T>
-__global__ void __launch_bounds__(256) k_diag(DevSymbolic S, const int32_t* __restrict__ sns, T* L, T* Linv, T* dvec,
-                                              int32_t* errflag) {
+// NW = warps per CTA: 8 for the few fat supernodes near the root; 2 on the populous leaf levels, where the CTA count
+// exceeds what the register file holds at 256 threads x 128 registers (2 CTAs per SM -> 3.5 waves of mostly idle
+// threads at 1024 leaves, and no registers left for the kernels of the other streams) -- 64-thread CTAs run 8 per SM.
+template <class T, int NW>
+__global__ void __launch_bounds__(32 * NW) k_diag(DevSymbolic S, const int32_t* __restrict__ sns, T* L, T* Linv, T* dvec,
+                                                  int32_t* errflag) {
     __shared__ T Ds[NB][NB + 1];   // current diagonal block: strictly lower = L_bb, diagonal = pivots
     __shared__ T Li[NB][NB + 1];   // inverse of the unit-lower L_bb (ones on, zeros above the diagonal)
     const int J = sns[blockIdx.x];
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(256) k_diag(DevSymbolic S, const int32_t* __re
         }
         __syncthreads();
         // block rows below (inside the diagonal block): L_Ib = A_Ib Linv_bb' D_b^-1
-        for (int I = b + 1 + warp; I < nbk; I += 8) {
+        for (int I = b + 1 + warp; I < nbk; I += NW) {
             blk.clear();
             blk.gemm(NB, lane,
                      [&](int i, int k) {
@@ -302,7 +313,7 @@ __global__ void __launch_bounds__(256) k_diag(DevSymbolic S, const int32_t* __re
         __syncthreads();
         // trailing update of the diagonal block: C_IK -= L_Ib D_b L_Kb'   for b < K <= I
         const int m = nbk - b - 1;
-        for (int p = warp; p < m * (m + 1) / 2; p += 8) {
+        for (int p = warp; p < m * (m + 1) / 2; p += NW) {
             int Ii = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
             while ((Ii + 1) * (Ii + 2) / 2 <= p) ++Ii;
             while (Ii * (Ii + 1) / 2 > p) --Ii;
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(256) k_diag(DevSymbolic S, const int32_t* __re
     }
     // off-diagonal blocks of the inverse, one block column per warp:
     //   Linv[I][Jc] = -Linv[I][I] * sum_{K=Jc}^{I-1} L[I][K] Linv[K][Jc]
-    for (int Jc = warp; Jc < nbk; Jc += 8) {
+    for (int Jc = warp; Jc < nbk; Jc += NW) {
         for (int I = Jc + 1; I < nbk; ++I) {
             blk.clear();
             for (int K = Jc; K < I; ++K)
@@ -451,7 +462,8 @@ template <class T>
 void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, T* L, T* Linv, T* dvec, int32_t* errflag,
                  cudaStream_t st, int64_t* launches) {
     if (nsns <= 0) return;
-    DRE_LAUNCH((k_diag<T>), nsns, 256, 0, st, S, sns, L, Linv, dvec, errflag);
+    if (nsns >= diag_narrow_min) DRE_LAUNCH((k_diag<T, 2>), nsns, 64, 0, st, S, sns, L, Linv, dvec, errflag);
+    else DRE_LAUNCH((k_diag<T, 8>), nsns, 256, 0, st, S, sns, L, Linv, dvec, errflag);
     if (launches) *launches += 1;
 }
 

@@ -1,5 +1,7 @@
-"""TEST INFRASTRUCTURE: builds tests/simt/libdre_emu.so -- the CUDA kernel sources of the product compiled by g++
-against the host-side SIMT emulator (tests/simt/stub/cuda_runtime.h).  Used only by tests/test_simt_kernels.py."""
+"""TEST INFRASTRUCTURE: builds tests/simt/libdre_emu.so -- the CUDA sources of the product (kernels AND the C-ABI
+layer context.cu) compiled by g++ against the host-side SIMT emulator (tests/simt/stub/).  The library exports the
+kernel-level harness (emu_*) and the whole C ABI of include/dre_b200.h (dre_*) running on the emulator.  Used only by
+tests/test_simt_*.py; the product loads libdre_b200.so and nothing else."""
 from __future__ import annotations
 
 import os
@@ -9,10 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "differentialriccatiequations.jl_b200", "csrc")
 LIB = os.path.join(HERE, "libdre_emu.so")
-KERNEL_SOURCES = ["sparse_kernels.cu", "dense_kernels.cu"]
+KERNEL_SOURCES = ["sparse_kernels.cu", "dense_kernels.cu", "context.cu"]
 DEPS = [os.path.join(CSRC, f) for f in KERNEL_SOURCES + ["symbolic.cpp", "symbolic.h", "kernels.h", "common.cuh",
                                                            "schedule.h"]] + \
-       [os.path.join(HERE, "emu_harness.cpp"), os.path.join(HERE, "stub", "cuda_runtime.h")]
+       [os.path.join(ROOT, "include", "dre_b200.h"), os.path.join(HERE, "emu_harness.cpp"),
+        os.path.join(HERE, "stub", "cuda_runtime.h"), os.path.join(HERE, "stub", "cusolverDn.h")]
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-DDRE_SIMT_EMU", "-fvisibility=hidden", "-fno-strict-aliasing",
          "-I", os.path.join(HERE, "stub"), "-I", CSRC]
 

@@ -133,6 +133,10 @@ def tall_gemm(alpha, X, W, beta, Y, w_trans=False):
     return Y
 
 
+def set_diag_narrow_min(v):
+    lib().emu_set_diag_narrow_min(int(v))
+
+
 def counters():
     c = (C.c_long * 3)()
     lib().emu_counters(c)

@@ -219,6 +219,9 @@ EMU_API void emu_panel_transposes(double* panel, int64_t ldd, const double* cm, 
     launch_panel_to_colmajor(back, ldb, panel, ldd, n, cols, iperm, nullptr, &launches);
 }
 
+// tuning knobs of the launchers (so that small test problems reach every kernel variant)
+EMU_API void emu_set_diag_narrow_min(int v) { dre::diag_narrow_min = v; }
+
 EMU_API void emu_counters(long* out) {
     out[0] = simt::M().launches;
     out[1] = simt::M().ctas;

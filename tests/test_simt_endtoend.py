@@ -1,0 +1,102 @@
+"""CPU tier: the WHOLE product stack -- host mirror (api.py) -> C ABI (csrc/context.cu) -> CUDA kernel sources --
+executed on the host-side SIMT emulator (tests/simt/: libdre_emu.so exports the C ABI of include/dre_b200.h built
+from the same sources with g++; cuSOLVER's Dsyevd is replaced by a Jacobi eigensolver, streams are synchronous).
+These are the lock-step parity checks of tests/test_gpu_parity.py at the smallest size, so that the arithmetic of
+the hot path is pinned against the oracle even when no GPU is at hand.  The fixture swaps the library inside this
+test process only; the product never loads anything but libdre_b200.so."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+import dre_b200
+from dre_b200 import api, capi
+from oracle import dre_oracle as O
+from tests.simt import build_emu
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    """api.* on top of the emulated C ABI; `emulated(sweep2=True)` selects the row-split sweeps."""
+    saved = (capi.LIB_PATH, capi._lib)
+    monkeypatch.setenv("DRE_NO_PRIME", "1")   # (the Jacobi stand-in needs no kernel priming)
+
+    def start(sweep2=False):
+        monkeypatch.setenv("DRE_SWEEP2", "1" if sweep2 else "0")
+        api.reset_backend()
+        capi.LIB_PATH, capi._lib = build_emu.build(), None
+        api.reset_backend()
+
+    yield start
+    api.reset_backend()
+    capi.LIB_PATH, capi._lib = saved
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_emulated_abi_block_solve_smw_and_compress(emulated):
+    """dre_shift_solve incl. the fused Sherman-Morrison-Woodbury correction (real and complex shift),
+    dre_ldlt_compress / dre_ldlt_norm against dense NumPy."""
+    emulated()
+    n = 371
+    E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
+    api.upload_pencil(E, A)
+    rng = np.random.default_rng(0)
+    R = rng.standard_normal((n, 20))
+    K = 0.05 * rng.standard_normal((n, B.shape[1]))
+    F = api.lr_update(api.PencilCombo(1.0, -1.0 / 200.0), -1.0, api.DeviceMatrix.from_host(K),
+                      api.DeviceMatrix.from_host(B), transposed=True)
+    for mu in (-0.37, -0.02 + 0.11j):
+        cx = isinstance(mu, complex)
+        out = api.solve_block(api.BlockLinearProblem(F, api.DeviceMatrix.from_host(R)), mu=mu)
+        V = out[0].to_host() + 1j * out[1].to_host() if cx else out.to_host()
+        M = (A + (-1.0 / 200.0 + mu) * E).toarray() - K @ B.T
+        assert _rel(M @ V, R) < 1e-11
+    L = rng.standard_normal((n, 30)) @ rng.standard_normal((30, 90))
+    D = np.diag(rng.standard_normal(90))
+    X = api.lowrank(api.DeviceMatrix.from_host(L), D)
+    Xd = L @ D @ L.T
+    assert abs(api.norm(X) - np.linalg.norm(Xd)) < 1e-12 * np.linalg.norm(Xd)
+    Xc = api.compress_(X)
+    a, Lc, Dc = Xc.alphas[0], Xc.Ls[0].to_host(), Xc.Ds[0]
+    assert Lc.shape[1] == 30
+    assert _rel(a * Lc @ Dc @ Lc.T, Xd) < 1e-13
+
+
+def _lockstep(n, nsteps, ros):
+    from tests import test_gpu_parity as P
+
+    dt = -100.0 if ros == 1 else -50.0
+    so, ro = P._oracle_run(n, nsteps, O.Ros1() if ros == 1 else O.Ros2(), dt=dt)
+    adi = api.ADI(shifts=P.ForcedShifts([r["shifts"] for r in ro.runs]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sg, rg = P._gpu_run(n, nsteps, api.Ros1(adi) if ros == 1 else api.Ros2(adi), dt=dt)
+    for Ko, Kg in zip(so.K, sg.K):
+        assert np.linalg.norm(Kg - Ko) <= 1e-8 * np.linalg.norm(Ko)
+    assert [r["iters"] for r in ro.runs] == [r["iters"] for r in rg.runs]
+    for a_, b_ in zip(ro.runs, rg.runs):
+        ra = np.array([x for _, x in a_["res"]])
+        rb = np.array([x for _, x in b_["res"]])
+        assert np.max(np.abs(ra - rb) / ra) <= 1e-10
+
+
+@pytest.mark.parametrize("sweep2", [False, True])
+def test_emulated_lockstep_parity_ros1(emulated, sweep2):
+    """One low-rank Ros1 step at n = 371 (36 ADI iterations, shifts replayed from the oracle): K(t) within 1e-8,
+    every ADI residual norm within 1e-10 relative, identical iteration counts -- the north-star tolerances -- with
+    the per-level sweeps and with the row-split sweeps (DRE_SWEEP2)."""
+    emulated(sweep2=sweep2)
+    _lockstep(371, 1, 1)
+
+
+@pytest.mark.skipif(os.environ.get("DRE_TEST_SLOW") != "1", reason="2 minutes per variant: set DRE_TEST_SLOW=1")
+@pytest.mark.parametrize("sweep2", [False, True])
+def test_emulated_lockstep_parity_ros2_complex_shifts(emulated, sweep2):
+    """One Ros2 step (two ADI solves, complex shift pairs: the complex-symmetric factorization and sweeps)."""
+    emulated(sweep2=sweep2)
+    _lockstep(371, 1, 2)

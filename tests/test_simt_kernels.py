@@ -87,6 +87,26 @@ def test_emulated_row_split_sweeps(n, leaf, cap, nrhs):
     S.close()
 
 
+def test_emulated_narrow_diag_kernel():
+    """k_diag with 64-thread CTAs (DRE_DIAG_NARROW_MIN): same factor arrays as the 256-thread variant, bit for bit
+    (the work distribution over warps changes, the arithmetic of every block does not)."""
+    n = 1357
+    E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
+    S = emu.Solver(E, A, 96, 256)
+    try:
+        for mu in (-0.37, -0.02 + 0.11j):
+            emu.set_diag_narrow_min(1 << 30)
+            assert S.factor(1.0, mu) == 0
+            ref = [S.get(w).copy() for w in ("L", "Linv", "dvec")]
+            emu.set_diag_narrow_min(1)
+            assert S.factor(1.0, mu) == 0
+            for w, r in zip(("L", "Linv", "dvec"), ref):
+                assert np.array_equal(S.get(w), r, equal_nan=True), w   # never-written entries above the diagonal blocks stay poisoned
+    finally:
+        emu.set_diag_narrow_min(1 << 30)
+        S.close()
+
+
 def test_emulated_sweeps_with_extra_rhs_panel():
     """The forward sweep reads [R, Vt] where the two panels lie (RhsSource): the SMW columns of the closed loop."""
     n = 371
