@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
     if force or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + [
-            "-gencode", "arch=compute_100a,code=sm_100a", "-lcusolver", "-lcudart",
+            "-gencode", "arch=compute_100a,code=sm_100a", "-lcusolver", "-lcudart", "-lpthread",
             "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
         subprocess.run(cmd, check=True)
     return LIB

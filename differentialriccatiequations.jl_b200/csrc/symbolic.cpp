@@ -4,6 +4,8 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -30,29 +32,55 @@ struct Dissector {
     std::vector<int32_t> stamp;    // region membership stamp
     std::vector<int32_t> d1, d2;   // BFS distances
     std::vector<int8_t> part;      // 0 / 1 / 2 (=separator)
-    std::vector<int32_t> queue_;
-    int32_t cur_stamp = 0;
+    std::atomic<int32_t> cur_stamp{0};
+    // The two halves of a dissected region are independent, so the top levels of the recursion run as parallel
+    // tasks (par_depth levels -> up to 2^par_depth tasks).  The per-vertex arrays above are shared: a task only
+    // touches vertices of its own region (every neighbour access is guarded by the region stamp, and the stamps of
+    // the separators above it do not change while it runs); the BFS queue and the output are per task, and the
+    // outputs are concatenated in the sequential order (left half, right half, separator), so the ordering does not
+    // depend on the number of threads.
+    int par_depth = 0;
+    struct Out {
+        std::vector<int32_t> order;      // perm: new -> old
+        std::vector<int32_t> block_end;  // end offsets (in `order`) of supernode blocks
+        void emit_block(const std::vector<int32_t>& verts) {
+            if (verts.empty()) return;
+            for (int32_t v : verts) order.push_back(v);
+            block_end.push_back((int32_t)order.size());
+        }
+        void append(const Out& o) {
+            const int32_t base = (int32_t)order.size();
+            order.insert(order.end(), o.order.begin(), o.order.end());
+            for (int32_t e : o.block_end) block_end.push_back(base + e);
+        }
+    };
+    struct Scratch {
+        std::vector<int32_t> queue_;
+    };
     // output
-    std::vector<int32_t> order;      // perm: new -> old
-    std::vector<int32_t> block_end;  // end offsets (in `order`) of supernode blocks
+    Out out;
 
     Dissector(const Graph& g_, int32_t leaf_) : g(g_), leaf(leaf_) {
         stamp.assign(g.n, -1);
         d1.assign(g.n, -1);
         d2.assign(g.n, -1);
         part.assign(g.n, 0);
-        queue_.reserve(g.n);
-        order.reserve(g.n);
+        out.order.reserve(g.n);
+        int threads = (int)std::thread::hardware_concurrency();
+        if (const char* ev = getenv("DRE_SYMBOLIC_THREADS")) threads = atoi(ev);
+        threads = std::max(1, std::min(threads, 64));
+        while ((1 << par_depth) < threads) ++par_depth;
     }
 
-    void emit_block(const std::vector<int32_t>& verts) {
-        if (verts.empty()) return;
-        for (int32_t v : verts) order.push_back(v);
-        block_end.push_back((int32_t)order.size());
+    void run(std::vector<int32_t>& verts) {
+        Scratch sc;
+        sc.queue_.reserve(g.n);
+        dissect(verts, out, sc, 0);
     }
 
     // BFS inside the region marked with `st`; fills dist for reached vertices, returns visit order in queue_
-    int32_t bfs(int32_t src, int32_t st, std::vector<int32_t>& dist, const std::vector<int32_t>& verts) {
+    int32_t bfs(int32_t src, int32_t st, std::vector<int32_t>& dist, const std::vector<int32_t>& verts,
+                std::vector<int32_t>& queue_) {
         for (int32_t v : verts) dist[v] = -1;
         queue_.clear();
         queue_.push_back(src);
@@ -146,13 +174,14 @@ struct Dissector {
         return best;
     }
 
-    void dissect(std::vector<int32_t>& verts) {
-        if ((int32_t)verts.size() <= leaf) { emit_block(verts); return; }
+    void dissect(std::vector<int32_t>& verts, Out& out, Scratch& sc, int depth) {
+        std::vector<int32_t>& queue_ = sc.queue_;
+        if ((int32_t)verts.size() <= leaf) { out.emit_block(verts); return; }
         int32_t st = ++cur_stamp;
         for (int32_t v : verts) stamp[v] = st;
 
         // connected components: small ones are packed into shared blocks, large ones dissected
-        int32_t reached = bfs(verts[0], st, d1, verts);
+        int32_t reached = bfs(verts[0], st, d1, verts, queue_);
         if (reached < (int32_t)verts.size()) {
             std::vector<std::vector<int32_t>> big;
             std::vector<int32_t> pending;
@@ -174,19 +203,19 @@ struct Dissector {
                 if ((int32_t)queue_.size() > leaf) {
                     big.emplace_back(queue_.begin(), queue_.end());
                 } else {
-                    if ((int32_t)(pending.size() + queue_.size()) > leaf) { emit_block(pending); pending.clear(); }
+                    if ((int32_t)(pending.size() + queue_.size()) > leaf) { out.emit_block(pending); pending.clear(); }
                     pending.insert(pending.end(), queue_.begin(), queue_.end());
                 }
             }
-            emit_block(pending);
+            out.emit_block(pending);
             verts.clear(); verts.shrink_to_fit();
-            for (auto& c : big) dissect(c);
+            for (auto& c : big) dissect(c, out, sc, depth);
             return;
         }
         // pseudo-peripheral pair (s, t)
         int32_t s = verts[0], ecc = -1;
         for (int it = 0; it < 5; ++it) {
-            bfs(s, st, d1, verts);
+            bfs(s, st, d1, verts, queue_);
             int32_t far = queue_.back(), e = d1[far];
             // among the last level pick the minimum-degree vertex
             int64_t bestdeg = INT64_MAX;
@@ -200,11 +229,11 @@ struct Dissector {
             ecc = e;
             s = far;
         }
-        bfs(s, st, d1, verts);
+        bfs(s, st, d1, verts, queue_);
         int32_t t = queue_.back();
         ecc = d1[t];
-        if (ecc < 2) { emit_block(verts); return; }  // clique-like: keep as one dense supernode
-        bfs(t, st, d2, verts);
+        if (ecc < 2) { out.emit_block(verts); return; }  // clique-like: keep as one dense supernode
+        bfs(t, st, d2, verts, queue_);
 
         std::vector<int32_t> key(verts.size());
         // candidate A: BFS level set from s
@@ -223,7 +252,7 @@ struct Dissector {
         Cand* best = nullptr;
         if (ca.ok) best = &ca;
         if (cb.ok && (!best || cb.cost < best->cost)) best = &cb;
-        if (!best) { emit_block(verts); return; }
+        if (!best) { out.emit_block(verts); return; }
 
         std::vector<int32_t> p0, p1, sep;
         p0.reserve(best->p0); p1.reserve(best->p1); sep.reserve(best->s);
@@ -232,9 +261,22 @@ struct Dissector {
         }
         verts.clear(); verts.shrink_to_fit();
         ca.lab.clear(); cb.lab.clear();
-        dissect(p0);
-        dissect(p1);
-        emit_block(sep);
+        if (depth < par_depth && p0.size() + p1.size() >= 2048) {
+            Out o0, o1;
+            std::thread left([&]() {
+                Scratch s0;
+                s0.queue_.reserve(p0.size());
+                dissect(p0, o0, s0, depth + 1);
+            });
+            dissect(p1, o1, sc, depth + 1);
+            left.join();
+            out.append(o0);
+            out.append(o1);
+        } else {
+            dissect(p0, out, sc, depth + 1);
+            dissect(p1, out, sc, depth + 1);
+        }
+        out.emit_block(sep);
     }
 };
 
@@ -372,10 +414,10 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
     {
         std::vector<int32_t> all(n);
         std::iota(all.begin(), all.end(), 0);
-        dis.dissect(all);
+        dis.run(all);
     }
-    if ((int64_t)dis.order.size() != n) return "analyze: internal error (ordering incomplete)";
-    S.perm = dis.order;
+    if ((int64_t)dis.out.order.size() != n) return "analyze: internal error (ordering incomplete)";
+    S.perm = dis.out.order;
     S.iperm.assign(n, -1);
     for (int64_t k = 0; k < n; ++k) S.iperm[S.perm[k]] = (int32_t)k;
     // supernodes = dissection blocks, split into chains of at most max_snode columns (a chain link's
@@ -386,7 +428,7 @@ std::string analyze(int64_t n, const int64_t* Ecp, const int64_t* Eri, const dou
         S.sn_first.clear();
         S.sn_first.push_back(0);
         int32_t b0 = 0;
-        for (int32_t b1 : dis.block_end) {
+        for (int32_t b1 : dis.out.block_end) {
             const int32_t size = b1 - b0;
             const int32_t nchunk = (size + cap - 1) / cap;
             const int32_t csz = (size + nchunk - 1) / nchunk;
