@@ -294,6 +294,11 @@ int check_errflag(dre_context* c) {
 
 // host wall-clock trace of the C-ABI internals (DRE_TRACE=1): where does the launching thread block?
 static const bool g_trace = getenv("DRE_TRACE") != nullptr;
+// DRE_RR_STATS=1: totals of the rank-revealing Gram-Schmidt rounds, printed when a context dies
+static const bool g_rr_stats = getenv("DRE_RR_STATS") != nullptr;
+struct RRTotals {
+    long calls = 0, blocks = 0, rounds = 0, productive = 0, skipped = 0, syncs = 0, rest_projections = 0;
+} g_rr;
 struct HostTrace {
     const char* name;
     std::chrono::steady_clock::time_point t0;
@@ -630,14 +635,25 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
             for (int j = 0; j < pbig; ++j) rem2[j] = c->h_pinned[16 + j];
             have_rem = true;
         }
+        // Optional eager projection of the rest of the block (DRE_RR_EAGER=1, off by default): as soon as a sub-panel
+        // has added directions, the columns behind it are projected against them in ONE fat Gram / tall-GEMM pair
+        // and their remainder norms are refreshed, so that sub-panels the new directions exhaust are skipped
+        // instead of each paying a projection, a Gram, a selection and a synchronisation to find nothing.  On the
+        // emulator (n = 371, three Ros1 steps) it trades 7 unproductive rounds for 75 extra projections -- a loss;
+        // whether it pays at n = 79 841 (where tracing showed 539 of 1215 wide-sub-panel rounds finding nothing)
+        // depends on how many of those the norm test already skips: to be measured with DRE_RR_STATS=1 on the GPU.
+        static const bool eager = getenv("DRE_RR_EAGER") && atoi(getenv("DRE_RR_EAGER")) != 0;
+        int proj_rest = rho0;   // columns behind the current sub-panel are orthogonal to the basis [0, proj_rest)
+        g_rr.blocks++;
         for (int sc = 0; sc < pbig; sc += PB) {
             const int pb = std::min(PB, pbig - sc);
+            const int proj_entry = eager ? proj_rest : rho0;
             if (have_rem && !g_trace) {
                 double m2 = 0.0;
                 for (int j = sc; j < sc + pb; ++j) m2 = std::max(m2, rem2[j]);
                 const double drop0 = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
                 // (projections against directions added inside this block can only shrink the columns further)
-                if (m2 < drop0 * drop0) { s.skipped++; continue; }
+                if (m2 < drop0 * drop0) { s.skipped++; g_rr.skipped++; continue; }
             }
             double* Pw = Pbig + sc;
             double* RTrow = s.RT + (int64_t)(rt_row0 + c0 + sc) * s.ldrt;
@@ -652,15 +668,19 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
             }
             for (int round = 0; round < 8; ++round) {
                 s.rounds++;
-                const int nnew = s.rho - rho0;   // directions added inside this block
+                g_rr.rounds++;
+                // directions added inside this block that this sub-panel has not been projected against yet
+                // (round 0 of an eagerly projected sub-panel: none; later rounds re-project against all of them)
+                const int pfrom = (round == 0) ? proj_entry : rho0;
+                const int nnew = s.rho - pfrom;
                 if (nnew > 0) {
                     CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
                     // same rule as for the block passes: one pass unless the block holds large columns
                     for (int pass = 0; pass < npass; ++pass) {
-                        rc = gram_dev(c, Pw, PBIG, pb, s.Q + rho0, s.ldq, nnew, n, nullptr, c->cbuf.p, nnew,
-                                      RTrow + rho0, s.ldrt);
+                        rc = gram_dev(c, Pw, PBIG, pb, s.Q + pfrom, s.ldq, nnew, n, nullptr, c->cbuf.p, nnew,
+                                      RTrow + pfrom, s.ldrt);
                         if (rc) return rc;
-                        rc = tall_gemm(c, -1.0, s.Q + rho0, s.ldq, nnew, c->cbuf.p, nnew, 1, 1.0, Pw, PBIG, pb, n);
+                        rc = tall_gemm(c, -1.0, s.Q + pfrom, s.ldq, nnew, c->cbuf.p, nnew, 1, 1.0, Pw, PBIG, pb, n);
                         if (rc) return rc;
                     }
                 }
@@ -676,6 +696,7 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                 CU(cudaMemcpyAsync(hi, c->ibuf.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
                 CU(cudaMemcpyAsync(c->h_pinned, c->small.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
                 CU(cudaStreamSynchronize(c->st));
+                g_rr.syncs++;
                 const int nsel = hi[0];
                 const double dfirst = c->h_pinned[0];
                 const double remaining = c->h_pinned[1];
@@ -723,10 +744,34 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                             std::sqrt(remaining / std::max(trace_d0, 1e-300)), std::sqrt(s.scale2));
                 if (nsel == 0 || nsel2 == 0) break;
                 s.rho += nsel2;
+                g_rr.productive++;
                 // the remaining (unselected) columns are certified negligible when the Gram rounding noise
                 // (~1e-13 * dfirst) is below the drop threshold and the remaining Schur diagonal is too
                 const double drop_now = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
                 if (nsel2 == nsel && remaining <= drop_now * drop_now && 1e-13 * dfirst <= drop_now * drop_now) break;
+            }
+            const int rest0 = sc + pb, nrest = pbig - rest0;
+            if (eager && nrest > 0 && s.rho > proj_rest) {
+                const int nn = s.rho - proj_rest;
+                double* Prest = Pbig + rest0;
+                CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
+                for (int pass = 0; pass < npass; ++pass) {
+                    rc = gram_dev(c, Prest, PBIG, nrest, s.Q + proj_rest, s.ldq, nn, n, nullptr, c->cbuf.p, nn,
+                                  s.RT + (int64_t)(rt_row0 + c0 + rest0) * s.ldrt + proj_rest, s.ldrt);
+                    if (rc) return rc;
+                    rc = tall_gemm(c, -1.0, s.Q + proj_rest, s.ldq, nn, c->cbuf.p, nn, 1, 1.0, Prest, PBIG, nrest, n);
+                    if (rc) return rc;
+                }
+                proj_rest = s.rho;
+                g_rr.rest_projections++;
+                constexpr int NBLK = 296;
+                launch_colnorm2(Prest, PBIG, n, nrest, c->gram_partial.p, NBLK, c->cnorm.p, c->st,
+                                &c->stats.kernel_launches);
+                CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, nrest * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+                CU(cudaStreamSynchronize(c->st));
+                g_rr.syncs++;
+                for (int j = 0; j < nrest; ++j) rem2[rest0 + j] = c->h_pinned[16 + j];
+                have_rem = true;
             }
         }
     }
@@ -925,6 +970,12 @@ static void prime_eigensolver(dre_context* c) {
 }
 
 int32_t dre_destroy(dre_context* c) {
+    if (g_rr_stats && c)
+        fprintf(stderr,
+                "[dre rr totals] blocks %ld rounds %ld productive %ld skipped sub-panels %ld rest projections %ld "
+                "round syncs %ld kernel launches (context) %lld\n",
+                g_rr.blocks, g_rr.rounds, g_rr.productive, g_rr.skipped, g_rr.rest_projections, g_rr.syncs,
+                (long long)c->stats.kernel_launches);
     if (!c) return DRE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
