@@ -381,7 +381,6 @@ int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) 
     T* dvec = (T*)fs.dvec;
     T* U = (T*)fs.U;
     CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), st));
-    if (c->upd_elems > 0) CU(cudaMemsetAsync(U, 0, (size_t)c->upd_elems * sizeof(T), st));
     enqueue_factor<T>(c->dS, dev_schedule(c), L, Linv, dvec, U, c->op_a, emu, c->d_errflag, st,
                       &c->stats.kernel_launches, c->sweep2);
     CU(cudaGetLastError());
@@ -396,7 +395,7 @@ int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs, const RhsSource& s
     Timer t(c, &c->stats.ms_solve);
     {
         HostTrace tr("tbuf.ensure");
-        CU(c->tbuf.ensure((size_t)std::max<int64_t>(S.sum_u, 1) * ldw * sizeof(T)));
+        CU(c->tbuf.ensure((size_t)std::max<int64_t>(S.rhs_total, 1) * ldw * sizeof(T)));
     }
     dre_context::FactorSlot& fs = c->slot[c->cur];
     const T* L = (const T*)fs.L;
@@ -1030,7 +1029,7 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     const Symbolic& S = c->sym;
     if (S.max_sn > SN_MAX) return fail(c, DRE_ERR_STATE, "internal error: supernode wider than SN_MAX");
     c->linv_elems = S.linv_off[S.nsn];
-    c->upd_elems = S.upd_off[S.nsn];
+    c->upd_elems = S.upd_total;
 
     int rc;
     int32_t *d_sn_first, *d_sn_rows, *d_relmap, *d_child_ptr, *d_child_idx;

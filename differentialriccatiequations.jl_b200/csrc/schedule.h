@@ -21,6 +21,7 @@ struct LevelWork {
     int fwd2_begin = 0, fwd2_count = 0, fwd2_q = 1;
     int bwd2_begin = 0, bwd2_count = 0, bwd2_q = 1;
     int has_children = 0;
+    int64_t upd_off = 0, upd_size = 0;   // this level's segment of the update-matrix pool (zeroed before the level runs)
 };
 
 struct LevelLists {
@@ -62,6 +63,8 @@ inline void build_level_lists(const Symbolic& S, LevelLists& out) {
         lw.l21_count = (int)out.l21_items.size() - lw.l21_begin;
         lw.schur_count = (int)out.schur_items.size() - lw.schur_begin;
         lw.ea_gy = std::min(64, std::max(1, max_f / 8));
+        lw.upd_off = S.upd_level_off[l];
+        lw.upd_size = S.upd_level_size[l];
         // Row-split sweeps.  Populous levels (enough supernodes to fill the machine with one CTA each at ~250
         // right-hand sides) keep a supernode in as few CTAs as possible; the sparse levels near the root spread
         // every supernode over one CTA per 64 rows.
@@ -94,7 +97,8 @@ struct DevSchedule {
     const int2* bwd2_items;
 };
 
-// numeric LDL^T of  a*A + emu*E  into (L, Linv, dvec); L and U must be zeroed by the caller.
+// numeric LDL^T of  a*A + emu*E  into (L, Linv, dvec); L must be zeroed by the caller, the pooled update matrices U
+// are zeroed level by level here (a level's segment recycles the space of levels that are already consumed).
 // m21: leave M21 = L21 Linv instead of L21 in the panels (what the row-split sweeps read).
 template <class T>
 inline void enqueue_factor(const DevSymbolic& dS, const DevSchedule& sch, T* L, T* Linv, T* dvec, T* U, double a, T emu,
@@ -102,6 +106,7 @@ inline void enqueue_factor(const DevSymbolic& dS, const DevSchedule& sch, T* L, 
     launch_assemble<T>(dS, L, a, emu, st, launches);
     for (int l = 0; l < sch.nlevels; ++l) {
         const LevelWork& lw = sch.levels[l];
+        if (lw.upd_size > 0) cudaMemsetAsync(U + lw.upd_off, 0, (size_t)lw.upd_size * sizeof(T), st);
         if (lw.ea_count > 0)
             launch_extend_add<T>(dS, sch.ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, U, st, launches);
         launch_diag<T>(dS, sch.level_sn + lw.sn_begin, lw.sn_count, L, Linv, dvec, errflag, st, launches);

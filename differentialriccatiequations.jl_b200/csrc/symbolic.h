@@ -33,8 +33,12 @@ struct Symbolic {
 
     std::vector<int64_t> panel_off;  // nsn+1: offset of the f_J x s_J column-major panel (ld = f_J) in L storage
     std::vector<int64_t> linv_off;   // nsn+1: offset of the s_J x s_J column-major inverse of the unit-lower diagonal block
-    std::vector<int64_t> upd_off;    // nsn+1: offset of the u_J x u_J column-major update matrix (no buffer reuse)
-    std::vector<int64_t> rhs_off;    // nsn: row offset of the u_J-row update vector of the solves (cumulative)
+    // Pooled by liveness (written on level(J), last read on level(parent(J))); see pool_by_level in symbolic.cpp
+    std::vector<int64_t> upd_off;    // nsn+1: offset of the u_J x u_J column-major update matrix; [nsn] = upd_total
+    std::vector<int64_t> rhs_off;    // nsn: row offset of the u_J-row update vector of the forward sweep
+    int64_t upd_total = 0;           // entries of the update-matrix pool
+    int64_t rhs_total = 0;           // rows of the update-vector pool
+    std::vector<int64_t> upd_level_off, upd_level_size;   // nlevels: the pool segment of every level (zeroed per level)
 
     // children lists (CSR by parent) and relative maps child-struct-row -> parent front local index
     std::vector<int32_t> child_ptr, child_idx;
@@ -53,7 +57,7 @@ struct Symbolic {
     int64_t nnz_L = 0;       // sum f_J*s_J (stored panel entries, incl. relaxed zeros)
     double flops = 0;        // real multiply-add pairs*2 of the supernodal LDL^T
     int32_t max_front = 0, max_sn = 0;
-    int64_t sum_u = 0;       // sum of u_J (rows of update vectors in a solve)
+    int64_t sum_u = 0;       // sum of u_J (statistics; the update vectors occupy rhs_total <= sum_u rows)
 
     int32_t sn_size(int32_t J) const { return sn_first[J + 1] - sn_first[J]; }
     int32_t sn_nrows(int32_t J) const { return (int32_t)(sn_rowptr[J + 1] - sn_rowptr[J]); }

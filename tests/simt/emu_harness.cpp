@@ -64,7 +64,7 @@ EMU_API int emu_open(int64_t n, const int64_t* Ecp, const int64_t* Eri, const do
     e->L.assign((size_t)std::max<int64_t>(S.nnz_L, 1) * 2, 0.0);
     e->Linv.assign((size_t)std::max<int64_t>(S.linv_off[S.nsn], 1) * 2, 0.0);
     e->dvec.assign((size_t)S.n * 2, 0.0);
-    e->U.assign((size_t)std::max<int64_t>(S.upd_off[S.nsn], 1) * 2, 0.0);
+    e->U.assign((size_t)std::max<int64_t>(S.upd_total, 1) * 2, 0.0);
     *out = e;
     return 0;
 }
@@ -75,7 +75,7 @@ EMU_API void emu_close(void* h) { delete (Emu*)h; }
 EMU_API void emu_sizes(void* h, int64_t* out) {
     const Symbolic& S = ((Emu*)h)->S;
     out[0] = S.n; out[1] = S.nsn; out[2] = S.nlevels; out[3] = S.nnz_L; out[4] = S.linv_off[S.nsn];
-    out[5] = S.upd_off[S.nsn]; out[6] = S.sum_u; out[7] = S.max_sn;
+    out[5] = S.upd_total; out[6] = S.rhs_total; out[7] = S.max_sn;
 }
 
 EMU_API void emu_perm(void* h, int32_t* perm) {
@@ -89,7 +89,7 @@ static int factor_t(Emu* e, double a, T emu, bool m21) {
     T* L = (T*)e->L.data();
     T* U = (T*)e->U.data();
     memset(L, 0, (size_t)S.nnz_L * sizeof(T));
-    memset(U, 0, (size_t)S.upd_off[S.nsn] * sizeof(T));
+    memset((void*)U, 0xFF, (size_t)S.upd_total * sizeof(T));   // the factorization zeroes its pool level by level
     // poison what the factorization must fully define itself
     memset(e->Linv.data(), 0xFF, e->Linv.size() * sizeof(double));
     memset(e->dvec.data(), 0xFF, e->dvec.size() * sizeof(double));
@@ -119,7 +119,7 @@ EMU_API void emu_get(void* h, int what, double* buf) {
 template <class T>
 static void sweeps_t(Emu* e, const RhsSource& src, T* W, int64_t ldw, int nrhs, int64_t* launches) {
     const Symbolic& S = e->S;
-    std::vector<T> tbuf((size_t)std::max<int64_t>(S.sum_u, 1) * ldw);
+    std::vector<T> tbuf((size_t)std::max<int64_t>(S.rhs_total, 1) * ldw);
     memset((void*)tbuf.data(), 0xFF, tbuf.size() * sizeof(T));
     memset((void*)W, 0xFF, sizeof(T) * (size_t)S.n * ldw);
     const T* L = (const T*)e->L.data();

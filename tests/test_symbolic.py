@@ -39,7 +39,24 @@ def _check_structure(S):
     assert sorted(S.level_sn.tolist()) == list(range(S.nsn))
     assert max(S.s(J) for J in range(S.nsn)) <= 256
     assert S.linv_off[-1] == sum(S.s(J) ** 2 for J in range(S.nsn))
-    assert S.upd_off[-1] == sum(S.u(J) ** 2 for J in range(S.nsn))
+    # update matrices / update vectors are pooled by liveness: supernode J owns its region from level(J) to
+    # level(parent(J)); regions of supernodes that are alive at the same time never overlap, the pool is no larger
+    # than the layout without reuse
+    assert S.upd_off[-1] <= sum(S.u(J) ** 2 for J in range(S.nsn))
+    for off, size, total in ((S.upd_off, lambda J: S.u(J) ** 2, int(S.upd_off[-1])),
+                             (S.rhs_off, lambda J: S.u(J), None)):
+        iv = []
+        for J in range(S.nsn):
+            P = S.sn_parent[J]
+            if size(J) == 0:
+                continue
+            iv.append((int(S.sn_level[J]), int(S.sn_level[P]) if P >= 0 else int(S.sn_level[J]), int(off[J]),
+                       int(off[J]) + size(J)))
+            assert total is None or iv[-1][3] <= total
+        for l in range(S.nlevels):
+            alive = sorted((a, b) for (l0, l1, a, b) in iv if l0 <= l <= l1)
+            for (a0, b0), (a1, b1) in zip(alive, alive[1:]):
+                assert b0 <= a1, "live regions overlap"
 
 
 @pytest.mark.parametrize("n", [371, 1357])
