@@ -350,7 +350,11 @@ def _run_ours(args):
                    f"shift generation replicated",
                    "l2_policy": "inputs larger than L2: factor panels + RHS/solution panels + X factor exceed 126 MB",
                    "adi_iters_per_timed_step": ct.iters, "rank_X_and_residual": ct.ranks,
-                   "symbolic": info},
+                   "symbolic": info,
+                   # opt-in code paths selected through the environment; empty = defaults
+                   "opt_in": {k: os.environ[k] for k in ("DRE_SWEEP2", "DRE_DIAG_NARROW_MIN", "DRE_RR_EAGER",
+                                                         "DRE_LEAF_SIZE", "DRE_MAX_SNODE", "DRE_NT8",
+                                                         "DRE_SYMBOLIC_THREADS") if k in os.environ}},
         "clocks": clocks,
         "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
         "gpu_counters": {k: st[k] for k in ("factorizations", "solves", "spmms", "grams", "tallgemms")},
