@@ -100,3 +100,39 @@ def test_emulated_lockstep_parity_ros2_complex_shifts(emulated, sweep2):
     """One Ros2 step (two ADI solves, complex shift pairs: the complex-symmetric factorization and sweeps)."""
     emulated(sweep2=sweep2)
     _lockstep(371, 1, 2)
+
+
+def test_emulated_adi_free_run_tiny_random_and_stepping(emulated):
+    """test/tiny_random.jl:10-57 through the emulated C ABI: standalone GALE ADI with its own Projection(2) shifts
+    (dre_rrqr, SpMM, Gram restrictions) on a random SPD pencil with a dense indefinite core, against the oracle run
+    iteration by iteration and against dense Bartels-Stewart; the stepping API; Cyclic(Heuristic) shifts (Arnoldi
+    with single-vector shifted solves)."""
+    from tests import test_gpu_parity as P
+
+    emulated()
+    P.test_adi_tiny_random_vs_oracle_and_dense(0)
+    n, g = 50, 4
+    rng = np.random.default_rng(3)
+    E, A = dre_b200.pencils.random_spd_pencil(n, seed=3)
+    G = rng.random((n, g))
+    prob_o = O.GALEProblem(E, A, -2 * O.lowrank(G, -np.eye(g)))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Xg = api.solve(api.GALEProblem(E, A, -2 * api.lowrank(G, -np.eye(g))),
+                       api.ADI(shifts=api.Cyclic(api.Heuristic(4, 8, 8)), maxiters=200))
+    assert O.delta(Xg.to_dense(), O.bartels_stewart(prob_o)) < 1e-9
+
+
+def test_emulated_ros1_free_run_first_step(emulated):
+    """One Ros1 step at n = 371 with the path's own Projection(2) shifts (no replay): K(t) within 1e-8 of the
+    oracle's free run (the first step is well conditioned, tests/test_gpu_parity.py::test_ros1_free_run_371)."""
+    from tests import test_gpu_parity as P
+
+    emulated()
+    so, ro = P._oracle_run(371, 1, O.Ros1(), dt=-100.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sg, rg = P._gpu_run(371, 1, api.Ros1(), dt=-100.0)
+    for Ko, Kg in zip(so.K, sg.K):
+        assert np.linalg.norm(Kg - Ko) <= 1e-8 * np.linalg.norm(Ko)
+    assert abs(rg.runs[0]["iters"] - ro.runs[0]["iters"]) <= 0.4 * ro.runs[0]["iters"]
