@@ -61,6 +61,7 @@ void launch_gather_rows(double* Wt, int64_t ldw, const double* V, int64_t ldv, c
                         int len, cudaStream_t st, int64_t* launches);
 
 // ---------------- sparse: CSR SpMM ----------------
+extern int spmm_variant;   // 1 = k_spmm, 2 = k_spmm2 (indices broadcast by shuffles, two nonzeros in flight)
 // Y[row][c] = beta*Y[row][c] + alpha * sum_j val[row,j] * X[col_j][c]      (row-major panels)
 void launch_spmm(const int32_t* ptr, const int32_t* col, const double* val, int64_t n, double alpha,
                  const double* X, int64_t ldx, double beta, double* Y, int64_t ldy, int cols, cudaStream_t st,

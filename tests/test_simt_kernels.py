@@ -122,16 +122,22 @@ def test_emulated_sweeps_with_extra_rhs_panel():
     S.close()
 
 
-def test_emulated_spmm():
+@pytest.mark.parametrize("variant", [1, 2])
+def test_emulated_spmm(variant):
+    """k_spmm and the opt-in k_spmm2 (DRE_SPMM2): 1 / 6 / 45 / 150 panel columns (one and two 128-column passes)."""
     n = 371
     E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
     S = emu.Solver(E, A)
     rng = np.random.default_rng(7)
-    for cols in (1, 6, 45):
-        X, Y = rng.standard_normal((n, cols)), rng.standard_normal((n, cols))
-        assert _rel(S.spmm("E", -0.7, X, 1.0, Y), Y - 0.7 * (E @ X)) < 1e-13
-        assert _rel(S.spmm("A", 2.0, X, 0.0, Y), 2.0 * (A @ X)) < 1e-13
-    S.close()
+    emu.set_spmm_variant(variant)
+    try:
+        for cols in (1, 6, 45, 150):
+            X, Y = rng.standard_normal((n, cols)), rng.standard_normal((n, cols))
+            assert _rel(S.spmm("E", -0.7, X, 1.0, Y), Y - 0.7 * (E @ X)) < 1e-13
+            assert _rel(S.spmm("A", 2.0, X, 0.0, np.full_like(Y, np.nan)), 2.0 * (A @ X)) < 1e-13
+    finally:
+        emu.set_spmm_variant(1)
+        S.close()
 
 
 @pytest.mark.parametrize("n,a,b", [(500, 7, 70), (333, 12, 200), (700, 64, 64), (257, 45, 130), (130, 70, 300),
