@@ -42,6 +42,14 @@ struct Arena {
     size_t next_chunk = (size_t)2 << 30;
     static size_t align_up(size_t b) { return (b + 511) & ~(size_t)511; }
     void* alloc(size_t bytes, size_t* got) {
+#ifdef DRE_SIMT_EMU
+        // emulator test tier (tests/simt/): one NaN-filled heap block per request, exactly as large as asked for, so
+        // that an address sanitizer sees every overrun and a read of never-written memory poisons the result
+        *got = bytes;
+        void* q = malloc(std::max<size_t>(bytes, 1));
+        if (q) memset(q, 0xFF, bytes);
+        return q;
+#endif
         bytes = align_up(std::max<size_t>(bytes, 512));
         for (int pass = 0; pass < 2; ++pass) {
             for (Chunk& ch : chunks)
@@ -77,6 +85,11 @@ struct Arena {
         return nullptr;
     }
     void release(void* p, size_t bytes) {
+#ifdef DRE_SIMT_EMU
+        (void)bytes;
+        free(p);
+        return;
+#endif
         for (Chunk& ch : chunks) {
             char* q = (char*)p;
             if (q < ch.base || q >= ch.base + ch.size) continue;
@@ -110,7 +123,11 @@ struct DBuf {
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) { arena->release(p, bytes); p = nullptr; cap = 0; bytes = 0; }
+#ifdef DRE_SIMT_EMU
+        const size_t want = n;   // no slack under the emulator: overruns must be visible
+#else
         const size_t want = n + n / 2 + 64;
+#endif
         size_t got = 0;
         void* q = arena->alloc(want * sizeof(T), &got);
         if (!q) return cudaErrorMemoryAllocation;
