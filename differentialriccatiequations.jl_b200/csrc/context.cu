@@ -1355,18 +1355,23 @@ int32_t dre_ldlt_norm(dre_context* c, dre_view L, const double* D, int64_t ldd, 
     if ((rc = gram_dev(c, vptr(c, L), vld(c, L), k, vptr(c, L), vld(c, L), k, c->sym.n, nullptr, c->gbuf.p, k, nullptr,
                        0)))
         return rc;
-    if ((rc = ensure_pinned(c, (size_t)k * k + k))) return rc;
+    if ((rc = ensure_pinned(c, (size_t)k * k + k + 2))) return rc;
     if (diag) {
-        CU(cudaStreamSynchronize(c->st));
+        // One host synchronisation per call (this runs once per ADI iteration): the pinned staging buffer is never
+        // in flight when a C-ABI call starts (every asynchronous copy that touches it is followed by a
+        // synchronisation inside the call that issued it), and the error flag rides on the same read-back.
         for (int i = 0; i < k; ++i) c->h_pinned[i] = D[i + (int64_t)i * ldd];
         CU(c->small.ensure(k + 8));
         CU(cudaMemcpyAsync(c->small.p + 8, c->h_pinned, k * sizeof(double), cudaMemcpyHostToDevice, c->st));
         launch_norm_diag(c->gbuf.p, k, k, c->small.p + 8, c->small.p, c->st, &c->stats.kernel_launches);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(c->h_pinned + k, c->small.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        int32_t* hflag = reinterpret_cast<int32_t*>(c->h_pinned + k + 1);
+        CU(cudaMemcpyAsync(hflag, c->d_errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
         const double v2 = c->h_pinned[k];
         *out = std::fabs(alpha) * std::sqrt(std::max(v2, 0.0));
+        return *hflag != 0 ? check_errflag(c) : DRE_OK;   // (check_errflag resets the flag and words the message)
     } else {
         CU(cudaMemcpyAsync(c->h_pinned, c->gbuf.p, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
