@@ -904,6 +904,13 @@ int32_t dre_create(int32_t device, dre_context** out) {
     if (prop.major < 10) return bail("libdre_b200 is built for sm_100a (B200) only");
     c->sm_count = prop.multiProcessorCount;
     if (const char* ev = getenv("DRE_SWEEP2")) c->sweep2 = atoi(ev) != 0;
+    // launcher variants (process-wide, re-read whenever a context is created so that tests can switch them)
+    {
+        const char* ev = getenv("DRE_SPMM2");
+        spmm_variant = (ev && atoi(ev) != 0) ? 2 : 1;
+        ev = getenv("DRE_DIAG_NARROW_MIN");
+        diag_narrow_min = ev ? std::max(1, atoi(ev)) : (1 << 30);
+    }
     e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     for (auto& fs : c->slot) {

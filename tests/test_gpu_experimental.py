@@ -74,3 +74,31 @@ def test_row_split_sweeps_lockstep_parity(sweep2, n, nsteps, ros):
         ra = np.array([x for _, x in a_["res"]])
         rb = np.array([x for _, x in b_["res"]])
         assert np.max(np.abs(ra - rb) / ra) <= 1e-10
+
+
+def test_spmm2_and_narrow_diag(monkeypatch):
+    """DRE_SPMM2=1 (k_spmm2) against SciPy, and DRE_DIAG_NARROW_MIN=1 (64-thread k_diag on every level): the block
+    solve must not change by a single bit (both knobs are re-read whenever a context is created)."""
+    n = 5177
+    E, A, B, C, _ = pencils.rail_pencil(n)
+    rng = np.random.default_rng(4)
+    R = rng.standard_normal((n, 250))
+    F = api.PencilCombo(1.0, -1.0 / 200.0)
+    M = (A + (-1.0 / 200.0 - 0.37) * E).tocsc()
+    outs = []
+    for narrow in (None, "1"):
+        if narrow:
+            monkeypatch.setenv("DRE_DIAG_NARROW_MIN", narrow)
+        monkeypatch.setenv("DRE_SPMM2", "1")
+        api.reset_backend()
+        api.upload_pencil(E, A)
+        X = api.DeviceMatrix.from_host(R)
+        Y = api.spmm("E", X, alpha=-0.7, Y=api.DeviceMatrix.from_host(R), beta=1.0)
+        assert _rel(Y.to_host(), R - 0.7 * (E @ R)) < 1e-13
+        out = api.solve_block(api.BlockLinearProblem(F, X), mu=-0.37).to_host()
+        assert _rel(M @ out, R) < 1e-11
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    monkeypatch.delenv("DRE_SPMM2")
+    monkeypatch.delenv("DRE_DIAG_NARROW_MIN")
+    api.reset_backend()

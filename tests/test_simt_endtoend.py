@@ -136,3 +136,27 @@ def test_emulated_ros1_free_run_first_step(emulated):
     for Ko, Kg in zip(so.K, sg.K):
         assert np.linalg.norm(Kg - Ko) <= 1e-8 * np.linalg.norm(Ko)
     assert abs(rg.runs[0]["iters"] - ro.runs[0]["iters"]) <= 0.4 * ro.runs[0]["iters"]
+
+
+def test_emulated_launcher_knobs_through_the_environment(emulated, monkeypatch):
+    """DRE_SPMM2 / DRE_DIAG_NARROW_MIN are re-read when a context is created: SpMM against SciPy with the shuffle
+    variant, and a block solve that is bit-identical with 64-thread k_diag CTAs on every level."""
+    n = 1357
+    E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
+    rng = np.random.default_rng(4)
+    R = rng.standard_normal((n, 40))
+    F = api.PencilCombo(1.0, -1.0 / 200.0)
+    outs = []
+    for narrow in (None, "1"):
+        if narrow:
+            monkeypatch.setenv("DRE_DIAG_NARROW_MIN", narrow)
+        monkeypatch.setenv("DRE_SPMM2", "1")
+        emulated()
+        api.upload_pencil(E, A)
+        X = api.DeviceMatrix.from_host(R)
+        Y = api.spmm("E", X, alpha=-0.7, Y=api.DeviceMatrix.from_host(R), beta=1.0)
+        assert _rel(Y.to_host(), R - 0.7 * (E @ R)) < 1e-13
+        outs.append(api.solve_block(api.BlockLinearProblem(F, X), mu=-0.37).to_host())
+    M = (A + (-1.0 / 200.0 - 0.37) * E).tocsc()
+    assert _rel(M @ outs[0], R) < 1e-11
+    assert np.array_equal(outs[0], outs[1])
