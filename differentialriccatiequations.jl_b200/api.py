@@ -371,6 +371,22 @@ def norm(X: LDLt) -> float:
     return float(out.value)
 
 
+def dot(X1: LDLt, X2: LDLt) -> float:
+    """src/LDLt.jl:91-108 -- Frobenius inner product tr(X1' X2): one Gram product A'C on the device
+    (dre_gemm_tn), the k1 x k2 core algebra on the host."""
+    if X1.n != X2.n:
+        raise ValueError("DimensionMismatch")
+    concatenate_(X1)
+    concatenate_(X2)
+    alpha, A, B = X1.alphas[0], X1.Ls[0], np.asarray(X1.Ds[0])
+    beta, Cm, D = X2.alphas[0], X2.Ls[0], np.asarray(X2.Ds[0])
+    if A.ncols == 0 or Cm.ncols == 0:
+        return 0.0
+    AtC = gemm_tn(A, Cm)
+    M = (B.T @ AtC @ D) * (alpha * beta)
+    return float(np.sum(AtC * M))
+
+
 # =============================================================================================
 # operators: pencil combinations and LowRankUpdate (src/LowRankUpdate.jl)
 # =============================================================================================
@@ -1027,6 +1043,119 @@ def solve_(cache: ADICache) -> LDLt:
 
 
 # =============================================================================================
+# low-rank (F)GMRES (src/lyapunov/gmres.jl, types.jl:44-52) -- SURVEY 8f rank 2
+# =============================================================================================
+class GMRES:  # types.jl:44-52
+    def __init__(self, *, maxiters=3, maxrestarts=0, reltol=None, abstol=None, ignore_initial_guess=False,
+                 compression=True, preconditioner=None):
+        self.maxiters, self.maxrestarts, self.reltol, self.abstol = maxiters, maxrestarts, reltol, abstol
+        self.ignore_initial_guess, self.compression, self.preconditioner = ignore_initial_guess, compression, preconditioner
+
+
+def lyapunov_operator(E, A, X: LDLt) -> LDLt:
+    """gmres.jl:105-117 -- L*X = A'XE + E'XA = a * lowrank([E'Z A'Z], [0 Y; Y 0]); two SpMMs into column views."""
+    a, Z, Y = X.destructure()
+    Y = np.asarray(Y)
+    k = Z.ncols
+    be = backend()
+    Z2 = DeviceMatrix.empty(2 * k)
+    spmm("E", Z, 1.0, Z2.cols(0, k), 0.0)
+    AtZ = _adj_matmul(A, Z)
+    be.check(be.lib.dre_mat_copy(be.h, Z2.cols(k, 2 * k).view, AtZ.view))
+    Y2 = np.zeros((2 * k, 2 * k), order="F")
+    Y2[:k, k:] = Y
+    Y2[k:, :k] = Y
+    return LDLt([a], [Z2], [Y2])
+
+
+def specialize(alg, prob):
+    """gmres.jl:119-134 -- shift parameters that depend only on (E, A) are computed once per GMRES solve."""
+    if isinstance(alg, Cyclic):
+        return Cyclic(specialize(alg.inner, prob))
+    if isinstance(alg, Heuristic):
+        return list(_take_many(shifts_init(alg, prob)))
+    if isinstance(alg, ADI):
+        out = ADI.__new__(ADI)
+        out.__dict__.update(alg.__dict__)
+        out.shifts = specialize(alg.shifts, prob)
+        return out
+    if isinstance(alg, GMRES):
+        out = GMRES.__new__(GMRES)
+        out.__dict__.update(alg.__dict__)
+        out.preconditioner = specialize(alg.preconditioner, prob)
+        return out
+    return alg
+
+
+def _solve_gmres(prob: GALEProblem, alg: GMRES, *, initial_guess=None, abstol=None, observer=None) -> LDLt:
+    """CommonSolve.solve(::GALEProblem, ::GMRES) -- gmres.jl:7-103 (FGMRES, Algorithm 2.2 of Saad 1993, on
+    low-rank iterates): residuals, operator applications, inner products, norms and compressions run on the GPU
+    through the same C-ABI calls as the ADI path; the (maxiters+1) x maxiters Hessenberg problem on the host."""
+    _observe(observer, "observe_gale_start", prob, alg)
+    prob = _device_problem(prob)
+    E, A, Cm = prob.E, prob.A, prob.C
+    maxiters, maxrestarts, compression = alg.maxiters, alg.maxrestarts, alg.compression
+    if alg.ignore_initial_guess or initial_guess is None:
+        initial_guess = Cm.zero()
+    X = initial_guess.to_device_()
+    reltol = alg.reltol if alg.reltol is not None else prob.A.shape[0] * EPS
+    if abstol is None:
+        abstol = alg.abstol if alg.abstol is not None else reltol * norm(Cm)
+    preconditioner = specialize(alg.preconditioner, prob)
+    H = np.zeros((maxiters + 1, maxiters))
+    b = np.zeros(maxiters + 1)
+    m, residual_norm, restarts = 0, np.inf, 0
+    for restarts in range(maxrestarts + 1):
+        m = 0
+        R0 = residual(prob, X)
+        beta = residual_norm = norm(R0)
+        _observe(observer, "observe_gale_step", 0, X, R0, beta)
+        if beta <= abstol:
+            break
+        V = [None] * (maxiters + 1)
+        Z = [None] * maxiters
+        V[0] = (1.0 / beta) * R0
+        b[:] = 0.0
+        b[0] = beta
+        y = np.zeros(0)
+        for j in range(maxiters):
+            if preconditioner is None:
+                Z[j] = V[j]
+            else:
+                Z[j] = solve(GALEProblem(E, A, V[j]), preconditioner, observer=observer)
+            W = lyapunov_operator(E, A, Z[j])
+            if compression:
+                compress_(W)
+            for i in range(j + 1):
+                H[i, j] = dot(V[i], W)
+                W = W - H[i, j] * V[i]
+            H[j + 1, j] = norm(W)
+            V[j + 1] = (1.0 / H[j + 1, j]) * W
+            m = j + 1
+            Hm, bm = H[:m + 1, :m], b[:m + 1]
+            y = np.linalg.lstsq(Hm, bm, rcond=None)[0]
+            residual_norm = float(np.linalg.norm(bm - Hm @ y))
+            if residual_norm <= abstol:
+                break
+            _observe(observer, "observe_gale_step", m, None, None, residual_norm)
+            if compression:
+                compress_(V[j + 1])
+        for j in range(m):
+            X = X + (-y[j]) * Z[j]
+        if compression and X.rank() > 0:
+            compress_(X)
+        _observe(observer, "observe_gale_step", m, X, None, residual_norm)
+        if residual_norm <= abstol:
+            break
+    if residual_norm > abstol:
+        _observe(observer, "observe_gale_failed")
+        warnings.warn("GMRES did not converge")
+    iters = restarts * maxiters + m
+    _observe(observer, "observe_gale_done", iters, X, None, residual_norm)
+    return X
+
+
+# =============================================================================================
 # Riccati drivers (src/riccati/*.jl)
 # =============================================================================================
 class GDREProblem:  # riccati/types.jl:11-20
@@ -1308,6 +1437,8 @@ def solve(prob, alg, **kw):
     (src/DifferentialRiccatiEquations.jl:78-94 for GDRE; solve = solve!(init(...)) for GALE)."""
     if isinstance(prob, GALEProblem) and isinstance(alg, ADI):
         return solve_(init(prob, alg, **kw))
+    if isinstance(prob, GALEProblem) and isinstance(alg, GMRES):
+        return _solve_gmres(prob, alg, **kw)
     if isinstance(prob, GDREProblem):
         dt = kw.pop("dt")
         save_state = kw.pop("save_state", False)

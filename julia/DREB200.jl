@@ -90,6 +90,7 @@ function Base.Matrix(D::DeviceMatrix)
     M
 end
 Base.similar(D::DeviceMatrix) = DeviceMatrix(D.p.ctx, D.ncols)
+view_cols(D::DeviceMatrix, r::UnitRange{Int}) = DeviceMatrix(D.p, D.col0 + first(r) - 1, length(r))   # no copy
 
 lowrank_device(E, A, L::Matrix, D::Matrix) = (set_pencil!(context(), E, A); DRE.lowrank(DeviceMatrix(context(), L), D))
 
@@ -196,6 +197,31 @@ function gemm_tn(X::DeviceMatrix, Y::DeviceMatrix)
     check(X.p.ctx, ccall((:dre_gemm_tn, LIB), Int32, (Ptr{Cvoid}, View, View, Ptr{Float64}, Int64),
                          X.p.ctx.h, view_of(X), view_of(Y), out, stride(out, 2)))
     out
+end
+
+# dot(::LDLᵀ, ::LDLᵀ) (src/LDLt.jl:91-108), the inner product of the low-rank (F)GMRES (src/lyapunov/gmres.jl:52-55):
+# the reference loops over the n rows of the outer factors; here one Gram product A'C on the device and
+# k1 x k2 algebra on the host.  With this method (and compress!/norm above, spmm! for LyapunovOperator * X) the
+# reference's generic GMRES driver runs unchanged on DeviceMatrix-backed LDLᵀ objects.
+function LinearAlgebra.dot(X1::DRE.LDLᵀ{Float64,DeviceMatrix,Matrix{Float64}},
+                           X2::DRE.LDLᵀ{Float64,DeviceMatrix,Matrix{Float64}})
+    DRE.concatenate!(X1)
+    DRE.concatenate!(X2)
+    α, A, B = X1.alphas[1], X1.Ls[1], X1.Ds[1]
+    β, C, D = X2.alphas[1], X2.Ls[1], X2.Ds[1]
+    AtC = gemm_tn(A, C)
+    M = (B' * AtC * D) .* (α * β)
+    sum(AtC .* M)
+end
+
+function Base.:(*)(L::DRE.LyapunovOperator, X::DRE.LDLᵀ{Float64,DeviceMatrix,Matrix{Float64}})   # gmres.jl:105-117
+    a, Z, Y = X
+    k = size(Z, 2)
+    Z2 = DeviceMatrix(Z.p.ctx, 2k)
+    spmm!(view_cols(Z2, 1:k), 'E', Z, 1.0, 0.0)
+    spmm!(view_cols(Z2, k+1:2k), 'A', Z, 1.0, 0.0)          # symmetric pencil: A'Z == AZ (closed loop: see api._adj_matmul)
+    O = zero(Y)
+    a * DRE.lowrank(Z2, [O Y; Y O])
 end
 
 # The remaining specialisations (residual, take_many!(::ProjectionShiftIterator), the K update and RHS

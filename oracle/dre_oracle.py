@@ -831,9 +831,126 @@ def adi_solve(cache: ADICache) -> LDLt:
     return cache.X
 
 
-def solve_gale(prob: GALEProblem, alg: ADI, **kw) -> LDLt:
-    """CommonSolve.solve(prob, alg; kw...) = solve!(init(prob, alg; kw...))."""
+def solve_gale(prob: GALEProblem, alg, **kw) -> LDLt:
+    """CommonSolve.solve(prob, alg; kw...) = solve!(init(prob, alg; kw...)) for ADI; GMRES has its own driver."""
+    if isinstance(alg, GMRES):
+        return solve_gale_gmres(prob, alg, **kw)
     return adi_solve(adi_init(prob, alg, **kw))
+
+
+# --------------------------------------------------------------------------------------------
+# LDLt.jl dot, lyapunov/gmres.jl  (SURVEY 8f rank 2: low-rank FGMRES with an ADI preconditioner)
+# --------------------------------------------------------------------------------------------
+def dot(X1: LDLt, X2: LDLt) -> float:
+    """src/LDLt.jl:91-108 -- Frobenius inner product tr(X1' X2) without forming n x n matrices."""
+    if X1.n != X2.n:
+        raise ValueError("DimensionMismatch")
+    concatenate(X1)
+    concatenate(X2)
+    alpha, A, B = X1.alphas[0], X1.Ls[0], X1.Ds[0]
+    beta, C, D = X2.alphas[0], X2.Ls[0], X2.Ds[0]
+    AtC = A.T @ C
+    M = (B.T @ AtC @ D) * (alpha * beta)
+    return float(np.sum(AtC * M))   # sum_i a_i' M c_i over the rows a_i of A, c_i of C
+
+
+class GMRES:  # src/lyapunov/types.jl:44-52
+    def __init__(self, *, maxiters=3, maxrestarts=0, reltol=None, abstol=None, ignore_initial_guess=False,
+                 compression=True, preconditioner=None):
+        self.maxiters, self.maxrestarts, self.reltol, self.abstol = maxiters, maxrestarts, reltol, abstol
+        self.ignore_initial_guess, self.compression, self.preconditioner = ignore_initial_guess, compression, preconditioner
+
+
+def lyapunov_operator(E, A, X: LDLt) -> LDLt:
+    """src/lyapunov/gmres.jl:105-117 -- L*X = A'XE + E'XA as a*lowrank([E'Z A'Z], [0 Y; Y 0])."""
+    a, Z, Y = X.destructure()
+    k = Y.shape[0]
+    Z2 = _hcat([E.T @ Z, _adj_matmul(A, Z)])
+    Y2 = np.zeros((2 * k, 2 * k))
+    Y2[:k, k:] = Y
+    Y2[k:, :k] = Y
+    return a * lowrank(Z2, Y2)
+
+
+def specialize(alg, prob):
+    """src/lyapunov/gmres.jl:119-134 -- shift parameters that only depend on (E, A) are computed once."""
+    if isinstance(alg, Cyclic):
+        return Cyclic(specialize(alg.inner, prob))
+    if isinstance(alg, Heuristic):
+        return list(_take_many(shifts_init(alg, prob)))
+    if isinstance(alg, (ADI, GMRES)):
+        out = copy.copy(alg)
+        if isinstance(alg, ADI):
+            out.shifts = specialize(alg.shifts, prob)
+        else:
+            out.preconditioner = specialize(alg.preconditioner, prob)
+        return out
+    return alg
+
+
+def solve_gale_gmres(prob: GALEProblem, alg: GMRES, *, initial_guess=None, abstol=None, observer=None) -> LDLt:
+    """src/lyapunov/gmres.jl:7-103 (Algorithm 2.2 of Saad's FGMRES paper on low-rank iterates)."""
+    _observe(observer, "observe_gale_start", prob, alg)
+    E, A, C = prob.E, prob.A, prob.C
+    maxiters, maxrestarts, compression = alg.maxiters, alg.maxrestarts, alg.compression
+    if alg.ignore_initial_guess or initial_guess is None:
+        initial_guess = C.zero()
+    X = initial_guess
+    reltol = alg.reltol if alg.reltol is not None else A.shape[0] * EPS
+    if abstol is None:
+        abstol = alg.abstol if alg.abstol is not None else reltol * norm(C)
+    preconditioner = specialize(alg.preconditioner, prob)
+    H = np.zeros((maxiters + 1, maxiters))
+    b = np.zeros(maxiters + 1)
+    m, residual_norm, restarts = 0, np.inf, 0
+    for restarts in range(maxrestarts + 1):
+        m = 0
+        R0 = gale_residual(prob, X)
+        beta = residual_norm = norm(R0)
+        _observe(observer, "observe_gale_step", 0, X, R0, beta)
+        if beta <= abstol:
+            break
+        V = [None] * (maxiters + 1)
+        Z = [None] * maxiters
+        V[0] = (1.0 / beta) * R0
+        b[:] = 0.0
+        b[0] = beta
+        y = np.zeros(0)
+        for j in range(maxiters):
+            if preconditioner is None:
+                Z[j] = V[j]
+            else:
+                Z[j] = solve_gale(GALEProblem(E, A, V[j]), preconditioner, observer=observer)
+            W = lyapunov_operator(E, A, Z[j])
+            if compression:
+                compress(W)
+            for i in range(j + 1):
+                H[i, j] = dot(V[i], W)
+                W = W - H[i, j] * V[i]
+            H[j + 1, j] = norm(W)
+            V[j + 1] = (1.0 / H[j + 1, j]) * W
+            m = j + 1
+            Hm, bm = H[:m + 1, :m], b[:m + 1]
+            y = np.linalg.lstsq(Hm, bm, rcond=None)[0]
+            residual_norm = float(np.linalg.norm(bm - Hm @ y))
+            if residual_norm <= abstol:
+                break
+            _observe(observer, "observe_gale_step", m, None, None, residual_norm)
+            if compression:
+                compress(V[j + 1])
+        for j in range(m):
+            X = X + (-y[j]) * Z[j]
+        if compression:
+            compress(X)
+        _observe(observer, "observe_gale_step", m, X, None, residual_norm)
+        if residual_norm <= abstol:
+            break
+    if residual_norm > abstol:
+        _observe(observer, "observe_gale_failed")
+        warnings.warn("GMRES did not converge")
+    iters = restarts * maxiters + m
+    _observe(observer, "observe_gale_done", iters, X, None, residual_norm)
+    return X
 
 
 # --------------------------------------------------------------------------------------------

@@ -102,3 +102,33 @@ def test_spmm2_and_narrow_diag(monkeypatch):
     monkeypatch.delenv("DRE_SPMM2")
     monkeypatch.delenv("DRE_DIAG_NARROW_MIN")
     api.reset_backend()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_gmres_and_fgmres_tiny_random(seed):
+    """SURVEY 8f rank 2 (test/tiny_random.jl:25-46): low-rank GMRES and FGMRES with an ADI preconditioner on the GPU
+    against dense Bartels-Stewart (developed on the emulator: tests/test_simt_endtoend.py)."""
+    from oracle import dre_oracle as O
+
+    api.reset_backend()
+    n, g = 50, 4
+    rng = np.random.default_rng(seed)
+    E, A = pencils.random_spd_pencil(n, seed=seed)
+    G = rng.random((n, g))
+    prob_o = O.GALEProblem(E, A, -2 * O.lowrank(G, -np.eye(g)))
+    res0 = O.norm(prob_o.C)
+    X_ref = O.bartels_stewart(prob_o)
+
+    def run(alg):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return api.solve(api.GALEProblem(E, A, -2 * api.lowrank(G, -np.eye(g))), alg).to_dense()
+
+    X_gmres = run(api.GMRES(maxiters=5, reltol=1e-8))
+    X_fgmres = run(api.GMRES(maxiters=3, maxrestarts=0, reltol=1e-10, preconditioner=api.ADI(
+        maxiters=10, shifts=api.Cyclic(api.Heuristic(10, 10, 10)), compression_interval=20, warn_convergence=False)))
+    assert np.linalg.norm(O.gale_residual_dense(prob_o, X_gmres)) / res0 < 2e-8
+    assert np.linalg.norm(O.gale_residual_dense(prob_o, X_fgmres)) / res0 < 1e-10
+    assert O.delta(X_gmres, X_ref) < 2e-8
+    assert O.delta(X_fgmres, X_ref) < 1e-10
+    api.reset_backend()

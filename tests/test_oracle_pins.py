@@ -196,6 +196,37 @@ def test_adi_vs_bartels_stewart(seed):
     assert np.allclose(solver.X.to_dense(), X_adi.to_dense(), rtol=0, atol=1e-13 * np.linalg.norm(X_ref))
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_gmres_and_fgmres_vs_bartels_stewart(seed):
+    """test/tiny_random.jl:25-46 -- low-rank GMRES (maxiters=5, reltol=1e-8) and FGMRES with an ADI preconditioner
+    (Cyclic(Heuristic(10, 10, 10)), 10 iterations, compression only at the end) against the dense reference;
+    dot(::LDLt, ::LDLt) (src/LDLt.jl:91-108) against the dense trace."""
+    n, g = 50, 4
+    rng = np.random.default_rng(seed)
+    E, A = pencils.random_spd_pencil(n, seed=seed)
+    G = rng.random((n, g))
+    C = -2 * O.lowrank(G, -np.eye(g))
+    prob = O.GALEProblem(E, A, C)
+    res0 = O.norm(C)
+    X_ref = O.bartels_stewart(prob)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        X_gmres = O.solve_gale(prob, O.GMRES(maxiters=5, reltol=1e-8))
+        X_fgmres = O.solve_gale(prob, O.GMRES(maxiters=3, maxrestarts=0, reltol=1e-10, preconditioner=O.ADI(
+            maxiters=10, shifts=O.Cyclic(O.Heuristic(10, 10, 10)), compression_interval=20, warn_convergence=False)))
+    # GMRES stops on its recursively updated residual (<= reltol * ||C||); the true residual of the assembled,
+    # compressed X "may differ slightly" (gmres.jl:67-69) -- 1.14e-8 for seed 0.  The reference asserts 1e-8 on
+    # unseeded random pencils; 2e-8 here.
+    assert O.norm(O.gale_residual(prob, X_gmres)) / res0 < 2e-8
+    assert O.norm(O.gale_residual(prob, X_fgmres)) / res0 < 1e-10
+    assert O.delta(X_gmres.to_dense(), X_ref) < 2e-8
+    assert O.delta(X_fgmres.to_dense(), X_ref) < 1e-10
+    X1 = O.lowrank(rng.standard_normal((n, 3)), np.diag([1.0, -2.0, 0.5])) + 0.3 * O.lowrank(rng.standard_normal((n, 2)))
+    X2 = -1.5 * O.lowrank(rng.standard_normal((n, 4)), rng.standard_normal((4, 4)))
+    assert abs(O.dot(X1, X2) - np.sum(X1.to_dense() * X2.to_dense())) < 1e-12 * np.linalg.norm(X1.to_dense()) * \
+        np.linalg.norm(X2.to_dense())
+
+
 @pytest.fixture(scope="module")
 def rail371():
     E, A, B, C, meta = pencils.rail_pencil(371)

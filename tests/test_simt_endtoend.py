@@ -160,3 +160,42 @@ def test_emulated_launcher_knobs_through_the_environment(emulated, monkeypatch):
     M = (A + (-1.0 / 200.0 - 0.37) * E).tocsc()
     assert _rel(M @ outs[0], R) < 1e-11
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_emulated_gmres_and_fgmres(emulated, seed):
+    """test/tiny_random.jl:25-46 through the emulated C ABI: low-rank GMRES(maxiters=5, reltol=1e-8) and FGMRES with an
+    ADI preconditioner (Cyclic(Heuristic(10, 10, 10)), 10 iterations) against dense Bartels-Stewart and against the
+    oracle's GMRES; dot(::LDLt, ::LDLt) against the dense trace.  (2e-8 instead of the reference's 1e-8: see
+    tests/test_oracle_pins.py::test_gmres_and_fgmres_vs_bartels_stewart.)"""
+    emulated()
+    n, g = 50, 4
+    rng = np.random.default_rng(seed)
+    E, A = dre_b200.pencils.random_spd_pencil(n, seed=seed)
+    G = rng.random((n, g))
+    prob_o = O.GALEProblem(E, A, -2 * O.lowrank(G, -np.eye(g)))
+    res0 = O.norm(prob_o.C)
+    X_ref = O.bartels_stewart(prob_o)
+
+    def run(alg):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return api.solve(api.GALEProblem(E, A, -2 * api.lowrank(G, -np.eye(g))), alg).to_dense()
+
+    X_gmres = run(api.GMRES(maxiters=5, reltol=1e-8))
+    X_fgmres = run(api.GMRES(maxiters=3, maxrestarts=0, reltol=1e-10, preconditioner=api.ADI(
+        maxiters=10, shifts=api.Cyclic(api.Heuristic(10, 10, 10)), compression_interval=20, warn_convergence=False)))
+    assert np.linalg.norm(O.gale_residual_dense(prob_o, X_gmres)) / res0 < 2e-8
+    assert np.linalg.norm(O.gale_residual_dense(prob_o, X_fgmres)) / res0 < 1e-10
+    assert O.delta(X_gmres, X_ref) < 2e-8
+    assert O.delta(X_fgmres, X_ref) < 1e-10
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Xo = O.solve_gale(prob_o, O.GMRES(maxiters=5, reltol=1e-8)).to_dense()
+    assert O.delta(X_gmres, Xo) < 1e-9     # same Krylov iterates as the oracle, up to compression round-off
+    L1, L2 = rng.standard_normal((n, 3)), rng.standard_normal((n, 4))
+    D1, D2 = np.diag([1.0, -2.0, 0.5]), rng.standard_normal((4, 4))
+    X1 = api.lowrank(L1, D1).to_device_() + 0.3 * api.lowrank(rng.standard_normal((n, 2))).to_device_()
+    X2 = -1.5 * api.lowrank(L2, D2).to_device_()
+    ref = np.sum(X1.to_dense() * X2.to_dense())
+    assert abs(api.dot(X1, X2) - ref) < 1e-12 * np.linalg.norm(X1.to_dense()) * np.linalg.norm(X2.to_dense())
