@@ -944,12 +944,66 @@ def _prefetch_next_factorization(cache: ADICache):
         queued += 1
 
 
+# Opt-in overlap of the residual norm with the next shifted solve (DRE_ASYNC_NORM=1).  The
+# reference computes norm(residual) after every ADI step only to test for convergence (adi.jl:118-127); the Gram
+# product behind it keeps the whole GPU busy for ~0.4 ms while the sweeps of the next step are latency bound.  With
+# the option on, step_ queues the norm on a side stream (dre_ldlt_norm_begin), starts the solve half of the NEXT step
+# from the already buffered shift while it runs (R is only read), and then collects the norm.  If ADI stops, the
+# speculative block is dropped; otherwise the next step adopts it and only runs its residual update.  Results are
+# identical: the same kernels run on the same data.
+import os as _os
+
+ASYNC_NORM = _os.environ.get("DRE_ASYNC_NORM", "0") not in ("", "0")
+
+
+def _speculate_next_solve(cache: ADICache):
+    """Queue V = (F' + mu E')^-1 R for the next buffered shift; returns (mu, V1, V2 or None) or None."""
+    peek = getattr(cache.shifts_oracle, "peek_many", None)
+    if peek is None or not _fused_inner(cache.alg) or _dist.active():
+        return None
+    if len(cache.shifts) >= cache.alg.maxiters:
+        return None
+    nxt = peek(2)
+    if not nxt:
+        return None
+    mu = complex(nxt[0])
+    if mu.imag != 0 and (len(nxt) < 2 or not np.isclose(complex(nxt[1]), np.conj(mu))):
+        return None
+    be = backend()
+    _, R, _T = cache.residual.destructure()
+    _set_operator(cache.prob.A, transpose=True)
+    V1 = DeviceMatrix.empty(R.ncols)
+    V2 = DeviceMatrix.empty(R.ncols) if mu.imag != 0 else None
+    be.check(be.lib.dre_adi_solve(be.h, mu.real, mu.imag, R.view, V1.view,
+                                  V2.view if V2 is not None else View(-1, 0, 0)))
+    return (mu, V1, V2)
+
+
+def _adopt_speculation(cache: ADICache, mu: complex):
+    """The block solved ahead of time for this shift, if any (and if the residual factor is still the same panel)."""
+    spec = getattr(cache, "_spec", None)
+    cache._spec = None
+    if spec is None:
+        return None
+    smu, V1, V2, Rid = spec
+    _, R, _T = cache.residual.destructure()
+    if smu != complex(mu) or Rid != (R.view.id, R.view.col0, R.view.ncols):
+        return None
+    cache.adopted_speculations = getattr(cache, "adopted_speculations", 0) + 1
+    return V1, V2
+
+
 def perform_single_step_(cache: ADICache, mu: float):
     """adi.jl:149-179: V = (A' + mu E')^-1 R; X += -2 mu alpha V T V'; R -= 2 mu E' V."""
     be = backend()
     prob, alg = cache.prob, cache.alg
     alpha, R, T = cache.residual.destructure()
-    if _fused_inner(alg):
+    adopted = _adopt_speculation(cache, complex(mu)) if _fused_inner(alg) else None
+    if adopted is not None:
+        V = adopted[0]
+        spmm("E", V, -2.0 * mu, R, 1.0)
+        _prefetch_next_factorization(cache)
+    elif _fused_inner(alg):
         # one C-ABI call: numeric LDL^T of A_s + mu E, block sweeps for [R, K'], SMW, SpMM update
         _set_operator(prob.A, transpose=True)
         V = DeviceMatrix.empty(R.ncols)
@@ -981,7 +1035,12 @@ def perform_double_step_(cache: ADICache, mu: complex):
     assert np.isclose(mu_next, np.conj(mu)), (mu, mu_next)
     cache.shifts.append(complex(mu_next))
     _observe(cache.observer, "observe_gale_metadata", "ADI shifts", mu_next)
-    if _fused_inner(alg):
+    adopted = _adopt_speculation(cache, complex(mu)) if _fused_inner(alg) else None
+    if adopted is not None:
+        V1, V2 = adopted
+        spmm("E", V1, -2.0 * math.sqrt(2.0) * mu.real, R, 1.0)
+        _prefetch_next_factorization(cache)
+    elif _fused_inner(alg):
         _set_operator(prob.A, transpose=True)
         V1 = DeviceMatrix.empty(R.ncols)
         V2 = DeviceMatrix.empty(R.ncols)
@@ -1007,6 +1066,27 @@ def perform_double_step_(cache: ADICache, mu: complex):
     cache.shifts_oracle.update(cache.X, R, V1, V2)
 
 
+def _residual_norm_overlapped(cache: ADICache) -> float:
+    """norm(cache.residual); with DRE_ASYNC_NORM=1 the next step's solve is queued while the norm is computed."""
+    X = cache.residual
+    if not ASYNC_NORM or len(X.alphas) != 1 or X.Ls[0].ncols == 0:
+        return norm(X)
+    D = np.asarray(X.Ds[0], dtype=np.float64)
+    if np.count_nonzero(D - np.diag(np.diag(D))) != 0:
+        return norm(X)          # dense core: the synchronous path finishes on the host
+    be = backend()
+    a, L = X.alphas[0], X.Ls[0]
+    d = np.ascontiguousarray(np.diag(D))
+    be.check(be.lib.dre_ldlt_norm_begin(be.h, L.view, capi._dptr(d), float(a)))
+    try:
+        spec = _speculate_next_solve(cache)
+        cache._spec = None if spec is None else (spec[0], spec[1], spec[2], (L.view.id, L.view.col0, L.view.ncols))
+    finally:
+        out = C.c_double(0.0)
+        be.check(be.lib.dre_ldlt_norm_end(be.h, C.byref(out)))
+    return float(out.value)
+
+
 def step_(cache: ADICache):
     """CommonSolve.step!(::ADICache) -- adi.jl:97-128."""
     alg, abstol, observer = cache.alg, cache.abstol, cache.observer
@@ -1019,7 +1099,7 @@ def step_(cache: ADICache):
         perform_double_step_(cache, complex(mu))
     if alg.compression and cache.last_compression >= alg.compression_interval:
         compress_cache_(cache)
-    res_norm = cache.residual_norm = _dist.agree_scalar(norm(cache.residual))
+    res_norm = cache.residual_norm = _dist.agree_scalar(_residual_norm_overlapped(cache))
     i = len(cache.shifts)
     _observe(observer, "observe_gale_step", i, cache.X, cache.residual, res_norm)
     if res_norm <= abstol:

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "dre_symbolic_export", "dre_create", "dre_destroy", "dre_sync", "dre_set_pencil", "dre_get_symbolic_info",
     "dre_mat_create", "dre_mat_free", "dre_mat_upload", "dre_mat_download", "dre_mat_copy", "dre_mat_axpby",
     "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_prefactor", "dre_shift_solve", "dre_adi_step", "dre_adi_solve", "dre_mat_devptr", "dre_get_stream",
-    "dre_ldlt_norm", "dre_ldlt_compress", "dre_hint_orthonormal", "dre_rrqr", "dre_debug_export", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
+    "dre_ldlt_norm", "dre_ldlt_norm_begin", "dre_ldlt_norm_end", "dre_ldlt_compress", "dre_hint_orthonormal", "dre_rrqr", "dre_debug_export", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
     "dre_stats_get",
 ]
 
@@ -103,6 +103,8 @@ def load():
     lib.dre_mat_devptr.argtypes = [p, View, C.POINTER(p), pi64]
     lib.dre_get_stream.argtypes = [p, C.POINTER(p)]
     lib.dre_ldlt_norm.argtypes = [p, View, pdbl, i64, dbl, pdbl]
+    lib.dre_ldlt_norm_begin.argtypes = [p, View, pdbl, dbl]
+    lib.dre_ldlt_norm_end.argtypes = [p, pdbl]
     lib.dre_ldlt_compress.argtypes = [p, i32, C.POINTER(View), C.POINTER(pdbl), pi64, pdbl, dbl, View, pdbl,
                                       C.POINTER(i32)]
     lib.dre_hint_orthonormal.argtypes = [p, View]

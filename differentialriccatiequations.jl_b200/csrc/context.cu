@@ -217,6 +217,15 @@ struct dre_context {
     dre_view op_U{-1, 0, 0}, op_Vt{-1, 0, 0};
 
     dre_view ortho_hint{-1, 0, 0};   // dre_hint_orthonormal: consumed by the next dre_ldlt_compress
+    // asynchronous residual norm (dre_ldlt_norm_begin / _end): own stream, events, workspaces and pinned slot
+    cudaStream_t norm_st = nullptr;
+    cudaEvent_t norm_in = nullptr, norm_done = nullptr;
+    DBuf<double> norm_partial, norm_g, norm_small;
+    double* h_norm = nullptr;
+    size_t h_norm_cap = 0;
+    bool norm_pending = false;
+    double norm_alpha = 0.0;
+    int norm_k = 0;
     // panels
     std::vector<Panel> panels;
     Arena arena;
@@ -239,7 +248,7 @@ namespace {
 
 template <class F>
 void for_each_workspace(dre_context* c, F f) {
-    f(c->tbuf); f(c->Wbuf); f(c->Ybuf); f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
+    f(c->tbuf); f(c->Wbuf); f(c->Ybuf); f(c->norm_partial); f(c->norm_g); f(c->norm_small); f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
     f(c->wsel); f(c->wsel2); f(c->small); f(c->stage); f(c->qws); f(c->pws); f(c->qtmp); f(c->rt); f(c->rt2);
     f(c->tmp_panel); f(c->evals); f(c->cnorm); f(c->syevd_work); f(c->ibuf);
 }
@@ -941,6 +950,8 @@ int32_t dre_create(int32_t device, dre_context** out) {
 
 static void release_pencil(dre_context* c) {
     for (auto& fs : c->slot) if (fs.st) cudaStreamSynchronize(fs.st);
+    if (c->norm_st) cudaStreamSynchronize(c->norm_st);
+    c->norm_pending = false;
     for (void* p : c->owned) cudaFree(p);
     c->owned.clear();
     for (auto& fs : c->slot) {
@@ -1006,6 +1017,10 @@ int32_t dre_destroy(dre_context* c) {
     release_pencil(c);
     for_each_workspace(c, [](auto& w) { w.forget(); });   // the arena (destroyed above) owned their memory
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_norm) cudaFreeHost(c->h_norm);
+    if (c->norm_in) cudaEventDestroy(c->norm_in);
+    if (c->norm_done) cudaEventDestroy(c->norm_done);
+    if (c->norm_st) cudaStreamDestroy(c->norm_st);
     if (c->d_errflag) cudaFree(c->d_errflag);
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1397,6 +1412,61 @@ int32_t dre_ldlt_norm(dre_context* c, dre_view L, const double* D, int64_t ldd, 
         *out = std::fabs(alpha) * std::sqrt(std::max(tr, 0.0));
     }
     return check_errflag(c);
+}
+
+int32_t dre_ldlt_norm_begin(dre_context* c, dre_view L, const double* d, double alpha) {
+    if (!c || !d) return fail(c, DRE_ERR_ARG, "null argument");
+    int rc;
+    if ((rc = check_view(c, L, "L"))) return rc;
+    if (c->norm_pending) return fail(c, DRE_ERR_STATE, "norm_begin: the previous asynchronous norm was not collected");
+    const int k = L.ncols;
+    if (!c->norm_st) {
+        CU(cudaStreamCreateWithFlags(&c->norm_st, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->norm_in, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->norm_done, cudaEventDisableTiming));
+    }
+    if ((size_t)k + 4 > c->h_norm_cap) {
+        if (c->h_norm) cudaFreeHost(c->h_norm);
+        c->h_norm = nullptr;
+        c->h_norm_cap = 0;
+        CU(cudaMallocHost((void**)&c->h_norm, ((size_t)k + 4 + 256) * sizeof(double)));
+        c->h_norm_cap = (size_t)k + 4 + 256;
+    }
+    const GramPlan plan = gram_plan(c->sym.n, k, k, c->sm_count);
+    // (growing a workspace is safe: no asynchronous norm is in flight here)
+    CU(c->norm_partial.ensure(plan.partial_elems));
+    CU(c->norm_g.ensure((size_t)k * k));
+    CU(c->norm_small.ensure((size_t)k + 8));
+    for (int i = 0; i < k; ++i) c->h_norm[i] = d[i];
+    CU(cudaEventRecord(c->norm_in, c->st));                 // behind everything queued on the main stream so far
+    CU(cudaStreamWaitEvent(c->norm_st, c->norm_in, 0));
+    launch_gram(vptr(c, L), vld(c, L), k, vptr(c, L), vld(c, L), k, c->sym.n, nullptr, c->norm_partial.p, plan,
+                c->norm_g.p, k, nullptr, 0, c->norm_st, &c->stats.kernel_launches);
+    CU(cudaMemcpyAsync(c->norm_small.p + 8, c->h_norm, k * sizeof(double), cudaMemcpyHostToDevice, c->norm_st));
+    launch_norm_diag(c->norm_g.p, k, k, c->norm_small.p + 8, c->norm_small.p, c->norm_st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_norm + k, c->norm_small.p, sizeof(double), cudaMemcpyDeviceToHost, c->norm_st));
+    CU(cudaMemcpyAsync(c->h_norm + k + 1, c->d_errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, c->norm_st));
+    CU(cudaEventRecord(c->norm_done, c->norm_st));
+    c->stats.grams++;
+    c->stats.flops_gram += 2.0 * (double)c->sym.n * k * k;
+    c->stats.bytes_gram += 8.0 * (double)c->sym.n * k;
+    c->norm_pending = true;
+    c->norm_alpha = alpha;
+    c->norm_k = k;
+    return DRE_OK;
+}
+
+int32_t dre_ldlt_norm_end(dre_context* c, double* out) {
+    if (!c || !out) return fail(c, DRE_ERR_ARG, "null argument");
+    if (!c->norm_pending) return fail(c, DRE_ERR_STATE, "norm_end without norm_begin");
+    CU(cudaEventSynchronize(c->norm_done));
+    CU(cudaStreamWaitEvent(c->st, c->norm_done, 0));        // later writers of L on the main stream are ordered behind it
+    c->norm_pending = false;
+    const int k = c->norm_k;
+    *out = std::fabs(c->norm_alpha) * std::sqrt(std::max(c->h_norm[k], 0.0));
+    const int32_t flag = *reinterpret_cast<const int32_t*>(c->h_norm + k + 1);
+    return flag != 0 ? check_errflag(c) : DRE_OK;
 }
 
 static int eig_sym_dev(dre_context* c, double* S, int k, double* d_evals) {

@@ -144,6 +144,13 @@ DRE_API int32_t dre_adi_solve(dre_context* ctx, double mu_re, double mu_im, dre_
 /* ---- low-rank algebra (src/LDLt.jl) ---- */
 /* |alpha| * || L D L' ||_F  (norm(::LDLt), src/LDLt.jl:77-89).  D: k x k host column-major. */
 DRE_API int32_t dre_ldlt_norm(dre_context* ctx, dre_view L, const double* D, int64_t ldd, double alpha, double* out);
+/* The same norm in two halves, for a DIAGONAL core d[0..k): _begin queues the Gram product and the reduction on a
+ * side stream of the library behind everything issued so far and returns at once; _end waits for it.  Between the
+ * two the caller may queue work that only READS L (the host side uses the gap to start the shifted solve of the
+ * next ADI iteration, src/lyapunov/adi.jl:97-128: the residual norm is only needed for the stopping test).  L must
+ * not be written or freed before _end returns. */
+DRE_API int32_t dre_ldlt_norm_begin(dre_context* ctx, dre_view L, const double* d, double alpha);
+DRE_API int32_t dre_ldlt_norm_end(dre_context* ctx, double* out);
 /* compress!(::LDLt) (src/LDLt.jl:204-225) of sum_i alphas[i] * Ls[i] * Ds[i] * Ls[i]':
  * orthonormal basis of hcat(Ls) (rank-revealing block Gram-Schmidt = orthf, :237-245), eigen-
  * decomposition of the projected core, truncation |lambda| >= tol_factor * max|lambda| * eps

@@ -132,3 +132,38 @@ def test_gmres_and_fgmres_tiny_random(seed):
     assert O.delta(X_gmres, X_ref) < 2e-8
     assert O.delta(X_fgmres, X_ref) < 1e-10
     api.reset_backend()
+
+
+@pytest.mark.parametrize("n,nsteps,ros", [(371, 3, 1), (1357, 2, 1), (371, 2, 2)])
+def test_async_norm_lockstep_parity(monkeypatch, n, nsteps, ros):
+    """DRE_ASYNC_NORM (side-stream residual norm + speculative solve of the next shift): the lock-step parity gate,
+    and the speculation must really be adopted."""
+    from tests import test_gpu_parity as P
+    from oracle import dre_oracle as O
+
+    api.reset_backend()
+    monkeypatch.setattr(api, "ASYNC_NORM", True)
+    adopted = []
+    orig = api.solve_
+
+    def counting_solve(cache):
+        out = orig(cache)
+        adopted.append((getattr(cache, "adopted_speculations", 0), len(cache.shifts)))
+        return out
+
+    monkeypatch.setattr(api, "solve_", counting_solve)
+    dt = -100.0 if ros == 1 else -50.0
+    so, ro = P._oracle_run(n, nsteps, O.Ros1() if ros == 1 else O.Ros2(), dt=dt)
+    adi = api.ADI(shifts=P.ForcedShifts([r["shifts"] for r in ro.runs]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sg, rg = P._gpu_run(n, nsteps, api.Ros1(adi) if ros == 1 else api.Ros2(adi), dt=dt)
+    for Ko, Kg in zip(so.K, sg.K):
+        assert np.linalg.norm(Kg - Ko) <= 1e-8 * np.linalg.norm(Ko)
+    assert [r["iters"] for r in ro.runs] == [r["iters"] for r in rg.runs]
+    for a_, b_ in zip(ro.runs, rg.runs):
+        ra = np.array([x for _, x in a_["res"]])
+        rb = np.array([x for _, x in b_["res"]])
+        assert np.max(np.abs(ra - rb) / ra) <= 1e-10
+    assert adopted[0][0] >= 0.4 * adopted[0][1], adopted
+    api.reset_backend()

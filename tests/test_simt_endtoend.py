@@ -199,3 +199,26 @@ def test_emulated_gmres_and_fgmres(emulated, seed):
     X2 = -1.5 * api.lowrank(L2, D2).to_device_()
     ref = np.sum(X1.to_dense() * X2.to_dense())
     assert abs(api.dot(X1, X2) - ref) < 1e-12 * np.linalg.norm(X1.to_dense()) * np.linalg.norm(X2.to_dense())
+
+
+@pytest.mark.parametrize("ros", [1, pytest.param(2, marks=pytest.mark.skipif(
+    os.environ.get("DRE_TEST_SLOW") != "1", reason="2 minutes: set DRE_TEST_SLOW=1"))])
+def test_emulated_async_norm_with_speculative_solve(emulated, monkeypatch, ros):
+    """DRE_ASYNC_NORM: the residual norm is queued on a side stream (dre_ldlt_norm_begin / _end) and the solve of the
+    next buffered shift is started before it is collected; the next step adopts the block.  Same lock-step parity as
+    the default path, and the speculation really is adopted (all but the first step of every ADI solve)."""
+    emulated()
+    monkeypatch.setattr(api, "ASYNC_NORM", True)
+    adopted = []
+    orig = api.solve_
+
+    def counting_solve(cache):
+        out = orig(cache)
+        adopted.append((getattr(cache, "adopted_speculations", 0), len(cache.shifts)))
+        return out
+
+    monkeypatch.setattr(api, "solve_", counting_solve)
+    _lockstep(371, 1, ros)
+    # (the second ADI solve of a Ros2 step carries a dense residual core: its norm finishes on the host and stays on
+    # the synchronous path)
+    assert adopted and adopted[0][0] >= 0.4 * adopted[0][1], adopted
