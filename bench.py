@@ -353,7 +353,7 @@ def _run_ours(args):
                    "symbolic": info,
                    # opt-in code paths selected through the environment; empty = defaults
                    "opt_in": {k: os.environ[k] for k in ("DRE_SWEEP2", "DRE_DIAG_NARROW_MIN", "DRE_RR_EAGER",
-                                                         "DRE_SPMM2", "DRE_ASYNC_NORM", "DRE_LEAF_SIZE", "DRE_MAX_SNODE", "DRE_NT8",
+                                                         "DRE_SPMM2", "DRE_ASYNC_NORM", "DRE_ASYNC_COMPRESS", "DRE_LEAF_SIZE", "DRE_MAX_SNODE", "DRE_NT8",
                                                          "DRE_SYMBOLIC_THREADS") if k in os.environ}},
         "clocks": clocks,
         "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),

@@ -23,6 +23,7 @@ from __future__ import annotations
 import ctypes as C
 import itertools
 import math
+import os as _os
 import warnings
 
 import numpy as np
@@ -43,6 +44,7 @@ _backend = None
 
 class Backend:
     def __init__(self, device=0):
+        self.device = device
         self.ctx = capi.Context(device)
         self.lib = self.ctx.lib
         self.h = self.ctx.h
@@ -75,6 +77,27 @@ class Backend:
         return DeviceMatrix(sp_, 0, cols)
 
 
+class _LaneBackend(Backend):
+    """Second context on the same device for the dense low-rank algebra only (dre_set_dense_only): the compression
+    lane of DRE_ASYNC_COMPRESS.  Its panels either belong to its own arena or wrap memory of the main context."""
+
+    def __init__(self, main: Backend):
+        super().__init__(main.device)
+        self.n = main.n
+        self.generation = 1
+        self.check(self.lib.dre_set_dense_only(self.h, main.n))
+
+
+def _lane(main: Backend) -> _LaneBackend:
+    lane = getattr(main, "_lane_be", None)
+    if lane is None or lane.n != main.n or getattr(main, "_lane_gen", None) != main.generation:
+        if lane is not None:
+            lane.ctx.close()
+        lane = main._lane_be = _LaneBackend(main)
+        main._lane_gen = main.generation
+    return lane
+
+
 def backend(device=None) -> Backend:
     global _backend
     if _backend is None:
@@ -85,6 +108,9 @@ def backend(device=None) -> Backend:
 def reset_backend():
     global _backend
     if _backend is not None:
+        lane = getattr(_backend, "_lane_be", None)
+        if lane is not None:
+            lane.ctx.close()
         _backend.ctx.close()
     _backend = None
 
@@ -104,6 +130,33 @@ class _Panel:
                 self.be.lib.dre_mat_free(self.be.h, self.id)
         except Exception:
             pass
+
+
+class _WrappedPanel:
+    """Panel of context `be` that aliases the memory of a DeviceMatrix owned by another context (dre_mat_wrap).
+    Keeps the owner alive; synchronises `be` before letting go, so that the owner's arena cannot hand the memory out
+    again while work queued through the alias is still running."""
+
+    def __init__(self, be: Backend, src: "DeviceMatrix"):
+        self.be, self.cols, self.gen, self.src = be, src.ncols, be.generation, src
+        owner = src.panel.be
+        ptr, ld = C.c_void_p(), C.c_int64()
+        owner.check(owner.lib.dre_mat_devptr(owner.h, src.view, C.byref(ptr), C.byref(ld)))
+        pid = C.c_int32(-1)
+        be.check(be.lib.dre_mat_wrap(be.h, ptr, ld.value, src.ncols, C.byref(pid)))
+        self.id = pid.value
+
+    def __del__(self):
+        try:
+            if self.be.ctx.h and self.gen == self.be.generation:
+                self.be.lib.dre_sync(self.be.h)
+                self.be.lib.dre_mat_free(self.be.h, self.id)
+        except Exception:
+            pass
+
+
+def _alias(be: Backend, src: "DeviceMatrix") -> "DeviceMatrix":
+    return DeviceMatrix(_WrappedPanel(be, src), 0, src.ncols)
 
 
 class DeviceMatrix:
@@ -152,9 +205,9 @@ class DeviceMatrix:
         return out
 
     def copy(self) -> "DeviceMatrix":
-        d = DeviceMatrix.empty(self.ncols)
+        be = self.panel.be
+        d = DeviceMatrix(_Panel(be, max(self.ncols, 0)), 0, self.ncols)
         if self.ncols:
-            be = self.panel.be
             be.check(be.lib.dre_mat_copy(be.h, d.view, self.view))
         return d
 
@@ -236,6 +289,7 @@ class LDLt:
         self.alphas, self.Ls, self.Ds = list(alphas), list(Ls), list(Ds)
 
     def destructure(self):  # :54-60
+        _join_pending(self)
         if len(self.Ls) > 1:
             compress_(self)
         return self.alphas[0], self.Ls[0], self.Ds[0]
@@ -252,6 +306,7 @@ class LDLt:
         return (self.n, self.n)
 
     def rank(self):  # :112
+        _join_pending(self)
         return sum(_ncols(L) for L in self.Ls)
 
     def to_device_(self):
@@ -262,12 +317,13 @@ class LDLt:
         return self
 
     def iszero(self):  # :114
-        return all(a == 0 for a in self.alphas) or self.rank() == 0
+        return all(a == 0 for a in self.alphas) or sum(_ncols(L) for L in self.Ls) == 0
 
     def zero(self):  # :116-121
         return LDLt([1.0], [DeviceMatrix.empty(0)], [np.zeros((0, 0))])
 
     def to_dense(self):  # :42-51 (testing only)
+        _join_pending(self)
         M = np.zeros((self.n, self.n))
         for a, L, D in zip(self.alphas, self.Ls, self.Ds):
             Lh = L.to_host()
@@ -279,15 +335,22 @@ class LDLt:
             return other
         if other.iszero():
             return self
-        return LDLt(self.alphas + other.alphas, self.Ls + other.Ls, self.Ds + other.Ds)
+        _join_pending(other)
+        out = LDLt(self.alphas + other.alphas, self.Ls + other.Ls, self.Ds + other.Ds)
+        p = getattr(self, "_pending", None)
+        if p is not None:       # the terms in flight keep their positions at the front of the sum
+            out._pending, self._pending = p, None
+        return out
 
     def __neg__(self):  # :150-153
+        _join_pending(self)
         return LDLt([-a for a in self.alphas], self.Ls, self.Ds)
 
     def __sub__(self, other):
         return self + (-other)
 
     def __rmul__(self, alpha):  # :156-159
+        _join_pending(self)
         return LDLt([alpha * a for a in self.alphas], self.Ls, self.Ds)
 
     def __truediv__(self, alpha):
@@ -318,6 +381,7 @@ def _dcat(Xs, alphas=None):
 
 def concatenate_(X: LDLt) -> LDLt:
     """src/LDLt.jl:174-191."""
+    _join_pending(X)
     if len(X.alphas) == 1:
         return X
     L = hcat(X.Ls)
@@ -328,13 +392,9 @@ def concatenate_(X: LDLt) -> LDLt:
     return X
 
 
-def compress_(X: LDLt) -> LDLt:
-    """src/LDLt.jl:204-225 -- one C-ABI call (dre_ldlt_compress); no concatenation copy is needed."""
-    be = backend()
-    terms = [(a, L, np.asfortranarray(D, dtype=np.float64)) for a, L, D in zip(X.alphas, X.Ls, X.Ds) if L.ncols]
+def _compress_call(be: Backend, terms):
+    """dre_ldlt_compress on context `be`; terms = [(alpha, DeviceMatrix of be, D F-ordered)].  Returns (L, lam)."""
     ktot = sum(L.ncols for _, L, _ in terms)
-    if ktot == 0:
-        raise ValueError("compress!: rank-0 input (reference: maximum of empty collection, src/LDLt.jl:216)")
     nt = len(terms)
     views = (View * nt)(*[L.view for _, L, _ in terms])
     dptrs = (C.POINTER(C.c_double) * nt)(*[capi._dptr(D) for _, _, D in terms])
@@ -349,13 +409,82 @@ def compress_(X: LDLt) -> LDLt:
     be.check(be.lib.dre_ldlt_compress(be.h, nt, views, dptrs, ldds, alphas, 100.0, out.view, capi._dptr(lam),
                                       C.byref(newrank)))
     k2 = newrank.value
-    _dist.assert_same_int(k2, "the rank after compress!")
     Lnew = out.cols(0, k2).copy()  # exact-size panel; the scratch panel is reused by the next compress!
     Lnew.orthonormal = True         # Q * (orthonormal eigenvectors): lets the next compress! skip these columns
+    return Lnew, lam[:k2]
+
+
+def compress_(X: LDLt) -> LDLt:
+    """src/LDLt.jl:204-225 -- one C-ABI call (dre_ldlt_compress); no concatenation copy is needed."""
+    _join_pending(X)
+    terms = [(a, L, np.asfortranarray(D, dtype=np.float64)) for a, L, D in zip(X.alphas, X.Ls, X.Ds) if L.ncols]
+    if sum(L.ncols for _, L, _ in terms) == 0:
+        raise ValueError("compress!: rank-0 input (reference: maximum of empty collection, src/LDLt.jl:216)")
+    Lnew, lam = _compress_call(backend(), terms)
+    _dist.assert_same_int(Lnew.ncols, "the rank after compress!")
     X.alphas[:] = [1.0]
     X.Ls[:] = [Lnew]
-    X.Ds[:] = [np.asfortranarray(np.diag(lam[:k2]))]
+    X.Ds[:] = [np.asfortranarray(np.diag(lam))]
     return X
+
+
+# Opt-in (DRE_ASYNC_COMPRESS=1, DESIGN.md section 4b): compress!(X) of adi.jl:143-147 on a second context ("lane":
+# own stream, workspaces, arena) and a host thread, while the ADI iteration carries on -- the following steps only
+# append terms to X (adi.jl:170-176), nothing reads it before the next compression or the end of the solve.
+ASYNC_COMPRESS = _os.environ.get("DRE_ASYNC_COMPRESS", "0") not in ("", "0")
+
+
+class _PendingCompress:
+    """The first `nterms` terms of an LDLt are being compressed on the lane; join() replaces them by the result."""
+
+    def __init__(self, X: LDLt):
+        import threading
+
+        main = backend()
+        self.lane = _lane(main)
+        main.ctx.sync()                      # every kernel that produced the terms has finished
+        keep = [(a, L, np.asfortranarray(D, dtype=np.float64)) for a, L, D in zip(X.alphas, X.Ls, X.Ds)]
+        self.nterms = len(keep)
+        self.src = keep                      # the main context's panels stay alive until join()
+        terms = []
+        for a, L, D in keep:
+            if L.ncols == 0:
+                continue
+            W = _alias(self.lane, L)
+            if getattr(L, "orthonormal", False):
+                W.orthonormal = True
+            terms.append((a, W, D))
+        self.terms, self.result, self.error = terms, None, None
+        self.thread = threading.Thread(target=self._run, name="dre-compress-lane", daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            res = _compress_call(self.lane, self.terms)
+            self.lane.ctx.sync()
+            self.result = res
+        except BaseException as e:           # re-raised by join() on the caller's thread
+            self.error = e
+
+    def join(self, X: LDLt):
+        self.thread.join()
+        self.terms = None                    # lane-side aliases of the inputs (the lane is idle now)
+        if self.error is not None:
+            raise self.error
+        Llane, lam = self.result
+        Lnew = _alias(backend(), Llane)      # the compressed factor stays in the lane's arena
+        Lnew.orthonormal = True
+        X.alphas[:self.nterms] = [1.0]
+        X.Ls[:self.nterms] = [Lnew]
+        X.Ds[:self.nterms] = [np.asfortranarray(np.diag(lam))]
+        self.src = None
+
+
+def _join_pending(X: LDLt):
+    p = getattr(X, "_pending", None)
+    if p is not None:
+        X._pending = None
+        p.join(X)
 
 
 def norm(X: LDLt) -> float:
@@ -915,6 +1044,14 @@ def compress_cache_(cache: ADICache):
     cache.last_compression = 0
 
 
+def _start_async_compress(cache: ADICache):
+    """compress_cache_ on the compression lane (DRE_ASYNC_COMPRESS): at most one compression is in flight."""
+    X = cache.X
+    _join_pending(X)
+    X._pending = _PendingCompress(X)
+    cache.last_compression = 0
+
+
 def _fused_inner(alg: ADI) -> bool:
     return isinstance(alg.inner_alg, (Backslash, ShermanMorrisonWoodbury))
 
@@ -951,8 +1088,6 @@ def _prefetch_next_factorization(cache: ADICache):
 # from the already buffered shift while it runs (R is only read), and then collects the norm.  If ADI stops, the
 # speculative block is dropped; otherwise the next step adopts it and only runs its residual update.  Results are
 # identical: the same kernels run on the same data.
-import os as _os
-
 ASYNC_NORM = _os.environ.get("DRE_ASYNC_NORM", "0") not in ("", "0")
 
 
@@ -1097,9 +1232,13 @@ def step_(cache: ADICache):
         perform_single_step_(cache, float(np.real(mu)))
     else:
         perform_double_step_(cache, complex(mu))
-    if alg.compression and cache.last_compression >= alg.compression_interval:
+    want_compress = alg.compression and cache.last_compression >= alg.compression_interval
+    on_lane = want_compress and ASYNC_COMPRESS and _fused_inner(alg) and not _dist.active()
+    if want_compress and not on_lane:
         compress_cache_(cache)
     res_norm = cache.residual_norm = _dist.agree_scalar(_residual_norm_overlapped(cache))
+    if on_lane:
+        _start_async_compress(cache)   # after the norm: its synchronisation guarantees the terms are complete
     i = len(cache.shifts)
     _observe(observer, "observe_gale_step", i, cache.X, cache.residual, res_norm)
     if res_norm <= abstol:
@@ -1117,6 +1256,7 @@ def solve_(cache: ADICache) -> LDLt:
         step_(cache)
     if cache.alg.compression and cache.last_compression > 0:
         compress_cache_(cache)
+    _join_pending(cache.X)
     iters = len(cache.shifts)
     _observe(cache.observer, "observe_gale_done", iters, cache.X, cache.residual, cache.residual_norm)
     return cache.X

@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "dre_last_error", "dre_version", "dre_symbolic_create", "dre_symbolic_destroy", "dre_symbolic_get_info",
     "dre_symbolic_export", "dre_create", "dre_destroy", "dre_sync", "dre_set_pencil", "dre_get_symbolic_info",
     "dre_mat_create", "dre_mat_free", "dre_mat_upload", "dre_mat_download", "dre_mat_copy", "dre_mat_axpby",
-    "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_prefactor", "dre_shift_solve", "dre_adi_step", "dre_adi_solve", "dre_mat_devptr", "dre_get_stream",
+    "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_prefactor", "dre_shift_solve", "dre_adi_step", "dre_adi_solve", "dre_mat_devptr", "dre_get_stream", "dre_set_dense_only", "dre_mat_wrap",
     "dre_ldlt_norm", "dre_ldlt_norm_begin", "dre_ldlt_norm_end", "dre_ldlt_compress", "dre_hint_orthonormal", "dre_rrqr", "dre_debug_export", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
     "dre_stats_get",
 ]
@@ -102,6 +102,8 @@ def load():
     lib.dre_adi_solve.argtypes = [p, dbl, dbl, View, View, View]
     lib.dre_mat_devptr.argtypes = [p, View, C.POINTER(p), pi64]
     lib.dre_get_stream.argtypes = [p, C.POINTER(p)]
+    lib.dre_set_dense_only.argtypes = [p, i64]
+    lib.dre_mat_wrap.argtypes = [p, p, i64, i32, C.POINTER(i32)]
     lib.dre_ldlt_norm.argtypes = [p, View, pdbl, i64, dbl, pdbl]
     lib.dre_ldlt_norm_begin.argtypes = [p, View, pdbl, dbl]
     lib.dre_ldlt_norm_end.argtypes = [p, pdbl]

@@ -146,6 +146,7 @@ struct Panel {
     int64_t ld = 0;
     bool alive = false;
     size_t cap = 0;   // bytes of the underlying block (>= n * ld * 8)
+    bool owned = true;   // false: memory of another context (dre_mat_wrap), never released here
 };
 
 }  // namespace
@@ -163,6 +164,7 @@ struct dre_context {
 
     // pencil
     bool has_pencil = false;
+    bool dense_only = false;   // dre_set_dense_only: a compression lane without a sparse solver
     Symbolic sym;
     DevSymbolic dS{};
     std::vector<void*> owned;  // device arrays of the symbolic structure
@@ -560,7 +562,7 @@ int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_
 }
 
 int shifted_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2, bool adi_pair) {
-    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    if (!c->has_pencil || c->dense_only) return fail(c, DRE_ERR_STATE, "no pencil set");
     int rc;
     if ((rc = check_view(c, R, "R"))) return rc;
     if ((rc = check_view(c, V1, "V1"))) return rc;
@@ -1038,6 +1040,7 @@ int32_t dre_destroy(dre_context* c) {
 }
 
 int32_t dre_sync(dre_context* c) {
+    if (c) cudaSetDevice(c->device);   // may be the first CUDA call of a host thread (compression lane)
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     CU(cudaStreamSynchronize(c->st));
     for (auto& fs : c->slot) CU(cudaStreamSynchronize(fs.st));
@@ -1050,6 +1053,7 @@ int32_t dre_set_pencil(dre_context* c, int64_t n, const int64_t* Ecp, const int6
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->st));
     release_pencil(c);
+    c->dense_only = false;
     for (Panel& p : c->panels) { p.alive = false; p.d = nullptr; }
     for_each_workspace(c, [](auto& w) { w.forget(); });
     c->arena.destroy();
@@ -1134,6 +1138,7 @@ int32_t dre_get_symbolic_info(const dre_context* c, dre_symbolic_info* info) {
 
 // ---- panels ----
 int32_t dre_mat_create(dre_context* c, int32_t cols, int32_t* id) {
+    if (c) cudaSetDevice(c->device);   // may be the first CUDA call of a host thread (compression lane)
     if (!c || !id) return fail(c, DRE_ERR_ARG, "null argument");
     if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
     if (cols < 0) return fail(c, DRE_ERR_ARG, "negative column count");
@@ -1164,7 +1169,7 @@ int32_t dre_mat_free(dre_context* c, int32_t id) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     if (id < 0 || id >= (int)c->panels.size() || !c->panels[id].alive) return fail(c, DRE_ERR_ARG, "invalid panel id");
     if (c->op_U.id == id || c->op_Vt.id == id) c->op_U = c->op_Vt = dre_view{-1, 0, 0};
-    c->arena.release(c->panels[id].d, c->panels[id].cap);
+    if (c->panels[id].owned) c->arena.release(c->panels[id].d, c->panels[id].cap);
     c->panels[id].alive = false;
     c->panels[id].d = nullptr;
     return DRE_OK;
@@ -1172,6 +1177,7 @@ int32_t dre_mat_free(dre_context* c, int32_t id) {
 
 int32_t dre_mat_upload(dre_context* c, dre_view dst, const double* host, int64_t ld) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (c->dense_only) return fail(c, DRE_ERR_STATE, "dense-only context: no row permutation to upload through");
     int rc;
     if ((rc = check_view(c, dst, "dst", true))) return rc;
     if (dst.ncols == 0) return DRE_OK;
@@ -1189,6 +1195,7 @@ int32_t dre_mat_upload(dre_context* c, dre_view dst, const double* host, int64_t
 
 int32_t dre_mat_download(dre_context* c, dre_view src, double* host, int64_t ld) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (c->dense_only) return fail(c, DRE_ERR_STATE, "dense-only context: no row permutation to download through");
     int rc;
     if ((rc = check_view(c, src, "src", true))) return rc;
     if (src.ncols == 0) return DRE_OK;
@@ -1205,6 +1212,7 @@ int32_t dre_mat_download(dre_context* c, dre_view src, double* host, int64_t ld)
 }
 
 int32_t dre_mat_copy(dre_context* c, dre_view dst, dre_view src) {
+    if (c) cudaSetDevice(c->device);   // may be the first CUDA call of a host thread (compression lane)
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     int rc;
     if ((rc = check_view(c, dst, "dst", true)) || (rc = check_view(c, src, "src", true))) return rc;
@@ -1235,7 +1243,7 @@ int32_t dre_mat_axpby(dre_context* c, double alpha, dre_view X, double beta, dre
 // ---- products ----
 int32_t dre_spmm(dre_context* c, int32_t op, double alpha, dre_view X, double beta, dre_view Y) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
-    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    if (!c->has_pencil || c->dense_only) return fail(c, DRE_ERR_STATE, "no pencil set");
     int rc;
     if ((rc = check_view(c, X, "X", true)) || (rc = check_view(c, Y, "Y", true))) return rc;
     if (X.ncols != Y.ncols) return fail(c, DRE_ERR_ARG, "spmm: column counts differ");
@@ -1308,6 +1316,7 @@ int32_t dre_set_operator(dre_context* c, double a, double e, double alpha, dre_v
 }
 
 int32_t dre_prefactor(dre_context* c, double mu_re, double mu_im) {
+    if (c && c->dense_only) return fail(c, DRE_ERR_STATE, "no pencil set");
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
     if (c->timing) return DRE_OK;   // per-class event timing serialises everything: no overlap to gain
@@ -1334,6 +1343,42 @@ int32_t dre_adi_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dr
 int32_t dre_get_stream(dre_context* c, void** stream) {
     if (!c || !stream) return fail(c, DRE_ERR_ARG, "null argument");
     *stream = (void*)c->st;
+    return DRE_OK;
+}
+
+int32_t dre_set_dense_only(dre_context* c, int64_t n) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (n <= 0) return fail(c, DRE_ERR_ARG, "dense-only context: bad row count");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->st));
+    release_pencil(c);
+    for (Panel& p : c->panels) { p.alive = false; p.d = nullptr; }
+    for_each_workspace(c, [](auto& w) { w.forget(); });
+    c->arena.destroy();
+    c->op_U = c->op_Vt = dre_view{-1, 0, 0};
+    c->sym = Symbolic();
+    c->sym.n = n;
+    c->levels.clear();
+    c->has_pencil = true;   // panels and the dense toolbox work; the sparse entry points find an empty schedule
+    c->dense_only = true;
+    return DRE_OK;
+}
+
+int32_t dre_mat_wrap(dre_context* c, void* device_ptr, int64_t ld, int32_t cols, int32_t* id) {
+    if (!c || !id || !device_ptr) return fail(c, DRE_ERR_ARG, "null argument");
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    if (cols < 0 || ld < std::max(cols, 1)) return fail(c, DRE_ERR_ARG, "wrap: bad shape");
+    Panel p;
+    p.d = (double*)device_ptr;
+    p.cols = cols;
+    p.ld = ld;
+    p.cap = 0;
+    p.owned = false;
+    p.alive = true;
+    for (size_t i = 0; i < c->panels.size(); ++i)
+        if (!c->panels[i].alive) { c->panels[i] = p; *id = (int32_t)i; return DRE_OK; }
+    c->panels.push_back(p);
+    *id = (int32_t)c->panels.size() - 1;
     return DRE_OK;
 }
 
@@ -1503,6 +1548,7 @@ static int rr_setup(dre_context* c, RRState& s, int ktot, double drop_rel, doubl
 int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, const double* const* Ds,
                           const int64_t* ldds, const double* alphas, double tol_factor, dre_view out, double* lam,
                           int32_t* newrank) {
+    if (c) cudaSetDevice(c->device);   // may be the first CUDA call of a host thread (compression lane)
     if (!c || !Ls || !Ds || !ldds || !alphas || !lam || !newrank) return fail(c, DRE_ERR_ARG, "null argument");
     if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
     int rc;
@@ -1633,6 +1679,7 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
 }
 
 int32_t dre_hint_orthonormal(dre_context* c, dre_view v) {
+    if (c) cudaSetDevice(c->device);   // may be the first CUDA call of a host thread (compression lane)
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     int rc;
     if ((rc = check_view(c, v, "view", true))) return rc;

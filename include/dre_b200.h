@@ -98,6 +98,16 @@ DRE_API int32_t dre_mat_copy(dre_context* ctx, dre_view dst, dre_view src);
  * with rows in the solver's internal ordering (identical on every rank for the same pencil).  The caller must
  * dre_sync() before touching the memory from another stream and must not keep the pointer past dre_mat_free. */
 DRE_API int32_t dre_mat_devptr(dre_context* ctx, dre_view v, void** ptr, int64_t* ld);
+/* A second context on the same device used as a "compression lane": dre_set_dense_only gives it the row count of
+ * the panels (no pencil, no sparse solver: only the dense low-rank algebra -- dre_ldlt_compress, dre_ldlt_norm,
+ * dre_gemm_*, dre_mat_copy -- may be called on it), dre_mat_wrap registers memory owned by ANOTHER context (address
+ * and leading dimension from dre_mat_devptr there) as a panel of this one without copying.  A wrapped panel is
+ * never released by this context (dre_mat_free only forgets it); the caller keeps the owner alive and orders the
+ * two contexts' streams (dre_sync on the producer before the consumer starts).  With both, the host side can run
+ * compress!(X) of src/lyapunov/adi.jl:143-147 on its own stream and thread while the ADI iteration that produced
+ * the terms carries on -- the following steps only append to X. */
+DRE_API int32_t dre_set_dense_only(dre_context* ctx, int64_t n);
+DRE_API int32_t dre_mat_wrap(dre_context* ctx, void* device_ptr, int64_t ld, int32_t cols, int32_t* id);
 /* The context's main CUDA stream (a cudaStream_t).  Collectives and copies queued on it by the host side are
  * ordered with the library's own work, so the multi-GPU exchange needs no host synchronisation. */
 DRE_API int32_t dre_get_stream(dre_context* ctx, void** stream);

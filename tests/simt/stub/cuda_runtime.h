@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 #define __global__
@@ -315,8 +316,14 @@ inline void run_cta() {
     m.ctas++;
 }
 
+inline std::mutex& launch_mutex() {
+    static std::mutex mx;
+    return mx;
+}
+
 template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem, F&& body) {
+    std::lock_guard<std::mutex> lock(launch_mutex());   // one kernel at a time, whichever host thread launches it
     Machine& m = M();
     if (m.cur) die("nested kernel launch");
     if (smem > Machine::DYN_SMEM) die("dynamic shared memory request exceeds 227 KB");

@@ -167,3 +167,28 @@ def test_async_norm_lockstep_parity(monkeypatch, n, nsteps, ros):
         assert np.max(np.abs(ra - rb) / ra) <= 1e-10
     assert adopted[0][0] >= 0.4 * adopted[0][1], adopted
     api.reset_backend()
+
+
+@pytest.mark.parametrize("n,nsteps", [(371, 3), (1357, 2)])
+def test_async_compress_lane_lockstep_parity(monkeypatch, n, nsteps):
+    """DRE_ASYNC_COMPRESS (compression lane: second context + host thread) together with DRE_ASYNC_NORM: the
+    lock-step parity gate must hold unchanged."""
+    from tests import test_gpu_parity as P
+    from oracle import dre_oracle as O
+
+    api.reset_backend()
+    monkeypatch.setattr(api, "ASYNC_COMPRESS", True)
+    monkeypatch.setattr(api, "ASYNC_NORM", True)
+    so, ro = P._oracle_run(n, nsteps, O.Ros1(), dt=-100.0)
+    adi = api.ADI(shifts=P.ForcedShifts([r["shifts"] for r in ro.runs]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sg, rg = P._gpu_run(n, nsteps, api.Ros1(adi), dt=-100.0)
+    for Ko, Kg in zip(so.K, sg.K):
+        assert np.linalg.norm(Kg - Ko) <= 1e-8 * np.linalg.norm(Ko)
+    assert [r["iters"] for r in ro.runs] == [r["iters"] for r in rg.runs]
+    for a_, b_ in zip(ro.runs, rg.runs):
+        ra = np.array([x for _, x in a_["res"]])
+        rb = np.array([x for _, x in b_["res"]])
+        assert np.max(np.abs(ra - rb) / ra) <= 1e-10
+    api.reset_backend()

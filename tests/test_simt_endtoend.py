@@ -222,3 +222,21 @@ def test_emulated_async_norm_with_speculative_solve(emulated, monkeypatch, ros):
     # (the second ADI solve of a Ros2 step carries a dense residual core: its norm finishes on the host and stays on
     # the synchronous path)
     assert adopted and adopted[0][0] >= 0.4 * adopted[0][1], adopted
+
+
+def test_emulated_async_compress_on_the_lane(emulated, monkeypatch):
+    """DRE_ASYNC_COMPRESS: compress!(X) every 10 ADI steps runs on a second context (dre_set_dense_only, panels of
+    the main context registered with dre_mat_wrap) and a host thread while the iteration carries on; the lock-step
+    parity of one Ros1 step must hold unchanged, and the lane must really have been used."""
+    emulated()
+    monkeypatch.setattr(api, "ASYNC_COMPRESS", True)
+    started = []
+    orig = api._PendingCompress.__init__
+
+    def counting_init(self, X):
+        started.append(len(X.alphas))
+        orig(self, X)
+
+    monkeypatch.setattr(api._PendingCompress, "__init__", counting_init)
+    _lockstep(371, 1, 1)
+    assert len(started) >= 3 and all(n_ >= 2 for n_ in started), started

@@ -18,8 +18,10 @@ run narrow DRE_DIAG_NARROW_MIN=296
 run spmm2 DRE_SPMM2=1
 run eager DRE_RR_EAGER=1 DRE_RR_STATS=1
 run async_norm DRE_ASYNC_NORM=1
+run async_compress DRE_ASYNC_COMPRESS=1
 run all DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1
 run all_async DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1 DRE_ASYNC_NORM=1
+run all_async2 DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1 DRE_ASYNC_NORM=1 DRE_ASYNC_COMPRESS=1
 run all_leaf64 DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1 DRE_LEAF_SIZE=64
 python - <<'PY'
 import glob, json, os
