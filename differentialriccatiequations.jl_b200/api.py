@@ -1269,7 +1269,8 @@ class GMRES:  # types.jl:44-52
     def __init__(self, *, maxiters=3, maxrestarts=0, reltol=None, abstol=None, ignore_initial_guess=False,
                  compression=True, preconditioner=None):
         self.maxiters, self.maxrestarts, self.reltol, self.abstol = maxiters, maxrestarts, reltol, abstol
-        self.ignore_initial_guess, self.compression, self.preconditioner = ignore_initial_guess, compression, preconditioner
+        self.ignore_initial_guess, self.compression = ignore_initial_guess, compression
+        self.preconditioner = preconditioner
 
 
 def lyapunov_operator(E, A, X: LDLt) -> LDLt:

@@ -250,7 +250,8 @@ namespace {
 
 template <class F>
 void for_each_workspace(dre_context* c, F f) {
-    f(c->tbuf); f(c->Wbuf); f(c->Ybuf); f(c->norm_partial); f(c->norm_g); f(c->norm_small); f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
+    f(c->tbuf); f(c->Wbuf); f(c->Ybuf); f(c->norm_partial); f(c->norm_g); f(c->norm_small);
+    f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
     f(c->wsel); f(c->wsel2); f(c->small); f(c->stage); f(c->qws); f(c->pws); f(c->qtmp); f(c->rt); f(c->rt2);
     f(c->tmp_panel); f(c->evals); f(c->cnorm); f(c->syevd_work); f(c->ibuf);
 }

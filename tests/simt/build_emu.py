@@ -16,7 +16,8 @@ DEPS = [os.path.join(CSRC, f) for f in KERNEL_SOURCES + ["symbolic.cpp", "symbol
                                                            "schedule.h"]] + \
        [os.path.join(ROOT, "include", "dre_b200.h"), os.path.join(HERE, "emu_harness.cpp"),
         os.path.join(HERE, "stub", "cuda_runtime.h"), os.path.join(HERE, "stub", "cusolverDn.h")]
-FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-pthread", "-DDRE_SIMT_EMU", "-fvisibility=hidden", "-fno-strict-aliasing",
+FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-pthread", "-DDRE_SIMT_EMU", "-fvisibility=hidden",
+         "-fno-strict-aliasing",
          "-I", os.path.join(HERE, "stub"), "-I", CSRC]
 
 

@@ -101,7 +101,8 @@ def test_emulated_narrow_diag_kernel():
             emu.set_diag_narrow_min(1)
             assert S.factor(1.0, mu) == 0
             for w, r in zip(("L", "Linv", "dvec"), ref):
-                assert np.array_equal(S.get(w), r, equal_nan=True), w   # never-written entries above the diagonal blocks stay poisoned
+                # (never-written entries above the diagonal blocks of Linv stay NaN-poisoned)
+                assert np.array_equal(S.get(w), r, equal_nan=True), w
     finally:
         emu.set_diag_narrow_min(1 << 30)
         S.close()
