@@ -362,6 +362,7 @@ def _run_ours(args):
         "roofline": roofline, "roofline_named_kernels": named, "kernel_classes": classes,
         "fp64_peak_tflops_measured": fp64_peak, "nccl_allgather": gathered,
         "cpu_baseline": cpu, "wall_s_timed_region": wall, "e2e_vs_resident_K_relerr": kerr,
+        "compression_lane": dict(api.LANE_STATS) if api.ASYNC_COMPRESS else None,
     }
     return out
 

@@ -434,15 +434,25 @@ def compress_(X: LDLt) -> LDLt:
 ASYNC_COMPRESS = _os.environ.get("DRE_ASYNC_COMPRESS", "0") not in ("", "0")
 
 
+LANE_STATS = {"compressions": 0, "lane_busy_s": 0.0, "join_wait_s": 0.0, "start_sync_s": 0.0}   # DRE_ASYNC_COMPRESS
+
+
 class _PendingCompress:
-    """The first `nterms` terms of an LDLt are being compressed on the lane; join() replaces them by the result."""
+    """The first `nterms` terms of an LDLt are being compressed on the lane; join() replaces them by the result.
+    LANE_STATS accumulates how long the lane worked and how long the ADI thread had to wait for it (wall clock):
+    join_wait_s close to lane_busy_s means the two did not overlap."""
 
     def __init__(self, X: LDLt):
         import threading
+        import time
+
+        t0 = time.perf_counter()
 
         main = backend()
         self.lane = _lane(main)
         main.ctx.sync()                      # every kernel that produced the terms has finished
+        LANE_STATS["start_sync_s"] += time.perf_counter() - t0
+        LANE_STATS["compressions"] += 1
         keep = [(a, L, np.asfortranarray(D, dtype=np.float64)) for a, L, D in zip(X.alphas, X.Ls, X.Ds)]
         self.nterms = len(keep)
         self.src = keep                      # the main context's panels stay alive until join()
@@ -459,15 +469,23 @@ class _PendingCompress:
         self.thread.start()
 
     def _run(self):
+        import time
+
+        t0 = time.perf_counter()
         try:
             res = _compress_call(self.lane, self.terms)
             self.lane.ctx.sync()
             self.result = res
         except BaseException as e:           # re-raised by join() on the caller's thread
             self.error = e
+        LANE_STATS["lane_busy_s"] += time.perf_counter() - t0
 
     def join(self, X: LDLt):
+        import time
+
+        t0 = time.perf_counter()
         self.thread.join()
+        LANE_STATS["join_wait_s"] += time.perf_counter() - t0
         self.terms = None                    # lane-side aliases of the inputs (the lane is idle now)
         if self.error is not None:
             raise self.error
