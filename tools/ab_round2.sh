@@ -23,6 +23,8 @@ run all DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1
 run all_async DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1 DRE_ASYNC_NORM=1
 run all_async2 DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1 DRE_ASYNC_NORM=1 DRE_ASYNC_COMPRESS=1
 run all_leaf64 DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1 DRE_LEAF_SIZE=64
+# nnz(L) 8.41M (leaf 96, 12 levels) -> 5.58M (leaf 48, 13 levels): the leaf level is FP64-bound, levels are cheap with sweep v2
+run all_leaf48 DRE_SWEEP2=1 DRE_DIAG_NARROW_MIN=296 DRE_SPMM2=1 DRE_LEAF_SIZE=48
 python - <<'PY'
 import glob, json, os
 rows = []
