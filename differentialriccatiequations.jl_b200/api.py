@@ -1251,7 +1251,7 @@ def step_(cache: ADICache):
     else:
         perform_double_step_(cache, complex(mu))
     want_compress = alg.compression and cache.last_compression >= alg.compression_interval
-    on_lane = want_compress and ASYNC_COMPRESS and _fused_inner(alg) and not _dist.active()
+    on_lane = want_compress and ASYNC_COMPRESS and _fused_inner(alg)   # (every rank of a sharded run has its own lane)
     if want_compress and not on_lane:
         compress_cache_(cache)
     res_norm = cache.residual_norm = _dist.agree_scalar(_residual_norm_overlapped(cache))

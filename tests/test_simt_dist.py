@@ -88,7 +88,13 @@ def _spawn(world, n):
     return sorted(res, key=lambda t: t[0])
 
 
-def test_sharded_ros1_on_the_emulator_matches_single_process():
+import pytest
+
+
+@pytest.mark.parametrize("lane", [False, True])
+def test_sharded_ros1_on_the_emulator_matches_single_process(lane, monkeypatch):
+    """lane=True: every rank additionally runs compress!(X) on its own compression lane (DRE_ASYNC_COMPRESS)."""
+    monkeypatch.setenv("DRE_ASYNC_COMPRESS", "1" if lane else "0")
     n = 371
     single = _spawn(1, n)[0]
     sharded = _spawn(2, n)
