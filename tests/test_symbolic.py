@@ -132,3 +132,20 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert b"sm_100a" in lib.dre_version()
+
+
+def test_threaded_dissection_is_deterministic(monkeypatch):
+    """The nested dissection runs the two halves of its top levels as parallel tasks (DRE_SYMBOLIC_THREADS); the
+    ordering, the supernode partition and every index map must not depend on the number of threads."""
+    E, A, B, C, _ = pencils.rail_pencil(20209)
+    names = ("perm", "sn_first", "sn_rows", "relmap", "level_sn", "asm_dest", "upd_off", "rhs_off")
+    ref = None
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("DRE_SYMBOLIC_THREADS", threads)
+        sa = capi.SymbolicAnalysis(E, A)
+        cur = {k: sa.export(k) for k in names}
+        if ref is None:
+            ref = cur
+        else:
+            for k in names:
+                assert np.array_equal(ref[k], cur[k]), (threads, k)
