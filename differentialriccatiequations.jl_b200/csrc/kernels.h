@@ -48,7 +48,8 @@ void launch_panel_to_colmajor(double* dst, int64_t ldd, const double* src, int64
 
 // Pivoted Cholesky selection on a pb x pb Gram matrix (pb <= 64), single CTA.
 //   thr = max(drop2, rel2 * max diag);  selects pivots while the Schur diagonal >= thr.
-//   Wsel (pb x 64 row-major, ld 64): Q = P * Wsel orthonormalises the selected columns.
+//   Wsel (64 x 64 row-major, ld 64; all 64 rows are written, rows >= pb and columns >= nsel with zeros): Q = P * Wsel
+//   orthonormalises the selected columns.
 //   info[0] = nsel, dinfo[0] = initial max diagonal, dinfo[1] = largest remaining diagonal.
 void launch_pivchol(const double* G, int64_t ldg, int pb, double drop2, double rel2, double* Wsel, int32_t* info,
                     double* dinfo, cudaStream_t st, int64_t* launches);

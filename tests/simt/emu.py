@@ -133,6 +133,43 @@ def tall_gemm(alpha, X, W, beta, Y, w_trans=False):
     return Y
 
 
+def pivchol(G, drop2, rel2):
+    """k_pivchol on a pb x pb Gram matrix (pb <= 64): returns (nsel, Wsel (pb x 64), dfirst, remaining)."""
+    G = _rm(G)
+    pb = G.shape[0]
+    W = np.full((64, 64), np.nan)      # the kernel owns a full 64 x 64 block (context.cu: wsel.ensure(PB * PB))
+    info = np.zeros(4, dtype=np.int32)
+    dinfo = np.zeros(4)
+    lib().emu_pivchol(_d(G), pb, pb, float(drop2), float(rel2), _d(W), info.ctypes.data_as(_ip), _d(dinfo))
+    return int(info[0]), W[:pb], float(dinfo[0]), float(dinfo[1])
+
+
+def norm_diag(G, t):
+    G, t = _rm(G), _rm(t)
+    out = np.zeros(1)
+    lib().emu_norm_diag(_d(G), G.shape[1], G.shape[0], _d(t), _d(out))
+    return float(out[0])
+
+
+def colnorm2(P, nblk=7):
+    P = _rm(P)
+    out = np.full(P.shape[1], np.nan)
+    lib().emu_colnorm2(_d(P), P.shape[1], P.shape[0], P.shape[1], nblk, _d(out))
+    return out
+
+
+def panel_roundtrip(M, iperm):
+    """column-major host matrix -> row-major permuted panel -> back (the upload / download kernels)."""
+    M = np.asfortranarray(M, dtype=np.float64)
+    n, cols = M.shape
+    ld = (cols + 1) & ~1
+    panel = np.full((n, ld), np.nan)
+    back = np.full((n, cols), np.nan, order="F")
+    ip = np.ascontiguousarray(iperm, dtype=np.int32)
+    lib().emu_panel_transposes(_d(panel), ld, _d(M), n, n, cols, ip.ctypes.data_as(_ip), _d(back), n)
+    return panel[:, :cols], back
+
+
 def set_diag_narrow_min(v):
     lib().emu_set_diag_narrow_min(int(v))
 

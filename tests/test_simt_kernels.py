@@ -161,3 +161,30 @@ def test_emulated_tall_gemm(n, a, b):
     assert _rel(emu.tall_gemm(1.5, X, W, 0.0, np.full_like(Y, np.nan)), 1.5 * X @ W) < 1e-13
     assert _rel(emu.tall_gemm(-1.0, X, W, 1.0, Y), Y - X @ W) < 1e-13
     assert _rel(emu.tall_gemm(1.0, X, np.ascontiguousarray(W.T), 1.0, Y, w_trans=True), Y + X @ W) < 1e-13
+
+
+def test_emulated_small_dense_helpers():
+    """k_pivchol (selection + inverse factor), k_norm_diag, k_colnorm2, k_cm2panel / k_panel2cm."""
+    rng = np.random.default_rng(12)
+    # pivoted Cholesky selection: a rank-5 Gram matrix of 40 columns; Q = P Wsel must be orthonormal and span P
+    n, pb, rk = 300, 40, 5
+    P = rng.standard_normal((n, rk)) @ rng.standard_normal((rk, pb))
+    G = P.T @ P
+    nsel, W, dfirst, remaining = emu.pivchol(G, 1e-20 * np.max(np.diag(G)), 1e-12)
+    assert nsel == rk and abs(dfirst - np.max(np.diag(G))) < 1e-12 * dfirst
+    Q = P @ W[:, :nsel]
+    assert np.linalg.norm(Q.T @ Q - np.eye(nsel)) < 1e-8
+    assert np.linalg.norm(P - Q @ (Q.T @ P)) < 1e-8 * np.linalg.norm(P)
+    assert np.all(W[:, nsel:] == 0.0) and remaining < 1e-10 * dfirst
+    # ||L diag(t) L'||_F^2 from G = L'L
+    L = rng.standard_normal((n, 23))
+    t = rng.standard_normal(23)
+    ref = np.linalg.norm(L @ np.diag(t) @ L.T) ** 2
+    assert abs(emu.norm_diag(L.T @ L, t) - ref) < 1e-12 * ref
+    # column norms
+    M = rng.standard_normal((n, 37))
+    assert np.allclose(emu.colnorm2(M), np.sum(M * M, axis=0), rtol=1e-13)
+    # upload / download transposes with the row permutation
+    iperm = rng.permutation(n).astype(np.int32)
+    panel, back = emu.panel_roundtrip(M, iperm)
+    assert np.array_equal(panel[iperm], M) and np.array_equal(back, M)
