@@ -307,9 +307,24 @@ inline void run_cta() {
         makecontext(&f.ctx, (void (*)())fiber_entry, 0);
 #endif
     }
+    // Scheduling order of the runnable fibers: thread order by default (maximal skew in one direction);
+    // SIMT_SCHED=reverse / random exposes dependences on the opposite / an arbitrary interleaving.
+    static const int sched_mode = [] {
+        const char* ev = getenv("SIMT_SCHED");
+        return !ev ? 0 : (strcmp(ev, "reverse") == 0 ? 1 : (strcmp(ev, "random") == 0 ? 2 : 0));
+    }();
+    static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+    std::vector<int> order(nt);
+    for (int i = 0; i < nt; ++i) order[i] = sched_mode == 1 ? nt - 1 - i : i;
     while (m.cta_alive > 0) {
         bool progress = false;
-        for (int i = 0; i < nt; ++i) {
+        if (sched_mode == 2)
+            for (int i = nt - 1; i > 0; --i) {
+                rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[i], order[(int)((rng_state >> 33) % (uint64_t)(i + 1))]);
+            }
+        for (int oi = 0; oi < nt; ++oi) {
+            const int i = order[oi];
             Fiber& f = m.fibers[i];
             if (f.state != RUN) continue;
             m.cur = &f;
