@@ -358,12 +358,26 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F&& body) {
     if (m.nthreads <= 0 || m.nthreads > 1024) die("bad block size");
     m.body = std::forward<F>(body);
     m.launches++;
-    for (unsigned z = 0; z < grid.z; ++z)
-        for (unsigned y = 0; y < grid.y; ++y)
-            for (unsigned x = 0; x < grid.x; ++x) {
-                m.bid = uint3{x, y, z};
-                run_cta();
-            }
+    // CTAs run one after the other: in launch order by default, reversed / shuffled with SIMT_SCHED=reverse / random
+    // (a kernel whose CTAs depend on each other's results within one launch is wrong on the GPU)
+    const char* ev = getenv("SIMT_SCHED");
+    const int mode = !ev ? 0 : (strcmp(ev, "reverse") == 0 ? 1 : (strcmp(ev, "random") == 0 ? 2 : 0));
+    const uint64_t total = (uint64_t)grid.x * grid.y * grid.z;
+    std::vector<uint64_t> order;
+    if (mode == 2) {
+        order.resize(total);
+        for (uint64_t i = 0; i < total; ++i) order[i] = i;
+        uint64_t st = 0x2545F4914F6CDD1Dull ^ total;
+        for (uint64_t i = total; i > 1; --i) {
+            st = st * 6364136223846793005ull + 1442695040888963407ull;
+            std::swap(order[i - 1], order[(st >> 33) % i]);
+        }
+    }
+    for (uint64_t k = 0; k < total; ++k) {
+        const uint64_t lin = mode == 2 ? order[k] : (mode == 1 ? total - 1 - k : k);
+        m.bid = uint3{(unsigned)(lin % grid.x), (unsigned)((lin / grid.x) % grid.y), (unsigned)(lin / ((uint64_t)grid.x * grid.y))};
+        run_cta();
+    }
     m.body = nullptr;
 }
 
