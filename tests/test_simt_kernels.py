@@ -58,11 +58,14 @@ def test_emulated_factorization_and_sweeps(n, leaf, cap, nrhs):
     S.close()
 
 
-@pytest.mark.parametrize("n,leaf,cap,nrhs", [(371, 0, 0, 37), (1357, 24, 40, 150), (1357, 96, 256, 70)])
+@pytest.mark.parametrize("n,leaf,cap,nrhs", [(371, 0, 0, 37), (1357, 24, 40, 150), (1357, 96, 256, 70),
+                                             (5177, 24, 40, 37)])
 def test_emulated_row_split_sweeps(n, leaf, cap, nrhs):
     """Sweep v2 (DRE_SWEEP2): k_m21 leaves M21 = L21 Linv in the panels, k_fwd2 / k_bwd2 spread the strips of a
     supernode over several CTAs.  (1357, 24, 40) has a populous leaf level (3 / 2 strips per warp) and sparse
-    upper levels (1 strip per warp, 16- and 32-column chunks); (1357, 96, 256) has supernodes of several row blocks."""
+    upper levels (1 strip per warp, 16- and 32-column chunks); (1357, 96, 256) has supernodes of several row blocks;
+    (5177, 24, 40) has populous levels WITH children (11 levels, 494 supernodes: the 3-strip variant with the
+    shared-memory tile of the children's contributions -- levels 1-4 of the n = 79 841 problem)."""
     E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
     S = emu.Solver(E, A, leaf, cap)
     H = _SymFromEmu(E, A, leaf, cap)
