@@ -4,6 +4,7 @@
 // test tier (tests/simt/emu_harness.cpp: host pointers), so that both run the same schedule.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.h"
@@ -32,6 +33,13 @@ struct LevelLists {
     std::vector<int2> fwd2_items;      // (J, rb): strips [rb*8q, (rb+1)*8q) of the ceil(s/8) + ceil(u/8) front strips
     std::vector<int2> bwd2_items;      // (J, rb): strips [rb*8q, (rb+1)*8q) of the ceil(s/8) supernode strips
 };
+
+// levels with at least this many supernodes count as populous for the row-split sweeps (37 x 8 chunks of 32
+// right-hand sides = two CTAs per SM at ~250 columns); DRE_SWEEP2_POPULOUS_MIN overrides it (tests)
+inline int sweep2_populous_min() {
+    const char* ev = getenv("DRE_SWEEP2_POPULOUS_MIN");
+    return ev ? std::max(1, atoi(ev)) : 37;
+}
 
 inline void build_level_lists(const Symbolic& S, LevelLists& out) {
     out.levels.assign(S.nlevels, LevelWork());
@@ -68,7 +76,7 @@ inline void build_level_lists(const Symbolic& S, LevelLists& out) {
         // Row-split sweeps.  Populous levels (enough supernodes to fill the machine with one CTA each at ~250
         // right-hand sides) keep a supernode in as few CTAs as possible; the sparse levels near the root spread
         // every supernode over one CTA per 64 rows.
-        const bool populous = lw.sn_count >= 37;
+        const bool populous = lw.sn_count >= sweep2_populous_min();
         lw.fwd2_q = populous ? 3 : 1;
         lw.bwd2_q = populous ? 2 : 1;
         lw.has_children = lw.ea_count > 0;

@@ -191,3 +191,22 @@ def test_emulated_small_dense_helpers():
     iperm = rng.permutation(n).astype(np.int32)
     panel, back = emu.panel_roundtrip(M, iperm)
     assert np.array_equal(panel[iperm], M) and np.array_equal(back, M)
+
+
+def test_emulated_row_split_sweeps_fat_populous_levels(monkeypatch):
+    """Every level treated as populous (DRE_SWEEP2_POPULOUS_MIN=1) on wide supernodes: the 3-strip forward / 2-strip
+    backward variants with fronts of more than 192 rows, i.e. several row blocks per supernode and a non-zero offset
+    into the children's contribution tile."""
+    monkeypatch.setenv("DRE_SWEEP2_POPULOUS_MIN", "1")
+    n = 20209                      # 9 levels, supernodes up to 141 columns, fronts of ~300 rows
+    E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
+    S = emu.Solver(E, A, 96, 256)
+    rng = np.random.default_rng(9)
+    R = rng.standard_normal((n, 8))
+    for mu in (-0.37, -0.02 + 0.11j):
+        dtype = complex if isinstance(mu, complex) else float
+        assert S.factor(1.0, mu, m21=True) == 0
+        W = S.sweeps(R)
+        M = (A + mu * E).tocsc().astype(dtype)
+        assert _rel(M @ W, R.astype(dtype)) < 1e-12
+    S.close()
