@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdre_b200.so")
 SOURCES = ["symbolic.cpp", "dense_kernels.cu", "sparse_kernels.cu", "context.cu"]
-HEADERS = ["symbolic.h", "kernels.h", "common.cuh", os.path.join("..", "..", "include", "dre_b200.h")]
+HEADERS = ["symbolic.h", "kernels.h", "common.cuh", "schedule.h", os.path.join("..", "..", "include", "dre_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
