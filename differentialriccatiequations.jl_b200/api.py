@@ -120,6 +120,7 @@ class _Panel:
 
     def __init__(self, be: Backend, cols: int):
         self.be, self.cols, self.gen = be, cols, be.generation
+        self.version = 0   # bumped by every in-place writer (_touch): validates the "orthonormal columns" hint
         pid = C.c_int32(-1)
         be.check(be.lib.dre_mat_create(be.h, cols, C.byref(pid)))
         self.id = pid.value
@@ -139,6 +140,7 @@ class _WrappedPanel:
 
     def __init__(self, be: Backend, src: "DeviceMatrix"):
         self.be, self.cols, self.gen, self.src = be, src.ncols, be.generation, src
+        self.version = 0
         owner = src.panel.be
         ptr, ld = C.c_void_p(), C.c_int64()
         owner.check(owner.lib.dre_mat_devptr(owner.h, src.view, C.byref(ptr), C.byref(ld)))
@@ -215,6 +217,20 @@ class DeviceMatrix:
         return self.to_host()
 
 
+def _touch(M: DeviceMatrix):
+    """Record an in-place write into M's panel: an "orthonormal columns" mark taken before it no longer holds
+    (the residual factor a compress! returned is overwritten by every ADI step, adi.jl:171)."""
+    M.panel.version += 1
+
+
+def _mark_orthonormal(M: DeviceMatrix):
+    M._ortho_version = M.panel.version
+
+
+def _is_orthonormal(M) -> bool:
+    return getattr(M, "_ortho_version", None) == M.panel.version
+
+
 def _as_device(M) -> DeviceMatrix:
     return M if isinstance(M, DeviceMatrix) else DeviceMatrix.from_host(M)
 
@@ -243,6 +259,7 @@ def spmm(op: str, X: DeviceMatrix, alpha=1.0, Y: DeviceMatrix | None = None, bet
         Y = DeviceMatrix.empty(X.ncols)
         beta = 0.0
     be.check(be.lib.dre_spmm(be.h, ord(op), float(alpha), X.view, float(beta), Y.view))
+    _touch(Y)
     return Y
 
 
@@ -265,6 +282,7 @@ def gemm_nn(X: DeviceMatrix, W, alpha=1.0, Y: DeviceMatrix | None = None, beta=0
         beta = 0.0
     assert W.shape[1] == Y.ncols
     be.check(be.lib.dre_gemm_nn(be.h, float(alpha), X.view, capi._dptr(W), max(W.shape[0], 1), float(beta), Y.view))
+    _touch(Y)
     return Y
 
 
@@ -400,7 +418,7 @@ def _compress_call(be: Backend, terms):
     dptrs = (C.POINTER(C.c_double) * nt)(*[capi._dptr(D) for _, _, D in terms])
     ldds = (C.c_int64 * nt)(*[max(D.shape[0], 1) for _, _, D in terms])
     alphas = (C.c_double * nt)(*[float(a) for a, _, _ in terms])
-    if getattr(terms[0][1], "orthonormal", False) and np.count_nonzero(terms[0][2] - np.diag(np.diag(terms[0][2]))) == 0:
+    if _is_orthonormal(terms[0][1]) and np.count_nonzero(terms[0][2] - np.diag(np.diag(terms[0][2]))) == 0:
         be.check(be.lib.dre_hint_orthonormal(be.h, terms[0][1].view))  # outer factor of the previous compress!
     cap = min(ktot, be.n)
     out = be.scratch(cap)  # persistent, geometrically grown: allocating ~2 GB per call costs tens of ms
@@ -410,7 +428,7 @@ def _compress_call(be: Backend, terms):
                                       C.byref(newrank)))
     k2 = newrank.value
     Lnew = out.cols(0, k2).copy()  # exact-size panel; the scratch panel is reused by the next compress!
-    Lnew.orthonormal = True         # Q * (orthonormal eigenvectors): lets the next compress! skip these columns
+    _mark_orthonormal(Lnew)         # Q * (orthonormal eigenvectors): lets the next compress! skip these columns
     return Lnew, lam[:k2]
 
 
@@ -461,8 +479,8 @@ class _PendingCompress:
             if L.ncols == 0:
                 continue
             W = _alias(self.lane, L)
-            if getattr(L, "orthonormal", False):
-                W.orthonormal = True
+            if _is_orthonormal(L):
+                _mark_orthonormal(W)
             terms.append((a, W, D))
         self.terms, self.result, self.error = terms, None, None
         self.thread = threading.Thread(target=self._run, name="dre-compress-lane", daemon=True)
@@ -491,7 +509,7 @@ class _PendingCompress:
             raise self.error
         Llane, lam = self.result
         Lnew = _alias(backend(), Llane)      # the compressed factor stays in the lane's arena
-        Lnew.orthonormal = True
+        _mark_orthonormal(Lnew)
         X.alphas[:self.nterms] = [1.0]
         X.Ls[:self.nterms] = [Lnew]
         X.Ds[:self.nterms] = [np.asfortranarray(np.diag(lam))]
@@ -750,6 +768,9 @@ class Wrapped(Shifts.Strategy):  # helpers.jl:48-58
 Shifts.Projection, Shifts.Heuristic, Shifts.Cyclic, Shifts.Wrapped = Projection, Heuristic, Cyclic, Wrapped
 
 
+ORTH_TRACE = None  # set to a list to record (singular values, kept directions) of every orth_restrict call
+
+
 def orth_restrict(Vs, E, A):
     """Q = orth(hcat(Vs)) (src/Stuff.jl:13-18) and the restrictions Q'EQ, Q'AQ (src/Stuff.jl:9,
     src/util/restrict.jl:5-8), without ever forming the SVD basis on the device: a rank-revealing QR
@@ -773,6 +794,8 @@ def orth_restrict(Vs, E, A):
     Q0 = Q0.cols(0, rho)
     U, s, _ = sla.svd(Rt[:, :rho].T, full_matrices=False, lapack_driver="gesdd")  # N = Q0 (U s W')
     ids = np.nonzero(np.abs(s) > n * EPS)[0]  # Stuff.jl:15-16
+    if ORTH_TRACE is not None:  # diagnostics of the free-run tests: singular values and kept count of this refill
+        ORTH_TRACE.append(dict(k=ktot, rho=rho, kept=len(ids), s=s.copy()))
     Us = U[:, ids]
     EQ = spmm("E", Q0)
     Et = gemm_tn(Q0, EQ)
@@ -1167,6 +1190,7 @@ def perform_single_step_(cache: ADICache, mu: float):
             spmm("E", V, -2.0 * mu, R, 1.0)
         else:
             be.check(be.lib.dre_adi_step(be.h, mu, 0.0, R.view, V.view, View(-1, 0, 0)))
+            _touch(R)
         _prefetch_next_factorization(cache)
     else:
         F = (prob.A.adjoint().plus_sparse(PencilCombo(0.0, mu)) if isinstance(prob.A, LowRankUpdate)
@@ -1202,6 +1226,7 @@ def perform_double_step_(cache: ADICache, mu: complex):
             spmm("E", V1, -2.0 * math.sqrt(2.0) * mu.real, R, 1.0)
         else:
             be.check(be.lib.dre_adi_step(be.h, mu.real, mu.imag, R.view, V1.view, V2.view))
+            _touch(R)
         _prefetch_next_factorization(cache)
     else:
         F = (prob.A.adjoint().plus_sparse(PencilCombo(0.0, 0.0)) if isinstance(prob.A, LowRankUpdate)
@@ -1210,8 +1235,10 @@ def perform_double_step_(cache: ADICache, mu: complex):
         d = mu.real / mu.imag
         V1 = Vr.copy()
         be.check(be.lib.dre_mat_axpby(be.h, math.sqrt(2.0) * d, Vi.view, math.sqrt(2.0), V1.view))
+        _touch(V1)
         V2 = Vi.copy()
         be.check(be.lib.dre_mat_axpby(be.h, 0.0, View(-1, 0, 0), math.sqrt(2 * d * d + 2), V2.view))
+        _touch(V2)
         spmm("E", V1, -2.0 * math.sqrt(2.0) * mu.real, R, 1.0)
     cache.increment = (-2.0 * mu.real * alpha) * (LDLt([1.0], [V1], [T]) + LDLt([1.0], [V2], [T]))
     cache.X = cache.X + cache.increment

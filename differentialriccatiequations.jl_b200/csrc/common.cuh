@@ -64,6 +64,15 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 #endif
 }
 
+// Function attributes (cudaFuncSetAttribute) are per device; the "already set" flags of the launchers are arrays
+// indexed by the device ordinal.
+#define DRE_MAX_DEVICES 64
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < DRE_MAX_DEVICES) ? dev : 0;
+}
+
 // ---- kernel launch / dynamic shared memory spelling ----
 // The kernel sources are also compiled by g++ against the host-side SIMT emulator of the CPU test tier
 // (tests/simt/stub/cuda_runtime.h, -DDRE_SIMT_EMU), which supplies its own versions of these three macros;

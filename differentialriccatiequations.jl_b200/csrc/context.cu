@@ -204,11 +204,13 @@ struct dre_context {
         cudaEvent_t released = nullptr;  // recorded on the main stream behind the last sweeps that read the slot
         bool has_reader = false;
         bool pending = false;        // queued by dre_prefactor and not yet adopted by a solve
+        uint64_t queued_at = 0;      // value of solve_seq when dre_prefactor queued it (stale-slot reclamation)
         cudaStream_t st = nullptr;   // side stream of this slot (factorizations of different slots overlap)
     };
     static constexpr int NSLOT = 4;  // the slot in use + up to three prefactorizations in flight
     FactorSlot slot[NSLOT];
     int cur = 0;
+    uint64_t solve_seq = 0;          // block solves so far (acquire_factor calls)
     DBuf<unsigned char> tbuf;
     DBuf<unsigned char> Wbuf;
     DBuf<double> btw, sol;
@@ -241,6 +243,7 @@ struct dre_context {
 
     // stats
     dre_stats stats{};
+    int64_t stats_stale_prefactors = 0;   // queued factorizations that were never adopted (reclaimed by pick_slot)
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
@@ -314,6 +317,12 @@ int check_errflag(dre_context* c) {
     CU(cudaStreamSynchronize(c->st));
     if (flag != 0) {
         CU(cudaMemsetAsync(c->d_errflag, 0, sizeof(int32_t), c->st));
+        if (flag == 1) {
+            // the flag does not say which factorization broke down (it may be one queued on a side stream): none of
+            // the held factors may be adopted again
+            CU(cudaDeviceSynchronize());
+            for (int i = 0; i < dre_context::NSLOT; ++i) c->slot[i].valid = c->slot[i].pending = false;
+        }
         return fail(c, DRE_ERR_NUMERIC,
                     flag == 1 ? "numeric factorization broke down (zero or non-finite pivot)"
                               : "Sherman-Morrison-Woodbury core is singular");
@@ -326,7 +335,8 @@ static const bool g_trace = getenv("DRE_TRACE") != nullptr;
 // DRE_RR_STATS=1: totals of the rank-revealing Gram-Schmidt rounds, printed when a context dies
 static const bool g_rr_stats = getenv("DRE_RR_STATS") != nullptr;
 struct RRTotals {
-    long calls = 0, blocks = 0, rounds = 0, productive = 0, skipped = 0, syncs = 0, rest_projections = 0;
+    long calls = 0, blocks = 0, rounds = 0, productive = 0, skipped = 0, syncs = 0, rest_projections = 0,
+         coef_only_passes = 0;
 } g_rr;
 struct HostTrace {
     const char* name;
@@ -457,6 +467,17 @@ inline bool slot_matches(const dre_context* c, const dre_context::FactorSlot& fs
 
 // slot to (re)fill: an empty one, else a consumed one, else (only when `allow_pending`) a queued one
 inline int pick_slot(dre_context* c, bool allow_pending) {
+    // A queued factorization is adopted within NSLOT - 1 solves (the host queues the next shifts of the buffer in
+    // order).  One that is still pending after more solves than that was queued for an ADI run that has ended
+    // early (convergence) or for a buffer that was refilled: it is stale and its slot is free again -- without
+    // this the pipeline depth would drop to one after the first converged solve.
+    for (int i = 0; i < dre_context::NSLOT; ++i) {
+        dre_context::FactorSlot& fs = c->slot[i];
+        if (fs.pending && c->solve_seq > fs.queued_at + (uint64_t)dre_context::NSLOT) {
+            fs.pending = false;
+            c->stats_stale_prefactors++;
+        }
+    }
     for (int i = 0; i < dre_context::NSLOT; ++i)
         if (i != c->cur && !c->slot[i].valid) return i;
     for (int i = 0; i < dre_context::NSLOT; ++i)
@@ -470,6 +491,7 @@ inline int pick_slot(dre_context* c, bool allow_pending) {
 template <class T>
 int acquire_factor(dre_context* c, double mu_re, double mu_im, T emu, cudaStream_t st) {
     const int tw = (int)(sizeof(T) / sizeof(double));
+    c->solve_seq++;
     for (int i = 0; i < dre_context::NSLOT; ++i) {
         dre_context::FactorSlot& fs = c->slot[i];
         if (slot_matches(c, fs, mu_re, mu_im, tw)) {
@@ -511,6 +533,7 @@ int prefactor_t(dre_context* c, double mu_re, double mu_im, T emu) {
     CU(cudaEventRecord(fs.ready, fs.st));
     fs.valid = true;
     fs.pending = true;
+    fs.queued_at = c->solve_seq;
     fs.a = c->op_a; fs.re = c->op_e + mu_re; fs.im = mu_im; fs.tw = tw;
     fs.has_reader = false;
     c->stats.prefactors++;
@@ -639,6 +662,21 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
         // single pass, and the second ("twice is enough") pass is only spent on blocks with large columns.  The
         // orthogonality of the basis does not depend on it: candidates are re-orthogonalised below.
         const int npass = (block_max2 <= 0.0025 * s.scale2) ? 1 : 2;
+        // remainder norms after the block passes: a sub-panel whose columns are all below the drop threshold
+        // cannot contribute a direction (pivoted Cholesky would select nothing) and is skipped without its
+        // Gram / selection / synchronisation
+        std::vector<double> rem2(pbig, 0.0);
+        bool have_rem = false;
+        auto remainder_norms = [&]() -> int {
+            constexpr int NBLK = 296;
+            launch_colnorm2(Pbig, PBIG, n, pbig, c->gram_partial.p, NBLK, c->cnorm.p, c->st, &c->stats.kernel_launches);
+            CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            g_rr.syncs++;
+            for (int j = 0; j < pbig; ++j) rem2[j] = c->h_pinned[16 + j];
+            have_rem = true;
+            return DRE_OK;
+        };
         if (rho0 > 0) {
             CU(c->cbuf.ensure((size_t)PBIG * rho0));
             for (int pass = 0; pass < npass; ++pass) {
@@ -646,22 +684,19 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                 rc = gram_dev(c, Pbig, PBIG, pbig, s.Q, s.ldq, rho0, n, nullptr, c->cbuf.p, rho0,
                               s.RT + (int64_t)(rt_row0 + c0) * s.ldrt, s.ldrt);
                 if (rc) return rc;
+                if (pass == 1 && have_rem) {
+                    // The first pass already left every column of the block below the drop threshold: the block adds
+                    // no direction, so the second pass only has to refine the coefficients (its Gram product above);
+                    // the remainder itself is never looked at again and its update is skipped.
+                    double m2 = 0.0;
+                    for (int j = 0; j < pbig; ++j) m2 = std::max(m2, rem2[j]);
+                    const double drop0 = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
+                    if (m2 < drop0 * drop0) { g_rr.coef_only_passes++; break; }
+                }
                 rc = tall_gemm(c, -1.0, s.Q, s.ldq, rho0, c->cbuf.p, rho0, 1, 1.0, Pbig, PBIG, pbig, n);
                 if (rc) return rc;
+                if ((rc = remainder_norms())) return rc;
             }
-        }
-        // remainder norms after the block passes: a sub-panel whose columns are all below the drop threshold
-        // cannot contribute a direction (pivoted Cholesky would select nothing) and is skipped without its
-        // Gram / selection / synchronisation
-        std::vector<double> rem2(pbig, 0.0);
-        bool have_rem = false;
-        if (rho0 > 0) {
-            constexpr int NBLK = 296;
-            launch_colnorm2(Pbig, PBIG, n, pbig, c->gram_partial.p, NBLK, c->cnorm.p, c->st, &c->stats.kernel_launches);
-            CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-            CU(cudaStreamSynchronize(c->st));
-            for (int j = 0; j < pbig; ++j) rem2[j] = c->h_pinned[16 + j];
-            have_rem = true;
         }
         // Optional eager projection of the rest of the block (DRE_RR_EAGER=1, off by default): as soon as a sub-panel
         // has added directions, the columns behind it are projected against them in ONE fat Gram / tall-GEMM pair
@@ -1010,8 +1045,9 @@ int32_t dre_destroy(dre_context* c) {
     if (g_rr_stats && c)
         fprintf(stderr,
                 "[dre rr totals] blocks %ld rounds %ld productive %ld skipped sub-panels %ld rest projections %ld "
-                "round syncs %ld kernel launches (context) %lld\n",
-                g_rr.blocks, g_rr.rounds, g_rr.productive, g_rr.skipped, g_rr.rest_projections, g_rr.syncs,
+                "coefficient-only second passes %ld round syncs %ld kernel launches (context) %lld\n",
+                g_rr.blocks, g_rr.rounds, g_rr.productive, g_rr.skipped, g_rr.rest_projections, g_rr.coef_only_passes,
+                g_rr.syncs,
                 (long long)c->stats.kernel_launches);
     if (!c) return DRE_OK;
     cudaSetDevice(c->device);
@@ -1563,7 +1599,15 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     if (ktot == 0) return DRE_OK;
     const int64_t n = c->sym.n;
     RRState s;
-    if ((rc = rr_setup(c, s, ktot, 3e-15, 0.0))) return rc;
+    // Basis directions are dropped at HALF the relative level at which compress! truncates the eigenvalues of the
+    // projected core below (tol_factor * eps, src/LDLt.jl:216-217): a direction whose coefficients are below
+    // sigma * scale changes X by at most O(sigma) ||X|| through its cross terms with the large directions, i.e. by
+    // no more than the truncation the reference applies itself.  (A tighter threshold -- 3e-15 was used before --
+    // sits inside the round-off left by the block projections (~30 eps per pass over n rows), so that late ADI
+    // increments "found" one to three noise directions per sub-panel: two thirds of all selection rounds.)
+    static const double drop_env = getenv("DRE_RR_DROP") ? atof(getenv("DRE_RR_DROP")) : 0.0;
+    const double drop_rel = drop_env > 0.0 ? drop_env : 0.5 * tol_factor * 2.220446049250313e-16;
+    if ((rc = rr_setup(c, s, ktot, drop_rel, 0.0))) return rc;
     const dre_view hint = c->ortho_hint;
     c->ortho_hint = dre_view{-1, 0, 0};
     std::vector<double> signs(ktot, 1.0);

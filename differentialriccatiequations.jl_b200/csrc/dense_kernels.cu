@@ -467,7 +467,8 @@ void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t l
         dim3 grid(tiles_a * tiles_b, plan.nsplit);
         DRE_LAUNCH((k_gram), grid, 256, 0, st, X, ldx, a, Y, ldy, b, n, roww, partial, tiles_b, plan.rows_per_split);
     } else {
-        static bool attr_set = false;
+        static bool attr_set_dev[DRE_MAX_DEVICES] = {};
+        bool& attr_set = attr_set_dev[current_device()];
         const int smem128 = G2ST * G2K * (G2LDA + 128 + 8) * (int)sizeof(double);
         const int smem64 = G2ST * G2K * (G2LDA + 64 + 8) * (int)sizeof(double);
         if (!attr_set) {
@@ -569,7 +570,8 @@ __global__ void __launch_bounds__(256) k_tall_gemm_smallk(double alpha, const do
 template <int T2N>
 static void launch_tall_gemm_t(double alpha, const double* X, int64_t ldx, int a, const double* W, int64_t ldw,
                                int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n, cudaStream_t st) {
-    static bool attr_set = false;
+    static bool attr_set_dev[DRE_MAX_DEVICES] = {};
+        bool& attr_set = attr_set_dev[current_device()];
     const int smem = T2ST * T2Cfg<T2N>::STAGE * (int)sizeof(double);
     if (!attr_set) {
         cudaFuncSetAttribute(k_tall_gemm2<T2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -587,7 +589,8 @@ void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const d
                       int64_t* launches) {
     if (b <= 0 || n <= 0) return;
     if (a <= TSK && b > 16) {
-        static bool attr_set = false;
+        static bool attr_set_dev[DRE_MAX_DEVICES] = {};
+        bool& attr_set = attr_set_dev[current_device()];
         const int smem = (T2M * TSLDX + TSK * TSLDW) * (int)sizeof(double);
         if (!attr_set) {
             cudaFuncSetAttribute(k_tall_gemm_smallk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -862,7 +865,8 @@ __global__ void __launch_bounds__(256) k_pivchol(const double* __restrict__ G, i
 
 void launch_pivchol(const double* G, int64_t ldg, int pb, double drop2, double rel2, double* Wsel, int32_t* info,
                     double* dinfo, cudaStream_t st, int64_t* launches) {
-    static bool attr_set = false;
+    static bool attr_set_dev[DRE_MAX_DEVICES] = {};
+        bool& attr_set = attr_set_dev[current_device()];
     const int smem = 2 * 64 * 65 * (int)sizeof(double);
     if (!attr_set) {
         cudaFuncSetAttribute(k_pivchol, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

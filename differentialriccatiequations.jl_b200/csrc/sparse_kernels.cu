@@ -698,11 +698,14 @@ static int bwd_smem(int smax) {
 
 template <class T, int NT, int Q, int NW>
 static void set_sweep_attrs() {
-    static bool done = false;
-    if (done) return;
+    // function attributes are per device: one flag per device ordinal (several contexts of one process may live on
+    // different GPUs)
+    static bool done[DRE_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (done[dev]) return;
     cudaFuncSetAttribute(k_fwd<T, NT, Q, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<T, NT>(8 * NW * Q));
     cudaFuncSetAttribute(k_bwd<T, NT, Q, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<T, NT>(8 * NW * Q));
-    done = true;
+    done[dev] = true;
 }
 
 // widest chunk that still gives every SM a CTA; narrow chunks for the few fat supernodes near the root
@@ -1162,10 +1165,11 @@ static void launch_fwd2_t(const DevSymbolic& S, const int2* items, int nitems, i
     constexpr int LDB = RhsLd<T, NT * MM<T>::CPN>::value;
     const int srows = (smax + 7) & ~7;
     const int smem = (int)sizeof(T) * (srows + (has_children ? 64 * Q : 0)) * LDB;
-    static int smem_set = 0;
-    if (smem > smem_set) {
+    static int smem_set[DRE_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (smem > smem_set[dev]) {
         cudaFuncSetAttribute(k_fwd2<T, NT, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        smem_set = smem;
+        smem_set[dev] = smem;
     }
     const int cw = NT * MM<T>::CPN;
     dim3 grid(nitems, (nrhs + cw - 1) / cw);
@@ -1179,10 +1183,11 @@ static void launch_bwd2_t(const DevSymbolic& S, const int2* items, int nitems, i
     constexpr int LDB = RhsLd<T, NT * MM<T>::CPN>::value;
     const int srows = (smax + 7) & ~7;
     const int smem = (int)sizeof(T) * (srows + 64) * LDB;
-    static int smem_set = 0;
-    if (smem > smem_set) {
+    static int smem_set[DRE_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (smem > smem_set[dev]) {
         cudaFuncSetAttribute(k_bwd2<T, NT, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        smem_set = smem;
+        smem_set[dev] = smem;
     }
     const int cw = NT * MM<T>::CPN;
     dim3 grid(nitems, (nrhs + cw - 1) / cw);
