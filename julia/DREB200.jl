@@ -224,9 +224,263 @@ function Base.:(*)(L::DRE.LyapunovOperator, X::DRE.LDLᵀ{Float64,DeviceMatrix,M
     a * DRE.lowrank(Z2, [O Y; Y O])
 end
 
-# The remaining specialisations (residual, take_many!(::ProjectionShiftIterator), the K update and RHS
-# assembly of lowrank_ros1/2.jl and newton.jl) follow api.py function by function:
-#   api.residual          -> DRE.residual(::GALEProblem{<:LDLᵀ{…DeviceMatrix…}}, ::LDLᵀ)
-#   api.orth_restrict     -> Shifts.take_many!(::ProjectionShiftIterator)   (dre_rrqr + host svd/eigvals)
-#   api._feedback         -> K = (B'L D)(L'E)                               (dre_gemm_tn, dre_spmm, dre_gemm_nn)
+# ==============================================================================================
+# The hooks that make the reference's OWN drivers run on DeviceMatrix-backed problems.
+#
+#   using DifferentialRiccatiEquations, DREB200
+#   ctx  = DREB200.context();  Ed, Ad = DREB200.pencil!(ctx, E, A)          # uploads once, symbolic analysis once
+#   X0   = lowrank(DREB200.DeviceMatrix(ctx, L0), D0)
+#   prob = GDREProblem(Ed, Ad, B, C, X0, tspan)                             # B, C stay host matrices
+#   sol  = solve(prob, Ros1(ADI(inner_alg = DREB200.Solver())); dt = -100)  # reference driver, unmodified
+#
+# Everything below is a METHOD OF A REFERENCE FUNCTION (or of Base/LinearAlgebra functions the reference's generic
+# code calls) specialised on the three types of this file:
+#   DeviceMatrix  n x k panel           (TL of LDLᵀ{T,TL,TD};  Adjoint{Float64,DeviceMatrix} = k x n, e.g. K)
+#   PencilOp      a*A + e*E, lazy       (<: AbstractSparseMatrix, so lr_update/`+` keep it lazy: LowRankUpdate.jl:38-39,66-70)
+#   Solver        <: BlockLinearSolver  (the `inner_alg` seam, blocklinear/types.jl:15-30)
+# ==============================================================================================
+
+# ---- PencilOp: the sparse part of every operator on the path is a combination of the two uploaded matrices ----
+# Ros1: A - E/(2τ) (lowrank_ros1.jl:39), Ros2: γτA - E/2 (lowrank_ros2.jl), ADI: A' + (μE)' (adi.jl:156,195).
+struct PencilOp{T<:Number} <: SparseArrays.AbstractSparseMatrix{T,Int64}
+    ctx::Context
+    a::T        # coefficient of A
+    e::T        # coefficient of E
+end
+function pencil!(ctx::Context, E::SparseMatrixCSC{Float64,Int64}, A::SparseMatrixCSC{Float64,Int64})
+    set_pencil!(ctx, E, A)
+    PencilOp(ctx, 0.0, 1.0), PencilOp(ctx, 1.0, 0.0)          # (E, A)
+end
+Base.size(P::PencilOp) = (P.ctx.n, P.ctx.n)
+Base.size(P::PencilOp, i::Integer) = i <= 2 ? P.ctx.n : 1
+SparseArrays.issparse(::PencilOp) = true                        # LowRankUpdate.jl:67 asserts it
+Base.adjoint(P::PencilOp{<:Real}) = P                           # symmetric pencil (dre_symbolic_create checks it)
+Base.adjoint(P::PencilOp{<:Complex}) = PencilOp(P.ctx, conj(P.a), conj(P.e))   # (conj(μ)E)' == μE', adi.jl:195
+Base.transpose(P::PencilOp) = P
+Base.:+(P::PencilOp, Q::PencilOp) = PencilOp(P.ctx, P.a + Q.a, P.e + Q.e)
+Base.:-(P::PencilOp, Q::PencilOp) = PencilOp(P.ctx, P.a - Q.a, P.e - Q.e)
+Base.:-(P::PencilOp) = PencilOp(P.ctx, -P.a, -P.e)
+Base.:*(s::Number, P::PencilOp) = PencilOp(P.ctx, s * P.a, s * P.e)
+Base.:*(P::PencilOp, s::Number) = s * P
+Base.:/(P::PencilOp, s::Number) = PencilOp(P.ctx, P.a / s, P.e / s)
+
+# P*L, P'L  (E'L, A'L: residual.jl:18, lowrank_ros1.jl:42, adi.jl:171,217)
+function Base.:*(P::PencilOp{<:Real}, L::DeviceMatrix)
+    Y = similar(L)
+    iszero(P.e) || spmm!(Y, 'E', L, P.e, 0.0)
+    iszero(P.a) || spmm!(Y, 'A', L, P.a, iszero(P.e) ? 0.0 : 1.0)
+    iszero(P.e) && iszero(P.a) && axpby!(Y, 0.0, Y, 0.0)
+    Y
+end
+# mul!(R, E', V, -2μ, true): the residual update of adi.jl:171,217 when the generic step methods are used
+function LinearAlgebra.mul!(Y::DeviceMatrix, P::PencilOp{<:Real}, X::DeviceMatrix, α::Number, β::Number)
+    iszero(P.e) || spmm!(Y, 'E', X, α * P.e, β)
+    iszero(P.a) || spmm!(Y, 'A', X, α * P.a, iszero(P.e) ? β : 1.0)
+    Y
+end
+LinearAlgebra.mul!(Y::DeviceMatrix, P::PencilOp{<:Real}, X::DeviceMatrix) = mul!(Y, P, X, true, false)
+# L'E as the lazy adjoint of E'L (k x n "row panel", lowrank_ros1.jl:28,56)
+Base.:*(Lt::Adjoint{Float64,DeviceMatrix}, P::PencilOp{<:Real}) = (P' * parent(Lt))'
+
+# ---- small-matrix products with panels ----
+axpby!(Y::DeviceMatrix, α, X::DeviceMatrix, β) =
+    (check(Y.p.ctx, ccall((:dre_mat_axpby, LIB), Int32, (Ptr{Cvoid}, Float64, View, Float64, View),
+                          Y.p.ctx.h, α, view_of(X), β, view_of(Y))); Y)
+function gemm_nn!(Y::DeviceMatrix, X::DeviceMatrix, W::Matrix{Float64}, α::Real, β::Real)
+    GC.@preserve W check(X.p.ctx, ccall((:dre_gemm_nn, LIB), Int32,
+        (Ptr{Cvoid}, Float64, View, Ptr{Float64}, Int64, Float64, View),
+        X.p.ctx.h, α, view_of(X), W, stride(W, 2), β, view_of(Y)))
+    Y
+end
+# host matrices that multiply panels (B, C') are uploaded once and cached by identity
+# (B is n x m, C is q x n: whichever orientation has n rows is the panel -- B, B' -> B;  C, C' -> C')
+const HOSTCACHE = IdDict{Any,DeviceMatrix}()
+function device_of(ctx::Context, M::Union{Matrix{Float64},Adjoint{Float64,Matrix{Float64}}})
+    key = M isa Adjoint ? parent(M) : M
+    get!(HOSTCACHE, key) do
+        DeviceMatrix(ctx, size(M, 1) == ctx.n ? Matrix(M) : Matrix(M'))
+    end
+end
+device_of(::Context, M::DeviceMatrix) = M
+device_of(::Context, M::Adjoint{Float64,DeviceMatrix}) = parent(M)
+
+# B'L -> host m x k  (lowrank_ros1.jl:26,54; newton.jl; smw)
+Base.:*(Bt::Adjoint{Float64,Matrix{Float64}}, L::DeviceMatrix) = gemm_tn(device_of(L.p.ctx, parent(Bt)), L)
+Base.:*(Lt::Adjoint{Float64,DeviceMatrix}, B::Matrix{Float64}) = gemm_tn(parent(Lt), device_of(parent(Lt).p.ctx, B))
+Base.:*(Xt::Adjoint{Float64,DeviceMatrix}, Y::DeviceMatrix) = gemm_tn(parent(Xt), Y)          # Q'(EQ), V*Q with V = K
+# L*W (W small host) and W*(L'E): K = (B'L D) * (L'E) stays a lazy adjoint of an n x m panel
+Base.:*(L::DeviceMatrix, W::Matrix{Float64}) = gemm_nn!(DeviceMatrix(L.p.ctx, size(W, 2)), L, W, 1.0, 0.0)
+Base.:*(W::Matrix{Float64}, Xt::Adjoint{Float64,DeviceMatrix}) = (parent(Xt) * Matrix(W'))'
+LinearAlgebra.mul!(Y::DeviceMatrix, U::DeviceMatrix, W::Matrix{Float64}, α::Number, β::Number) = gemm_nn!(Y, U, W, α, β)
+Base.Matrix(Kt::Adjoint{Float64,DeviceMatrix}) = Matrix(Matrix(parent(Kt))')                    # K(t) for the user
+# adapt(TL, BᵀLD) / adapt(TD, B'L) of lowrank_ros1.jl:26-28: small matrices stay on the host
+import Adapt
+Adapt.adapt_storage(::Type{DeviceMatrix}, M::Matrix{Float64}) = M
+Adapt.adapt_storage(::Type{<:Matrix}, M::Matrix{Float64}) = M
+
+# ---- _hcat / similar / column assignment (util/_hcat.jl:5-18; LDLt.jl:174-191) ----
+Base.similar(::Type{DeviceMatrix}, m::Int, k::Int) = (ctx = context(); @assert m == ctx.n; DeviceMatrix(ctx, k))
+function Base.setindex!(L::DeviceMatrix, X::DeviceMatrix, ::Colon, span::UnitRange{Int})
+    check(L.p.ctx, ccall((:dre_mat_copy, LIB), Int32, (Ptr{Cvoid}, View, View), L.p.ctx.h, view_of(view_cols(L, span)), view_of(X)))
+    X
+end
+Base.setindex!(L::DeviceMatrix, X::Union{Matrix{Float64},Adjoint{Float64,Matrix{Float64}}}, c::Colon, span::UnitRange{Int}) =
+    setindex!(L, device_of(L.p.ctx, X), c, span)                                               # C' in _hcat(TL, C', E'L)
+Base.hcat(Xs::DeviceMatrix...) = DRE._hcat(DeviceMatrix, Xs)                                   # projection.jl:58
+Base.copy(L::DeviceMatrix) = (Y = similar(L); Y[:, 1:L.ncols] = L; Y)
+Base.deepcopy_internal(L::DeviceMatrix, ::IdDict) = copy(L)                                     # residual.jl:9
+
+# ---- residual(::GALEProblem{<:LDLᵀ}, ::LDLᵀ)  (lyapunov/residual.jl:3-31) ----
+# The generic method already works through the products above; this one avoids the temporary A'L panel of the
+# closed-loop operator by writing the three blocks straight into column views of R.
+function DRE.residual(prob::DRE.GALEProblem{<:DRE.LDLᵀ{Float64,DeviceMatrix,Matrix{Float64}}},
+                      val::DRE.LDLᵀ{Float64,DeviceMatrix,Matrix{Float64}})
+    E, A, C = prob.E, prob.A, prob.C
+    iszero(val) && return deepcopy(C)
+    alpha, G, S = C
+    beta, L, D = val
+    n_G, n_0 = size(G, 2), size(L, 2)
+    dim = n_G + 2n_0
+    R = DeviceMatrix(L.p.ctx, dim)
+    R[:, 1:n_G] = G
+    spmm!(view_cols(R, n_G+1:n_G+n_0), 'E', L, 1.0, 0.0)
+    AtL = view_cols(R, n_G+n_0+1:dim)
+    if A isa DRE.LowRankUpdate                        # A'L = A_s'L + inv(α) V'(U'L), LowRankUpdate.jl:51-54,77-86
+        As, α, U, V = A
+        mul!(AtL, As', L)
+        mul!(AtL, parent(V), U' * L, inv(α), true)    # V = K is an Adjoint{DeviceMatrix}; U = B (host)
+    else
+        mul!(AtL, A', L)
+    end
+    T = zeros(dim, dim)
+    T[1:n_G, 1:n_G] .= alpha .* S
+    T[n_G+1:n_G+n_0, n_G+n_0+1:dim] .= beta .* D
+    T[n_G+n_0+1:dim, n_G+1:n_G+n_0] .= beta .* D
+    DRE.compress!(DRE.lowrank(R, T))
+end
+
+# ---- the BlockLinearSolver seam (blocklinear/types.jl:15-30, backslash.jl:8-21, sherman-morrison-woodbury.jl) ----
+# ADI(inner_alg = DREB200.Solver()).  prob.A is a PencilOp (plain GALE) or a LowRankUpdate over one (Ros1/Ros2/
+# Newton); prob.B the real n x r residual factor.  Real shifts return a DeviceMatrix, complex shifts a ComplexPanel.
+struct Solver <: DRE.BlockLinearSolver end
+struct ComplexPanel            # V = re + im*i of the complex double step (adi.jl:196-199)
+    re::DeviceMatrix
+    im::DeviceMatrix
+end
+Base.real(V::ComplexPanel) = V.re
+Base.imag(V::ComplexPanel) = V.im
+Base.iszero(::ComplexPanel) = false
+mutable struct SolverState     # init/solve!/rhs protocol: rhs(solver) is modified in place by the caller (heuristic.jl:51-60)
+    F
+    B::DeviceMatrix
+end
+CommonSolve.init(prob::DRE.BlockLinearProblem, ::Solver) = SolverState(prob.A, prob.B isa DeviceMatrix ? prob.B :
+                                                                       DeviceMatrix(context(), reshape(Vector{Float64}(prob.B), :, 1)))
+DRE.rhs(s::SolverState) = s.B
+split_operator(F::PencilOp) = (F, 1.0, nothing, nothing)
+split_operator(F::DRE.LowRankUpdate) = (F.A, Float64(F.α), F.U, F.V)
+function CommonSolve.solve!(s::SolverState)
+    P, α, U, V = split_operator(s.F)
+    ctx = P.ctx
+    z = View(-1, 0, 0)
+    # System handed over by the ADI step (adi.jl:156,195):  (A_s' + μE' + inv(α) U V) X = B  where, after
+    # adjoint(::LowRankUpdate) (LowRankUpdate.jl:51-54), U = K' is an n x m panel and V = B' a host adjoint.
+    # Library convention (include/dre_b200.h, dre_set_operator / dre_shift_solve): with operator panels (U_op, Vt_op)
+    # it solves (a A + (e + μ) E + inv(α) Vt_op U_op') X = B.  Hence Vt_op = U, U_op = V'.
+    a, e = real(P.a), P.e
+    Vt_op = U === nothing ? nothing : device_of(ctx, U)
+    U_op = V === nothing ? nothing : device_of(ctx, V)
+    check(ctx, ccall((:dre_set_operator, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, View, View),
+                     ctx.h, a, 0.0, α, U_op === nothing ? z : view_of(U_op), Vt_op === nothing ? z : view_of(Vt_op)))
+    R = s.B
+    if iszero(imag(e))
+        X = similar(R)
+        check(ctx, ccall((:dre_shift_solve, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, View, View, View),
+                         ctx.h, real(e), 0.0, view_of(R), view_of(X), z))
+        return X
+    else
+        Xr, Xi = similar(R), similar(R)
+        check(ctx, ccall((:dre_shift_solve, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, View, View, View),
+                         ctx.h, real(e), imag(e), view_of(R), view_of(Xr), view_of(Xi)))
+        return ComplexPanel(Xr, Xi)
+    end
+end
+CommonSolve.solve(prob::DRE.BlockLinearProblem, alg::Solver) = CommonSolve.solve!(CommonSolve.init(prob, alg))
+
+# ---- perform_single_step! / perform_double_step!  (lyapunov/adi.jl:149-225): ONE ccall per ADI step ----
+const DeviceADICache = DRE.ADICache{Float64,DeviceMatrix,DeviceMatrix,Matrix{Float64}}
+operator_of(A::PencilOp) = DeviceOperator(real(A.a), real(A.e), 1.0, nothing, nothing)
+function operator_of(F::DRE.LowRankUpdate)        # F = A_s + inv(α) U V with U = B (host), V = K (lazy adjoint panel)
+    ctx = F.A.ctx
+    DeviceOperator(real(F.A.a), real(F.A.e), Float64(F.α), device_of(ctx, F.U), parent(F.V))
+end
+function prefetch!(cache::DeviceADICache)
+    # the buffered shifts are known ahead (shifts/helpers.jl:106-113): factor the next ones on side streams
+    it = cache.shifts_oracle
+    hasproperty(it, :buffer) || return
+    ctx = only(cache.residual.Ls).p.ctx
+    left = cache.alg.maxiters - length(cache.shifts)
+    queued, skip = 0, false
+    for μ in Iterators.take(it.buffer, 6)
+        (left <= 0 || queued >= 3) && break
+        left -= 1
+        skip && (skip = false; continue)             # conjugate partner: one factorization serves the pair
+        skip = !isreal(μ)
+        prefactor!(ctx, Complex(μ)); queued += 1
+    end
+end
+function DRE.perform_single_step!(cache::DeviceADICache, μ)
+    alpha, R, T = cache.residual
+    ctx = R.p.ctx
+    V, _ = adi_step!(ctx, operator_of(cache.prob.A), Complex(μ), R)      # V = (F'+μE')⁻¹R;  R -= 2μ E'V
+    prefetch!(cache)
+    cache.increment = (-2real(μ) * alpha) * DRE.lowrank(V, T)
+    cache.X += cache.increment
+    cache.last_compression += 1
+    DRE.Shifts.update!(cache.shifts_oracle, cache.X, R, V)
+    nothing
+end
+function DRE.perform_double_step!(cache::DeviceADICache, μ)
+    alpha, R, T = cache.residual
+    ctx = R.p.ctx
+    μ_next = DRE.Shifts.take!(cache.shifts_oracle)
+    @assert μ_next ≈ conj(μ)
+    push!(cache.shifts, μ_next)
+    DRE.Callbacks.observe_gale_metadata!(cache.observer, "ADI shifts", μ_next)
+    # V₁ = √2(Re V + δ Im V), V₂ = √(2δ²+2) Im V are formed inside the kernel epilogue; R -= 2√2 Re(μ) E'V₁
+    V₁, V₂ = adi_step!(ctx, operator_of(cache.prob.A), Complex(μ), R)
+    prefetch!(cache)
+    cache.increment = (-2real(μ) * alpha) * (DRE.lowrank(V₁, T) + DRE.lowrank(V₂, T))
+    cache.X += cache.increment
+    cache.last_compression += 2
+    DRE.Shifts.update!(cache.shifts_oracle, cache.X, R, V₁, V₂)
+    nothing
+end
+
+# ---- Projection shifts: orth / restrict  (Stuff.jl:9-18, util/restrict.jl:5-8, shifts/projection.jl:54-73) ----
+# take_many! itself stays the reference's: hcat(Vs...) -> orth -> restrict(E,Q), restrict(A,Q) -> eigvals.
+function DRE.Stuff.orth(N::DeviceMatrix)
+    ctx = N.p.ctx
+    n, k = size(N)
+    cap = min(k, n)
+    Q0 = DeviceMatrix(ctx, cap)
+    Rt = zeros(k, cap)
+    rho = Ref{Int32}(0)
+    views = [view_of(N)]
+    ε = n * eps()
+    GC.@preserve views Rt check(ctx, ccall((:dre_rrqr, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{View}, Float64, Float64, View, Ptr{Float64}, Int64, Ref{Int32}),
+        ctx.h, 1, views, 1e-15, 1e-3 * ε, view_of(Q0), Rt, k, rho))
+    r = Int(rho[])
+    r == 0 && return DeviceMatrix(ctx, 0)
+    F = svd(Matrix(Rt[:, 1:r]'))                     # N = Q0 (U S W'): the singular values of N (Stuff.jl:14-16)
+    ids = findall(s -> abs(s) > ε, F.S)
+    view_cols(Q0, 1:r) * F.U[:, ids]                 # n x length(ids) panel
+end
+DRE.Stuff.restrict(P::PencilOp{<:Real}, Q::DeviceMatrix) = Q' * (P * Q)
+# restrict(::LowRankUpdate, Q) (util/restrict.jl:5-8) is generic: Q'U -> (U'Q)' and V*Q are the products above
+Base.:*(Qt::Adjoint{Float64,DeviceMatrix}, U::Adjoint{Float64,Matrix{Float64}}) = Qt * Matrix(U)
+
+# ---- concatenate! (LDLt.jl:174-191) works through _hcat above; _dcat is generic (host cores) ----
+# ---- zero / iszero / rank are generic (LDLt.jl:112-121) given size(::DeviceMatrix) ----
 end # module
