@@ -202,17 +202,32 @@ def _run_ours(args):
     api.backend(local)
     be = api.backend()
     warnings.simplefilter("ignore")
-    if dist is not None:
-        # ONE GDRE solve sharded over the ranks: RHS column blocks of every ADI block solve per rank, replicated
-        # factorization, NCCL all-gather of the solved blocks (dre_b200.dist)
+    mode = os.environ.get("DRE_DIST_MODE", "pipeline") if dist is not None else None
+    coll = dist if mode == "columns" else None   # data-path collectives every rank takes part in
+    if mode == "pipeline":
+        # ONE GDRE solve on the GPUs of the box as a two-stage pipeline (dre_b200.dist, "Pipeline mode"): rank 0 runs the
+        # ADI iteration chain and streams every increment of X to rank 1 over NCCL, rank 1 holds X and runs compress!;
+        # further ranks have no lane of this path and idle.  Ranks >= 1 serve until rank 0 ends the job.
+        from dre_b200 import dist as ddist
+
+        ddist.enable_pipeline(device=local)
+        if rank > 0:
+            served = ddist.serve(api)
+            print(f"[bench rank {rank}] {served}", file=sys.stderr, flush=True)
+            dist.barrier()
+            dist.destroy_process_group()
+            return None
+    elif mode == "columns":
+        # DRE_DIST_MODE=columns: RHS column blocks of every ADI block solve per rank, replicated factorization, NCCL
+        # all-gather of the solved blocks (measured to scale negatively: kept for comparison)
         from dre_b200 import dist as ddist
 
         ddist.enable(device=local)
 
     def barrier():
         be.ctx.sync()
-        if dist is not None:
-            dist.barrier()
+        if coll is not None:
+            coll.barrier()
 
     # ---- warm-up: W steps from t0 (also produces the state the timed steps start from) ----
     cw = IterCounter()
@@ -236,12 +251,14 @@ def _run_ours(args):
     wall = time.perf_counter() - t_wall
     barrier()
     st = be.ctx.stats()
-    if dist is not None:
+    if coll is not None:
         import torch
 
         tms = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        coll.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
+    # (pipeline mode: rank 1's work for these K steps lies inside rank 0's timed region -- every ADI solve ends with the
+    #  fetch of the compressed X from rank 1 -- so rank 0's device time IS the maximum over the ranks)
     value = K / (ms * 1e-3)   # one job, strong scaling: all ranks advance the same K time steps together
 
     # ---- instrumented pass (CUDA events around every kernel class) for the roofline ----
@@ -316,11 +333,11 @@ def _run_ours(args):
         except Exception:
             pass
     gathered = None
-    if dist is not None:
-        from dre_b200 import dist as ddist
-
+    if mode == "columns":
         stt = ddist.state()
         gathered = {"allgathers": stt.gathers, "bytes": stt.bytes_gathered}
+    elif mode == "pipeline":
+        gathered = dict(ddist.pipe_state().stats)
 
     # ---- timed region 2 (`e2e`): the same K steps through the public API from HOST buffers ----
     alphaW, LW, DW = XW.destructure()
@@ -329,18 +346,18 @@ def _run_ours(args):
     api.reset_backend()
     api.backend(local)
     be = api.backend()
-    if dist is not None:
-        dist.barrier()
+    if coll is not None:
+        coll.barrier()
     t0 = time.perf_counter()
     sol_e = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(LW_host, DW_host), (tW, tK)), api.Ros1(), dt=DT)
     be.ctx.sync()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()   # the NVML sampler (1 s period) runs across BOTH timed regions
-    if dist is not None:
+    if coll is not None:
         import torch
 
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        coll.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     h2d = (E.nnz + A.nnz) * 16 + 2 * (n + 1) * 8 + (B.size + C.size + LW_host.size) * 8
     d2h = (K + 1) * B.shape[1] * n * 8
@@ -354,6 +371,9 @@ def _run_ours(args):
     if rank == 0 and not args.no_cpu:
         cpu = cpu_sample(E, A, B, C, LW_host, DW_host, ct.iters[0] if ct.iters else 100, args.cpu_iters)
 
+    if mode == "pipeline":
+        gathered = dict(ddist.pipe_state().stats)
+        ddist.pipe_stop()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -368,9 +388,13 @@ def _run_ours(args):
                                f"dt={DT}, t0={T0}, ADI defaults (Projection(2), maxiters=100, compression every 10)",
                    "n": n, "nnz_E": meta["nnz_E"], "nnz_A": meta["nnz_A"],
                    "parallelism": "1 GPU" if world == 1 else
-                   f"one solve on {world} GPUs: RHS column blocks of every ADI block solve sharded over the ranks, "
-                   f"replicated per-shift factorization, NCCL all-gather of the solved blocks; Gram / compression / "
-                   f"shift generation replicated",
+                   (f"one solve on {world} GPUs, column mode: RHS column blocks of every ADI block solve sharded over the "
+                    f"ranks, replicated per-shift factorization, NCCL all-gather of the solved blocks; Gram / compression "
+                    f"/ shift generation replicated" if mode == "columns" else
+                    f"one solve on {world} GPUs as a two-stage pipeline: rank 0 runs the ADI iteration chain (factor, "
+                    f"sweeps, SMW, SpMM, norms, shifts) and streams every increment of X to rank 1 over NCCL, rank 1 "
+                    f"holds X and runs compress!; ranks >= 2 ({max(world - 2, 0)} of them) have no lane of this path and "
+                    f"idle"),
                    "l2_policy": "inputs larger than L2: factor panels + RHS/solution panels + X factor exceed 126 MB",
                    "adi_iters_per_timed_step": ct.iters, "rank_X_and_residual": ct.ranks,
                    "symbolic": info,
@@ -384,7 +408,7 @@ def _run_ours(args):
         "gpu_counters_prefactor": {k: st[k] for k in ("prefactors", "prefactor_hits")},
         "roofline": roofline, "roofline_side_stream": roofline_side, "roofline_named_kernels": named,
         "kernel_classes": classes,
-        "fp64_peak_tflops_measured": fp64_peak, "nccl_allgather": gathered,
+        "fp64_peak_tflops_measured": fp64_peak, "nccl_exchange": gathered,
         "cpu_baseline": cpu, "wall_s_timed_region": wall, "e2e_vs_resident_K_relerr": kerr,
         "compression_lane": dict(api.LANE_STATS) if api.ASYNC_COMPRESS else None,
     }

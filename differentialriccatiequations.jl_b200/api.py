@@ -88,6 +88,20 @@ class _LaneBackend(Backend):
         self.check(self.lib.dre_set_dense_only(self.h, main.n))
 
 
+class _PipeLaneBackend(Backend):
+    """Rank 1 of the multi-GPU pipeline mode (dre_b200.dist): a dense-only context that holds X and runs compress!."""
+
+    def __init__(self, n: int, device):
+        super().__init__(0 if device is None else device)
+        self.n = n
+        self.generation = 1
+        self.check(self.lib.dre_set_dense_only(self.h, n))
+
+
+def _pipe_lane_backend(n: int, device) -> Backend:
+    return _PipeLaneBackend(n, device)
+
+
 def _lane(main: Backend) -> _LaneBackend:
     lane = getattr(main, "_lane_be", None)
     if lane is None or lane.n != main.n or getattr(main, "_lane_gen", None) != main.generation:
@@ -514,6 +528,20 @@ class _PendingCompress:
         X.Ls[:self.nterms] = [Lnew]
         X.Ds[:self.nterms] = [np.asfortranarray(np.diag(lam))]
         self.src = None
+
+
+class _RemotePending:
+    """Multi-GPU pipeline mode: the terms of X have been streamed to rank 1, which holds and compresses the sum;
+    join() fetches the compressed factor (dre_b200.dist.pipe_fetch)."""
+
+    def join(self, X: LDLt):
+        # every term of X was streamed right after the step that produced it, so rank 1's X is the whole sum
+        be = backend()
+        Lnew, lam = _dist.pipe_fetch(be, lambda k: DeviceMatrix.empty(k))
+        _mark_orthonormal(Lnew)
+        X.alphas[:] = [1.0]
+        X.Ls[:] = [Lnew]
+        X.Ds[:] = [np.asfortranarray(np.diag(lam))]
 
 
 def _join_pending(X: LDLt):
@@ -1065,8 +1093,13 @@ def init(prob: GALEProblem, alg: ADI, *, initial_guess=None, initial_residual=No
         abstol = alg.abstol if alg.abstol is not None else reltol * norm(Cm)
     _observe(observer, "observe_gale_step", 0, X, initial_residual, residual_norm)
     increment = initial_residual.zero()
-    return ADICache(prob=prob, alg=alg, abstol=abstol, observer=observer, shifts_oracle=oracle, shifts=[], X=X,
-                    increment=increment, residual=initial_residual, residual_norm=residual_norm)
+    cache = ADICache(prob=prob, alg=alg, abstol=abstol, observer=observer, shifts_oracle=oracle, shifts=[], X=X,
+                     increment=increment, residual=initial_residual, residual_norm=residual_norm)
+    cache._piped = bool(_dist.pipeline_active() and alg.compression and _fused_inner(alg))
+    if cache._piped:
+        _join_pending(X)
+        _dist.pipe_begin(backend(), X)   # rank 1 holds the terms of X from now on (marked on cache.X at the first step)
+    return cache
 
 
 def isdone(cache: ADICache) -> bool:
@@ -1081,6 +1114,12 @@ def isdone(cache: ADICache) -> bool:
 
 def compress_cache_(cache: ADICache):
     """adi.jl:143-147."""
+    if getattr(cache, "_piped", False):
+        # pipeline mode: every term of X has already been streamed to rank 1; it compresses there while this
+        # rank's iteration carries on (nothing reads X before the next compression or the end of the solve)
+        _dist.pipe_compress()
+        cache.last_compression = 0
+        return
     compress_(cache.X)
     cache.last_compression = 0
 
@@ -1091,6 +1130,20 @@ def _start_async_compress(cache: ADICache):
     _join_pending(X)
     X._pending = _PendingCompress(X)
     cache.last_compression = 0
+
+
+def _pipe_stream_increment(cache: ADICache):
+    """Pipeline mode (dre_b200.dist): the new terms of X go to rank 1 as soon as they exist (asynchronous NCCL send
+    queued behind the solve on the library's stream)."""
+    if not getattr(cache, "_piped", False):
+        return
+    if not isinstance(getattr(cache.X, "_pending", None), _RemotePending):
+        cache.X._pending = _RemotePending()      # (X + increment returned a fresh object: X was zero)
+    be = backend()
+    inc = cache.increment
+    for a, L, D in zip(inc.alphas, inc.Ls, inc.Ds):
+        if L.ncols:
+            _dist.pipe_send_term(be, a, L, D)
 
 
 def _fused_inner(alg: ADI) -> bool:
@@ -1199,6 +1252,7 @@ def perform_single_step_(cache: ADICache, mu: float):
         spmm("E", V, -2.0 * mu, R, 1.0)
     cache.increment = (-2.0 * mu * alpha) * LDLt([1.0], [V], [T])
     cache.X = cache.X + cache.increment
+    _pipe_stream_increment(cache)
     cache.last_compression += 1
     cache.shifts_oracle.update(cache.X, R, V)
 
@@ -1242,6 +1296,7 @@ def perform_double_step_(cache: ADICache, mu: complex):
         spmm("E", V1, -2.0 * math.sqrt(2.0) * mu.real, R, 1.0)
     cache.increment = (-2.0 * mu.real * alpha) * (LDLt([1.0], [V1], [T]) + LDLt([1.0], [V2], [T]))
     cache.X = cache.X + cache.increment
+    _pipe_stream_increment(cache)
     cache.last_compression += 2
     cache.shifts_oracle.update(cache.X, R, V1, V2)
 

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdre_b200.so")
-SOURCES = ["symbolic.cpp", "dense_kernels.cu", "sparse_kernels.cu", "context.cu"]
+SOURCES = ["symbolic.cpp", "dense_kernels.cu", "sparse_kernels.cu", "eigensolver.cu", "context.cu"]
 HEADERS = ["symbolic.h", "kernels.h", "common.cuh", "schedule.h", os.path.join("..", "..", "include", "dre_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
     if force or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + [
-            "-gencode", "arch=compute_100a,code=sm_100a", "-lcusolver", "-lcudart", "-lpthread",
+            "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lpthread",
             "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
         subprocess.run(cmd, check=True)
     return LIB

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "dre_symbolic_export", "dre_create", "dre_destroy", "dre_sync", "dre_set_pencil", "dre_get_symbolic_info",
     "dre_mat_create", "dre_mat_free", "dre_mat_upload", "dre_mat_download", "dre_mat_copy", "dre_mat_axpby",
     "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_prefactor", "dre_shift_solve", "dre_adi_step", "dre_adi_solve", "dre_mat_devptr", "dre_get_stream", "dre_set_dense_only", "dre_mat_wrap",
-    "dre_ldlt_norm", "dre_ldlt_norm_begin", "dre_ldlt_norm_end", "dre_ldlt_compress", "dre_hint_orthonormal", "dre_rrqr", "dre_debug_export", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
+    "dre_ldlt_norm", "dre_ldlt_norm_begin", "dre_ldlt_norm_end", "dre_ldlt_compress", "dre_hint_orthonormal", "dre_rrqr", "dre_debug_export", "dre_debug_eigh", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
     "dre_stats_get",
 ]
 
@@ -112,6 +112,7 @@ def load():
     lib.dre_hint_orthonormal.argtypes = [p, View]
     lib.dre_rrqr.argtypes = [p, i32, C.POINTER(View), dbl, dbl, View, pdbl, i64, C.POINTER(i32)]
     lib.dre_debug_export.argtypes = [p, C.c_char_p, p, i64, pi64]
+    lib.dre_debug_eigh.argtypes = [p, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.dre_timer_start.argtypes = [p]
     lib.dre_timer_stop.argtypes = [p, pdbl]
     lib.dre_stats_reset.argtypes = [p, i32]
@@ -232,6 +233,15 @@ class Context:
         self.check(self.lib.dre_debug_export(self.h, what.encode(), buf.ctypes.data_as(C.c_void_p), ln.value,
                                              C.byref(ln)))
         return buf
+
+    def debug_eigh(self, A):
+        """The library's own symmetric eigensolver on a host matrix: (ascending eigenvalues, eigenvector columns)."""
+        A = np.asfortranarray(np.asarray(A, dtype=np.float64))
+        k = A.shape[0]
+        w = np.empty(k)
+        V = np.empty((k, k), order="F")
+        self.check(self.lib.dre_debug_eigh(self.h, k, _dptr(A), _dptr(w), _dptr(V)))
+        return w, V
 
     def timer_start(self):
         self.check(self.lib.dre_timer_start(self.h))

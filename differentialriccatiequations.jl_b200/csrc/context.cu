@@ -1,9 +1,12 @@
 // C ABI of libdre_b200.so (include/dre_b200.h): context, device memory, orchestration of the
-// hand-written kernels.  Host-side C++17; the only third-party device library used is cuSOLVER's
-// dense symmetric eigensolver for the small (rho x rho) projected core inside compress!
-// (the reference calls LAPACK syevr for the same matrix, src/LDLt.jl:214).
+// hand-written kernels.  Host-side C++17; no third-party device library: the small (rho x rho) projected core
+// inside compress! (LAPACK syevr in the reference, src/LDLt.jl:214) goes through the in-tree eigensolver of
+// eigensolver.cu.  (Only the host-side SIMT emulator of the CPU test tier, which cannot run a cooperative
+// launch, substitutes its own Jacobi routine behind the cuSOLVER-shaped stub of tests/simt/stub/.)
 #include <cuda_runtime.h>
+#ifdef DRE_SIMT_EMU
 #include <cusolverDn.h>
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -160,7 +163,9 @@ struct dre_context {
     int sm_count = 148;
     cudaStream_t st = nullptr;
     std::string err;
+#ifdef DRE_SIMT_EMU
     cusolverDnHandle_t cusolver = nullptr;
+#endif
 
     // pencil
     bool has_pencil = false;
@@ -236,7 +241,8 @@ struct dre_context {
 
     // dense workspaces
     DBuf<double> gram_partial, gbuf, gbuf2, cbuf, wsel, wsel2, small, stage, qws, pws, qtmp, rt, rt2, tmp_panel, evals, cnorm;
-    DBuf<double> syevd_work;
+    DBuf<double> syevd_work;            // eigensolver workspace (d, e, tau, reflectors, Q)
+    DBuf<unsigned char> eig_rots;       // plane rotations of the QL iteration + rank table
     DBuf<int32_t> ibuf;
     double* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
@@ -256,7 +262,7 @@ void for_each_workspace(dre_context* c, F f) {
     f(c->tbuf); f(c->Wbuf); f(c->Ybuf); f(c->norm_partial); f(c->norm_g); f(c->norm_small);
     f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
     f(c->wsel); f(c->wsel2); f(c->small); f(c->stage); f(c->qws); f(c->pws); f(c->qtmp); f(c->rt); f(c->rt2);
-    f(c->tmp_panel); f(c->evals); f(c->cnorm); f(c->syevd_work); f(c->ibuf);
+    f(c->tmp_panel); f(c->evals); f(c->cnorm); f(c->syevd_work); f(c->eig_rots); f(c->ibuf);
 }
 
 int fail(dre_context* c, int code, const std::string& msg) {
@@ -680,19 +686,20 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
         if (rho0 > 0) {
             CU(c->cbuf.ensure((size_t)PBIG * rho0));
             for (int pass = 0; pass < npass; ++pass) {
-                // C' = P' Q (pbig x rho0): coefficients, accumulated into the RT rows of this block
-                rc = gram_dev(c, Pbig, PBIG, pbig, s.Q, s.ldq, rho0, n, nullptr, c->cbuf.p, rho0,
-                              s.RT + (int64_t)(rt_row0 + c0) * s.ldrt, s.ldrt);
-                if (rc) return rc;
                 if (pass == 1 && have_rem) {
                     // The first pass already left every column of the block below the drop threshold: the block adds
-                    // no direction, so the second pass only has to refine the coefficients (its Gram product above);
-                    // the remainder itself is never looked at again and its update is skipped.
+                    // no direction and its remainder is discarded as a whole.  A second pass would only move the
+                    // part of that remainder that lies in span(Q) -- at most drop * scale per column, i.e. no more
+                    // than what is being discarded anyway -- into the coefficients, so it is skipped altogether.
                     double m2 = 0.0;
                     for (int j = 0; j < pbig; ++j) m2 = std::max(m2, rem2[j]);
                     const double drop0 = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
                     if (m2 < drop0 * drop0) { g_rr.coef_only_passes++; break; }
                 }
+                // C' = P' Q (pbig x rho0): coefficients, accumulated into the RT rows of this block
+                rc = gram_dev(c, Pbig, PBIG, pbig, s.Q, s.ldq, rho0, n, nullptr, c->cbuf.p, rho0,
+                              s.RT + (int64_t)(rt_row0 + c0) * s.ldrt, s.ldrt);
+                if (rc) return rc;
                 rc = tall_gemm(c, -1.0, s.Q, s.ldq, rho0, c->cbuf.p, rho0, 1, 1.0, Pbig, PBIG, pbig, n);
                 if (rc) return rc;
                 if ((rc = remainder_norms())) return rc;
@@ -934,7 +941,6 @@ int32_t dre_symbolic_export(const dre_symbolic* s, const char* what, void* buf, 
     return fail(nullptr, DRE_ERR_ARG, "dre_symbolic_export: unknown array name " + w);
 }
 
-static void prime_eigensolver(dre_context* c);
 
 int32_t dre_create(int32_t device, dre_context** out) {
     if (!out) return fail(nullptr, DRE_ERR_ARG, "null argument");
@@ -971,8 +977,10 @@ int32_t dre_create(int32_t device, dre_context** out) {
     cudaEventCreate(&c->ev1);
     cudaEventCreate(&c->tev0);
     cudaEventCreate(&c->tev1);
+#ifdef DRE_SIMT_EMU
     if (cusolverDnCreate(&c->cusolver) != CUSOLVER_STATUS_SUCCESS) return bail("cusolverDnCreate failed");
     cusolverDnSetStream(c->cusolver, c->st);
+#endif
     e = cudaMalloc((void**)&c->d_errflag, sizeof(int32_t));
     if (e != cudaSuccess) return bail("cudaMalloc failed");
     cudaMemset(c->d_errflag, 0, sizeof(int32_t));
@@ -981,7 +989,6 @@ int32_t dre_create(int32_t device, dre_context** out) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    prime_eigensolver(c);
     *out = c;
     return DRE_OK;
 }
@@ -1004,48 +1011,11 @@ static void release_pencil(dre_context* c) {
     c->has_pencil = false;
 }
 
-// cuSOLVER loads its kernels lazily, per size class, at the first call that needs them (CUDA lazy module loading):
-// 1.5 - 2.3 s stalls were measured inside individual compress! calls of the first time steps whenever the projected
-// core crossed a size threshold (tools/step_times.py).  One throw-away Dsyevd per size class at the first context
-// of the process moves that cost to start-up (DRE_NO_PRIME=1 skips it).
-static void prime_eigensolver(dre_context* c) {
-    static bool done = false;
-    if (done || getenv("DRE_NO_PRIME")) return;
-    done = true;
-    const int sizes[] = {32, 128, 256, 512, 1024};
-    const int nmax = 1024;
-    double* A = nullptr;
-    double* w = nullptr;
-    if (cudaMalloc((void**)&A, sizeof(double) * nmax * nmax) != cudaSuccess) { cudaGetLastError(); return; }
-    if (cudaMalloc((void**)&w, sizeof(double) * nmax) != cudaSuccess) { cudaGetLastError(); cudaFree(A); return; }
-    std::vector<double> h((size_t)nmax * nmax);
-    for (int k : sizes) {
-        for (int j = 0; j < k; ++j)
-            for (int i = 0; i < k; ++i) h[(size_t)i + (size_t)j * k] = (i == j) ? 1.0 + j : 1.0 / (1.0 + i + j);
-        cudaMemcpyAsync(A, h.data(), sizeof(double) * k * k, cudaMemcpyHostToDevice, c->st);
-        int lwork = 0;
-        if (cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, A, k, w,
-                                        &lwork) != CUSOLVER_STATUS_SUCCESS)
-            break;
-        double* work = nullptr;
-        int* info = nullptr;
-        if (cudaMalloc((void**)&work, sizeof(double) * (lwork + 8)) != cudaSuccess) { cudaGetLastError(); break; }
-        if (cudaMalloc((void**)&info, sizeof(int)) != cudaSuccess) { cudaGetLastError(); cudaFree(work); break; }
-        cusolverDnDsyevd(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, A, k, w, work, lwork, info);
-        cudaStreamSynchronize(c->st);
-        cudaFree(work);
-        cudaFree(info);
-    }
-    cudaFree(A);
-    cudaFree(w);
-    cudaGetLastError();
-}
-
 int32_t dre_destroy(dre_context* c) {
     if (g_rr_stats && c)
         fprintf(stderr,
                 "[dre rr totals] blocks %ld rounds %ld productive %ld skipped sub-panels %ld rest projections %ld "
-                "coefficient-only second passes %ld round syncs %ld kernel launches (context) %lld\n",
+                "skipped second passes %ld round syncs %ld kernel launches (context) %lld\n",
                 g_rr.blocks, g_rr.rounds, g_rr.productive, g_rr.skipped, g_rr.rest_projections, g_rr.coef_only_passes,
                 g_rr.syncs,
                 (long long)c->stats.kernel_launches);
@@ -1061,7 +1031,9 @@ int32_t dre_destroy(dre_context* c) {
     if (c->norm_done) cudaEventDestroy(c->norm_done);
     if (c->norm_st) cudaStreamDestroy(c->norm_st);
     if (c->d_errflag) cudaFree(c->d_errflag);
+#ifdef DRE_SIMT_EMU
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
+#endif
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->tev0) cudaEventDestroy(c->tev0);
@@ -1551,18 +1523,34 @@ int32_t dre_ldlt_norm_end(dre_context* c, double* out) {
     return flag != 0 ? check_errflag(c) : DRE_OK;
 }
 
+// eigen-decomposition of the symmetric k x k matrix S (device, ld k): on return row j of S (row-major view) is the
+// eigenvector of the j-th smallest eigenvalue, d_evals[j]
 static int eig_sym_dev(dre_context* c, double* S, int k, double* d_evals) {
-    HostTrace tr("eig_sym_dev (syevd)", c->st);
+    HostTrace tr("eig_sym_dev", c->st);
+#ifdef DRE_SIMT_EMU
     int lwork = 0;
     if (cusolverDnDsyevd_bufferSize(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, S, k, d_evals,
                                     &lwork) != CUSOLVER_STATUS_SUCCESS)
-        return fail(c, DRE_ERR_LIB, "cusolverDnDsyevd_bufferSize failed");
+        return fail(c, DRE_ERR_LIB, "emulator eigensolver: bufferSize failed");
     CU(c->syevd_work.ensure((size_t)lwork + 8));
     CU(c->ibuf.ensure(8));
     if (cusolverDnDsyevd(c->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, k, S, k, d_evals,
                          c->syevd_work.p, lwork, c->ibuf.p + 4) != CUSOLVER_STATUS_SUCCESS)
-        return fail(c, DRE_ERR_LIB, "cusolverDnDsyevd failed");
+        return fail(c, DRE_ERR_LIB, "emulator eigensolver failed");
     return DRE_OK;
+#else
+    CU(c->syevd_work.ensure(eig_sym_work_doubles(k)));
+    std::vector<double> hev((size_t)k);
+    auto grow = [](void* ctx, size_t bytes) -> void* {
+        dre_context* cc = (dre_context*)ctx;
+        return cc->eig_rots.ensure(bytes) == cudaSuccess ? (void*)cc->eig_rots.p : nullptr;
+    };
+    const int rc = eig_sym(S, k, d_evals, hev.data(), c->syevd_work.p, grow, c, c->sm_count, c->st,
+                           &c->stats.kernel_launches);
+    if (rc == 2) return fail(c, DRE_ERR_NUMERIC, "symmetric eigensolver: QL iteration did not converge");
+    if (rc != 0) return fail(c, DRE_ERR_CUDA, std::string("symmetric eigensolver: ") + cudaGetErrorString(cudaGetLastError()));
+    return DRE_OK;
+#endif
 }
 
 static int rr_setup(dre_context* c, RRState& s, int ktot, double drop_rel, double drop_abs) {
@@ -1788,6 +1776,21 @@ int32_t dre_debug_export(dre_context* c, const char* what, void* buf, int64_t ca
         CU(cudaMemcpy(buf, src, std::min<size_t>(bytes, (size_t)cap_bytes), cudaMemcpyDeviceToHost));
     }
     return check_errflag(c);
+}
+
+int32_t dre_debug_eigh(dre_context* c, int32_t k, const double* A, double* evals, double* evecs) {
+    if (!c || !A || !evals || !evecs || k <= 0) return fail(c, DRE_ERR_ARG, "dre_debug_eigh: bad argument");
+    cudaSetDevice(c->device);
+    CU(c->gbuf.ensure((size_t)k * k));
+    CU(c->evals.ensure((size_t)k));
+    CU(cudaMemcpyAsync(c->gbuf.p, A, (size_t)k * k * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    int rc = eig_sym_dev(c, c->gbuf.p, k, c->evals.p);
+    if (rc) return rc;
+    // row j of the row-major result = eigenvector j = column j of the column-major output
+    CU(cudaMemcpyAsync(evecs, c->gbuf.p, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(evals, c->evals.p, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return DRE_OK;
 }
 
 int32_t dre_timer_start(dre_context* c) {

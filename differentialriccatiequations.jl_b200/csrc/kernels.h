@@ -61,6 +61,15 @@ void launch_norm_diag(const double* G, int64_t ldg, int r, const double* t, doub
 void launch_gather_rows(double* Wt, int64_t ldw, const double* V, int64_t ldv, const int32_t* ids, int nsel,
                         int len, cudaStream_t st, int64_t* launches);
 
+// ---------------- small symmetric eigenproblem (eigensolver.cu) ----------------
+// S (k x k symmetric, device, ld k) is overwritten: row j of the row-major view = eigenvector of the j-th smallest
+// eigenvalue; h_evals (host) and d_evals (device) receive the ascending eigenvalues.  work: eig_sym_work_doubles(k)
+// doubles of device scratch; grow_rots(ctx, bytes) returns a device buffer of at least `bytes` (rotations of the
+// host QL iteration).  Synchronises st.  Returns 0 ok, 1 CUDA error, 2 no convergence.
+size_t eig_sym_work_doubles(int k);
+int eig_sym(double* S, int k, double* d_evals, double* h_evals, double* work, void* (*grow_rots)(void*, size_t),
+            void* grow_ctx, int sm_count, cudaStream_t st, int64_t* launches);
+
 // ---------------- sparse: CSR SpMM ----------------
 extern int spmm_variant;   // 1 = k_spmm, 2 = k_spmm2 (indices broadcast by shuffles, two nonzeros in flight)
 // Y[row][c] = beta*Y[row][c] + alpha * sum_j val[row,j] * X[col_j][c]      (row-major panels)

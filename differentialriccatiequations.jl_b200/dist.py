@@ -224,3 +224,317 @@ def assert_same_int(v: int, what: str):
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=st.group)
     if int(t[0].item()) != -int(t[1].item()):
         raise RuntimeError(f"ranks disagree on {what}: max {int(t[0])} min {-int(t[1])}")
+
+
+# =============================================================================================
+# Pipeline mode (default for world_size > 1): the two lanes of the ADI loop on two GPUs
+# =============================================================================================
+# What a time step costs on ONE GPU (n = 79 841, profiles/r02_results.md): the latency-bound ADI iteration chain
+# (factor -> sweeps -> SMW -> SpMM -> residual norm, ~2.6 ms x 100) and the column compression compress!(X) of
+# adi.jl:143-147 (rank-revealing Gram-Schmidt rounds + fat DMMA passes, ~35 ms x 12) are about the same size, and
+# nothing in the iteration reads X: a step only appends the term (-2 mu alpha) V T V' (adi.jl:170-176).  Sharding
+# the RHS columns of the solves over the ranks ("columns" mode above, DRE_DIST_MODE=columns) therefore divides the
+# smaller half of the step and pays an all-gather per iteration; it was measured to scale negatively.  Pipeline mode
+# gives each lane its own GPU instead:
+#   rank 0  runs the reference's drivers unchanged and streams every increment (V panel + core) to rank 1 right
+#           after the step that produced it (NCCL send on the library's stream, asynchronous);
+#   rank 1  holds X: appends the terms, runs compress!(X) whenever rank 0's loop reaches a compression point
+#           (adi.jl:112-114) and returns the compressed factor when X is read (end of the ADI solve);
+#   ranks >= 2 have no lane of this path to run and idle until the job ends.
+# Control messages travel over a gloo group (CPU tensors), panels over NCCL.  Same arithmetic on the same operands
+# in the same order as the single-GPU path: results are identical.
+_PIPE = None
+CMD_STOP, CMD_BEGIN, CMD_TERM, CMD_COMPRESS, CMD_FETCH = 0, 1, 2, 3, 4
+_HDR = 8
+
+
+class _Pipe:
+    def __init__(self, rank, world, device, ctl, data_backend):
+        self.rank, self.world, self.device, self.ctl, self.data_backend = rank, world, device, ctl, data_backend
+        self.token = 0            # identifies the compressed factor rank 1 currently holds as its first term
+        self.sends = []           # outstanding isend works (and the panels they read)
+        self.stats = {"terms_sent": 0, "bytes_sent": 0, "compress_cmds": 0, "fetches": 0, "fetch_wait_s": 0.0}
+
+
+def enable_pipeline(device=None):
+    """All ranks call this once after torch.distributed is initialised (NCCL for GPUs, gloo for the CPU tests)."""
+    global _PIPE
+    import datetime
+
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        raise RuntimeError("dre_b200.dist.enable_pipeline: torch.distributed is not initialised")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    data_backend = dist.get_backend()
+    ctl = None
+    if data_backend != "gloo":
+        ctl = dist.new_group(ranks=list(range(world)), backend="gloo", timeout=datetime.timedelta(seconds=900))
+    _PIPE = _Pipe(rank, world, device, ctl, data_backend)
+    return _PIPE
+
+
+def pipeline_active() -> bool:
+    return _PIPE is not None and _PIPE.world > 1 and _PIPE.rank == 0
+
+
+def pipe_state():
+    return _PIPE
+
+
+def _dev_str():
+    return "cpu" if _PIPE.data_backend == "gloo" else f"cuda:{_PIPE.device if _PIPE.device is not None else 0}"
+
+
+def _send_hdr(dst, vals):
+    import torch
+    import torch.distributed as dist
+
+    h = torch.zeros(_HDR, dtype=torch.float64)
+    h[:len(vals)] = torch.tensor([float(v) for v in vals], dtype=torch.float64)
+    dist.send(h, dst=dst, group=_PIPE.ctl)
+
+
+def _recv_hdr(src):
+    import torch
+    import torch.distributed as dist
+
+    h = torch.zeros(_HDR, dtype=torch.float64)
+    dist.recv(h, src=src, group=_PIPE.ctl)
+    return h.tolist()
+
+
+def _panel_io(be, M):
+    """(tensor aliasing the panel, context manager that makes torch's current stream the library's stream)."""
+    import contextlib
+
+    import torch
+
+    if _PIPE.data_backend == "gloo":        # CPU tests: the emulator's "device" memory is host memory
+        ptr, ld = C.c_void_p(), C.c_int64()
+        be.check(be.lib.dre_mat_devptr(be.h, M.view, C.byref(ptr), C.byref(ld)))
+        be.check(be.lib.dre_sync(be.h))
+        buf = (C.c_double * (be.n * ld.value)).from_address(ptr.value)
+        full = torch.from_numpy(np.frombuffer(buf, dtype=np.float64).reshape(be.n, ld.value))
+        return full[:, :M.ncols], contextlib.nullcontext()
+    ptr, ld = C.c_void_p(), C.c_int64()
+    be.check(be.lib.dre_mat_devptr(be.h, M.view, C.byref(ptr), C.byref(ld)))
+    dev = _PIPE.device if _PIPE.device is not None else 0
+    t = torch.as_tensor(_CudaArray(ptr.value, be.n, M.ncols, ld.value), device=f"cuda:{dev}")
+    sp = C.c_void_p()
+    be.check(be.lib.dre_get_stream(be.h, C.byref(sp)))
+    return t, torch.cuda.stream(torch.cuda.ExternalStream(sp.value, device=f"cuda:{dev}"))
+
+
+def _send_panel(be, M, dst):
+    """Asynchronous send of an n x k panel, ordered behind the kernels that wrote it; the panel is kept alive
+    until the send has completed (reaped at the next compression point / fetch)."""
+    import torch
+    import torch.distributed as dist
+
+    t, on_stream = _panel_io(be, M)
+    with on_stream:
+        if _PIPE.data_backend == "gloo":
+            t = t.contiguous()
+        elif not t.is_contiguous():
+            # a column view of a wider panel / a padded leading dimension: NCCL wants one dense buffer.  Staged through
+            # a small ring of persistent buffers (a fresh 150 MB torch tensor per ADI step would push the caching
+            # allocator into cudaMalloc / cudaFree, i.e. device synchronisations on the ADI chain).
+            ring = _PIPE.__dict__.setdefault("ring", {})
+            slots = ring.setdefault(tuple(t.shape), [])
+            buf = None
+            for sl in slots:
+                if sl[1] is None or sl[1].is_completed():
+                    buf = sl
+                    break
+            if buf is None:
+                buf = [torch.empty(t.shape, dtype=t.dtype, device=t.device), None]
+                slots.append(buf)
+            buf[0].copy_(t)
+            t = buf[0]
+            w = dist.isend(t, dst=dst)
+            buf[1] = w
+            _PIPE.sends.append((w, M, t))
+            _PIPE.stats["bytes_sent"] += t.numel() * 8
+            return
+        w = dist.isend(t, dst=dst)
+    _PIPE.sends.append((w, M, t))
+    _PIPE.stats["bytes_sent"] += t.numel() * 8
+
+
+def _reap_sends(block=False):
+    keep = []
+    for w, M, t in _PIPE.sends:
+        if block:
+            w.wait()
+        elif not w.is_completed():
+            keep.append((w, M, t))
+    _PIPE.sends = keep
+
+
+def _recv_panel(be, M, src):
+    import torch
+    import torch.distributed as dist
+
+    t, on_stream = _panel_io(be, M)
+    with on_stream:
+        if t.is_contiguous():
+            dist.recv(t, src=src)
+        else:
+            tmp = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+            dist.recv(tmp, src=src)
+            t.copy_(tmp)
+        if _PIPE.data_backend != "gloo":
+            torch.cuda.current_stream().synchronize()
+
+
+def _send_small(arr, dst):
+    """Small float64 array (cores, eigenvalues) over the control group."""
+    import torch
+    import torch.distributed as dist
+
+    a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64)).ravel()
+    if a.size:
+        dist.send(torch.from_numpy(a.copy()), dst=dst, group=_PIPE.ctl)
+
+
+def _recv_small(count, src):
+    import torch
+    import torch.distributed as dist
+
+    out = torch.zeros(int(count), dtype=torch.float64)
+    if count:
+        dist.recv(out, src=src, group=_PIPE.ctl)
+    return out.numpy()
+
+
+# ---- rank 0 side -------------------------------------------------------------------------------------------------
+def pipe_begin(be, X0):
+    """Start of an ADI solve (adi.jl:29-69): rank 1's X becomes the initial guess.  If the initial guess is the
+    very factor rank 1 returned last (Ros1/Ros2 pass the previous X, lowrank_ros1.jl:48-49) nothing is transferred."""
+    p = _PIPE
+    same = False
+    if len(X0.Ls) == 1 and p.token != 0 and getattr(X0.Ls[0], "_pipe_token", None) == p.token and X0.alphas[0] == 1.0:
+        D0 = np.asarray(X0.Ds[0])
+        lam = getattr(X0.Ls[0], "_pipe_lam", None)
+        same = (lam is not None and D0.shape == (lam.size, lam.size) and np.array_equal(np.diag(D0), lam)
+                and np.count_nonzero(D0 - np.diag(np.diag(D0))) == 0)
+    _send_hdr(1, [CMD_BEGIN, be.n, 1.0 if same else 0.0])
+    if not same:
+        p.token = 0
+        for a, L, D in zip(X0.alphas, X0.Ls, X0.Ds):
+            if L.ncols:
+                pipe_send_term(be, a, L, D)
+
+
+def pipe_send_term(be, alpha, L, D):
+    D = np.asfortranarray(np.asarray(D, dtype=np.float64))
+    diag = np.count_nonzero(D - np.diag(np.diag(D))) == 0
+    _send_hdr(1, [CMD_TERM, L.ncols, float(alpha), 1.0 if diag else 0.0])
+    _send_small(np.diag(D) if diag else D, 1)
+    _send_panel(be, L, 1)
+    _PIPE.stats["terms_sent"] += 1
+    _reap_sends()
+
+
+def pipe_compress():
+    _send_hdr(1, [CMD_COMPRESS])
+    _PIPE.stats["compress_cmds"] += 1
+
+
+def pipe_fetch(be, make_panel):
+    """compress!(X) on rank 1 (if more than one term is pending) and its result: (DeviceMatrix, eigenvalues)."""
+    import time
+
+    p = _PIPE
+    _send_hdr(1, [CMD_FETCH])
+    t0 = time.perf_counter()
+    h = _recv_hdr(1)
+    k2, token = int(h[0]), int(h[1])
+    lam = _recv_small(k2, 1)
+    L = make_panel(k2)
+    if k2:
+        _recv_panel(be, L, 1)
+    p.stats["fetch_wait_s"] += time.perf_counter() - t0
+    p.stats["fetches"] += 1
+    _reap_sends(block=True)
+    p.token = token
+    L._pipe_token = token
+    L._pipe_lam = np.array(lam, copy=True)
+    return L, lam
+
+
+def pipe_stop():
+    """Rank 0 releases the other ranks (end of the job)."""
+    if _PIPE is None or _PIPE.world < 2 or _PIPE.rank != 0:
+        return
+    _reap_sends(block=True)
+    for r in range(1, _PIPE.world):
+        _send_hdr(r, [CMD_STOP])
+
+
+# ---- rank 1 (and the idle ranks) ---------------------------------------------------------------------------------
+def serve(api):
+    """Rank >= 1: the compression lane (rank 1) or an idle wait for the end of the job (ranks >= 2)."""
+    p = _PIPE
+    if p.rank >= 2:
+        while int(_recv_hdr(0)[0]) != CMD_STOP:
+            pass
+        return {"role": "idle"}
+    be = None
+    terms = []      # (alpha, DeviceMatrix, core)
+    served = {"role": "compress", "terms": 0, "compressions": 0, "fetches": 0, "busy_s": 0.0}
+    import time
+
+    def compress_now():
+        nonlocal terms
+        live = [(a, L, np.asfortranarray(D)) for a, L, D in terms if L.ncols]
+        if len(live) == 1 and api._is_orthonormal(live[0][1]):
+            return
+        if not live:
+            return
+        t0 = time.perf_counter()
+        Lnew, lam = api._compress_call(be, live)
+        be.ctx.sync()
+        served["busy_s"] += time.perf_counter() - t0
+        served["compressions"] += 1
+        terms = [(1.0, Lnew, np.asfortranarray(np.diag(lam)))]
+
+    while True:
+        h = _recv_hdr(0)
+        cmd = int(h[0])
+        if cmd == CMD_STOP:
+            break
+        if cmd == CMD_BEGIN:
+            n = int(h[1])
+            if be is None or be.n != n:
+                be = api._pipe_lane_backend(n, p.device)
+                terms = []
+            if h[2] == 0.0:
+                terms = []
+        elif cmd == CMD_TERM:
+            k, alpha, diag = int(h[1]), h[2], h[3] != 0.0
+            core = _recv_small(k if diag else k * k, 0)
+            D = np.diag(core) if diag else core.reshape(k, k, order="F")
+            L = api.DeviceMatrix(api._Panel(be, k), 0, k)
+            _recv_panel(be, L, 0)
+            terms.append((alpha, L, np.asfortranarray(D)))
+            served["terms"] += 1
+        elif cmd == CMD_COMPRESS:
+            compress_now()
+        elif cmd == CMD_FETCH:
+            compress_now()
+            p.token += 1
+            if terms:
+                _, L, D = terms[0]
+                lam = np.diag(D).copy()
+            else:
+                L, lam = None, np.zeros(0)
+            k2 = 0 if L is None else L.ncols
+            _send_hdr(0, [k2, p.token])
+            _send_small(lam, 0)
+            if k2:
+                _send_panel(be, L, 0)
+                _reap_sends(block=True)
+            served["fetches"] += 1
+    return served

@@ -187,6 +187,11 @@ DRE_API int32_t dre_rrqr(dre_context* ctx, int32_t nviews, const dre_view* views
  * interleaved complex (complex shift).  Copies at most cap_bytes and returns the full size in *len_bytes. */
 DRE_API int32_t dre_debug_export(dre_context* ctx, const char* what, void* buf, int64_t cap_bytes, int64_t* len_bytes);
 
+/* The library's own symmetric eigensolver (Householder tridiagonalisation in one cooperative launch, implicit QL
+ * on the host, rotations applied on the device; replaces LAPACK syevr of src/LDLt.jl:214) on a k x k symmetric
+ * host matrix A (column-major): evals ascending, column j of evecs (column-major, k x k) = eigenvector j. */
+DRE_API int32_t dre_debug_eigh(dre_context* ctx, int32_t k, const double* A, double* evals, double* evecs);
+
 /* ---- timing / counters for bench.py ---- */
 typedef struct {
     int64_t kernel_launches;    /* launches of this library's own kernels since the last reset */

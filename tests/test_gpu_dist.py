@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _run(rank, world, port, n, nsteps, q):
+def _run(rank, world, port, n, nsteps, q, mode="columns"):
     import scipy.sparse.linalg as spla
     import torch
     import torch.distributed as tdist
@@ -38,7 +38,15 @@ def _run(rank, world, port, n, nsteps, q):
         tdist.init_process_group("nccl", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120),
                                  device_id=torch.device(f"cuda:{rank}"))
     api.backend(device=rank)
-    if world > 1:
+    if world > 1 and mode == "pipeline":
+        ddist.enable_pipeline(device=rank)
+        if rank > 0:
+            served = ddist.serve(api)
+            q.put((rank, served))
+            tdist.barrier()
+            tdist.destroy_process_group()
+            return
+    elif world > 1:
         ddist.enable(device=rank)
     E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
     L0 = spla.splu(E.tocsc()).solve(C.T)
@@ -52,6 +60,13 @@ def _run(rank, world, port, n, nsteps, q):
         warnings.simplefilter("ignore")
         sol = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(L0, 0.01 * np.eye(C.shape[0])),
                                         (4500.0, 4500.0 - 100.0 * nsteps)), api.Ros1(), dt=-100.0, observer=Obs())
+    if world > 1 and mode == "pipeline":
+        stats = dict(ddist.pipe_state().stats)
+        ddist.pipe_stop()
+        q.put((rank, [np.asarray(K) for K in sol.K], iters, stats))
+        tdist.barrier()
+        tdist.destroy_process_group()
+        return
     gathered = ddist.state().bytes_gathered if world > 1 else 0
     q.put((rank, [np.asarray(K) for K in sol.K], iters, gathered))
     if world > 1:
@@ -59,13 +74,13 @@ def _run(rank, world, port, n, nsteps, q):
         tdist.destroy_process_group()
 
 
-def _spawn(world, n, nsteps):
+def _spawn(world, n, nsteps, mode="columns"):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_run, args=(r, world, port, n, nsteps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_run, args=(r, world, port, n, nsteps, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -90,3 +105,22 @@ def test_sharded_ros1_matches_single_gpu():
             assert np.linalg.norm(Ks - K1) <= 1e-10 * np.linalg.norm(K1)
     for Ka, Kb in zip(sharded[0][1], sharded[1][1]):
         assert np.array_equal(Ka, Kb)  # ranks stay bit-identical
+
+
+def test_pipeline_mode_matches_single_gpu():
+    """Pipeline mode (dre_b200.dist, default for world_size > 1): rank 0 runs the ADI iteration and streams every
+    increment of X over NCCL to rank 1, which holds X and runs compress! there.  Same K(t), same iteration counts."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, nsteps = 5177, 2
+    single = _spawn(1, n, nsteps)[0]
+    piped = _spawn(2, n, nsteps, mode="pipeline")
+    r0 = piped[0]
+    assert r0[2] == single[2]
+    for Kp, K1 in zip(r0[1], single[1]):
+        assert np.linalg.norm(Kp - K1) <= 1e-10 * np.linalg.norm(K1)
+    st = r0[3]
+    assert st["terms_sent"] == sum(single[2]) + 1 and st["fetches"] == nsteps and st["bytes_sent"] > 0
+    assert piped[1][1]["role"] == "compress" and piped[1][1]["compressions"] > 0

@@ -291,3 +291,35 @@ def test_rrqr_orth(rail):
     lam = np.sort_complex(sla.eigvals(At, Et))
     ref = np.sort_complex(sla.eigvals(Q.T @ (A @ Q), Q.T @ (E @ Q)))
     assert np.allclose(lam, ref, rtol=1e-8)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 31, 64, 130, 300, 517])
+def test_symmetric_eigensolver_vs_lapack(k):
+    """The in-tree eigensolver behind compress! (src/LDLt.jl:214 calls LAPACK): backward error and orthogonality
+    at LAPACK level on the kinds of cores this path produces -- indefinite with +-pairs (T = [0 D; D 0] of the
+    Lyapunov residual, src/lyapunov/residual.jl:21-28), eigenvalues decaying over 16 decades, exact rank
+    deficiency, repeated eigenvalues."""
+    ctx = api.backend().ctx
+    rng = np.random.default_rng(k)
+    cases = []
+    Q, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    cases.append((Q * np.logspace(0, -16, k) * rng.choice([-1.0, 1.0], k)) @ Q.T)          # graded, indefinite
+    h = k // 2
+    if h:
+        D = np.diag(rng.standard_normal(h))
+        Tm = np.zeros((k, k))
+        Tm[:h, h:2 * h] = D
+        Tm[h:2 * h, :h] = D
+        cases.append(Q @ Tm @ Q.T)                                                          # exact +- pairs (+ a zero)
+        cases.append(Tm)                                                                    # already sparse / reducible
+    G = rng.standard_normal((k, max(1, k // 3)))
+    cases.append(G @ G.T)                                                                   # rank deficient
+    cases.append(np.eye(k) * 3.0 + 1e-9 * (Q + Q.T))                                        # clustered
+    for S in cases:
+        S = 0.5 * (S + S.T)
+        w, V = ctx.debug_eigh(S)
+        nrm = max(np.linalg.norm(S, 2), 1e-300)
+        assert np.all(np.diff(w) >= 0)
+        assert np.linalg.norm(V.T @ V - np.eye(k)) <= 50 * k * 2.2e-16
+        assert np.linalg.norm(S @ V - V * w) <= 50 * k * 2.2e-16 * nrm
+        assert np.max(np.abs(w - np.linalg.eigvalsh(S))) <= 50 * k * 2.2e-16 * nrm
