@@ -303,12 +303,64 @@ def gemm_nn(X: DeviceMatrix, W, alpha=1.0, Y: DeviceMatrix | None = None, beta=0
 # =============================================================================================
 # observers (src/Callbacks.jl:97-187)
 # =============================================================================================
+# Host-side timer tree with the reference's @timeit_debug section names (TimerOutputs); off unless
+# enable_debug_timings(True) -- the analogue of TimerOutputs.enable_debug_timings(DifferentialRiccatiEquations).  The
+# library marks the same sections as NVTX ranges (csrc/context.cu: Range).
+TIMERS: dict = {}
+COUNTS: dict = {}
+_DEBUG_TIMINGS = False
+
+
+def enable_debug_timings(on: bool = True):
+    global _DEBUG_TIMINGS
+    _DEBUG_TIMINGS = bool(on)
+    if on:
+        TIMERS.clear()
+        COUNTS.clear()
+
+
+class _timeit:
+    __slots__ = ("label", "t0")
+
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        if _DEBUG_TIMINGS:
+            import time
+
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if _DEBUG_TIMINGS:
+            import time
+
+            TIMERS[self.label] = TIMERS.get(self.label, 0.0) + time.perf_counter() - self.t0
+            COUNTS[self.label] = COUNTS.get(self.label, 0) + 1
+        return False
+
+
+def _timed(label):
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapper(*a, **kw):
+            if not _DEBUG_TIMINGS:
+                return fn(*a, **kw)
+            with _timeit(label):
+                return fn(*a, **kw)
+        return wrapper
+    return deco
+
+
 def _observe(observer, name, *args):
     if observer is None:
         return
     fn = getattr(observer, name, None)
     if fn is not None:
-        fn(*args)
+        with _timeit("callbacks"):
+            fn(*args)
 
 
 # =============================================================================================
@@ -411,6 +463,7 @@ def _dcat(Xs, alphas=None):
     return D
 
 
+@_timed("concatenate!(::LDLt)")
 def concatenate_(X: LDLt) -> LDLt:
     """src/LDLt.jl:174-191."""
     _join_pending(X)
@@ -446,6 +499,7 @@ def _compress_call(be: Backend, terms):
     return Lnew, lam[:k2]
 
 
+@_timed("compress!(::LDLt)")
 def compress_(X: LDLt) -> LDLt:
     """src/LDLt.jl:204-225 -- one C-ABI call (dre_ldlt_compress); no concatenation copy is needed."""
     _join_pending(X)
@@ -551,6 +605,7 @@ def _join_pending(X: LDLt):
         p.join(X)
 
 
+@_timed("norm(::LDLt)")
 def norm(X: LDLt) -> float:
     """src/LDLt.jl:77-89."""
     be = backend()
@@ -564,6 +619,7 @@ def norm(X: LDLt) -> float:
     return float(out.value)
 
 
+@_timed("dot(::LDLt, ::LDLt)")
 def dot(X1: LDLt, X2: LDLt) -> float:
     """src/LDLt.jl:91-108 -- Frobenius inner product tr(X1' X2): one Gram product A'C on the device
     (dre_gemm_tn), the k1 x k2 core algebra on the host."""
@@ -1035,6 +1091,7 @@ def _device_problem(prob: GALEProblem) -> GALEProblem:
     return GALEProblem(E, A, Cm)
 
 
+@_timed("residual(::GALEProblem, ::LDLt)")
 def residual(prob: GALEProblem, val: LDLt) -> LDLt:
     """src/lyapunov/residual.jl:3-31."""
     E, A, Cm = prob.E, prob.A, prob.C
@@ -1325,13 +1382,16 @@ def _residual_norm_overlapped(cache: ADICache) -> float:
 def step_(cache: ADICache):
     """CommonSolve.step!(::ADICache) -- adi.jl:97-128."""
     alg, abstol, observer = cache.alg, cache.abstol, cache.observer
-    mu = cache.shifts_oracle.take()
+    with _timeit("shifts"):
+        mu = cache.shifts_oracle.take()
     cache.shifts.append(complex(mu))
     _observe(observer, "observe_gale_metadata", "ADI shifts", mu)
     if np.imag(mu) == 0:
-        perform_single_step_(cache, float(np.real(mu)))
+        with _timeit("solve (real)"):      # (the fused C call also holds the residual update of adi.jl:171)
+            perform_single_step_(cache, float(np.real(mu)))
     else:
-        perform_double_step_(cache, complex(mu))
+        with _timeit("solve (complex)"):
+            perform_double_step_(cache, complex(mu))
     want_compress = alg.compression and cache.last_compression >= alg.compression_interval
     on_lane = want_compress and ASYNC_COMPRESS and _fused_inner(alg)   # (every rank of a sharded run has its own lane)
     if want_compress and not on_lane:
@@ -1627,6 +1687,7 @@ def _solve_ros2(prob: GDREProblem, alg: Ros2, *, dt, save_state, observer) -> DR
     return DRESolution(Xs, Ks, tstops)
 
 
+@_timed("residual(::GAREProblem, ::LDLt)")
 def gare_residual(prob: GAREProblem, X: LDLt, *, AtL=None, EtL=None, BtLD=None, DLtGLD=None, _dev=None) -> LDLt:
     """src/riccati/residual.jl:6-52."""
     be = backend()

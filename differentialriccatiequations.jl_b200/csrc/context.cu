@@ -18,6 +18,10 @@
 #include <string>
 #include <vector>
 
+#ifndef DRE_SIMT_EMU
+#include <nvtx3/nvToolsExt.h>   // header-only (the injection library is looked up at run time; no link dependency)
+#endif
+
 #include "../../include/dre_b200.h"
 #include "kernels.h"
 #include "schedule.h"
@@ -363,6 +367,18 @@ struct HostTrace {
     }
 };
 
+// NVTX ranges named after the reference's @timeit_debug sections (src/lyapunov/adi.jl:157,196, src/LDLt.jl:77,204,211,
+// 214, src/blocklinear/sherman-morrison-woodbury.jl:10,19,36), so that a profiler timeline of this library lines up
+// with the reference's TimerOutputs tree.  Zero cost unless a profiler is attached.
+struct Range {
+#ifndef DRE_SIMT_EMU
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+#else
+    explicit Range(const char*) {}
+#endif
+};
+
 struct Timer {
     dre_context* c;
     double* acc;
@@ -566,15 +582,19 @@ int shifted_solve_t(dre_context* c, double mu_re, double mu_im, dre_view R, dre_
     make_emu(c->op_e, mu_re, mu_im, emu);
     const int tw = (int)(sizeof(T) / sizeof(double));  // 1 or 2 doubles per element
     int rc = DRE_OK;
-    rc = acquire_factor<T>(c, mu_re, mu_im, emu, c->st);
-    if (rc) return rc;
+    Range r_solve(sizeof(T) == 8 ? "solve (real)" : "solve (complex)");
+    Range r_smw(m > 0 ? "Sherman-Morrison-Woodbury" : "Backslash");
     {
+        Range r_sparse("solve (sparse)");
+        rc = acquire_factor<T>(c, mu_re, mu_im, emu, c->st);
+        if (rc) return rc;
         HostTrace tr(sizeof(T) == 8 ? "sweeps<double> launch" : "sweeps<cplx> launch");
         rc = solve_sweeps<T>(c, W, ldw, nrhs, rhs_src);
     }
     if (rc) return rc;
     T* Sol = nullptr;
     if (m > 0) {
+        Range r_dense("solve (dense)");
         CU(c->btw.ensure((size_t)m * nrhs * tw));
         CU(c->sol.ensure((size_t)m * r * tw));
         rc = gram_dev(c, vptr(c, c->op_U), vld(c, c->op_U), m, (const double*)W, ldw * tw, nrhs * tw, n, nullptr,
@@ -1423,6 +1443,7 @@ int32_t dre_ldlt_norm(dre_context* c, dre_view L, const double* D, int64_t ldd, 
     const int k = L.ncols;
     if (k == 0) { *out = 0.0; return DRE_OK; }
     if (!D || ldd < k) return fail(c, DRE_ERR_ARG, "norm: bad core matrix");
+    Range r_norm("norm(::LDLt)");
     bool diag = true;
     for (int j = 0; j < k && diag; ++j)
         for (int i = 0; i < k; ++i)
@@ -1526,6 +1547,7 @@ int32_t dre_ldlt_norm_end(dre_context* c, double* out) {
 // eigen-decomposition of the symmetric k x k matrix S (device, ld k): on return row j of S (row-major view) is the
 // eigenvector of the j-th smallest eigenvalue, d_evals[j]
 static int eig_sym_dev(dre_context* c, double* S, int k, double* d_evals) {
+    Range r_eigen("eigen");
     HostTrace tr("eig_sym_dev", c->st);
 #ifdef DRE_SIMT_EMU
     int lwork = 0;
@@ -1586,6 +1608,7 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     *newrank = 0;
     if (ktot == 0) return DRE_OK;
     const int64_t n = c->sym.n;
+    Range r_compress("compress!(::LDLt)");
     RRState s;
     // Basis directions are dropped at HALF the relative level at which compress! truncates the eigenvalues of the
     // projected core below (tol_factor * eps, src/LDLt.jl:216-217): a direction whose coefficients are below
@@ -1634,6 +1657,7 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
                 for (int j = 0; j < k; ++j) s.scale2 = std::max(s.scale2, c->h_pinned[j] * c->h_pinned[j]);
                 s.rho = k;
             } else {
+                Range r_orthf("orthf");
                 HostTrace tr("compress: rr block (diag core)", c->st);
                 if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, c->evals.p, row0))) return rc;
             }
@@ -1642,6 +1666,7 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
             // src/lyapunov/residual.jl:21-28): exactly as the reference does (src/LDLt.jl:206-213) the basis is
             // built from the raw columns and the core enters afterwards, S += R_t' (alpha_t D_t) R_t.
             dense_terms.push_back({t, row0, k});
+            Range r_orthf("orthf");
             HostTrace tr("compress: rr block (dense core)", c->st);
             if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, nullptr, row0))) return rc;
         }
@@ -1734,6 +1759,7 @@ int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double d
     *rho_out = 0;
     if (ktot == 0) return DRE_OK;
     if (!Rt || ldr < ktot) return fail(c, DRE_ERR_ARG, "rrqr: bad Rt");
+    Range r_shifts("shifts");
     RRState s;
     if ((rc = rr_setup(c, s, ktot, drop_rel, drop_abs))) return rc;
     int row0 = 0;

@@ -18,6 +18,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -210,16 +212,25 @@ bool tql_rotations(std::vector<double>& d, std::vector<double>& e, std::vector<R
     e.resize(n, 0.0);
     e[n - 1] = 0.0;
     const double eps = 2.220446049250313e-16;
+    // Deflation: the classical relative test, or an off-diagonal entry below 0.1 eps ||T|| -- an absolute perturbation
+    // three orders of magnitude under the level at which compress! truncates eigenvalues (100 eps max|lambda|,
+    // src/LDLt.jl:216-217); it keeps the iteration from grinding on round-off-sized trailing blocks of rank-deficient
+    // cores, where the relative test compares noise with noise.
+    double anorm = 0.0;
+    for (int i = 0; i < n; ++i)
+        anorm = std::max(anorm, std::fabs(d[i]) + std::fabs(e[i]) + (i > 0 ? std::fabs(e[i - 1]) : 0.0));
+    if (!std::isfinite(anorm)) return false;
+    const double tiny = 0.1 * eps * anorm;
     for (int l = 0; l < n; ++l) {
         int iter = 0;
         for (;;) {
             int m = l;
             for (; m < n - 1; ++m) {
                 const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
-                if (std::fabs(e[m]) <= eps * dd) break;
+                if (std::fabs(e[m]) <= eps * dd || std::fabs(e[m]) <= tiny) break;
             }
             if (m == l) break;
-            if (++iter > 60) return false;
+            if (++iter > 200) return false;
             double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
             double r = std::hypot(g, 1.0);
             g = d[m] - d[l] + e[l] / (g + std::copysign(r, g));
@@ -287,6 +298,7 @@ int eig_sym(double* S, int k, double* d_evals, double* h_evals, double* work, vo
         // one warp per trailing row at the start; the barrier cost grows with the CTA count
         int grid = std::min(std::min(max_blocks, 64), (k + 7) / 8);
         grid = std::max(grid, 1);
+        if (const char* ev = getenv("DRE_EIG_GRID")) grid = std::max(1, std::min(atoi(ev), max_blocks));
         void* args[] = {&S, &k, &d, &e, &Vst, &tau, &pbuf};
         if (cudaLaunchCooperativeKernel((void*)k_tridiag, dim3(grid), dim3(TD_THREADS), args, smem, st) != cudaSuccess)
             return 1;
@@ -317,6 +329,14 @@ int eig_sym(double* S, int k, double* d_evals, double* h_evals, double* work, vo
     if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
     std::vector<Rot> rots;
     rots.reserve((size_t)k * k);
+    if (getenv("DRE_EIG_DEBUG")) {
+        int bad = 0;
+        double dmax = 0.0, emax = 0.0;
+        for (int i = 0; i < k; ++i) { if (!std::isfinite(hd[i])) ++bad; else dmax = std::max(dmax, std::fabs(hd[i])); }
+        for (int i = 0; i + 1 < k; ++i) { if (!std::isfinite(he[i])) ++bad; else emax = std::max(emax, std::fabs(he[i])); }
+        fprintf(stderr, "[dre eig] k %d non-finite %d max|d| %.3e max|e| %.3e d0 %.6e e0 %.6e\n", k, bad, dmax, emax, hd[0],
+                he[0]);
+    }
     if (!tql_rotations(hd, he, rots)) return 2;
     std::vector<int32_t> order(k), rank(k);
     std::iota(order.begin(), order.end(), 0);

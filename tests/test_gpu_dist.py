@@ -90,26 +90,11 @@ def _spawn(world, n, nsteps, mode="columns"):
     return sorted(res, key=lambda t: t[0])
 
 
-def test_sharded_ros1_matches_single_gpu():
-    import torch
-
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    n, nsteps = 1357, 2
-    single = _spawn(1, n, nsteps)[0]
-    sharded = _spawn(2, n, nsteps)
-    assert sharded[0][3] > 0  # the all-gather really ran
-    for r in sharded:
-        assert r[2] == single[2]  # identical ADI iteration counts on every rank
-        for Ks, K1 in zip(r[1], single[1]):
-            assert np.linalg.norm(Ks - K1) <= 1e-10 * np.linalg.norm(K1)
-    for Ka, Kb in zip(sharded[0][1], sharded[1][1]):
-        assert np.array_equal(Ka, Kb)  # ranks stay bit-identical
-
-
-def test_pipeline_mode_matches_single_gpu():
-    """Pipeline mode (dre_b200.dist, default for world_size > 1): rank 0 runs the ADI iteration and streams every
-    increment of X over NCCL to rank 1, which holds X and runs compress! there.  Same K(t), same iteration counts."""
+def test_two_gpu_modes_match_single_gpu():
+    """Both multi-GPU modes of dre_b200.dist against the single-GPU run (same K(t), same ADI iteration counts).
+    Pipeline mode (default for world_size > 1): rank 0 runs the ADI iteration and streams every increment of X over
+    NCCL to rank 1, which holds X and runs compress! there.  Column mode (DRE_DIST_MODE=columns): RHS column blocks of
+    every block solve per rank, replicated factorization, NCCL all-gather; the ranks stay bit-identical."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -124,3 +109,14 @@ def test_pipeline_mode_matches_single_gpu():
     st = r0[3]
     assert st["terms_sent"] == sum(single[2]) + 1 and st["fetches"] == nsteps and st["bytes_sent"] > 0
     assert piped[1][1]["role"] == "compress" and piped[1][1]["compressions"] > 0
+
+    n, nsteps = 1357, 2
+    single = _spawn(1, n, nsteps)[0]
+    sharded = _spawn(2, n, nsteps)
+    assert sharded[0][3] > 0  # the all-gather really ran
+    for r in sharded:
+        assert r[2] == single[2]  # identical ADI iteration counts on every rank
+        for Ks, K1 in zip(r[1], single[1]):
+            assert np.linalg.norm(Ks - K1) <= 1e-10 * np.linalg.norm(K1)
+    for Ka, Kb in zip(sharded[0][1], sharded[1][1]):
+        assert np.array_equal(Ka, Kb)  # ranks stay bit-identical
