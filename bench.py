@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 METRIC = "GDRE Ros1 LRSIF steps/sec at n=79841"
 DT = -100.0
 T0 = 4500.0
+# BASELINE.json configs reachable with --config (the default, 4, is the one the metric is quoted on)
+CONFIGS = {2: dict(n=5177, ros=1, dt=-100.0), 3: dict(n=20209, ros=2, dt=-50.0), 4: dict(n=79841, ros=1, dt=-100.0)}
 
 
 def _peaks():
@@ -198,6 +200,9 @@ def _run_ours(args):
     from dre_b200 import api
 
     n, K, W = args.n, args.steps, args.warmup
+    global DT
+    DT = args.dt
+    Ros = api.Ros1 if args.ros == 1 else api.Ros2
     E, A, B, C, L0, D0, meta = _problem(n)
     api.backend(local)
     be = api.backend()
@@ -232,7 +237,7 @@ def _run_ours(args):
     # ---- warm-up: W steps from t0 (also produces the state the timed steps start from) ----
     cw = IterCounter()
     tW = T0 + W * DT
-    sol = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(L0, D0), (T0, tW)), api.Ros1(), dt=DT, observer=cw)
+    sol = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(L0, D0), (T0, tW)), Ros(), dt=DT, observer=cw)
     XW = sol.X[-1]
     info = be.ctx.symbolic_info()
 
@@ -246,7 +251,7 @@ def _run_ours(args):
     be.ctx.stats_reset(False)
     be.ctx.timer_start()
     t_wall = time.perf_counter()
-    solK = api.solve(api.GDREProblem(E, A, B, C, XW, (tW, tK)), api.Ros1(), dt=DT, observer=ct)
+    solK = api.solve(api.GDREProblem(E, A, B, C, XW, (tW, tK)), Ros(), dt=DT, observer=ct)
     ms = be.ctx.timer_stop()
     wall = time.perf_counter() - t_wall
     barrier()
@@ -264,7 +269,7 @@ def _run_ours(args):
     # ---- instrumented pass (CUDA events around every kernel class) for the roofline ----
     XK = solK.X[-1]
     be.ctx.stats_reset(True)
-    api.solve(api.GDREProblem(E, A, B, C, XK, (tK, tK + DT)), api.Ros1(), dt=DT)
+    api.solve(api.GDREProblem(E, A, B, C, XK, (tK, tK + DT)), Ros(), dt=DT)
     sti = be.ctx.stats()
     be.ctx.stats_reset(False)
     hbm_peak, peak_src = _peaks()
@@ -349,7 +354,7 @@ def _run_ours(args):
     if coll is not None:
         coll.barrier()
     t0 = time.perf_counter()
-    sol_e = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(LW_host, DW_host), (tW, tK)), api.Ros1(), dt=DT)
+    sol_e = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(LW_host, DW_host), (tW, tK)), Ros(), dt=DT)
     be.ctx.sync()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()   # the NVML sampler (1 s period) runs across BOTH timed regions
@@ -368,7 +373,7 @@ def _run_ours(args):
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample of the same step ----
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu and args.ros == 1:
         cpu = cpu_sample(E, A, B, C, LW_host, DW_host, ct.iters[0] if ct.iters else 100, args.cpu_iters)
 
     if mode == "pipeline":
@@ -380,12 +385,13 @@ def _run_ours(args):
     if rank != 0:
         return None
     out = {
-        "metric": METRIC if n == 79841 else METRIC.replace("79841", str(n)), "value": value, "unit": "steps/s",
+        "metric": METRIC.replace("79841", str(n)).replace("Ros1", f"Ros{args.ros}"), "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Rail-shaped synthetic 2D P1-FEM pencil n={n} (7 inputs, 6 outputs), low-rank Ros1, "
+        "config": {"workload": f"Rail-shaped synthetic 2D P1-FEM pencil n={n} (7 inputs, 6 outputs), low-rank Ros{args.ros}, "
                                f"dt={DT}, t0={T0}, ADI defaults (Projection(2), maxiters=100, compression every 10)",
+                   "baseline_config": args.config,
                    "n": n, "nnz_E": meta["nnz_E"], "nnz_A": meta["nnz_A"],
                    "parallelism": "1 GPU" if world == 1 else
                    (f"one solve on {world} GPUs, column mode: RHS column blocks of every ADI block solve sharded over the "
@@ -476,23 +482,28 @@ def run_reference(args):
     from oracle import dre_oracle as O
 
     n, K, W = args.n, args.steps, args.warmup
+    global DT
+    DT = args.dt
+    ORos = O.Ros1 if args.ros == 1 else O.Ros2
+    if args.ros != 1:
+        args.full_steps = True   # the per-ADI-iteration sample below is written for the Ros1 step
     E, A, B, C, L0, D0, meta = _problem(n)
     cores = os.cpu_count() or 1
     nthreads = min(cores, 16)
     warnings.simplefilter("ignore")
     tau = -DT
-    workload = (f"Rail-shaped synthetic 2D P1-FEM pencil n={n} (7 inputs, 6 outputs), low-rank Ros1, "
+    workload = (f"Rail-shaped synthetic 2D P1-FEM pencil n={n} (7 inputs, 6 outputs), low-rank Ros{args.ros}, "
                 f"dt={DT}, t0={T0}, ADI defaults (Projection(2), maxiters=100, compression every 10)")
     extrap = None
     with threadpool_limits(limits=nthreads):
         if args.full_steps:
             cw = IterCounter()
             tW = T0 + W * DT
-            sol = O.solve_gdre(O.GDREProblem(E, A, B, C, O.lowrank(L0, D0), (T0, tW)), O.Ros1(), dt=DT, observer=cw,
+            sol = O.solve_gdre(O.GDREProblem(E, A, B, C, O.lowrank(L0, D0), (T0, tW)), ORos(), dt=DT, observer=cw,
                                save_state=True)
             ct = IterCounter()
             t0 = time.perf_counter()
-            O.solve_gdre(O.GDREProblem(E, A, B, C, sol.X[-1], (tW, tW + K * DT)), O.Ros1(), dt=DT, observer=ct)
+            O.solve_gdre(O.GDREProblem(E, A, B, C, sol.X[-1], (tW, tW + K * DT)), ORos(), dt=DT, observer=ct)
             est = (time.perf_counter() - t0) / K
             ms_per_step = est * 1e3
             sample = (f"oracle port on {nthreads} host threads: {W} whole warm-up steps, then {K} WHOLE time steps timed "
@@ -539,7 +550,7 @@ def run_reference(args):
                       f"mean at roughly its natural 1-in-10 rate) + ADI init {t_init:.1f} s; steps/s EXTRAPOLATED to "
                       f"{iters} ADI iterations per step -- an order-of-magnitude figure, not a measurement of whole steps")
     value = 1.0 / est
-    out = {"impl": "reference", "metric": METRIC if n == 79841 else METRIC.replace("79841", str(n)), "value": value,
+    out = {"impl": "reference", "metric": METRIC.replace("79841", str(n)).replace("Ros1", f"Ros{args.ros}"), "value": value,
            "unit": "steps/s", "n_gpus": world, "steps": K,
            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
@@ -553,13 +564,88 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def run_config5(args):
+    """BASELINE config 5: 3D heat-equation pencil (nside^3 unknowns, 8 inputs / 8 outputs): standalone GALE ADI
+    (test/tiny_random.jl:15-19 shape: dense identity core) and GARE Newton-ADI (test/rail.jl:74-88).  One GPU per
+    solve (the per-shift factorization is replicated by construction, SURVEY 8e: extra GPUs cannot share it); prints
+    one JSON line with the wall time of both solves, the factorization / sweep rates and the storage the symbolic
+    analysis asks for."""
+    import numpy as np
+
+    import dre_b200
+    from dre_b200 import api
+
+    warnings.simplefilter("ignore")
+    N = args.nside
+    t0 = time.perf_counter()
+    E, A, B, C, meta = dre_b200.pencils.heat3d_pencil(N)
+    n = E.shape[0]
+    api.backend(0)
+    be = api.backend()
+    be.ensure_pencil(E, A)
+    t_sym = time.perf_counter() - t0
+    info = be.ctx.symbolic_info()
+    q = C.shape[0]
+
+    class Obs:
+        def __init__(self):
+            self.iters, self.res = [], []
+
+        def observe_gale_done(self, it, X, res, rn):
+            self.iters.append(int(it))
+            self.res.append(float(rn))
+
+    out = {}
+    for name in ("gale_adi", "gare_newton_adi"):
+        obs = Obs()
+        be.ctx.sync()
+        be.ctx.stats_reset(True)
+        t0 = time.perf_counter()
+        if name == "gale_adi":
+            Cl = api.lowrank(np.asfortranarray(C.T), np.eye(q))
+            X = api.solve(api.GALEProblem(E, A, Cl), api.ADI(), observer=obs)
+            rhs_norm = api.norm(api.lowrank(np.asfortranarray(C.T), np.eye(q)))
+        else:
+            are = api.GAREProblem(E, A, api.lowrank(B), api.lowrank(np.asfortranarray(C.T)))
+            X = api.solve(are, api.Newton(api.ADI(ignore_initial_guess=True), maxiters=10, reltol=1e-10), observer=obs)
+            rhs_norm = api.norm(api.lowrank(np.asfortranarray(C.T)))
+        be.ctx.sync()
+        wall = time.perf_counter() - t0
+        st = be.ctx.stats()
+        be.ctx.stats_reset(False)
+        d = {"wall_s": wall, "adi_iterations": obs.iters, "final_adi_residuals": obs.res, "rank_X": int(X.rank()),
+             "rhs_norm": rhs_norm, "factorizations": st["factorizations"], "solves": st["solves"]}
+        if st["factorizations"]:
+            d["factor_ms_avg"] = st["ms_factor"] / st["factorizations"]
+            d["factor_TFLOPs"] = st["flops_factor"] / (st["ms_factor"] * 1e-3) / 1e12 if st["ms_factor"] else None
+        if st["solves"]:
+            d["sweeps_ms_avg"] = st["ms_solve"] / st["solves"]
+            d["sweeps_TFLOPs"] = st["flops_solve"] / (st["ms_solve"] * 1e-3) / 1e12 if st["ms_solve"] else None
+        out[name] = d
+    line = {"metric": f"3D heat FEM n={n}: GALE ADI + GARE Newton-ADI wall seconds", "value": out["gale_adi"]["wall_s"] +
+            out["gare_newton_adi"]["wall_s"], "unit": "s", "n_gpus": 1, "higher_is_better": False, "dtype": "f64",
+            "data": "synthetic", "vs_baseline": None,
+            "config": {"workload": f"synthetic 3D heat-equation pencil {N}^3 = {n} unknowns, 7-point operators, 8 inputs / 8 "
+                                   f"outputs; standalone GALE ADI (defaults) and Newton(ADI(ignore_initial_guess)) reltol "
+                                   f"1e-10", "baseline_config": 5, "n": n, "nnz_E": meta["nnz_E"], "nnz_A": meta["nnz_A"],
+                       "symbolic": info, "symbolic_and_upload_s": t_sym,
+                       "note": "event timing per kernel class is on (stats_reset(True)): the factor / sweep averages are "
+                               "serialised device times, the wall times include that instrumentation"},
+            "solves": out}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=79841)
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 4 (default, the headline n=79841 Ros1), 3 (n=20209 Ros2), 2 (n=5177 Ros1), "
+                         "5 (3D heat GALE ADI + Newton-ADI, see --nside)")
+    ap.add_argument("--nside", type=int, default=60, help="config 5: grid points per side (n = nside^3)")
     ap.add_argument("--cpu-iters", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
@@ -568,6 +654,13 @@ def main():
     ap.add_argument("--blas-threads", type=int, default=2, help="host BLAS threads during the GPU arm")
     args = ap.parse_args()
     os.environ.setdefault("OPENBLAS_NUM_THREADS", str(min(os.cpu_count() or 1, 16)))
+    if args.config == 5:
+        run_config5(args)
+        return
+    cfg = CONFIGS[args.config]
+    if args.n is None:
+        args.n = cfg["n"]
+    args.ros, args.dt = cfg["ros"], cfg["dt"]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -245,6 +245,11 @@ struct dre_context {
 
     // dense workspaces
     DBuf<double> gram_partial, gbuf, gbuf2, cbuf, wsel, wsel2, small, stage, qws, pws, qtmp, rt, rt2, tmp_panel, evals, cnorm;
+    // look-ahead stage of the rank-revealing Gram-Schmidt (rr_process_chunks)
+    cudaStream_t look_st = nullptr;
+    cudaEvent_t look_done[2] = {nullptr, nullptr}, look_basis = nullptr;
+    double* h_look = nullptr;
+    DBuf<double> look_partial, look_cbuf, look_cnorm, cscale;
     DBuf<double> syevd_work;            // eigensolver workspace (d, e, tau, reflectors, Q)
     DBuf<unsigned char> eig_rots;       // plane rotations of the QL iteration + rank table
     DBuf<int32_t> ibuf;
@@ -267,6 +272,7 @@ void for_each_workspace(dre_context* c, F f) {
     f(c->btw); f(c->sol); f(c->gram_partial); f(c->gbuf); f(c->gbuf2); f(c->cbuf);
     f(c->wsel); f(c->wsel2); f(c->small); f(c->stage); f(c->qws); f(c->pws); f(c->qtmp); f(c->rt); f(c->rt2);
     f(c->tmp_panel); f(c->evals); f(c->cnorm); f(c->syevd_work); f(c->eig_rots); f(c->ibuf);
+    f(c->look_partial); f(c->look_cbuf); f(c->look_cnorm); f(c->cscale);
 }
 
 int fail(dre_context* c, int code, const std::string& msg) {
@@ -411,6 +417,34 @@ int gram_dev(dre_context* c, const double* X, int64_t ldx, int a, const double* 
     c->stats.grams++;
     c->stats.flops_gram += 2.0 * (double)n * a * b;
     c->stats.bytes_gram += 8.0 * (double)n * ((X == Y && a == b) ? a : (a + b));
+    return DRE_OK;
+}
+
+// the same on an explicit stream with its own (pre-sized) partial-sum workspace: the look-ahead stage of compress!
+int gram_dev_on(dre_context* c, cudaStream_t st, DBuf<double>& partial, const double* X, int64_t ldx, int a,
+                const double* Y, int64_t ldy, int b, int64_t n, const double* roww, double* out1, int64_t ld1,
+                double* out2, int64_t ld2) {
+    if (a <= 0 || b <= 0) return DRE_OK;
+    GramPlan plan = gram_plan(n, a, b, c->sm_count);
+    if (plan.partial_elems > partial.cap) {
+        if (st != c->st) CU(cudaStreamSynchronize(st));   // (never on the sized-up-front path)
+        CU(partial.ensure(plan.partial_elems));
+    }
+    launch_gram(X, ldx, a, Y, ldy, b, n, roww, partial.p, plan, out1, ld1, out2, ld2, st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    c->stats.grams++;
+    c->stats.flops_gram += 2.0 * (double)n * a * b;
+    c->stats.bytes_gram += 8.0 * (double)n * (a + b);
+    return DRE_OK;
+}
+
+int tall_gemm_on(dre_context* c, cudaStream_t st, double alpha, const double* X, int64_t ldx, int a, const double* W,
+                 int64_t ldw, int w_trans, double beta, double* Y, int64_t ldy, int b, int64_t n) {
+    launch_tall_gemm(alpha, X, ldx, a, W, ldw, w_trans, beta, Y, ldy, b, n, st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    c->stats.tallgemms++;
+    c->stats.flops_tallgemm += 2.0 * (double)n * a * b;
+    c->stats.bytes_tallgemm += 8.0 * (double)n * (a + (beta == 0.0 ? 1.0 : 2.0) * b);
     return DRE_OK;
 }
 
@@ -644,15 +678,74 @@ struct RRState {
     int skipped = 0;   // sub-panels skipped because their remainder was below the drop threshold
 };
 
-int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds, int cols, const double* d_colscale,
-                     int rt_row0) {
-    // Block Gram-Schmidt in two granularities: a block of up to PBIG columns is projected twice against the
-    // basis it finds (two fat Gram + tall-GEMM pairs, where the flops are), then its 64-column sub-panels
-    // only have to be projected against the few directions added inside the block before the pivoted-
-    // Cholesky selection / CholQR2 of their remainder.
+struct RRChunk {
+    const double* src;        // n x cols columns of an input term (row-major, leading dimension lds)
+    int64_t lds;
+    int cols;                 // <= 256
+    const double* colscale;   // device, per column (nullptr: none)
+    int rt_row;               // first row of this chunk's coefficients in RT
+};
+
+// Stage 1 of a chunk (stream `st`: the look-ahead stream or the main one): scaled copy into work buffer `slot`,
+// original column norms, ONE projection pass against the basis columns [0, rho_snap) with the coefficients
+// accumulated into the chunk's RT rows, remainder norms; both norm vectors go to the pinned slot.
+int rr_stage1(dre_context* c, RRState& s, const RRChunk& ch, int slot, int rho_snap, cudaStream_t st, bool side) {
     const int64_t n = c->sym.n;
-    constexpr int PB = 64, PBIG = 256;
-    CU(c->pws.ensure((size_t)n * PBIG));
+    constexpr int PBIG = 256, NBLK = 296;
+    double* Pb = c->pws.p + (size_t)slot * n * PBIG;
+    DBuf<double>& partial = side ? c->look_partial : c->gram_partial;
+    double* cn = c->look_cnorm.p + (size_t)slot * 2 * PBIG;
+    launch_copy_scale(Pb, PBIG, ch.src, ch.lds, n, ch.cols, ch.colscale, st, &c->stats.kernel_launches);
+    launch_colnorm2(Pb, PBIG, n, ch.cols, partial.p, NBLK, cn, st, &c->stats.kernel_launches);
+    if (rho_snap > 0) {
+        double* cb = side ? c->look_cbuf.p : c->cbuf.p;
+        int rc = gram_dev_on(c, st, partial, Pb, PBIG, ch.cols, s.Q, s.ldq, rho_snap, n, nullptr, cb, rho_snap,
+                             s.RT + (int64_t)ch.rt_row * s.ldrt, s.ldrt);
+        if (rc) return rc;
+        rc = tall_gemm_on(c, st, -1.0, s.Q, s.ldq, rho_snap, cb, rho_snap, 1, 1.0, Pb, PBIG, ch.cols, n);
+        if (rc) return rc;
+        launch_colnorm2(Pb, PBIG, n, ch.cols, partial.p, NBLK, cn + PBIG, st, &c->stats.kernel_launches);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_look + (size_t)slot * 2 * PBIG, cn, 2 * PBIG * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->look_done[slot], st));
+    return DRE_OK;
+}
+
+// Block Gram-Schmidt in two granularities over a list of chunks (<= 256 columns each, in input order).
+//   stage 1 (fat, DMMA bound): the chunk is projected against the basis as it stood when the stage was queued;
+//   stage 2 (latency bound):   a second pass if the chunk holds large columns, then its 64-column sub-panels are
+//                              projected against the directions added since that snapshot, and pivoted-Cholesky
+//                              selection / CholQR2 rounds extract the new directions of their remainders.
+// LOOK-AHEAD: stage 1 of chunk i+1 is queued on a second stream BEFORE stage 2 of chunk i starts, against the
+// basis columns that exist at that moment (they are never rewritten), in the other of two work buffers; the fat
+// Gram / tall-GEMM kernels then fill the SMs the small selection kernels leave idle.  The directions chunk i adds
+// are simply part of "added since the snapshot" for chunk i+1.  (Off while per-class event timing is on and under
+// DRE_TRACE: both want one stream.  DRE_RR_LOOKAHEAD=0 disables it.)
+int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& chunks) {
+    const int64_t n = c->sym.n;
+    constexpr int PB = 64, PBIG = 256, NBLK = 296;
+    const int nch = (int)chunks.size();
+    if (nch == 0) return DRE_OK;
+    static const bool look_env = !(getenv("DRE_RR_LOOKAHEAD") && atoi(getenv("DRE_RR_LOOKAHEAD")) == 0);
+    const bool look = look_env && nch > 1 && !c->timing && !g_trace;
+    int rc;
+    if (!c->look_st) {
+        CU(cudaStreamCreateWithFlags(&c->look_st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&c->look_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->look_basis, cudaEventDisableTiming));
+        CU(cudaMallocHost((void**)&c->h_look, 4 * PBIG * sizeof(double)));
+    }
+    // every buffer the look-ahead stream touches is sized once, up front (no reallocation while it is in flight)
+    CU(c->pws.ensure((size_t)n * PBIG * 2));
+    CU(c->look_cnorm.ensure(4 * PBIG));
+    CU(c->look_cbuf.ensure((size_t)PBIG * s.qcap));
+    {
+        size_t pe = (size_t)NBLK * PBIG;
+        for (int b = 64; b < s.qcap + 64; b += 64) pe = std::max(pe, gram_plan(n, PBIG, std::min(b, s.qcap), c->sm_count).partial_elems);
+        CU(c->look_partial.ensure(pe));
+        CU(c->gram_partial.ensure((size_t)NBLK * PBIG));
+    }
     CU(c->qtmp.ensure((size_t)n * PB));
     CU(c->gbuf.ensure(PB * PB));
     CU(c->gbuf2.ensure(PB * PB));
@@ -660,93 +753,88 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
     CU(c->wsel2.ensure(PB * PB));
     CU(c->ibuf.ensure(8));
     CU(c->small.ensure(8));
-    int rc = ensure_pinned(c, 16);
-    if (rc) return rc;
-    double* Pbig = c->pws.p;
+    CU(c->cnorm.ensure(PBIG));
+    if ((rc = ensure_pinned(c, PBIG + 16))) return rc;
     double* Qt = c->qtmp.p;
-    for (int c0 = 0; c0 < cols; c0 += PBIG) {
-        const int pbig = std::min(PBIG, cols - c0);
-        launch_copy_scale(Pbig, PBIG, src + c0, lds, n, pbig, d_colscale ? d_colscale + c0 : nullptr, c->st,
-                          &c->stats.kernel_launches);
-        double block_max2 = 0.0;
-        {   // the drop threshold is relative to the largest ORIGINAL column norm met so far
-            constexpr int NBLK = 296;
-            CU(c->gram_partial.ensure((size_t)NBLK * PBIG));
-            CU(c->cnorm.ensure(PBIG));
-            launch_colnorm2(Pbig, PBIG, n, pbig, c->gram_partial.p, NBLK, c->cnorm.p, c->st, &c->stats.kernel_launches);
-            if ((rc = ensure_pinned(c, PBIG + 16))) return rc;
-            CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-            CU(cudaStreamSynchronize(c->st));
-            for (int j = 0; j < pbig; ++j) {
-                s.scale2 = std::max(s.scale2, c->h_pinned[16 + j]);
-                block_max2 = std::max(block_max2, c->h_pinned[16 + j]);
-            }
+    std::vector<int> snap(nch, 0);
+    auto queue_stage1 = [&](int i) -> int {
+        snap[i] = s.rho;
+        if (look) {
+            // behind everything queued on the main stream so far: the basis columns [0, rho) are complete and the
+            // rounds that used this work buffer (chunk i - 2) are over
+            CU(cudaEventRecord(c->look_basis, c->st));
+            CU(cudaStreamWaitEvent(c->look_st, c->look_basis, 0));
+            return rr_stage1(c, s, chunks[i], i & 1, snap[i], c->look_st, true);
         }
-        const int rho0 = s.rho;
-        // One projection pass leaves a basis component of ~30 eps |p| in a column p.  Columns below 5 % of the
-        // global scale therefore stay an order of magnitude under the drop threshold (3e-15 * scale) after a
-        // single pass, and the second ("twice is enough") pass is only spent on blocks with large columns.  The
-        // orthogonality of the basis does not depend on it: candidates are re-orthogonalised below.
-        const int npass = (block_max2 <= 0.0025 * s.scale2) ? 1 : 2;
+        CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
+        return rr_stage1(c, s, chunks[i], i & 1, snap[i], c->st, false);
+    };
+    if (look && (rc = queue_stage1(0))) return rc;
+    for (int i = 0; i < nch; ++i) {
+        const RRChunk& ch = chunks[i];
+        const int pbig = ch.cols;
+        if (look) {
+            if (i + 1 < nch && (rc = queue_stage1(i + 1))) return rc;
+        } else if ((rc = queue_stage1(i))) return rc;
+        CU(cudaEventSynchronize(c->look_done[i & 1]));
+        if (look) CU(cudaStreamWaitEvent(c->st, c->look_done[i & 1], 0));
+        g_rr.syncs++;
+        double* Pbig = c->pws.p + (size_t)(i & 1) * n * PBIG;
+        const double* hn = c->h_look + (size_t)(i & 1) * 2 * PBIG;
+        const int rho0 = snap[i];
+        double block_max2 = 0.0;
+        for (int j = 0; j < pbig; ++j) {   // the drop threshold is relative to the largest ORIGINAL column norm met so far
+            s.scale2 = std::max(s.scale2, hn[j]);
+            block_max2 = std::max(block_max2, hn[j]);
+        }
         // remainder norms after the block passes: a sub-panel whose columns are all below the drop threshold
         // cannot contribute a direction (pivoted Cholesky would select nothing) and is skipped without its
         // Gram / selection / synchronisation
         std::vector<double> rem2(pbig, 0.0);
-        bool have_rem = false;
-        auto remainder_norms = [&]() -> int {
-            constexpr int NBLK = 296;
-            launch_colnorm2(Pbig, PBIG, n, pbig, c->gram_partial.p, NBLK, c->cnorm.p, c->st, &c->stats.kernel_launches);
-            CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-            CU(cudaStreamSynchronize(c->st));
-            g_rr.syncs++;
-            for (int j = 0; j < pbig; ++j) rem2[j] = c->h_pinned[16 + j];
-            have_rem = true;
-            return DRE_OK;
-        };
-        if (rho0 > 0) {
-            CU(c->cbuf.ensure((size_t)PBIG * rho0));
-            for (int pass = 0; pass < npass; ++pass) {
-                if (pass == 1 && have_rem) {
-                    // The first pass already left every column of the block below the drop threshold: the block adds
-                    // no direction and its remainder is discarded as a whole.  A second pass would only move the
-                    // part of that remainder that lies in span(Q) -- at most drop * scale per column, i.e. no more
-                    // than what is being discarded anyway -- into the coefficients, so it is skipped altogether.
-                    double m2 = 0.0;
-                    for (int j = 0; j < pbig; ++j) m2 = std::max(m2, rem2[j]);
-                    const double drop0 = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
-                    if (m2 < drop0 * drop0) { g_rr.coef_only_passes++; break; }
-                }
-                // C' = P' Q (pbig x rho0): coefficients, accumulated into the RT rows of this block
+        const bool have_rem = rho0 > 0;
+        if (have_rem)
+            for (int j = 0; j < pbig; ++j) rem2[j] = hn[PBIG + j];
+        // One projection pass leaves a basis component of ~30 eps |p| in a column p.  Columns below 5 % of the
+        // global scale therefore stay an order of magnitude under the drop threshold after a single pass, and the
+        // second ("twice is enough") pass is only spent on chunks with large columns.  The orthogonality of the
+        // basis does not depend on it: candidates are re-orthogonalised below.
+        const int npass = (block_max2 <= 0.0025 * s.scale2) ? 1 : 2;
+        if (rho0 > 0 && npass == 2) {
+            // If the first pass already left every column of the chunk below the drop threshold, the chunk adds no
+            // direction and its remainder is discarded as a whole: a second pass would only move the part of that
+            // remainder that lies in span(Q) -- at most drop * scale per column, no more than what is being
+            // discarded anyway -- into the coefficients, so it is skipped.
+            double m2 = 0.0;
+            for (int j = 0; j < pbig; ++j) m2 = std::max(m2, rem2[j]);
+            const double drop0 = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
+            if (m2 < drop0 * drop0) {
+                g_rr.coef_only_passes++;
+            } else {
+                CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
                 rc = gram_dev(c, Pbig, PBIG, pbig, s.Q, s.ldq, rho0, n, nullptr, c->cbuf.p, rho0,
-                              s.RT + (int64_t)(rt_row0 + c0) * s.ldrt, s.ldrt);
+                              s.RT + (int64_t)ch.rt_row * s.ldrt, s.ldrt);
                 if (rc) return rc;
                 rc = tall_gemm(c, -1.0, s.Q, s.ldq, rho0, c->cbuf.p, rho0, 1, 1.0, Pbig, PBIG, pbig, n);
                 if (rc) return rc;
-                if ((rc = remainder_norms())) return rc;
+                launch_colnorm2(Pbig, PBIG, n, pbig, c->gram_partial.p, NBLK, c->cnorm.p, c->st, &c->stats.kernel_launches);
+                CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+                CU(cudaStreamSynchronize(c->st));
+                g_rr.syncs++;
+                for (int j = 0; j < pbig; ++j) rem2[j] = c->h_pinned[16 + j];
             }
         }
-        // Optional eager projection of the rest of the block (DRE_RR_EAGER=1, off by default): as soon as a sub-panel
-        // has added directions, the columns behind it are projected against them in ONE fat Gram / tall-GEMM pair
-        // and their remainder norms are refreshed, so that sub-panels the new directions exhaust are skipped
-        // instead of each paying a projection, a Gram, a selection and a synchronisation to find nothing.  On the
-        // emulator (n = 371, three Ros1 steps) it trades 7 unproductive rounds for 75 extra projections -- a loss;
-        // whether it pays at n = 79 841 (where tracing showed 539 of 1215 wide-sub-panel rounds finding nothing)
-        // depends on how many of those the norm test already skips: to be measured with DRE_RR_STATS=1 on the GPU.
-        static const bool eager = getenv("DRE_RR_EAGER") && atoi(getenv("DRE_RR_EAGER")) != 0;
-        int proj_rest = rho0;   // columns behind the current sub-panel are orthogonal to the basis [0, proj_rest)
         g_rr.blocks++;
         for (int sc = 0; sc < pbig; sc += PB) {
             const int pb = std::min(PB, pbig - sc);
-            const int proj_entry = eager ? proj_rest : rho0;
             if (have_rem && !g_trace) {
                 double m2 = 0.0;
                 for (int j = sc; j < sc + pb; ++j) m2 = std::max(m2, rem2[j]);
                 const double drop0 = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
-                // (projections against directions added inside this block can only shrink the columns further)
+                // (projections against directions added since the snapshot can only shrink the columns further)
                 if (m2 < drop0 * drop0) { s.skipped++; g_rr.skipped++; continue; }
             }
             double* Pw = Pbig + sc;
-            double* RTrow = s.RT + (int64_t)(rt_row0 + c0 + sc) * s.ldrt;
+            double* RTrow = s.RT + (int64_t)(ch.rt_row + sc) * s.ldrt;
             double trace_d0 = 0.0;
             if (g_trace) {   // diagnostic only: largest squared column norm of the sub-panel's remainder so far
                 rc = gram_dev(c, Pw, PBIG, pb, Pw, PBIG, pb, n, nullptr, c->gbuf.p, PB, nullptr, 0);
@@ -754,23 +842,22 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                 std::vector<double> hg((size_t)PB * PB);
                 CU(cudaMemcpyAsync(hg.data(), c->gbuf.p, sizeof(double) * PB * PB, cudaMemcpyDeviceToHost, c->st));
                 CU(cudaStreamSynchronize(c->st));
-                for (int i = 0; i < pb; ++i) trace_d0 = std::max(trace_d0, hg[(size_t)i * PB + i]);
+                for (int k = 0; k < pb; ++k) trace_d0 = std::max(trace_d0, hg[(size_t)k * PB + k]);
             }
             for (int round = 0; round < 8; ++round) {
                 s.rounds++;
                 g_rr.rounds++;
-                // directions added inside this block that this sub-panel has not been projected against yet
-                // (round 0 of an eagerly projected sub-panel: none; later rounds re-project against all of them)
-                const int pfrom = (round == 0) ? proj_entry : rho0;
-                const int nnew = s.rho - pfrom;
+                // directions added since the snapshot (by earlier chunks / sub-panels / rounds) that this sub-panel
+                // has not been projected against in this round
+                const int nnew = s.rho - rho0;
                 if (nnew > 0) {
                     CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
-                    // same rule as for the block passes: one pass unless the block holds large columns
+                    // same rule as for the block passes: one pass unless the chunk holds large columns
                     for (int pass = 0; pass < npass; ++pass) {
-                        rc = gram_dev(c, Pw, PBIG, pb, s.Q + pfrom, s.ldq, nnew, n, nullptr, c->cbuf.p, nnew,
-                                      RTrow + pfrom, s.ldrt);
+                        rc = gram_dev(c, Pw, PBIG, pb, s.Q + rho0, s.ldq, nnew, n, nullptr, c->cbuf.p, nnew,
+                                      RTrow + rho0, s.ldrt);
                         if (rc) return rc;
-                        rc = tall_gemm(c, -1.0, s.Q + pfrom, s.ldq, nnew, c->cbuf.p, nnew, 1, 1.0, Pw, PBIG, pb, n);
+                        rc = tall_gemm(c, -1.0, s.Q + rho0, s.ldq, nnew, c->cbuf.p, nnew, 1, 1.0, Pw, PBIG, pb, n);
                         if (rc) return rc;
                     }
                 }
@@ -827,9 +914,9 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                 }
                 if (g_trace)
                     fprintf(stderr,
-                            "[dre rr] row0 %5d c0 %4d pb %2d round %d rho %4d nsel %2d nsel2 %2d rem/col %.2e left %.2e "
+                            "[dre rr] row0 %5d pb %2d round %d rho %4d nsel %2d nsel2 %2d rem/col %.2e left %.2e "
                             "scale %.2e\n",
-                            rt_row0, c0 + sc, pb, round, s.rho, nsel, nsel2,
+                            ch.rt_row + sc, pb, round, s.rho, nsel, nsel2,
                             std::sqrt(dfirst / std::max(trace_d0, 1e-300)),
                             std::sqrt(remaining / std::max(trace_d0, 1e-300)), std::sqrt(s.scale2));
                 if (nsel == 0 || nsel2 == 0) break;
@@ -840,32 +927,17 @@ int rr_process_block(dre_context* c, RRState& s, const double* src, int64_t lds,
                 const double drop_now = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
                 if (nsel2 == nsel && remaining <= drop_now * drop_now && 1e-13 * dfirst <= drop_now * drop_now) break;
             }
-            const int rest0 = sc + pb, nrest = pbig - rest0;
-            if (eager && nrest > 0 && s.rho > proj_rest) {
-                const int nn = s.rho - proj_rest;
-                double* Prest = Pbig + rest0;
-                CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
-                for (int pass = 0; pass < npass; ++pass) {
-                    rc = gram_dev(c, Prest, PBIG, nrest, s.Q + proj_rest, s.ldq, nn, n, nullptr, c->cbuf.p, nn,
-                                  s.RT + (int64_t)(rt_row0 + c0 + rest0) * s.ldrt + proj_rest, s.ldrt);
-                    if (rc) return rc;
-                    rc = tall_gemm(c, -1.0, s.Q + proj_rest, s.ldq, nn, c->cbuf.p, nn, 1, 1.0, Prest, PBIG, nrest, n);
-                    if (rc) return rc;
-                }
-                proj_rest = s.rho;
-                g_rr.rest_projections++;
-                constexpr int NBLK = 296;
-                launch_colnorm2(Prest, PBIG, n, nrest, c->gram_partial.p, NBLK, c->cnorm.p, c->st,
-                                &c->stats.kernel_launches);
-                CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, nrest * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-                CU(cudaStreamSynchronize(c->st));
-                g_rr.syncs++;
-                for (int j = 0; j < nrest; ++j) rem2[rest0 + j] = c->h_pinned[16 + j];
-                have_rem = true;
-            }
         }
     }
+    if (look) CU(cudaStreamSynchronize(c->look_st));   // (nothing is pending there; keeps the invariant explicit)
     return DRE_OK;
+}
+
+// chunks of one term (column blocks of at most 256 columns)
+void rr_add_term(std::vector<RRChunk>& chunks, const double* src, int64_t lds, int cols, const double* colscale,
+                 int rt_row0) {
+    for (int c0 = 0; c0 < cols; c0 += 256)
+        chunks.push_back(RRChunk{src + c0, lds, std::min(256, cols - c0), colscale ? colscale + c0 : nullptr, rt_row0 + c0});
 }
 
 }  // namespace
@@ -1047,6 +1119,10 @@ int32_t dre_destroy(dre_context* c) {
     for_each_workspace(c, [](auto& w) { w.forget(); });   // the arena (destroyed above) owned their memory
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_norm) cudaFreeHost(c->h_norm);
+    if (c->h_look) cudaFreeHost(c->h_look);
+    for (int i = 0; i < 2; ++i) if (c->look_done[i]) cudaEventDestroy(c->look_done[i]);
+    if (c->look_basis) cudaEventDestroy(c->look_basis);
+    if (c->look_st) cudaStreamDestroy(c->look_st);
     if (c->norm_in) cudaEventDestroy(c->norm_in);
     if (c->norm_done) cudaEventDestroy(c->norm_done);
     if (c->norm_st) cudaStreamDestroy(c->norm_st);
@@ -1624,53 +1700,68 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     std::vector<double> signs(ktot, 1.0);
     struct DenseTerm { int t, row0, k; };
     std::vector<DenseTerm> dense_terms;
-    int row0 = 0;
-    for (int t = 0; t < nterms; ++t) {
-        const int k = Ls[t].ncols;
-        if (k == 0) continue;
-        const double* D = Ds[t];
-        const int64_t ldd = ldds[t];
-        if (!D || ldd < k) return fail(c, DRE_ERR_ARG, "compress: bad core matrix");
-        bool diag = true;
-        for (int j = 0; j < k && diag; ++j)
-            for (int i = 0; i < k; ++i)
-                if (i != j && D[i + (int64_t)j * ldd] != 0.0) { diag = false; break; }
-        if ((rc = ensure_pinned(c, (size_t)k * k + 64))) return rc;
-        CU(cudaStreamSynchronize(c->st));
-        if (diag) {
+    // column scalings |alpha d_j|^(1/2) of the diagonal-core terms (1 for the columns of dense-core terms, whose core
+    // enters after the basis is built, exactly as in the reference, src/LDLt.jl:206-213), uploaded once
+    if ((rc = ensure_pinned(c, (size_t)ktot + 64))) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    std::vector<char> is_diag(nterms, 0);
+    {
+        int row0 = 0;
+        for (int t = 0; t < nterms; ++t) {
+            const int k = Ls[t].ncols;
+            if (k == 0) continue;
+            const double* D = Ds[t];
+            const int64_t ldd = ldds[t];
+            if (!D || ldd < k) return fail(c, DRE_ERR_ARG, "compress: bad core matrix");
+            bool diag = true;
+            for (int j = 0; j < k && diag; ++j)
+                for (int i = 0; i < k; ++i)
+                    if (i != j && D[i + (int64_t)j * ldd] != 0.0) { diag = false; break; }
+            is_diag[t] = diag;
             for (int j = 0; j < k; ++j) {
-                const double v = alphas[t] * D[j + (int64_t)j * ldd];
-                c->h_pinned[j] = std::sqrt(std::fabs(v));
-                signs[row0 + j] = (v < 0.0) ? -1.0 : 1.0;
+                if (diag) {
+                    const double v = alphas[t] * D[j + (int64_t)j * ldd];
+                    c->h_pinned[row0 + j] = std::sqrt(std::fabs(v));
+                    signs[row0 + j] = (v < 0.0) ? -1.0 : 1.0;
+                } else {
+                    c->h_pinned[row0 + j] = 1.0;
+                }
             }
-            CU(c->evals.ensure(k));
-            CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, k * sizeof(double), cudaMemcpyHostToDevice, c->st));
-            const bool hinted = s.rho == 0 && hint.id == Ls[t].id && hint.col0 == Ls[t].col0 &&
-                                hint.ncols == Ls[t].ncols && k + 64 <= s.qcap;
+            if (!diag) dense_terms.push_back({t, row0, k});
+            row0 += k;
+        }
+    }
+    CU(c->cscale.ensure((size_t)ktot));
+    CU(cudaMemcpyAsync(c->cscale.p, c->h_pinned, ktot * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    std::vector<RRChunk> chunks;
+    {
+        int row0 = 0;
+        for (int t = 0; t < nterms; ++t) {
+            const int k = Ls[t].ncols;
+            if (k == 0) continue;
+            const bool hinted = is_diag[t] && s.rho == 0 && chunks.empty() && hint.id == Ls[t].id &&
+                                hint.col0 == Ls[t].col0 && hint.ncols == Ls[t].ncols && k + 64 <= s.qcap;
             if (hinted) {
                 // the caller vouches that these columns are orthonormal (the outer factor a previous compress!
                 // produced): they ARE the first k basis vectors, their coefficients are the column scalings
                 launch_copy_scale(s.Q, s.ldq, vptr(c, Ls[t]), vld(c, Ls[t]), n, k, nullptr, c->st,
                                   &c->stats.kernel_launches);
-                CU(cudaMemcpy2DAsync(s.RT + (int64_t)row0 * s.ldrt, (size_t)(s.ldrt + 1) * sizeof(double), c->evals.p,
-                                     sizeof(double), sizeof(double), k, cudaMemcpyDeviceToDevice, c->st));
-                for (int j = 0; j < k; ++j) s.scale2 = std::max(s.scale2, c->h_pinned[j] * c->h_pinned[j]);
+                CU(cudaMemcpy2DAsync(s.RT + (int64_t)row0 * s.ldrt, (size_t)(s.ldrt + 1) * sizeof(double),
+                                     c->cscale.p + row0, sizeof(double), sizeof(double), k, cudaMemcpyDeviceToDevice,
+                                     c->st));
+                for (int j = 0; j < k; ++j) s.scale2 = std::max(s.scale2, c->h_pinned[row0 + j] * c->h_pinned[row0 + j]);
                 s.rho = k;
             } else {
-                Range r_orthf("orthf");
-                HostTrace tr("compress: rr block (diag core)", c->st);
-                if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, c->evals.p, row0))) return rc;
+                rr_add_term(chunks, vptr(c, Ls[t]), vld(c, Ls[t]), k, is_diag[t] ? c->cscale.p + row0 : nullptr, row0);
             }
-        } else {
-            // Non-diagonal core (e.g. T = [aS 0 0; 0 0 bD; 0 bD 0] of the Lyapunov residual,
-            // src/lyapunov/residual.jl:21-28): exactly as the reference does (src/LDLt.jl:206-213) the basis is
-            // built from the raw columns and the core enters afterwards, S += R_t' (alpha_t D_t) R_t.
-            dense_terms.push_back({t, row0, k});
-            Range r_orthf("orthf");
-            HostTrace tr("compress: rr block (dense core)", c->st);
-            if ((rc = rr_process_block(c, s, vptr(c, Ls[t]), vld(c, Ls[t]), k, nullptr, row0))) return rc;
+            row0 += k;
         }
-        row0 += k;
+    }
+    CU(cudaStreamSynchronize(c->st));   // (h_pinned is reused by the rounds)
+    {
+        Range r_orthf("orthf");
+        HostTrace tr("compress: rank-revealing Gram-Schmidt", c->st);
+        if ((rc = rr_process_chunks(c, s, chunks))) return rc;
     }
     const int rho = s.rho;
     if (rho == 0) return check_errflag(c);
@@ -1763,12 +1854,14 @@ int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double d
     RRState s;
     if ((rc = rr_setup(c, s, ktot, drop_rel, drop_abs))) return rc;
     int row0 = 0;
+    std::vector<RRChunk> chunks;
     for (int t = 0; t < nviews; ++t) {
         const int k = views[t].ncols;
         if (k == 0) continue;
-        if ((rc = rr_process_block(c, s, vptr(c, views[t]), vld(c, views[t]), k, nullptr, row0))) return rc;
+        rr_add_term(chunks, vptr(c, views[t]), vld(c, views[t]), k, nullptr, row0);
         row0 += k;
     }
+    if ((rc = rr_process_chunks(c, s, chunks))) return rc;
     const int rho = s.rho;
     if (rho > Q.ncols) return fail(c, DRE_ERR_ARG, "rrqr: Q panel too small");
     *rho_out = rho;

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -151,63 +152,146 @@ __global__ void __launch_bounds__(TD_THREADS) k_tridiag(double* A, int k, double
     }
 }
 
-// Q (k x k, row-major Qm[i*k + c]) = H_0 H_1 ... H_{k-3}, H_j = I - tau_j [0; v_j][0; v_j]' acting on rows j+1..k-1
-__global__ void __launch_bounds__(128) k_form_q(double* Qm, int k, const double* Vst, const double* tau) {
-    extern __shared__ double vs[];   // [k]
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int i = 0; i < k; ++i)
-        if (c < k) Qm[(size_t)i * k + c] = (i == c) ? 1.0 : 0.0;
-    for (int j = k - 3; j >= 0; --j) {
-        const int m = k - j - 1;
-        __syncthreads();
-        for (int i = threadIdx.x; i < m; i += blockDim.x) vs[i] = Vst[(size_t)j * k + i];
-        __syncthreads();
+// Q = H_0 H_1 ... H_{k-3} (H_j = I - tau_j [0; v_j][0; v_j]' acting on rows j+1..k-1), stored TRANSPOSED:
+// Qt[c*k + i] = Q[i][c].  Backward accumulation; every column of Q is independent: one warp per column, the column
+// lives in registers (lane l owns the elements l, l+32, ...: NS slots cover k <= 32 NS), the reflector is read
+// coalesced from L2 and the dot product is a shuffle tree -- no memory round trip inside the dependent chain.
+template <int NS>
+__global__ void __launch_bounds__(256) k_form_qt(double* Qt, int k, const double* __restrict__ Vst,
+                                                 const double* __restrict__ tau) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= k) return;
+    double col[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) col[q] = (lane + 32 * q == c) ? 1.0 : 0.0;
+    for (int j = min(k - 3, c - 1); j >= 0; --j) {   // H_j leaves the columns c <= j untouched
         const double t = tau[j];
-        if (c < j + 1 || c >= k || t == 0.0) continue;
-        double* col = Qm + (size_t)(j + 1) * k + c;
+        if (t == 0.0) continue;
+        const double* v = Vst + (size_t)j * k - (j + 1);   // v[idx] for the row index idx >= j+1
+        double vv[NS];
         double z = 0.0;
-        for (int i = 0; i < m; ++i) z += vs[i] * col[(size_t)i * k];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const int idx = lane + 32 * q;
+            vv[q] = (idx > j && idx < k) ? v[idx] : 0.0;
+            z = fma(vv[q], col[q], z);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
         z *= t;
-        for (int i = 0; i < m; ++i) col[(size_t)i * k] -= z * vs[i];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) col[q] = fma(-z, vv[q], col[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        const int idx = lane + 32 * q;
+        if (idx < k) Qt[(size_t)c * k + idx] = col[q];
     }
 }
 
-struct Rot {
-    double c, s;
-    int i, pad;
-};
+// generic fallback for k > 1024 (not met on this path): column in global memory
+__global__ void __launch_bounds__(256) k_form_qt_big(double* Qt, int k, const double* __restrict__ Vst,
+                                                     const double* __restrict__ tau) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= k) return;
+    double* col = Qt + (size_t)c * k;
+    for (int idx = lane; idx < k; idx += 32) col[idx] = (idx == c) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int j = min(k - 3, c - 1); j >= 0; --j) {
+        const double t = tau[j];
+        if (t == 0.0) continue;
+        const double* v = Vst + (size_t)j * k - (j + 1);
+        double z = 0.0;
+        for (int idx = j + 1 + lane; idx < k; idx += 32) z = fma(v[idx], col[idx], z);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        z *= t;
+        for (int idx = j + 1 + lane; idx < k; idx += 32) col[idx] = fma(-z, v[idx], col[idx]);
+        __syncwarp();
+    }
+}
 
-// rows [r0, r0 + nr) of Q (row-major): z[i+1] = s z[i] + c f,  z[i] = c z[i] - s f  for every recorded rotation,
-// then Out[rank[i]*k + row] = z[i]
-__global__ void k_apply_rot(const double* Qm, int k, const Rot* rots, int nrot, const int32_t* rank, double* Out,
-                            int rows_per_cta) {
-    extern __shared__ double zs[];   // [rows_per_cta][k + 1]
+struct Rot {      // plane rotation of the QL iteration
+    double c, s;
+};
+struct Sweep {    // (part of) one QL sweep: rotations rots[off .. off+len) act on the pairs (hi, hi+1), (hi-1, hi), ...
+    int off, hi, len, pad;
+};
+constexpr int ROT_TILE = 1024;   // rotations per shared-memory tile; the host splits sweeps at tile boundaries
+
+// Eigenvectors V = Q G_1 G_2 ...: rows [r0, r0 + nr) of Q, one thread of warp 0 per row with the row in shared
+// memory.  A sweep is the chain
+//   f = z[i+1];  z[i+1] = s z[i] + c f;  z[i] = c z[i] - s f      for i = hi, hi-1, ..., hi-len+1
+// in which the new z[i] is the f of the next rotation: it is carried in a register, so the only dependent operation
+// per rotation is one FMA, and the loads of z[i] are hoisted four rotations ahead of the stores (indices descend).
+// The rotation parameters stream through two shared-memory tiles: warps 1..3 fetch tile t+1 from global memory while
+// warp 0 runs the chains of tile t (a dependent global load per rotation cost 180 cycles per rotation before).
+// Finally Out[rank[i]*k + row] = z[i] (transposed, sorted by eigenvalue).  Qt is Q transposed (k_form_qt).
+__global__ void __launch_bounds__(128) k_apply_rot(const double* __restrict__ Qt, int k, const Rot* __restrict__ rots,
+                                                   int nrot, const Sweep* __restrict__ sweeps,
+                                                   const int32_t* __restrict__ tile_first, int ntiles,
+                                                   const int32_t* __restrict__ rank, double* Out, int rows_per_cta) {
+    extern __shared__ double zs[];   // [rows_per_cta][ldz], then two rotation tiles
     const int ldz = k + 1 + ((k & 1) ? 1 : 0);   // odd leading dimension: lanes of a warp hit different banks
+    Rot* tiles = reinterpret_cast<Rot*>(zs + (size_t)rows_per_cta * ldz + (((size_t)rows_per_cta * ldz) & 1));
     const int r0 = blockIdx.x * rows_per_cta;
     const int nr = min(rows_per_cta, k - r0);
-    for (int idx = threadIdx.x; idx < nr * k; idx += blockDim.x) {
-        const int r = idx / k, i = idx - r * k;
-        zs[r * ldz + i] = Qm[(size_t)(r0 + r) * k + i];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < nr * k; idx += blockDim.x) {
+        const int i = idx / nr, r = idx - i * nr;
+        zs[r * ldz + i] = Qt[(size_t)i * k + (r0 + r)];
     }
+    for (int g = tid; g < min(ROT_TILE, nrot); g += blockDim.x) tiles[g] = rots[g];
     __syncthreads();
-    if ((int)threadIdx.x < nr) {
-        double* z = zs + threadIdx.x * ldz;
-        for (int q = 0; q < nrot; ++q) {
-            const Rot R = rots[q];
-            const double f = z[R.i + 1], g = z[R.i];
-            z[R.i + 1] = R.s * g + R.c * f;
-            z[R.i] = R.c * g - R.s * f;
+    for (int t = 0; t < ntiles; ++t) {
+        const Rot* R = tiles + (size_t)(t & 1) * ROT_TILE;
+        if (tid >= 32) {   // loader warps: next tile
+            Rot* Rn = tiles + (size_t)((t + 1) & 1) * ROT_TILE;
+            const int g0 = (t + 1) * ROT_TILE;
+            for (int g = tid - 32; g < ROT_TILE && g0 + g < nrot; g += blockDim.x - 32) Rn[g] = rots[g0 + g];
+        } else if (tid < nr) {
+            double* z = zs + tid * ldz;
+            const int base = t * ROT_TILE;
+            for (int q = tile_first[t]; q < tile_first[t + 1]; ++q) {
+                const Sweep sw = sweeps[q];
+                const Rot* Rs = R + (sw.off - base);
+                double carry = z[sw.hi + 1];
+                int u = 0;
+                for (; u + 4 <= sw.len; u += 4) {
+                    const int i = sw.hi - u;
+                    const double z0 = z[i], z1 = z[i - 1], z2 = z[i - 2], z3 = z[i - 3];
+                    const Rot a = Rs[u], b = Rs[u + 1], c2 = Rs[u + 2], d = Rs[u + 3];
+                    z[i + 1] = fma(a.s, z0, a.c * carry);
+                    carry = fma(-a.s, carry, a.c * z0);
+                    z[i] = fma(b.s, z1, b.c * carry);
+                    carry = fma(-b.s, carry, b.c * z1);
+                    z[i - 1] = fma(c2.s, z2, c2.c * carry);
+                    carry = fma(-c2.s, carry, c2.c * z2);
+                    z[i - 2] = fma(d.s, z3, d.c * carry);
+                    carry = fma(-d.s, carry, d.c * z3);
+                }
+                for (; u < sw.len; ++u) {
+                    const int i = sw.hi - u;
+                    const double z0 = z[i];
+                    const Rot a = Rs[u];
+                    z[i + 1] = fma(a.s, z0, a.c * carry);
+                    carry = fma(-a.s, carry, a.c * z0);
+                }
+                z[sw.hi - sw.len + 1] = carry;
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nr * k; idx += blockDim.x) {
+    for (int idx = tid; idx < nr * k; idx += blockDim.x) {
         const int i = idx / nr, r = idx - i * nr;
         Out[(size_t)rank[i] * k + (r0 + r)] = zs[r * ldz + i];
     }
 }
 
 // implicit QL with Wilkinson shifts on the symmetric tridiagonal (d, e); rotations are recorded in application order
-bool tql_rotations(std::vector<double>& d, std::vector<double>& e, std::vector<Rot>& rots) {
+bool tql_rotations(std::vector<double>& d, std::vector<double>& e, std::vector<Rot>& rots, std::vector<Sweep>& sweeps) {
     const int n = (int)d.size();
     e.resize(n, 0.0);
     e[n - 1] = 0.0;
@@ -236,10 +320,14 @@ bool tql_rotations(std::vector<double>& d, std::vector<double>& e, std::vector<R
             g = d[m] - d[l] + e[l] / (g + std::copysign(r, g));
             double s = 1.0, c = 1.0, p = 0.0;
             int i = m - 1;
+            const int off0 = (int)rots.size();
             for (; i >= l; --i) {
                 double f = s * e[i];
                 const double b = c * e[i];
-                r = std::hypot(f, g);
+                // (plain sqrt: f and g are entries of a matrix of moderate norm -- the core was formed from
+                //  coefficients of unit-norm basis vectors -- so f*f + g*g neither overflows nor loses everything)
+                r = std::sqrt(f * f + g * g);
+                if (!(r > 1e-150) && r != 0.0) r = std::hypot(f, g);
                 e[i + 1] = r;
                 if (r == 0.0) {
                     d[i + 1] -= p;
@@ -253,7 +341,15 @@ bool tql_rotations(std::vector<double>& d, std::vector<double>& e, std::vector<R
                 p = s * r;
                 d[i + 1] = g + p;
                 g = c * r - b;
-                rots.push_back(Rot{c, s, i, 0});
+                rots.push_back(Rot{c, s});
+            }
+            // recorded in pieces that do not cross a tile of ROT_TILE rotations: a piece ends by storing the carried
+            // element, which is exactly what the next piece picks up as its first f
+            for (int o = off0, hi = m - 1, end = (int)rots.size(); o < end;) {
+                const int len = std::min(end - o, ROT_TILE - o % ROT_TILE);
+                sweeps.push_back(Sweep{o, hi, len, 0});
+                o += len;
+                hi -= len;
             }
             if (r == 0.0 && i >= l) continue;
             d[l] -= p;
@@ -310,34 +406,36 @@ int eig_sym(double* S, int k, double* d_evals, double* h_evals, double* work, vo
             return 1;
         if (k == 2 && cudaMemcpyAsync(e, S + 1, sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return 1;
     }
+    const bool dbg = getenv("DRE_EIG_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(now() - t0).count();
+    };
+    auto t_start = now();
+    double t_tri = 0.0, t_q = 0.0, t_ql = 0.0;
+    if (dbg) { cudaStreamSynchronize(st); t_tri = ms_since(t_start); }
     std::vector<double> hd(k), he(std::max(k - 1, 1), 0.0);
     if (cudaMemcpyAsync(hd.data(), d, k * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
     if (k > 1 && cudaMemcpyAsync(he.data(), e, (k - 1) * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
         return 1;
-    // explicit Q, queued before the host works on the tridiagonal
+    // explicit Q (transposed), queued before the host works on the tridiagonal
     {
-        const size_t smem = (size_t)k * sizeof(double);
-        static bool attr_dev[DRE_MAX_DEVICES] = {};
-        bool& attr = attr_dev[current_device()];
-        if (!attr && smem > 40 * 1024) {
-            cudaFuncSetAttribute(k_form_q, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr = true;
-        }
-        k_form_q<<<(k + 127) / 128, 128, smem, st>>>(Qm, k, Vst, tau);
+        const int blocks = (k * 32 + 255) / 256;
+        if (k <= 256) k_form_qt<8><<<blocks, 256, 0, st>>>(Qm, k, Vst, tau);
+        else if (k <= 512) k_form_qt<16><<<blocks, 256, 0, st>>>(Qm, k, Vst, tau);
+        else if (k <= 768) k_form_qt<24><<<blocks, 256, 0, st>>>(Qm, k, Vst, tau);
+        else if (k <= 1024) k_form_qt<32><<<blocks, 256, 0, st>>>(Qm, k, Vst, tau);
+        else k_form_qt_big<<<blocks, 256, 0, st>>>(Qm, k, Vst, tau);
         if (launches) *launches += 1;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    if (dbg) t_q = ms_since(t_start);
     std::vector<Rot> rots;
-    rots.reserve((size_t)k * k);
-    if (getenv("DRE_EIG_DEBUG")) {
-        int bad = 0;
-        double dmax = 0.0, emax = 0.0;
-        for (int i = 0; i < k; ++i) { if (!std::isfinite(hd[i])) ++bad; else dmax = std::max(dmax, std::fabs(hd[i])); }
-        for (int i = 0; i + 1 < k; ++i) { if (!std::isfinite(he[i])) ++bad; else emax = std::max(emax, std::fabs(he[i])); }
-        fprintf(stderr, "[dre eig] k %d non-finite %d max|d| %.3e max|e| %.3e d0 %.6e e0 %.6e\n", k, bad, dmax, emax, hd[0],
-                he[0]);
-    }
-    if (!tql_rotations(hd, he, rots)) return 2;
+    std::vector<Sweep> sweeps;
+    rots.reserve((size_t)k * k + 64);
+    sweeps.reserve((size_t)4 * k + 64);
+    if (!tql_rotations(hd, he, rots, sweeps)) return 2;
+    if (dbg) t_ql = ms_since(t_start);
     std::vector<int32_t> order(k), rank(k);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hd[a] < hd[b]; });
@@ -345,31 +443,52 @@ int eig_sym(double* S, int k, double* d_evals, double* h_evals, double* work, vo
         rank[order[j]] = j;
         h_evals[j] = hd[order[j]];
     }
-    const size_t rot_bytes = rots.size() * sizeof(Rot), rank_off = (rot_bytes + 63) & ~(size_t)63;
+    const int nrot = (int)rots.size(), ntiles = (nrot + ROT_TILE - 1) / ROT_TILE;
+    std::vector<int32_t> tile_first(ntiles + 1, 0);
+    {
+        int q = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            tile_first[t] = q;
+            while (q < (int)sweeps.size() && sweeps[q].off < (t + 1) * ROT_TILE) ++q;
+        }
+        tile_first[ntiles] = (int)sweeps.size();
+    }
+    const size_t rot_bytes = rots.size() * sizeof(Rot), sw_off = (rot_bytes + 63) & ~(size_t)63;
+    const size_t sw_bytes = sweeps.size() * sizeof(Sweep), tf_off = (sw_off + sw_bytes + 63) & ~(size_t)63;
+    const size_t tf_bytes = tile_first.size() * sizeof(int32_t), rank_off = (tf_off + tf_bytes + 63) & ~(size_t)63;
     char* dev = (char*)grow_rots(grow_ctx, rank_off + (size_t)k * sizeof(int32_t) + 64);
     if (!dev) return 1;
     if (!rots.empty() && cudaMemcpyAsync(dev, rots.data(), rot_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
+    if (!sweeps.empty() &&
+        cudaMemcpyAsync(dev + sw_off, sweeps.data(), sw_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return 1;
+    if (cudaMemcpyAsync(dev + tf_off, tile_first.data(), tf_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
     if (cudaMemcpyAsync(dev + rank_off, rank.data(), k * sizeof(int32_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
         return 1;
     if (cudaMemcpyAsync(d_evals, h_evals, k * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
     {
         const int ldz = k + 1 + ((k & 1) ? 1 : 0);
-        int rows = (int)std::min<size_t>(32, (200 * 1024) / ((size_t)ldz * sizeof(double)));
-        if (rows < 1) return 1;   // k > 25 000: not a "small core" any more
-        const size_t smem = (size_t)rows * ldz * sizeof(double);
+        const size_t tile_bytes = 2 * ROT_TILE * sizeof(Rot);
+        // the chains are latency bound and independent per row: few rows per CTA, so that they spread over many SMs
+        int rows = (int)std::min<size_t>(8, (200 * 1024 - tile_bytes - 16) / ((size_t)ldz * sizeof(double)));
+        if (rows < 1) return 1;   // k > 20 000: not a "small core" any more
+        const size_t smem = ((size_t)rows * ldz + 1) * sizeof(double) + tile_bytes;
         static size_t attr_dev[DRE_MAX_DEVICES] = {};
         size_t& attr = attr_dev[current_device()];
         if (smem > attr && smem > 40 * 1024) {
             cudaFuncSetAttribute(k_apply_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr = 200 * 1024;
         }
-        const int threads = std::max(32, ((rows + 31) / 32) * 32) * 4;   // extra warps for the tile load / store
-        k_apply_rot<<<(k + rows - 1) / rows, threads, smem, st>>>(Qm, k, (const Rot*)dev, (int)rots.size(),
-                                                                 (const int32_t*)(dev + rank_off), S, rows);
+        k_apply_rot<<<(k + rows - 1) / rows, 128, smem, st>>>(Qm, k, (const Rot*)dev, nrot, (const Sweep*)(dev + sw_off),
+                                                             (const int32_t*)(dev + tf_off), ntiles,
+                                                             (const int32_t*)(dev + rank_off), S, rows);
         if (launches) *launches += 1;
     }
     // the host vectors (rots, rank) must outlive the asynchronous uploads
     if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    if (dbg)
+        fprintf(stderr, "[dre eig] k %d: tridiag %.2f ms, +form Q %.2f, +host QL %.2f (%zu rotations, %zu sweeps), +apply %.2f\n",
+                k, t_tri, t_q - t_tri, t_ql - t_q, rots.size(), sweeps.size(), ms_since(t_start) - t_ql);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -191,3 +191,37 @@ def test_free_run_divergence_is_the_orth_knife_edge(n, nsteps):
         # so the iteration counts of converging solves may move by a step or two but not more
         for a, b in zip(ro.runs, rg.runs):
             assert abs(a["iters"] - b["iters"]) <= max(2, 0.1 * a["iters"]), (a["iters"], b["iters"])
+
+
+def test_config5_heat3d_gale_adi_and_newton_small():
+    """BASELINE config 5 at test size (3D heat pencil 14^3 = 2744 unknowns, 8 inputs / 8 outputs; the bench line
+    `bench.py --config 5` runs 60^3 and larger): standalone GALE ADI with a dense identity core
+    (test/tiny_random.jl:15-19) against the dense Lyapunov residual, lock-step against the oracle's ADI, and
+    Newton-ADI for the GARE (test/rail.jl:74-88: residual < reltol ||Q||)."""
+    import dre_b200
+
+    E, A, B, C, _ = dre_b200.pencils.heat3d_pencil(14)
+    q = C.shape[0]
+    ro, rg = Recorder(), Recorder()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Co = O.lowrank(np.asfortranarray(C.T), np.eye(q))
+        prob_o = O.GALEProblem(E, A, Co)
+        Xo = O.solve_gale(prob_o, O.ADI(), observer=ro)
+        Cg = api.lowrank(np.asfortranarray(C.T), np.eye(q))
+        adi = api.ADI(shifts=ForcedShifts([r["shifts"] for r in ro.runs]))
+        Xg = api.solve(api.GALEProblem(E, A, Cg), adi, observer=rg)
+    assert [r["iters"] for r in ro.runs] == [r["iters"] for r in rg.runs]
+    ra = np.array([x for _, x in ro.runs[0]["res"]])
+    rb = np.array([x for _, x in rg.runs[0]["res"]])
+    assert np.max(np.abs(ra - rb)) <= 1e-10 * O.norm(Co)
+    Xd = Xg.to_dense()
+    assert np.linalg.norm(O.gale_residual_dense(prob_o, Xd)) <= 1e-10 * O.norm(Co)
+    assert O.delta(Xd, Xo.to_dense()) <= 1e-9
+    reltol = 1e-10
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        are = api.GAREProblem(E, A, api.lowrank(B), api.lowrank(np.asfortranarray(C.T)))
+        Xn = api.solve(are, api.Newton(api.ADI(ignore_initial_guess=True), maxiters=10, reltol=reltol))
+    are_o = O.GAREProblem(E, A, O.lowrank(B), O.lowrank(np.asfortranarray(C.T)))
+    assert np.linalg.norm(O.gare_residual_dense(are_o, Xn.to_dense())) < reltol * O.norm(are_o.Q)
