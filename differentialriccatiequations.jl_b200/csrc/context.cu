@@ -215,9 +215,17 @@ struct dre_context {
         bool pending = false;        // queued by dre_prefactor and not yet adopted by a solve
         uint64_t queued_at = 0;      // value of solve_seq when dre_prefactor queued it (stale-slot reclamation)
         cudaStream_t st = nullptr;   // side stream of this slot (factorizations of different slots overlap)
+        // The launch sequence of a numeric factorization only depends on the pencil's symbolic structure: it is
+        // captured once per slot and scalar type ([0] real, [1] complex) as a CUDA graph and replayed for every shift;
+        // the two shift-dependent scalars travel through the device parameter block d_prm (k_set_prm).
+#ifndef DRE_SIMT_EMU
+        cudaGraphExec_t fgraph[2] = {nullptr, nullptr};
+#endif
+        double* d_prm = nullptr;
     };
     static constexpr int NSLOT = 4;  // the slot in use + up to three prefactorizations in flight
     FactorSlot slot[NSLOT];
+    int64_t factor_graph_nodes = 0;  // kernels in one captured factorization
     int cur = 0;
     uint64_t solve_seq = 0;          // block solves so far (acquire_factor calls)
     DBuf<unsigned char> tbuf;
@@ -467,6 +475,17 @@ inline DevSchedule dev_schedule(const dre_context* c) {
                        c->d_schur_items, c->d_fwd2_items, c->d_bwd2_items};
 }
 
+#ifndef DRE_SIMT_EMU
+static const bool g_graphs = !(getenv("DRE_GRAPHS") && atoi(getenv("DRE_GRAPHS")) == 0);
+#else
+static const bool g_graphs = false;
+#endif
+
+inline double re_of(double v) { return v; }
+inline double im_of(double) { return 0.0; }
+inline double re_of(cplx v) { return v.x; }
+inline double im_of(cplx v) { return v.y; }
+
 template <class T>
 int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) {
     const Symbolic& S = c->sym;
@@ -475,6 +494,39 @@ int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) 
     T* Linv = (T*)fs.Linv;
     T* dvec = (T*)fs.dvec;
     T* U = (T*)fs.U;
+#ifndef DRE_SIMT_EMU
+    if (g_graphs) {
+        const int gi = sizeof(T) == sizeof(double) ? 0 : 1;
+        if (!fs.d_prm) CU(cudaMalloc((void**)&fs.d_prm, 4 * sizeof(double)));
+        if (!fs.fgraph[gi]) {
+            // capture on a stream of its own (thread-local mode: the compression lane's thread may allocate meanwhile)
+            cudaStream_t cs = nullptr;
+            CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            int64_t nl = 0;
+            CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), cs);
+            enqueue_factor<T>(c->dS, dev_schedule(c), L, Linv, dvec, U, 0.0, zero<T>(), c->d_errflag, cs, &nl, c->sweep2,
+                              fs.d_prm);
+            cudaError_t e = cudaStreamEndCapture(cs, &g);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&fs.fgraph[gi], g, 0);
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            if (e != cudaSuccess) {
+                fs.fgraph[gi] = nullptr;
+                return fail(c, DRE_ERR_CUDA, std::string("factor graph capture: ") + cudaGetErrorString(e));
+            }
+            c->factor_graph_nodes = nl;
+        }
+        launch_set_prm(fs.d_prm, c->op_a, re_of(emu), im_of(emu), st, &c->stats.kernel_launches);
+        CU(cudaGraphLaunch(fs.fgraph[gi], st));
+        c->stats.kernel_launches += c->factor_graph_nodes;   // kernels inside the graph (memsets not counted)
+        c->stats.factorizations++;
+        c->stats.flops_factor += S.flops * (sizeof(T) == sizeof(double) ? 1.0 : 4.0);
+        return DRE_OK;
+    }
+#endif
     CU(cudaMemsetAsync(L, 0, (size_t)S.nnz_L * sizeof(T), st));
     enqueue_factor<T>(c->dS, dev_schedule(c), L, Linv, dvec, U, c->op_a, emu, c->d_errflag, st,
                       &c->stats.kernel_launches, c->sweep2);
@@ -1098,6 +1150,14 @@ static void release_pencil(dre_context* c) {
         if (fs.U) cudaFree(fs.U);
         fs.L = fs.Linv = fs.dvec = fs.U = nullptr;
         fs.valid = fs.has_reader = fs.pending = false;
+#ifndef DRE_SIMT_EMU
+        for (auto& g : fs.fgraph) {
+            if (g) cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+        if (fs.d_prm) cudaFree(fs.d_prm);
+        fs.d_prm = nullptr;
+#endif
     }
     c->cur = 0;
     c->has_pencil = false;

@@ -106,15 +106,18 @@ struct DevSymbolic {
 };
 
 template <class T>
-void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t st, int64_t* launches);
+void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t st, int64_t* launches,
+                     const double* prm = nullptr);
+void launch_set_prm(double* prm, double a, double re, double im, cudaStream_t st, int64_t* launches);
 // parents of one level gather their children's update matrices (grid.y = gy column classes)
 template <class T>
 void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparents, int gy, T* L, T* U,
                        cudaStream_t st, int64_t* launches);
+extern int diag_variant;      // launch_diag: 2 = k_diag2 (default), 1 = k_diag
 extern int diag_narrow_min;   // launch_diag: levels with >= this many supernodes use 64-thread CTAs
 // LDL^T of the s x s diagonal blocks of one level + inverse of the unit-lower factor (one CTA per supernode)
 template <class T>
-void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, T* L, T* Linv, T* dvec, int32_t* errflag,
+void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, T* L, T* Linv, T* dvec, int32_t* errflag,
                  cudaStream_t st, int64_t* launches);
 // L21 = A21 Linv' D^-1; items: (J, 64-row slab)
 template <class T>

@@ -110,14 +110,15 @@ struct DevSchedule {
 // m21: leave M21 = L21 Linv instead of L21 in the panels (what the row-split sweeps read).
 template <class T>
 inline void enqueue_factor(const DevSymbolic& dS, const DevSchedule& sch, T* L, T* Linv, T* dvec, T* U, double a, T emu,
-                           int32_t* errflag, cudaStream_t st, int64_t* launches, bool m21 = false) {
-    launch_assemble<T>(dS, L, a, emu, st, launches);
+                           int32_t* errflag, cudaStream_t st, int64_t* launches, bool m21 = false,
+                           const double* prm = nullptr) {
+    launch_assemble<T>(dS, L, a, emu, st, launches, prm);
     for (int l = 0; l < sch.nlevels; ++l) {
         const LevelWork& lw = sch.levels[l];
         if (lw.upd_size > 0) cudaMemsetAsync(U + lw.upd_off, 0, (size_t)lw.upd_size * sizeof(T), st);
         if (lw.ea_count > 0)
             launch_extend_add<T>(dS, sch.ea_parents + lw.ea_begin, lw.ea_count, lw.ea_gy, L, U, st, launches);
-        launch_diag<T>(dS, sch.level_sn + lw.sn_begin, lw.sn_count, L, Linv, dvec, errflag, st, launches);
+        launch_diag<T>(dS, sch.level_sn + lw.sn_begin, lw.sn_count, lw.smax, L, Linv, dvec, errflag, st, launches);
         if (lw.l21_count > 0) launch_l21<T>(dS, sch.l21_items + lw.l21_begin, lw.l21_count, L, Linv, dvec, st, launches);
         if (lw.schur_count > 0)
             launch_schur<T>(dS, sch.schur_items + lw.schur_begin, lw.schur_count, L, dvec, U, st, launches);

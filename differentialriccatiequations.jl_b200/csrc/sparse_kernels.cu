@@ -41,6 +41,8 @@ static int diag_narrow_min_default() {
     return ev ? std::max(1, atoi(ev)) : (1 << 30);
 }
 int diag_narrow_min = diag_narrow_min_default();
+// 2: k_diag2 (block column in shared memory, inverse built inside the elimination loop); 1: k_diag
+int diag_variant = (getenv("DRE_DIAG_V") && atoi(getenv("DRE_DIAG_V")) == 1) ? 1 : 2;
 
 __device__ __forceinline__ int sn_s(const DevSymbolic& S, int J) { return S.sn_first[J + 1] - S.sn_first[J]; }
 __device__ __forceinline__ int sn_u(const DevSymbolic& S, int J) { return (int)(S.sn_rowptr[J + 1] - S.sn_rowptr[J]); }
@@ -165,9 +167,20 @@ struct Blk32 {
 // ------------------------------------------------------------------------------------------
 // assembly: L[dest] = a*A + (e+mu)*E on the lower-triangular union pattern
 // ------------------------------------------------------------------------------------------
+// prm != nullptr: the two scalars come from a device parameter block {a, Re(e+mu), Im(e+mu)} written on the same stream
+// just before (k_set_prm), so that the launch sequence of a numeric factorization is shift-independent and can be
+// replayed as a CUDA graph.
+__device__ __forceinline__ void emu_from(const double* prm, double& out) { out = prm[1]; }
+__device__ __forceinline__ void emu_from(const double* prm, cplx& out) { out = mk(prm[1], prm[2]); }
+
 template <class T>
 __global__ void k_assemble(int64_t nasm, const int64_t* __restrict__ dest, const double* __restrict__ va,
-                           const double* __restrict__ ve, T* __restrict__ L, double a, T emu) {
+                           const double* __restrict__ ve, T* __restrict__ L, double a, T emu,
+                           const double* __restrict__ prm) {
+    if (prm) {
+        a = prm[0];
+        emu_from(prm, emu);
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nasm; i += (int64_t)gridDim.x * blockDim.x) {
         T v;
         from_real(a * va[i], v);
@@ -175,11 +188,24 @@ __global__ void k_assemble(int64_t nasm, const int64_t* __restrict__ dest, const
     }
 }
 
+__global__ void k_set_prm(double* prm, double a, double re, double im) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        prm[0] = a;
+        prm[1] = re;
+        prm[2] = im;
+    }
+}
+
+void launch_set_prm(double* prm, double a, double re, double im, cudaStream_t st, int64_t* launches) {
+    DRE_LAUNCH((k_set_prm), 1, 32, 0, st, prm, a, re, im);
+    if (launches) *launches += 1;
+}
+
 template <class T>
-void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t st, int64_t* launches) {
+void launch_assemble(const DevSymbolic& S, T* L, double a, T emu, cudaStream_t st, int64_t* launches, const double* prm) {
     int blocks = (int)std::min<int64_t>((S.nasm + 255) / 256, 148 * 8);
     if (blocks < 1) blocks = 1;
-    DRE_LAUNCH((k_assemble<T>), blocks, 256, 0, st, S.nasm, S.asm_dest, S.asm_a, S.asm_e, L, a, emu);
+    DRE_LAUNCH((k_assemble<T>), blocks, 256, 0, st, S.nasm, S.asm_dest, S.asm_a, S.asm_e, L, a, emu, prm);
     if (launches) *launches += 1;
 }
 
@@ -379,6 +405,147 @@ __global__ void __launch_bounds__(32 * NW) k_diag(DevSymbolic S, const int32_t* 
     }
 }
 
+// k_diag, second version (default; DRE_DIAG_V=1 selects the kernel above).  Same results in the same arrays.
+// What the first version spends its time on (ncu launch list, n = 79 841: 2.0 of the 3.2 ms of a factorization; a
+// 200-column supernode near the root takes 413 us on its own): every 32x32x32 block product fetches its operands
+// from global memory / L2 behind dependent loads, the inverse is finished by one serial chain of block products per
+// block column after the factorization, and only one warp in eight works during the 32x32 steps.  Here
+//  * the current block column (rows jb..s-1, 32 columns) lives in shared memory: the 32x32 LDL^T, its inverse, the
+//    solve of the rows below and BOTH operands of the trailing update are served from there;
+//  * the inverse is built row block by row block INSIDE the elimination loop,
+//        Linv[b][Jc] = -Linv[b][b] * sum_{K=Jc}^{b-1} L[b][K] Linv[K][Jc]      (all Jc < b are independent),
+//    as further work items of step b next to the trailing-update blocks, so it adds no chain of its own.
+template <class T, int NW>
+__global__ void __launch_bounds__(32 * NW) k_diag2(DevSymbolic S, const int32_t* __restrict__ sns, T* L, T* Linv, T* dvec,
+                                                   int32_t* errflag, int prow_cap) {
+    constexpr int LDP = NB + 4;   // fragment loads (8 rows x 4 columns per half warp) hit 16 different banks
+    DRE_DYN_SMEM_ALIGNED(unsigned char, dre_smem_raw);
+    T* Pn = reinterpret_cast<T*>(dre_smem_raw);   // [prow_cap][LDP]: block column b, rows jb .. s-1
+    T* Li = Pn + (size_t)prow_cap * LDP;          // [NB][LDP]: inverse of the unit-lower L_bb
+    T* dd = Li + NB * LDP;                        // [NB] pivots of block b, then [NB] their reciprocals
+    T* rd = dd + NB;
+    const int J = sns[blockIdx.x];
+    const int s = sn_s(S, J), f = s + sn_u(S, J);
+    T* P = L + S.panel_off[J];
+    T* LI = Linv + S.linv_off[J];
+    T* dv = dvec + S.sn_first[J];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbk = (s + NB - 1) / NB;
+    Blk32<T> blk;
+
+    for (int b = 0; b < nbk; ++b) {
+        const int jb = b * NB, nb = min(NB, s - jb);
+        const int mr = s - jb, mrb = (mr + NB - 1) / NB, mr32 = mrb * NB;
+        // (1) block column -> shared memory (identity padding in the diagonal block, zero rows below the supernode)
+        for (int idx = tid; idx < mr32 * NB; idx += 32 * NW) {
+            const int col = idx / mr32, row = idx - col * mr32;
+            T v = (row == col) ? one<T>() : zero<T>();
+            if (row < mr && col < nb && (row >= NB || col <= row)) v = P[(int64_t)(jb + row) + (int64_t)(jb + col) * f];
+            Pn[row * LDP + col] = v;
+        }
+        __syncthreads();
+        // (2) 32x32 LDL^T and the inverse of its unit-lower factor by one warp (lane i holds row i)
+        if (warp == 0) {
+            T a[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) a[c] = Pn[lane * LDP + c];
+            warp_ldlt32<T>(a, lane, errflag);
+#pragma unroll
+            for (int c = 0; c < NB; ++c) Pn[lane * LDP + c] = a[c];
+            __syncwarp();
+            T x[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                T v0 = zero<T>(), v1 = zero<T>();
+#pragma unroll
+                for (int k = 0; k + 1 < i; k += 2) {
+                    fma_acc(v0, Pn[i * LDP + k], x[k]);
+                    fma_acc(v1, Pn[i * LDP + k + 1], x[k + 1]);
+                }
+                if (i & 1) fma_acc(v0, Pn[i * LDP + i - 1], x[i - 1]);
+                x[i] = sub((i == lane) ? one<T>() : zero<T>(), add(v0, v1));
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) Li[i * LDP + lane] = x[i];
+            const T d = Pn[lane * LDP + lane];
+            dd[lane] = d;
+            rd[lane] = recip(d);
+        }
+        __syncthreads();
+        // (3) rows below: L_Ib = A_Ib Linv_bb' D_b^-1 (both operands in shared memory, in place)
+        for (int I = 1 + warp; I < mrb; I += NW) {
+            blk.clear();
+            blk.gemm(NB, lane, [&](int i, int k) { return Pn[(I * NB + i) * LDP + k]; },
+                     [&](int k, int j) { return Li[j * LDP + k]; });
+            __syncwarp();
+            blk.each(lane, [&](int i, int j, T v) { Pn[(I * NB + i) * LDP + j] = mul(v, rd[j]); });
+        }
+        __syncthreads();
+        // (4) the finished block column, the diagonal block of the inverse and the pivots go to global memory
+        for (int idx = tid; idx < mr32 * NB; idx += 32 * NW) {
+            const int col = idx / mr32, row = idx - col * mr32;
+            if (row < mr && col < nb && (row >= NB || col <= row))
+                P[(int64_t)(jb + row) + (int64_t)(jb + col) * f] = Pn[row * LDP + col];
+        }
+        for (int idx = tid; idx < NB * NB; idx += 32 * NW) {
+            const int c = idx / NB, i = idx - c * NB;
+            if (i < nb && c < nb) LI[(int64_t)(jb + i) + (int64_t)(jb + c) * s] = Li[i * LDP + c];
+        }
+        if (tid < nb) dv[jb + tid] = dd[tid];
+        // (5) work items of this step: trailing-update blocks (I, K), b < K <= I, and the blocks Jc < b of row block b
+        //     of the inverse
+        const int m = mrb - 1, npairs = m * (m + 1) / 2;
+        for (int p = warp; p < npairs + b; p += NW) {
+            if (p < npairs) {
+                int Ii = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
+                while ((Ii + 1) * (Ii + 2) / 2 <= p) ++Ii;
+                while (Ii * (Ii + 1) / 2 > p) --Ii;
+                const int Ki = p - Ii * (Ii + 1) / 2;
+                const int I = 1 + Ii, K = 1 + Ki;   // relative to block b
+                blk.clear();
+                blk.gemm(NB, lane, [&](int i, int k) { return Pn[(I * NB + i) * LDP + k]; },
+                         [&](int k, int j) { return mul(Pn[(K * NB + j) * LDP + k], dd[k]); });
+                blk.each(lane, [&](int i, int j, T v) {
+                    const int row = jb + I * NB + i, col = jb + K * NB + j;
+                    if (row < s && col < s) {
+                        T* t = P + ((int64_t)row + (int64_t)col * f);
+                        *t = sub(*t, v);
+                    }
+                });
+            } else {
+                const int Jc = p - npairs;
+                blk.clear();
+                for (int K = Jc; K < b; ++K)
+                    blk.gemm(NB, lane,
+                             [&](int i, int k) {
+                                 return (i < nb) ? P[(int64_t)(jb + i) + (int64_t)(K * NB + k) * f] : zero<T>();
+                             },
+                             [&](int k, int j) { return LI[(int64_t)(K * NB + k) + (int64_t)(Jc * NB + j) * s]; });
+                blk.each(lane, [&](int i, int j, T v) {
+                    if (i < nb) LI[(int64_t)(jb + i) + (int64_t)(Jc * NB + j) * s] = v;
+                });
+                __syncwarp();
+                blk.clear();
+                blk.gemm(NB, lane, [&](int i, int k) { return Li[i * LDP + k]; },
+                         [&](int k, int j) {
+                             return (k < nb) ? LI[(int64_t)(jb + k) + (int64_t)(Jc * NB + j) * s] : zero<T>();
+                         });
+                __syncwarp();
+                blk.each(lane, [&](int i, int j, T v) {
+                    if (i < nb) LI[(int64_t)(jb + i) + (int64_t)(Jc * NB + j) * s] = sub(zero<T>(), v);
+                });
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class T>
+static int diag2_smem(int smax) {
+    const int cap = (smax + NB - 1) / NB * NB;
+    return (int)sizeof(T) * ((cap + NB) * (NB + 4) + 2 * NB);
+}
+
 // L21 = A21 Linv' D^-1.  CTA = (supernode, 64-row slab of L21), warp = 8 rows x all s columns, computed in
 // place from the last column block to the first (block c only reads columns <= c of the warp's own rows).
 template <class T>
@@ -459,11 +626,23 @@ void launch_extend_add(const DevSymbolic& S, const int32_t* parents, int nparent
 }
 
 template <class T>
-void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, T* L, T* Linv, T* dvec, int32_t* errflag,
+void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, T* L, T* Linv, T* dvec, int32_t* errflag,
                  cudaStream_t st, int64_t* launches) {
     if (nsns <= 0) return;
-    if (nsns >= diag_narrow_min) DRE_LAUNCH((k_diag<T, 2>), nsns, 64, 0, st, S, sns, L, Linv, dvec, errflag);
-    else DRE_LAUNCH((k_diag<T, 8>), nsns, 256, 0, st, S, sns, L, Linv, dvec, errflag);
+    if (diag_variant == 2) {
+        static bool done[DRE_MAX_DEVICES] = {};
+        const int dev = current_device();
+        if (!done[dev]) {
+            cudaFuncSetAttribute(k_diag2<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag2_smem<T>(SN_MAX));
+            done[dev] = true;
+        }
+        DRE_LAUNCH((k_diag2<T, 8>), nsns, 256, (diag2_smem<T>(smax)), st, S, sns, L, Linv, dvec, errflag,
+                   (smax + NB - 1) / NB * NB);
+    } else if (nsns >= diag_narrow_min) {
+        DRE_LAUNCH((k_diag<T, 2>), nsns, 64, 0, st, S, sns, L, Linv, dvec, errflag);
+    } else {
+        DRE_LAUNCH((k_diag<T, 8>), nsns, 256, 0, st, S, sns, L, Linv, dvec, errflag);
+    }
     if (launches) *launches += 1;
 }
 
@@ -1227,10 +1406,10 @@ void launch_bwd2_level(const DevSymbolic& S, const int2* items, int nitems, int 
 
 // ---- explicit instantiations ----
 #define DRE_INST(T)                                                                                                  \
-    template void launch_assemble<T>(const DevSymbolic&, T*, double, T, cudaStream_t, int64_t*);                     \
+    template void launch_assemble<T>(const DevSymbolic&, T*, double, T, cudaStream_t, int64_t*, const double*);                     \
     template void launch_extend_add<T>(const DevSymbolic&, const int32_t*, int, int, T*, T*, cudaStream_t,           \
                                        int64_t*);                                                                    \
-    template void launch_diag<T>(const DevSymbolic&, const int32_t*, int, T*, T*, T*, int32_t*, cudaStream_t,        \
+    template void launch_diag<T>(const DevSymbolic&, const int32_t*, int, int, T*, T*, T*, int32_t*, cudaStream_t,        \
                                  int64_t*);                                                                          \
     template void launch_l21<T>(const DevSymbolic&, const int2*, int, T*, const T*, const T*, cudaStream_t,          \
                                 int64_t*);                                                                           \

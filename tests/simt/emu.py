@@ -174,6 +174,10 @@ def set_diag_narrow_min(v):
     lib().emu_set_diag_narrow_min(int(v))
 
 
+def set_diag_variant(v):
+    lib().emu_set_diag_variant(int(v))
+
+
 def set_spmm_variant(v):
     lib().emu_set_spmm_variant(int(v))
 

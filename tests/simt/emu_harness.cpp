@@ -221,6 +221,7 @@ EMU_API void emu_panel_transposes(double* panel, int64_t ldd, const double* cm, 
 
 // tuning knobs of the launchers (so that small test problems reach every kernel variant)
 EMU_API void emu_set_diag_narrow_min(int v) { dre::diag_narrow_min = v; }
+EMU_API void emu_set_diag_variant(int v) { dre::diag_variant = v; }
 EMU_API void emu_set_spmm_variant(int v) { dre::spmm_variant = v; }
 
 EMU_API void emu_counters(long* out) {

@@ -91,24 +91,36 @@ def test_emulated_row_split_sweeps(n, leaf, cap, nrhs):
 
 
 def test_emulated_narrow_diag_kernel():
-    """k_diag with 64-thread CTAs (DRE_DIAG_NARROW_MIN): same factor arrays as the 256-thread variant, bit for bit
-    (the work distribution over warps changes, the arithmetic of every block does not)."""
+    """k_diag (first version, DRE_DIAG_V=1) with 64-thread CTAs (DRE_DIAG_NARROW_MIN): same factor arrays as its
+    256-thread variant, bit for bit (the work distribution over warps changes, the arithmetic of every block does
+    not); the default k_diag2 (block column in shared memory, inverse built inside the elimination loop) agrees with
+    both to round-off, on chains of wide supernodes and on ragged last blocks."""
     n = 1357
     E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
-    S = emu.Solver(E, A, 96, 256)
-    try:
-        for mu in (-0.37, -0.02 + 0.11j):
+    for leaf, cap in ((96, 256), (40, 72)):
+        S = emu.Solver(E, A, leaf, cap)
+        try:
+            for mu in (-0.37, -0.02 + 0.11j):
+                emu.set_diag_variant(1)
+                emu.set_diag_narrow_min(1 << 30)
+                assert S.factor(1.0, mu) == 0
+                ref = [S.get(w).copy() for w in ("L", "Linv", "dvec")]
+                emu.set_diag_narrow_min(1)
+                assert S.factor(1.0, mu) == 0
+                for w, r in zip(("L", "Linv", "dvec"), ref):
+                    # (never-written entries above the diagonal blocks of Linv stay NaN-poisoned)
+                    assert np.array_equal(S.get(w), r, equal_nan=True), w
+                emu.set_diag_variant(2)
+                assert S.factor(1.0, mu) == 0
+                for w, r in zip(("L", "Linv", "dvec"), ref):
+                    got = S.get(w)
+                    assert np.array_equal(np.isnan(got), np.isnan(r)), w
+                    ok = ~np.isnan(r)
+                    assert np.max(np.abs(got[ok] - r[ok])) <= 1e-12 * np.max(np.abs(r[ok])), w
+        finally:
+            emu.set_diag_variant(2)
             emu.set_diag_narrow_min(1 << 30)
-            assert S.factor(1.0, mu) == 0
-            ref = [S.get(w).copy() for w in ("L", "Linv", "dvec")]
-            emu.set_diag_narrow_min(1)
-            assert S.factor(1.0, mu) == 0
-            for w, r in zip(("L", "Linv", "dvec"), ref):
-                # (never-written entries above the diagonal blocks of Linv stay NaN-poisoned)
-                assert np.array_equal(S.get(w), r, equal_nan=True), w
-    finally:
-        emu.set_diag_narrow_min(1 << 30)
-        S.close()
+            S.close()
 
 
 def test_emulated_sweeps_with_extra_rhs_panel():
