@@ -1207,7 +1207,8 @@ def _fused_inner(alg: ADI) -> bool:
     return isinstance(alg.inner_alg, (Backslash, ShermanMorrisonWoodbury))
 
 
-PREFACTOR_DEPTH = 3  # factorizations queued ahead of the ADI step in flight (the library keeps 4 factor slots)
+# factorizations queued ahead of the ADI step in flight (the library keeps 4 factor slots); DRE_PREFACTOR_DEPTH=0..3
+PREFACTOR_DEPTH = max(0, min(3, int(_os.environ.get("DRE_PREFACTOR_DEPTH", "3"))))
 
 
 def _prefetch_next_factorization(cache: ADICache):

@@ -358,6 +358,47 @@ int check_errflag(dre_context* c) {
 static const bool g_trace = getenv("DRE_TRACE") != nullptr;
 // DRE_RR_STATS=1: totals of the rank-revealing Gram-Schmidt rounds, printed when a context dies
 static const bool g_rr_stats = getenv("DRE_RR_STATS") != nullptr;
+// DRE_TIMELINE=<file>: device-side timeline of the streams (events recorded around the launch groups, resolved against
+// a base event when the context dies; no synchronisation while the job runs).  Lines: "<ms begin> <ms end> <lane> <name>",
+// lane 0 = main stream, 1..4 = factor slots' side streams, 5 = look-ahead / norm streams.
+#ifndef DRE_SIMT_EMU
+static const char* g_timeline = getenv("DRE_TIMELINE");
+struct TlSpan { const char* name; int lane; cudaEvent_t e0, e1; };
+static std::vector<TlSpan> g_tl;
+static cudaEvent_t g_tl_base = nullptr;
+struct TlScope {
+    cudaStream_t st; size_t idx = (size_t)-1;
+    TlScope(const char* name, int lane, cudaStream_t s) : st(s) {
+        if (!g_timeline || g_tl.size() > 400000) return;
+        if (!g_tl_base) { cudaEventCreate(&g_tl_base); cudaEventRecord(g_tl_base, s); }
+        TlSpan sp{name, lane, nullptr, nullptr};
+        cudaEventCreate(&sp.e0); cudaEventCreate(&sp.e1);
+        cudaEventRecord(sp.e0, s);
+        idx = g_tl.size();
+        g_tl.push_back(sp);
+    }
+    ~TlScope() { if (idx != (size_t)-1) cudaEventRecord(g_tl[idx].e1, st); }
+};
+static void tl_dump() {
+    if (!g_timeline || g_tl.empty()) return;
+    cudaDeviceSynchronize();
+    FILE* f = fopen(g_timeline, "w");
+    if (!f) return;
+    for (auto& sp : g_tl) {
+        float a = 0, b = 0;
+        if (cudaEventElapsedTime(&a, g_tl_base, sp.e0) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&b, g_tl_base, sp.e1) != cudaSuccess) continue;
+        fprintf(f, "%.4f %.4f %d %s\n", a, b, sp.lane, sp.name);
+        cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1);
+    }
+    fclose(f);
+    g_tl.clear();
+}
+#else
+struct TlScope { TlScope(const char*, int, cudaStream_t) {} };
+static void tl_dump() {}
+#endif
+
 struct RRTotals {
     long calls = 0, blocks = 0, rounds = 0, productive = 0, skipped = 0, syncs = 0, rest_projections = 0,
          coef_only_passes = 0;
@@ -490,6 +531,7 @@ template <class T>
 int factor(dre_context* c, dre_context::FactorSlot& fs, cudaStream_t st, T emu) {
     const Symbolic& S = c->sym;
     Timer t(c, &c->stats.ms_factor);
+    TlScope tl(sizeof(T) == 8 ? "factor" : "factor(cplx)", st == c->st ? 0 : 1 + (int)(&fs - c->slot), st);
     T* L = (T*)fs.L;
     T* Linv = (T*)fs.Linv;
     T* dvec = (T*)fs.dvec;
@@ -540,6 +582,7 @@ template <class T>
 int solve_sweeps(dre_context* c, T* W, int64_t ldw, int nrhs, const RhsSource& src) {
     const Symbolic& S = c->sym;
     Timer t(c, &c->stats.ms_solve);
+    TlScope tl("sweeps", 0, c->st);
     {
         HostTrace tr("tbuf.ensure");
         CU(c->tbuf.ensure((size_t)std::max<int64_t>(S.rhs_total, 1) * ldw * sizeof(T)));
@@ -1174,6 +1217,7 @@ int32_t dre_destroy(dre_context* c) {
     if (!c) return DRE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
+    tl_dump();
     c->arena.destroy();
     release_pencil(c);
     for_each_workspace(c, [](auto& w) { w.forget(); });   // the arena (destroyed above) owned their memory
@@ -1342,6 +1386,7 @@ int32_t dre_mat_free(dre_context* c, int32_t id) {
 
 int32_t dre_mat_upload(dre_context* c, dre_view dst, const double* host, int64_t ld) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    TlScope tl_api("upload", 0, c ? c->st : nullptr);
     if (c->dense_only) return fail(c, DRE_ERR_STATE, "dense-only context: no row permutation to upload through");
     int rc;
     if ((rc = check_view(c, dst, "dst", true))) return rc;
@@ -1360,6 +1405,7 @@ int32_t dre_mat_upload(dre_context* c, dre_view dst, const double* host, int64_t
 
 int32_t dre_mat_download(dre_context* c, dre_view src, double* host, int64_t ld) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    TlScope tl_api("download", 0, c ? c->st : nullptr);
     if (c->dense_only) return fail(c, DRE_ERR_STATE, "dense-only context: no row permutation to download through");
     int rc;
     if ((rc = check_view(c, src, "src", true))) return rc;
@@ -1378,6 +1424,7 @@ int32_t dre_mat_download(dre_context* c, dre_view src, double* host, int64_t ld)
 
 int32_t dre_mat_copy(dre_context* c, dre_view dst, dre_view src) {
     if (c) cudaSetDevice(c->device);   // may be the first CUDA call of a host thread (compression lane)
+    TlScope tl_api("mat_copy", 0, c ? c->st : nullptr);
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     int rc;
     if ((rc = check_view(c, dst, "dst", true)) || (rc = check_view(c, src, "src", true))) return rc;
@@ -1392,6 +1439,7 @@ int32_t dre_mat_copy(dre_context* c, dre_view dst, dre_view src) {
 
 int32_t dre_mat_axpby(dre_context* c, double alpha, dre_view X, double beta, dre_view Y) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    TlScope tl_api("axpby", 0, c ? c->st : nullptr);
     int rc;
     if ((rc = check_view(c, Y, "Y", true))) return rc;
     if (Y.ncols == 0) return DRE_OK;
@@ -1417,6 +1465,7 @@ int32_t dre_spmm(dre_context* c, int32_t op, double alpha, dre_view X, double be
     const double* val = (op == 'E' || op == 'e') ? c->d_csr_e : (op == 'A' || op == 'a') ? c->d_csr_a : nullptr;
     if (!val) return fail(c, DRE_ERR_ARG, "spmm: op must be 'E' or 'A'");
     Timer t(c, &c->stats.ms_spmm);
+    TlScope tl("spmm", 0, c->st);
     launch_spmm(c->d_csr_ptr, c->d_csr_col, val, c->sym.n, alpha, vptr(c, X), vld(c, X), beta, vptr(c, Y), vld(c, Y),
                 X.ncols, c->st, &c->stats.kernel_launches);
     CU(cudaGetLastError());
@@ -1428,6 +1477,7 @@ int32_t dre_spmm(dre_context* c, int32_t op, double alpha, dre_view X, double be
 
 int32_t dre_gemm_tn(dre_context* c, dre_view X, dre_view Y, double* out, int64_t ld) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    TlScope tl_api("gemm_tn", 0, c ? c->st : nullptr);
     int rc;
     if ((rc = check_view(c, X, "X", true)) || (rc = check_view(c, Y, "Y", true))) return rc;
     const int a = X.ncols, b = Y.ncols;
@@ -1447,6 +1497,7 @@ int32_t dre_gemm_tn(dre_context* c, dre_view X, dre_view Y, double* out, int64_t
 
 int32_t dre_gemm_nn(dre_context* c, double alpha, dre_view X, const double* W, int64_t ldw, double beta, dre_view Y) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    TlScope tl_api("gemm_nn", 0, c ? c->st : nullptr);
     int rc;
     if ((rc = check_view(c, X, "X", true)) || (rc = check_view(c, Y, "Y", true))) return rc;
     const int a = X.ncols, b = Y.ncols;
@@ -1580,6 +1631,7 @@ int32_t dre_ldlt_norm(dre_context* c, dre_view L, const double* D, int64_t ldd, 
     if (k == 0) { *out = 0.0; return DRE_OK; }
     if (!D || ldd < k) return fail(c, DRE_ERR_ARG, "norm: bad core matrix");
     Range r_norm("norm(::LDLt)");
+    TlScope tl("norm", 0, c->st);
     bool diag = true;
     for (int j = 0; j < k && diag; ++j)
         for (int i = 0; i < k; ++i)
@@ -1741,6 +1793,7 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
         ktot += Ls[t].ncols;
     }
     if ((rc = check_view(c, out, "out", true))) return rc;
+    TlScope tl("compress", 0, c->st);
     *newrank = 0;
     if (ktot == 0) return DRE_OK;
     const int64_t n = c->sym.n;
@@ -1899,6 +1952,7 @@ int32_t dre_hint_orthonormal(dre_context* c, dre_view v) {
 int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double drop_rel, double drop_abs, dre_view Q,
                  double* Rt, int64_t ldr, int32_t* rho_out) {
     if (!c || !views || !rho_out) return fail(c, DRE_ERR_ARG, "null argument");
+    TlScope tl_api("rrqr", 0, c ? c->st : nullptr);
     if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
     int rc;
     int ktot = 0;
@@ -1938,8 +1992,13 @@ int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double d
 
 int32_t dre_debug_export(dre_context* c, const char* what, void* buf, int64_t cap_bytes, int64_t* len_bytes) {
     if (!c || !what || !len_bytes) return fail(c, DRE_ERR_ARG, "null argument");
-    if (!c->has_pencil || !c->slot[c->cur].valid) return fail(c, DRE_ERR_STATE, "no numeric factorization held");
     const std::string w(what);
+    if (w == "timeline") {   // DRE_TIMELINE=<file>: resolve and write the recorded spans now
+        tl_dump();
+        *len_bytes = 0;
+        return DRE_OK;
+    }
+    if (!c->has_pencil || !c->slot[c->cur].valid) return fail(c, DRE_ERR_STATE, "no numeric factorization held");
     const dre_context::FactorSlot& fs = c->slot[c->cur];
     const size_t tw = (size_t)fs.tw * sizeof(double);
     const void* src = nullptr;

@@ -43,6 +43,8 @@ static int diag_narrow_min_default() {
 int diag_narrow_min = diag_narrow_min_default();
 // 2: k_diag2 (block column in shared memory, inverse built inside the elimination loop); 1: k_diag
 int diag_variant = (getenv("DRE_DIAG_V") && atoi(getenv("DRE_DIAG_V")) == 1) ? 1 : 2;
+// thread-block cluster of 4 CTAs per supernode on the levels with few fat supernodes (DRE_DIAG_CLUSTER=0: off)
+int diag_cluster = (getenv("DRE_DIAG_CLUSTER") && atoi(getenv("DRE_DIAG_CLUSTER")) == 0) ? 1 : 4;
 
 __device__ __forceinline__ int sn_s(const DevSymbolic& S, int J) { return S.sn_first[J + 1] - S.sn_first[J]; }
 __device__ __forceinline__ int sn_u(const DevSymbolic& S, int J) { return (int)(S.sn_rowptr[J + 1] - S.sn_rowptr[J]); }
@@ -150,6 +152,44 @@ struct Blk32 {
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt) MM<T>::mma(acc[mt][nt], a[mt], b, lane);
             }
+        }
+    }
+    // The same product for operands that come from global memory / L2: the fragments of the next two k-steps are in
+    // flight while the current one feeds the tensor cores (gemm() above issues the eight loads of a k-step and then
+    // waits a full L2 latency for them: ~3 us per 32x32x32 product, against ~1.3 us with shared-memory operands).
+    template <class FA, class FB>
+    __device__ __forceinline__ void gemm_stream(int K, int lane, FA fa, FB fb) {
+        const int kk = lane & 3, r = lane >> 2, bc = MM<T>::bcol(lane);
+        T a[3][4], b[3][NTW];
+        auto load = [&](int slot, int k0) {
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) a[slot][mt] = fa(mt * 8 + r, k0 + kk);
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) b[slot][nt] = fb(k0 + kk, nt * MM<T>::CPN + bc);
+        };
+        auto mma_slot = [&](int slot) {
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) MM<T>::mma(acc[mt][nt], a[slot][mt], b[slot][nt], lane);
+        };
+        if (K <= 0) return;
+        load(0, 0);
+        if (K > 4) load(1, 4);
+        int k0 = 0;
+        for (; k0 + 12 <= K; k0 += 12) {   // slots rotate 0,1,2 (fully unrolled so that they stay in registers)
+            if (k0 + 8 < K) load(2, k0 + 8);
+            mma_slot(0);
+            if (k0 + 12 < K) load(0, k0 + 12);
+            mma_slot(1);
+            if (k0 + 16 < K) load(1, k0 + 16);
+            mma_slot(2);
+        }
+        if (k0 < K) {
+            if (k0 + 8 < K) load(2, k0 + 8);
+            mma_slot(0);
+            if (k0 + 4 < K) mma_slot(1);
+            if (k0 + 8 < K) mma_slot(2);
         }
     }
     // f(i, j, value) for every element of the block held by this lane
@@ -405,6 +445,74 @@ __global__ void __launch_bounds__(32 * NW) k_diag(DevSymbolic S, const int32_t* 
     }
 }
 
+// LDL^T of a 32x32 block held in shared memory (row i at A + i*LDA, LDA odd: lane-strided accesses are conflict
+// free), by one warp, lane i = row i.  No register arrays: the register version above (warp_ldlt32) is compiled
+// into a rolled loop over a LOCAL-memory copy of the row (ptxas keeps the dynamically indexed array in local memory:
+// LDL -> DFMA -> STL per update), which made the 32x32 step ~50 us.  The reciprocal of the NEXT pivot is started
+// right after the one update it depends on, so its latency hides behind the remaining updates of the column.
+// On exit: strictly lower part = unit-lower factor, diagonal = pivots, rdiag[i] = 1 / pivot i.
+template <class T, int LDA>
+__device__ __forceinline__ void warp_ldlt32_smem(T* A, T* rdiag, int lane, int32_t* errflag) {
+    T d = A[0];
+    if (lane == 0 && is_bad(d)) atomicExch(errflag, 1);
+    T rdv = recip(d);
+    for (int j = 0; j < NB; ++j) {
+        const T w = A[lane * LDA + j];          // unscaled column entry of this row (rows > j use it)
+        const T l = mul(w, rdv);
+        if (lane == j) rdiag[j] = rdv;
+        T rdn = rdv;
+        if (j + 1 < NB) {
+            // the update that the next pivot waits for
+            const T wk = A[(j + 1) * LDA + j];
+            if (lane >= j + 1) A[lane * LDA + j + 1] = sub(A[lane * LDA + j + 1], mul(l, wk));
+            __syncwarp();
+            const T dn = A[(j + 1) * LDA + j + 1];
+            if (lane == j + 1 && is_bad(dn)) atomicExch(errflag, 1);
+            rdn = recip(dn);
+            // remaining columns in groups of eight: all loads of a group are issued before its first store (the
+            // compiler keeps shared-memory loads behind earlier stores; element by element the loop ran one
+            // LDS -> DFMA -> STS latency chain per entry)
+            for (int k0 = j + 2; k0 < NB; k0 += 8) {
+                T wk2[8], av[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = k0 + q;
+                    wk2[q] = (k < NB) ? A[k * LDA + j] : zero<T>();
+                    av[q] = (k < NB && lane >= k) ? A[lane * LDA + k] : zero<T>();
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = k0 + q;
+                    if (k < NB && lane >= k) A[lane * LDA + k] = sub(av[q], mul(l, wk2[q]));
+                }
+            }
+        }
+        __syncwarp();
+        if (lane > j) A[lane * LDA + j] = l;
+        rdv = rdn;
+    }
+    __syncwarp();
+}
+
+// X = inverse of the unit-lower factor held in A (as left by warp_ldlt32_smem); X row i at X + i*LDX.
+// Lane c owns column c: X[i][c] = delta_ic - sum_{k<i} L[i][k] X[k][c]; every lane only reads back what it wrote.
+template <class T, int LDA, int LDX>
+__device__ __forceinline__ void warp_trinv32_smem(const T* A, T* X, int lane) {
+    for (int i = 0; i < NB; ++i) {
+        T v0 = zero<T>(), v1 = zero<T>(), v2 = zero<T>(), v3 = zero<T>();
+        int k = 0;
+        for (; k + 4 <= i; k += 4) {
+            fma_acc(v0, A[i * LDA + k], X[k * LDX + lane]);
+            fma_acc(v1, A[i * LDA + k + 1], X[(k + 1) * LDX + lane]);
+            fma_acc(v2, A[i * LDA + k + 2], X[(k + 2) * LDX + lane]);
+            fma_acc(v3, A[i * LDA + k + 3], X[(k + 3) * LDX + lane]);
+        }
+        for (; k < i; ++k) fma_acc(v0, A[i * LDA + k], X[k * LDX + lane]);
+        X[i * LDX + lane] = sub((i == lane) ? one<T>() : zero<T>(), add(add(v0, v1), add(v2, v3)));
+    }
+    __syncwarp();
+}
+
 // k_diag, second version (default; DRE_DIAG_V=1 selects the kernel above).  Same results in the same arrays.
 // What the first version spends its time on (ncu launch list, n = 79 841: 2.0 of the 3.2 ms of a factorization; a
 // 200-column supernode near the root takes 413 us on its own): every 32x32x32 block product fetches its operands
@@ -415,16 +523,83 @@ __global__ void __launch_bounds__(32 * NW) k_diag(DevSymbolic S, const int32_t* 
 //  * the inverse is built row block by row block INSIDE the elimination loop,
 //        Linv[b][Jc] = -Linv[b][b] * sum_{K=Jc}^{b-1} L[b][K] Linv[K][Jc]      (all Jc < b are independent),
 //    as further work items of step b next to the trailing-update blocks, so it adds no chain of its own.
-template <class T, int NW>
-__global__ void __launch_bounds__(32 * NW) k_diag2(DevSymbolic S, const int32_t* __restrict__ sns, T* L, T* Linv, T* dvec,
-                                                   int32_t* errflag, int prow_cap) {
+// LDL^T of a 32x32 block AND the inverse of its unit-lower factor by the whole CTA (NW warps): lane = row i, warp g owns
+// the columns k = g (mod NW).  One barrier per column; per column every thread updates at most 32/NW entries of its row
+// of A and of X (Gauss-Jordan: X <- (I - l_j e_j') X), all independent.  A single warp doing the same (warp_ldlt32_smem
+// + warp_trinv32_smem) issues ~9000 dependent instructions per block (~30 us measured, 45 % of k_diag2 on the fat
+// supernodes); here the chain per column is  pivot -> reciprocal -> l -> update -> barrier.
+// A: [NB][LDA] (strictly lower <- unit-lower factor, diagonal <- pivots);  X: [NB][LDX];  rdiag[NB] <- 1 / pivot.
+template <class T, int NW, int LDA, int LDX>
+__device__ __forceinline__ void cta_ldlt32_inv(T* A, T* X, T* rdiag, int lane, int warp, int32_t* errflag) {
+    constexpr int CPW = NB / NW;   // columns per warp
+    for (int q = 0; q < CPW; ++q) {
+        const int c = warp + q * NW;
+        X[lane * LDX + c] = (lane == c) ? one<T>() : zero<T>();
+    }
+    __syncthreads();
+    for (int j = 0; j < NB; ++j) {
+        const T d = A[j * LDA + j];
+        if (warp == 0 && lane == j && is_bad(d)) atomicExch(errflag, 1);
+        const T rdv = recip(d);
+        const T l = mul(A[lane * LDA + j], rdv);   // rows > j use it
+        T wk[CPW], av[CPW], xj[CPW], xv[CPW];
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            const int k = warp + q * NW;
+            const bool ua = k > j && lane >= k, ux = k <= j && lane > j;
+            wk[q] = ua ? A[k * LDA + j] : zero<T>();
+            av[q] = ua ? A[lane * LDA + k] : zero<T>();
+            xj[q] = ux ? X[j * LDX + k] : zero<T>();
+            xv[q] = ux ? X[lane * LDX + k] : zero<T>();
+        }
+        // (column j keeps its UNSCALED entries until the end of the loop, so nothing a slower thread still reads in
+        // this column is overwritten here: one barrier per column)
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            const int k = warp + q * NW;
+            if (k > j && lane >= k) A[lane * LDA + k] = sub(av[q], mul(l, wk[q]));
+            if (k <= j && lane > j) X[lane * LDX + k] = sub(xv[q], mul(l, xj[q]));
+        }
+        if (warp == (j % NW) && lane == j) rdiag[j] = rdv;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < CPW; ++q) {
+        const int k = warp + q * NW;
+        if (lane > k) A[lane * LDA + k] = mul(A[lane * LDA + k], rdiag[k]);
+    }
+    __syncthreads();
+}
+
+// cluster-wide barrier with release / acquire semantics (global-memory writes of the other CTAs become visible)
+template <int CL>
+__device__ __forceinline__ void diag_step_barrier() {
+#ifndef DRE_SIMT_EMU
+    if (CL > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        return;
+    }
+#endif
+    __syncthreads();
+}
+
+// CL = CTAs per supernode (a thread-block cluster): every CTA of the cluster keeps its own copy of the block column and
+// repeats the (cheap) 32x32 step and the solve of the rows below; the block products of the trailing update and of the
+// inverse -- the bulk of the work, FP64-pipe bound on ONE SM for the fat supernodes near the root -- are dealt out over
+// all warps of the cluster.  Only the CTAs exchange data through global memory (L2) behind the cluster barrier.
+template <class T, int NW, int MINB, int CL>
+__global__ void __launch_bounds__(32 * NW, MINB) k_diag2(DevSymbolic S, const int32_t* __restrict__ sns, T* L, T* Linv, T* dvec,
+                                                         int32_t* errflag, int prow_cap) {
     constexpr int LDP = NB + 4;   // fragment loads (8 rows x 4 columns per half warp) hit 16 different banks
     DRE_DYN_SMEM_ALIGNED(unsigned char, dre_smem_raw);
     T* Pn = reinterpret_cast<T*>(dre_smem_raw);   // [prow_cap][LDP]: block column b, rows jb .. s-1
-    T* Li = Pn + (size_t)prow_cap * LDP;          // [NB][LDP]: inverse of the unit-lower L_bb
-    T* dd = Li + NB * LDP;                        // [NB] pivots of block b, then [NB] their reciprocals
+    T* Li0 = Pn + (size_t)prow_cap * LDP;         // 2 x [NB][LDP]: inverse of the unit-lower L_bb (steps b, b-1)
+    T* dd = Li0 + 2 * NB * LDP;                   // [NB] pivots of block b, then [NB] their reciprocals
     T* rd = dd + NB;
-    const int J = sns[blockIdx.x];
+    constexpr int LDD = NB + 1;
+    T* Ds = rd + NB;                              // [NB][LDD]: the diagonal block while one warp factors it
+    const int J = sns[blockIdx.x / CL];
+    const int crank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;
     const int s = sn_s(S, J), f = s + sn_u(S, J);
     T* P = L + S.panel_off[J];
     T* LI = Linv + S.linv_off[J];
@@ -433,44 +608,58 @@ __global__ void __launch_bounds__(32 * NW) k_diag2(DevSymbolic S, const int32_t*
     const int nbk = (s + NB - 1) / NB;
     Blk32<T> blk;
 
+    // block Jc of row block rb of the inverse: Linv[rb][Jc] = -Linv[rb][rb] sum_{K=Jc}^{rb-1} L[rb][K] Linv[K][Jc]
+    auto inverse_item = [&](int rb, int Jc, const T* Lirb) {
+        const int jr = rb * NB, nr = min(NB, s - jr);
+        blk.clear();
+        {
+            const T* Arow = P + jr + (int64_t)(Jc * NB) * f;            // L[rb][Jc ..], k-th column at + k*f
+            const T* Bcol = LI + Jc * NB + (int64_t)(Jc * NB) * s;      // Linv[Jc ..][Jc], k-th row at + k
+            blk.gemm_stream((rb - Jc) * NB, lane,
+                            [&](int i, int k) { return (i < nr) ? Arow[i + (int64_t)k * f] : zero<T>(); },
+                            [&](int k, int j) { return Bcol[k + (int64_t)j * s]; });
+        }
+        blk.each(lane, [&](int i, int j, T v) {
+            if (i < nr) LI[(int64_t)(jr + i) + (int64_t)(Jc * NB + j) * s] = v;
+        });
+        __syncwarp();
+        blk.clear();
+        blk.gemm(NB, lane, [&](int i, int k) { return Lirb[i * LDP + k]; },
+                 [&](int k, int j) { return (k < nr) ? LI[(int64_t)(jr + k) + (int64_t)(Jc * NB + j) * s] : zero<T>(); });
+        __syncwarp();
+        blk.each(lane, [&](int i, int j, T v) {
+            if (i < nr) LI[(int64_t)(jr + i) + (int64_t)(Jc * NB + j) * s] = sub(zero<T>(), v);
+        });
+    };
+
     for (int b = 0; b < nbk; ++b) {
         const int jb = b * NB, nb = min(NB, s - jb);
         const int mr = s - jb, mrb = (mr + NB - 1) / NB, mr32 = mrb * NB;
+        T* Li = Li0 + (b & 1) * NB * LDP;
         // (1) block column -> shared memory (identity padding in the diagonal block, zero rows below the supernode)
-        for (int idx = tid; idx < mr32 * NB; idx += 32 * NW) {
-            const int col = idx / mr32, row = idx - col * mr32;
-            T v = (row == col) ? one<T>() : zero<T>();
-            if (row < mr && col < nb && (row >= NB || col <= row)) v = P[(int64_t)(jb + row) + (int64_t)(jb + col) * f];
-            Pn[row * LDP + col] = v;
+        for (int col = warp; col < NB; col += NW) {
+            const T* Pc = P + (int64_t)jb + (int64_t)(jb + col) * f;
+            for (int row0 = lane; row0 < mr32; row0 += 32 * 8) {   // eight loads in flight before the first store
+                T v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int row = row0 + 32 * q;
+                    v[q] = (row == col) ? one<T>() : zero<T>();
+                    if (row < mr && col < nb && (row >= NB || col <= row)) v[q] = Pc[row];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int row = row0 + 32 * q;
+                    if (row < mr32) Pn[row * LDP + col] = v[q];
+                }
+            }
         }
         __syncthreads();
-        // (2) 32x32 LDL^T and the inverse of its unit-lower factor by one warp (lane i holds row i)
-        if (warp == 0) {
-            T a[NB];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) a[c] = Pn[lane * LDP + c];
-            warp_ldlt32<T>(a, lane, errflag);
-#pragma unroll
-            for (int c = 0; c < NB; ++c) Pn[lane * LDP + c] = a[c];
-            __syncwarp();
-            T x[NB];
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                T v0 = zero<T>(), v1 = zero<T>();
-#pragma unroll
-                for (int k = 0; k + 1 < i; k += 2) {
-                    fma_acc(v0, Pn[i * LDP + k], x[k]);
-                    fma_acc(v1, Pn[i * LDP + k + 1], x[k + 1]);
-                }
-                if (i & 1) fma_acc(v0, Pn[i * LDP + i - 1], x[i - 1]);
-                x[i] = sub((i == lane) ? one<T>() : zero<T>(), add(v0, v1));
-            }
-#pragma unroll
-            for (int i = 0; i < NB; ++i) Li[i * LDP + lane] = x[i];
-            const T d = Pn[lane * LDP + lane];
-            dd[lane] = d;
-            rd[lane] = recip(d);
-        }
+        // (2) 32x32 LDL^T and the inverse of its unit-lower factor by the whole CTA, in shared memory
+        for (int r = warp; r < NB; r += NW) Ds[r * LDD + lane] = Pn[r * LDP + lane];
+        __syncthreads();
+        cta_ldlt32_inv<T, NW, LDD, LDP>(Ds, Li, rd, lane, warp, errflag);
+        if (warp == 0) dd[lane] = Ds[lane * LDD + lane];
         __syncthreads();
         // (3) rows below: L_Ib = A_Ib Linv_bb' D_b^-1 (both operands in shared memory, in place)
         for (int I = 1 + warp; I < mrb; I += NW) {
@@ -482,68 +671,56 @@ __global__ void __launch_bounds__(32 * NW) k_diag2(DevSymbolic S, const int32_t*
         }
         __syncthreads();
         // (4) the finished block column, the diagonal block of the inverse and the pivots go to global memory
-        for (int idx = tid; idx < mr32 * NB; idx += 32 * NW) {
-            const int col = idx / mr32, row = idx - col * mr32;
-            if (row < mr && col < nb && (row >= NB || col <= row))
-                P[(int64_t)(jb + row) + (int64_t)(jb + col) * f] = Pn[row * LDP + col];
-        }
-        for (int idx = tid; idx < NB * NB; idx += 32 * NW) {
-            const int c = idx / NB, i = idx - c * NB;
-            if (i < nb && c < nb) LI[(int64_t)(jb + i) + (int64_t)(jb + c) * s] = Li[i * LDP + c];
-        }
-        if (tid < nb) dv[jb + tid] = dd[tid];
-        // (5) work items of this step: trailing-update blocks (I, K), b < K <= I, and the blocks Jc < b of row block b
-        //     of the inverse
-        const int m = mrb - 1, npairs = m * (m + 1) / 2;
-        for (int p = warp; p < npairs + b; p += NW) {
-            if (p < npairs) {
-                int Ii = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
-                while ((Ii + 1) * (Ii + 2) / 2 <= p) ++Ii;
-                while (Ii * (Ii + 1) / 2 > p) --Ii;
-                const int Ki = p - Ii * (Ii + 1) / 2;
-                const int I = 1 + Ii, K = 1 + Ki;   // relative to block b
-                blk.clear();
-                blk.gemm(NB, lane, [&](int i, int k) { return Pn[(I * NB + i) * LDP + k]; },
-                         [&](int k, int j) { return mul(Pn[(K * NB + j) * LDP + k], dd[k]); });
-                blk.each(lane, [&](int i, int j, T v) {
-                    const int row = jb + I * NB + i, col = jb + K * NB + j;
-                    if (row < s && col < s) {
-                        T* t = P + ((int64_t)row + (int64_t)col * f);
-                        *t = sub(*t, v);
-                    }
-                });
-            } else {
-                const int Jc = p - npairs;
-                blk.clear();
-                for (int K = Jc; K < b; ++K)
-                    blk.gemm(NB, lane,
-                             [&](int i, int k) {
-                                 return (i < nb) ? P[(int64_t)(jb + i) + (int64_t)(K * NB + k) * f] : zero<T>();
-                             },
-                             [&](int k, int j) { return LI[(int64_t)(K * NB + k) + (int64_t)(Jc * NB + j) * s]; });
-                blk.each(lane, [&](int i, int j, T v) {
-                    if (i < nb) LI[(int64_t)(jb + i) + (int64_t)(Jc * NB + j) * s] = v;
-                });
-                __syncwarp();
-                blk.clear();
-                blk.gemm(NB, lane, [&](int i, int k) { return Li[i * LDP + k]; },
-                         [&](int k, int j) {
-                             return (k < nb) ? LI[(int64_t)(jb + k) + (int64_t)(Jc * NB + j) * s] : zero<T>();
-                         });
-                __syncwarp();
-                blk.each(lane, [&](int i, int j, T v) {
-                    if (i < nb) LI[(int64_t)(jb + i) + (int64_t)(Jc * NB + j) * s] = sub(zero<T>(), v);
-                });
+        if (crank == 0) {
+            for (int col = warp; col < nb; col += NW) {
+                T* Pc = P + (int64_t)jb + (int64_t)(jb + col) * f;
+                for (int row = lane; row < mr; row += 32)
+                    if (row >= NB || col <= row) Pc[row] = (row < NB) ? Ds[row * LDD + col] : Pn[row * LDP + col];
+                if (lane < nb) LI[(int64_t)(jb + lane) + (int64_t)(jb + col) * s] = Li[lane * LDP + col];
             }
+            if (tid < nb) dv[jb + tid] = dd[tid];
         }
-        __syncthreads();
+        // (5) work items of this step, dealt out over the warps of the cluster: trailing-update blocks (I, K),
+        //     b < K <= I, and the blocks Jc < b-1 of row block b-1 of the inverse (one step behind: they need nothing
+        //     of step b, and their longest item balances the shrinking trailing update)
+        const int m = mrb - 1, npairs = m * (m + 1) / 2;
+        const int ninv = b >= 2 ? b - 1 : 0;
+        const T* Liprev = Li0 + ((b - 1) & 1) * NB * LDP;
+        for (int p = crank * NW + warp; p < npairs + ninv; p += CL * NW) {
+            if (p < ninv) {   // (the long items first)
+                inverse_item(b - 1, p, Liprev);
+                continue;
+            }
+            const int pp = p - ninv;
+            int Ii = (int)((sqrtf(8.0f * pp + 1.0f) - 1.0f) * 0.5f);
+            while ((Ii + 1) * (Ii + 2) / 2 <= pp) ++Ii;
+            while (Ii * (Ii + 1) / 2 > pp) --Ii;
+            const int Ki = pp - Ii * (Ii + 1) / 2;
+            const int I = 1 + Ii, K = 1 + Ki;   // relative to block b
+            blk.clear();
+            blk.gemm(NB, lane, [&](int i, int k) { return Pn[(I * NB + i) * LDP + k]; },
+                     [&](int k, int j) { return mul(Pn[(K * NB + j) * LDP + k], dd[k]); });
+            blk.each(lane, [&](int i, int j, T v) {
+                const int row = jb + I * NB + i, col = jb + K * NB + j;
+                if (row < s && col < s) {
+                    T* t = P + ((int64_t)row + (int64_t)col * f);
+                    *t = sub(*t, v);
+                }
+            });
+        }
+        diag_step_barrier<CL>();
+    }
+    // row block nbk-1 of the inverse
+    if (nbk >= 2) {
+        const T* Lilast = Li0 + ((nbk - 1) & 1) * NB * LDP;
+        for (int Jc = crank * NW + warp; Jc < nbk - 1; Jc += CL * NW) inverse_item(nbk - 1, Jc, Lilast);
     }
 }
 
 template <class T>
 static int diag2_smem(int smax) {
     const int cap = (smax + NB - 1) / NB * NB;
-    return (int)sizeof(T) * ((cap + NB) * (NB + 4) + 2 * NB);
+    return (int)sizeof(T) * ((cap + 2 * NB) * (NB + 4) + 2 * NB + NB * (NB + 1));
 }
 
 // L21 = A21 Linv' D^-1.  CTA = (supernode, 64-row slab of L21), warp = 8 rows x all s columns, computed in
@@ -630,14 +807,46 @@ void launch_diag(const DevSymbolic& S, const int32_t* sns, int nsns, int smax, T
                  cudaStream_t st, int64_t* launches) {
     if (nsns <= 0) return;
     if (diag_variant == 2) {
+        // real: 128 registers (2 x 256 or 4 x 128 threads per SM); complex: 255 registers (1 x 256 or 2 x 128).
+        // Populous levels (the 1024 leaves) take 128-thread CTAs: the 32x32 steps of a supernode are serial work of
+        // one warp, so what counts there is how many supernodes an SM holds at once.  Levels with a handful of fat
+        // supernodes (near the root) give each supernode a cluster of 4 CTAs.
+        constexpr int MB8 = sizeof(T) == sizeof(double) ? 2 : 1, MB4 = 2 * MB8;
         static bool done[DRE_MAX_DEVICES] = {};
         const int dev = current_device();
         if (!done[dev]) {
-            cudaFuncSetAttribute(k_diag2<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag2_smem<T>(SN_MAX));
+            cudaFuncSetAttribute(k_diag2<T, 8, MB8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag2_smem<T>(SN_MAX));
+            cudaFuncSetAttribute(k_diag2<T, 4, MB4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag2_smem<T>(SN_MAX));
+#ifndef DRE_SIMT_EMU
+            cudaFuncSetAttribute(k_diag2<T, 8, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag2_smem<T>(SN_MAX));
+#endif
             done[dev] = true;
         }
-        DRE_LAUNCH((k_diag2<T, 8>), nsns, 256, (diag2_smem<T>(smax)), st, S, sns, L, Linv, dvec, errflag,
-                   (smax + NB - 1) / NB * NB);
+        const int cap = (smax + NB - 1) / NB * NB;
+        bool launched = false;
+#ifndef DRE_SIMT_EMU
+        if (diag_cluster > 1 && nsns * 4 <= 148 && smax > 2 * NB) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(nsns * 4);
+            cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = diag2_smem<T>(smax);
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            launched = cudaLaunchKernelEx(&cfg, k_diag2<T, 8, 1, 4>, S, sns, L, Linv, dvec, errflag, cap) == cudaSuccess;
+            if (!launched) cudaGetLastError();
+        }
+#endif
+        if (launched) {
+        } else if (nsns >= 2 * 148)
+            DRE_LAUNCH((k_diag2<T, 4, MB4, 1>), nsns, 128, (diag2_smem<T>(smax)), st, S, sns, L, Linv, dvec, errflag, cap);
+        else
+            DRE_LAUNCH((k_diag2<T, 8, MB8, 1>), nsns, 256, (diag2_smem<T>(smax)), st, S, sns, L, Linv, dvec, errflag, cap);
     } else if (nsns >= diag_narrow_min) {
         DRE_LAUNCH((k_diag<T, 2>), nsns, 64, 0, st, S, sns, L, Linv, dvec, errflag);
     } else {

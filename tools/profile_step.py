@@ -33,3 +33,7 @@ be.ctx.sync()
 _rt.cudaProfilerStop()
 print("PROFILE_REGION_END %.3f s for %d iterations; residual cols %d, rank X %d" % (time.perf_counter() - t0, iters, cache.residual.Ls[0].ncols, cache.X.rank()), flush=True)
 print(be.ctx.stats())
+import os
+if os.environ.get("DRE_TIMELINE"):   # device-side timeline of the streams (context.cu: TlScope)
+    ln = ctypes.c_int64()
+    be.lib.dre_debug_export(be.h, b"timeline", None, 0, ctypes.byref(ln))
