@@ -1001,21 +1001,21 @@ def _take_many(gen):
 
 
 def _arnoldi_ritz(op, b0, k, desc):
-    """heuristic.jl:103-130 -- Arnoldi with twice-repeated MGS on host vectors; ``op`` runs on the GPU."""
-    n = len(b0)
+    """heuristic.jl:103-130 -- Arnoldi with twice-repeated MGS.  The Krylov basis lives in ONE device panel
+    (n x (k+1)); ``op`` maps a device column to a device column (SpMM + shifted solve); every orthogonalisation
+    step is one ``dre_arnoldi_orth`` call (chain of dot/update launches, k+2 doubles back).  Only H is on the host,
+    like the reference keeps it (``H = zeros(k + 1, k)``)."""
+    be = backend()
     H = np.zeros((k + 1, k))
-    V = np.zeros((n, k + 1))
-    V[:, 0] = (1.0 / np.linalg.norm(b0)) * b0
+    V = DeviceMatrix.empty(k + 1)
+    v0 = np.asfortranarray(((1.0 / np.linalg.norm(b0)) * np.asarray(b0, dtype=np.float64)).reshape(-1, 1))
+    be.check(be.lib.dre_mat_upload(be.h, V.cols(0, 1).view, capi._dptr(v0), v0.shape[0]))
+    h = np.zeros(k + 2)
     for j in range(k):
-        w = np.array(op(V[:, j]), dtype=float).reshape(n)
-        for _ in range(2):
-            for i in range(j + 1):
-                g = float(V[:, i] @ w)
-                H[i, j] += g
-                w -= V[:, i] * g
-        beta = float(np.linalg.norm(w))
-        H[j + 1, j] = beta
-        V[:, j + 1] = (1.0 / beta) * w
+        w = op(V.cols(j, j + 1))
+        be.check(be.lib.dre_arnoldi_orth(be.h, V.cols(0, j + 1).view, w.view, V.cols(j + 1, j + 2).view,
+                                         capi._dptr(h)))
+        H[:j + 2, j] = h[:j + 2]
     ritz = sla.eigvals(H[:k, :k])
     if np.all(np.imag(ritz) == 0):
         ritz = np.real(ritz)
@@ -1031,13 +1031,11 @@ def shifts_init(strategy, prob):
         n = backend().n
         b0 = np.ones(n)  # heuristic.jl:75-80
 
-        def op_plus(x):  # E \ (A x)
-            Ax = _matmul(A, DeviceMatrix.from_host(x))
-            return solve_block(BlockLinearProblem(E, Ax), strategy.alg_E).to_host()[:, 0]
+        def op_plus(x):  # E \ (A x), device column -> device column
+            return solve_block(BlockLinearProblem(E, _matmul(A, x)), strategy.alg_E)
 
         def op_minus(x):  # A \ (E x)
-            Ex = _matmul(E, DeviceMatrix.from_host(x))
-            return solve_block(BlockLinearProblem(A, Ex), strategy.alg_A).to_host()[:, 0]
+            return solve_block(BlockLinearProblem(A, _matmul(E, x)), strategy.alg_A)
 
         R_plus = _arnoldi_ritz(op_plus, b0, strategy.k_plus, "E^-1 A")
         R_minus = _arnoldi_ritz(op_minus, b0, strategy.k_minus, "A^-1 E")

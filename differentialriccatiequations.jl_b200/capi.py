@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "dre_mat_create", "dre_mat_free", "dre_mat_upload", "dre_mat_download", "dre_mat_copy", "dre_mat_axpby",
     "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_prefactor", "dre_shift_solve", "dre_adi_step", "dre_adi_solve", "dre_mat_devptr", "dre_get_stream", "dre_set_dense_only", "dre_mat_wrap",
     "dre_ldlt_norm", "dre_ldlt_norm_begin", "dre_ldlt_norm_end", "dre_ldlt_compress", "dre_hint_orthonormal", "dre_rrqr", "dre_debug_export", "dre_debug_eigh", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
-    "dre_stats_get",
+    "dre_stats_get", "dre_arnoldi_orth",
 ]
 
 
@@ -92,6 +92,7 @@ def load():
     lib.dre_mat_download.argtypes = [p, View, pdbl, i64]
     lib.dre_mat_copy.argtypes = [p, View, View]
     lib.dre_mat_axpby.argtypes = [p, dbl, View, dbl, View]
+    lib.dre_arnoldi_orth.argtypes = [p, View, View, View, pdbl]
     lib.dre_spmm.argtypes = [p, i32, dbl, View, dbl, View]
     lib.dre_gemm_tn.argtypes = [p, View, View, pdbl, i64]
     lib.dre_gemm_nn.argtypes = [p, dbl, View, pdbl, i64, dbl, View]

@@ -522,6 +522,21 @@ static const bool g_graphs = !(getenv("DRE_GRAPHS") && atoi(getenv("DRE_GRAPHS")
 static const bool g_graphs = false;
 #endif
 
+// Stream priorities (DRE_PRIO=1, opt-in until measured): the ADI chain (main stream) runs at the highest priority, the
+// prefactor side streams one step below, a compression lane (dre_set_dense_only) and the look-ahead stage at the
+// lowest -- the block scheduler then hands a freed SM to the waiting CTA of the latency-bound chain instead of the
+// next CTA of a Gram kernel that was launched earlier.  level: 0 highest, 1 middle, 2 lowest.
+static const bool g_prio = getenv("DRE_PRIO") && atoi(getenv("DRE_PRIO")) != 0;
+static cudaError_t make_stream(cudaStream_t* s, int level) {
+    if (!g_prio) return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+    int least = 0, greatest = 0;   // numerically: greatest priority <= least priority
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (e != cudaSuccess) return e;
+    int pr = greatest + level * std::max(1, (least - greatest) / 2);
+    if (pr > least) pr = least;
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, pr);
+}
+
 inline double re_of(double v) { return v; }
 inline double im_of(double) { return 0.0; }
 inline double re_of(cplx v) { return v.x; }
@@ -826,7 +841,7 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
     const bool look = look_env && nch > 1 && !c->timing && !g_trace;
     int rc;
     if (!c->look_st) {
-        CU(cudaStreamCreateWithFlags(&c->look_st, cudaStreamNonBlocking));
+        CU(make_stream(&c->look_st, c->dense_only ? 2 : 1));
         for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&c->look_done[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->look_basis, cudaEventDisableTiming));
         CU(cudaMallocHost((void**)&c->h_look, 4 * PBIG * sizeof(double)));
@@ -1151,10 +1166,10 @@ int32_t dre_create(int32_t device, dre_context** out) {
         ev = getenv("DRE_DIAG_NARROW_MIN");
         diag_narrow_min = ev ? std::max(1, atoi(ev)) : (1 << 30);
     }
-    e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    e = make_stream(&c->st, 0);
     if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     for (auto& fs : c->slot) {
-        e = cudaStreamCreateWithFlags(&fs.st, cudaStreamNonBlocking);
+        e = make_stream(&fs.st, 1);
         if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
         cudaEventCreateWithFlags(&fs.ready, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&fs.released, cudaEventDisableTiming);
@@ -1453,6 +1468,41 @@ int32_t dre_mat_axpby(dre_context* c, double alpha, dre_view X, double beta, dre
     return DRE_OK;
 }
 
+// ---- Heuristic shifts: one Arnoldi orthogonalisation step on device-resident vectors (heuristic.jl:111-125) ----
+int32_t dre_arnoldi_orth(dre_context* c, dre_view V, dre_view w, dre_view vnext, double* h) {
+    if (!c || !h) return fail(c, DRE_ERR_ARG, "null argument");
+    TlScope tl_api("arnoldi_orth", 0, c->st);
+    int rc;
+    if ((rc = check_view(c, V, "V")) || (rc = check_view(c, w, "w", true)) || (rc = check_view(c, vnext, "vnext", true)))
+        return rc;
+    if (V.ncols < 1 || w.ncols != 1 || vnext.ncols != 1)
+        return fail(c, DRE_ERR_ARG, "arnoldi_orth: V needs >= 1 column, w and vnext exactly one");
+    if (views_overlap(V, w) || views_overlap(V, vnext) || views_overlap(w, vnext))
+        return fail(c, DRE_ERR_ARG, "arnoldi_orth: views overlap");
+    if (c->norm_pending) return fail(c, DRE_ERR_STATE, "arnoldi_orth: an asynchronous norm is pending (shared scratch)");
+    const int nb = V.ncols, ncoef = 2 * nb + 1;
+    CU(c->norm_small.ensure((size_t)2 * 296 + ncoef + 8));
+    if ((size_t)ncoef + 4 > c->h_norm_cap) {
+        if (c->h_norm) cudaFreeHost(c->h_norm);
+        c->h_norm = nullptr;
+        c->h_norm_cap = 0;
+        CU(cudaMallocHost((void**)&c->h_norm, ((size_t)ncoef + 4 + 256) * sizeof(double)));
+        c->h_norm_cap = (size_t)ncoef + 4 + 256;
+    }
+    double* part = c->norm_small.p;
+    double* coef = c->norm_small.p + 2 * 296;
+    launch_arnoldi_mgs(vptr(c, V), vld(c, V), nb, vptr(c, w), vld(c, w), vptr(c, vnext), vld(c, vnext), c->sym.n, part,
+                       coef, c->st, &c->stats.kernel_launches);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_norm, coef, ncoef * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < nb; ++i) h[i] = (0.0 + c->h_norm[i]) + c->h_norm[nb + i];   // H[i,j] += g, twice
+    h[nb] = c->h_norm[2 * nb];
+    if (!(h[nb] > 0.0) || !std::isfinite(h[nb]))
+        return fail(c, DRE_ERR_NUMERIC, "arnoldi_orth: the Krylov space is exhausted (zero or non-finite remainder)");
+    return DRE_OK;
+}
+
 // ---- products ----
 int32_t dre_spmm(dre_context* c, int32_t op, double alpha, dre_view X, double beta, dre_view Y) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
@@ -1577,6 +1627,13 @@ int32_t dre_set_dense_only(dre_context* c, int64_t n) {
     c->levels.clear();
     c->has_pencil = true;   // panels and the dense toolbox work; the sparse entry points find an empty schedule
     c->dense_only = true;
+    if (g_prio) {   // a lane yields to the ADI chain of the main context
+        cudaStream_t low = nullptr;
+        CU(make_stream(&low, 2));
+        cudaStreamDestroy(c->st);
+        c->st = low;
+        if (c->look_st) { cudaStreamDestroy(c->look_st); c->look_st = nullptr; CU(make_stream(&c->look_st, 2)); }
+    }
     return DRE_OK;
 }
 
@@ -1684,7 +1741,7 @@ int32_t dre_ldlt_norm_begin(dre_context* c, dre_view L, const double* d, double 
     if (c->norm_pending) return fail(c, DRE_ERR_STATE, "norm_begin: the previous asynchronous norm was not collected");
     const int k = L.ncols;
     if (!c->norm_st) {
-        CU(cudaStreamCreateWithFlags(&c->norm_st, cudaStreamNonBlocking));
+        CU(make_stream(&c->norm_st, 0));
         CU(cudaEventCreateWithFlags(&c->norm_in, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->norm_done, cudaEventDisableTiming));
     }

@@ -390,12 +390,15 @@ GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
     int tiles = ((a + G2A - 1) / G2A) * ((b + tbw - 1) / tbw);   // pipelined kernel: 64 x 128 (64 x 64) output tiles
     if (tiles < 1) tiles = 1;
     int64_t chunks = (n + GK - 1) / GK;
-    int want = std::max(1, (2 * sm_count) / tiles);   // at most 2 CTAs per SM: ONE full wave (19 x 16 tiles = 304 CTAs
-                                                      // on 296 slots was measured at twice the time of 18 x 16)
+    // DRE_GRAM_WAVES=w (default 1): w waves of shorter CTAs -- only useful together with stream priorities (DRE_PRIO),
+    // where a low-priority Gram kernel should give SMs back to the ADI chain every few tens of microseconds
+    static const int waves = std::max(1, getenv("DRE_GRAM_WAVES") ? atoi(getenv("DRE_GRAM_WAVES")) : 1);
+    int want = std::max(1, (2 * sm_count * waves) / tiles);   // at most 2 CTAs per SM: ONE full wave (19 x 16 tiles = 304
+                                                      // CTAs on 296 slots was measured at twice the time of 18 x 16)
     if (a <= 16 && b >= 64) want = std::max(1, 8 * sm_count / ((b + 255) / 256));  // skinny kernel: thread per column
     int64_t maxsplit = std::max<int64_t>(1, chunks / 8);          // at least 8 chunks (128 rows) per split
     int nsplit = (int)std::min<int64_t>(want, maxsplit);
-    nsplit = std::min(nsplit, (a <= 16 && b >= 64) ? 1184 : 320);   // skinny kernel: bytes in flight need many CTAs
+    nsplit = std::min(nsplit, (a <= 16 && b >= 64) ? 1184 : 320 * waves);   // skinny kernel: bytes in flight need many CTAs
     int64_t cps = (chunks + nsplit - 1) / nsplit;
     p.rows_per_split = cps * GK;
     p.nsplit = (int)((n + p.rows_per_split - 1) / p.rows_per_split);
@@ -701,6 +704,86 @@ void launch_axpby(double alpha, const double* X, int64_t ldx, double beta, doubl
     int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
     DRE_LAUNCH((k_axpby), blocks, 256, 0, st, alpha, X, ldx, beta, Y, ldy, n, cols);
     if (launches) *launches += 1;
+}
+
+// ---- Arnoldi step of the Heuristic shift strategy (heuristic.jl:111-125) on device-resident vectors ----
+// The twice-repeated modified Gram-Schmidt sweep is a chain of 2(j+1) dependent dot products / updates on n-vectors.
+// One launch per link: stage s first applies the update of the previous link, w -= g_{s-1} v_{s-1} (g_{s-1} is rebuilt by
+// every CTA from the previous stage's per-CTA partial sums, in one fixed order, so all CTAs subtract the same number),
+// then forms its partial of v_s . w (last stage: of w . w).  No host round trip inside the sweep; the coefficients are
+// collected with one copy at the end.  Basis columns are strided (row-major panel) but the whole basis sits in L2.
+constexpr int MGS_MAXB = 296;
+__device__ __forceinline__ double mgs_sum_partials(const double* part, int nb, double* sh) {
+    // warp 0: lane l adds part[l], part[l+32], ... in order, then a shuffle tree; result broadcast through sh[0]
+    if (threadIdx.x < 32) {
+        double a = 0.0;
+        for (int i = threadIdx.x; i < nb; i += 32) a += part[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+        if (threadIdx.x == 0) sh[0] = a;
+    }
+    __syncthreads();
+    const double g = sh[0];
+    __syncthreads();
+    return g;
+}
+
+__global__ void __launch_bounds__(256) k_mgs_stage(const double* __restrict__ V, int64_t ldv, int ci_prev, int ci,
+                                                   double* __restrict__ w, int64_t ldw, int64_t n,
+                                                   const double* __restrict__ part_prev, int nb_prev,
+                                                   double* __restrict__ part, double* __restrict__ g_out) {
+    __shared__ double sh[8];
+    double g = 0.0;
+    if (ci_prev >= 0) {
+        g = mgs_sum_partials(part_prev, nb_prev, sh);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *g_out = g;
+    }
+    double acc = 0.0;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        double wr = w[r * ldw];
+        if (ci_prev >= 0) {
+            wr -= V[r * ldv + ci_prev] * g;
+            w[r * ldw] = wr;
+        }
+        acc = fma(ci >= 0 ? V[r * ldv + ci] : wr, wr, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += sh[i];
+        part[blockIdx.x] = a;
+    }
+}
+
+// beta = ||w|| from the partials of the last stage; v_next = (1/beta) w  (heuristic.jl:123-124)
+__global__ void __launch_bounds__(256) k_mgs_finish(const double* __restrict__ w, int64_t ldw, double* __restrict__ vn,
+                                                    int64_t ldvn, int64_t n, const double* __restrict__ part_prev,
+                                                    int nb_prev, double* __restrict__ beta_out) {
+    __shared__ double sh[8];
+    const double beta = sqrt(mgs_sum_partials(part_prev, nb_prev, sh));
+    if (blockIdx.x == 0 && threadIdx.x == 0) *beta_out = beta;
+    const double inv = 1.0 / beta;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        vn[r * ldvn] = inv * w[r * ldw];
+}
+
+void launch_arnoldi_mgs(const double* V, int64_t ldv, int nbasis, double* w, int64_t ldw, double* vnext, int64_t ldvn,
+                        int64_t n, double* partials, double* coef, cudaStream_t st, int64_t* launches) {
+    // partials: 2 * MGS_MAXB doubles (ping-pong); coef: 2 * nbasis + 1 doubles (g of every link in order, then beta)
+    const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, MGS_MAXB));
+    const int links = 2 * nbasis;
+    for (int s = 0; s <= links; ++s) {
+        const int ci = s < links ? s % nbasis : -1;
+        const int cp = s > 0 ? (s - 1) % nbasis : -1;
+        DRE_LAUNCH((k_mgs_stage), nb, 256, 0, st, V, ldv, cp, ci, w, ldw, n, partials + ((s + 1) & 1) * MGS_MAXB, nb,
+                   partials + (s & 1) * MGS_MAXB, coef + (s > 0 ? s - 1 : 0));
+    }
+    DRE_LAUNCH((k_mgs_finish), nb, 256, 0, st, w, ldw, vnext, ldvn, n, partials + (links & 1) * MGS_MAXB, nb,
+               coef + links);
+    if (launches) *launches += links + 2;
 }
 
 // column-major staging (original row order) <-> row-major panel (solver row order), 32x32 smem transpose

@@ -37,6 +37,11 @@ void launch_colnorm2(const double* P, int64_t ldp, int64_t n, int cols, double* 
 void launch_combine_cols(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, int cols,
                          const int32_t* idx2, const double* w1, const double* w2, cudaStream_t st, int64_t* launches);
 // Y = alpha*X + beta*Y
+// Arnoldi step of the Heuristic shifts (heuristic.jl:111-125): twice-repeated MGS of w against V[:, 0:nbasis] and
+// vnext = w / ||w||, all on device; coef receives the 2*nbasis projection coefficients in order and then ||w||.
+// partials: scratch of 2 * 296 doubles.
+void launch_arnoldi_mgs(const double* V, int64_t ldv, int nbasis, double* w, int64_t ldw, double* vnext, int64_t ldvn,
+                        int64_t n, double* partials, double* coef, cudaStream_t st, int64_t* launches);
 void launch_axpby(double alpha, const double* X, int64_t ldx, double beta, double* Y, int64_t ldy, int64_t n,
                   int cols, cudaStream_t st, int64_t* launches);
 // gather/scatter rows with permutation + transpose between host-style column-major staging and row-major panels

@@ -114,6 +114,14 @@ DRE_API int32_t dre_get_stream(dre_context* ctx, void** stream);
 /* Y = alpha*X + beta*Y (X may be an empty view when alpha == 0) */
 DRE_API int32_t dre_mat_axpby(dre_context* ctx, double alpha, dre_view X, double beta, dre_view Y);
 
+/* ---- Heuristic shifts on device ----
+ * One Arnoldi step of compute_ritz_values (src/shifts/heuristic.jl:111-125) on device-resident vectors: the
+ * twice-repeated modified Gram-Schmidt of w (n x 1, on entry the operator applied to the last basis vector; on exit
+ * the unnormalised remainder) against the basis V (n x (j+1)), then vnext = (1/||w||) * w.  h receives the j+2
+ * entries H[0..j, j] (sum of both sweeps, accumulated as the reference does) and H[j+1, j] = ||w||.  Synchronises
+ * (j+2 doubles D2H).  DRE_ERR_NUMERIC when the remainder vanishes. */
+DRE_API int32_t dre_arnoldi_orth(dre_context* ctx, dre_view V, dre_view w, dre_view vnext, double* h);
+
 /* ---- products ----
  * op: 'E' or 'A' (the pencil is symmetric, so E' L / A' L of src/lyapunov/residual.jl:18,
  * lowrank_ros1.jl:42 use the same kernels).  Y = alpha*op*X + beta*Y.   */

@@ -481,6 +481,31 @@ DRE.Stuff.restrict(P::PencilOp{<:Real}, Q::DeviceMatrix) = Q' * (P * Q)
 # restrict(::LowRankUpdate, Q) (util/restrict.jl:5-8) is generic: Q'U -> (U'Q)' and V*Q are the products above
 Base.:*(Qt::Adjoint{Float64,DeviceMatrix}, U::Adjoint{Float64,Matrix{Float64}}) = Qt * Matrix(U)
 
+# ---- Heuristic shifts with device-resident Arnoldi vectors  (shifts/heuristic.jl:39-130) ----
+# init(::Heuristic, prob) stays the reference's.  arnoldi_b0 puts the start vector on the device, the operator closures
+# (mul!(rhs(solver), A, x); solve!(solver)) go through spmm! / SolverState above, and compute_ritz_values keeps the
+# Krylov basis in ONE n x (k+1) panel: each step's twice-repeated MGS sweep and the normalisation are one
+# dre_arnoldi_orth call (chain of dot/update launches on the stream, k+2 doubles back); H stays on the host.
+DRE.Shifts.arnoldi_b0(E::PencilOp) = DeviceMatrix(E.ctx, reshape(ones(Float64, size(E, 2)), :, 1))
+function DRE.Shifts.compute_ritz_values(A, b0::DeviceMatrix, k::Int, desc::String)
+    ctx = b0.p.ctx
+    H = zeros(k + 1, k)
+    V = DeviceMatrix(ctx, k + 1)
+    V[:, 1:1] = b0
+    lmul_cols!(view_cols(V, 1:1), 1.0 / sqrt(size(b0, 1)))            # (1/norm(b0)) * b0 with b0 = ones(n)
+    h = zeros(k + 2)
+    for j in 1:k
+        w = A(view_cols(V, j:j))                                       # device column -> device column
+        GC.@preserve h check(ctx, ccall((:dre_arnoldi_orth, LIB), Int32, (Ptr{Cvoid}, View, View, View, Ptr{Float64}),
+                                        ctx.h, view_of(view_cols(V, 1:j)), view_of(w), view_of(view_cols(V, j+1:j+1)), h))
+        H[1:j+1, j] .= @view h[1:j+1]
+    end
+    ritz = eigvals(@view H[1:k, 1:k])
+    DRE.Shifts.stabilize_ritz_values!(ritz, desc)
+end
+lmul_cols!(Y::DeviceMatrix, β::Float64) = (check(Y.p.ctx, ccall((:dre_mat_axpby, LIB), Int32,
+    (Ptr{Cvoid}, Float64, View, Float64, View), Y.p.ctx.h, 0.0, View(-1, 0, 0), β, view_of(Y))); Y)
+
 # ---- concatenate! (LDLt.jl:174-191) works through _hcat above; _dcat is generic (host cores) ----
 # ---- zero / iszero / rank are generic (LDLt.jl:112-121) given size(::DeviceMatrix) ----
 end # module

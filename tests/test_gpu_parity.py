@@ -240,3 +240,86 @@ def test_newton_adi_residual():
         Xd = X.to_dense()
         are_o = O.GAREProblem(E, A, O.lowrank(B), O.lowrank(C.T))
         assert np.linalg.norm(O.gare_residual_dense(are_o, Xd)) < reltol * O.norm(are_o.Q)
+
+
+class _NewtonRec(Recorder):
+    """Newton-Kleinman trace: residual norm of every outer iteration, line-search / inexact decisions, inner ADI runs."""
+
+    def __init__(self):
+        super().__init__()
+        self.gare_res, self.meta = [], []
+
+    def observe_gare_step(self, i, X, res, rn):
+        self.gare_res.append((i, float(rn)))
+
+    def observe_gare_metadata(self, desc, val):
+        self.meta.append((desc, float(val)))
+
+
+def _heuristic_shift_lists(n, closed_loop):
+    """Shifts.init(Heuristic(10, 20, 20), prob) (heuristic.jl:39-66) on the device and in the oracle, same pencil."""
+    E, A, B, C, _ = pencils.rail_pencil(n)
+    q = C.shape[0]
+    rng = np.random.default_rng(5)
+    K = 0.05 * rng.standard_normal((n, B.shape[1]))
+    prob_g = api._device_problem(api.GALEProblem(E, A, api.lowrank(np.asfortranarray(C.T), np.eye(q))))
+    Eo, Ao = E, A
+    if closed_loop:   # the operator Ros1 / Newton hand to Shifts.init: F = A - E/(2 tau) - B K' (lowrank_ros1.jl:39)
+        Fg = api.lr_update(api.PencilCombo(1.0, -1.0 / 200.0), -1.0, api.DeviceMatrix.from_host(B),
+                           api.DeviceMatrix.from_host(K), transposed=True)
+        prob_g = api.GALEProblem(prob_g.E, Fg, prob_g.C)
+        Ao = O.lr_update((A - E / 200.0).tocsc(), -1.0, B, K.T)
+    st_g, st_o = api.Heuristic(10, 20, 20), O.Heuristic(10, 20, 20)
+    sh_g = api._take_many(api.shifts_init(st_g, prob_g))
+    sh_o = O._take_many(O.shifts_init(st_o, O.GALEProblem(Eo, Ao, O.lowrank(C.T, np.eye(q)))))
+    return np.array(sh_g, dtype=complex), np.array(sh_o, dtype=complex)
+
+
+@pytest.mark.parametrize("n,closed_loop", [(371, False), (371, True), (1357, True)])
+def test_heuristic_shifts_device_arnoldi_vs_oracle(n, closed_loop):
+    """the Heuristic strategy with device-resident Arnoldi vectors (dre_arnoldi_orth: the
+    twice-repeated MGS of heuristic.jl:111-125 as a chain of launches, operator applications through dre_spmm +
+    dre_shift_solve incl. the Sherman-Morrison-Woodbury correction for the closed-loop operator) selects the same
+    shifts as the oracle: same count, same order, every value within 1e-8 relative."""
+    sh_g, sh_o = _heuristic_shift_lists(n, closed_loop)
+    assert len(sh_g) == len(sh_o) and len(sh_g) >= 10
+    assert np.all(sh_g.real < 0)
+    assert np.max(np.abs(sh_g - sh_o) / np.abs(sh_o)) < 1e-8
+
+
+def _newton_pair(n, b_scale=1.0, **newton_kw):
+    E, A, B, C, _ = pencils.rail_pencil(n)
+    B = b_scale * B
+    out = []
+    for mod in (O, api):
+        rec = _NewtonRec()
+        are = mod.GAREProblem(E, A, mod.lowrank(B), mod.lowrank(np.asfortranarray(C.T)))
+        adi = mod.ADI(ignore_initial_guess=True, shifts=mod.Cyclic(mod.Heuristic(10, 20, 20)), maxiters=200)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            solve = mod.solve if mod is api else mod.solve_gare_newton
+            X = solve(are, mod.Newton(adi, **newton_kw), observer=rec)
+        out.append((X.to_dense(), rec))
+    return out
+
+
+@pytest.mark.parametrize("kw", [dict(maxiters=10, reltol=1e-10, inexact=False, linesearch=False),
+                                dict(maxiters=10, reltol=1e-10, linesearch=True, inexact=True, inexact_hybrid=True)],
+                         ids=["classical", "linesearch-inexact-hybrid"])
+def test_newton_kleinman_iterates_vs_oracle(kw):
+    """Row a3: the Newton-Kleinman drivers (newton.jl:3-147) step by step against the oracle -- same number of outer
+    iterations, every GARE residual norm within 1e-8 relative to ||Q||, the same line-search step lengths and
+    inexact/hybrid decisions (newton.jl:51-85,113-127), identical ADI iteration counts of every inner solve, final X
+    within 1e-8.  Cyclic(Heuristic) shifts: deterministic, so free run == lock step."""
+    # (with the input weights scaled by 10 the first Kleinman iterate overshoots and the Armijo search halves twice)
+    (Xo, ro), (Xg, rg) = _newton_pair(371, b_scale=10.0 if kw.get("linesearch") else 1.0, **kw)
+    assert [i for i, _ in rg.gare_res] == [i for i, _ in ro.gare_res]
+    q0 = ro.gare_res[0][1]
+    for (_, a), (_, b) in zip(rg.gare_res, ro.gare_res):
+        assert abs(a - b) <= 1e-8 * q0
+    assert [d for d, _ in rg.meta] == [d for d, _ in ro.meta]
+    assert np.allclose([v for _, v in rg.meta], [v for _, v in ro.meta], rtol=0, atol=1e-12)
+    if kw.get("linesearch"):
+        assert any(d == "line search" for d, _ in rg.meta)
+    assert [r["iters"] for r in rg.runs] == [r["iters"] for r in ro.runs]
+    assert np.linalg.norm(Xg - Xo) <= 1e-8 * np.linalg.norm(Xo)

@@ -123,6 +123,25 @@ def test_emulated_adi_free_run_tiny_random_and_stepping(emulated):
     assert O.delta(Xg.to_dense(), O.bartels_stewart(prob_o)) < 1e-9
 
 
+@pytest.mark.parametrize("closed_loop", [False, True])
+def test_emulated_heuristic_shifts_device_arnoldi(emulated, closed_loop):
+    """dre_arnoldi_orth (k_mgs_stage / k_mgs_finish) through the emulated C ABI: Heuristic(10, 20, 20) shifts of the
+    open-loop pencil and of the closed-loop operator equal the oracle's (tests/test_gpu_parity.py)."""
+    from tests import test_gpu_parity as P
+
+    emulated()
+    P.test_heuristic_shifts_device_arnoldi_vs_oracle(371, closed_loop)
+
+
+def test_emulated_newton_kleinman_iterates(emulated):
+    """Newton-Kleinman with line search and the inexact/hybrid forcing, step by step against the oracle."""
+    from tests import test_gpu_parity as P
+
+    emulated()
+    P.test_newton_kleinman_iterates_vs_oracle(dict(maxiters=10, reltol=1e-10, linesearch=True, inexact=True,
+                                                   inexact_hybrid=True))
+
+
 def test_emulated_ros1_free_run_first_step(emulated):
     """One Ros1 step at n = 371 with the path's own Projection(2) shifts (no replay): K(t) within 1e-8 of the
     oracle's free run (the first step is well conditioned, tests/test_gpu_parity.py::test_ros1_free_run_371)."""
