@@ -609,6 +609,7 @@ def _join_pending(X: LDLt):
 def norm(X: LDLt) -> float:
     """src/LDLt.jl:77-89."""
     be = backend()
+    X.to_device_()
     concatenate_(X)
     a, L, D = X.alphas[0], X.Ls[0], X.Ds[0]
     if L.ncols == 0:
@@ -625,6 +626,8 @@ def dot(X1: LDLt, X2: LDLt) -> float:
     (dre_gemm_tn), the k1 x k2 core algebra on the host."""
     if X1.n != X2.n:
         raise ValueError("DimensionMismatch")
+    X1.to_device_()
+    X2.to_device_()
     concatenate_(X1)
     concatenate_(X2)
     alpha, A, B = X1.alphas[0], X1.Ls[0], np.asarray(X1.Ds[0])

@@ -402,7 +402,11 @@ static void tl_dump() {}
 struct RRTotals {
     long calls = 0, blocks = 0, rounds = 0, productive = 0, skipped = 0, syncs = 0, rest_projections = 0,
          coef_only_passes = 0;
+    double ms_rounds = 0, ms_core = 0, ms_eig = 0, ms_final = 0;   // host wall clock between the syncs compress! has anyway
 } g_rr;
+static inline double wall_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 struct HostTrace {
     const char* name;
     std::chrono::steady_clock::time_point t0;
@@ -1225,10 +1229,11 @@ int32_t dre_destroy(dre_context* c) {
     if (g_rr_stats && c)
         fprintf(stderr,
                 "[dre rr totals] blocks %ld rounds %ld productive %ld skipped sub-panels %ld rest projections %ld "
-                "skipped second passes %ld round syncs %ld kernel launches (context) %lld\n",
+                "skipped second passes %ld round syncs %ld kernel launches (context) %lld; compress! calls %ld: "
+                "Gram-Schmidt %.1f ms, core %.1f ms, eigen %.1f ms, L<-QV %.1f ms (host wall clock)\n",
                 g_rr.blocks, g_rr.rounds, g_rr.productive, g_rr.skipped, g_rr.rest_projections, g_rr.coef_only_passes,
                 g_rr.syncs,
-                (long long)c->stats.kernel_launches);
+                (long long)c->stats.kernel_launches, g_rr.calls, g_rr.ms_rounds, g_rr.ms_core, g_rr.ms_eig, g_rr.ms_final);
     if (!c) return DRE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
@@ -1928,6 +1933,7 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
         }
     }
     CU(cudaStreamSynchronize(c->st));   // (h_pinned is reused by the rounds)
+    const double t_w0 = wall_ms();
     {
         Range r_orthf("orthf");
         HostTrace tr("compress: rank-revealing Gram-Schmidt", c->st);
@@ -1939,6 +1945,7 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     // dense-core terms):  M = C RT block by block, then one Gram product RT' M over the ktot coefficient rows.
     if ((rc = ensure_pinned(c, (size_t)ktot + rho + 64))) return rc;
     CU(cudaStreamSynchronize(c->st));
+    const double t_w1 = wall_ms();
     for (int i = 0; i < ktot; ++i) c->h_pinned[i] = signs[i];
     CU(c->evals.ensure((size_t)ktot + rho));
     CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, ktot * sizeof(double), cudaMemcpyHostToDevice, c->st));
@@ -1969,9 +1976,12 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     }
     if ((rc = gram_dev(c, s.RT, s.ldrt, rho, Mmat, s.ldrt, rho, ktot, c->evals.p, c->gbuf.p, rho, nullptr, 0))) return rc;
     double* d_ev = c->evals.p + ktot;
+    double t_w2 = 0.0;
+    if (g_rr_stats) { CU(cudaStreamSynchronize(c->st)); t_w2 = wall_ms(); }
     if ((rc = eig_sym_dev(c, c->gbuf.p, rho, d_ev))) return rc;
     CU(cudaMemcpyAsync(c->h_pinned, d_ev, rho * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
+    const double t_w3 = wall_ms();
     double lmax = 0.0;
     for (int i = 0; i < rho; ++i) lmax = std::max(lmax, std::fabs(c->h_pinned[i]));
     const double eps_ = tol_factor * lmax * 2.220446049250313e-16;
@@ -1993,6 +2003,13 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
         if ((rc = tall_gemm(c, 1.0, s.Q, s.ldq, rho, c->gbuf2.p, rho, 1, 0.0, vptr(c, out), vld(c, out), k2, n)))
             return rc;
         CU(cudaStreamSynchronize(c->st));
+    }
+    if (g_rr_stats) {
+        g_rr.calls++;
+        g_rr.ms_rounds += t_w1 - t_w0;
+        g_rr.ms_core += t_w2 - t_w1;
+        g_rr.ms_eig += t_w3 - t_w2;
+        g_rr.ms_final += wall_ms() - t_w3;
     }
     return check_errflag(c);
 }

@@ -474,17 +474,96 @@ def pipe_stop():
 
 
 # ---- rank 1 (and the idle ranks) ---------------------------------------------------------------------------------
+class _TensorPanel:
+    """Panel of the lane's context that aliases a torch tensor (n x ld, float64) filled by the receiver thread
+    (dre_mat_wrap).  Synchronises the context before the tensor goes back to torch's allocator."""
+
+    def __init__(self, be, tensor, cols):
+        self.be, self.cols, self.gen, self.tensor = be, cols, be.generation, tensor
+        self.version = 0
+        pid = C.c_int32(-1)
+        be.check(be.lib.dre_mat_wrap(be.h, C.c_void_p(tensor.data_ptr()), int(tensor.stride(0)), cols, C.byref(pid)))
+        self.id = pid.value
+
+    def __del__(self):
+        try:
+            if self.be.ctx.h and self.gen == self.be.generation:
+                self.be.lib.dre_sync(self.be.h)
+                self.be.lib.dre_mat_free(self.be.h, self.id)
+        except Exception:
+            pass
+
+
+def _recv_panel_tensor(n, k, src):
+    """Receiver thread of rank 1: an n x k panel into a fresh torch tensor with an even leading dimension (the
+    library wants 16-byte rows); complete when this returns."""
+    import torch
+    import torch.distributed as dist
+
+    dev = _dev_str()
+    kp = k + (k & 1)
+    if kp == k:
+        t = torch.empty((n, k), dtype=torch.float64, device=dev)
+        dist.recv(t, src=src)
+    else:
+        tmp = torch.empty((n, k), dtype=torch.float64, device=dev)
+        dist.recv(tmp, src=src)
+        t = torch.zeros((n, kp), dtype=torch.float64, device=dev)
+        t[:, :k].copy_(tmp)
+    if _PIPE.data_backend != "gloo":
+        torch.cuda.current_stream().synchronize()
+    return t
+
+
 def serve(api):
-    """Rank >= 1: the compression lane (rank 1) or an idle wait for the end of the job (ranks >= 2)."""
+    """Rank >= 1: the compression lane (rank 1) or an idle wait for the end of the job (ranks >= 2).
+
+    Rank 1 runs two host threads.  The RECEIVER posts every receive as soon as rank 0 announces it (control
+    headers and cores over gloo -- whose send is a rendezvous: it completes only once the peer has posted the
+    matching receive -- and panels over NCCL into fresh torch tensors) and queues the commands in order; the
+    WORKER (this thread) appends terms and runs compress!.  With a single thread rank 0's sends waited for the
+    running compress! and the two lanes ran one after the other (profiles/r02_results.md: 1.26 steps/s on two
+    GPUs, the same as on one)."""
     p = _PIPE
     if p.rank >= 2:
         while int(_recv_hdr(0)[0]) != CMD_STOP:
             pass
         return {"role": "idle"}
+    import queue
+    import threading
+    import time
+
     be = None
     terms = []      # (alpha, DeviceMatrix, core)
-    served = {"role": "compress", "terms": 0, "compressions": 0, "fetches": 0, "busy_s": 0.0}
-    import time
+    served = {"role": "compress", "terms": 0, "compressions": 0, "fetches": 0, "busy_s": 0.0, "idle_s": 0.0}
+    inbox = queue.Queue()
+
+    def receiver():
+        try:
+            if p.data_backend != "gloo":
+                import torch
+
+                torch.cuda.set_device(p.device if p.device is not None else 0)
+                torch.cuda.set_stream(torch.cuda.Stream())
+            n = 0
+            while True:
+                h = _recv_hdr(0)
+                cmd = int(h[0])
+                if cmd == CMD_BEGIN:
+                    n = int(h[1])
+                if cmd == CMD_TERM:
+                    k, diag = int(h[1]), h[3] != 0.0
+                    core = _recv_small(k if diag else k * k, 0)
+                    inbox.put((cmd, h, core, _recv_panel_tensor(n, k, 0)))
+                else:
+                    inbox.put((cmd, h, None, None))
+                if cmd == CMD_STOP:
+                    return
+        except BaseException as e:  # noqa: BLE001  (the worker re-raises it)
+            inbox.put((-1, e, None, None))
+
+    th = threading.Thread(target=receiver, name="dre-pipe-receiver", daemon=True)
+    th.start()
 
     def compress_now():
         nonlocal terms
@@ -501,23 +580,24 @@ def serve(api):
         terms = [(1.0, Lnew, np.asfortranarray(np.diag(lam)))]
 
     while True:
-        h = _recv_hdr(0)
-        cmd = int(h[0])
+        t0 = time.perf_counter()
+        cmd, h, core, tensor = inbox.get()
+        served["idle_s"] += time.perf_counter() - t0
+        if cmd == -1:
+            raise h
         if cmd == CMD_STOP:
             break
         if cmd == CMD_BEGIN:
             n = int(h[1])
             if be is None or be.n != n:
-                be = api._pipe_lane_backend(n, p.device)
                 terms = []
+                be = api._pipe_lane_backend(n, p.device)
             if h[2] == 0.0:
                 terms = []
         elif cmd == CMD_TERM:
             k, alpha, diag = int(h[1]), h[2], h[3] != 0.0
-            core = _recv_small(k if diag else k * k, 0)
             D = np.diag(core) if diag else core.reshape(k, k, order="F")
-            L = api.DeviceMatrix(api._Panel(be, k), 0, k)
-            _recv_panel(be, L, 0)
+            L = api.DeviceMatrix(_TensorPanel(be, tensor, k), 0, k)
             terms.append((alpha, L, np.asfortranarray(D)))
             served["terms"] += 1
         elif cmd == CMD_COMPRESS:
@@ -537,4 +617,5 @@ def serve(api):
                 _send_panel(be, L, 0)
                 _reap_sends(block=True)
             served["fetches"] += 1
+    th.join(timeout=5.0)
     return served
