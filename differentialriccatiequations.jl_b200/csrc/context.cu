@@ -358,6 +358,8 @@ int check_errflag(dre_context* c) {
 static const bool g_trace = getenv("DRE_TRACE") != nullptr;
 // DRE_RR_STATS=1: totals of the rank-revealing Gram-Schmidt rounds, printed when a context dies
 static const bool g_rr_stats = getenv("DRE_RR_STATS") != nullptr;
+// DRE_RR_LEGACY=1: round-2 A/B switch, the per-sub-panel projections against everything since the look-ahead snapshot
+static const bool g_rr_legacy = getenv("DRE_RR_LEGACY") != nullptr;
 // DRE_TIMELINE=<file>: device-side timeline of the streams (events recorded around the launch groups, resolved against
 // a base event when the context dies; no synchronisation while the job runs).  Lines: "<ms begin> <ms end> <lane> <name>",
 // lane 0 = main stream, 1..4 = factor slots' side streams, 5 = look-ahead / norm streams.
@@ -938,9 +940,34 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
             }
         }
         g_rr.blocks++;
+        // Directions added since the snapshot (by the previous chunk, whose stage 2 ran while this chunk's stage 1
+        // was in flight): the WHOLE chunk is projected against them here, in one fat Gram / tall-GEMM pair per pass,
+        // and its remainder norms are refreshed; the sub-panels below then only see the directions this chunk adds
+        // itself.  (Before, every sub-panel re-projected against everything since the snapshot in every round:
+        // 4 x npass x rounds narrow launches per chunk, most of them to find nothing.)
+        const int rho_cs = s.rho;
+        if (rho_cs > rho0 && !g_rr_legacy) {
+            CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
+            for (int pass = 0; pass < npass; ++pass) {
+                rc = gram_dev(c, Pbig, PBIG, pbig, s.Q + rho0, s.ldq, rho_cs - rho0, n, nullptr, c->cbuf.p, rho_cs - rho0,
+                              s.RT + (int64_t)ch.rt_row * s.ldrt + rho0, s.ldrt);
+                if (rc) return rc;
+                rc = tall_gemm(c, -1.0, s.Q + rho0, s.ldq, rho_cs - rho0, c->cbuf.p, rho_cs - rho0, 1, 1.0, Pbig, PBIG,
+                               pbig, n);
+                if (rc) return rc;
+            }
+            launch_colnorm2(Pbig, PBIG, n, pbig, c->gram_partial.p, NBLK, c->cnorm.p, c->st, &c->stats.kernel_launches);
+            CU(cudaMemcpyAsync(c->h_pinned + 16, c->cnorm.p, pbig * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            g_rr.syncs++;
+            g_rr.rest_projections++;
+            for (int j = 0; j < pbig; ++j) rem2[j] = c->h_pinned[16 + j];
+        }
+        const int rho_base = g_rr_legacy ? rho0 : rho_cs;   // what the sub-panels have been projected against already
+        const bool have_rem2 = have_rem || (rho_cs > rho0 && !g_rr_legacy);
         for (int sc = 0; sc < pbig; sc += PB) {
             const int pb = std::min(PB, pbig - sc);
-            if (have_rem && !g_trace) {
+            if (have_rem2 && !g_trace) {
                 double m2 = 0.0;
                 for (int j = sc; j < sc + pb; ++j) m2 = std::max(m2, rem2[j]);
                 const double drop0 = std::max(s.drop_rel * std::sqrt(s.scale2), s.drop_abs);
@@ -963,15 +990,15 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
                 g_rr.rounds++;
                 // directions added since the snapshot (by earlier chunks / sub-panels / rounds) that this sub-panel
                 // has not been projected against in this round
-                const int nnew = s.rho - rho0;
+                const int nnew = s.rho - rho_base;
                 if (nnew > 0) {
                     CU(c->cbuf.ensure((size_t)PBIG * std::max(s.rho, PB)));
                     // same rule as for the block passes: one pass unless the chunk holds large columns
                     for (int pass = 0; pass < npass; ++pass) {
-                        rc = gram_dev(c, Pw, PBIG, pb, s.Q + rho0, s.ldq, nnew, n, nullptr, c->cbuf.p, nnew,
-                                      RTrow + rho0, s.ldrt);
+                        rc = gram_dev(c, Pw, PBIG, pb, s.Q + rho_base, s.ldq, nnew, n, nullptr, c->cbuf.p, nnew,
+                                      RTrow + rho_base, s.ldrt);
                         if (rc) return rc;
-                        rc = tall_gemm(c, -1.0, s.Q + rho0, s.ldq, nnew, c->cbuf.p, nnew, 1, 1.0, Pw, PBIG, pb, n);
+                        rc = tall_gemm(c, -1.0, s.Q + rho_base, s.ldq, nnew, c->cbuf.p, nnew, 1, 1.0, Pw, PBIG, pb, n);
                         if (rc) return rc;
                     }
                 }
@@ -1950,31 +1977,31 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     CU(c->evals.ensure((size_t)ktot + rho));
     CU(cudaMemcpyAsync(c->evals.p, c->h_pinned, ktot * sizeof(double), cudaMemcpyHostToDevice, c->st));
     CU(c->gbuf.ensure((size_t)rho * rho));
-    const double* Mmat = s.RT;
-    if (!dense_terms.empty()) {
-        CU(c->rt2.ensure((size_t)ktot * s.ldrt));
-        CU(cudaMemcpyAsync(c->rt2.p, s.RT, (size_t)ktot * s.ldrt * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-        for (const DenseTerm& dt : dense_terms) {
-            const double* D = Ds[dt.t];
-            const int64_t ldd = ldds[dt.t];
-            const int k = dt.k;
-            if ((rc = ensure_pinned(c, (size_t)k * k + 64))) return rc;
-            CU(cudaStreamSynchronize(c->st));
-            for (int j = 0; j < k; ++j)
-                for (int i = 0; i < k; ++i)
-                    c->h_pinned[i + (int64_t)j * k] =
-                        0.5 * alphas[dt.t] * (D[i + (int64_t)j * ldd] + D[j + (int64_t)i * ldd]);
-            CU(c->gbuf2.ensure((size_t)k * k));
-            CU(cudaMemcpyAsync(c->gbuf2.p, c->h_pinned, (size_t)k * k * sizeof(double), cudaMemcpyHostToDevice, c->st));
-            // M_block (k x rho) = C_t (k x k, symmetric) * RT_block (k x rho)
-            if ((rc = tall_gemm(c, 1.0, c->gbuf2.p, k, k, s.RT + (int64_t)dt.row0 * s.ldrt, s.ldrt, 0, 0.0,
-                                c->rt2.p + (int64_t)dt.row0 * s.ldrt, s.ldrt, rho, k)))
-                return rc;
-            CU(cudaStreamSynchronize(c->st));   // h_pinned / gbuf2 are reused
-        }
-        Mmat = c->rt2.p;
+    // M = C RT: rows of the diagonal-core terms scaled by their signs (exact), dense-core blocks replaced by
+    // C_t RT_block; then S = RT' M is an ordinary Gram product over the ktot coefficient rows on the DMMA path
+    // (the row-weighted scalar kernel spent 5-10 ms on the 2.5 GFLOP of a rank-700 core).
+    CU(c->rt2.ensure((size_t)ktot * s.ldrt));
+    launch_copy_scale(c->rt2.p, s.ldrt, s.RT, s.ldrt, ktot, rho, nullptr, c->st, &c->stats.kernel_launches, c->evals.p);
+    CU(cudaGetLastError());
+    for (const DenseTerm& dt : dense_terms) {
+        const double* D = Ds[dt.t];
+        const int64_t ldd = ldds[dt.t];
+        const int k = dt.k;
+        if ((rc = ensure_pinned(c, (size_t)k * k + 64))) return rc;
+        CU(cudaStreamSynchronize(c->st));
+        for (int j = 0; j < k; ++j)
+            for (int i = 0; i < k; ++i)
+                c->h_pinned[i + (int64_t)j * k] =
+                    0.5 * alphas[dt.t] * (D[i + (int64_t)j * ldd] + D[j + (int64_t)i * ldd]);
+        CU(c->gbuf2.ensure((size_t)k * k));
+        CU(cudaMemcpyAsync(c->gbuf2.p, c->h_pinned, (size_t)k * k * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        // M_block (k x rho) = C_t (k x k, symmetric) * RT_block (k x rho)
+        if ((rc = tall_gemm(c, 1.0, c->gbuf2.p, k, k, s.RT + (int64_t)dt.row0 * s.ldrt, s.ldrt, 0, 0.0,
+                            c->rt2.p + (int64_t)dt.row0 * s.ldrt, s.ldrt, rho, k)))
+            return rc;
+        CU(cudaStreamSynchronize(c->st));   // h_pinned / gbuf2 are reused
     }
-    if ((rc = gram_dev(c, s.RT, s.ldrt, rho, Mmat, s.ldrt, rho, ktot, c->evals.p, c->gbuf.p, rho, nullptr, 0))) return rc;
+    if ((rc = gram_dev(c, s.RT, s.ldrt, rho, c->rt2.p, s.ldrt, rho, ktot, nullptr, c->gbuf.p, rho, nullptr, 0))) return rc;
     double* d_ev = c->evals.p + ktot;
     double t_w2 = 0.0;
     if (g_rr_stats) { CU(cudaStreamSynchronize(c->st)); t_w2 = wall_ms(); }

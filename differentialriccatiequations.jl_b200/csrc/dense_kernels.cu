@@ -615,7 +615,8 @@ void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const d
 // elementwise helpers
 // ------------------------------------------------------------------------------------------
 __global__ void k_copy_scale(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
-                             int64_t n, int cols, const double* __restrict__ colscale) {
+                             int64_t n, int cols, const double* __restrict__ colscale,
+                             const double* __restrict__ rowscale) {
     const int64_t total = n * cols;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -623,15 +624,16 @@ __global__ void k_copy_scale(double* __restrict__ dst, int64_t ldd, const double
         const int c = (int)(idx % cols);
         double v = src[row * lds + c];
         if (colscale) v *= colscale[c];
+        if (rowscale) v *= rowscale[row];
         dst[row * ldd + c] = v;
     }
 }
 
 void launch_copy_scale(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, int cols,
-                       const double* colscale, cudaStream_t st, int64_t* launches) {
+                       const double* colscale, cudaStream_t st, int64_t* launches, const double* rowscale) {
     if (n <= 0 || cols <= 0) return;
     int blocks = (int)std::min<int64_t>((n * cols + 255) / 256, 148 * 16);
-    DRE_LAUNCH((k_copy_scale), blocks, 256, 0, st, dst, ldd, src, lds, n, cols, colscale);
+    DRE_LAUNCH((k_copy_scale), blocks, 256, 0, st, dst, ldd, src, lds, n, cols, colscale, rowscale);
     if (launches) *launches += 1;
 }
 

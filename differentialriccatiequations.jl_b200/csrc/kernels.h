@@ -29,7 +29,7 @@ void launch_tall_gemm(double alpha, const double* X, int64_t ldx, int a, const d
 
 // dst[row][c] = src[row][c] * (colscale ? colscale[c] : 1)
 void launch_copy_scale(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, int cols,
-                       const double* colscale, cudaStream_t st, int64_t* launches);
+                       const double* colscale, cudaStream_t st, int64_t* launches, const double* rowscale = nullptr);
 // out[c] = sum_rows P[row][c]^2, cols <= 256; partial needs nblk*cols doubles
 void launch_colnorm2(const double* P, int64_t ldp, int64_t n, int cols, double* partial, int nblk, double* out,
                      cudaStream_t st, int64_t* launches);

@@ -502,14 +502,20 @@ def _recv_panel_tensor(n, k, src):
 
     dev = _dev_str()
     kp = k + (k & 1)
+    # every buffer has one of a few sizes (columns rounded up to 64): torch's caching allocator then recycles the
+    # blocks of compressed-away terms instead of calling cudaMalloc (a device synchronisation in the middle of the
+    # running compress!) for each new column count
+    cap = n * ((kp + 63) // 64 * 64)
+    flat = torch.empty(cap, dtype=torch.float64, device=dev)
     if kp == k:
-        t = torch.empty((n, k), dtype=torch.float64, device=dev)
+        t = flat[: n * k].view(n, k)
         dist.recv(t, src=src)
     else:
-        tmp = torch.empty((n, k), dtype=torch.float64, device=dev)
+        tmp = torch.empty(cap, dtype=torch.float64, device=dev)[: n * k].view(n, k)
         dist.recv(tmp, src=src)
-        t = torch.zeros((n, kp), dtype=torch.float64, device=dev)
+        t = flat[: n * kp].view(n, kp)
         t[:, :k].copy_(tmp)
+        t[:, k:].zero_()
     if _PIPE.data_backend != "gloo":
         torch.cuda.current_stream().synchronize()
     return t
