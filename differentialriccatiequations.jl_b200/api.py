@@ -491,10 +491,12 @@ def _compress_call(be: Backend, terms):
     out = be.scratch(cap)  # persistent, geometrically grown: allocating ~2 GB per call costs tens of ms
     lam = np.zeros(cap)
     newrank = C.c_int32(0)
-    be.check(be.lib.dre_ldlt_compress(be.h, nt, views, dptrs, ldds, alphas, 100.0, out.view, capi._dptr(lam),
-                                      C.byref(newrank)))
+    with _timeit("compress!: dre_ldlt_compress"):
+        be.check(be.lib.dre_ldlt_compress(be.h, nt, views, dptrs, ldds, alphas, 100.0, out.view, capi._dptr(lam),
+                                          C.byref(newrank)))
     k2 = newrank.value
-    Lnew = out.cols(0, k2).copy()  # exact-size panel; the scratch panel is reused by the next compress!
+    with _timeit("compress!: copy out"):
+        Lnew = out.cols(0, k2).copy()  # exact-size panel; the scratch panel is reused by the next compress!
     _mark_orthonormal(Lnew)         # Q * (orthonormal eigenvectors): lets the next compress! skip these columns
     return Lnew, lam[:k2]
 
@@ -508,9 +510,11 @@ def compress_(X: LDLt) -> LDLt:
         raise ValueError("compress!: rank-0 input (reference: maximum of empty collection, src/LDLt.jl:216)")
     Lnew, lam = _compress_call(backend(), terms)
     _dist.assert_same_int(Lnew.ncols, "the rank after compress!")
-    X.alphas[:] = [1.0]
-    X.Ls[:] = [Lnew]
-    X.Ds[:] = [np.asfortranarray(np.diag(lam))]
+    with _timeit("compress!: release terms"):
+        del terms
+        X.alphas[:] = [1.0]
+        X.Ls[:] = [Lnew]
+        X.Ds[:] = [np.asfortranarray(np.diag(lam))]
     return X
 
 

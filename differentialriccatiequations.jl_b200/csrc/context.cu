@@ -358,8 +358,11 @@ int check_errflag(dre_context* c) {
 static const bool g_trace = getenv("DRE_TRACE") != nullptr;
 // DRE_RR_STATS=1: totals of the rank-revealing Gram-Schmidt rounds, printed when a context dies
 static const bool g_rr_stats = getenv("DRE_RR_STATS") != nullptr;
-// DRE_RR_LEGACY=1: round-2 A/B switch, the per-sub-panel projections against everything since the look-ahead snapshot
-static const bool g_rr_legacy = getenv("DRE_RR_LEGACY") != nullptr;
+// DRE_RR_CHUNKPROJ=1: project the WHOLE chunk against the directions added since its look-ahead snapshot before its
+// sub-panels are visited (default: every sub-panel does so itself, round by round).  Measured on the B200
+// (profiles/r02_results.md, steady state, 4 compress! calls): selection 57.7 -> 34.4 ms but 33.6 ms for the extra
+// chunk passes and one more sync per chunk: 104.4 vs 98.7 ms in total -- no gain, so it stays opt-in.
+static const bool g_rr_legacy = getenv("DRE_RR_CHUNKPROJ") == nullptr || atoi(getenv("DRE_RR_CHUNKPROJ")) == 0;
 // DRE_TIMELINE=<file>: device-side timeline of the streams (events recorded around the launch groups, resolved against
 // a base event when the context dies; no synchronisation while the job runs).  Lines: "<ms begin> <ms end> <lane> <name>",
 // lane 0 = main stream, 1..4 = factor slots' side streams, 5 = look-ahead / norm streams.
@@ -405,6 +408,8 @@ struct RRTotals {
     long calls = 0, blocks = 0, rounds = 0, productive = 0, skipped = 0, syncs = 0, rest_projections = 0,
          coef_only_passes = 0;
     double ms_rounds = 0, ms_core = 0, ms_eig = 0, ms_final = 0;   // host wall clock between the syncs compress! has anyway
+    double ms_wait_stage1 = 0, ms_chunk_proj = 0, ms_select = 0, ms_extend = 0;   // inside the Gram-Schmidt phase
+    double ms_entry_sync = 0, ms_setup = 0;   // waiting for the work queued before the call; argument checks + uploads
 } g_rr;
 static inline double wall_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -892,9 +897,12 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
         if (look) {
             if (i + 1 < nch && (rc = queue_stage1(i + 1))) return rc;
         } else if ((rc = queue_stage1(i))) return rc;
+        const double t_s1 = wall_ms();
         CU(cudaEventSynchronize(c->look_done[i & 1]));
         if (look) CU(cudaStreamWaitEvent(c->st, c->look_done[i & 1], 0));
         g_rr.syncs++;
+        const double t_s2 = wall_ms();
+        g_rr.ms_wait_stage1 += t_s2 - t_s1;
         double* Pbig = c->pws.p + (size_t)(i & 1) * n * PBIG;
         const double* hn = c->h_look + (size_t)(i & 1) * 2 * PBIG;
         const int rho0 = snap[i];
@@ -963,6 +971,7 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
             g_rr.rest_projections++;
             for (int j = 0; j < pbig; ++j) rem2[j] = c->h_pinned[16 + j];
         }
+        g_rr.ms_chunk_proj += wall_ms() - t_s2;
         const int rho_base = g_rr_legacy ? rho0 : rho_cs;   // what the sub-panels have been projected against already
         const bool have_rem2 = have_rem || (rho_cs > rho0 && !g_rr_legacy);
         for (int sc = 0; sc < pbig; sc += PB) {
@@ -988,6 +997,7 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
             for (int round = 0; round < 8; ++round) {
                 s.rounds++;
                 g_rr.rounds++;
+                const double t_r0 = wall_ms();
                 // directions added since the snapshot (by earlier chunks / sub-panels / rounds) that this sub-panel
                 // has not been projected against in this round
                 const int nnew = s.rho - rho_base;
@@ -1016,6 +1026,8 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
                 CU(cudaStreamSynchronize(c->st));
                 g_rr.syncs++;
                 const int nsel = hi[0];
+                const double t_r1 = wall_ms();
+                g_rr.ms_select += t_r1 - t_r0;
                 const double dfirst = c->h_pinned[0];
                 const double remaining = c->h_pinned[1];
                 if (round == 0) s.scale2 = std::max(s.scale2, dfirst);
@@ -1052,6 +1064,7 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
                     CU(cudaMemcpyAsync(hi + 2, c->ibuf.p + 2, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
                     CU(cudaStreamSynchronize(c->st));
                     nsel2 = hi[2];
+                    g_rr.ms_extend += wall_ms() - t_r1;
                 }
                 if (g_trace)
                     fprintf(stderr,
@@ -1252,15 +1265,21 @@ static void release_pencil(dre_context* c) {
     c->has_pencil = false;
 }
 
+static void rr_print_totals(dre_context* c) {
+    fprintf(stderr,
+            "[dre rr totals] blocks %ld rounds %ld productive %ld skipped sub-panels %ld rest projections %ld "
+            "skipped second passes %ld round syncs %ld kernel launches (context) %lld; compress!/rrqr calls %ld: "
+            "Gram-Schmidt %.1f ms (wait stage 1 %.1f, chunk projections %.1f, selection %.1f, extension %.1f), core %.1f ms, "
+            "eigen %.1f ms, L<-QV %.1f ms; entry sync %.1f ms, setup %.1f ms (host wall clock)\n",
+            g_rr.blocks, g_rr.rounds, g_rr.productive, g_rr.skipped, g_rr.rest_projections, g_rr.coef_only_passes,
+            g_rr.syncs, (long long)c->stats.kernel_launches, g_rr.calls, g_rr.ms_rounds, g_rr.ms_wait_stage1,
+            g_rr.ms_chunk_proj, g_rr.ms_select, g_rr.ms_extend, g_rr.ms_core, g_rr.ms_eig, g_rr.ms_final,
+            g_rr.ms_entry_sync, g_rr.ms_setup);
+    g_rr = RRTotals{};
+}
+
 int32_t dre_destroy(dre_context* c) {
-    if (g_rr_stats && c)
-        fprintf(stderr,
-                "[dre rr totals] blocks %ld rounds %ld productive %ld skipped sub-panels %ld rest projections %ld "
-                "skipped second passes %ld round syncs %ld kernel launches (context) %lld; compress! calls %ld: "
-                "Gram-Schmidt %.1f ms, core %.1f ms, eigen %.1f ms, L<-QV %.1f ms (host wall clock)\n",
-                g_rr.blocks, g_rr.rounds, g_rr.productive, g_rr.skipped, g_rr.rest_projections, g_rr.coef_only_passes,
-                g_rr.syncs,
-                (long long)c->stats.kernel_launches, g_rr.calls, g_rr.ms_rounds, g_rr.ms_core, g_rr.ms_eig, g_rr.ms_final);
+    if (g_rr_stats && c) rr_print_totals(c);
     if (!c) return DRE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
@@ -1905,7 +1924,9 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     // column scalings |alpha d_j|^(1/2) of the diagonal-core terms (1 for the columns of dense-core terms, whose core
     // enters after the basis is built, exactly as in the reference, src/LDLt.jl:206-213), uploaded once
     if ((rc = ensure_pinned(c, (size_t)ktot + 64))) return rc;
+    const double t_e0 = wall_ms();
     CU(cudaStreamSynchronize(c->st));
+    const double t_e1 = wall_ms();
     std::vector<char> is_diag(nterms, 0);
     {
         int row0 = 0;
@@ -2033,6 +2054,8 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     }
     if (g_rr_stats) {
         g_rr.calls++;
+        g_rr.ms_entry_sync += t_e1 - t_e0;
+        g_rr.ms_setup += t_w0 - t_e1;
         g_rr.ms_rounds += t_w1 - t_w0;
         g_rr.ms_core += t_w2 - t_w1;
         g_rr.ms_eig += t_w3 - t_w2;
@@ -2151,6 +2174,7 @@ int32_t dre_timer_stop(dre_context* c, double* ms) {
 
 int32_t dre_stats_reset(dre_context* c, int32_t enable_event_timing) {
     if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (g_rr_stats && g_rr.calls) rr_print_totals(c);   // (totals since the last reset; a reset starts a new window)
     c->stats = dre_stats{};
     c->timing = enable_event_timing != 0;
     return DRE_OK;
