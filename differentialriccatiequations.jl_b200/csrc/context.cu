@@ -485,7 +485,10 @@ int gram_dev_on(dre_context* c, cudaStream_t st, DBuf<double>& partial, const do
                 const double* Y, int64_t ldy, int b, int64_t n, const double* roww, double* out1, int64_t ld1,
                 double* out2, int64_t ld2) {
     if (a <= 0 || b <= 0) return DRE_OK;
-    GramPlan plan = gram_plan(n, a, b, c->sm_count);
+    // the look-ahead stream's fat Gram products run next to the latency-bound selection rounds of the main stream:
+    // DRE_LOOK_WAVES > 1 cuts them into that many waves of shorter-lived CTAs, so that (with DRE_PRIO=1) a freed SM
+    // goes to the waiting small kernel instead of staying with a one-wave kernel for its whole ~1 ms
+    GramPlan plan = gram_plan(n, a, b, c->sm_count, st != c->st ? g_look_waves : 0);
     if (plan.partial_elems > partial.cap) {
         if (st != c->st) CU(cudaStreamSynchronize(st));   // (never on the sized-up-front path)
         CU(partial.ensure(plan.partial_elems));
@@ -538,6 +541,7 @@ static const bool g_graphs = false;
 // lowest -- the block scheduler then hands a freed SM to the waiting CTA of the latency-bound chain instead of the
 // next CTA of a Gram kernel that was launched earlier.  level: 0 highest, 1 middle, 2 lowest.
 static const bool g_prio = getenv("DRE_PRIO") && atoi(getenv("DRE_PRIO")) != 0;
+static const int g_look_waves = getenv("DRE_LOOK_WAVES") ? std::max(0, atoi(getenv("DRE_LOOK_WAVES"))) : 0;
 static cudaError_t make_stream(cudaStream_t* s, int level) {
     if (!g_prio) return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
     int least = 0, greatest = 0;   // numerically: greatest priority <= least priority
@@ -863,7 +867,8 @@ int rr_process_chunks(dre_context* c, RRState& s, const std::vector<RRChunk>& ch
     CU(c->look_cbuf.ensure((size_t)PBIG * s.qcap));
     {
         size_t pe = (size_t)NBLK * PBIG;
-        for (int b = 64; b < s.qcap + 64; b += 64) pe = std::max(pe, gram_plan(n, PBIG, std::min(b, s.qcap), c->sm_count).partial_elems);
+        for (int b = 64; b < s.qcap + 64; b += 64)
+            pe = std::max(pe, gram_plan(n, PBIG, std::min(b, s.qcap), c->sm_count, g_look_waves).partial_elems);
         CU(c->look_partial.ensure(pe));
         CU(c->gram_partial.ensure((size_t)NBLK * PBIG));
     }

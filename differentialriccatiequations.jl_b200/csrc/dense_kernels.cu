@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) k_tall_gemm2(double alpha, const double* 
     }
 }
 
-GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
+GramPlan gram_plan(int64_t n, int a, int b, int sm_count, int waves_override) {
     GramPlan p;
     const int tbw = b <= 64 ? 64 : G2B;
     int tiles = ((a + G2A - 1) / G2A) * ((b + tbw - 1) / tbw);   // pipelined kernel: 64 x 128 (64 x 64) output tiles
@@ -392,7 +392,8 @@ GramPlan gram_plan(int64_t n, int a, int b, int sm_count) {
     int64_t chunks = (n + GK - 1) / GK;
     // DRE_GRAM_WAVES=w (default 1): w waves of shorter CTAs -- only useful together with stream priorities (DRE_PRIO),
     // where a low-priority Gram kernel should give SMs back to the ADI chain every few tens of microseconds
-    static const int waves = std::max(1, getenv("DRE_GRAM_WAVES") ? atoi(getenv("DRE_GRAM_WAVES")) : 1);
+    static const int waves_env = std::max(1, getenv("DRE_GRAM_WAVES") ? atoi(getenv("DRE_GRAM_WAVES")) : 1);
+    const int waves = waves_override > 0 ? waves_override : waves_env;
     int want = std::max(1, (2 * sm_count * waves) / tiles);   // at most 2 CTAs per SM: ONE full wave (19 x 16 tiles = 304
                                                       // CTAs on 296 slots was measured at twice the time of 18 x 16)
     if (a <= 16 && b >= 64) want = std::max(1, 8 * sm_count / ((b + 255) / 256));  // skinny kernel: thread per column

@@ -17,7 +17,8 @@ struct GramPlan {
     int64_t rows_per_split;
     size_t partial_elems;  // required workspace (doubles)
 };
-GramPlan gram_plan(int64_t n, int a, int b, int sm_count);
+// waves > 0 overrides DRE_GRAM_WAVES: that many waves of shorter-lived CTAs (more row splits)
+GramPlan gram_plan(int64_t n, int a, int b, int sm_count, int waves_override = 0);
 void launch_gram(const double* X, int64_t ldx, int a, const double* Y, int64_t ldy, int b, int64_t n,
                  const double* roww, double* partial, const GramPlan& plan, double* out1, int64_t ld1,
                  double* out2, int64_t ld2, cudaStream_t st, int64_t* launches);

@@ -140,7 +140,13 @@ DRE_API int32_t dre_set_operator(dre_context* ctx, double a, double e, double al
 /* Solve (F' + mu E') V = R   (src/lyapunov/adi.jl:156-159 real, :195-198 complex):
  * numeric supernodal LDL^T of a*A+(e+mu)*E, block forward/backward sweeps for [R, Vt] and the fused
  * Sherman-Morrison-Woodbury correction (src/blocklinear/sherman-morrison-woodbury.jl:10-45).
- * mu_im == 0: V1 = V (V2 ignored).  mu_im != 0: V1 = Re V, V2 = Im V. */
+ * mu_im == 0: V1 = V (V2 ignored).  mu_im != 0: V1 = Re V, V2 = Im V.
+ * SCOPE: E and A must be structurally and numerically symmetric (dre_set_pencil / dre_symbolic_create reject anything
+ * else).  The LDL^T does NOT pivot (the reference's UMFPACK does): it is meant for the definite FEM pencils of this
+ * path, whose shifted matrices a*A + (e+mu)*E are (complex-)symmetric with a definite real part; a zero or non-finite
+ * pivot returns DRE_ERR_NUMERIC, a merely tiny pivot of an indefinite pencil does not -- verify one solve residual
+ * (tests/c_abi_smoke.c does) before trusting such a pencil.  The low-rank update may have at most 32 columns
+ * (m <= 32; the configurations of this path have 7-8), else DRE_ERR_ARG. */
 DRE_API int32_t dre_shift_solve(dre_context* ctx, double mu_re, double mu_im, dre_view R, dre_view V1, dre_view V2);
 /* Hint: the shift the NEXT dre_adi_step / dre_shift_solve will use (the ADI shift buffer is known ahead,
  * src/shifts/helpers.jl:106-113).  Queues the numeric factorization for it on a side stream into the spare
