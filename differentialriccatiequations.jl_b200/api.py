@@ -1238,14 +1238,16 @@ def _prefetch_next_factorization(cache: ADICache):
         queued += 1
 
 
-# Opt-in overlap of the residual norm with the next shifted solve (DRE_ASYNC_NORM=1).  The
+# Overlap of the residual norm with the next shifted solve.  The
 # reference computes norm(residual) after every ADI step only to test for convergence (adi.jl:118-127); the Gram
 # product behind it keeps the whole GPU busy for ~0.4 ms while the sweeps of the next step are latency bound.  With
 # the option on, step_ queues the norm on a side stream (dre_ldlt_norm_begin), starts the solve half of the NEXT step
 # from the already buffered shift while it runs (R is only read), and then collects the norm.  If ADI stops, the
 # speculative block is dropped; otherwise the next step adopts it and only runs its residual update.  Results are
 # identical: the same kernels run on the same data.
-ASYNC_NORM = _os.environ.get("DRE_ASYNC_NORM", "0") not in ("", "0")
+# Default since run r02v (1.331 -> 1.356 steps/s at n = 79 841); DRE_ASYNC_NORM=0 restores the synchronous norm.  Single-GPU
+# runs only: the multi-GPU modes keep the plain sequence (their exchange steps are ordered behind the norm).
+ASYNC_NORM = _os.environ.get("DRE_ASYNC_NORM", "1") not in ("", "0")
 
 
 def _speculate_next_solve(cache: ADICache):
@@ -1367,7 +1369,8 @@ def perform_double_step_(cache: ADICache, mu: complex):
 def _residual_norm_overlapped(cache: ADICache) -> float:
     """norm(cache.residual); with DRE_ASYNC_NORM=1 the next step's solve is queued while the norm is computed."""
     X = cache.residual
-    if not ASYNC_NORM or len(X.alphas) != 1 or X.Ls[0].ncols == 0:
+    if (not ASYNC_NORM or len(X.alphas) != 1 or X.Ls[0].ncols == 0 or _dist.active()
+            or getattr(cache, "_piped", False)):
         return norm(X)
     D = np.asarray(X.Ds[0], dtype=np.float64)
     if np.count_nonzero(D - np.diag(np.diag(D))) != 0:

@@ -358,6 +358,9 @@ int check_errflag(dre_context* c) {
 static const bool g_trace = getenv("DRE_TRACE") != nullptr;
 // DRE_RR_STATS=1: totals of the rank-revealing Gram-Schmidt rounds, printed when a context dies
 static const bool g_rr_stats = getenv("DRE_RR_STATS") != nullptr;
+// fat Gram products of compress!'s look-ahead stream in that many waves of shorter-lived CTAs (see gram_dev_on);
+// default 4 since run r02u (with stream priorities: 775 -> 748 ms per step; 8 and 16 waves add nothing)
+static const int g_look_waves = getenv("DRE_LOOK_WAVES") ? std::max(0, atoi(getenv("DRE_LOOK_WAVES"))) : 4;
 // DRE_RR_CHUNKPROJ=1: project the WHOLE chunk against the directions added since its look-ahead snapshot before its
 // sub-panels are visited (default: every sub-panel does so itself, round by round).  Measured on the B200
 // (profiles/r02_results.md, steady state, 4 compress! calls): selection 57.7 -> 34.4 ms but 33.6 ms for the extra
@@ -536,12 +539,12 @@ static const bool g_graphs = !(getenv("DRE_GRAPHS") && atoi(getenv("DRE_GRAPHS")
 static const bool g_graphs = false;
 #endif
 
-// Stream priorities (DRE_PRIO=1, opt-in until measured): the ADI chain (main stream) runs at the highest priority, the
-// prefactor side streams one step below, a compression lane (dre_set_dense_only) and the look-ahead stage at the
-// lowest -- the block scheduler then hands a freed SM to the waiting CTA of the latency-bound chain instead of the
-// next CTA of a Gram kernel that was launched earlier.  level: 0 highest, 1 middle, 2 lowest.
-static const bool g_prio = getenv("DRE_PRIO") && atoi(getenv("DRE_PRIO")) != 0;
-static const int g_look_waves = getenv("DRE_LOOK_WAVES") ? std::max(0, atoi(getenv("DRE_LOOK_WAVES"))) : 0;
+// Stream priorities (default on since run r02u: +3 % alone, +4 % with DRE_LOOK_WAVES; DRE_PRIO=0 turns them off): the
+// ADI chain and the selection rounds of compress! (main stream) run at the highest priority, the prefactor side
+// streams and the look-ahead stage one step below, a compression lane (dre_set_dense_only) at the lowest -- the block
+// scheduler then hands a freed SM to the waiting CTA of the latency-bound chain instead of the next CTA of a fat
+// Gram kernel that was launched earlier.  level: 0 highest, 1 middle, 2 lowest.
+static const bool g_prio = !(getenv("DRE_PRIO") && atoi(getenv("DRE_PRIO")) == 0);
 static cudaError_t make_stream(cudaStream_t* s, int level) {
     if (!g_prio) return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
     int least = 0, greatest = 0;   // numerically: greatest priority <= least priority
