@@ -501,6 +501,49 @@ def _compress_call(be: Backend, terms):
     return Lnew, lam[:k2]
 
 
+class CompressStream:
+    """compress! in three phases on context `be` (dre_compress_begin / _add / _finish): terms are orthogonalised as
+    they are added, finish() runs the core / eigen / L <- QV tail.  Same result as _compress_call on the same terms
+    in the same order (identical code path: dre_ldlt_compress is begin + add + finish)."""
+
+    def __init__(self, be: Backend, max_cols: int):
+        self.be, self.max_cols, self.cols, self.nterms = be, int(max_cols), 0, 0
+        be.check(be.lib.dre_compress_begin(be.h, self.max_cols, 100.0))
+
+    def room_for(self, cols: int) -> bool:
+        return self.cols + cols <= self.max_cols
+
+    def add(self, terms):
+        """terms = [(alpha, DeviceMatrix of be, D)]"""
+        be = self.be
+        terms = [(a, L, np.asfortranarray(D, dtype=np.float64)) for a, L, D in terms if L.ncols]
+        if not terms:
+            return
+        nt = len(terms)
+        views = (View * nt)(*[L.view for _, L, _ in terms])
+        dptrs = (C.POINTER(C.c_double) * nt)(*[capi._dptr(D) for _, _, D in terms])
+        ldds = (C.c_int64 * nt)(*[max(D.shape[0], 1) for _, _, D in terms])
+        alphas = (C.c_double * nt)(*[float(a) for a, _, _ in terms])
+        if (self.nterms == 0 and _is_orthonormal(terms[0][1])
+                and np.count_nonzero(terms[0][2] - np.diag(np.diag(terms[0][2]))) == 0):
+            be.check(be.lib.dre_hint_orthonormal(be.h, terms[0][1].view))
+        be.check(be.lib.dre_compress_add(be.h, nt, views, dptrs, ldds, alphas))
+        self.cols += sum(L.ncols for _, L, _ in terms)
+        self.nterms += nt
+
+    def finish(self):
+        be = self.be
+        cap = max(min(self.cols, be.n), 1)
+        out = be.scratch(cap)
+        lam = np.zeros(cap)
+        newrank = C.c_int32(0)
+        be.check(be.lib.dre_compress_finish(be.h, out.view, capi._dptr(lam), C.byref(newrank)))
+        k2 = newrank.value
+        Lnew = out.cols(0, k2).copy()
+        _mark_orthonormal(Lnew)
+        return Lnew, lam[:k2]
+
+
 @_timed("compress!(::LDLt)")
 def compress_(X: LDLt) -> LDLt:
     """src/LDLt.jl:204-225 -- one C-ABI call (dre_ldlt_compress); no concatenation copy is needed."""

@@ -162,6 +162,22 @@ struct dre_symbolic {
     Symbolic sym;
 };
 
+namespace {
+// state of a rank-revealing block Gram-Schmidt run (compress!, rrqr)
+struct RRState {
+    double* Q = nullptr;   // n x qcap row-major
+    int64_t ldq = 0;
+    int qcap = 0;
+    int rho = 0;
+    double* RT = nullptr;  // ktot x ldrt row-major: coefficients of every input column in the basis
+    int64_t ldrt = 0;
+    double scale2 = 0.0;   // largest squared column norm seen so far
+    double drop_rel = 3e-15, drop_abs = 0.0;
+    int rounds = 0;
+    int skipped = 0;   // sub-panels skipped because their remainder was below the drop threshold
+};
+}  // namespace
+
 struct dre_context {
     int device = 0;
     int sm_count = 148;
@@ -237,7 +253,16 @@ struct dre_context {
     double op_a = 1.0, op_e = 0.0, op_alpha = 1.0;
     dre_view op_U{-1, 0, 0}, op_Vt{-1, 0, 0};
 
-    dre_view ortho_hint{-1, 0, 0};   // dre_hint_orthonormal: consumed by the next dre_ldlt_compress
+    dre_view ortho_hint{-1, 0, 0};   // dre_hint_orthonormal: consumed by the next dre_ldlt_compress / dre_compress_add
+    struct CompressJob {             // dre_compress_begin .. dre_compress_finish
+        bool active = false;
+        int kcap = 0, ktot = 0;
+        double tol_factor = 100.0;
+        RRState s;
+        std::vector<double> signs;
+        struct Dense { int row0 = 0, k = 0; std::vector<double> C; };
+        std::vector<Dense> dense;
+    } cjob;
     // asynchronous residual norm (dre_ldlt_norm_begin / _end): own stream, events, workspaces and pinned slot
     cudaStream_t norm_st = nullptr;
     cudaEvent_t norm_in = nullptr, norm_done = nullptr;
@@ -793,18 +818,6 @@ int shifted_solve(dre_context* c, double mu_re, double mu_im, dre_view R, dre_vi
 // ---------------------------------------------------------------------------------------------
 // rank-revealing block Gram-Schmidt (shared by compress! and rrqr)
 // ---------------------------------------------------------------------------------------------
-struct RRState {
-    double* Q = nullptr;   // n x qcap row-major
-    int64_t ldq = 0;
-    int qcap = 0;
-    int rho = 0;
-    double* RT = nullptr;  // ktot x ldrt row-major: coefficients of every input column in the basis
-    int64_t ldrt = 0;
-    double scale2 = 0.0;   // largest squared column norm seen so far
-    double drop_rel = 3e-15, drop_abs = 0.0;
-    int rounds = 0;
-    int skipped = 0;   // sub-panels skipped because their remainder was below the drop threshold
-};
 
 struct RRChunk {
     const double* src;        // n x cols columns of an input term (row-major, leading dimension lds)
@@ -1896,25 +1909,21 @@ static int rr_setup(dre_context* c, RRState& s, int ktot, double drop_rel, doubl
     return DRE_OK;
 }
 
-int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, const double* const* Ds,
-                          const int64_t* ldds, const double* alphas, double tol_factor, dre_view out, double* lam,
-                          int32_t* newrank) {
+// compress! in three phases (dre_compress_begin / _add / _finish; dre_ldlt_compress = all three in one call).  The job
+// (basis, coefficient rows, signs, dense cores) lives in the context between the calls, so that a caller who receives
+// the terms one by one -- the compression lane of the multi-GPU pipeline mode -- can orthogonalise each increment while
+// the next one is still being computed, and only the core / eigen / L <- QV tail is left when compress! is due.
+int32_t dre_compress_begin(dre_context* c, int32_t max_cols, double tol_factor) {
     if (c) cudaSetDevice(c->device);   // may be the first CUDA call of a host thread (compression lane)
-    if (!c || !Ls || !Ds || !ldds || !alphas || !lam || !newrank) return fail(c, DRE_ERR_ARG, "null argument");
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
     if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
-    int rc;
-    int ktot = 0;
-    for (int t = 0; t < nterms; ++t) {
-        if ((rc = check_view(c, Ls[t], "Ls[i]", true))) return rc;
-        ktot += Ls[t].ncols;
-    }
-    if ((rc = check_view(c, out, "out", true))) return rc;
-    TlScope tl("compress", 0, c->st);
-    *newrank = 0;
-    if (ktot == 0) return DRE_OK;
-    const int64_t n = c->sym.n;
-    Range r_compress("compress!(::LDLt)");
-    RRState s;
+    if (max_cols < 0) return fail(c, DRE_ERR_ARG, "compress: negative capacity");
+    dre_context::CompressJob& job = c->cjob;
+    job = dre_context::CompressJob{};
+    job.active = true;
+    job.kcap = max_cols;
+    job.tol_factor = tol_factor;
+    if (max_cols == 0) return DRE_OK;
     // Basis directions are dropped at HALF the relative level at which compress! truncates the eigenvalues of the
     // projected core below (tol_factor * eps, src/LDLt.jl:216-217): a direction whose coefficients are below
     // sigma * scale changes X by at most O(sigma) ||X|| through its cross terms with the large directions, i.e. by
@@ -1923,19 +1932,42 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     // increments "found" one to three noise directions per sub-panel: two thirds of all selection rounds.)
     static const double drop_env = getenv("DRE_RR_DROP") ? atof(getenv("DRE_RR_DROP")) : 0.0;
     const double drop_rel = drop_env > 0.0 ? drop_env : 0.5 * tol_factor * 2.220446049250313e-16;
-    if ((rc = rr_setup(c, s, ktot, drop_rel, 0.0))) return rc;
+    int rc;
+    if ((rc = rr_setup(c, job.s, max_cols, drop_rel, 0.0))) return rc;
+    CU(c->cscale.ensure((size_t)max_cols));
+    job.signs.reserve(max_cols);
+    return DRE_OK;
+}
+
+int32_t dre_compress_add(dre_context* c, int32_t nterms, const dre_view* Ls, const double* const* Ds,
+                         const int64_t* ldds, const double* alphas) {
+    if (c) cudaSetDevice(c->device);
+    if (!c || !Ls || !Ds || !ldds || !alphas) return fail(c, DRE_ERR_ARG, "null argument");
+    dre_context::CompressJob& job = c->cjob;
+    if (!job.active) return fail(c, DRE_ERR_STATE, "dre_compress_add without dre_compress_begin");
+    int rc;
+    int kadd = 0;
+    for (int t = 0; t < nterms; ++t) {
+        if ((rc = check_view(c, Ls[t], "Ls[i]", true))) return rc;
+        kadd += Ls[t].ncols;
+    }
     const dre_view hint = c->ortho_hint;
     c->ortho_hint = dre_view{-1, 0, 0};
-    std::vector<double> signs(ktot, 1.0);
-    struct DenseTerm { int t, row0, k; };
-    std::vector<DenseTerm> dense_terms;
+    if (kadd == 0) return DRE_OK;
+    if (job.ktot + kadd > job.kcap) return fail(c, DRE_ERR_ARG, "compress: more columns than dre_compress_begin reserved");
+    TlScope tl("compress", 0, c->st);
+    const int64_t n = c->sym.n;
+    Range r_compress("compress!(::LDLt)");
+    RRState& s = job.s;
     // column scalings |alpha d_j|^(1/2) of the diagonal-core terms (1 for the columns of dense-core terms, whose core
     // enters after the basis is built, exactly as in the reference, src/LDLt.jl:206-213), uploaded once
-    if ((rc = ensure_pinned(c, (size_t)ktot + 64))) return rc;
+    if ((rc = ensure_pinned(c, (size_t)kadd + 64))) return rc;
     const double t_e0 = wall_ms();
     CU(cudaStreamSynchronize(c->st));
     const double t_e1 = wall_ms();
     std::vector<char> is_diag(nterms, 0);
+    const int base = job.ktot;
+    job.signs.resize((size_t)base + kadd, 1.0);
     {
         int row0 = 0;
         for (int t = 0; t < nterms; ++t) {
@@ -1953,41 +1985,51 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
                 if (diag) {
                     const double v = alphas[t] * D[j + (int64_t)j * ldd];
                     c->h_pinned[row0 + j] = std::sqrt(std::fabs(v));
-                    signs[row0 + j] = (v < 0.0) ? -1.0 : 1.0;
+                    job.signs[base + row0 + j] = (v < 0.0) ? -1.0 : 1.0;
                 } else {
                     c->h_pinned[row0 + j] = 1.0;
                 }
             }
-            if (!diag) dense_terms.push_back({t, row0, k});
+            if (!diag) {   // the symmetrised core alpha (D + D') / 2 is kept until dre_compress_finish
+                dre_context::CompressJob::Dense dt;
+                dt.row0 = base + row0;
+                dt.k = k;
+                dt.C.resize((size_t)k * k);
+                for (int j = 0; j < k; ++j)
+                    for (int i = 0; i < k; ++i)
+                        dt.C[i + (size_t)j * k] = 0.5 * alphas[t] * (D[i + (int64_t)j * ldd] + D[j + (int64_t)i * ldd]);
+                job.dense.push_back(std::move(dt));
+            }
             row0 += k;
         }
     }
-    CU(c->cscale.ensure((size_t)ktot));
-    CU(cudaMemcpyAsync(c->cscale.p, c->h_pinned, ktot * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->cscale.p + base, c->h_pinned, kadd * sizeof(double), cudaMemcpyHostToDevice, c->st));
     std::vector<RRChunk> chunks;
     {
         int row0 = 0;
         for (int t = 0; t < nterms; ++t) {
             const int k = Ls[t].ncols;
             if (k == 0) continue;
-            const bool hinted = is_diag[t] && s.rho == 0 && chunks.empty() && hint.id == Ls[t].id &&
+            const bool hinted = is_diag[t] && s.rho == 0 && job.ktot == 0 && chunks.empty() && hint.id == Ls[t].id &&
                                 hint.col0 == Ls[t].col0 && hint.ncols == Ls[t].ncols && k + 64 <= s.qcap;
             if (hinted) {
                 // the caller vouches that these columns are orthonormal (the outer factor a previous compress!
                 // produced): they ARE the first k basis vectors, their coefficients are the column scalings
                 launch_copy_scale(s.Q, s.ldq, vptr(c, Ls[t]), vld(c, Ls[t]), n, k, nullptr, c->st,
                                   &c->stats.kernel_launches);
-                CU(cudaMemcpy2DAsync(s.RT + (int64_t)row0 * s.ldrt, (size_t)(s.ldrt + 1) * sizeof(double),
-                                     c->cscale.p + row0, sizeof(double), sizeof(double), k, cudaMemcpyDeviceToDevice,
-                                     c->st));
+                CU(cudaMemcpy2DAsync(s.RT + (int64_t)(base + row0) * s.ldrt, (size_t)(s.ldrt + 1) * sizeof(double),
+                                     c->cscale.p + base + row0, sizeof(double), sizeof(double), k,
+                                     cudaMemcpyDeviceToDevice, c->st));
                 for (int j = 0; j < k; ++j) s.scale2 = std::max(s.scale2, c->h_pinned[row0 + j] * c->h_pinned[row0 + j]);
                 s.rho = k;
             } else {
-                rr_add_term(chunks, vptr(c, Ls[t]), vld(c, Ls[t]), k, is_diag[t] ? c->cscale.p + row0 : nullptr, row0);
+                rr_add_term(chunks, vptr(c, Ls[t]), vld(c, Ls[t]), k, is_diag[t] ? c->cscale.p + base + row0 : nullptr,
+                            base + row0);
             }
             row0 += k;
         }
     }
+    job.ktot += kadd;
     CU(cudaStreamSynchronize(c->st));   // (h_pinned is reused by the rounds)
     const double t_w0 = wall_ms();
     {
@@ -1995,6 +2037,31 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
         HostTrace tr("compress: rank-revealing Gram-Schmidt", c->st);
         if ((rc = rr_process_chunks(c, s, chunks))) return rc;
     }
+    if (g_rr_stats) {
+        g_rr.ms_entry_sync += t_e1 - t_e0;
+        g_rr.ms_setup += t_w0 - t_e1;
+        g_rr.ms_rounds += wall_ms() - t_w0;
+    }
+    return check_errflag(c);
+}
+
+int32_t dre_compress_finish(dre_context* c, dre_view out, double* lam, int32_t* newrank) {
+    if (c) cudaSetDevice(c->device);
+    if (!c || !lam || !newrank) return fail(c, DRE_ERR_ARG, "null argument");
+    dre_context::CompressJob& job = c->cjob;
+    if (!job.active) return fail(c, DRE_ERR_STATE, "dre_compress_finish without dre_compress_begin");
+    job.active = false;
+    int rc;
+    if ((rc = check_view(c, out, "out", true))) return rc;
+    *newrank = 0;
+    const int ktot = job.ktot;
+    if (ktot == 0) return DRE_OK;
+    TlScope tl("compress", 0, c->st);
+    Range r_compress("compress!(::LDLt)");
+    const int64_t n = c->sym.n;
+    RRState& s = job.s;
+    const double tol_factor = job.tol_factor;
+    const std::vector<double>& signs = job.signs;
     const int rho = s.rho;
     if (rho == 0) return check_errflag(c);
     // S = RT' C RT (rho x rho), C = blockdiag(diag(signs) for the scaled diagonal-core terms, alpha_t D_t for the
@@ -2008,20 +2075,14 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     CU(c->gbuf.ensure((size_t)rho * rho));
     // M = C RT: rows of the diagonal-core terms scaled by their signs (exact), dense-core blocks replaced by
     // C_t RT_block; then S = RT' M is an ordinary Gram product over the ktot coefficient rows on the DMMA path
-    // (the row-weighted scalar kernel spent 5-10 ms on the 2.5 GFLOP of a rank-700 core).
     CU(c->rt2.ensure((size_t)ktot * s.ldrt));
     launch_copy_scale(c->rt2.p, s.ldrt, s.RT, s.ldrt, ktot, rho, nullptr, c->st, &c->stats.kernel_launches, c->evals.p);
     CU(cudaGetLastError());
-    for (const DenseTerm& dt : dense_terms) {
-        const double* D = Ds[dt.t];
-        const int64_t ldd = ldds[dt.t];
+    for (const dre_context::CompressJob::Dense& dt : job.dense) {
         const int k = dt.k;
         if ((rc = ensure_pinned(c, (size_t)k * k + 64))) return rc;
         CU(cudaStreamSynchronize(c->st));
-        for (int j = 0; j < k; ++j)
-            for (int i = 0; i < k; ++i)
-                c->h_pinned[i + (int64_t)j * k] =
-                    0.5 * alphas[dt.t] * (D[i + (int64_t)j * ldd] + D[j + (int64_t)i * ldd]);
+        std::memcpy(c->h_pinned, dt.C.data(), (size_t)k * k * sizeof(double));
         CU(c->gbuf2.ensure((size_t)k * k));
         CU(cudaMemcpyAsync(c->gbuf2.p, c->h_pinned, (size_t)k * k * sizeof(double), cudaMemcpyHostToDevice, c->st));
         // M_block (k x rho) = C_t (k x k, symmetric) * RT_block (k x rho)
@@ -2062,14 +2123,32 @@ int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, co
     }
     if (g_rr_stats) {
         g_rr.calls++;
-        g_rr.ms_entry_sync += t_e1 - t_e0;
-        g_rr.ms_setup += t_w0 - t_e1;
-        g_rr.ms_rounds += t_w1 - t_w0;
         g_rr.ms_core += t_w2 - t_w1;
         g_rr.ms_eig += t_w3 - t_w2;
         g_rr.ms_final += wall_ms() - t_w3;
     }
     return check_errflag(c);
+}
+
+int32_t dre_ldlt_compress(dre_context* c, int32_t nterms, const dre_view* Ls, const double* const* Ds,
+                          const int64_t* ldds, const double* alphas, double tol_factor, dre_view out, double* lam,
+                          int32_t* newrank) {
+    if (c) cudaSetDevice(c->device);   // may be the first CUDA call of a host thread (compression lane)
+    if (!c || !Ls || !Ds || !ldds || !alphas || !lam || !newrank) return fail(c, DRE_ERR_ARG, "null argument");
+    if (!c->has_pencil) return fail(c, DRE_ERR_STATE, "no pencil set");
+    int rc;
+    int ktot = 0;
+    for (int t = 0; t < nterms; ++t) {
+        if ((rc = check_view(c, Ls[t], "Ls[i]", true))) return rc;
+        ktot += Ls[t].ncols;
+    }
+    if ((rc = check_view(c, out, "out", true))) return rc;
+    *newrank = 0;
+    const dre_view hint = c->ortho_hint;   // (dre_compress_begin leaves it alone; _add consumes it)
+    if ((rc = dre_compress_begin(c, ktot, tol_factor))) return rc;
+    c->ortho_hint = hint;
+    if ((rc = dre_compress_add(c, nterms, Ls, Ds, ldds, alphas))) { c->cjob.active = false; return rc; }
+    return dre_compress_finish(c, out, lam, newrank);
 }
 
 int32_t dre_hint_orthonormal(dre_context* c, dre_view v) {

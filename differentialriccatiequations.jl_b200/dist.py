@@ -571,15 +571,57 @@ def serve(api):
     th = threading.Thread(target=receiver, name="dre-pipe-receiver", daemon=True)
     th.start()
 
-    def compress_now():
-        nonlocal terms
-        live = [(a, L, np.asfortranarray(D)) for a, L, D in terms if L.ncols]
-        if len(live) == 1 and api._is_orthonormal(live[0][1]):
+    # Streaming compress! (default; DRE_PIPE_STREAM=0: one dre_ldlt_compress call per compression point): every term
+    # is handed to the open job (api.CompressStream = dre_compress_begin / _add / _finish) as soon as it has arrived,
+    # so the lane orthogonalises increment i while rank 0 computes i+1 and only the core / eigen / L <- QV tail is
+    # left when the compression point comes.  Same terms in the same order: same result.
+    streaming = os.environ.get("DRE_PIPE_STREAM", "1") not in ("", "0")
+    job = None       # open CompressStream; job_n = how many of `terms` it holds
+    job_n = 0
+
+    def feed():
+        """Hand the terms that are not in the job yet to it (opening one when at least two terms exist)."""
+        nonlocal job, job_n
+        if not streaming or be is None:
             return
-        if not live:
+        live = [(a, L, D) for a, L, D in terms if L.ncols]
+        if job is None:
+            if len(live) < 2:
+                return
+            # room for the terms at hand plus a dozen increments of the widest kind seen so far; if a solve ever
+            # needs more, the job is dropped and the compression point falls back to the one-call path
+            widest = max(L.ncols for _, L, _ in live)
+            job = api.CompressStream(be, sum(L.ncols for _, L, _ in live) + 16 * max(widest, 64))
+            job_n = 0
+        new = live[job_n:]
+        if not new:
+            return
+        if not job.room_for(sum(L.ncols for _, L, _ in new)):
+            job = None
+            job_n = 0
             return
         t0 = time.perf_counter()
-        Lnew, lam = api._compress_call(be, live)
+        job.add(new)
+        served["busy_s"] += time.perf_counter() - t0
+        job_n = len(live)
+
+    def compress_now():
+        nonlocal terms, job, job_n
+        live = [(a, L, np.asfortranarray(D)) for a, L, D in terms if L.ncols]
+        if len(live) == 1 and api._is_orthonormal(live[0][1]):
+            job, job_n = None, 0
+            return
+        if not live:
+            job, job_n = None, 0
+            return
+        feed()
+        t0 = time.perf_counter()
+        if job is not None and job_n == len(live):
+            Lnew, lam = job.finish()
+            served["streamed"] = served.get("streamed", 0) + 1
+        else:
+            Lnew, lam = api._compress_call(be, live)
+        job, job_n = None, 0
         be.ctx.sync()
         served["busy_s"] += time.perf_counter() - t0
         served["compressions"] += 1
@@ -597,15 +639,18 @@ def serve(api):
             n = int(h[1])
             if be is None or be.n != n:
                 terms = []
+                job, job_n = None, 0
                 be = api._pipe_lane_backend(n, p.device)
             if h[2] == 0.0:
                 terms = []
+                job, job_n = None, 0
         elif cmd == CMD_TERM:
             k, alpha, diag = int(h[1]), h[2], h[3] != 0.0
             D = np.diag(core) if diag else core.reshape(k, k, order="F")
             L = api.DeviceMatrix(_TensorPanel(be, tensor, k), 0, k)
             terms.append((alpha, L, np.asfortranarray(D)))
             served["terms"] += 1
+            feed()
         elif cmd == CMD_COMPRESS:
             compress_now()
         elif cmd == CMD_FETCH:

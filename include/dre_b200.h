@@ -183,7 +183,18 @@ DRE_API int32_t dre_ldlt_norm_end(dre_context* ctx, double* out);
 DRE_API int32_t dre_ldlt_compress(dre_context* ctx, int32_t nterms, const dre_view* Ls, const double* const* Ds,
                           const int64_t* ldds, const double* alphas, double tol_factor, dre_view out,
                           double* lam, int32_t* newrank);
-/* Hint for the NEXT dre_ldlt_compress only: the columns of `v` are orthonormal (they are the outer factor a
+/* The same compress! in three phases, for callers that receive the terms of X one by one (the compression lane of the
+ * multi-GPU pipeline mode appends one ADI increment per step, src/lyapunov/adi.jl:170-176, and compresses every
+ * `compression_interval` steps, :143-147): _begin reserves room for at most max_cols columns in total and resets the
+ * job; every _add orthogonalises its terms against the basis built so far (so the work of an increment overlaps the
+ * computation of the next one); _finish runs the core / eigen-decomposition / L <- Q V tail and ends the job.
+ * dre_ldlt_compress(terms) == _begin(total columns) + _add(terms) + _finish.  One job per context at a time;
+ * the panels passed to _add must stay alive and unchanged only for the duration of that call. */
+DRE_API int32_t dre_compress_begin(dre_context* ctx, int32_t max_cols, double tol_factor);
+DRE_API int32_t dre_compress_add(dre_context* ctx, int32_t nterms, const dre_view* Ls, const double* const* Ds,
+                         const int64_t* ldds, const double* alphas);
+DRE_API int32_t dre_compress_finish(dre_context* ctx, dre_view out, double* lam, int32_t* newrank);
+/* Hint for the NEXT dre_ldlt_compress / dre_compress_add only: the columns of `v` are orthonormal (they are the outer factor a
  * previous compress! produced, src/LDLt.jl:219-222).  If `v` is the first term of that call and its core is
  * diagonal, its columns are adopted as the first basis vectors without re-orthogonalisation.  Results agree
  * with the unhinted call to round-off. */

@@ -37,6 +37,47 @@ def emulated(monkeypatch):
 def _rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
+def _streamed_compress_case(n, rng):
+    """An ADI-shaped compress!: an orthonormal first term with a diagonal core plus increments that mostly lie in its
+    span, one term with a dense core; returns (terms as host arrays, dense X)."""
+    Q0, _ = np.linalg.qr(rng.standard_normal((n, 40)))
+    d0 = rng.standard_normal(40)
+    terms = [(1.0, Q0, np.diag(d0))]
+    dense = Q0 @ np.diag(d0) @ Q0.T
+    for i in range(4):
+        V = Q0 @ rng.standard_normal((40, 24)) * 10.0 ** (-i) + 10.0 ** (-2 * i - 1) * rng.standard_normal((n, 24))
+        if i == 2:
+            S = rng.standard_normal((24, 24))
+            S = S + S.T
+        else:
+            S = np.diag(rng.standard_normal(24))
+        a = -0.7 * (i + 1)
+        terms.append((a, V, S))
+        dense = dense + a * V @ S @ V.T
+    return terms, dense
+
+
+def test_emulated_streamed_compress_matches_one_call(emulated):
+    """dre_compress_begin / _add / _finish against dre_ldlt_compress and the dense sum (emulator twin of
+    tests/test_gpu_kernels.py::test_streamed_compress_matches_one_call)."""
+    emulated()
+    n = 371
+    E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
+    api.upload_pencil(E, A)
+    terms, dense = _streamed_compress_case(n, np.random.default_rng(11))
+    be = api.backend()
+    dev = [(a, api.DeviceMatrix.from_host(L), np.asfortranarray(D)) for a, L, D in terms]
+    L1, lam1 = api._compress_call(be, dev)
+    job = api.CompressStream(be, sum(L.shape[1] for _, L, _ in terms) + 64)
+    job.add(dev[:2])
+    for t in dev[2:]:
+        job.add([t])
+    L2, lam2 = job.finish()
+    X1 = L1.to_host() @ np.diag(lam1) @ L1.to_host().T
+    X2 = L2.to_host() @ np.diag(lam2) @ L2.to_host().T
+    assert _rel(X1, dense) < 1e-12 and _rel(X2, dense) < 1e-12
+    assert abs(len(lam1) - len(lam2)) <= 1
+
 
 def test_emulated_abi_block_solve_smw_and_compress(emulated):
     """dre_shift_solve incl. the fused Sherman-Morrison-Woodbury correction (real and complex shift),
