@@ -571,11 +571,16 @@ def serve(api):
     th = threading.Thread(target=receiver, name="dre-pipe-receiver", daemon=True)
     th.start()
 
-    # Streaming compress! (default; DRE_PIPE_STREAM=0: one dre_ldlt_compress call per compression point): every term
-    # is handed to the open job (api.CompressStream = dre_compress_begin / _add / _finish) as soon as it has arrived,
-    # so the lane orthogonalises increment i while rank 0 computes i+1 and only the core / eigen / L <- QV tail is
-    # left when the compression point comes.  Same terms in the same order: same result.
-    streaming = os.environ.get("DRE_PIPE_STREAM", "1") not in ("", "0")
+    # Streaming compress! (DRE_PIPE_STREAM=1, opt-in): every term is handed to the open job (api.CompressStream =
+    # dre_compress_begin / _add / _finish) as soon as it has arrived, so the lane orthogonalises increment i while
+    # rank 0 computes i+1 and only the core / eigen / L <- QV tail is left when the compression point comes.
+    # Measured on two B200s (profiles/r02_results.md, run r02w): 1.69 steps/s against 1.78 with one
+    # dre_ldlt_compress call per compression point -- one-term jobs lose the look-ahead overlap of the chunk pipeline
+    # (lane busy 47 instead of 43 ms per compress!), the lane stays the longer of the two lanes either way, and the
+    # different projection order changes round-off, i.e. the free-running shift sequence (the 2-GPU run is no longer
+    # bit-identical to the 1-GPU run).  It becomes the right default once compress! is shorter than the ten
+    # iterations it covers.
+    streaming = os.environ.get("DRE_PIPE_STREAM", "0") not in ("", "0")
     job = None       # open CompressStream; job_n = how many of `terms` it holds
     job_n = 0
 
