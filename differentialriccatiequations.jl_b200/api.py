@@ -42,6 +42,10 @@ EPS = float(np.finfo(np.float64).eps)
 _backend = None
 
 
+# DRE_CHECK_PENCIL=0 skips the content check when the very same matrix objects are passed again
+_CHECK_PENCIL_VALUES = _os.environ.get("DRE_CHECK_PENCIL", "1") not in ("", "0")
+
+
 class Backend:
     def __init__(self, device=0):
         self.device = device
@@ -53,16 +57,40 @@ class Backend:
         self.E = self.A = None
         self.n = None
 
+    @staticmethod
+    def _pencil_key(E, A):
+        """Content key of the pencil (shape, nnz and a CRC of structure and values): an equal copy of the resident
+        pencil is recognised (no re-upload that would invalidate every DeviceMatrix), values changed in place are too
+        (no stale factorization).  ~4 ms at n = 79 841; evaluated once per solve / init, never per ADI step."""
+        import zlib
+
+        def crc(M):
+            c = 0
+            for arr in (M.indptr, M.indices, M.data):
+                c = zlib.crc32(np.ascontiguousarray(arr).view(np.uint8), c)
+            return c
+
+        return (E.shape, A.shape, E.nnz, A.nnz, E.format, A.format, crc(E), crc(A))
+
     def ensure_pencil(self, E, A):
-        key = (id(E), id(A), E.shape, E.nnz, A.nnz)
-        if self.pencil_key == key:
-            return
         if not (sp.issparse(E) and sp.issparse(A)):
             raise TypeError("E and A must be scipy sparse matrices")
+        def quick(M):   # cheap signature for the hot case below (0.3 ms at n = 79 841)
+            return (M.nnz, float(M.data.sum()), float(np.dot(M.data, M.data)))
+
+        if getattr(self, "E", None) is E and getattr(self, "A", None) is A and self.pencil_key is not None:
+            # the very objects of the last call (every time step of a Rosenbrock solve): only an in-place change of
+            # their values is possible, which the sums catch
+            if not _CHECK_PENCIL_VALUES or self._pencil_quick == (quick(E), quick(A)):
+                return
+        key = self._pencil_key(E, A)
+        if self.pencil_key == key:
+            self.E, self.A, self._pencil_quick = E, A, (quick(E), quick(A))
+            return
         self.ctx.set_pencil(E, A)
         self.generation += 1
         self.pencil_key = key
-        self.E, self.A = E, A  # keep alive: the key uses id()
+        self.E, self.A, self._pencil_quick = E, A, (quick(E), quick(A))
         self.n = E.shape[0]
 
     def check(self, rc):

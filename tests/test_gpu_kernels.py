@@ -370,3 +370,23 @@ def test_symmetric_eigensolver_vs_lapack(k):
         assert np.linalg.norm(V.T @ V - np.eye(k)) <= 50 * k * 2.2e-16
         assert np.linalg.norm(S @ V - V * w) <= 50 * k * 2.2e-16 * nrm
         assert np.max(np.abs(w - np.linalg.eigvalsh(S))) <= 50 * k * 2.2e-16 * nrm
+
+
+def test_pencil_is_recognised_by_content(rail):
+    """an equal copy of the resident pencil does not trigger a re-upload (which would invalidate every
+    DeviceMatrix), values changed in place do."""
+    E, A, B, C = rail
+    be = api.backend()
+    g = be.generation
+    M = api.DeviceMatrix.from_host(np.ones((E.shape[0], 2)))
+    E2 = E.copy()
+    api.upload_pencil(E2, A)
+    assert be.generation == g
+    assert np.array_equal(M.to_host(), np.ones((E.shape[0], 2)))      # the panel is still valid
+    E2.data *= 2.0
+    api.upload_pencil(E2, A)
+    assert be.generation == g + 1
+    Y = api.spmm("E", api.DeviceMatrix.from_host(np.ones((E.shape[0], 2))))
+    assert _rel(Y.to_host(), 2.0 * (E @ np.ones((E.shape[0], 2)))) < 1e-14
+    api.upload_pencil(E, A)
+    assert be.generation == g + 2

@@ -149,3 +149,19 @@ def test_threaded_dissection_is_deterministic(monkeypatch):
         else:
             for k in names:
                 assert np.array_equal(ref[k], cur[k]), (threads, k)
+
+
+def test_pencil_key_is_content_based():
+    """the resident pencil is recognised by content (an equal copy does not trigger a re-upload that would
+    invalidate every DeviceMatrix; values changed in place are noticed)."""
+    from dre_b200 import api
+
+    E, A, _, _, _ = dre_b200.pencils.rail_pencil(371)
+    k = api.Backend._pencil_key(E, A)
+    assert api.Backend._pencil_key(E.copy(), A.copy()) == k
+    E2 = E.copy()
+    E2.data[3] *= 1.0 + 1e-12
+    assert api.Backend._pencil_key(E2, A) != k
+    A2 = A.copy()
+    A2.indices[[0, 1]] = A2.indices[[1, 0]]
+    assert api.Backend._pencil_key(E, A2) != k
