@@ -391,8 +391,10 @@ int eig_sym(double* S, int k, double* d_evals, double* h_evals, double* work, vo
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tridiag, TD_THREADS, smem);
             max_blocks = std::max(1, per_sm) * sm_count;
         }
-        // one warp per trailing row at the start; the barrier cost grows with the CTA count
-        int grid = std::min(std::min(max_blocks, 64), (k + 7) / 8);
+        // one warp per trailing row at the start; the barrier cost grows with the CTA count, the bandwidth of the
+        // matrix-vector product too (tools/eig_grid_sweep.py on the B200: k = 420: 3.75 / 3.08 / 3.04 ms with 32 / 64 /
+        // 96 CTAs, k = 690: 9.98 / 7.58 / 6.36 ms)
+        int grid = std::min(std::min(max_blocks, k > 512 ? 96 : 64), (k + 7) / 8);
         grid = std::max(grid, 1);
         if (const char* ev = getenv("DRE_EIG_GRID")) grid = std::max(1, std::min(atoi(ev), max_blocks));
         void* args[] = {&S, &k, &d, &e, &Vst, &tau, &pbuf};
