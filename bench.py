@@ -397,10 +397,11 @@ def _run_ours(args):
                    (f"one solve on {world} GPUs, column mode: RHS column blocks of every ADI block solve sharded over the "
                     f"ranks, replicated per-shift factorization, NCCL all-gather of the solved blocks; Gram / compression "
                     f"/ shift generation replicated" if mode == "columns" else
-                    f"one solve on {world} GPUs as a two-stage pipeline: rank 0 runs the ADI iteration chain (factor, "
-                    f"sweeps, SMW, SpMM, norms, shifts) and streams every increment of X to rank 1 over NCCL, rank 1 "
-                    f"holds X and runs compress!; ranks >= 2 ({max(world - 2, 0)} of them) have no lane of this path and "
-                    f"idle"),
+                    f"one solve on {world} GPUs as a pipeline: rank 0 runs the ADI iteration chain (factor, sweeps, SMW, "
+                    f"SpMM, norms, shifts) and streams every increment of X over NCCL to {_nlanes()} compression lane(s) "
+                    f"(rank 1" + (" and rank 2, taking the compression points in turn" if _nlanes() > 1 else "") +
+                    f"), which hold X and run compress!; the other {max(world - 1 - _nlanes(), 0)} rank(s) have no lane "
+                    f"of this path and idle"),
                    "l2_policy": "inputs larger than L2: factor panels + RHS/solution panels + X factor exceed 126 MB",
                    "adi_iters_per_timed_step": ct.iters, "rank_X_and_residual": ct.ranks,
                    "symbolic": info,
@@ -633,6 +634,13 @@ def run_config5(args):
                                "serialised device times, the wall times include that instrumentation"},
             "solves": out}
     print(json.dumps(line), flush=True)
+
+
+def _nlanes():
+    from dre_b200 import dist as ddist
+
+    p = ddist.pipe_state()
+    return p.nlanes if p is not None else 0
 
 
 def main():

@@ -541,6 +541,10 @@ class CompressStream:
     def room_for(self, cols: int) -> bool:
         return self.cols + cols <= self.max_cols
 
+    def scale_hint(self, scale: float):
+        """The largest scaled column norm the job will meet (dre_compress_scale_hint); before the first add."""
+        self.be.check(self.be.lib.dre_compress_scale_hint(self.be.h, float(scale)))
+
     def add(self, terms):
         """terms = [(alpha, DeviceMatrix of be, D)]"""
         be = self.be

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "dre_symbolic_export", "dre_create", "dre_destroy", "dre_sync", "dre_set_pencil", "dre_get_symbolic_info",
     "dre_mat_create", "dre_mat_free", "dre_mat_upload", "dre_mat_download", "dre_mat_copy", "dre_mat_axpby",
     "dre_spmm", "dre_gemm_tn", "dre_gemm_nn", "dre_set_operator", "dre_prefactor", "dre_shift_solve", "dre_adi_step", "dre_adi_solve", "dre_mat_devptr", "dre_get_stream", "dre_set_dense_only", "dre_mat_wrap",
-    "dre_ldlt_norm", "dre_ldlt_norm_begin", "dre_ldlt_norm_end", "dre_ldlt_compress", "dre_compress_begin", "dre_compress_add", "dre_compress_finish", "dre_hint_orthonormal", "dre_rrqr", "dre_debug_export", "dre_debug_eigh", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
+    "dre_ldlt_norm", "dre_ldlt_norm_begin", "dre_ldlt_norm_end", "dre_ldlt_compress", "dre_compress_begin", "dre_compress_scale_hint", "dre_compress_add", "dre_compress_finish", "dre_hint_orthonormal", "dre_rrqr", "dre_debug_export", "dre_debug_eigh", "dre_timer_start", "dre_timer_stop", "dre_stats_reset",
     "dre_stats_get", "dre_arnoldi_orth",
 ]
 
@@ -111,6 +111,7 @@ def load():
     lib.dre_ldlt_compress.argtypes = [p, i32, C.POINTER(View), C.POINTER(pdbl), pi64, pdbl, dbl, View, pdbl,
                                       C.POINTER(i32)]
     lib.dre_compress_begin.argtypes = [p, i32, dbl]
+    lib.dre_compress_scale_hint.argtypes = [p, dbl]
     lib.dre_compress_add.argtypes = [p, i32, C.POINTER(View), C.POINTER(pdbl), pi64, pdbl]
     lib.dre_compress_finish.argtypes = [p, View, pdbl, C.POINTER(i32)]
     lib.dre_hint_orthonormal.argtypes = [p, View]

@@ -1939,6 +1939,14 @@ int32_t dre_compress_begin(dre_context* c, int32_t max_cols, double tol_factor) 
     return DRE_OK;
 }
 
+int32_t dre_compress_scale_hint(dre_context* c, double scale) {
+    if (!c) return fail(nullptr, DRE_ERR_ARG, "null context");
+    if (!c->cjob.active) return fail(c, DRE_ERR_STATE, "dre_compress_scale_hint without dre_compress_begin");
+    if (!(scale >= 0.0) || !std::isfinite(scale)) return fail(c, DRE_ERR_ARG, "compress: bad scale hint");
+    c->cjob.s.scale2 = std::max(c->cjob.s.scale2, scale * scale);
+    return DRE_OK;
+}
+
 int32_t dre_compress_add(dre_context* c, int32_t nterms, const dre_view* Ls, const double* const* Ds,
                          const int64_t* ldds, const double* alphas) {
     if (c) cudaSetDevice(c->device);

@@ -244,15 +244,19 @@ def assert_same_int(v: int, what: str):
 # Control messages travel over a gloo group (CPU tensors), panels over NCCL.  Same arithmetic on the same operands
 # in the same order as the single-GPU path: results are identical.
 _PIPE = None
-CMD_STOP, CMD_BEGIN, CMD_TERM, CMD_COMPRESS, CMD_FETCH = 0, 1, 2, 3, 4
+CMD_STOP, CMD_BEGIN, CMD_TERM, CMD_COMPRESS, CMD_FETCH, CMD_PREV = 0, 1, 2, 3, 4, 5
 _HDR = 8
 
 
 class _Pipe:
     def __init__(self, rank, world, device, ctl, data_backend):
         self.rank, self.world, self.device, self.ctl, self.data_backend = rank, world, device, ctl, data_backend
-        self.token = 0            # identifies the compressed factor rank 1 currently holds as its first term
+        self.token = 0            # identifies the compressed factor the holding lane currently has as its first term
         self.sends = []           # outstanding isend works (and the panels they read)
+        # DRE_PIPE_LANES=2 (needs >= 3 ranks): two compression lanes take the compression points in turn, see serve()
+        self.nlanes = max(1, min(world - 1, int(os.environ.get("DRE_PIPE_LANES", "1"))))
+        self.lanes = list(range(1, 1 + self.nlanes))
+        self.cur = 1              # rank 0: the lane the next terms go to (= the lane that holds X between solves)
         self.stats = {"terms_sent": 0, "bytes_sent": 0, "compress_cmds": 0, "fetches": 0, "fetch_wait_s": 0.0}
 
 
@@ -409,9 +413,21 @@ def _recv_small(count, src):
 
 
 # ---- rank 0 side -------------------------------------------------------------------------------------------------
+def _scale_of(X0):
+    """sqrt of the largest |alpha d_j| over the diagonal-core terms of X0 (0 if unknown): the column scale compress!
+    measures its drop threshold against; a lane that starts a job without X needs it as a hint."""
+    sc = 0.0
+    for a, L, D in zip(X0.alphas, X0.Ls, X0.Ds):
+        D = np.asarray(D)
+        if L.ncols and D.ndim == 2 and D.shape[0] and np.count_nonzero(D - np.diag(np.diag(D))) == 0:
+            sc = max(sc, float(np.sqrt(np.max(np.abs(a * np.diag(D))))))
+    return sc
+
+
 def pipe_begin(be, X0):
-    """Start of an ADI solve (adi.jl:29-69): rank 1's X becomes the initial guess.  If the initial guess is the
-    very factor rank 1 returned last (Ros1/Ros2 pass the previous X, lowrank_ros1.jl:48-49) nothing is transferred."""
+    """Start of an ADI solve (adi.jl:29-69): the holding lane's X becomes the initial guess.  If the initial guess is
+    the very factor that lane returned last (Ros1/Ros2 pass the previous X, lowrank_ros1.jl:48-49) nothing is
+    transferred."""
     p = _PIPE
     same = False
     if len(X0.Ls) == 1 and p.token != 0 and getattr(X0.Ls[0], "_pipe_token", None) == p.token and X0.alphas[0] == 1.0:
@@ -419,7 +435,11 @@ def pipe_begin(be, X0):
         lam = getattr(X0.Ls[0], "_pipe_lam", None)
         same = (lam is not None and D0.shape == (lam.size, lam.size) and np.array_equal(np.diag(D0), lam)
                 and np.count_nonzero(D0 - np.diag(np.diag(D0))) == 0)
-    _send_hdr(1, [CMD_BEGIN, be.n, 1.0 if same else 0.0])
+    has_base = same or any(L.ncols for L in X0.Ls)
+    scale = _scale_of(X0)
+    for lane in p.lanes:
+        mine = lane == p.cur
+        _send_hdr(lane, [CMD_BEGIN, be.n, 1.0 if (same and mine) else 0.0, 1.0 if (has_base and mine) else 0.0, scale])
     if not same:
         p.token = 0
         for a, L, D in zip(X0.alphas, X0.Ls, X0.Ds):
@@ -428,33 +448,41 @@ def pipe_begin(be, X0):
 
 
 def pipe_send_term(be, alpha, L, D):
+    dst = _PIPE.cur
     D = np.asfortranarray(np.asarray(D, dtype=np.float64))
     diag = np.count_nonzero(D - np.diag(np.diag(D))) == 0
-    _send_hdr(1, [CMD_TERM, L.ncols, float(alpha), 1.0 if diag else 0.0])
-    _send_small(np.diag(D) if diag else D, 1)
-    _send_panel(be, L, 1)
+    _send_hdr(dst, [CMD_TERM, L.ncols, float(alpha), 1.0 if diag else 0.0])
+    _send_small(np.diag(D) if diag else D, dst)
+    _send_panel(be, L, dst)
     _PIPE.stats["terms_sent"] += 1
     _reap_sends()
 
 
 def pipe_compress():
-    _send_hdr(1, [CMD_COMPRESS])
-    _PIPE.stats["compress_cmds"] += 1
+    """Compression point (adi.jl:143-147): the current lane compresses what it holds and -- with two lanes -- hands
+    the result to the other lane, which receives the following terms."""
+    p = _PIPE
+    nxt = p.lanes[(p.lanes.index(p.cur) + 1) % p.nlanes]
+    _send_hdr(p.cur, [CMD_COMPRESS, nxt])
+    p.cur = nxt
+    p.stats["compress_cmds"] += 1
 
 
 def pipe_fetch(be, make_panel):
-    """compress!(X) on rank 1 (if more than one term is pending) and its result: (DeviceMatrix, eigenvalues)."""
+    """compress!(X) on the current lane (if more than one term is pending) and its result: (DeviceMatrix, eigenvalues)."""
     import time
 
     p = _PIPE
-    _send_hdr(1, [CMD_FETCH])
+    src = p.cur
+    p.fetch_seq = getattr(p, "fetch_seq", 0) + 1
+    _send_hdr(src, [CMD_FETCH, p.fetch_seq])   # the token that will identify the returned factor (unique over lanes)
     t0 = time.perf_counter()
-    h = _recv_hdr(1)
+    h = _recv_hdr(src)
     k2, token = int(h[0]), int(h[1])
-    lam = _recv_small(k2, 1)
+    lam = _recv_small(k2, src)
     L = make_panel(k2)
     if k2:
-        _recv_panel(be, L, 1)
+        _recv_panel(be, L, src)
     p.stats["fetch_wait_s"] += time.perf_counter() - t0
     p.stats["fetches"] += 1
     _reap_sends(block=True)
@@ -473,7 +501,7 @@ def pipe_stop():
         _send_hdr(r, [CMD_STOP])
 
 
-# ---- rank 1 (and the idle ranks) ---------------------------------------------------------------------------------
+# ---- lanes (rank 1, or ranks 1 and 2) and the idle ranks ------------------------------------------------------------
 class _TensorPanel:
     """Panel of the lane's context that aliases a torch tensor (n x ld, float64) filled by the receiver thread
     (dre_mat_wrap).  Synchronises the context before the tensor goes back to torch's allocator."""
@@ -522,16 +550,26 @@ def _recv_panel_tensor(n, k, src):
 
 
 def serve(api):
-    """Rank >= 1: the compression lane (rank 1) or an idle wait for the end of the job (ranks >= 2).
+    """Rank >= 1: a compression lane or an idle wait for the end of the job.
 
-    Rank 1 runs two host threads.  The RECEIVER posts every receive as soon as rank 0 announces it (control
-    headers and cores over gloo -- whose send is a rendezvous: it completes only once the peer has posted the
-    matching receive -- and panels over NCCL into fresh torch tensors) and queues the commands in order; the
-    WORKER (this thread) appends terms and runs compress!.  With a single thread rank 0's sends waited for the
-    running compress! and the two lanes ran one after the other (profiles/r02_results.md: 1.26 steps/s on two
-    GPUs, the same as on one)."""
+    A lane runs several host threads.  The RECEIVERS (one per peer that can send to it: rank 0, and the other lane
+    when there are two) post every receive as soon as the peer announces it (control headers and cores over gloo --
+    whose send is a rendezvous: it completes only once the peer has posted the matching receive -- and panels over
+    NCCL into fresh torch tensors) and queue the messages in order; the WORKER (this thread) appends terms and runs
+    compress!.  With a single thread rank 0's sends waited for the running compress! and the two GPUs ran one after
+    the other (profiles/r02_results.md: 1.26 steps/s on two GPUs, the same as on one).
+
+    TWO LANES (DRE_PIPE_LANES=2, >= 3 ranks).  compress! number k+1 needs X_k, the result of number k, but most of
+    its work does not: the Gram-Schmidt of its ten increments among themselves.  So the lanes take the compression
+    points in turn; rank 0 sends the increments of k+1 to the lane that did not get those of k; at its compression
+    point that lane orthogonalises them first (dre_compress_begin / _add), then adds X_k -- handed over by the other
+    lane when its compress! ends -- as the LAST term (one more _add), and finishes.  Only that tail (~10 ms) is on
+    the lane-to-lane dependency chain, each lane has twice the time per compress!.  Any term order gives the same
+    X up to round-off (the orthonormal basis spans the same space); the drop threshold of the basis is relative to
+    the largest column met, which the increments-first order would only learn at the end, so the lane passes the
+    scale of the last X it knows as a hint (dre_compress_scale_hint)."""
     p = _PIPE
-    if p.rank >= 2:
+    if p.rank not in p.lanes:
         while int(_recv_hdr(0)[0]) != CMD_STOP:
             pass
         return {"role": "idle"}
@@ -539,18 +577,27 @@ def serve(api):
     import threading
     import time
 
+    me = p.rank
+    others = [r for r in p.lanes if r != me]
     be = None
-    terms = []      # (alpha, DeviceMatrix, core)
-    served = {"role": "compress", "terms": 0, "compressions": 0, "fetches": 0, "busy_s": 0.0, "idle_s": 0.0}
-    inbox = queue.Queue()
+    terms = []        # (alpha, DeviceMatrix, core) in arrival order
+    base_ok = False   # the terms at hand include X (the initial guess, or this lane's / the other lane's last result)
+    scale_hint = 0.0
+    served = {"role": "compress", "terms": 0, "compressions": 0, "fetches": 0, "busy_s": 0.0, "idle_s": 0.0,
+              "prev_wait_s": 0.0, "handovers": 0}
+    inbox = queue.Queue()      # commands of rank 0, in order
+    prevbox = queue.Queue()    # X_k handed over by the other lane
+
+    def cuda_thread_setup():
+        if p.data_backend != "gloo":
+            import torch
+
+            torch.cuda.set_device(p.device if p.device is not None else 0)
+            torch.cuda.set_stream(torch.cuda.Stream())
 
     def receiver():
         try:
-            if p.data_backend != "gloo":
-                import torch
-
-                torch.cuda.set_device(p.device if p.device is not None else 0)
-                torch.cuda.set_stream(torch.cuda.Stream())
+            cuda_thread_setup()
             n = 0
             while True:
                 h = _recv_hdr(0)
@@ -568,8 +615,23 @@ def serve(api):
         except BaseException as e:  # noqa: BLE001  (the worker re-raises it)
             inbox.put((-1, e, None, None))
 
-    th = threading.Thread(target=receiver, name="dre-pipe-receiver", daemon=True)
-    th.start()
+    def prev_receiver(src):
+        try:
+            cuda_thread_setup()
+            while True:
+                h = _recv_hdr(src)
+                if int(h[0]) == CMD_STOP:
+                    return
+                k, n = int(h[1]), int(h[2])
+                lam = _recv_small(k, src)
+                prevbox.put((lam, _recv_panel_tensor(n, k, src) if k else None, k))
+        except BaseException as e:  # noqa: BLE001
+            prevbox.put((e, None, -1))
+
+    threads = [threading.Thread(target=receiver, name="dre-pipe-receiver", daemon=True)]
+    threads += [threading.Thread(target=prev_receiver, args=(r,), name=f"dre-pipe-prev-{r}", daemon=True) for r in others]
+    for th in threads:
+        th.start()
 
     # Streaming compress! (DRE_PIPE_STREAM=1, opt-in): every term is handed to the open job (api.CompressStream =
     # dre_compress_begin / _add / _finish) as soon as it has arrived, so the lane orthogonalises increment i while
@@ -584,6 +646,13 @@ def serve(api):
     job = None       # open CompressStream; job_n = how many of `terms` it holds
     job_n = 0
 
+    def open_job(live):
+        widest = max(L.ncols for _, L, _ in live)
+        j = api.CompressStream(be, sum(L.ncols for _, L, _ in live) + 16 * max(widest, 64))
+        if not base_ok and scale_hint > 0.0:
+            j.scale_hint(scale_hint)
+        return j
+
     def feed():
         """Hand the terms that are not in the job yet to it (opening one when at least two terms exist)."""
         nonlocal job, job_n
@@ -595,8 +664,7 @@ def serve(api):
                 return
             # room for the terms at hand plus a dozen increments of the widest kind seen so far; if a solve ever
             # needs more, the job is dropped and the compression point falls back to the one-call path
-            widest = max(L.ncols for _, L, _ in live)
-            job = api.CompressStream(be, sum(L.ncols for _, L, _ in live) + 16 * max(widest, 64))
+            job = open_job(live)
             job_n = 0
         new = live[job_n:]
         if not new:
@@ -610,8 +678,38 @@ def serve(api):
         served["busy_s"] += time.perf_counter() - t0
         job_n = len(live)
 
+    def take_prev():
+        """X_k from the other lane (blocks until its compress! has ended); appended as the last term."""
+        nonlocal base_ok, scale_hint
+        t0 = time.perf_counter()
+        lam, tensor, k = prevbox.get()
+        served["prev_wait_s"] += time.perf_counter() - t0
+        if k < 0:
+            raise lam
+        if k:
+            L = api.DeviceMatrix(_TensorPanel(be, tensor, k), 0, k)
+            api._mark_orthonormal(L)      # (the outer factor of a compress!)
+            terms.append((1.0, L, np.asfortranarray(np.diag(lam))))
+            scale_hint = max(scale_hint, float(np.sqrt(np.max(np.abs(lam)))))
+        base_ok = True
+
     def compress_now():
-        nonlocal terms, job, job_n
+        nonlocal terms, job, job_n, scale_hint
+        if not base_ok:
+            # increments first, X last: everything that does not need X runs before the hand-over is awaited
+            live = [(a, L, np.asfortranarray(D)) for a, L, D in terms if L.ncols]
+            if live:
+                t0 = time.perf_counter()
+                if job is None:
+                    job = open_job(live)
+                    job_n = 0
+                if job.room_for(sum(L.ncols for _, L, _ in live[job_n:])):
+                    job.add(live[job_n:])
+                    job_n = len(live)
+                else:
+                    job, job_n = None, 0
+                served["busy_s"] += time.perf_counter() - t0
+            take_prev()
         live = [(a, L, np.asfortranarray(D)) for a, L, D in terms if L.ncols]
         if len(live) == 1 and api._is_orthonormal(live[0][1]):
             job, job_n = None, 0
@@ -621,7 +719,9 @@ def serve(api):
             return
         feed()
         t0 = time.perf_counter()
-        if job is not None and job_n == len(live):
+        if job is not None and job.room_for(sum(L.ncols for _, L, _ in live[job_n:])):
+            if job_n < len(live):
+                job.add(live[job_n:])
             Lnew, lam = job.finish()
             served["streamed"] = served.get("streamed", 0) + 1
         else:
@@ -631,6 +731,8 @@ def serve(api):
         served["busy_s"] += time.perf_counter() - t0
         served["compressions"] += 1
         terms = [(1.0, Lnew, np.asfortranarray(np.diag(lam)))]
+        if lam.size:
+            scale_hint = max(scale_hint, float(np.sqrt(np.max(np.abs(lam)))))
 
     while True:
         t0 = time.perf_counter()
@@ -639,6 +741,8 @@ def serve(api):
         if cmd == -1:
             raise h
         if cmd == CMD_STOP:
+            for r in others:           # releases the hand-over receiver of the other lane
+                _send_hdr(r, [CMD_STOP])
             break
         if cmd == CMD_BEGIN:
             n = int(h[1])
@@ -649,6 +753,8 @@ def serve(api):
             if h[2] == 0.0:
                 terms = []
                 job, job_n = None, 0
+            base_ok = h[3] != 0.0
+            scale_hint = float(h[4])
         elif cmd == CMD_TERM:
             k, alpha, diag = int(h[1]), h[2], h[3] != 0.0
             D = np.diag(core) if diag else core.reshape(k, k, order="F")
@@ -657,21 +763,42 @@ def serve(api):
             served["terms"] += 1
             feed()
         elif cmd == CMD_COMPRESS:
+            nxt = int(h[1]) if len(h) > 1 and h[1] else me
             compress_now()
+            if nxt != me:
+                # hand X_k over to the lane that is collecting the increments of the next compression point
+                if terms:
+                    _, L, D = terms[0]
+                    lam = np.diag(D).copy()
+                else:
+                    L, lam = None, np.zeros(0)
+                k2 = 0 if L is None else L.ncols
+                _send_hdr(nxt, [CMD_PREV, k2, be.n])
+                _send_small(lam, nxt)
+                if k2:
+                    _send_panel(be, L, nxt)
+                    _reap_sends(block=True)
+                terms = []
+                base_ok = False
+                served["handovers"] += 1
+            else:
+                base_ok = True
         elif cmd == CMD_FETCH:
             compress_now()
-            p.token += 1
+            token = int(h[1]) if len(h) > 1 and h[1] else p.token + 1
+            p.token = token
             if terms:
                 _, L, D = terms[0]
                 lam = np.diag(D).copy()
             else:
                 L, lam = None, np.zeros(0)
             k2 = 0 if L is None else L.ncols
-            _send_hdr(0, [k2, p.token])
+            _send_hdr(0, [k2, token])
             _send_small(lam, 0)
             if k2:
                 _send_panel(be, L, 0)
                 _reap_sends(block=True)
             served["fetches"] += 1
-    th.join(timeout=5.0)
+    for th in threads:
+        th.join(timeout=5.0)
     return served

@@ -191,6 +191,11 @@ DRE_API int32_t dre_ldlt_compress(dre_context* ctx, int32_t nterms, const dre_vi
  * dre_ldlt_compress(terms) == _begin(total columns) + _add(terms) + _finish.  One job per context at a time;
  * the panels passed to _add must stay alive and unchanged only for the duration of that call. */
 DRE_API int32_t dre_compress_begin(dre_context* ctx, int32_t max_cols, double tol_factor);
+/* Optional, between _begin and the first _add: a lower bound for the largest scaled column norm
+ * max_j |alpha d_j|^(1/2) ||l_j|| the job will meet (for an orthonormal factor: sqrt(max |lambda|)).  Directions are
+ * dropped relative to the largest column seen so far; a caller that adds the small terms first and the large one
+ * last (two compression lanes) passes the scale of the large one here. */
+DRE_API int32_t dre_compress_scale_hint(dre_context* ctx, double scale);
 DRE_API int32_t dre_compress_add(dre_context* ctx, int32_t nterms, const dre_view* Ls, const double* const* Ds,
                          const int64_t* ldds, const double* alphas);
 DRE_API int32_t dre_compress_finish(dre_context* ctx, dre_view out, double* lam, int32_t* newrank);

@@ -20,7 +20,8 @@ def _free_port():
     return p
 
 
-def _run(rank, world, port, n, nsteps, q, mode="columns"):
+def _run(rank, world, port, n, nsteps, q, mode="columns", lanes=1, forced=None):
+    os.environ["DRE_PIPE_LANES"] = str(lanes)
     import scipy.sparse.linalg as spla
     import torch
     import torch.distributed as tdist
@@ -50,16 +51,32 @@ def _run(rank, world, port, n, nsteps, q, mode="columns"):
         ddist.enable(device=rank)
     E, A, B, C, _ = dre_b200.pencils.rail_pencil(n)
     L0 = spla.splu(E.tocsc()).solve(C.T)
-    iters = []
+    iters, shifts = [], [[]]
 
     class Obs:
+        def observe_gale_metadata(self, desc, mu):
+            shifts[-1].append(complex(mu))
+
         def observe_gale_done(self, it, X, res, rn):
             iters.append(it)
+            shifts.append([])
+
+    class Forced(api.Shifts.Strategy):
+        """replays, for the i-th ADI solve, the shifts another run consumed in its i-th solve"""
+
+        def __init__(self, lists):
+            self.lists, self.i = lists, 0
+
+        def init(self, prob):
+            lst = self.lists[self.i]
+            self.i += 1
+            return api._ListIterator([z.real if z.imag == 0 else z for z in lst] + [-1.0] * 4)
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
+        alg = api.Ros1(api.ADI(shifts=Forced(forced))) if forced is not None else api.Ros1()
         sol = api.solve(api.GDREProblem(E, A, B, C, api.lowrank(L0, 0.01 * np.eye(C.shape[0])),
-                                        (4500.0, 4500.0 - 100.0 * nsteps)), api.Ros1(), dt=-100.0, observer=Obs())
+                                        (4500.0, 4500.0 - 100.0 * nsteps)), alg, dt=-100.0, observer=Obs())
     if world > 1 and mode == "pipeline":
         stats = dict(ddist.pipe_state().stats)
         ddist.pipe_stop()
@@ -68,19 +85,19 @@ def _run(rank, world, port, n, nsteps, q, mode="columns"):
         tdist.destroy_process_group()
         return
     gathered = ddist.state().bytes_gathered if world > 1 else 0
-    q.put((rank, [np.asarray(K) for K in sol.K], iters, gathered))
+    q.put((rank, [np.asarray(K) for K in sol.K], iters, gathered, shifts[:len(iters)]))
     if world > 1:
         ddist.disable()
         tdist.destroy_process_group()
 
 
-def _spawn(world, n, nsteps, mode="columns"):
+def _spawn(world, n, nsteps, mode="columns", lanes=1, forced=None):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_run, args=(r, world, port, n, nsteps, q, mode)) for r in range(world)]
+    procs = [ctx.Process(target=_run, args=(r, world, port, n, nsteps, q, mode, lanes, forced)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -120,3 +137,24 @@ def test_two_gpu_modes_match_single_gpu():
             assert np.linalg.norm(Ks - K1) <= 1e-10 * np.linalg.norm(K1)
     for Ka, Kb in zip(sharded[0][1], sharded[1][1]):
         assert np.array_equal(Ka, Kb)  # ranks stay bit-identical
+
+
+def test_three_gpu_two_lane_pipeline_lockstep():
+    """DRE_PIPE_LANES=2 (three GPUs): the two compression lanes take the compression points in turn and X_k is added
+    last (dre_compress_begin / _scale_hint / _add / _finish).  Different term order = different round-off, so the
+    comparison with the single-GPU run is the lock-step one (its shifts are replayed): K(t) within 1e-8, identical ADI
+    iteration counts."""
+    import torch
+
+    if torch.cuda.device_count() < 3:
+        pytest.skip("needs three GPUs")
+    n, nsteps = 5177, 2
+    single = _spawn(1, n, nsteps)[0]
+    piped = _spawn(3, n, nsteps, mode="pipeline", lanes=2, forced=single[4])
+    r0 = piped[0]
+    assert r0[2] == single[2]
+    for Kp, K1 in zip(r0[1], single[1]):
+        assert np.linalg.norm(Kp - K1) <= 1e-8 * np.linalg.norm(K1)
+    lanes = [piped[1][1], piped[2][1]]
+    assert all(l["role"] == "compress" and l["compressions"] > 0 and l["handovers"] > 0 for l in lanes)
+    assert sum(l["terms"] for l in lanes) == r0[3]["terms_sent"]
