@@ -244,6 +244,12 @@ def assert_same_int(v: int, what: str):
 # Control messages travel over a gloo group (CPU tensors), panels over NCCL.  Same arithmetic on the same operands
 # in the same order as the single-GPU path: results are identical.
 _PIPE = None
+# NCCL aborts when two host threads of one process launch on the same device at the same time ("host threads racing to
+# launch NCCL on same device", seen with two lanes: the receiver of rank 0's terms and the receiver of the other lane's
+# hand-over).  Every NCCL enqueue of a lane goes through this lock; the stream synchronisations stay outside it.
+import threading as _threading
+
+_NCCL_LOCK = _threading.Lock()
 CMD_STOP, CMD_BEGIN, CMD_TERM, CMD_COMPRESS, CMD_FETCH, CMD_PREV = 0, 1, 2, 3, 4, 5
 _HDR = 8
 
@@ -356,12 +362,14 @@ def _send_panel(be, M, dst):
                 slots.append(buf)
             buf[0].copy_(t)
             t = buf[0]
-            w = dist.isend(t, dst=dst)
+            with _NCCL_LOCK:
+                w = dist.isend(t, dst=dst)
             buf[1] = w
             _PIPE.sends.append((w, M, t))
             _PIPE.stats["bytes_sent"] += t.numel() * 8
             return
-        w = dist.isend(t, dst=dst)
+        with _NCCL_LOCK:
+            w = dist.isend(t, dst=dst)
     _PIPE.sends.append((w, M, t))
     _PIPE.stats["bytes_sent"] += t.numel() * 8
 
@@ -537,10 +545,12 @@ def _recv_panel_tensor(n, k, src):
     flat = torch.empty(cap, dtype=torch.float64, device=dev)
     if kp == k:
         t = flat[: n * k].view(n, k)
-        dist.recv(t, src=src)
+        with _NCCL_LOCK:
+            dist.recv(t, src=src)
     else:
         tmp = torch.empty(cap, dtype=torch.float64, device=dev)[: n * k].view(n, k)
-        dist.recv(tmp, src=src)
+        with _NCCL_LOCK:
+            dist.recv(tmp, src=src)
         t = flat[: n * kp].view(n, kp)
         t[:, :k].copy_(tmp)
         t[:, k:].zero_()
