@@ -250,6 +250,13 @@ _PIPE = None
 import threading as _threading
 
 _NCCL_LOCK = _threading.Lock()
+
+
+def _nccl_lock():
+    """The lock for NCCL enqueues (asynchronous: held for microseconds); nothing for gloo, whose recv blocks."""
+    import contextlib
+
+    return _NCCL_LOCK if _PIPE is not None and _PIPE.data_backend != "gloo" else contextlib.nullcontext()
 CMD_STOP, CMD_BEGIN, CMD_TERM, CMD_COMPRESS, CMD_FETCH, CMD_PREV = 0, 1, 2, 3, 4, 5
 _HDR = 8
 
@@ -362,13 +369,13 @@ def _send_panel(be, M, dst):
                 slots.append(buf)
             buf[0].copy_(t)
             t = buf[0]
-            with _NCCL_LOCK:
+            with _nccl_lock():
                 w = dist.isend(t, dst=dst)
             buf[1] = w
             _PIPE.sends.append((w, M, t))
             _PIPE.stats["bytes_sent"] += t.numel() * 8
             return
-        with _NCCL_LOCK:
+        with _nccl_lock():
             w = dist.isend(t, dst=dst)
     _PIPE.sends.append((w, M, t))
     _PIPE.stats["bytes_sent"] += t.numel() * 8
@@ -545,11 +552,11 @@ def _recv_panel_tensor(n, k, src):
     flat = torch.empty(cap, dtype=torch.float64, device=dev)
     if kp == k:
         t = flat[: n * k].view(n, k)
-        with _NCCL_LOCK:
+        with _nccl_lock():
             dist.recv(t, src=src)
     else:
         tmp = torch.empty(cap, dtype=torch.float64, device=dev)[: n * k].view(n, k)
-        with _NCCL_LOCK:
+        with _nccl_lock():
             dist.recv(tmp, src=src)
         t = flat[: n * kp].view(n, kp)
         t[:, :k].copy_(tmp)

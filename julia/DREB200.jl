@@ -154,6 +154,33 @@ end
 hint_orthonormal!(L::DeviceMatrix) =
     check(L.p.ctx, ccall((:dre_hint_orthonormal, LIB), Int32, (Ptr{Cvoid}, View), L.p.ctx.h, view_of(L)))
 
+# compress! in three phases for a process that receives the terms of X one by one (the compression lane of the
+# multi-GPU pipeline mode: `dre_b200.dist.serve` is the executable pattern).  compress_begin! reserves room,
+# compress_add! orthogonalises terms against the basis built so far, compress_finish! returns (L, lambda);
+# compress!(X) above is the three in one call.  compress_scale_hint! is for a lane that adds X last.
+compress_begin!(ctx::Context, max_cols::Integer; tol_factor = 100.0) =
+    check(ctx, ccall((:dre_compress_begin, LIB), Int32, (Ptr{Cvoid}, Int32, Float64), ctx.h, max_cols, tol_factor))
+compress_scale_hint!(ctx::Context, scale::Real) =
+    check(ctx, ccall((:dre_compress_scale_hint, LIB), Int32, (Ptr{Cvoid}, Float64), ctx.h, scale))
+function compress_add!(ctx::Context, alphas::Vector{Float64}, Ls::Vector{DeviceMatrix}, Ds::Vector{Matrix{Float64}})
+    nt = length(Ls)
+    views = [view_of(L) for L in Ls]
+    Dp = [pointer(D) for D in Ds]
+    ldds = Int64[max(stride(D, 2), 1) for D in Ds]
+    GC.@preserve Ds check(ctx, ccall((:dre_compress_add, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{View}, Ptr{Ptr{Float64}}, Ptr{Int64}, Ptr{Float64}),
+        ctx.h, nt, views, Dp, ldds, alphas))
+end
+function compress_finish!(ctx::Context, cap::Integer)
+    out = DeviceMatrix(ctx, cap)
+    lam = Vector{Float64}(undef, cap)
+    newrank = Ref{Int32}(0)
+    check(ctx, ccall((:dre_compress_finish, LIB), Int32, (Ptr{Cvoid}, View, Ptr{Float64}, Ref{Int32}),
+                     ctx.h, view_of(out), lam, newrank))
+    k = Int(newrank[])
+    DeviceMatrix(out.p, 0, k), lam[1:k]
+end
+
 # The context's CUDA stream (cudaStream_t) for stream-ordered collectives on the raw panel pointers.
 function cuda_stream(ctx::Context)
     s = Ref{Ptr{Cvoid}}(C_NULL)
