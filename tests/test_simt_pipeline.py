@@ -83,6 +83,17 @@ def _run(rank, world, port, n, nsteps, ros, q, lanes=1, forced=None):
         tdist.destroy_process_group()
 
 
+_SINGLE = {}
+
+
+def _single(n, nsteps, ros):
+    """the single-process run both tests compare with (once per session)"""
+    key = (n, nsteps, ros)
+    if key not in _SINGLE:
+        _SINGLE[key] = _spawn(1, n, nsteps, ros)[0]
+    return _SINGLE[key]
+
+
 def _spawn(world, n, nsteps, ros, lanes=1, forced=None):
     import torch.multiprocessing as mp
 
@@ -102,7 +113,7 @@ def _spawn(world, n, nsteps, ros, lanes=1, forced=None):
 @pytest.mark.parametrize("world,ros", [(3, 1)])
 def test_pipeline_mode_matches_single_process(world, ros):
     n, nsteps = 371, 2
-    single = _spawn(1, n, nsteps, ros)[0]
+    single = _single(n, nsteps, ros)
     piped = _spawn(world, n, nsteps, ros)
     r0 = piped[0]
     assert r0[2] == single[2]                                   # identical ADI iteration counts
@@ -125,7 +136,7 @@ def test_two_lane_pipeline_lockstep_with_single_process():
     means different round-off, so the comparison is the lock-step one (the shifts of the single-process run are
     replayed): K(t) within 1e-8, identical ADI iteration counts, final ranks within one."""
     n, nsteps = 371, 2
-    single = _spawn(1, n, nsteps, 1)[0]
+    single = _single(n, nsteps, 1)
     piped = _spawn(3, n, nsteps, 1, lanes=2, forced=single[5])
     r0 = piped[0]
     assert r0[2] == single[2]
