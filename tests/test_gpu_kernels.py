@@ -312,7 +312,7 @@ def test_streamed_compress_matches_one_call(rail):
     X1 = L1.to_host() @ np.diag(lam1) @ L1.to_host().T
     X2 = L2.to_host() @ np.diag(lam2) @ L2.to_host().T
     assert _rel(X1, dense) < 1e-12 and _rel(X2, dense) < 1e-12
-    assert abs(len(lam1) - len(lam2)) <= 1
+    assert abs(len(lam1) - len(lam2)) <= 2   # (two eigenvalues of this case sit within 2x of the truncation threshold)
     assert np.linalg.norm(L2.to_host().T @ L2.to_host() - np.eye(len(lam2))) < 1e-11
     # a job that runs out of room reports it instead of overrunning its workspace
     job = api.CompressStream(be, 50)
