@@ -2183,6 +2183,9 @@ int32_t dre_rrqr(dre_context* c, int32_t nviews, const dre_view* views, double d
     *rho_out = 0;
     if (ktot == 0) return DRE_OK;
     if (!Rt || ldr < ktot) return fail(c, DRE_ERR_ARG, "rrqr: bad Rt");
+    // the basis and coefficient workspaces are shared with an open dre_compress_begin .. _finish job
+    if (c->cjob.active)
+        return fail(c, DRE_ERR_STATE, "rrqr: a compress job is open on this context (dre_compress_finish it first)");
     Range r_shifts("shifts");
     RRState s;
     if ((rc = rr_setup(c, s, ktot, drop_rel, drop_abs))) return rc;

@@ -188,8 +188,9 @@ DRE_API int32_t dre_ldlt_compress(dre_context* ctx, int32_t nterms, const dre_vi
  * `compression_interval` steps, :143-147): _begin reserves room for at most max_cols columns in total and resets the
  * job; every _add orthogonalises its terms against the basis built so far (so the work of an increment overlaps the
  * computation of the next one); _finish runs the core / eigen-decomposition / L <- Q V tail and ends the job.
- * dre_ldlt_compress(terms) == _begin(total columns) + _add(terms) + _finish.  One job per context at a time;
- * the panels passed to _add must stay alive and unchanged only for the duration of that call. */
+ * dre_ldlt_compress(terms) == _begin(total columns) + _add(terms) + _finish.  One job per context at a time (a new
+ * _begin or a dre_ldlt_compress call drops an open job; dre_rrqr, which shares the job's workspaces, refuses to run
+ * while one is open); the panels passed to _add must stay alive and unchanged only for the duration of that call. */
 DRE_API int32_t dre_compress_begin(dre_context* ctx, int32_t max_cols, double tol_factor);
 /* Optional, between _begin and the first _add: a lower bound for the largest scaled column norm
  * max_j |alpha d_j|^(1/2) ||l_j|| the job will meet (for an orthonormal factor: sqrt(max |lambda|)).  Directions are

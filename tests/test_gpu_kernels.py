@@ -320,6 +320,12 @@ def test_streamed_compress_matches_one_call(rail):
     assert not job.room_for(24)
     with pytest.raises(Exception):
         job.add(dev[1:2])
+    # while a job is open the rank-revealing QR (shared workspaces) refuses to run; finishing the job releases it
+    with pytest.raises(Exception):
+        api.orth_restrict([dev[1][1]], api.PencilCombo(0.0, 1.0), api.PencilCombo(1.0, 0.0))
+    L3, lam3 = job.finish()
+    assert _rel(L3.to_host() @ np.diag(lam3) @ L3.to_host().T, terms[0][1] @ terms[0][2] @ terms[0][1].T) < 1e-12
+    api.orth_restrict([dev[1][1]], api.PencilCombo(0.0, 1.0), api.PencilCombo(1.0, 0.0))
 
 
 def test_rrqr_orth(rail):

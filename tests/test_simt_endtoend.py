@@ -77,6 +77,18 @@ def test_emulated_streamed_compress_matches_one_call(emulated):
     X2 = L2.to_host() @ np.diag(lam2) @ L2.to_host().T
     assert _rel(X1, dense) < 1e-12 and _rel(X2, dense) < 1e-12
     assert abs(len(lam1) - len(lam2)) <= 2   # (two eigenvalues of this case sit within 2x of the truncation threshold)
+    # a job that runs out of room reports it; while it is open the rank-revealing QR (shared workspaces) refuses to
+    # run; finishing the job releases it
+    job = api.CompressStream(be, 50)
+    job.add(dev[:1])
+    assert not job.room_for(24)
+    with pytest.raises(Exception):
+        job.add(dev[1:2])
+    with pytest.raises(Exception):
+        api.orth_restrict([dev[1][1]], api.PencilCombo(0.0, 1.0), api.PencilCombo(1.0, 0.0))
+    L3, lam3 = job.finish()
+    assert _rel(L3.to_host() @ np.diag(lam3) @ L3.to_host().T, terms[0][1] @ terms[0][2] @ terms[0][1].T) < 1e-12
+    api.orth_restrict([dev[1][1]], api.PencilCombo(0.0, 1.0), api.PencilCombo(1.0, 0.0))
 
 
 def test_emulated_abi_block_solve_smw_and_compress(emulated):
