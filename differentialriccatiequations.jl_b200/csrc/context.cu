@@ -1920,10 +1920,9 @@ int32_t dre_compress_begin(dre_context* c, int32_t max_cols, double tol_factor) 
     if (max_cols < 0) return fail(c, DRE_ERR_ARG, "compress: negative capacity");
     dre_context::CompressJob& job = c->cjob;
     job = dre_context::CompressJob{};
-    job.active = true;
     job.kcap = max_cols;
     job.tol_factor = tol_factor;
-    if (max_cols == 0) return DRE_OK;
+    if (max_cols == 0) { job.active = true; return DRE_OK; }
     // Basis directions are dropped at HALF the relative level at which compress! truncates the eigenvalues of the
     // projected core below (tol_factor * eps, src/LDLt.jl:216-217): a direction whose coefficients are below
     // sigma * scale changes X by at most O(sigma) ||X|| through its cross terms with the large directions, i.e. by
@@ -1936,6 +1935,7 @@ int32_t dre_compress_begin(dre_context* c, int32_t max_cols, double tol_factor) 
     if ((rc = rr_setup(c, job.s, max_cols, drop_rel, 0.0))) return rc;
     CU(c->cscale.ensure((size_t)max_cols));
     job.signs.reserve(max_cols);
+    job.active = true;   // (only now: a failed allocation leaves no half-open job behind)
     return DRE_OK;
 }
 
