@@ -71,7 +71,9 @@ def _run(rank, world, port, n, nsteps, ros, q, lanes=1, forced=None):
     dt = -100.0 if ros == 1 else -50.0
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        adi = api.ADI(shifts=Forced(forced)) if forced is not None else None
+        # (30 ADI iterations per solve keep the emulated runs short: three compression points per solve, the second
+        #  step starts from the factor the lane returned for the first)
+        adi = api.ADI(maxiters=30, shifts=Forced(forced)) if forced is not None else api.ADI(maxiters=30)
         alg = api.Ros1(adi) if ros == 1 else api.Ros2(adi)
         sol = api.solve(api.GDREProblem(E, A, B, Cm, api.lowrank(L0, 0.01 * np.eye(Cm.shape[0])),
                                         (4500.0, 4500.0 + nsteps * dt)), alg, dt=dt, observer=Obs())
